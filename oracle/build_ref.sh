@@ -1,0 +1,47 @@
+#!/bin/bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE ONLY.
+# Compiles the reference's own CPU sources, from where they lie under /root/reference,
+# into oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot):
+#   libbwaref.so   bwa_index/*.c library objects (OCC_INTV_SHIFT 7) + oracle/ref_shim.c
+#   libforkksw.so  src/ksw.c + oracle/fork_ksw_shim.c  (fork's ksw_extend2 with opt_ext)
+#   bwa7 / bwa6    the reference's index builder compiled with OCC_INTV_SHIFT 7 / 6,
+#                  i.e. the two passes of the reference's build_index.sh:46-66
+# The reference's bwt.h hard-codes OCC_INTV_SHIFT and its own build script rewrites that
+# line with sed between the two passes; we do the same on a scratch copy under $TMPDIR.
+# Nothing from /root/reference is copied into the repository.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF_ROOT:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/bwa_index" ]; then
+  echo "[build_ref] $REF not present; keeping whatever is in $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d)"
+trap 'rm -rf "$TMP"' EXIT
+CFLAGS="-O2 -g -fcommon -fPIC -w -DHAVE_PTHREAD"
+LOBJS="utils kthread kstring ksw bwt bntseq bwa bwamem bwamem_pair bwamem_extra QSufSort bwt_gen rope rle is bwtindex"
+AOBJS="bwashm bwase bwaseqio bwtgap bwtaln bamlite bwape kopen pemerge maxk bwtsw2_core bwtsw2_main bwtsw2_aux bwt_lite bwtsw2_chain fastmap bwtsw2_pair main"
+for shift in 7 6; do
+  D="$TMP/s$shift"; mkdir -p "$D"
+  cp "$REF"/bwa_index/*.c "$REF"/bwa_index/*.h "$D"/
+  sed -i "s,#define OCC_INTV_SHIFT.*,#define OCC_INTV_SHIFT $shift,g" "$D/bwt.h"
+  ( cd "$D"
+    for o in $LOBJS $AOBJS; do gcc -c $CFLAGS $o.c -o $o.o & done; wait
+    objs=""; for o in $LOBJS $AOBJS; do objs="$objs $o.o"; done
+    gcc $CFLAGS $objs -o "$OUT/bwa$shift" -lm -lz -lpthread -lrt
+    if [ "$shift" = 7 ]; then
+      lobjs=""; for o in $LOBJS; do lobjs="$lobjs $o.o"; done
+      gcc -c $CFLAGS -fopenmp -I. "$HERE/ref_shim.c" -o ref_shim.o
+      gcc -shared $CFLAGS -fopenmp $lobjs ref_shim.o -o "$OUT/libbwaref.so" -lm -lz -lpthread -lrt
+    fi )
+done
+F="$TMP/fork"; mkdir -p "$F"
+cp "$REF"/src/ksw.c "$REF"/src/ksw.h "$F"/
+[ -f "$REF/src/malloc_wrap.h" ] && cp "$REF/src/malloc_wrap.h" "$F"/
+( cd "$F"
+  gcc -c $CFLAGS ksw.c -o ksw.o
+  gcc -c $CFLAGS -I. "$HERE/fork_ksw_shim.c" -o shim.o
+  gcc -shared $CFLAGS ksw.o shim.o -o "$OUT/libforkksw.so" -lm )
+echo "[build_ref] built: $(ls "$OUT")"

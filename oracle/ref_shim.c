@@ -1,0 +1,143 @@
+/*
+ * oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY.
+ * Thin C entry points around the UNMODIFIED reference CPU functions, compiled by
+ * oracle/build_ref.sh together with the reference's own bwa_index/ *.c files (taken from
+ * /root/reference where they lie; OCC_INTV_SHIFT set to 7 exactly as the reference's
+ * build_index.sh:46 does) into oracle/_ref/libbwaref.so.  This file contains no reference
+ * code: it only calls bwt_restore_bwt / bwt_smem1 / bwt_sa / ksw_extend2 through the
+ * reference headers.  The one thing it replaces is the .sa reader: the reference's
+ * bwt_restore_sa (bwa_index/bwt.c:501-527) cannot read the u32 + packed-hi-bit file that
+ * bwt_dump_sa (bwa_index/bwt.c:472-487) writes, so the samples are
+ * loaded here into the same bwt_t fields.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "bwt.h"
+#include "ksw.h"
+#include "bwa.h"
+
+void *ref_load(const char *bwt128_path, const char *sa_path)
+{
+    bwt_t *bwt = bwt_restore_bwt(bwt128_path);
+    if (!sa_path) return bwt;
+    FILE *fp = fopen(sa_path, "rb");
+    if (!fp) return NULL;
+    uint64_t hdr[7];
+    if (fread(hdr, 8, 7, fp) != 7 || hdr[0] != bwt->primary || hdr[6] != bwt->seq_len) { fclose(fp); return NULL; }
+    bwt->sa_intv = (int)hdr[5];
+    bwt->n_sa = (bwt->seq_len + bwt->sa_intv) / bwt->sa_intv;
+    bwt->sa = (uint32_t *)calloc(bwt->n_sa, 4);
+    bwt->sa[0] = (uint32_t)-1;
+    if (fread(bwt->sa + 1, 4, bwt->n_sa - 1, fp) != bwt->n_sa - 1) { fclose(fp); return NULL; }
+    uint8_t ps;
+    if (fread(&ps, 1, 1, fp) != 1) { fclose(fp); return NULL; }
+    bwt->pack_size = ps;
+    bwt->pack_mask = ps >= 32 ? 0xffffffffu : ((1u << ps) - 1);
+    if ((bwt->seq_len >> 32) == 0) bwt->pack_mask = 0; /* bwa_index/bwt.c:88-91: msb == 0 */
+    size_t nhi = (size_t)ps * bwt->n_sa / 32 + 1;
+    bwt->sa_bits = (uint32_t *)calloc(nhi + 1, 4);
+    size_t got = fread(bwt->sa_bits, 4, nhi, fp); (void)got;
+    fclose(fp);
+    return bwt;
+}
+
+void ref_free(void *h) { if (h) bwt_destroy((bwt_t *)h); }
+
+uint64_t ref_seq_len(void *h) { return ((bwt_t *)h)->seq_len; }
+uint64_t ref_primary(void *h) { return ((bwt_t *)h)->primary; }
+
+/* out: 5 x u64 per interval = x0, x1, x2, start, end */
+int ref_smem1(void *h, int len, const uint8_t *q, int x, int min_intv, uint64_t *out, int *n_out)
+{
+    bwtintv_v mem = {0, 0, 0};
+    int ret = bwt_smem1((bwt_t *)h, len, q, x, min_intv, &mem, 0);
+    for (size_t i = 0; i < mem.n; ++i) {
+        out[5 * i + 0] = mem.a[i].x[0]; out[5 * i + 1] = mem.a[i].x[1]; out[5 * i + 2] = mem.a[i].x[2];
+        out[5 * i + 3] = mem.a[i].info >> 32; out[5 * i + 4] = (uint32_t)mem.a[i].info;
+    }
+    *n_out = (int)mem.n;
+    free(mem.a);
+    return ret;
+}
+
+uint64_t ref_sa(void *h, uint64_t k) { return bwt_sa((bwt_t *)h, k); }
+
+void ref_occ4(void *h, uint64_t k, uint64_t cnt[4]) { bwt_occ4((bwt_t *)h, k, cnt); }
+
+void ref_extend(void *h, const uint64_t ik[3], uint64_t ok[12], int is_back)
+{
+    bwtintv_t i, o[4];
+    i.x[0] = ik[0]; i.x[1] = ik[1]; i.x[2] = ik[2]; i.info = 0;
+    bwt_extend((bwt_t *)h, &i, o, is_back);
+    for (int a = 0; a < 4; ++a) { ok[3 * a] = o[a].x[0]; ok[3 * a + 1] = o[a].x[1]; ok[3 * a + 2] = o[a].x[2]; }
+}
+
+/* stock (always banded) ksw_extend2, bwa_index/ksw.c:380 */
+int ref_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                    int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                    int32_t out[6])
+{
+    int qle, tle, gtle, gscore, max_off;
+    int sc = ksw_extend2(qlen, query, tlen, target, 5, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0,
+                         &qle, &tle, &gtle, &gscore, &max_off);
+    out[0] = sc; out[1] = qle; out[2] = tle; out[3] = gtle; out[4] = gscore; out[5] = max_off;
+    return sc;
+}
+
+/* ---- whole-batch drivers used as the CPU "reference" arm of bench.py ---- */
+
+/* pass-1 SMEMs (len >= min_seed_len) + sampled SA lookups per read, like
+ * mem_collect_intv pass 1 + the mem_chain loop (bwa_index/bwamem.c:121-131,278-283).
+ * Returns the number of seeds produced; a checksum keeps the work observable. */
+int64_t ref_seed_batch(void *h, const uint8_t *reads, const uint64_t *read_off, int64_t n_reads,
+                       int min_seed_len, int max_occ, int n_threads, uint64_t *checksum)
+{
+    bwt_t *bwt = (bwt_t *)h;
+    int64_t total = 0; uint64_t sum = 0;
+#pragma omp parallel num_threads(n_threads) reduction(+:total,sum)
+    {
+        bwtintv_v mem = {0, 0, 0}, t0 = {0, 0, 0}, t1 = {0, 0, 0};
+        bwtintv_v *tmpv[2] = {&t0, &t1};
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const uint8_t *q = reads + read_off[r];
+            int len = (int)(read_off[r + 1] - read_off[r]), x = 0;
+            if (len < min_seed_len) continue;
+            while (x < len) {
+                if (q[x] < 4) {
+                    x = bwt_smem1(bwt, len, q, x, 1, &mem, tmpv);
+                    for (size_t i = 0; i < mem.n; ++i) {
+                        bwtintv_t *p = &mem.a[i];
+                        int slen = (int)((uint32_t)p->info - (p->info >> 32));
+                        if (slen < min_seed_len) continue;
+                        int64_t step = p->x[2] > (uint64_t)max_occ ? p->x[2] / max_occ : 1, k, count;
+                        for (k = count = 0; k < (int64_t)p->x[2] && count < max_occ; k += step, ++count) {
+                            uint64_t pos = bwt_sa(bwt, p->x[0] + k);
+                            sum += pos ^ ((uint64_t)slen << 40);
+                            ++total;
+                        }
+                    }
+                } else ++x;
+            }
+        }
+        free(mem.a); free(t0.a); free(t1.a);
+    }
+    if (checksum) *checksum = sum;
+    return total;
+}
+
+void ref_ksw_batch(int64_t n, const uint8_t *qseq, const uint32_t *qoff, const uint32_t *qlen,
+                   const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen, const uint32_t *h0,
+                   const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop,
+                   int32_t *out6, int n_threads)
+{
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 256)
+    for (int64_t a = 0; a < n; ++a)
+        ref_ksw_extend2((int)qlen[a], qseq + qoff[a], (int)tlen[a], tseq + toff[a], mat, o_del, e_del, o_ins, e_ins,
+                        w, end_bonus, zdrop, (int)h0[a], out6 + 6 * a);
+}

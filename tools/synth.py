@@ -1,0 +1,164 @@
+"""Deterministic synthetic inputs: genomes, reads, extension jobs.
+
+Everything is produced from numpy's PCG64 with fixed seeds, so the CPU oracle, the
+reference arm and the CUDA path all see byte-identical inputs on any machine.
+Base codes follow the reference: A=0 C=1 G=2 T=3 N=4 (nst_nt4_table, src/bntseq.c).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GENOME_SEED = 20261017
+READS_SEED = 20261018
+EXT_SEED = 777
+
+
+def make_genome(n_bases: int, seed: int = GENOME_SEED, repeats: bool = False) -> np.ndarray:
+    """i.i.d. uniform ACGT genome as uint8 codes.  `repeats=True` overwrites ~5 % of it with
+    diverged copies of a few elements (stress profile for the max_occ path)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = rng.integers(0, 4, size=n_bases, dtype=np.uint8)
+    if repeats and n_bases >= 4000:
+        n_el = 4
+        target = n_bases // 20
+        placed = 0
+        els = [rng.integers(0, 4, size=int(rng.integers(300, min(6000, n_bases // 8))), dtype=np.uint8) for _ in range(n_el)]
+        while placed < target:
+            e = els[int(rng.integers(0, n_el))].copy()
+            mut = rng.random(e.size) < 0.10
+            e[mut] = (e[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+            p = int(rng.integers(0, n_bases - e.size))
+            g[p:p + e.size] = e
+            placed += e.size
+    return g
+
+
+def revcomp(codes: np.ndarray) -> np.ndarray:
+    out = codes[..., ::-1].copy()
+    m = out < 4
+    out[m] = 3 - out[m]
+    return out
+
+
+def make_reads(genome: np.ndarray, n_reads: int, read_len: int = 150, seed: int = READS_SEED,
+               sub_rate: float = 0.01, ins_rate: float = 0.0005, del_rate: float = 0.0005,
+               n_rate: float = 0.0):
+    """Returns (reads[n_reads, read_len] uint8, pos[n_reads] int64, strand[n_reads] uint8).
+    Odd read index = reverse-complement strand; substitutions go to a different base;
+    indels have length 1."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    G = genome.size
+    pad = 16
+    pos = rng.integers(0, G - read_len - pad, size=n_reads, dtype=np.int64)
+    idx = pos[:, None] + np.arange(read_len + pad, dtype=np.int64)[None, :]
+    raw = genome[idx]                                    # n x (L+pad)
+    sub = rng.random((n_reads, read_len + pad)) < sub_rate
+    shift = rng.integers(1, 4, size=(n_reads, read_len + pad), dtype=np.uint8)
+    raw = np.where(sub, (raw + shift) & 3, raw).astype(np.uint8)
+    ins = rng.random((n_reads, read_len)) < ins_rate
+    dele = rng.random((n_reads, read_len)) < del_rate
+    ins_base = rng.integers(0, 4, size=(n_reads, read_len), dtype=np.uint8)
+    reads = raw[:, :read_len].copy()
+    rows = np.nonzero(ins.any(axis=1) | dele.any(axis=1))[0]
+    for r in rows:
+        src = raw[r]
+        out = []
+        j = 0
+        while len(out) < read_len and j < src.size:
+            if j < read_len and ins[r, j]:
+                out.append(ins_base[r, j])
+                if len(out) >= read_len:
+                    break
+            if j < read_len and dele[r, j]:
+                j += 1
+                continue
+            out.append(src[j])
+            j += 1
+        while len(out) < read_len:
+            out.append(0)
+        reads[r] = np.asarray(out[:read_len], dtype=np.uint8)
+    if n_rate > 0:
+        nm = rng.random((n_reads, read_len)) < n_rate
+        reads[nm] = 4
+    strand = (np.arange(n_reads) & 1).astype(np.uint8)
+    odd = strand == 1
+    reads[odd] = revcomp(reads[odd])
+    return reads, pos, strand
+
+
+def reads_to_fasta(reads: np.ndarray, pos: np.ndarray, strand: np.ndarray, path: str) -> None:
+    """single-line FASTA, one read per line (boundary requirement of seed_gpu, seed_gen.cu:1708)."""
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    with open(path, "wb") as fh:
+        for i in range(reads.shape[0]):
+            fh.write(b">r%d_%d_%d\n" % (i, int(pos[i]), int(strand[i])))
+            fh.write(lut[reads[i]].tobytes())
+            fh.write(b"\n")
+
+
+def genome_to_fasta(genome: np.ndarray, path: str, name: str = "chr1", width: int = 60) -> None:
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    txt = lut[genome]
+    with open(path, "wb") as fh:
+        fh.write(b">" + name.encode() + b"\n")
+        for i in range(0, txt.size, width):
+            fh.write(txt[i:i + width].tobytes())
+            fh.write(b"\n")
+
+
+def make_ext_jobs(n_jobs: int, qlen_choices=(100, 150, 200, 250, 300), w: int = 100, seed: int = EXT_SEED,
+                  sub_rate: float = 0.05, indel_rate: float = 0.01, n_job_frac: float = 0.01,
+                  h0_range=(19, 150), pad8: bool = True, qlen_range=None, tail_random: bool = True):
+    """Extension-only sweep jobs (C4): target = query with `sub_rate` substitutions and
+    `indel_rate` indels, then a random tail up to tlen = qlen + min(qlen, 2w).
+    Returns a dict of GASAL-style host arrays: byte codes 0..4 with per-job offsets (each
+    sequence padded to a multiple of 8 with code 4 when pad8), lengths and h0."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if qlen_range is not None:
+        qlens = rng.integers(qlen_range[0], qlen_range[1] + 1, size=n_jobs)
+    else:
+        qlens = rng.choice(np.asarray(qlen_choices), size=n_jobs)
+    tlens = qlens + np.minimum(qlens, 2 * w)
+    h0 = rng.integers(h0_range[0], h0_range[1] + 1, size=n_jobs).astype(np.uint32)
+
+    def padded(n):
+        return (n + 7) // 8 * 8 if pad8 else n
+
+    qoff = np.zeros(n_jobs, dtype=np.uint32)
+    toff = np.zeros(n_jobs, dtype=np.uint32)
+    qp = np.asarray([padded(int(x)) for x in qlens], dtype=np.int64)
+    tp = np.asarray([padded(int(x)) for x in tlens], dtype=np.int64)
+    qoff[1:] = np.cumsum(qp)[:-1]
+    toff[1:] = np.cumsum(tp)[:-1]
+    qseq = np.full(int(qp.sum()), 4, dtype=np.uint8)
+    tseq = np.full(int(tp.sum()), 4, dtype=np.uint8)
+    for a in range(n_jobs):
+        ql, tl = int(qlens[a]), int(tlens[a])
+        q = rng.integers(0, 4, size=ql, dtype=np.uint8)
+        t = q.copy()
+        sm = rng.random(ql) < sub_rate
+        t[sm] = (t[sm] + rng.integers(1, 4, size=int(sm.sum()), dtype=np.uint8)) & 3
+        ev = rng.random(ql) < indel_rate
+        if ev.any():
+            parts = []
+            last = 0
+            for p in np.nonzero(ev)[0]:
+                parts.append(t[last:p])
+                if rng.random() < 0.5:
+                    parts.append(rng.integers(0, 4, size=int(rng.integers(1, 4)), dtype=np.uint8))  # insertion in target
+                    last = p
+                else:
+                    last = min(ql, p + int(rng.integers(1, 4)))                                     # deletion from target
+            parts.append(t[last:])
+            t = np.concatenate(parts)
+        if t.size < tl:
+            tail = rng.integers(0, 4, size=tl - t.size, dtype=np.uint8) if tail_random else np.zeros(tl - t.size, np.uint8)
+            t = np.concatenate([t, tail])
+        t = t[:tl]
+        if rng.random() < n_job_frac:
+            q[int(rng.integers(0, ql))] = 4
+            t[int(rng.integers(0, tl))] = 4
+        qseq[qoff[a]:qoff[a] + ql] = q
+        tseq[toff[a]:toff[a] + tl] = t
+    return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff,
+                qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
