@@ -1,0 +1,328 @@
+"""Python-side loader for libbwamem_b200.so (ctypes over the C ABI in include/bwamem_b200.h).
+
+This module holds no compute: every call goes straight into the CUDA library.  It exists so
+tests and bench.py can drive the same C entry points the `gase_aln` driver would bind.
+The directory name contains '-', so import it through `load_package()` in tests/conftest.py /
+__graft_entry__.py (importlib by path, module name `bwa_mem_gpu_b200`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "libbwamem_b200.so")
+
+ERR = {0: "OK", -1: "ERR_ARG", -2: "ERR_IO", -3: "ERR_FORMAT", -4: "ERR_CUDA", -5: "ERR_NOMEM", -6: "ERR_CAPACITY"}
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR.get(code, code)}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into the in-tree shared library."""
+    csrc = os.path.join(PKG_DIR, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".h", ".cuh"))]
+    srcs += [os.path.join(ROOT, "include", "bwamem_b200.h")]
+    comp = os.path.join(ROOT, "include", "compat")
+    if os.path.isdir(comp):
+        srcs += [os.path.join(comp, f) for f in os.listdir(comp)]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        nvcc = "/usr/local/cuda/bin/nvcc"
+        if not os.path.exists(nvcc):
+            if os.path.exists(LIB_PATH):
+                return LIB_PATH
+            raise RuntimeError("nvcc not found and libbwamem_b200.so is not built")
+        subprocess.check_call(["make", "-C", csrc, "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("primary", C.c_uint64), ("seq_len", C.c_uint64), ("L2", C.c_uint64 * 5), ("n_buckets", C.c_uint64),
+                ("n_sa", C.c_uint64), ("sa_intv", C.c_int32), ("pack_size", C.c_int32), ("device", C.c_int32),
+                ("hbm_bytes", C.c_uint64)]
+
+
+class SeedParams(C.Structure):
+    _fields_ = [("min_seed_len", C.c_int32), ("max_occ", C.c_int32)]
+
+
+class Seeds(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_seeds", C.c_uint64), ("rbeg", C.POINTER(C.c_uint64)),
+                ("qbeg_qend", C.POINTER(C.c_int32)), ("score", C.POINTER(C.c_uint32)),
+                ("n_seeds_per_read", C.POINTER(C.c_uint32)), ("seed_off", C.POINTER(C.c_uint64))]
+
+
+class ExtParams(C.Structure):
+    _fields_ = [("mat", C.c_int8 * 25), ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32),
+                ("e_ins", C.c_int32), ("w", C.c_int32), ("end_bonus", C.c_int32), ("zdrop", C.c_int32),
+                ("use_band", C.c_int32), ("pen_clip", C.c_int32)]
+
+
+# every symbol include/bwamem_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "bwa_b200_last_error", "bwa_b200_version", "bwa_b200_device_count", "bwa_b200_host_alloc", "bwa_b200_host_free",
+    "bwa_b200_index_load", "bwa_b200_index_from_host", "bwa_b200_index_clone_to", "bwa_b200_index_info",
+    "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
+    "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
+    "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
+    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
+    "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
+    "bwa_b200_extend_wait", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
+    "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
+]
+
+_lib = None
+vp = C.c_void_p
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly if it is missing: there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is not built; run __graft_entry__.build() (needs nvcc). "
+                               "There is no CPU fallback for the hot paths.")
+        L = C.CDLL(LIB_PATH)
+        L.bwa_b200_last_error.restype = C.c_char_p
+        L.bwa_b200_host_alloc.restype = vp
+        L.bwa_b200_host_alloc.argtypes = [C.c_size_t]
+        L.bwa_b200_host_free.argtypes = [vp]
+        L.bwa_b200_index_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.bwa_b200_index_from_host.argtypes = [C.c_uint64, vp, vp, C.c_uint64, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.bwa_b200_index_clone_to.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.bwa_b200_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
+        L.bwa_b200_index_free.argtypes = [vp]
+        L.bwa_b200_build_index.argtypes = [vp, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int]
+        L.bwa_b200_packed_words.argtypes = [vp, C.c_uint64]
+        L.bwa_b200_packed_words.restype = C.c_size_t
+        L.bwa_b200_pack_ascii.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_int]
+        L.bwa_b200_pack_codes.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_int]
+        L.bwa_b200_seeder_create.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+        L.bwa_b200_seeder_destroy.argtypes = [vp]
+        L.bwa_b200_seed_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(Seeds)]
+        L.bwa_b200_seeds_free.argtypes = [C.POINTER(Seeds)]
+        L.bwa_b200_seed_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams)]
+        L.bwa_b200_seed_device_result.argtypes = [vp, C.POINTER(Seeds)]
+        L.bwa_b200_seeder_stream.argtypes = [vp]
+        L.bwa_b200_seeder_stream.restype = vp
+        L.bwa_b200_seed_device_smems.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.bwa_b200_seeder_launches.argtypes = [vp]
+        L.bwa_b200_seeder_launches.restype = C.c_uint64
+        L.bwa_b200_ext_params_default.argtypes = [C.POINTER(ExtParams)]
+        L.bwa_b200_fill_scmat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
+        L.bwa_b200_extender_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+        L.bwa_b200_extender_destroy.argtypes = [vp]
+        L.bwa_b200_extend_async.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64,
+                                            vp, vp, vp, vp, vp, vp, vp]
+        L.bwa_b200_extend_query.argtypes = [vp]
+        L.bwa_b200_extend_wait.argtypes = [vp]
+        L.bwa_b200_extend_device.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.bwa_b200_pack_device.argtypes = [vp, vp, C.c_uint64, vp]
+        L.bwa_b200_extender_stream.argtypes = [vp]
+        L.bwa_b200_extender_stream.restype = vp
+        L.bwa_b200_extender_launches.argtypes = [vp]
+        L.bwa_b200_extender_launches.restype = C.c_uint64
+        L.bwa_b200_extender_last_cells.argtypes = [vp]
+        L.bwa_b200_extender_last_cells.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B200Error(rc, lib().bwa_b200_last_error().decode())
+
+
+def _p(a):
+    """raw pointer of a numpy array (kept alive by the caller) or an int device pointer"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def build_index(fwd_codes: np.ndarray, prefix: str, sa_intv: int = 16, also_stock_layout: bool = False, n_threads: int = 0):
+    fwd = np.ascontiguousarray(fwd_codes, dtype=np.uint8)
+    check(lib().bwa_b200_build_index(_p(fwd), fwd.size, sa_intv, prefix.encode(), int(also_stock_layout), n_threads))
+
+
+def pack_codes(reads_flat: np.ndarray, base_off: np.ndarray, n_threads: int = 0):
+    """codes (0..4) -> (packed u32 words, word_off u64[n+1], read_len u32[n])"""
+    reads_flat = np.ascontiguousarray(reads_flat, dtype=np.uint8)
+    base_off = np.ascontiguousarray(base_off, dtype=np.uint64)
+    n = base_off.size - 1
+    lens = (base_off[1:] - base_off[:-1]).astype(np.uint32)
+    n_words = int(((lens.astype(np.uint64) + 7) // 8).sum())
+    packed = np.zeros(max(n_words, 1), np.uint32)
+    woff = np.zeros(n + 1, np.uint64)
+    rl = np.zeros(max(n, 1), np.uint32)
+    check(lib().bwa_b200_pack_codes(_p(reads_flat), _p(base_off), n, _p(packed), _p(woff), _p(rl), n_threads))
+    return packed[:n_words], woff, rl[:n]
+
+
+def pack_ascii(ascii_bytes: np.ndarray, base_off: np.ndarray, n_threads: int = 0):
+    ascii_bytes = np.ascontiguousarray(ascii_bytes, dtype=np.uint8)
+    base_off = np.ascontiguousarray(base_off, dtype=np.uint64)
+    n = base_off.size - 1
+    lens = (base_off[1:] - base_off[:-1]).astype(np.uint32)
+    n_words = int(((lens.astype(np.uint64) + 7) // 8).sum())
+    packed = np.zeros(max(n_words, 1), np.uint32)
+    woff = np.zeros(n + 1, np.uint64)
+    rl = np.zeros(max(n, 1), np.uint32)
+    check(lib().bwa_b200_pack_ascii(_p(ascii_bytes), _p(base_off), n, _p(packed), _p(woff), _p(rl), n_threads))
+    return packed[:n_words], woff, rl[:n]
+
+
+class Index:
+    """Device-resident FMD index (bwt_restore_bwt_gpu + bwt_restore_sa_gpu + gpu_cpy_wrapper)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def load(cls, bwt_path: str, sa_path: str | None, device: int = 0):
+        h = vp()
+        check(lib().bwa_b200_index_load(bwt_path.encode(), sa_path.encode() if sa_path else None, device, C.byref(h)))
+        return cls(h)
+
+    def clone_to(self, device: int):
+        h = vp()
+        check(lib().bwa_b200_index_clone_to(self.h, device, C.byref(h)))
+        return Index(h)
+
+    def info(self) -> IndexInfo:
+        info = IndexInfo()
+        check(lib().bwa_b200_index_info(self.h, C.byref(info)))
+        return info
+
+    def free(self):
+        if self.h:
+            lib().bwa_b200_index_free(self.h)
+            self.h = None
+
+
+class Seeder:
+    def __init__(self, index: Index, max_reads: int, max_words: int):
+        self.h = vp()
+        self.index = index
+        check(lib().bwa_b200_seeder_create(index.h, max_reads, max_words, C.byref(self.h)))
+
+    def seed_host(self, packed, word_off, read_len, min_seed_len=19, max_occ=500):
+        """host arrays in, numpy arrays out (copies of the malloc'ed result)."""
+        n = read_len.size
+        p = SeedParams(min_seed_len, max_occ)
+        out = Seeds()
+        check(lib().bwa_b200_seed_host(self.h, _p(packed), _p(word_off), _p(read_len), n, C.byref(p), C.byref(out)))
+        tot = int(out.n_seeds)
+        res = dict(
+            total=tot,
+            rbeg=np.ctypeslib.as_array(out.rbeg, shape=(max(tot, 1),))[:tot].copy(),
+            qq=np.ctypeslib.as_array(out.qbeg_qend, shape=(max(tot, 1) * 2,))[:2 * tot].copy().reshape(-1, 2),
+            score=np.ctypeslib.as_array(out.score, shape=(max(tot, 1),))[:tot].copy(),
+            n_seeds=np.ctypeslib.as_array(out.n_seeds_per_read, shape=(max(n, 1),))[:n].copy(),
+            seed_off=np.ctypeslib.as_array(out.seed_off, shape=(max(n, 1),))[:n].copy(),
+        )
+        lib().bwa_b200_seeds_free(C.byref(out))
+        return res
+
+    def seed_device(self, d_packed: int, d_word_off: int, d_read_len: int, n_reads: int, min_seed_len=19, max_occ=500):
+        p = SeedParams(min_seed_len, max_occ)
+        check(lib().bwa_b200_seed_device(self.h, d_packed, d_word_off, d_read_len, n_reads, C.byref(p)))
+
+    def device_result(self) -> Seeds:
+        out = Seeds()
+        check(lib().bwa_b200_seed_device_result(self.h, C.byref(out)))
+        return out
+
+    def smems(self, n_reads: int, cap: int):
+        n_smems = np.zeros(max(n_reads, 1), np.uint32)
+        qb = np.zeros(cap, np.int32)
+        qe = np.zeros(cap, np.int32)
+        k = np.zeros(cap, np.uint64)
+        s = np.zeros(cap, np.uint64)
+        tot = C.c_uint64()
+        check(lib().bwa_b200_seed_device_smems(self.h, n_reads, _p(n_smems), _p(qb), _p(qe), _p(k), _p(s), cap, C.byref(tot)))
+        t = int(tot.value)
+        return dict(n_smems=n_smems[:n_reads], qbeg=qb[:t], qend=qe[:t], k=k[:t], s=s[:t])
+
+    @property
+    def stream(self) -> int:
+        return int(lib().bwa_b200_seeder_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_seeder_launches(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_seeder_destroy(self.h)
+            self.h = None
+
+
+def ext_params(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, w=100, end_bonus=5, zdrop=100, use_band=1, pen_clip=5) -> ExtParams:
+    p = ExtParams()
+    lib().bwa_b200_fill_scmat(a, b, p.mat)
+    p.o_del, p.e_del, p.o_ins, p.e_ins = o_del, e_del, o_ins, e_ins
+    p.w, p.end_bonus, p.zdrop, p.use_band, p.pen_clip = w, end_bonus, zdrop, use_band, pen_clip
+    return p
+
+
+class Extender:
+    def __init__(self, device: int = 0, max_jobs: int = 1 << 16, max_q: int = 1 << 20, max_t: int = 1 << 21):
+        self.h = vp()
+        check(lib().bwa_b200_extender_create(device, max_jobs, max_q, max_t, C.byref(self.h)))
+
+    def extend_host(self, jobs: dict, params: ExtParams, want_triple: bool = True):
+        """jobs: qseq,tseq (uint8 codes), qoff,toff,qlen,tlen,h0 (uint32).  Returns (res6[n,6], triple[3,n])."""
+        n = jobs["qlen"].size
+        res = np.zeros((n, 6), np.int32)
+        tri = np.zeros((3, n), np.int32) if want_triple else None
+        check(lib().bwa_b200_extend_async(self.h, C.byref(params), n, _p(jobs["qseq"]), jobs["qseq"].size, _p(jobs["qoff"]),
+                                          _p(jobs["qlen"]), _p(jobs["tseq"]), jobs["tseq"].size, _p(jobs["toff"]),
+                                          _p(jobs["tlen"]), _p(jobs["h0"]), _p(res),
+                                          _p(tri[0]) if want_triple else None, _p(tri[1]) if want_triple else None,
+                                          _p(tri[2]) if want_triple else None))
+        check(lib().bwa_b200_extend_wait(self.h))
+        return res, tri
+
+    def extend_async(self, params, n, qseq, q_bytes, qoff, qlen, tseq, t_bytes, toff, tlen, h0, res6, sc=None, qe=None, te=None):
+        check(lib().bwa_b200_extend_async(self.h, C.byref(params), n, _p(qseq), q_bytes, _p(qoff), _p(qlen), _p(tseq), t_bytes,
+                                          _p(toff), _p(tlen), _p(h0), _p(res6), _p(sc), _p(qe), _p(te)))
+
+    def extend_device(self, params, n, d_qp, d_qoff, d_qlen, d_tp, d_toff, d_tlen, d_h0, d_res6):
+        check(lib().bwa_b200_extend_device(self.h, C.byref(params), n, d_qp, d_qoff, d_qlen, d_tp, d_toff, d_tlen, d_h0, d_res6))
+
+    def pack_device(self, d_bytes: int, n_bytes: int, d_packed: int):
+        check(lib().bwa_b200_pack_device(self.h, d_bytes, n_bytes, d_packed))
+
+    def query(self) -> int:
+        return int(lib().bwa_b200_extend_query(self.h))
+
+    def wait(self):
+        check(lib().bwa_b200_extend_wait(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().bwa_b200_extender_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_extender_launches(self.h))
+
+    def last_cells(self) -> int:
+        return int(lib().bwa_b200_extender_last_cells(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_extender_destroy(self.h)
+            self.h = None

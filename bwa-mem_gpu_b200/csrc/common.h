@@ -1,0 +1,43 @@
+// common.h -- shared declarations of the B200 hot-path library (internal).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <cuda_runtime.h>
+#include "bwamem_b200.h"
+
+namespace b200 {
+
+void set_error(const char *fmt, ...);
+
+#define B200_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            b200::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return BWA_B200_ERR_CUDA;                                                       \
+        }                                                                                   \
+    } while (0)
+
+// Device view of the FMD index, passed by value to kernels (lives in the constant bank).
+struct IndexView {
+    const uint32_t *bkt;     // 32-byte buckets: {cnt[4], sym[4]} per 64 BWT symbols
+    const uint32_t *sa;      // low 32 bits of the sampled suffix array
+    const uint32_t *sa_hi;   // packed high bits
+    uint64_t primary, seq_len;
+    uint64_t L2[5];
+    uint32_t sa_shift;       // log2(sa_intv)
+    uint32_t pack_size, pack_mask;
+};
+
+} // namespace b200
+
+struct bwa_b200_index {
+    int device = 0;
+    b200::IndexView v{};
+    uint32_t *d_bkt = nullptr, *d_sa = nullptr, *d_sa_hi = nullptr;
+    uint64_t n_words = 0, n_sa = 0, n_hi = 0;
+    int sa_intv = 0, pack_size = 0;
+};

@@ -1,0 +1,484 @@
+// extend.cu -- ksw_extend2-equivalent banded seed extension, sm_100a.
+//
+// Parity target: ksw_extend2 (src/ksw.c:864-986; stock bwa_index/ksw.c:380-479): affine gaps,
+// band, z-drop, end bonus; outputs max score, qle, tle, gtle, gscore, max_off -- bit-exact,
+// including the reference's row-window semantics: row i evaluates columns [beg_i, end_i) only,
+// the window is re-derived from zeros of the previous row, and state outside the window keeps
+// whatever an earlier row (or the initial row) left there.  Those semantics are row-sequential,
+// so the inter-query kernel below keeps rows in order per job and never speculates across rows.
+//
+//   ext_inter_kernel   one job per lane.  The per-column state {H(i-1,j-1), E(i,j)} lives in
+//                      shared memory as one 32-bit word per column (two 16-bit fields), laid out
+//                      [column][lane] so lanes never conflict; the query is staged next to it
+//                      as 4-bit codes.  DPX min/max instructions (VIADDMNMX / VIMNMX3) implement
+//                      the recurrences.  Jobs are sorted by query length on the device and
+//                      launched per length bin, so lanes of a warp run similar trip counts and
+//                      each bin gets exactly the shared memory its longest query needs.
+//
+// This is not a port of GASAL2's KSW kernel (one thread per alignment with eh[] in local
+// memory, no band, zdrop = 0, fixed clip penalty): band, z-drop, end bonus and separate
+// insertion/deletion penalties are honoured, and all six outputs are returned.
+#include "common.h"
+#include <cub/cub.cuh>
+
+namespace {
+
+struct ExtParams {
+    int8_t  mat[32];
+    int32_t o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, use_band, pen_clip;
+    int32_t max_score;           // max entry of mat (band clamp, src/ksw.c:886-887)
+};
+
+constexpr int N_BINS = 7;
+__constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
+
+struct JobView {
+    const uint8_t  *qb, *tb;     // byte-per-base sequences (BYTES) ...
+    const uint32_t *qp, *tp;     // ... or 4-bit packed (offsets in bases, multiples of 8)
+    const uint32_t *qoff, *qlen, *toff, *tlen, *h0;
+};
+
+// sort key: query length, with jobs whose scores could overflow 16 bits pushed behind bit 20
+__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, uint32_t *keys, uint32_t *vals)
+{
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    uint32_t q = qlen[a];
+    uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
+    keys[a] = (q > 0xfffffu ? 0xfffffu : q) | (bound >= 65535ull ? (1u << 20) : 0u);
+    vals[a] = a;
+}
+
+// bin b of the narrow class covers sorted positions [range[b], range[b+1]); range[N_BINS+1] = n
+__global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag)
+{
+    int b = threadIdx.x;
+    if (b > N_BINS + 1) return;
+    // first position whose key exceeds the bin's upper bound
+    uint32_t bound = b == 0 ? 0u : (b <= N_BINS ? (uint32_t)c_bin_hi[b - 1] : 0xffffffffu);
+    uint32_t lo = 0, hi = n;
+    if (b == 0) { range[0] = 0; return; }
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] <= bound) lo = mid + 1; else hi = mid; }
+    range[b] = lo;
+    // anything past the last bin (query > 1024 or scores beyond 16 bits) is not handled by this kernel
+    if (b == N_BINS && lo < n) atomicExch(err_flag, 2);
+}
+
+__device__ __forceinline__ int sext8(uint32_t lo, uint32_t hi, int qb)
+{ // entry qb (0..4) of a packed 5 x int8 matrix row
+    uint32_t v = qb < 4 ? (lo >> (8 * qb)) : hi;
+    return (int)(int8_t)(v & 0xffu);
+}
+
+template <bool BYTES>
+__global__ void __launch_bounds__(128)
+ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
+                 int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
+                 int *__restrict__ err_flag)
+{
+    extern __shared__ uint32_t smem[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    uint32_t *eh = smem;                                   // [(max_q + 1)][nt]   h | e << 16
+    uint32_t *qs = smem + (size_t)(max_q + 1) * nt;        // [ceil(max_q / 8)][nt] 4-bit codes
+    const uint32_t lo = range[bin], hi = range[bin + 1];
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    unsigned long long my_cells = 0;
+
+    for (uint32_t base = lo + blockIdx.x * nt; base < hi; base += gridDim.x * nt) {
+        const uint32_t pos = base + tid;
+        if (pos < hi) {
+            const uint32_t a = order[pos];
+            const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
+            const uint32_t qo = J.qoff[a], to = J.toff[a];
+            if (qlen > max_q || qlen < 1 || h0 < 1) { atomicExch(err_flag, 1); continue; }
+
+            // stage the query
+            for (int j8 = 0; j8 < qlen; j8 += 8) {
+                uint32_t wv;
+                if (BYTES) {
+                    wv = 0;
+                    for (int u = 0; u < 8; ++u) { uint32_t c = j8 + u < qlen ? J.qb[qo + j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+                } else wv = J.qp[(qo + j8) >> 3];
+                qs[(j8 >> 3) * nt + tid] = wv;
+            }
+            // first row: H(-1,-1) = h0, then one gap open, then extensions (src/ksw.c:880-883)
+            {
+                int v = h0;
+                eh[tid] = (uint32_t)v;
+                v = h0 > oe_ins ? h0 - oe_ins : 0;
+                for (int j = 1; j <= qlen; ++j) {
+                    eh[j * nt + tid] = (uint32_t)v;
+                    v = v > P.e_ins ? v - P.e_ins : 0;
+                }
+            }
+            // band clamp (src/ksw.c:885-893)
+            int w = P.w;
+            {
+                int max_ins = (int)((double)(qlen * P.max_score + P.end_bonus - P.o_ins) / P.e_ins + 1.);
+                max_ins = max_ins > 1 ? max_ins : 1;
+                w = w < max_ins ? w : max_ins;
+                int max_del = (int)((double)(qlen * P.max_score + P.end_bonus - P.o_del) / P.e_del + 1.);
+                max_del = max_del > 1 ? max_del : 1;
+                w = w < max_del ? w : max_del;
+            }
+            int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+            int beg = 0, end = qlen;
+            uint32_t tword = 0;
+            for (int i = 0; i < tlen; ++i) {
+                int tbv;
+                if (BYTES) { tbv = J.tb[to + i]; tbv = tbv > 4 ? 4 : tbv; }
+                else {
+                    if ((i & 7) == 0) tword = J.tp[(to + i) >> 3];
+                    tbv = (int)((tword >> (28 - 4 * (i & 7))) & 15u);
+                    tbv = tbv > 4 ? 4 : tbv;
+                }
+                const int8_t *mr = P.mat + tbv * 5;
+                const uint32_t mlo = (uint32_t)(uint8_t)mr[0] | (uint32_t)(uint8_t)mr[1] << 8 | (uint32_t)(uint8_t)mr[2] << 16 | (uint32_t)(uint8_t)mr[3] << 24;
+                const uint32_t mhi = (uint32_t)(uint8_t)mr[4];
+                if (P.use_band) {
+                    if (beg < i - w) beg = i - w;
+                    if (end > i + w + 1) end = i + w + 1;
+                    if (end > qlen) end = qlen;
+                }
+                int h1 = 0, f = 0;
+                if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 < 0 ? 0 : h1; }
+                uint32_t key = 0;                      // (row max << 16) | column, last column wins ties
+                uint32_t qw = beg < end ? qs[(beg >> 3) * nt + tid] : 0u;
+                for (int j = beg; j < end; ++j) {
+                    if ((j & 7) == 0) qw = qs[(j >> 3) * nt + tid];
+                    const uint32_t p = eh[j * nt + tid];
+                    int M = (int)(p & 0xffffu), e = (int)(p >> 16);
+                    const int qb = (int)((qw >> (28 - 4 * (j & 7))) & 7u);
+                    const int sc = sext8(mlo, mhi, qb);
+                    M = M ? M + sc : 0;
+                    int h = __vimax3_s32(M, e, f);
+                    const uint32_t kj = ((uint32_t)h << 16) | (uint32_t)j;
+                    key = key > kj ? key : kj;
+                    const int t1 = __viaddmax_s32(M, -oe_del, 0);
+                    const int en = __viaddmax_s32(e, -P.e_del, t1);
+                    const int t2 = __viaddmax_s32(M, -oe_ins, 0);
+                    f = __viaddmax_s32(f, -P.e_ins, t2);
+                    eh[j * nt + tid] = (uint32_t)h1 | ((uint32_t)en << 16);
+                    h1 = h;
+                }
+                my_cells += (unsigned long long)(end > beg ? end - beg : 0);
+                eh[end * nt + tid] = (uint32_t)h1;     // H(i, end-1); E = 0
+                const int m = (int)(key >> 16), mj = beg < end ? (int)(key & 0xffffu) : -1;
+                if (end == qlen && beg < end) {        // `j == qlen` after the column loop
+                    best_ie = gscore > h1 ? best_ie : i;
+                    gscore = gscore > h1 ? gscore : h1;
+                }
+                if (m == 0) break;
+                if (m > best) {
+                    best = m; best_i = i; best_j = mj;
+                    const int d = mj > i ? mj - i : i - mj;
+                    max_off = max_off > d ? max_off : d;
+                } else if (P.zdrop > 0) {
+                    const int di = i - best_i, dj = mj - best_j;
+                    if (di > dj) { if (best - m - (di - dj) * P.e_del > P.zdrop) break; }
+                    else         { if (best - m - (dj - di) * P.e_ins > P.zdrop) break; }
+                }
+                int j = beg;
+                while (j < end && eh[j * nt + tid] == 0u) ++j;
+                beg = j;
+                j = end;
+                while (j >= beg && eh[j * nt + tid] == 0u) --j;
+                end = j + 2 < qlen ? j + 2 : qlen;
+            }
+            bwa_b200_ext_result_t r;
+            r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = best_ie + 1; r.gscore = gscore; r.max_off = max_off;
+            res[a] = r;
+        }
+    }
+    // one atomic per warp for the evaluated-cell counter
+    for (int o = 16; o > 0; o >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, o);
+    if ((tid & 31) == 0 && my_cells) atomicAdd(cells_total, my_cells);
+}
+
+// (score, qend, tend) after the local-vs-to-end rule (src/bwamem.c:1892-1901)
+__global__ void triple_kernel(uint32_t n, const bwa_b200_ext_result_t *res, const uint32_t *qlen, int pen_clip,
+                              int32_t *score, int32_t *qend, int32_t *tend)
+{
+    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    bwa_b200_ext_result_t r = res[a];
+    bool local = r.gscore <= 0 || r.gscore <= r.score - pen_clip;
+    score[a] = local ? r.score : r.gscore;
+    qend[a] = local ? r.qle : (int32_t)qlen[a];
+    tend[a] = local ? r.tle : r.gtle;
+}
+
+__global__ void pack_kernel(const uint8_t *__restrict__ bytes, uint64_t n_words, uint64_t n_bytes, uint32_t *__restrict__ packed)
+{
+    uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n_words) return;
+    uint32_t wv = 0;
+    for (int u = 0; u < 8; ++u) {
+        uint64_t p = wi * 8 + u;
+        uint32_t c = p < n_bytes ? bytes[p] : 4u;
+        wv |= (c > 4u ? 4u : c) << (28 - 4 * u);
+    }
+    packed[wi] = wv;
+}
+
+} // namespace
+
+struct bwa_b200_extender {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t max_jobs = 0, max_q = 0, max_t = 0;
+    uint8_t *d_q = nullptr, *d_t = nullptr;
+    uint32_t *d_qoff = nullptr, *d_qlen = nullptr, *d_toff = nullptr, *d_tlen = nullptr, *d_h0 = nullptr;
+    uint32_t *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_order = nullptr, *d_range = nullptr;
+    bwa_b200_ext_result_t *d_res = nullptr;
+    int32_t *d_tri = nullptr;
+    unsigned long long *d_cells = nullptr;
+    int *d_err = nullptr;
+    void *d_cub = nullptr;
+    size_t cub_bytes = 0;
+    unsigned long long *h_cells = nullptr;
+    int *h_err = nullptr;
+    uint64_t launches = 0;
+    bool pending = false;
+    int smem_optin = 0;
+};
+
+static int ext_grow_jobs(bwa_b200_extender *e, uint64_t n)
+{
+    if (n <= e->max_jobs) return BWA_B200_OK;
+    uint64_t cap = n + n / 4 + 256;
+    cudaFree(e->d_qoff); cudaFree(e->d_qlen); cudaFree(e->d_toff); cudaFree(e->d_tlen); cudaFree(e->d_h0);
+    cudaFree(e->d_keys); cudaFree(e->d_keys2); cudaFree(e->d_vals); cudaFree(e->d_order); cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cub);
+    e->d_qoff = e->d_qlen = e->d_toff = e->d_tlen = e->d_h0 = e->d_keys = e->d_keys2 = e->d_vals = e->d_order = nullptr;
+    e->d_res = nullptr; e->d_tri = nullptr; e->d_cub = nullptr; e->max_jobs = 0;
+    B200_CUDA(cudaMalloc(&e->d_qoff, cap * 4)); B200_CUDA(cudaMalloc(&e->d_qlen, cap * 4));
+    B200_CUDA(cudaMalloc(&e->d_toff, cap * 4)); B200_CUDA(cudaMalloc(&e->d_tlen, cap * 4));
+    B200_CUDA(cudaMalloc(&e->d_h0, cap * 4));
+    B200_CUDA(cudaMalloc(&e->d_keys, cap * 4)); B200_CUDA(cudaMalloc(&e->d_keys2, cap * 4));
+    B200_CUDA(cudaMalloc(&e->d_vals, cap * 4)); B200_CUDA(cudaMalloc(&e->d_order, cap * 4));
+    B200_CUDA(cudaMalloc(&e->d_res, cap * sizeof(bwa_b200_ext_result_t)));
+    B200_CUDA(cudaMalloc(&e->d_tri, cap * 3 * 4));
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, e->cub_bytes, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)cap, 0, 21, e->stream));
+    B200_CUDA(cudaMalloc(&e->d_cub, e->cub_bytes + 16));
+    e->max_jobs = cap;
+    return BWA_B200_OK;
+}
+
+static int ext_grow_seq(bwa_b200_extender *e, uint64_t qb, uint64_t tb)
+{
+    if (qb > e->max_q) { cudaFree(e->d_q); e->d_q = nullptr; e->max_q = 0; uint64_t c = qb + qb / 4 + 64; B200_CUDA(cudaMalloc(&e->d_q, c)); e->max_q = c; }
+    if (tb > e->max_t) { cudaFree(e->d_t); e->d_t = nullptr; e->max_t = 0; uint64_t c = tb + tb / 4 + 64; B200_CUDA(cudaMalloc(&e->d_t, c)); e->max_t = c; }
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_fill_scmat(int a, int b, int8_t mat[25])
+{ // bwa_fill_scmat (src/bwa.c): match a, mismatch -b, anything against N -1
+    int k = 0;
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) mat[k++] = (int8_t)(i == j ? a : -b); mat[k++] = -1; }
+    for (int j = 0; j < 5; ++j) mat[k++] = -1;
+}
+
+extern "C" void bwa_b200_ext_params_default(bwa_b200_ext_params_t *p)
+{
+    if (!p) return;
+    bwa_b200_fill_scmat(1, 4, p->mat);
+    p->o_del = p->o_ins = 6; p->e_del = p->e_ins = 1;
+    p->w = 100; p->end_bonus = 5; p->zdrop = 100; p->use_band = 1; p->pen_clip = 5;
+}
+
+extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t max_query_bytes, uint64_t max_target_bytes,
+                                        bwa_b200_extender_t **out)
+{
+    if (!out) { b200::set_error("extender_create: bad argument"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(device));
+    bwa_b200_extender *e = new bwa_b200_extender();
+    e->device = device;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->n_sm = prop.multiProcessorCount;
+    e->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    B200_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&e->d_range, (N_BINS + 2) * 4));
+    B200_CUDA(cudaMalloc(&e->d_cells, 8));
+    B200_CUDA(cudaMalloc(&e->d_err, 4));
+    B200_CUDA(cudaMemset(e->d_cells, 0, 8));
+    B200_CUDA(cudaMemset(e->d_err, 0, 4));
+    B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&e->h_err, 4, cudaHostAllocDefault));
+    *e->h_cells = 0; *e->h_err = 0;
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
+    if (rc) return rc;
+    rc = ext_grow_seq(e, max_query_bytes ? max_query_bytes : 1024, max_target_bytes ? max_target_bytes : 1024);
+    if (rc) return rc;
+    *out = e;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_extender_destroy(bwa_b200_extender_t *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_q); cudaFree(e->d_t); cudaFree(e->d_qoff); cudaFree(e->d_qlen); cudaFree(e->d_toff); cudaFree(e->d_tlen);
+    cudaFree(e->d_h0); cudaFree(e->d_keys); cudaFree(e->d_keys2); cudaFree(e->d_vals); cudaFree(e->d_order); cudaFree(e->d_range);
+    cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cells); cudaFree(e->d_err); cudaFree(e->d_cub);
+    cudaFreeHost(e->h_cells); cudaFreeHost(e->h_err);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" void *bwa_b200_extender_stream(bwa_b200_extender_t *e) { return e ? (void *)e->stream : nullptr; }
+extern "C" uint64_t bwa_b200_extender_launches(const bwa_b200_extender_t *e) { return e ? e->launches : 0; }
+
+static void to_dev_params(const bwa_b200_ext_params_t *p, ExtParams *d)
+{
+    memset(d, 0, sizeof(*d));
+    memcpy(d->mat, p->mat, 25);
+    d->o_del = p->o_del; d->e_del = p->e_del; d->o_ins = p->o_ins; d->e_ins = p->e_ins;
+    d->w = p->w; d->end_bonus = p->end_bonus; d->zdrop = p->zdrop; d->use_band = p->use_band; d->pen_clip = p->pen_clip;
+    int mx = 0;
+    for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
+    d->max_score = mx;
+}
+
+// sort by query length, derive bin ranges, launch one kernel per bin (empty bins exit at once)
+template <bool BYTES>
+static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n, const JobView &J,
+                      bwa_b200_ext_result_t *d_res)
+{
+    if (p->e_del <= 0 || p->e_ins <= 0) { b200::set_error("extend: gap extension penalties must be positive"); return BWA_B200_ERR_ARG; }
+    ExtParams P;
+    to_dev_params(p, &P);
+    B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
+    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, e->d_keys, e->d_vals);
+    size_t tmp = e->cub_bytes;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
+    range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err);
+    e->launches += 3;
+    static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
+    for (int b = 0; b < N_BINS; ++b) {
+        const int L = bin_hi[b];
+        const size_t per_thread = ((size_t)(L + 1) + (size_t)(L + 7) / 8) * 4;
+        int nt = 128;
+        while (nt > 32 && per_thread * nt > (size_t)e->smem_optin / 2) nt -= 32;
+        size_t smem = per_thread * nt;
+        if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ext_inter_kernel<BYTES>, nt, smem));
+        if (occ < 1) occ = 1;
+        uint32_t max_blocks = (n + nt - 1) / nt;
+        uint32_t grid = (uint32_t)(e->n_sm * occ);
+        if (grid > max_blocks) grid = max_blocks;
+        if (grid < 1) grid = 1;
+        ext_inter_kernel<BYTES><<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err);
+        e->launches += 1;
+    }
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                     const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                                     const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                                     const uint32_t *h0, bwa_b200_ext_result_t *res6,
+                                     int32_t *aln_score, int32_t *query_end, int32_t *target_end)
+{
+    if (!e || !p || !qseq || !tseq || !qoff || !qlen || !toff || !tlen || !h0) { b200::set_error("extend_async: null argument"); return BWA_B200_ERR_ARG; }
+    if (n_jobs == 0) { b200::set_error("extend_async: n_jobs == 0"); return BWA_B200_ERR_ARG; }      // gasal_align.cu:32-35
+    if (q_bytes == 0 || t_bytes == 0) { b200::set_error("extend_async: empty batch"); return BWA_B200_ERR_ARG; }
+    if (n_jobs >= 0x7fffffffull) { b200::set_error("extend_async: too many jobs"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(e->device));
+    int rc = ext_grow_jobs(e, n_jobs);
+    if (rc) return rc;
+    rc = ext_grow_seq(e, q_bytes, t_bytes);
+    if (rc) return rc;
+    const uint32_t n = (uint32_t)n_jobs;
+    cudaStream_t st = e->stream;
+    B200_CUDA(cudaMemcpyAsync(e->d_q, qseq, q_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_t, tseq, t_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_qoff, qoff, n * 4ull, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_qlen, qlen, n * 4ull, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_toff, toff, n * 4ull, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_tlen, tlen, n * 4ull, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(e->d_h0, h0, n * 4ull, cudaMemcpyHostToDevice, st));
+    JobView J{e->d_q, e->d_t, nullptr, nullptr, e->d_qoff, e->d_qlen, e->d_toff, e->d_tlen, e->d_h0};
+    rc = ext_launch<true>(e, p, n, J, e->d_res);
+    if (rc) return rc;
+    if (res6) B200_CUDA(cudaMemcpyAsync(res6, e->d_res, n * sizeof(bwa_b200_ext_result_t), cudaMemcpyDeviceToHost, st));
+    if (aln_score || query_end || target_end) {
+        triple_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_res, e->d_qlen, p->pen_clip, e->d_tri, e->d_tri + e->max_jobs, e->d_tri + 2 * e->max_jobs);
+        e->launches += 1;
+        if (aln_score) B200_CUDA(cudaMemcpyAsync(aln_score, e->d_tri, n * 4ull, cudaMemcpyDeviceToHost, st));
+        if (query_end) B200_CUDA(cudaMemcpyAsync(query_end, e->d_tri + e->max_jobs, n * 4ull, cudaMemcpyDeviceToHost, st));
+        if (target_end) B200_CUDA(cudaMemcpyAsync(target_end, e->d_tri + 2 * e->max_jobs, n * 4ull, cudaMemcpyDeviceToHost, st));
+    }
+    B200_CUDA(cudaMemcpyAsync(e->h_cells, e->d_cells, 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, st));
+    e->pending = true;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_extend_query(bwa_b200_extender_t *e)
+{
+    if (!e) return BWA_B200_ERR_ARG;
+    cudaError_t st = cudaStreamQuery(e->stream);
+    if (st == cudaSuccess) { e->pending = false; return 0; }
+    if (st == cudaErrorNotReady) return 1;
+    b200::set_error("extend_query: %s", cudaGetErrorString(st));
+    return BWA_B200_ERR_CUDA;
+}
+
+extern "C" int bwa_b200_extend_wait(bwa_b200_extender_t *e)
+{
+    if (!e) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+    e->pending = false;
+    if (*e->h_err) {
+        *e->h_err = 0;
+        cudaMemsetAsync(e->d_err, 0, 4, e->stream);
+        b200::set_error("extend: a job had qlen < 1, qlen > 1024 or h0 < 1 (ksw_extend2 asserts h0 > 0, src/ksw.c:869)");
+        return BWA_B200_ERR_ARG;
+    }
+    return BWA_B200_OK;
+}
+
+extern "C" uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e)
+{
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaMemcpyAsync(e->h_cells, e->d_cells, 8, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    return *e->h_cells;
+}
+
+extern "C" int bwa_b200_extend_device(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                      const uint32_t *dev_qpacked, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
+                                      const uint32_t *dev_tpacked, const uint32_t *dev_toff, const uint32_t *dev_tlen,
+                                      const uint32_t *dev_h0, bwa_b200_ext_result_t *dev_res6)
+{
+    if (!e || !p || !dev_qpacked || !dev_tpacked || !dev_qoff || !dev_qlen || !dev_toff || !dev_tlen || !dev_h0 || !dev_res6) { b200::set_error("extend_device: null argument"); return BWA_B200_ERR_ARG; }
+    if (n_jobs == 0 || n_jobs >= 0x7fffffffull) { b200::set_error("extend_device: bad n_jobs"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(e->device));
+    int rc = ext_grow_jobs(e, n_jobs);
+    if (rc) return rc;
+    JobView J{nullptr, nullptr, dev_qpacked, dev_tpacked, dev_qoff, dev_qlen, dev_toff, dev_tlen, dev_h0};
+    rc = ext_launch<false>(e, p, (uint32_t)n_jobs, J, dev_res6);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
+    e->pending = true;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_pack_device(bwa_b200_extender_t *e, const uint8_t *dev_bytes, uint64_t n_bytes, uint32_t *dev_packed)
+{
+    if (!e || !dev_bytes || !dev_packed) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(e->device));
+    uint64_t n_words = (n_bytes + 7) / 8;
+    if (n_words == 0) return BWA_B200_OK;
+    pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, e->stream>>>(dev_bytes, n_words, n_bytes, dev_packed);
+    e->launches += 1;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}

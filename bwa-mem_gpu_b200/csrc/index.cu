@@ -1,0 +1,336 @@
+// index.cu -- FMD index: file loader, HBM upload, peer replication, host-side builder.
+//
+// File formats are the reference's (bwa_index/bwt.c:461-487 writers; seed_gen.cu:1386-1468
+// readers; bwa_index/bwtindex.c:174-197 bucket layout).  In HBM the bucket array is kept
+// exactly as on disk: 32 bytes = one DRAM/L2 sector per 64 BWT symbols, so every occurrence
+// lookup costs one sector.
+#include "common.h"
+#include <algorithm>
+#include <cstdarg>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+namespace b200 {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+} // namespace b200
+
+extern "C" const char *bwa_b200_last_error(void) { return b200::g_err; }
+extern "C" int bwa_b200_version(void) { return 100; }
+
+extern "C" int bwa_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" void *bwa_b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void bwa_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static int ilog2(uint64_t x) { int r = 0; while ((1ull << r) < x) ++r; return r; }
+
+extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], const uint32_t *bwt_words, uint64_t n_words,
+                                        const uint32_t *sa, const uint32_t *sa_hi, uint64_t n_sa, int sa_intv, int pack_size,
+                                        int device, bwa_b200_index_t **out)
+{
+    if (!L2 || !bwt_words || !out || n_words < 8) { b200::set_error("index_from_host: bad argument"); return BWA_B200_ERR_ARG; }
+    if (sa && (sa_intv <= 0 || (sa_intv & (sa_intv - 1)))) { b200::set_error("SA interval %d is not a power of two", sa_intv); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(device));
+    bwa_b200_index *idx = new bwa_b200_index();
+    idx->device = device;
+    idx->n_words = n_words;
+    idx->n_sa = sa ? n_sa : 0;
+    idx->sa_intv = sa_intv;
+    idx->pack_size = pack_size;
+    uint64_t seq_len = L2[4];
+    // pad the bucket array to a whole bucket so 256-bit loads of the last one stay in bounds
+    uint64_t padded = (n_words + 7) / 8 * 8 + 8;
+    B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
+    B200_CUDA(cudaMemset(idx->d_bkt, 0, padded * 4));
+    B200_CUDA(cudaMemcpy(idx->d_bkt, bwt_words, n_words * 4, cudaMemcpyHostToDevice));
+    if (sa) {
+        B200_CUDA(cudaMalloc(&idx->d_sa, n_sa * 4));
+        B200_CUDA(cudaMemcpy(idx->d_sa, sa, n_sa * 4, cudaMemcpyHostToDevice));
+        idx->n_hi = (uint64_t)pack_size * n_sa / 32 + 1;
+        B200_CUDA(cudaMalloc(&idx->d_sa_hi, idx->n_hi * 4));
+        if (sa_hi) B200_CUDA(cudaMemcpy(idx->d_sa_hi, sa_hi, idx->n_hi * 4, cudaMemcpyHostToDevice));
+        else B200_CUDA(cudaMemset(idx->d_sa_hi, 0, idx->n_hi * 4));
+    }
+    b200::IndexView &v = idx->v;
+    v.bkt = idx->d_bkt; v.sa = idx->d_sa; v.sa_hi = idx->d_sa_hi;
+    v.primary = primary; v.seq_len = seq_len;
+    for (int i = 0; i < 5; ++i) v.L2[i] = L2[i];
+    v.sa_shift = sa ? (uint32_t)ilog2((uint64_t)sa_intv) : 0;
+    v.pack_size = (uint32_t)pack_size;
+    // bwa_index/bwt.c:82-112: no high bits are kept when seq_len < 2^32
+    v.pack_mask = (seq_len >> 32) == 0 ? 0u : (pack_size >= 32 ? 0xffffffffu : ((1u << pack_size) - 1));
+    *out = idx;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_index_load(const char *bwt_path, const char *sa_path, int device, bwa_b200_index_t **out)
+{
+    if (!bwt_path || !out) { b200::set_error("index_load: bad argument"); return BWA_B200_ERR_ARG; }
+    FILE *fp = fopen(bwt_path, "rb");
+    if (!fp) { b200::set_error("cannot open %s", bwt_path); return BWA_B200_ERR_IO; }
+    fseek(fp, 0, SEEK_END);
+    long fsz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (fsz < 40 + 32) { fclose(fp); b200::set_error("%s: too short", bwt_path); return BWA_B200_ERR_FORMAT; }
+    uint64_t primary, L2[5] = {0, 0, 0, 0, 0};
+    uint64_t n_words = (uint64_t)(fsz - 40) >> 2;
+    std::vector<uint32_t> words(n_words);
+    bool ok = fread(&primary, 8, 1, fp) == 1 && fread(L2 + 1, 8, 4, fp) == 4 && fread(words.data(), 4, n_words, fp) == n_words;
+    fclose(fp);
+    if (!ok) { b200::set_error("%s: short read", bwt_path); return BWA_B200_ERR_IO; }
+    uint64_t seq_len = L2[4];
+    // 32-bit-occ / 64-symbol layout has 4*ceil(n/64) + ceil(n/16) + 4 words
+    uint64_t expect = 4 * ((seq_len + 63) / 64) + (seq_len + 15) / 16 + 4;
+    if (n_words != expect) {
+        b200::set_error("%s: %llu payload words, expected %llu for the 32-bit-occ 64-symbol bucket layout (seq_len %llu); "
+                        "was the index built with `bwa index -s bwt` (OCC_INTV_SHIFT 6)?", bwt_path,
+                        (unsigned long long)n_words, (unsigned long long)expect, (unsigned long long)seq_len);
+        return BWA_B200_ERR_FORMAT;
+    }
+    if (!sa_path) return bwa_b200_index_from_host(primary, L2, words.data(), n_words, nullptr, nullptr, 0, 0, 0, device, out);
+    fp = fopen(sa_path, "rb");
+    if (!fp) { b200::set_error("cannot open %s", sa_path); return BWA_B200_ERR_IO; }
+    uint64_t hdr[7];
+    if (fread(hdr, 8, 7, fp) != 7) { fclose(fp); b200::set_error("%s: short header", sa_path); return BWA_B200_ERR_IO; }
+    if (hdr[0] != primary) { fclose(fp); b200::set_error("SA-BWT inconsistency: primary is not the same."); return BWA_B200_ERR_FORMAT; }
+    if (hdr[6] != seq_len) { fclose(fp); b200::set_error("SA-BWT inconsistency: seq_len is not the same."); return BWA_B200_ERR_FORMAT; }
+    int sa_intv = (int)hdr[5];
+    if (sa_intv <= 0 || (sa_intv & (sa_intv - 1))) { fclose(fp); b200::set_error("%s: bad SA interval", sa_path); return BWA_B200_ERR_FORMAT; }
+    uint64_t n_sa = (seq_len + (uint64_t)sa_intv) / (uint64_t)sa_intv;
+    std::vector<uint32_t> sa(n_sa);
+    sa[0] = 0xffffffffu;
+    uint8_t ps = 0;
+    ok = fread(sa.data() + 1, 4, n_sa - 1, fp) == n_sa - 1 && fread(&ps, 1, 1, fp) == 1;
+    if (!ok || ps == 0 || ps > 32) { fclose(fp); b200::set_error("%s: short read / bad pack_size", sa_path); return BWA_B200_ERR_FORMAT; }
+    uint64_t n_hi = (uint64_t)ps * n_sa / 32 + 1;
+    std::vector<uint32_t> hi(n_hi, 0);
+    size_t got = fread(hi.data(), 4, n_hi, fp); (void)got;
+    fclose(fp);
+    return bwa_b200_index_from_host(primary, L2, words.data(), n_words, sa.data(), hi.data(), n_sa, sa_intv, ps, device, out);
+}
+
+extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, bwa_b200_index_t **out)
+{
+    if (!src || !out) { b200::set_error("index_clone_to: bad argument"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(device));
+    bwa_b200_index *idx = new bwa_b200_index(*src);
+    idx->device = device;
+    idx->d_bkt = idx->d_sa = idx->d_sa_hi = nullptr;
+    uint64_t padded = (src->n_words + 7) / 8 * 8 + 8;
+    B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
+    B200_CUDA(cudaMemcpyPeer(idx->d_bkt, device, src->d_bkt, src->device, padded * 4));
+    if (src->d_sa) {
+        B200_CUDA(cudaMalloc(&idx->d_sa, src->n_sa * 4));
+        B200_CUDA(cudaMemcpyPeer(idx->d_sa, device, src->d_sa, src->device, src->n_sa * 4));
+        B200_CUDA(cudaMalloc(&idx->d_sa_hi, src->n_hi * 4));
+        B200_CUDA(cudaMemcpyPeer(idx->d_sa_hi, device, src->d_sa_hi, src->device, src->n_hi * 4));
+    }
+    idx->v.bkt = idx->d_bkt; idx->v.sa = idx->d_sa; idx->v.sa_hi = idx->d_sa_hi;
+    *out = idx;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_index_info(const bwa_b200_index_t *idx, bwa_b200_index_info_t *info)
+{
+    if (!idx || !info) return BWA_B200_ERR_ARG;
+    info->primary = idx->v.primary; info->seq_len = idx->v.seq_len;
+    for (int i = 0; i < 5; ++i) info->L2[i] = idx->v.L2[i];
+    info->n_buckets = (idx->v.seq_len + 63) / 64;
+    info->n_sa = idx->n_sa; info->sa_intv = idx->sa_intv; info->pack_size = idx->pack_size;
+    info->device = idx->device;
+    info->hbm_bytes = ((idx->n_words + 7) / 8 * 8 + 8) * 4 + idx->n_sa * 4 + idx->n_hi * 4;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_index_free(bwa_b200_index_t *idx)
+{
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    cudaFree(idx->d_bkt); cudaFree(idx->d_sa); cudaFree(idx->d_sa_hi);
+    delete idx;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-side index construction.  Suffix array of T = fwd + revcomp(fwd) by a 12-mer counting
+// sort followed by per-bucket comparison sorts on a 2-bit packed copy of T (32 bases per
+// 64-bit window), then BWT, occurrence buckets and SA samples in the reference's formats.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Packed {
+    std::vector<uint64_t> w;   // base i at bits 62-2*(i%32) of word i/32; zero padded
+    uint64_t n = 0;
+    inline uint64_t window(uint64_t i) const
+    { // 32 bases starting at i
+        uint64_t q = i >> 5, r = (i & 31) * 2;
+        uint64_t hi = w[q] << r;
+        uint64_t lo = r ? (w[q + 1] >> (64 - r)) : 0;
+        return hi | lo;
+    }
+    // suffix order with an implicit sentinel smaller than every base
+    inline bool less(uint64_t a, uint64_t b) const
+    {
+        uint64_t lim = n - std::max(a, b);
+        for (uint64_t off = 0; off < lim; off += 32) {
+            uint64_t x = window(a + off), y = window(b + off);
+            if (x != y) return x < y;
+        }
+        return a > b; // common prefix as long as the shorter one: the shorter suffix is smaller
+    }
+};
+
+template <class F> void parallel_for(uint64_t n, int n_threads, F f)
+{
+    if (n_threads <= 1 || n < 2) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    uint64_t chunk = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        uint64_t a = std::min(n, chunk * t), b = std::min(n, a + chunk);
+        th.emplace_back([=] { f(a, b, t); });
+    }
+    for (auto &x : th) x.join();
+}
+
+int write_file(const std::string &path, const std::vector<std::pair<const void *, size_t>> &parts)
+{
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) { b200::set_error("cannot write %s", path.c_str()); return BWA_B200_ERR_IO; }
+    for (auto &p : parts)
+        if (p.second && fwrite(p.first, 1, p.second, fp) != p.second) { fclose(fp); b200::set_error("short write %s", path.c_str()); return BWA_B200_ERR_IO; }
+    fclose(fp);
+    return BWA_B200_OK;
+}
+
+} // namespace
+
+extern "C" int bwa_b200_build_index(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *prefix,
+                                    int also_stock_layout, int n_threads)
+{
+    if (!fwd || !prefix || l_pac == 0 || sa_intv <= 0 || (sa_intv & (sa_intv - 1))) { b200::set_error("build_index: bad argument"); return BWA_B200_ERR_ARG; }
+    const uint64_t n = 2 * l_pac;
+    if (n >= 0xffffffffull) { b200::set_error("build_index: host builder handles 2*l_pac < 2^32 (got %llu)", (unsigned long long)n); return BWA_B200_ERR_CAPACITY; }
+    if (n_threads < 1) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    for (uint64_t i = 0; i < l_pac; ++i) if (fwd[i] > 3) { b200::set_error("build_index: code %d at %llu (only A,C,G,T)", fwd[i], (unsigned long long)i); return BWA_B200_ERR_ARG; }
+
+    // text + packed text
+    std::vector<uint8_t> T(n);
+    for (uint64_t i = 0; i < l_pac; ++i) { T[i] = fwd[i]; T[n - 1 - i] = (uint8_t)(3 - fwd[i]); }
+    Packed P;
+    P.n = n;
+    P.w.assign(n / 32 + 3, 0);
+    for (uint64_t i = 0; i < n; ++i) P.w[i >> 5] |= (uint64_t)T[i] << (62 - 2 * (i & 31));
+
+    // counting sort on the first K bases (zero padded past the end); shared atomic histogram
+    const int K = n > (1ull << 26) ? 13 : (n > (1ull << 20) ? 11 : 8);
+    const uint64_t NB = 1ull << (2 * K);
+    auto key = [&](uint64_t i) { return P.window(i) >> (64 - 2 * K); };
+    std::vector<uint32_t> start(NB + 1, 0), cursor(NB, 0);
+    std::vector<uint32_t> sa(n);
+    {
+        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int) {
+            for (uint64_t i = a; i < b; ++i) __atomic_fetch_add(&cursor[key(i)], 1u, __ATOMIC_RELAXED);
+        });
+        uint64_t run = 0;
+        for (uint64_t k = 0; k < NB; ++k) { start[k] = (uint32_t)run; run += cursor[k]; cursor[k] = start[k]; }
+        start[NB] = (uint32_t)run;
+        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int) {
+            for (uint64_t i = a; i < b; ++i) sa[__atomic_fetch_add(&cursor[key(i)], 1u, __ATOMIC_RELAXED)] = (uint32_t)i;
+        });
+        std::vector<uint32_t>().swap(cursor);
+        // per-bucket sorts, dynamically scheduled (a strict total order: result is unique)
+        std::atomic<uint64_t> next(0);
+        const uint64_t grain = 4096;
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t)
+            th.emplace_back([&] {
+                for (;;) {
+                    uint64_t k0 = next.fetch_add(grain);
+                    if (k0 >= NB) break;
+                    uint64_t k1 = std::min(NB, k0 + grain);
+                    for (uint64_t k = k0; k < k1; ++k) {
+                        uint32_t a = start[k], b = start[k + 1];
+                        if (b - a > 1) std::sort(sa.begin() + a, sa.begin() + b, [&](uint32_t x, uint32_t y) { return P.less(x, y); });
+                    }
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    {
+        // ---- BWT with '$' removed, primary, L2
+        uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0};
+        for (uint64_t i = 0; i < n; ++i) ++L2[T[i] + 1];
+        for (int c = 1; c <= 4; ++c) L2[c] += L2[c - 1];
+        std::vector<uint8_t> B(n);
+        // rows: 0 = empty suffix (char T[n-1]); row r>=1 = sa[r-1]
+        {
+            uint64_t j = 0;
+            B[j++] = T[n - 1];
+            for (uint64_t r = 1; r <= n; ++r) {
+                uint32_t p = sa[r - 1];
+                if (p == 0) { primary = r; continue; }
+                B[j++] = T[p - 1];
+            }
+        }
+        const uint64_t n_raw = (n + 15) / 16;
+        std::vector<uint32_t> raw(n_raw, 0);
+        for (uint64_t i = 0; i < n; ++i) raw[i >> 4] |= (uint32_t)B[i] << ((~i & 15) << 1);
+
+        // ---- GPU layout: u32 counts + 4 words per 64 symbols, trailing counts (bwtindex.c:174-197)
+        std::vector<uint32_t> g;
+        g.reserve(4 * ((n + 63) / 64) + n_raw + 4);
+        {
+            uint32_t c[4] = {0, 0, 0, 0};
+            for (uint64_t i = 0; i < n; ++i) {
+                if ((i & 63) == 0) g.insert(g.end(), c, c + 4);
+                if ((i & 15) == 0) g.push_back(raw[i >> 4]);
+                ++c[B[i]];
+            }
+            g.insert(g.end(), c, c + 4);
+        }
+        int rc = write_file(std::string(prefix) + ".bwt", {{&primary, 8}, {L2 + 1, 32}, {g.data(), g.size() * 4}});
+        if (rc) return rc;
+        if (also_stock_layout) { // u64 counts + 8 words per 128 symbols (bwtindex.c:151-172)
+            std::vector<uint32_t> s;
+            s.reserve(8 * ((n + 127) / 128) + n_raw + 8);
+            uint64_t c[4] = {0, 0, 0, 0};
+            for (uint64_t i = 0; i < n; ++i) {
+                if ((i & 127) == 0) { const uint32_t *cw = (const uint32_t *)c; s.insert(s.end(), cw, cw + 8); }
+                if ((i & 15) == 0) s.push_back(raw[i >> 4]);
+                ++c[B[i]];
+            }
+            const uint32_t *cw = (const uint32_t *)c;
+            s.insert(s.end(), cw, cw + 8);
+            rc = write_file(std::string(prefix) + ".bwt128", {{&primary, 8}, {L2 + 1, 32}, {s.data(), s.size() * 4}});
+            if (rc) return rc;
+        }
+        // ---- SA samples (bwa_index/bwt.c:64-148, 472-487)
+        const uint64_t n_sa = (n + (uint64_t)sa_intv) / (uint64_t)sa_intv;
+        std::vector<uint32_t> smp(n_sa);
+        smp[0] = 0xffffffffu;
+        for (uint64_t j = 1; j < n_sa; ++j) smp[j] = sa[j * (uint64_t)sa_intv - 1];
+        uint8_t pack_size = 1;                 // seq_len < 2^32 here: msb == 0 -> pack_size 1, mask 0
+        std::vector<uint32_t> hi((uint64_t)pack_size * n_sa / 32 + 1, 0);
+        uint64_t intv64 = (uint64_t)sa_intv, seq_len = n;
+        rc = write_file(std::string(prefix) + ".sa", {{&primary, 8}, {L2 + 1, 32}, {&intv64, 8}, {&seq_len, 8},
+                                                       {smp.data() + 1, (n_sa - 1) * 4}, {&pack_size, 1}, {hi.data(), hi.size() * 4}});
+        return rc;
+    }
+}

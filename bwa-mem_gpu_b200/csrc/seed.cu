@@ -1,0 +1,653 @@
+// seed.cu -- SMEM seeding over the FMD index + SA locate, sm_100a.
+//
+// Parity target: the reference's CPU path  mem_collect_intv pass 1 -> bwt_smem1 -> bwt_extend ->
+// bwt_2occ4, then bwt_sa on the rows mem_chain reads (bwa_index/bwamem.c:121-131,278-283;
+// src/bwt.c:340-566; bwa_index/bwt.c:151-172).  This is not a port of GPUSeed: the decomposition
+// below keeps the CPU algorithm's exact work (one bwt_extend per step, including its
+// interval-merging rule) while giving every lane an independent dependent-load chain.
+//
+//   fwd_kernel     one lane per read.  Runs the forward phases of successive bwt_smem1 calls
+//                  (x0 = 0, x_{i+1} = ret(x_i)) as one loop over the read: one bidirectional
+//                  extension (two 32-byte buckets, fetched with one 256-bit load each) per base.
+//                  Every change of interval size is recorded as a candidate (x, end, k, s).
+//   back_kernel    persistent lanes, one read at a time per lane, fetched dynamically.  For each
+//                  forward segment the candidates are walked backwards longest-first; a per-lane
+//                  "envelope" of the interval sizes of the previous (longer) candidate reproduces
+//                  the `ok[c].x[2] != curr->a[curr->n-1].x[2]` merge test and the
+//                  `curr->n == 0` / start-coordinate emission test of src/bwt.c:528-553 exactly,
+//                  so the number of extensions equals the CPU's.  Each loop iteration performs
+//                  exactly one backward extension for every lane, whatever its read/segment.
+//   fill_kernel    expands SMEMs to (row, qbeg, qend, score) entries at their final offsets.
+//   locate_kernel  persistent lanes, one SA row per lane: LF-walk to a sampled row; symbol and
+//                  occurrence count of a step come from the same 32-byte bucket.
+//
+// HBM traffic per read is dominated by random 32-byte sectors of the bucket array (one sector per
+// occurrence lookup); candidates cost 16 B written + read once per size change.
+#include "common.h"
+#include <cub/cub.cuh>
+
+using b200::IndexView;
+
+namespace {
+
+constexpr int FWD_THREADS = 128;
+constexpr int BACK_THREADS = 128;
+constexpr int ENV_SMEM = 24;          // envelope entries kept in shared memory per lane
+constexpr int LOC_THREADS = 128;
+
+struct __align__(16) Cand {           // one forward candidate / (after back_kernel) one SMEM
+    uint64_t k;                       // x[0]: first SA row
+    uint32_t s;                       // x[2]: interval size; 0 after back_kernel = not an SMEM
+    uint16_t x;                       // segment start (candidate) / SMEM begin (after back_kernel)
+    uint16_t end;                     // exclusive end on the read
+};
+
+// ----------------------------------------------------------------------------- bucket access
+struct Bkt { uint32_t c[4]; uint32_t w[4]; };
+
+__device__ __forceinline__ Bkt ld_bucket(const uint32_t *bkt, uint64_t b)
+{ // one 32-byte sector, one LDG.256 on sm_100
+    Bkt r;
+    const uint32_t *p = bkt + b * 8;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.c[0]), "=r"(r.c[1]), "=r"(r.c[2]), "=r"(r.c[3]), "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
+                 : "l"(p));
+    return r;
+}
+
+// even-bit mask selecting the first n (0..16) symbols of word `wi` when the bucket keeps n_tot
+// symbols; symbol i of a word sits at bits (15-i)*2
+__device__ __forceinline__ uint32_t keep_mask(int n_tot, int wi)
+{
+    int sh = 2 * n_tot - 32 * wi;
+    sh = sh < 0 ? 0 : sh;
+    return __funnelshift_rc(0u, 0xffffffffu, (uint32_t)sh) & 0x55555555u;
+}
+
+// occurrences of all four bases among the first n (1..64) symbols of a bucket, plus its counters
+__device__ __forceinline__ void bucket_occ4(const Bkt &b, int n, uint32_t cnt[4])
+{
+    uint32_t a = 0, c = 0, g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t w = b.w[i], h = w >> 1, m = keep_mask(n, i);
+        a += __popc(~w & ~h & m);
+        c += __popc(w & ~h & m);
+        g += __popc(~w & h & m);
+    }
+    cnt[0] = b.c[0] + a; cnt[1] = b.c[1] + c; cnt[2] = b.c[2] + g;
+    cnt[3] = b.c[3] + ((uint32_t)n - a - c - g);
+}
+
+// occurrences of one base among the first n symbols
+__device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base)
+{
+    uint32_t pat = (uint32_t)base * 0x55555555u, r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t y = b.w[i] ^ pat;
+        r += __popc(~y & ~(y >> 1) & keep_mask(n, i));
+    }
+    uint32_t base_cnt = base == 0 ? b.c[0] : (base == 1 ? b.c[1] : (base == 2 ? b.c[2] : b.c[3]));
+    return base_cnt + r;
+}
+
+// cumulative counts by select chain (a dynamic index into the kernel-parameter copy of the index
+// view would force it onto the local stack)
+__device__ __forceinline__ uint64_t L2_at(const IndexView &ix, int b)
+{
+    return b == 0 ? ix.L2[0] : (b == 1 ? ix.L2[1] : (b == 2 ? ix.L2[2] : (b == 3 ? ix.L2[3] : ix.L2[4])));
+}
+
+__device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, uint64_t woff, int i)
+{
+    uint32_t w = __ldg(packed + woff + (uint32_t)(i >> 3));
+    return (int)((w >> (28 - 4 * (i & 7))) & 15u);
+}
+
+// ------------------------------------------------------------------------------- fwd_kernel
+__global__ void __launch_bounds__(FWD_THREADS)
+fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+           const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, uint32_t cand_stride,
+           Cand *__restrict__ cand, uint32_t *__restrict__ n_cand)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int len = (int)read_len[r];
+    const uint64_t woff = word_off[r];
+    Cand *out = cand + (uint64_t)r * cand_stride;
+    uint32_t n_out = 0;
+    if (len < min_seed_len) { n_cand[r] = 0; return; }   // mem_chain: read shorter than a seed
+
+    uint64_t k = 0, l = 0;
+    uint32_t s = 0;
+    int x = -1, i = 0;
+    uint32_t word = 0;
+    bool active = false;
+    auto push = [&](int end) {
+        if (end >= min_seed_len) { Cand c; c.k = k; c.s = s; c.x = (uint16_t)x; c.end = (uint16_t)end; out[n_out++] = c; }
+    };
+    auto start_at = [&](int b, int p) {
+        k = L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = L2_at(ix, 3 - b) + 1; x = p; active = true;
+    };
+
+    word = __ldg(packed + woff);
+    while (i < len) {
+        int b = (int)((word >> (28 - 4 * (i & 7))) & 15u);
+        if (!active) {                       // looking for the first base of a segment
+            if (b < 4) start_at(b, i);
+            ++i;
+            if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
+            continue;
+        }
+        if (b > 3) {                         // ambiguous base ends the segment (src/bwt.c:516-519)
+            push(i);
+            active = false;
+            ++i;
+            if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
+            continue;
+        }
+        // forward extension by complement(b): bwt_extend(ik, ok, 0)  (src/bwt.c:455-470)
+        const int cb = 3 - b;
+        uint64_t p0 = l - 1, p1 = l - 1 + s;                 // rows; both >= 0
+        uint64_t j0 = p0 - (p0 >= ix.primary), j1 = p1 - (p1 >= ix.primary);
+        Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
+        Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);
+        uint32_t tk[4], tl[4];
+        bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
+        bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
+        uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
+        uint32_t ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
+        uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
+        uint64_t nk = k + (uint64_t)(l <= ix.primary && l + s - 1 >= ix.primary);
+        if (cb < 3) nk += s3;
+        if (cb < 2) nk += s2;
+        if (cb < 1) nk += s1;
+        if (ns != s) {
+            push(i);
+            if (ns == 0) {                   // cannot extend: next bwt_smem1 call starts here
+                start_at(b, i);
+                ++i;
+                if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
+                continue;
+            }
+        }
+        k = nk; l = L2_at(ix, cb) + 1 + tkc; s = ns;
+        ++i;
+        if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
+    }
+    if (active) push(len);                   // reached the end of the read (src/bwt.c:521-522)
+    n_cand[r] = n_out;
+}
+
+// ------------------------------------------------------------------------------ back_kernel
+__device__ __forceinline__ uint32_t seeds_of(uint32_t s, int max_occ)
+{ // bwa_index/bwamem.c:278-283
+    if (max_occ <= 0) return s;
+    uint32_t step = s > (uint32_t)max_occ ? s / (uint32_t)max_occ : 1u;
+    uint32_t cnt = (s + step - 1) / step;
+    return cnt < (uint32_t)max_occ ? cnt : (uint32_t)max_occ;
+}
+
+__global__ void __launch_bounds__(BACK_THREADS)
+back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_occ,
+            uint32_t cand_stride, Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
+            uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds,
+            uint32_t *__restrict__ env_spill, uint32_t env_stride, unsigned long long *__restrict__ next_read)
+{
+    __shared__ uint32_t env_s[ENV_SMEM][BACK_THREADS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + tid;
+    uint32_t *env_g = env_spill + gtid * env_stride;     // steps >= ENV_SMEM (rare)
+
+    bool finished = false, has_read = false, need_cand = true, first = true;
+    uint32_t r = 0;
+    int slot = -1, cur_x = -1, t = 0, t_head = 0, env_len = 0, x = 0, end = 0;
+    uint64_t woff = 0, ck = 0;
+    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0;
+    Cand *rc = nullptr;
+
+    for (;;) {
+        if (!finished && need_cand) {
+            for (;;) {
+                if (!has_read) {
+                    r = (uint32_t)atomicAdd(next_read, 1ull);
+                    if (r >= n_reads) { finished = true; break; }
+                    slot = (int)n_cand[r] - 1;
+                    cur_x = -1; acc_smems = 0; acc_seeds = 0;
+                    woff = word_off[r];
+                    rc = cand + (uint64_t)r * cand_stride;
+                    has_read = true;
+                }
+                if (slot < 0) { n_smems[r] = acc_smems; n_seeds[r] = acc_seeds; has_read = false; continue; }
+                Cand c = rc[slot];
+                ck = c.k; cs = c.s; x = c.x; end = c.end;
+                if (x != cur_x) { cur_x = x; first = true; t_head = 0; env_len = 0; }
+                t = 0;
+                need_cand = false;
+                break;
+            }
+        }
+        if (__all_sync(0xffffffffu, finished)) break;
+        if (!finished) {
+            const int i = x - 1 - t;
+            int b = 4;
+            if (i >= 0) b = read_base(packed, woff, i);
+            bool fail = true;
+            uint64_t nk = 0;
+            uint32_t ns = 0;
+            if (b < 4) {       // backward extension by b: only x[0], x[2] are needed downstream
+                uint64_t p0 = ck - 1, p1 = ck - 1 + cs;
+                uint64_t j0 = p0 - (p0 >= ix.primary), j1 = p1 - (p1 >= ix.primary);
+                Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
+                Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);
+                uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b);
+                uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b);
+                ns = ol - ok;
+                nk = L2_at(ix, b) + 1 + ok;
+                fail = ns == 0;
+            }
+            if (fail) {
+                // candidate stops after t steps: SMEM iff no longer match of this segment stopped here
+                Cand o; o.k = ck; o.s = 0; o.x = (uint16_t)(x - t); o.end = (uint16_t)end;
+                if (first || t > t_head) {
+                    if (end - (x - t) >= min_seed_len) { o.s = cs; ++acc_smems; acc_seeds += seeds_of(cs, max_occ); }
+                    t_head = t; env_len = t; first = false;
+                }
+                rc[slot] = o;
+                --slot; need_cand = true;
+            } else {
+                uint32_t prev = 0;
+                if (t < env_len) prev = t < ENV_SMEM ? env_s[t][tid] : env_g[t - ENV_SMEM];
+                if (t < env_len && prev == ns) {        // same interval as the longer match: contained
+                    Cand o; o.k = ck; o.s = 0; o.x = (uint16_t)x; o.end = (uint16_t)end;
+                    rc[slot] = o;
+                    --slot; need_cand = true;
+                } else {
+                    if (t < ENV_SMEM) env_s[t][tid] = ns; else env_g[t - ENV_SMEM] = ns;
+                    ck = nk; cs = ns; ++t;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ fill_kernel
+__global__ void __launch_bounds__(128)
+fill_kernel(uint32_t n_reads, int max_occ, uint32_t cand_stride, const Cand *__restrict__ cand,
+            const uint32_t *__restrict__ n_cand, const uint64_t *__restrict__ seed_off,
+            uint64_t *__restrict__ rbeg, int2 *__restrict__ qq, uint32_t *__restrict__ score, uint64_t cap)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const Cand *rc = cand + (uint64_t)r * cand_stride;
+    uint32_t n = n_cand[r];
+    uint64_t o = seed_off[r];
+    for (uint32_t j = 0; j < n; ++j) {
+        Cand c = rc[j];
+        if (c.s == 0) continue;
+        uint32_t step = (max_occ > 0 && c.s > (uint32_t)max_occ) ? c.s / (uint32_t)max_occ : 1u;
+        uint32_t cnt = seeds_of(c.s, max_occ);
+        for (uint32_t t = 0; t < cnt; ++t, ++o) {
+            if (o >= cap) return;
+            rbeg[o] = c.k + (uint64_t)t * step;
+            qq[o] = make_int2((int)c.x, (int)c.end);
+            score[o] = t == 0 ? c.s : 0u;
+        }
+    }
+}
+
+// SMEM-only dump used by tests: (qbeg, qend, k, s) per SMEM in read order
+__global__ void smem_dump_kernel(uint32_t n_reads, uint32_t cand_stride, const Cand *__restrict__ cand,
+                                 const uint32_t *__restrict__ n_cand, const uint64_t *__restrict__ smem_off,
+                                 int32_t *qbeg, int32_t *qend, uint64_t *k, uint64_t *s, uint64_t cap)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const Cand *rc = cand + (uint64_t)r * cand_stride;
+    uint64_t o = smem_off[r];
+    for (uint32_t j = 0; j < n_cand[r]; ++j) {
+        Cand c = rc[j];
+        if (c.s == 0) continue;
+        if (o < cap) { qbeg[o] = c.x; qend[o] = c.end; k[o] = c.k; s[o] = c.s; }
+        ++o;
+    }
+}
+
+// ---------------------------------------------------------------------------- locate_kernel
+__global__ void __launch_bounds__(LOC_THREADS)
+locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long long *__restrict__ total_p,
+              uint64_t cap, unsigned long long *__restrict__ next_seed)
+{
+    const uint64_t total = min((uint64_t)*total_p, cap);
+    const uint64_t mask = (1ull << ix.sa_shift) - 1;
+    bool finished = false, need = true;
+    uint64_t idx = 0, k = 0, steps = 0;
+    for (;;) {
+        if (!finished && need) {
+            idx = atomicAdd(next_seed, 1ull);
+            if (idx >= total) finished = true;
+            else { k = rbeg[idx]; steps = 0; need = false; }
+        }
+        if (__all_sync(0xffffffffu, finished)) break;
+        if (!finished) {
+            if ((k & mask) == 0) {
+                uint64_t j = k >> ix.sa_shift, pos;
+                if (j == 0) pos = steps - 1;                         // sa[0] == -1 (bwa_index/bwt.c:160-163)
+                else {
+                    uint64_t hi = 0;
+                    if (ix.pack_mask) {
+                        uint32_t per = 32u / ix.pack_size;
+                        hi = (ix.sa_hi[j / per] >> ((uint32_t)(j % per) * ix.pack_size)) & ix.pack_mask;
+                    }
+                    pos = steps + ((uint64_t)ix.sa[j] | hi << 32);
+                }
+                rbeg[idx] = pos;
+                need = true;
+            } else if (k == ix.primary) {                            // bwt_invPsi: row of '$'
+                k = 0; ++steps;
+            } else {
+                uint64_t j = k - (k > ix.primary);
+                Bkt b = ld_bucket(ix.bkt, j >> 6);
+                int off = (int)(j & 63);
+                int sym = (int)((b.w[off >> 4] >> ((~off & 15) << 1)) & 3u);
+                k = L2_at(ix, sym) + bucket_occ1(b, off + 1, sym);
+                ++steps;
+            }
+        }
+    }
+}
+
+__global__ void total_kernel(const uint32_t *n_per, const uint64_t *off, uint32_t n, unsigned long long *total)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = n ? off[n - 1] + n_per[n - 1] : 0ull;
+}
+
+struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
+
+} // namespace
+
+// =============================================================================== host side
+struct bwa_b200_seeder {
+    const bwa_b200_index *idx = nullptr;
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t max_reads = 0, max_words = 0;
+    uint32_t max_read_len = 0, cand_stride = 0, env_stride = 0;
+    // inputs (host API)
+    uint32_t *d_packed = nullptr, *d_len = nullptr;
+    uint64_t *d_woff = nullptr;
+    // workspace
+    Cand *d_cand = nullptr;
+    uint64_t cand_cap = 0;
+    uint32_t *d_ncand = nullptr, *d_nsmems = nullptr, *d_nseeds = nullptr, *d_env = nullptr;
+    uint64_t *d_seed_off = nullptr, *d_smem_off = nullptr;
+    unsigned long long *d_counters = nullptr;     // [0] next_read, [1] next_seed, [2] total seeds, [3] total smems
+    void *d_cub = nullptr;
+    size_t cub_bytes = 0;
+    // outputs
+    uint64_t *d_rbeg = nullptr;
+    int2 *d_qq = nullptr;
+    uint32_t *d_score = nullptr;
+    uint64_t seed_cap = 0;
+    uint64_t last_n_reads = 0, last_total = 0;
+    int back_grid = 0, loc_grid = 0;
+    uint64_t launches = 0;
+    bwa_b200_seed_params_t last_p{19, 500};
+    // pinned staging for the scalar read-backs
+    unsigned long long *h_counters = nullptr;
+};
+
+static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, int min_seed_len)
+{
+    uint32_t stride = max_len >= (uint32_t)min_seed_len ? max_len - (uint32_t)min_seed_len + 2 : 2;
+    uint64_t need = n_reads * (uint64_t)stride;
+    if (need > s->cand_cap) {
+        if (s->d_cand) B200_CUDA(cudaFree(s->d_cand));
+        s->d_cand = nullptr;
+        B200_CUDA(cudaMalloc(&s->d_cand, need * sizeof(Cand)));
+        s->cand_cap = need;
+    }
+    s->cand_stride = stride;
+    uint32_t env_stride = max_len > ENV_SMEM ? max_len - ENV_SMEM : 1;
+    if (env_stride > s->env_stride) {
+        if (s->d_env) B200_CUDA(cudaFree(s->d_env));
+        s->d_env = nullptr;
+        B200_CUDA(cudaMalloc(&s->d_env, (uint64_t)s->back_grid * BACK_THREADS * env_stride * 4));
+        s->env_stride = env_stride;
+    }
+    return BWA_B200_OK;
+}
+
+static int seeder_ensure_out(bwa_b200_seeder *s, uint64_t n_seeds)
+{
+    if (n_seeds <= s->seed_cap) return BWA_B200_OK;
+    uint64_t cap = n_seeds + n_seeds / 8 + 1024;
+    if (s->d_rbeg) { cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score); }
+    s->d_rbeg = nullptr; s->d_qq = nullptr; s->d_score = nullptr; s->seed_cap = 0;
+    B200_CUDA(cudaMalloc(&s->d_rbeg, cap * 8));
+    B200_CUDA(cudaMalloc(&s->d_qq, cap * 8));
+    B200_CUDA(cudaMalloc(&s->d_score, cap * 4));
+    s->seed_cap = cap;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_reads, uint64_t max_words,
+                                      bwa_b200_seeder_t **out)
+{
+    if (!idx || !out || max_reads == 0) { b200::set_error("seeder_create: bad argument"); return BWA_B200_ERR_ARG; }
+    if (max_reads >= 0xffffffffull) { b200::set_error("seeder_create: at most 2^32-2 reads per batch"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(idx->device));
+    bwa_b200_seeder *s = new bwa_b200_seeder();
+    s->idx = idx; s->device = idx->device;
+    s->max_reads = max_reads; s->max_words = max_words;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, idx->device));
+    s->n_sm = prop.multiProcessorCount;
+    int occ_b = 0, occ_l = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_kernel, BACK_THREADS, 0));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel, LOC_THREADS, 0));
+    s->back_grid = s->n_sm * (occ_b > 0 ? occ_b : 1);
+    s->loc_grid = s->n_sm * (occ_l > 0 ? occ_l : 1);
+    B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&s->d_packed, (max_words ? max_words : 1) * 4));
+    B200_CUDA(cudaMalloc(&s->d_len, max_reads * 4));
+    B200_CUDA(cudaMalloc(&s->d_woff, (max_reads + 1) * 8));
+    B200_CUDA(cudaMalloc(&s->d_ncand, max_reads * 4));
+    B200_CUDA(cudaMalloc(&s->d_nsmems, max_reads * 4));
+    B200_CUDA(cudaMalloc(&s->d_nseeds, max_reads * 4));
+    B200_CUDA(cudaMalloc(&s->d_seed_off, max_reads * 8));
+    B200_CUDA(cudaMalloc(&s->d_smem_off, max_reads * 8));
+    B200_CUDA(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
+    B200_CUDA(cudaHostAlloc(&s->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, it, s->d_seed_off, (int)max_reads, s->stream));
+    B200_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes + 16));
+    *out = s;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_packed); cudaFree(s->d_len); cudaFree(s->d_woff); cudaFree(s->d_cand); cudaFree(s->d_ncand);
+    cudaFree(s->d_nsmems); cudaFree(s->d_nseeds); cudaFree(s->d_env); cudaFree(s->d_seed_off); cudaFree(s->d_smem_off);
+    cudaFree(s->d_counters); cudaFree(s->d_cub); cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score);
+    cudaFreeHost(s->h_counters);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" void *bwa_b200_seeder_stream(bwa_b200_seeder_t *s) { return s ? (void *)s->stream : nullptr; }
+extern "C" uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s) { return s ? s->launches : 0; }
+
+// enqueue fwd -> back -> scan -> (total) ; then fill + locate once the output capacity is known
+static int seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t *d_woff, const uint32_t *d_len,
+                      uint64_t n_reads, uint32_t max_len, const bwa_b200_seed_params_t *p)
+{
+    if (n_reads > s->max_reads) { b200::set_error("seed: %llu reads > capacity %llu", (unsigned long long)n_reads, (unsigned long long)s->max_reads); return BWA_B200_ERR_CAPACITY; }
+    if (max_len > 65535) { b200::set_error("seed: reads longer than 65535 bases are not supported"); return BWA_B200_ERR_ARG; }
+    if (p->min_seed_len < 1) { b200::set_error("seed: min_seed_len < 1"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(s->device));
+    s->last_n_reads = n_reads; s->last_total = 0; s->last_p = *p;
+    if (n_reads == 0) return BWA_B200_OK;
+    int rc = seeder_ensure_cand(s, n_reads, max_len, p->min_seed_len);
+    if (rc) return rc;
+    const IndexView &ix = s->idx->v;
+    const uint32_t n = (uint32_t)n_reads;
+    B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    fwd_kernel<<<(n + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, s->stream>>>(
+        ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand);
+    back_kernel<<<s->back_grid, BACK_THREADS, 0, s->stream>>>(
+        ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride, s->d_cand, s->d_ncand,
+        s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0);
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
+    size_t tmp = s->cub_bytes;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_seed_off, (int)n, s->stream));
+    total_kernel<<<1, 1, 0, s->stream>>>(s->d_nseeds, s->d_seed_off, n, s->d_counters + 2);
+    s->launches += 4;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+static int seeder_finish(bwa_b200_seeder *s, bool need_total_on_host)
+{
+    if (s->last_n_reads == 0) return BWA_B200_OK;
+    const IndexView &ix = s->idx->v;
+    const uint32_t n = (uint32_t)s->last_n_reads;
+    // the seed total sizes the output arrays: one 8-byte read-back
+    B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    s->last_total = s->h_counters[2];
+    int rc = seeder_ensure_out(s, s->last_total);
+    if (rc) return rc;
+    if (s->last_total) {
+        if (!ix.sa) { b200::set_error("seed: index has no suffix array samples"); return BWA_B200_ERR_ARG; }
+        fill_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
+                                                             s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap);
+        locate_kernel<<<s->loc_grid, LOC_THREADS, 0, s->stream>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1);
+        s->launches += 2;
+        B200_CUDA(cudaGetLastError());
+    }
+    (void)need_total_on_host;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_seed_device(bwa_b200_seeder_t *s, const uint32_t *dev_packed, const uint64_t *dev_word_off,
+                                    const uint32_t *dev_read_len, uint64_t n_reads, const bwa_b200_seed_params_t *p)
+{
+    if (!s || !p || (n_reads && (!dev_packed || !dev_word_off || !dev_read_len))) { b200::set_error("seed_device: bad argument"); return BWA_B200_ERR_ARG; }
+    // the longest read bounds the candidate stride; reduce it on device
+    uint32_t max_len = 0;
+    if (n_reads) {
+        B200_CUDA(cudaSetDevice(s->device));
+        size_t tmp = 0;
+        uint32_t *d_max = (uint32_t *)(s->d_counters + 3);
+        B200_CUDA(cub::DeviceReduce::Max(nullptr, tmp, dev_read_len, d_max, (int)n_reads, s->stream));
+        if (tmp > s->cub_bytes) { cudaFree(s->d_cub); s->d_cub = nullptr; B200_CUDA(cudaMalloc(&s->d_cub, tmp + 16)); s->cub_bytes = tmp; }
+        B200_CUDA(cub::DeviceReduce::Max(s->d_cub, tmp, dev_read_len, d_max, (int)n_reads, s->stream));
+        B200_CUDA(cudaMemcpyAsync(s->h_counters + 3, d_max, 4, cudaMemcpyDeviceToHost, s->stream));
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+        max_len = *(uint32_t *)(s->h_counters + 3);
+        s->launches += 1;
+    }
+    int rc = seeder_run(s, dev_packed, dev_word_off, dev_read_len, n_reads, max_len, p);
+    if (rc) return rc;
+    return seeder_finish(s, false);
+}
+
+extern "C" int bwa_b200_seed_device_result(bwa_b200_seeder_t *s, bwa_b200_seeds_t *v)
+{
+    if (!s || !v) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    v->n_reads = s->last_n_reads; v->n_seeds = s->last_total;
+    v->rbeg = s->d_rbeg; v->qbeg_qend = (int32_t *)s->d_qq; v->score = s->d_score;
+    v->n_seeds_per_read = s->d_nseeds; v->seed_off = s->d_seed_off;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_seed_host(bwa_b200_seeder_t *s, const uint32_t *packed, const uint64_t *word_off,
+                                  const uint32_t *read_len, uint64_t n_reads, const bwa_b200_seed_params_t *p,
+                                  bwa_b200_seeds_t *out)
+{
+    if (!s || !p || !out || (n_reads && (!packed || !word_off || !read_len))) { b200::set_error("seed_host: bad argument"); return BWA_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    out->n_reads = n_reads;
+    if (n_reads > s->max_reads) { b200::set_error("seed_host: %llu reads > capacity %llu", (unsigned long long)n_reads, (unsigned long long)s->max_reads); return BWA_B200_ERR_CAPACITY; }
+    uint64_t n_words = n_reads ? word_off[n_reads] : 0;
+    if (n_words > s->max_words) { b200::set_error("seed_host: %llu words > capacity %llu", (unsigned long long)n_words, (unsigned long long)s->max_words); return BWA_B200_ERR_CAPACITY; }
+    B200_CUDA(cudaSetDevice(s->device));
+    uint32_t max_len = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) max_len = read_len[r] > max_len ? read_len[r] : max_len;
+    if (n_reads) {
+        B200_CUDA(cudaMemcpyAsync(s->d_packed, packed, n_words * 4, cudaMemcpyHostToDevice, s->stream));
+        B200_CUDA(cudaMemcpyAsync(s->d_woff, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        B200_CUDA(cudaMemcpyAsync(s->d_len, read_len, n_reads * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    int rc = seeder_run(s, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, p);
+    if (rc) return rc;
+    rc = seeder_finish(s, true);
+    if (rc) return rc;
+    const uint64_t tot = s->last_total;
+    out->n_seeds = tot;
+    out->rbeg = (uint64_t *)malloc((tot ? tot : 1) * 8);
+    out->qbeg_qend = (int32_t *)malloc((tot ? tot : 1) * 8);
+    out->score = (uint32_t *)malloc((tot ? tot : 1) * 4);
+    out->n_seeds_per_read = (uint32_t *)malloc((n_reads ? n_reads : 1) * 4);
+    out->seed_off = (uint64_t *)malloc((n_reads ? n_reads : 1) * 8);
+    if (!out->rbeg || !out->qbeg_qend || !out->score || !out->n_seeds_per_read || !out->seed_off) { bwa_b200_seeds_free(out); b200::set_error("seed_host: out of host memory"); return BWA_B200_ERR_NOMEM; }
+    if (n_reads) {
+        if (tot) {
+            B200_CUDA(cudaMemcpyAsync(out->rbeg, s->d_rbeg, tot * 8, cudaMemcpyDeviceToHost, s->stream));
+            B200_CUDA(cudaMemcpyAsync(out->qbeg_qend, s->d_qq, tot * 8, cudaMemcpyDeviceToHost, s->stream));
+            B200_CUDA(cudaMemcpyAsync(out->score, s->d_score, tot * 4, cudaMemcpyDeviceToHost, s->stream));
+        }
+        B200_CUDA(cudaMemcpyAsync(out->n_seeds_per_read, s->d_nseeds, n_reads * 4, cudaMemcpyDeviceToHost, s->stream));
+        B200_CUDA(cudaMemcpyAsync(out->seed_off, s->d_seed_off, n_reads * 8, cudaMemcpyDeviceToHost, s->stream));
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_seeds_free(bwa_b200_seeds_t *r)
+{
+    if (!r) return;
+    free(r->rbeg); free(r->qbeg_qend); free(r->score); free(r->n_seeds_per_read); free(r->seed_off);
+    memset(r, 0, sizeof(*r));
+}
+
+extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads, uint32_t *host_n_smems,
+                                          int32_t *host_qbeg, int32_t *host_qend, uint64_t *host_k, uint64_t *host_s,
+                                          uint64_t cap, uint64_t *total)
+{
+    if (!s || n_reads != s->last_n_reads) { b200::set_error("seed_device_smems: no matching batch"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(s->device));
+    if (n_reads == 0) { if (total) *total = 0; return BWA_B200_OK; }
+    const uint32_t n = (uint32_t)n_reads;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nsmems, U32ToU64());
+    size_t tmp = s->cub_bytes;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_smem_off, (int)n, s->stream));
+    total_kernel<<<1, 1, 0, s->stream>>>(s->d_nsmems, s->d_smem_off, n, s->d_counters + 3);
+    B200_CUDA(cudaMemcpyAsync(s->h_counters + 3, s->d_counters + 3, 8, cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    uint64_t tot = s->h_counters[3];
+    if (total) *total = tot;
+    B200_CUDA(cudaMemcpy(host_n_smems, s->d_nsmems, n_reads * 4, cudaMemcpyDeviceToHost));
+    if (tot == 0) return BWA_B200_OK;
+    if (tot > cap) { b200::set_error("seed_device_smems: %llu SMEMs > cap", (unsigned long long)tot); return BWA_B200_ERR_CAPACITY; }
+    int32_t *d_qb, *d_qe; uint64_t *d_k, *d_s;
+    B200_CUDA(cudaMalloc(&d_qb, tot * 4)); B200_CUDA(cudaMalloc(&d_qe, tot * 4));
+    B200_CUDA(cudaMalloc(&d_k, tot * 8)); B200_CUDA(cudaMalloc(&d_s, tot * 8));
+    smem_dump_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, s->cand_stride, s->d_cand, s->d_ncand, s->d_smem_off, d_qb, d_qe, d_k, d_s, tot);
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    B200_CUDA(cudaMemcpy(host_qbeg, d_qb, tot * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(host_qend, d_qe, tot * 4, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(host_k, d_k, tot * 8, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(host_s, d_s, tot * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_qb); cudaFree(d_qe); cudaFree(d_k); cudaFree(d_s);
+    return BWA_B200_OK;
+}

@@ -1,0 +1,202 @@
+/*
+ * bwamem_b200.h -- C ABI of the B200-native BWA-MEM hot paths (libbwamem_b200.so).
+ *
+ * Two data-parallel paths, each a drop-in for one library boundary of the reference's
+ * `gase_aln` driver (sflorescu/BWA-MEM_GPU):
+ *
+ *   1. SMEM seeding over the FMD index      replaces GPUSeed   (src/GPUSeed/seed_gen.h:92-106)
+ *   2. ksw_extend2-equivalent seed extension replaces GASAL2 KSW (GASAL2/src/gasal_align.h:96-102,
+ *                                            ctors.h:5-15, host_batch.h:13, interfaces.h:9)
+ *
+ * Everything here is plain C: pointers, sizes, opaque handles.  The source-compatible
+ * wrappers that carry the reference's own names (seed_gpu(), gasal_aln_async(), ...) live in
+ * include/compat/ and forward to these entry points.
+ *
+ * Results are bit-exact with the reference's CPU functions bwt_smem1 / bwt_sa
+ * (src/bwt.c:483-566, bwa_index/bwt.c:151-172) and ksw_extend2 (src/ksw.c:864-986).
+ * There is no CPU fallback: every compute entry point returns BWA_B200_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Conventions: all functions return 0 on success or a negative BWA_B200_ERR_* code;
+ * bwa_b200_last_error() returns a thread-local message.  "dev" pointers are device
+ * pointers on the handle's device; "host" pointers should be pinned for full PCIe speed
+ * (bwa_b200_host_alloc) but pageable memory works.
+ */
+#ifndef BWAMEM_B200_H
+#define BWAMEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BWA_B200_OK             0
+#define BWA_B200_ERR_ARG       -1
+#define BWA_B200_ERR_IO        -2
+#define BWA_B200_ERR_FORMAT    -3
+#define BWA_B200_ERR_CUDA      -4
+#define BWA_B200_ERR_NOMEM     -5
+#define BWA_B200_ERR_CAPACITY  -6
+
+const char *bwa_b200_last_error(void);
+int  bwa_b200_version(void);
+
+/* ------------------------------------------------------------------ runtime */
+int  bwa_b200_device_count(void);
+/* pinned host memory helpers (replace cudaMallocHost / cudaHostAlloc in the callers,
+ * seed_gen.cu:1670-1672, GASAL2/src/host_batch.cpp:17) */
+void *bwa_b200_host_alloc(size_t bytes);
+void  bwa_b200_host_free(void *p);
+
+/* -------------------------------------------------------------------- index */
+/* FMD index in the reference's GPU file layout: .bwt = u64 primary, u64 L2[1..4], then one
+ * 32-byte bucket per 64 BWT symbols {u32 cnt[A,C,G,T]; u32 sym[4]} (bwa_index/bwtindex.c:174-197);
+ * .sa = sampled suffix array, u32 + packed high bits (bwa_index/bwt.c:472-487). */
+typedef struct bwa_b200_index bwa_b200_index_t;
+
+typedef struct {
+    uint64_t primary, seq_len, L2[5];
+    uint64_t n_buckets;        /* 32-byte occurrence buckets resident in HBM */
+    uint64_t n_sa;
+    int32_t  sa_intv, pack_size;
+    int32_t  device;
+    uint64_t hbm_bytes;        /* total device bytes held by this index */
+} bwa_b200_index_info_t;
+
+/* replaces bwt_restore_bwt_gpu + bwt_restore_sa_gpu + gpu_cpy_wrapper
+ * (seed_gen.cu:1386-1468,1524-1556; called from src/fastmap.c:446-453) */
+int  bwa_b200_index_load(const char *bwt_path, const char *sa_path, int device, bwa_b200_index_t **out);
+/* same from host arrays (bwt_words = file payload after the 40-byte header; sa has n_sa entries) */
+int  bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], const uint32_t *bwt_words, uint64_t n_words,
+                              const uint32_t *sa, const uint32_t *sa_hi, uint64_t n_sa, int sa_intv, int pack_size,
+                              int device, bwa_b200_index_t **out);
+/* replicate a resident index onto another device with a peer copy over NVLink */
+int  bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, bwa_b200_index_t **out);
+int  bwa_b200_index_info(const bwa_b200_index_t *idx, bwa_b200_index_info_t *info);
+void bwa_b200_index_free(bwa_b200_index_t *idx);          /* replaces free_gpuseed_data */
+
+/* Host-side index construction in the reference's on-disk format (bwa_index/bwtindex.c:287-358,
+ * build_index.sh): writes <prefix>.bwt (32-bit occ, 64-symbol buckets) and <prefix>.sa; with
+ * also_stock_layout != 0 additionally <prefix>.bwt128 (stock 64-bit occ, 128-symbol buckets) so
+ * the unmodified CPU bwa can be timed on the same index.  fwd = forward strand, codes 0..3.
+ * Output is byte-identical to the reference's `bwa index -s sa -r R` + `bwa index -s bwt`. */
+int  bwa_b200_build_index(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *prefix,
+                          int also_stock_layout, int n_threads);
+
+/* ---------------------------------------------------------------- read batch */
+/* 4-bit packing used on the wire and in HBM: 8 bases per u32, base 0 in bits 31..28, codes
+ * A0 C1 G2 T3 N4 (as pack_4bit_fow, seed_gen.cu:1088-1108); every read starts on a word
+ * boundary.  word_off has n_reads+1 entries. */
+size_t bwa_b200_packed_words(const uint32_t *read_len, uint64_t n_reads);
+int  bwa_b200_pack_ascii(const char *bases, const uint64_t *base_off, uint64_t n_reads,
+                         uint32_t *packed, uint64_t *word_off, uint32_t *read_len, int n_threads);
+int  bwa_b200_pack_codes(const uint8_t *codes, const uint64_t *base_off, uint64_t n_reads,
+                         uint32_t *packed, uint64_t *word_off, uint32_t *read_len, int n_threads);
+
+/* ------------------------------------------------------------------- seeding */
+typedef struct bwa_b200_seeder bwa_b200_seeder_t;
+
+typedef struct {
+    int32_t min_seed_len;      /* opt->min_seed_len, default 19                              */
+    int32_t max_occ;           /* > 0: locate only the rows mem_chain reads (bwa_index/bwamem.c:278-283):
+                                  count = min(s, max_occ) rows k + t*step, step = s > max_occ ? s/max_occ : 1.
+                                  <= 0: locate all s rows of every SMEM (reference GPU layout,
+                                  seed_gen.cu:520-545)                                       */
+} bwa_b200_seed_params_t;
+
+/* flat result, layout of mem_seed_v_gpu (seed_gen.h:68-75): seeds of read r are
+ * [seed_off[r], seed_off[r] + n_seeds[r]), ordered by SMEM (ascending query start) then SA row;
+ * score = occurrence count s of the SMEM on the first seed of each SMEM group, 0 on the others. */
+typedef struct {
+    uint64_t  n_reads, n_seeds;
+    uint64_t *rbeg;            /* reference position in [0, 2*l_pac)          */
+    int32_t  *qbeg_qend;       /* pairs {qbeg, qend}  (int2 in the reference) */
+    uint32_t *score;
+    uint32_t *n_seeds_per_read;
+    uint64_t *seed_off;        /* exclusive prefix sum                        */
+} bwa_b200_seeds_t;
+
+int  bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_reads, uint64_t max_words,
+                            bwa_b200_seeder_t **out);
+void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s);
+
+/* host in, host out: H2D of the packed batch, kernels, D2H of the seeds.  The arrays of `out`
+ * are allocated with malloc() (the reference's caller frees them with free(), src/fastmap.c:537-542). */
+int  bwa_b200_seed_host(bwa_b200_seeder_t *s, const uint32_t *packed, const uint64_t *word_off,
+                        const uint32_t *read_len, uint64_t n_reads, const bwa_b200_seed_params_t *p,
+                        bwa_b200_seeds_t *out);
+void bwa_b200_seeds_free(bwa_b200_seeds_t *r);
+
+/* device in, device out (inputs already resident): enqueues on the seeder's stream.  The result
+ * stays in the seeder's workspace until the next call; bwa_b200_seed_device_result synchronises
+ * and reports the device pointers. */
+int  bwa_b200_seed_device(bwa_b200_seeder_t *s, const uint32_t *dev_packed, const uint64_t *dev_word_off,
+                          const uint32_t *dev_read_len, uint64_t n_reads, const bwa_b200_seed_params_t *p);
+int  bwa_b200_seed_device_result(bwa_b200_seeder_t *s, bwa_b200_seeds_t *dev_view);
+void *bwa_b200_seeder_stream(bwa_b200_seeder_t *s);       /* cudaStream_t */
+/* per-phase launch counters and SMEM-only view for tests: qbeg,qend,k,s per SMEM in read order */
+int  bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads, uint32_t *host_n_smems,
+                                int32_t *host_qbeg, int32_t *host_qend, uint64_t *host_k, uint64_t *host_s,
+                                uint64_t cap, uint64_t *total);
+uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s);
+
+/* ----------------------------------------------------------------- extension */
+typedef struct bwa_b200_extender bwa_b200_extender_t;
+
+/* the arguments of ksw_extend2 that are constant over a batch (src/ksw.c:864-866) plus the
+ * clip penalty of the local-vs-to-end rule (src/bwamem.c:1892-1901).  The reference boundary
+ * cannot express w/zdrop/end_bonus/o_ins/e_ins; this struct is how they arrive. */
+typedef struct {
+    int8_t  mat[25];           /* 5x5 substitution matrix, row = target base (bwa_fill_scmat) */
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t w;                 /* band width                                                 */
+    int32_t end_bonus;
+    int32_t zdrop;
+    int32_t use_band;          /* opt_ext of the fork's ksw_extend2 (src/ksw.c:902-907)       */
+    int32_t pen_clip;          /* for the (score,qend,tend) triple                            */
+} bwa_b200_ext_params_t;
+
+void bwa_b200_ext_params_default(bwa_b200_ext_params_t *p);   /* a=1 b=4 o=6 e=1 w=100 zdrop=100 clip=5 */
+void bwa_b200_fill_scmat(int a, int b, int8_t mat[25]);
+
+typedef struct {               /* all six outputs of ksw_extend2 */
+    int32_t score, qle, tle, gtle, gscore, max_off;
+} bwa_b200_ext_result_t;
+
+int  bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t max_query_bytes, uint64_t max_target_bytes,
+                              bwa_b200_extender_t **out);
+void bwa_b200_extender_destroy(bwa_b200_extender_t *e);
+
+/* Job batch in the GASAL host layout (GASAL2/src/host_batch.cpp:79-153, src/bwamem.c:1102-1167):
+ * one byte per base, codes 0..4, job a = qseq[qoff[a] .. qoff[a]+qlen[a]) vs tseq[toff[a] ..);
+ * h0[a] = host_seed_scores[a].  Asynchronous: returns after enqueueing H2D, kernels and D2H on the
+ * extender's stream (gasal_aln_async).  res6 / triple may be NULL.  triple receives
+ * {aln_score, query_batch_end, target_batch_end} per job after the local-vs-to-end rule. */
+int  bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                           const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                           const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                           const uint32_t *h0, bwa_b200_ext_result_t *res6,
+                           int32_t *aln_score, int32_t *query_end, int32_t *target_end);
+/* 0 = done, 1 = still running (gasal_is_aln_async_done returns 0 / -1) */
+int  bwa_b200_extend_query(bwa_b200_extender_t *e);
+int  bwa_b200_extend_wait(bwa_b200_extender_t *e);
+
+/* device-resident variant: sequences already packed 4-bit in HBM (8 bases per u32, first base in
+ * the high nibble, each sequence starting on a word boundary; offsets in bases, multiples of 8). */
+int  bwa_b200_extend_device(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                            const uint32_t *dev_qpacked, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
+                            const uint32_t *dev_tpacked, const uint32_t *dev_toff, const uint32_t *dev_tlen,
+                            const uint32_t *dev_h0, bwa_b200_ext_result_t *dev_res6);
+/* pack a byte-per-base device buffer into the 4-bit layout (gasal_pack_kernel equivalent) */
+int  bwa_b200_pack_device(bwa_b200_extender_t *e, const uint8_t *dev_bytes, uint64_t n_bytes, uint32_t *dev_packed);
+void *bwa_b200_extender_stream(bwa_b200_extender_t *e);
+uint64_t bwa_b200_extender_launches(const bwa_b200_extender_t *e);
+/* cells evaluated by the last batch (sum over rows of end-beg), counted on device */
+uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWAMEM_B200_H */

@@ -1,0 +1,228 @@
+"""GPU parity tests: the CUDA hot paths, called through the C ABI, against the CPU oracle and the
+golden vectors made from the reference's own CPU functions.  Bit-exact: every comparison is ==."""
+import os
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def flat(reads_list):
+    lens = np.array([len(r) for r in reads_list], np.uint64)
+    off = np.zeros(len(reads_list) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    return (np.concatenate(reads_list).astype(np.uint8) if reads_list else np.zeros(0, np.uint8)), off
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    assert pkg.lib().bwa_b200_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def dev_index(gpu, small_index, oracle):
+    g, prefix = small_index
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    yield g, idx, oi
+    idx.free()
+    oi.close()
+
+
+def seed_compare(gpu, idx, oi, reads_flat, off, min_seed_len, max_occ):
+    packed, woff, rl = gpu.pack_codes(reads_flat, off)
+    n = rl.size
+    sd = gpu.Seeder(idx, max(n, 1), max(packed.size, 1))
+    got = sd.seed_host(packed, woff, rl, min_seed_len, max_occ)
+    want = oi.seed_batch(reads_flat, off, min_seed_len, max_occ if max_occ > 0 else 0, n_threads=4)
+    sm = sd.smems(n, max(1024, int(reads_flat.size)))
+    wsm = oi.smem_batch(reads_flat, off, min_seed_len)
+    sd.destroy()
+    assert (sm["n_smems"] == wsm["n_smems"]).all()
+    for key in ("qbeg", "qend", "k", "s"):
+        assert (sm[key] == wsm[key]).all(), key
+    assert got["total"] == want["total"]
+    assert (got["n_seeds"] == want["n_seeds"]).all()
+    assert (got["seed_off"] == want["seed_off"]).all()
+    assert (got["qq"][:, 0] == want["qbeg"]).all() and (got["qq"][:, 1] == want["qend"]).all()
+    assert (got["score"] == want["score"]).all()
+    assert (got["rbeg"] == want["rbeg"]).all()
+    return got, want
+
+
+def test_index_info(dev_index):
+    g, idx, oi = dev_index
+    info = idx.info()
+    assert info.seq_len == 2 * g.size == oi.seq_len
+    assert info.sa_intv == 16 and info.n_buckets == (info.seq_len + 63) // 64
+
+
+@pytest.mark.parametrize("max_occ", [500, 7, 0])
+def test_seeding_matches_oracle(gpu, dev_index, max_occ):
+    g, idx, oi = dev_index
+    reads, _, _ = synth.make_reads(g, 3000, 150, seed=5, n_rate=0.002)
+    got, want = seed_compare(gpu, idx, oi, reads.reshape(-1).copy(), (np.arange(3001) * 150).astype(np.uint64), 19, max_occ)
+    assert got["total"] > 3000
+
+
+def test_seeding_ragged_and_edge_reads(gpu, dev_index):
+    g, idx, oi = dev_index
+    rng = np.random.default_rng(3)
+    rl = []
+    base, _, _ = synth.make_reads(g, 400, 250, seed=9, sub_rate=0.02, n_rate=0.003)
+    for i in range(400):
+        rl.append(base[i, :int(rng.integers(1, 251))])
+    rl.append(np.full(40, 4, np.uint8))                       # all N
+    rl.append(np.zeros(5, np.uint8))                          # shorter than a seed
+    rl.append(np.zeros(300, np.uint8))                        # poly-A, not in the genome as a whole
+    rl.append(np.array([1], np.uint8))                        # single base
+    rl.append(g[1000:1019].copy())                            # exactly min_seed_len
+    rl.append(g[5000:5600].copy())                            # long exact read
+    rl.append(synth.revcomp(g[7000:7400].copy()))
+    f, off = flat(rl)
+    seed_compare(gpu, idx, oi, f, off, 19, 500)
+    seed_compare(gpu, idx, oi, f, off, 10, 3)
+    seed_compare(gpu, idx, oi, f, off, 30, 500)
+
+
+def test_seeding_empty_batch(gpu, dev_index):
+    _, idx, _ = dev_index
+    sd = gpu.Seeder(idx, 16, 16)
+    got = sd.seed_host(np.zeros(1, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+    assert got["total"] == 0 and got["n_seeds"].size == 0
+    sd.destroy()
+
+
+def test_seeding_golden_from_reference(gpu, tmp_path):
+    """CUDA path against SMEMs/seeds produced by the reference's bwt_smem1 / bwt_sa (make_golden.py)"""
+    gold = np.load(os.path.join(GOLD, "seed_golden.npz"))
+    g = synth.make_repeat_genome(int(gold["genome_len"]), seed=int(gold["genome_seed"]))
+    prefix = str(tmp_path / "g")
+    gpu.build_index(g, prefix, sa_intv=int(gold["sa_intv"]), n_threads=4)
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    reads = gold["reads"]
+    n, L = reads.shape
+    off = (np.arange(n + 1) * L).astype(np.uint64)
+    packed, woff, rl = gpu.pack_codes(reads.reshape(-1).copy(), off)
+    sd = gpu.Seeder(idx, n, packed.size)
+    got = sd.seed_host(packed, woff, rl, 19, int(gold["max_occ"]))
+    sm = sd.smems(n, 1 << 16)
+    assert (sm["n_smems"] == gold["n_smems"]).all()
+    for key in ("qbeg", "qend", "k", "s"):
+        assert (sm[key] == gold[key]).all(), key
+    assert (got["n_seeds"] == gold["n_seeds"]).all()
+    assert (got["rbeg"] == gold["rbeg"]).all()
+    assert (got["score"] == gold["score"]).all()
+    sd.destroy()
+    idx.free()
+
+
+def test_seeding_device_api_and_seed_text_property(gpu, dev_index):
+    """device-resident entry point; every located seed must spell the read substring on fwd+revcomp"""
+    import torch
+    g, idx, oi = dev_index
+    reads, _, _ = synth.make_reads(g, 20000, 150, seed=77)
+    f = reads.reshape(-1).copy()
+    off = (np.arange(20001) * 150).astype(np.uint64)
+    packed, woff, rl = gpu.pack_codes(f, off)
+    d_packed = torch.from_numpy(packed.view(np.int32)).cuda()
+    d_woff = torch.from_numpy(woff.view(np.int64)).cuda()
+    d_rl = torch.from_numpy(rl.view(np.int32)).cuda()
+    sd = gpu.Seeder(idx, 20000, packed.size)
+    sd.seed_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), 20000, 19, 500)
+    v = sd.device_result()
+    tot = int(v.n_seeds)
+    assert tot > 20000
+    import ctypes as C
+
+    class DevArr:      # wrap a raw device pointer for torch through the CUDA array interface
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(C.cast(ptr, C.c_void_p).value, False), version=2)
+
+    rbeg = torch.as_tensor(DevArr(v.rbeg, tot, "<i8"), device="cuda")
+    qq = torch.as_tensor(DevArr(v.qbeg_qend, tot * 2, "<i4"), device="cuda")
+    nper = torch.as_tensor(DevArr(v.n_seeds_per_read, 20000, "<i4"), device="cuda")
+    rbeg = rbeg.cpu().numpy().astype(np.uint64)
+    qq = qq.cpu().numpy().reshape(-1, 2)
+    nper = nper.cpu().numpy().astype(np.uint32)
+    want = oi.seed_batch(f, off, 19, 500, n_threads=4)
+    assert (nper == want["n_seeds"]).all() and (rbeg == want["rbeg"]).all()
+    T = np.concatenate([g, synth.revcomp(g)])
+    rid = np.repeat(np.arange(20000), nper)
+    for j in np.random.default_rng(0).integers(0, tot, 2000):
+        b, e = qq[j]
+        assert (T[int(rbeg[j]):int(rbeg[j]) + (e - b)] == reads[rid[j], b:e]).all()
+    sd.destroy()
+
+
+# ------------------------------------------------------------------------------- extension
+
+@pytest.mark.parametrize("name", ["ksw_band", "ksw_noband", "ksw_narrow", "ksw_asym"])
+def test_extension_golden_from_reference(gpu, oracle, name):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    jobs = {k: np.ascontiguousarray(gold[k]) for k in ("qseq", "tseq", "qoff", "toff", "qlen", "tlen", "h0")}
+    kw = {k: int(v) for k, v in zip(gold["param_names"], gold["param_values"])}
+    ex = gpu.Extender(0)
+    res, tri = ex.extend_host(jobs, gpu.ext_params(**kw))
+    assert (res == gold["res6"]).all()
+    sc, qe, te = oracle.gasal_triple(gold["res6"], jobs["qlen"], kw.get("pen_clip", 5))
+    assert (tri[0] == sc).all() and (tri[1] == qe).all() and (tri[2] == te).all()
+    ex.destroy()
+
+
+@pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=16, zdrop=100), dict(w=300, zdrop=0, use_band=0),
+                                dict(w=5, zdrop=20), dict(w=50, zdrop=100, o_del=4, e_del=2, o_ins=7, e_ins=1, a=2, b=3, end_bonus=0)])
+def test_extension_matches_oracle(gpu, oracle, kw):
+    ex = gpu.Extender(0)
+    for seed, extra in ((31, dict(qlen_range=(1, 300), h0_range=(1, 200))),
+                        (32, dict(qlen_range=(1, 90), sub_rate=0.3, indel_rate=0.1, n_job_frac=0.2, h0_range=(1, 30))),
+                        (33, dict(qlen_range=(200, 700), h0_range=(19, 150), pad8=False))):
+        jobs = synth.make_ext_jobs(1500 if seed != 33 else 200, w=kw["w"], seed=seed, **extra)
+        want, cnt = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+        res, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
+        bad = np.nonzero((res != want).any(axis=1))[0]
+        assert bad.size == 0, (bad[:5], res[bad[:5]], want[bad[:5]])
+        assert ex.last_cells() == cnt["cells"]
+    ex.destroy()
+
+
+def test_extension_device_packed_path(gpu, oracle):
+    import torch
+    kw = dict(w=100, zdrop=100)
+    jobs = synth.make_ext_jobs(3000, w=100, seed=41, qlen_range=(1, 200), h0_range=(1, 150))
+    want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+    ex = gpu.Extender(0)
+    dq = torch.from_numpy(jobs["qseq"]).cuda()
+    dt = torch.from_numpy(jobs["tseq"]).cuda()
+    qp = torch.empty((dq.numel() + 7) // 8, dtype=torch.int32, device="cuda")
+    tp = torch.empty((dt.numel() + 7) // 8, dtype=torch.int32, device="cuda")
+    ex.pack_device(dq.data_ptr(), dq.numel(), qp.data_ptr())
+    ex.pack_device(dt.data_ptr(), dt.numel(), tp.data_ptr())
+    dev = {k: torch.from_numpy(jobs[k].view(np.int32)).cuda() for k in ("qoff", "toff", "qlen", "tlen", "h0")}
+    out = torch.zeros(3000 * 6, dtype=torch.int32, device="cuda")
+    ex.extend_device(gpu.ext_params(**kw), 3000, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(),
+                     tp.data_ptr(), dev["toff"].data_ptr(), dev["tlen"].data_ptr(), dev["h0"].data_ptr(), out.data_ptr())
+    ex.wait()
+    assert (out.cpu().numpy().reshape(-1, 6) == want).all()
+    ex.destroy()
+
+
+def test_extension_rejects_bad_jobs(gpu):
+    jobs = synth.make_ext_jobs(8, w=100, seed=1, qlen_range=(10, 20))
+    jobs["h0"][3] = 0                                  # ksw_extend2 asserts h0 > 0
+    ex = gpu.Extender(0)
+    with pytest.raises(gpu.B200Error):
+        ex.extend_host(jobs, gpu.ext_params())
+    jobs = synth.make_ext_jobs(4, w=100, seed=1, qlen_range=(10, 20))
+    res, _ = ex.extend_host(jobs, gpu.ext_params())   # the extender recovers after an error
+    assert (res[:, 0] >= jobs["h0"].astype(np.int32)).all()
+    with pytest.raises(gpu.B200Error):                 # n_jobs == 0 (gasal_aln_async exits, gasal_align.cu:32)
+        gpu.check(gpu.lib().bwa_b200_extend_async(ex.h, gpu.ext_params(), 0, jobs["qseq"].ctypes.data, 8, jobs["qoff"].ctypes.data,
+                                                  jobs["qlen"].ctypes.data, jobs["tseq"].ctypes.data, 8, jobs["toff"].ctypes.data,
+                                                  jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data, None, None, None, None))
+    ex.destroy()

@@ -1,0 +1,70 @@
+"""CPU tests: oracle vs golden vectors (generated from the reference's own CPU functions, see
+tests/golden/make_golden.py), host index builder vs golden hashes, oracle internal consistency."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def test_builder_matches_reference_hashes(pkg, tmp_path):
+    """index files byte-identical to the reference's `bwa index` output (hashes recorded by make_golden.py)"""
+    gold = np.load(os.path.join(GOLD, "index_hashes.npz"), allow_pickle=True)
+    for n, rep, seed, intv, h_bwt, h_sa, h_128 in gold["rows"]:
+        g = synth.make_genome(int(n), seed=int(seed), repeats=bool(int(rep)))
+        prefix = str(tmp_path / f"g{n}")
+        pkg.build_index(g, prefix, sa_intv=int(intv), also_stock_layout=True, n_threads=4)
+        assert sha(prefix + ".bwt") == h_bwt
+        assert sha(prefix + ".sa") == h_sa
+        assert sha(prefix + ".bwt128") == h_128
+
+
+def test_oracle_smems_match_reference_golden(oracle, pkg, tmp_path):
+    gold = np.load(os.path.join(GOLD, "seed_golden.npz"))
+    g = synth.make_repeat_genome(int(gold["genome_len"]), seed=int(gold["genome_seed"]))
+    prefix = str(tmp_path / "g")
+    pkg.build_index(g, prefix, sa_intv=int(gold["sa_intv"]), n_threads=4)
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    reads = gold["reads"]
+    n, L = reads.shape
+    off = (np.arange(n + 1) * L).astype(np.uint64)
+    res = oi.smem_batch(reads.reshape(-1).copy(), off, 19)
+    assert (res["n_smems"] == gold["n_smems"]).all()
+    for key in ("qbeg", "qend", "k", "s"):
+        assert (res[key] == gold[key]).all(), key
+    sb = oi.seed_batch(reads.reshape(-1).copy(), off, 19, int(gold["max_occ"]), n_threads=2)
+    assert (sb["n_seeds"] == gold["n_seeds"]).all()
+    assert (sb["rbeg"] == gold["rbeg"]).all()
+    assert (sb["score"] == gold["score"]).all()
+    oi.close()
+
+
+@pytest.mark.parametrize("name", ["ksw_band", "ksw_noband", "ksw_narrow", "ksw_asym"])
+def test_oracle_ksw_matches_reference_golden(oracle, name):
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    jobs = {k: gold[k] for k in ("qseq", "tseq", "qoff", "toff", "qlen", "tlen", "h0")}
+    kw = {k: int(v) for k, v in zip(gold["param_names"], gold["param_values"])}
+    res, cnt = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=2)
+    assert (res == gold["res6"]).all()
+    assert cnt["cells"] > 0
+
+
+def test_oracle_edge_cases(oracle):
+    """tlen == 0, 1-base queries, all-N query, h0 == 1"""
+    p = oracle.make_params()
+    q = np.array([0, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4], np.uint8)
+    t = np.array([0, 1, 2, 3, 0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0], np.uint8)
+    jobs = dict(qseq=q, tseq=t, qoff=np.array([0, 8, 16], np.uint32), toff=np.array([0, 0, 8], np.uint32),
+                qlen=np.array([1, 8, 1], np.uint32), tlen=np.array([0, 8, 8], np.uint32), h0=np.array([5, 1, 30], np.uint32))
+    res, _ = oracle.ksw_batch(jobs, p, n_threads=1)
+    assert list(res[0]) == [5, 0, 0, 0, -1, 0]          # no target rows: score = h0
+    assert res[1][0] == 1                                # all-N query never beats h0
+    assert res[2][0] == 30

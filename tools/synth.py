@@ -33,6 +33,23 @@ def make_genome(n_bases: int, seed: int = GENOME_SEED, repeats: bool = False) ->
     return g
 
 
+def make_repeat_genome(n_bases: int, unit_len: int = 1000, copies: int = 30, div: float = 0.02, seed: int = 7) -> np.ndarray:
+    """random genome whose second half holds `copies` diverged tandem copies of one unit:
+    SMEMs inside the unit have tens of occurrences (exercises the max_occ sampling rule)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = rng.integers(0, 4, size=n_bases, dtype=np.uint8)
+    unit = rng.integers(0, 4, size=unit_len, dtype=np.uint8)
+    p = n_bases - copies * unit_len
+    assert p > 0
+    for _ in range(copies):
+        e = unit.copy()
+        mut = rng.random(unit_len) < div
+        e[mut] = (e[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+        g[p:p + unit_len] = e
+        p += unit_len
+    return g
+
+
 def revcomp(codes: np.ndarray) -> np.ndarray:
     out = codes[..., ::-1].copy()
     m = out < 4
