@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s end-to-end (seed + extend) on synthetic reads, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...
+
+Workload at N=1: BASELINE.json configs[1] -- 1M synthetic 150 bp reads (1 % sub, 0.1 % indel) vs a
+synthetic 100 Mb genome.  A step is one pass of the hot path over the batch: SMEM seeding (+ SA
+locate) of every read, on-device cut of the left/right extension jobs of each read's longest seed,
+and ksw_extend2 on all of them (bwa_b200_seed_extend_*).  Reads shard across ranks (weak scaling:
+every rank owns a full batch and a replica of the index); no data-path collective.
+
+`value` is measured with inputs resident in HBM (CUDA events on the pipeline stream); `e2e` goes
+through the host-buffer C-ABI call with H2D/D2H inside the timed region.  The oracle is used only
+for the cpu_baseline leg and for `--impl reference`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+from tools import synth  # noqa: E402
+
+METRIC = "reads_per_s_end_to_end_seed_extend"
+UNIT = "reads/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def prepare_data(args, rank, world, dist):
+    """genome + index (built once per box, shared through /tmp) and this rank's read batch"""
+    cache = os.environ.get("BWA_B200_CACHE", "/tmp/bwa_b200_bench")
+    os.makedirs(cache, exist_ok=True)
+    prefix = os.path.join(cache, f"g{args.genome}_s{synth.GENOME_SEED}")
+    t0 = time.time()
+    genome = synth.make_genome(args.genome, seed=synth.GENOME_SEED)
+    pkg = ge.load_package()
+    if rank == 0 and not (os.path.exists(prefix + ".sa") and os.path.exists(prefix + ".bwt") and os.path.exists(prefix + ".bwt128")):
+        pkg.build_index(genome, prefix + ".tmp", sa_intv=16, also_stock_layout=True, n_threads=0)
+        for ext in (".bwt", ".bwt128", ".sa"):
+            os.replace(prefix + ".tmp" + ext, prefix + ext)
+    if dist is not None:
+        dist.barrier()
+    t1 = time.time()
+    reads, pos, strand = synth.make_reads(genome, args.reads, args.read_len, seed=synth.READS_SEED + rank)
+    log(f"[rank {rank}] genome+index {t1 - t0:.1f}s, reads {time.time() - t1:.1f}s")
+    return genome, prefix, reads
+
+
+def run_reference(args, rank, world, dist):
+    """CPU arm: the reference's own bwt_smem1 / bwt_sa / ksw_extend2 (oracle/_ref, kind "reference") or,
+    if that library did not travel, the oracle port; all host threads; bounded sample per step."""
+    from oracle import oracle_py as O
+    if rank != 0:
+        return
+    genome, prefix, reads = prepare_data(args, 0, 1, None)
+    sample = min(args.reads, args.cpu_sample)
+    f = reads[:sample].reshape(-1).copy()
+    off = (np.arange(sample + 1) * args.read_len).astype(np.uint64)
+    params = O.make_params()
+    threads = O.default_threads()
+    if O.have_ref():
+        h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+        assert h, "ref_load failed"
+        kind = "reference"
+        step = lambda: O.ref_pipeline(h, genome, f, off, params, 19, 500, threads)  # noqa: E731
+    else:
+        oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
+        kind = "port"
+        step = lambda: O.pipeline(oi, genome, f, off, params, 19, 500, threads)  # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{args.reads} synthetic {args.read_len}bp reads (1% sub, 0.1% indel) vs synthetic {args.genome} bp genome",
+                       "sample_reads_per_step": sample, "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"first {sample} reads of the batch per step, {threads} host threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--genome", type=int, default=100_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world, None)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dref = dist if world > 1 else None
+
+    pkg = ge.load_package()
+    pkg.build()
+    genome, prefix, reads = prepare_data(args, rank, world, dref)
+    n, L = reads.shape
+    flat = reads.reshape(-1)
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+    packed, woff, rl = pkg.pack_codes(flat, off)
+
+    idx = pkg.Index.load(prefix + ".bwt", prefix + ".sa", local)
+    idx.attach_ref(genome)
+    info = idx.info()
+    pl = pkg.Pipeline(idx, n, packed.size, L)
+    sp, ep = pkg.SeedParams(19, 500), pkg.ext_params()
+
+    # resident inputs
+    d_packed = torch.from_numpy(packed.view(np.int32)).cuda()
+    d_woff = torch.from_numpy(woff.view(np.int64)).cuda()
+    d_rl = torch.from_numpy(rl.view(np.int32)).cuda()
+    d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB)
+    stream = torch.cuda.ExternalStream(pl.stream)
+
+    def step_device():
+        pl.run_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
+
+    pl.profile(True)
+    for _ in range(args.warmup):
+        step_device()
+        pl.sync()
+    torch.cuda.synchronize()
+    if dref:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = pl.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ktimes = {}
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                       # evict L2 between timed iterations (outside the event pair)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        pl.sync()
+        for name, ms in pl.kernel_times():
+            ktimes.setdefault(name, []).append(ms)
+    torch.cuda.synchronize()
+    if dref:
+        dist.barrier()
+    clocks = sampler.stop()
+    gpu_launches = pl.launches - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tot = pl.totals()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dref:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step)
+    h_packed = torch.from_numpy(packed).pin_memory() if False else None
+    pin = {}
+    for name, arr in (("packed", packed), ("woff", woff), ("rl", rl)):
+        tns = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+        tns.numpy()[:] = arr.view(np.uint8)
+        pin[name] = tns
+    h_out = torch.empty(n * 72, dtype=torch.uint8).pin_memory()
+    out_np = h_out.numpy().view(pkg.READ_RESULT_DTYPE)
+
+    def step_host():
+        pkg.check(pkg.lib().bwa_b200_seed_extend_host(pl.h, pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(),
+                                                     n, sp, ep, h_out.data_ptr()))
+
+    pl.profile(False)
+    step_host()
+    torch.cuda.synchronize()
+    if dref:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dref:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t.item())
+    h2d = int(packed.nbytes + woff.nbytes + rl.nbytes)
+    d2h = int(n * 72)
+    mapped = int((out_np["seed_qbeg"] >= 0).sum())
+
+    if rank != 0:
+        if dref:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA-event time per launch, live, over the timed steps)
+    pk, pk_src = peaks()
+    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
+    step_kernel_ms = sum(kavg.values())
+    from oracle import oracle_py as O
+    oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    s_n = min(n, 20_000)
+    sf = reads[:s_n].reshape(-1).copy()
+    soff = (np.arange(s_n + 1) * L).astype(np.uint64)
+    _, fc, kc = O.pipeline(oi, genome, sf, soff, O.make_params(), 19, 500, O.default_threads())
+    per_read = {k: v / s_n for k, v in fc.items()}
+    alg = {   # algorithmic bytes per read of each seeding kernel: 32 B per distinct bucket / LF step, 4 B per SA sample
+        "fwd_kernel": 32.0 * per_read["n_bucket_fwd"],
+        "back_kernel": 32.0 * (per_read["n_bucket"] - per_read["n_bucket_fwd"] - per_read["n_lf"]),
+        "locate_kernel": 32.0 * per_read["n_lf"] + 4.0 * per_read["n_located"],
+    }
+    seed_k = {k: kavg[k] for k in alg if k in kavg}
+    dom = max(seed_k, key=seed_k.get) if seed_k else None
+    roofline = None
+    if dom:
+        achieved = alg[dom] * n / (seed_k[dom] / 1e3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                    "algorithmic_bytes_per_read": alg[dom], "ms_per_launch": seed_k[dom], "share_of_step": seed_k[dom] / step_kernel_ms}
+    ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel"))
+    gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
+    seed_ms = sum(seed_k.values())
+    # INT-ALU roofline of the extension kernel: 15 integer ops per cell, 64 int lanes/clk/SM on the ALU pipe
+    int_peak_gops = 148 * 64 * (pk.get("sm_max_mhz", 1965.0) / 1e3)
+    ext_roof = {"bound": "int_alu", "achieved_gcups": gcups, "peak_gcups_int32": int_peak_gops / 15.0,
+                "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None, "ops_per_cell": 15,
+                "cells_per_step": tot["cells"], "ms_per_step": ext_ms}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sample = min(n, args.cpu_sample)
+        cf = reads[:sample].reshape(-1).copy()
+        coff = (np.arange(sample + 1) * L).astype(np.uint64)
+        threads = O.default_threads()
+        if O.have_ref():
+            h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+            kind, fn = "reference", (lambda: O.ref_pipeline(h, genome, cf, coff, O.make_params(), 19, 500, threads))
+        else:
+            kind, fn = "port", (lambda: O.pipeline(oi, genome, cf, coff, O.make_params(), 19, 500, threads))
+        fn()
+        t0 = time.perf_counter()
+        ref_out = fn()
+        cdt = time.perf_counter() - t0
+        ref_out = ref_out[0] if isinstance(ref_out, tuple) else ref_out
+        same = bool(ref_out.tobytes() == out_np[:sample].tobytes())
+        cpu_baseline = {"value": sample / cdt, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"first {sample} reads of the batch, {threads} host threads, same pipeline on CPU",
+                        "gpu_output_identical_on_sample": same}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{n} synthetic {L}bp reads (1% sub, 0.1% indel) vs synthetic {args.genome} bp genome, per GPU",
+                   "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100, "sa_intv": 16,
+                   "index_hbm_bytes": int(info.hbm_bytes), "l2_policy": "512 MB memset between timed steps (L2 flush) and inputs + workspace > L2",
+                   "parallelism": f"reads sharded over {world} rank(s), index replicated, no collective"},
+        "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
+        "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
+                        "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
+                        "kernel_ms": kavg, "oracle_work_per_read": per_read},
+    }
+    print(json.dumps(line), flush=True)
+    if dref:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

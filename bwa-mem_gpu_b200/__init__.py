@@ -67,6 +67,21 @@ class ExtParams(C.Structure):
                 ("use_band", C.c_int32), ("pen_clip", C.c_int32)]
 
 
+class ExtResult(C.Structure):
+    _fields_ = [("score", C.c_int32), ("qle", C.c_int32), ("tle", C.c_int32), ("gtle", C.c_int32),
+                ("gscore", C.c_int32), ("max_off", C.c_int32)]
+
+
+class ReadResult(C.Structure):
+    _fields_ = [("seed_rbeg", C.c_int64), ("seed_qbeg", C.c_int32), ("seed_qend", C.c_int32), ("n_seeds", C.c_int32),
+                ("h0", C.c_int32), ("left", ExtResult), ("right", ExtResult)]
+
+
+READ_RESULT_DTYPE = np.dtype([("seed_rbeg", "<i8"), ("seed_qbeg", "<i4"), ("seed_qend", "<i4"), ("n_seeds", "<i4"), ("h0", "<i4"),
+                              ("left", "<i4", (6,)), ("right", "<i4", (6,))])
+assert READ_RESULT_DTYPE.itemsize == C.sizeof(ReadResult) == 72
+
+
 # every symbol include/bwamem_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bwa_b200_last_error", "bwa_b200_version", "bwa_b200_device_count", "bwa_b200_host_alloc", "bwa_b200_host_free",
@@ -78,6 +93,9 @@ SYMBOLS = [
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
+    "bwa_b200_index_attach_ref", "bwa_b200_pipeline_create", "bwa_b200_pipeline_destroy", "bwa_b200_seed_extend_host",
+    "bwa_b200_seed_extend_device", "bwa_b200_pipeline_sync", "bwa_b200_pipeline_stream", "bwa_b200_pipeline_launches",
+    "bwa_b200_pipeline_totals", "bwa_b200_pipeline_profile", "bwa_b200_pipeline_kernel_times",
 ]
 
 _lib = None
@@ -133,6 +151,19 @@ def lib():
         L.bwa_b200_extender_launches.restype = C.c_uint64
         L.bwa_b200_extender_last_cells.argtypes = [vp]
         L.bwa_b200_extender_last_cells.restype = C.c_uint64
+        L.bwa_b200_index_attach_ref.argtypes = [vp, vp, C.c_uint64]
+        L.bwa_b200_pipeline_create.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+        L.bwa_b200_pipeline_destroy.argtypes = [vp]
+        L.bwa_b200_seed_extend_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ExtParams), vp]
+        L.bwa_b200_seed_extend_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(SeedParams), C.POINTER(ExtParams), vp]
+        L.bwa_b200_pipeline_sync.argtypes = [vp]
+        L.bwa_b200_pipeline_stream.argtypes = [vp]
+        L.bwa_b200_pipeline_stream.restype = vp
+        L.bwa_b200_pipeline_launches.argtypes = [vp]
+        L.bwa_b200_pipeline_launches.restype = C.c_uint64
+        L.bwa_b200_pipeline_totals.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.bwa_b200_pipeline_profile.argtypes = [vp, C.c_int]
+        L.bwa_b200_pipeline_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
         _lib = L
     return _lib
 
@@ -204,6 +235,10 @@ class Index:
         info = IndexInfo()
         check(lib().bwa_b200_index_info(self.h, C.byref(info)))
         return info
+
+    def attach_ref(self, fwd_codes: np.ndarray):
+        fwd = np.ascontiguousarray(fwd_codes, dtype=np.uint8)
+        check(lib().bwa_b200_index_attach_ref(self.h, _p(fwd), fwd.size))
 
     def free(self):
         if self.h:
@@ -325,4 +360,55 @@ class Extender:
     def destroy(self):
         if self.h:
             lib().bwa_b200_extender_destroy(self.h)
+            self.h = None
+
+
+class Pipeline:
+    """Fused seed -> extend pass (bwa_b200_seed_extend_*)."""
+
+    def __init__(self, index: Index, max_reads: int, max_words: int, max_read_len: int):
+        self.h = vp()
+        self.index = index
+        check(lib().bwa_b200_pipeline_create(index.h, max_reads, max_words, max_read_len, C.byref(self.h)))
+
+    def run_host(self, packed, word_off, read_len, seed_params: SeedParams, ext_p: ExtParams, out=None):
+        n = read_len.size
+        if out is None:
+            out = np.zeros(max(n, 1), READ_RESULT_DTYPE)
+        check(lib().bwa_b200_seed_extend_host(self.h, _p(packed), _p(word_off), _p(read_len), n, C.byref(seed_params),
+                                              C.byref(ext_p), _p(out)))
+        return out[:n]
+
+    def run_device(self, d_packed, d_woff, d_len, n, max_read_len, seed_params, ext_p, d_out):
+        check(lib().bwa_b200_seed_extend_device(self.h, d_packed, d_woff, d_len, n, max_read_len, C.byref(seed_params),
+                                                C.byref(ext_p), d_out))
+
+    def sync(self):
+        check(lib().bwa_b200_pipeline_sync(self.h))
+
+    def totals(self):
+        out = (C.c_uint64 * 3)()
+        check(lib().bwa_b200_pipeline_totals(self.h, out))
+        return dict(seeds=int(out[0]), jobs=int(out[1]), cells=int(out[2]))
+
+    def profile(self, on: bool):
+        check(lib().bwa_b200_pipeline_profile(self.h, int(on)))
+
+    def kernel_times(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().bwa_b200_pipeline_kernel_times(self.h, names, ms, 64)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    @property
+    def stream(self) -> int:
+        return int(lib().bwa_b200_pipeline_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_pipeline_launches(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_pipeline_destroy(self.h)
             self.h = None

@@ -38,6 +38,8 @@ struct bwa_b200_index {
     int device = 0;
     b200::IndexView v{};
     uint32_t *d_bkt = nullptr, *d_sa = nullptr, *d_sa_hi = nullptr;
+    uint32_t *d_pac = nullptr;      // optional 2-bit forward reference (16 bases per word)
+    uint64_t l_pac = 0;
     uint64_t n_words = 0, n_sa = 0, n_hi = 0;
     int sa_intv = 0, pack_size = 0;
 };

@@ -18,7 +18,7 @@
 // This is not a port of GASAL2's KSW kernel (one thread per alignment with eh[] in local
 // memory, no band, zdrop = 0, fixed clip penalty): band, z-drop, end bonus and separate
 // insertion/deletion penalties are honoured, and all six outputs are returned.
-#include "common.h"
+#include "internal.h"
 #include <cub/cub.cuh>
 
 namespace {
@@ -90,7 +90,12 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
             const uint32_t a = order[pos];
             const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
             const uint32_t qo = J.qoff[a], to = J.toff[a];
-            if (qlen > max_q || qlen < 1 || h0 < 1) { atomicExch(err_flag, 1); continue; }
+            if (qlen == 0) {               // absent job (pipeline slots): ksw_extend2 is never called, score stays h0
+                bwa_b200_ext_result_t r0; r0.score = h0; r0.qle = 0; r0.tle = 0; r0.gtle = 0; r0.gscore = -1; r0.max_off = 0;
+                res[a] = r0;
+                continue;
+            }
+            if (qlen > max_q || h0 < 1) { atomicExch(err_flag, 1); continue; }
 
             // stage the query
             for (int j8 = 0; j8 < qlen; j8 += 8) {
@@ -223,26 +228,6 @@ __global__ void pack_kernel(const uint8_t *__restrict__ bytes, uint64_t n_words,
 
 } // namespace
 
-struct bwa_b200_extender {
-    int device = 0, n_sm = 0;
-    cudaStream_t stream = nullptr;
-    uint64_t max_jobs = 0, max_q = 0, max_t = 0;
-    uint8_t *d_q = nullptr, *d_t = nullptr;
-    uint32_t *d_qoff = nullptr, *d_qlen = nullptr, *d_toff = nullptr, *d_tlen = nullptr, *d_h0 = nullptr;
-    uint32_t *d_keys = nullptr, *d_keys2 = nullptr, *d_vals = nullptr, *d_order = nullptr, *d_range = nullptr;
-    bwa_b200_ext_result_t *d_res = nullptr;
-    int32_t *d_tri = nullptr;
-    unsigned long long *d_cells = nullptr;
-    int *d_err = nullptr;
-    void *d_cub = nullptr;
-    size_t cub_bytes = 0;
-    unsigned long long *h_cells = nullptr;
-    int *h_err = nullptr;
-    uint64_t launches = 0;
-    bool pending = false;
-    int smem_optin = 0;
-};
-
 static int ext_grow_jobs(bwa_b200_extender *e, uint64_t n)
 {
     if (n <= e->max_jobs) return BWA_B200_OK;
@@ -325,7 +310,7 @@ extern "C" void bwa_b200_extender_destroy(bwa_b200_extender_t *e)
     cudaFree(e->d_h0); cudaFree(e->d_keys); cudaFree(e->d_keys2); cudaFree(e->d_vals); cudaFree(e->d_order); cudaFree(e->d_range);
     cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cells); cudaFree(e->d_err); cudaFree(e->d_cub);
     cudaFreeHost(e->h_cells); cudaFreeHost(e->h_err);
-    cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -352,12 +337,16 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     ExtParams P;
     to_dev_params(p, &P);
     B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
+    if (e->prof) e->prof->begin("ext_sort", e->stream);
     key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, e->d_keys, e->d_vals);
     size_t tmp = e->cub_bytes;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
     range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err);
+    if (e->prof) e->prof->end(e->stream);
     e->launches += 3;
     static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
+    static const char *bin_name[N_BINS] = {"ext_inter_kernel_q16", "ext_inter_kernel_q32", "ext_inter_kernel_q64", "ext_inter_kernel_q128",
+                                           "ext_inter_kernel_q256", "ext_inter_kernel_q512", "ext_inter_kernel_q1024"};
     for (int b = 0; b < N_BINS; ++b) {
         const int L = bin_hi[b];
         const size_t per_thread = ((size_t)(L + 1) + (size_t)(L + 7) / 8) * 4;
@@ -372,7 +361,8 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
-        ext_inter_kernel<BYTES><<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err);
+        B200_LAUNCH(e->prof, bin_name[b], e->stream,
+            (ext_inter_kernel<BYTES><<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     B200_CUDA(cudaGetLastError());
@@ -438,7 +428,7 @@ extern "C" int bwa_b200_extend_wait(bwa_b200_extender_t *e)
     if (*e->h_err) {
         *e->h_err = 0;
         cudaMemsetAsync(e->d_err, 0, 4, e->stream);
-        b200::set_error("extend: a job had qlen < 1, qlen > 1024 or h0 < 1 (ksw_extend2 asserts h0 > 0, src/ksw.c:869)");
+        b200::set_error("extend: a job had qlen > 1024, scores beyond 16 bits, or h0 < 1 (ksw_extend2 asserts h0 > 0, src/ksw.c:869)");
         return BWA_B200_ERR_ARG;
     }
     return BWA_B200_OK;
@@ -465,6 +455,21 @@ extern "C" int bwa_b200_extend_device(bwa_b200_extender_t *e, const bwa_b200_ext
     if (rc) return rc;
     JobView J{nullptr, nullptr, dev_qpacked, dev_tpacked, dev_qoff, dev_qlen, dev_toff, dev_tlen, dev_h0};
     rc = ext_launch<false>(e, p, (uint32_t)n_jobs, J, dev_res6);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
+    e->pending = true;
+    return BWA_B200_OK;
+}
+
+int b200_ext_run_packed(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n,
+                        const uint32_t *d_qp, const uint32_t *d_qoff, const uint32_t *d_qlen,
+                        const uint32_t *d_tp, const uint32_t *d_toff, const uint32_t *d_tlen,
+                        const uint32_t *d_h0, bwa_b200_ext_result_t *d_res)
+{
+    int rc = ext_grow_jobs(e, n);
+    if (rc) return rc;
+    JobView J{nullptr, nullptr, d_qp, d_tp, d_qoff, d_qlen, d_toff, d_tlen, d_h0};
+    rc = ext_launch<false>(e, p, n, J, d_res);
     if (rc) return rc;
     B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
     e->pending = true;

@@ -134,6 +134,7 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
     bwa_b200_index *idx = new bwa_b200_index(*src);
     idx->device = device;
     idx->d_bkt = idx->d_sa = idx->d_sa_hi = nullptr;
+    idx->d_pac = nullptr; idx->l_pac = 0;
     uint64_t padded = (src->n_words + 7) / 8 * 8 + 8;
     B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
     B200_CUDA(cudaMemcpyPeer(idx->d_bkt, device, src->d_bkt, src->device, padded * 4));
@@ -164,7 +165,7 @@ extern "C" void bwa_b200_index_free(bwa_b200_index_t *idx)
 {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    cudaFree(idx->d_bkt); cudaFree(idx->d_sa); cudaFree(idx->d_sa_hi);
+    cudaFree(idx->d_bkt); cudaFree(idx->d_sa); cudaFree(idx->d_sa_hi); cudaFree(idx->d_pac);
     delete idx;
 }
 

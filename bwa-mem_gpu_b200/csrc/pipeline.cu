@@ -1,0 +1,369 @@
+// pipeline.cu -- fused seed -> extend pass: seeds stay in HBM, extension jobs are cut on the
+// device from a resident 2-bit reference, one record per read is produced.
+//
+// Job construction follows the reference's mem_chain2aln for a chain of one seed
+// (cal_max_gap src/bwamem.c:996-1002; rmax window and strand clamp :1180-1201; left/right job
+// shapes and h0 = seed_len * a :1356-1424); see include/bwamem_b200.h for what is and is not
+// claimed.  Kernels here are plumbing around the two hot kernels (seed.cu, extend.cu): a
+// per-read selection, a word-parallel sequence cutter and a gather.
+#include "internal.h"
+
+namespace {
+
+struct Rules { int a, o_del, e_del, o_ins, e_ins, w; };
+
+__device__ __forceinline__ int max_gap(const Rules &r, int qlen)
+{
+    int l_del = (int)((double)(qlen * r.a - r.o_del) / r.e_del + 1.);
+    int l_ins = (int)((double)(qlen * r.a - r.o_ins) / r.e_ins + 1.);
+    int l = l_del > l_ins ? l_del : l_ins;
+    l = l > 1 ? l : 1;
+    return l < (r.w << 1) ? l : (r.w << 1);
+}
+
+struct JobAux { int64_t start; int32_t qfrom; int32_t dir; };   // dir -1: left job (reversed), +1: right job
+
+// one lane per read: choose the seed, shape both jobs
+__global__ void choose_kernel(uint32_t n_reads, int64_t l_pac, Rules R, const uint32_t *__restrict__ read_len,
+                              const uint32_t *__restrict__ n_seeds, const uint64_t *__restrict__ seed_off,
+                              const uint64_t *__restrict__ rbeg, const int2 *__restrict__ qq, uint64_t seed_cap,
+                              uint32_t qstride, uint32_t tstride,
+                              bwa_b200_read_result_t *__restrict__ out,
+                              uint32_t *__restrict__ jq_len, uint32_t *__restrict__ jt_len, uint32_t *__restrict__ j_h0,
+                              uint32_t *__restrict__ jq_off, uint32_t *__restrict__ jt_off, JobAux *__restrict__ aux)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int len = (int)read_len[r];
+    const uint32_t ns = n_seeds[r];
+    const uint64_t so = seed_off[r];
+    int64_t best = -1; int best_len = -1;
+    if (so + ns <= seed_cap)
+        for (uint32_t i = 0; i < ns; ++i) {
+            int2 q = qq[so + i];
+            int sl = q.y - q.x;
+            int64_t rb = (int64_t)rbeg[so + i];
+            if (rb < l_pac && rb + sl > l_pac) continue;           // bridges forward/reverse (bns_intv2rid < 0)
+            if (sl > best_len) { best_len = sl; best = (int64_t)i; }
+        }
+    bwa_b200_read_result_t o;
+    o.seed_rbeg = -1; o.seed_qbeg = -1; o.seed_qend = -1; o.n_seeds = (int32_t)ns; o.h0 = 0;
+    o.left = bwa_b200_ext_result_t{0, 0, 0, 0, 0, 0}; o.right = o.left;
+    uint32_t lq = 0, lt = 0, rq = 0, rt = 0, h0 = 0;
+    JobAux la{0, 0, -1}, ra{0, 0, 1};
+    if (best >= 0) {
+        int2 q = qq[so + best];
+        int64_t rb = (int64_t)rbeg[so + best];
+        int slen = q.y - q.x;
+        int64_t rmax0 = rb - (q.x + max_gap(R, q.x));
+        int64_t rmax1 = rb + slen + ((len - q.y) + max_gap(R, len - q.y));
+        if (rmax0 < 0) rmax0 = 0;
+        if (rmax1 > (l_pac << 1)) rmax1 = l_pac << 1;
+        if (rmax0 < l_pac && l_pac < rmax1) { if (rb < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+        h0 = (uint32_t)(slen * R.a);
+        o.seed_rbeg = rb; o.seed_qbeg = q.x; o.seed_qend = q.y; o.h0 = (int32_t)h0;
+        lq = (uint32_t)q.x; lt = q.x > 0 ? (uint32_t)(rb - rmax0) : 0u;
+        rq = (uint32_t)(len - q.y); rt = q.y < len ? (uint32_t)(rmax1 - (rb + slen)) : 0u;
+        la.start = rb; la.qfrom = q.x; ra.start = rb + slen; ra.qfrom = q.y;
+    }
+    out[r] = o;
+    const uint32_t jl = 2 * r, jr = 2 * r + 1;
+    jq_len[jl] = lq; jt_len[jl] = lt; j_h0[jl] = h0; jq_off[jl] = jl * qstride * 8; jt_off[jl] = jl * tstride * 8; aux[jl] = la;
+    jq_len[jr] = rq; jt_len[jr] = rt; j_h0[jr] = h0; jq_off[jr] = jr * qstride * 8; jt_off[jr] = jr * tstride * 8; aux[jr] = ra;
+}
+
+__device__ __forceinline__ uint32_t text_base(const uint32_t *__restrict__ pac, int64_t l_pac, int64_t p)
+{ // T = fwd + revcomp(fwd); pac: 16 bases per word, base i at bits (15 - i%16)*2
+    bool rev = p >= l_pac;
+    int64_t q = rev ? 2 * l_pac - 1 - p : p;
+    uint32_t b = (pac[q >> 4] >> ((~q & 15) << 1)) & 3u;
+    return rev ? 3u - b : b;
+}
+
+// one lane per output word (8 bases) of every job's query and target slot
+__global__ void cut_kernel(uint32_t n_jobs, int64_t l_pac, const uint32_t *__restrict__ pac,
+                           const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off,
+                           const uint32_t *__restrict__ jq_len, const uint32_t *__restrict__ jt_len,
+                           const JobAux *__restrict__ aux, uint32_t qstride, uint32_t tstride,
+                           uint32_t *__restrict__ qp, uint32_t *__restrict__ tp)
+{
+    const uint32_t per_job = qstride + tstride;
+    const uint64_t total = (uint64_t)n_jobs * per_job;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(g / per_job), wi = (uint32_t)(g % per_job);
+        const JobAux a = aux[j];
+        if (wi < qstride) {
+            const uint32_t ql = jq_len[j];
+            if (wi * 8 >= ql) continue;
+            const uint64_t wo = word_off[j >> 1];
+            uint32_t wv = 0;
+            for (uint32_t u = 0; u < 8; ++u) {
+                uint32_t i = wi * 8 + u, c = 4;
+                if (i < ql) {
+                    int pos = a.dir < 0 ? a.qfrom - 1 - (int)i : a.qfrom + (int)i;
+                    c = (packed_reads[wo + (uint32_t)(pos >> 3)] >> (28 - 4 * (pos & 7))) & 15u;
+                }
+                wv |= c << (28 - 4 * u);
+            }
+            qp[(uint64_t)j * qstride + wi] = wv;
+        } else {
+            const uint32_t ti = wi - qstride, tl = jt_len[j];
+            if (ti * 8 >= tl) continue;
+            uint32_t wv = 0;
+            for (uint32_t u = 0; u < 8; ++u) {
+                uint32_t i = ti * 8 + u, c = 4;
+                if (i < tl) c = text_base(pac, l_pac, a.dir < 0 ? a.start - 1 - (int64_t)i : a.start + (int64_t)i);
+                wv |= c << (28 - 4 * u);
+            }
+            tp[(uint64_t)j * tstride + ti] = wv;
+        }
+    }
+}
+
+__global__ void gather_kernel(uint32_t n_reads, const bwa_b200_ext_result_t *__restrict__ res, const uint32_t *__restrict__ jq_len,
+                              bwa_b200_read_result_t *__restrict__ out, unsigned long long *__restrict__ n_jobs_live)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t live = 0;
+    if (r < n_reads) {
+        out[r].left = res[2 * r];
+        out[r].right = res[2 * r + 1];
+        live = (jq_len[2 * r] > 0) + (jq_len[2 * r + 1] > 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+    if ((threadIdx.x & 31) == 0 && live) atomicAdd(n_jobs_live, (unsigned long long)live);
+}
+
+} // namespace
+
+struct bwa_b200_pipeline {
+    const bwa_b200_index *idx = nullptr;
+    bwa_b200_seeder *seeder = nullptr;
+    bwa_b200_extender *ext = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0, n_sm = 0;
+    uint64_t max_reads = 0;
+    uint32_t max_read_len = 0, qstride = 0, tstride = 0;
+    uint32_t *d_jq_len = nullptr, *d_jt_len = nullptr, *d_j_h0 = nullptr, *d_jq_off = nullptr, *d_jt_off = nullptr;
+    JobAux *d_aux = nullptr;
+    uint32_t *d_qp = nullptr, *d_tp = nullptr;
+    uint64_t qp_words = 0, tp_words = 0;
+    bwa_b200_ext_result_t *d_res = nullptr;
+    bwa_b200_read_result_t *d_out = nullptr;
+    unsigned long long *d_live = nullptr, *h_tot = nullptr;
+    uint64_t launches = 0;
+    b200::Prof prof;
+    bool profiling = false;
+    // state of the batch in flight (for overflow repair)
+    const uint32_t *b_packed = nullptr; const uint64_t *b_woff = nullptr; const uint32_t *b_len = nullptr;
+    uint64_t b_n = 0; uint32_t b_maxlen = 0;
+    bwa_b200_seed_params_t b_sp{19, 500}; bwa_b200_ext_params_t b_ep{}; bwa_b200_read_result_t *b_out = nullptr;
+};
+
+extern "C" int bwa_b200_index_attach_ref(bwa_b200_index_t *idx, const uint8_t *fwd, uint64_t l_pac)
+{
+    if (!idx || !fwd || 2 * l_pac != idx->v.seq_len) { b200::set_error("attach_ref: l_pac does not match the index (seq_len = 2*l_pac)"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(idx->device));
+    uint64_t n_words = (l_pac + 15) / 16 + 1;
+    std::vector<uint32_t> w(n_words, 0);
+    for (uint64_t i = 0; i < l_pac; ++i) w[i >> 4] |= (uint32_t)(fwd[i] & 3) << ((~i & 15) << 1);
+    if (idx->d_pac) cudaFree(idx->d_pac);
+    idx->d_pac = nullptr;
+    B200_CUDA(cudaMalloc(&idx->d_pac, n_words * 4));
+    B200_CUDA(cudaMemcpy(idx->d_pac, w.data(), n_words * 4, cudaMemcpyHostToDevice));
+    idx->l_pac = l_pac;
+    return BWA_B200_OK;
+}
+
+static int pipe_alloc_jobs(bwa_b200_pipeline *p, uint32_t max_len, const bwa_b200_ext_params_t *ep)
+{
+    // slot sizes: query <= read, target <= query + min(cal_max_gap, 2w)
+    uint32_t qstride = (max_len + 7) / 8;
+    int a = ep->mat[0] > 0 ? ep->mat[0] : 1;
+    double gd = (double)((int)max_len * a - ep->o_del) / ep->e_del + 1., gi = (double)((int)max_len * a - ep->o_ins) / ep->e_ins + 1.;
+    int64_t gap = (int64_t)(gd > gi ? gd : gi);
+    if (gap < 1) gap = 1;
+    if (gap > 2 * (int64_t)ep->w) gap = 2 * (int64_t)ep->w;
+    uint32_t tstride = (uint32_t)((max_len + gap + 7) / 8) + 1;
+    uint64_t nj = 2 * p->max_reads;
+    if (qstride > p->qstride || !p->d_qp) {
+        cudaFree(p->d_qp); p->d_qp = nullptr;
+        B200_CUDA(cudaMalloc(&p->d_qp, nj * qstride * 4));
+        p->qstride = qstride;
+    }
+    if (tstride > p->tstride || !p->d_tp) {
+        cudaFree(p->d_tp); p->d_tp = nullptr;
+        B200_CUDA(cudaMalloc(&p->d_tp, nj * tstride * 4));
+        p->tstride = tstride;
+    }
+    if ((uint64_t)nj * p->tstride * 8 >= 0xffffffffull) { b200::set_error("pipeline: batch too large for 32-bit job offsets; use smaller batches"); return BWA_B200_ERR_CAPACITY; }
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_pipeline_create(const bwa_b200_index_t *idx, uint64_t max_reads, uint64_t max_words,
+                                        uint32_t max_read_len, bwa_b200_pipeline_t **out)
+{
+    if (!idx || !out || !max_reads) { b200::set_error("pipeline_create: bad argument"); return BWA_B200_ERR_ARG; }
+    if (!idx->d_pac) { b200::set_error("pipeline_create: no reference attached (bwa_b200_index_attach_ref)"); return BWA_B200_ERR_ARG; }
+    bwa_b200_pipeline *p = new bwa_b200_pipeline();
+    p->idx = idx; p->device = idx->device; p->max_reads = max_reads; p->max_read_len = max_read_len;
+    int rc = bwa_b200_seeder_create(idx, max_reads, max_words, &p->seeder);
+    if (rc) return rc;
+    rc = bwa_b200_extender_create(idx->device, 2 * max_reads, 1024, 1024, &p->ext);
+    if (rc) return rc;
+    p->stream = p->seeder->stream;
+    cudaStreamDestroy(p->ext->stream);          // everything runs on one stream, in order
+    p->ext->stream = p->stream; p->ext->own_stream = false;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, idx->device));
+    p->n_sm = prop.multiProcessorCount;
+    uint64_t nj = 2 * max_reads;
+    B200_CUDA(cudaMalloc(&p->d_jq_len, nj * 4)); B200_CUDA(cudaMalloc(&p->d_jt_len, nj * 4)); B200_CUDA(cudaMalloc(&p->d_j_h0, nj * 4));
+    B200_CUDA(cudaMalloc(&p->d_jq_off, nj * 4)); B200_CUDA(cudaMalloc(&p->d_jt_off, nj * 4)); B200_CUDA(cudaMalloc(&p->d_aux, nj * sizeof(JobAux)));
+    B200_CUDA(cudaMalloc(&p->d_res, nj * sizeof(bwa_b200_ext_result_t)));
+    B200_CUDA(cudaMalloc(&p->d_out, max_reads * sizeof(bwa_b200_read_result_t)));
+    B200_CUDA(cudaMalloc(&p->d_live, 8));
+    B200_CUDA(cudaHostAlloc(&p->h_tot, 32, cudaHostAllocDefault));
+    *out = p;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_pipeline_destroy(bwa_b200_pipeline_t *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    p->seeder->prof = nullptr; p->ext->prof = nullptr;
+    bwa_b200_extender_destroy(p->ext);
+    bwa_b200_seeder_destroy(p->seeder);
+    cudaFree(p->d_jq_len); cudaFree(p->d_jt_len); cudaFree(p->d_j_h0); cudaFree(p->d_jq_off); cudaFree(p->d_jt_off); cudaFree(p->d_aux);
+    cudaFree(p->d_qp); cudaFree(p->d_tp); cudaFree(p->d_res); cudaFree(p->d_out); cudaFree(p->d_live);
+    cudaFreeHost(p->h_tot);
+    delete p;
+}
+
+static int pipe_enqueue(bwa_b200_pipeline *p)
+{
+    const uint32_t n = (uint32_t)p->b_n;
+    cudaStream_t st = p->stream;
+    b200::Prof *prof = p->profiling ? &p->prof : nullptr;
+    p->seeder->prof = prof; p->ext->prof = prof;
+    if (prof) prof->reset();
+    int rc = pipe_alloc_jobs(p, p->b_maxlen, &p->b_ep);
+    if (rc) return rc;
+    rc = b200_seeder_run(p->seeder, p->b_packed, p->b_woff, p->b_len, p->b_n, p->b_maxlen, &p->b_sp);
+    if (rc) return rc;
+    Rules R{p->b_ep.mat[0], p->b_ep.o_del, p->b_ep.e_del, p->b_ep.o_ins, p->b_ep.e_ins, p->b_ep.w};
+    bwa_b200_seeder *s = p->seeder;
+    B200_CUDA(cudaMemsetAsync(p->d_live, 0, 8, st));
+    B200_LAUNCH(prof, "choose_kernel", st,
+        (choose_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, (int64_t)p->idx->l_pac, R, p->b_len, s->d_nseeds, s->d_seed_off, s->d_rbeg,
+                                                       s->d_qq, s->seed_cap, p->qstride, p->tstride, p->b_out, p->d_jq_len, p->d_jt_len,
+                                                       p->d_j_h0, p->d_jq_off, p->d_jt_off, p->d_aux)));
+    B200_LAUNCH(prof, "cut_kernel", st,
+        (cut_kernel<<<p->n_sm * 16, 256, 0, st>>>(2 * n, (int64_t)p->idx->l_pac, p->idx->d_pac, p->b_packed, p->b_woff, p->d_jq_len,
+                                                 p->d_jt_len, p->d_aux, p->qstride, p->tstride, p->d_qp, p->d_tp)));
+    rc = b200_ext_run_packed(p->ext, &p->b_ep, 2 * n, p->d_qp, p->d_jq_off, p->d_jq_len, p->d_tp, p->d_jt_off, p->d_jt_len, p->d_j_h0, p->d_res);
+    if (rc) return rc;
+    B200_LAUNCH(prof, "gather_kernel", st,
+        (gather_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_res, p->d_jq_len, p->b_out, p->d_live)));
+    p->launches += 3;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_seed_extend_device(bwa_b200_pipeline_t *p, const uint32_t *dev_packed, const uint64_t *dev_word_off,
+                                           const uint32_t *dev_read_len, uint64_t n_reads, uint32_t max_read_len,
+                                           const bwa_b200_seed_params_t *sp, const bwa_b200_ext_params_t *ep,
+                                           bwa_b200_read_result_t *dev_out)
+{
+    if (!p || !sp || !ep || !dev_out || (n_reads && (!dev_packed || !dev_word_off || !dev_read_len))) { b200::set_error("seed_extend_device: bad argument"); return BWA_B200_ERR_ARG; }
+    if (n_reads > p->max_reads) { b200::set_error("seed_extend: %llu reads > capacity", (unsigned long long)n_reads); return BWA_B200_ERR_CAPACITY; }
+    if (sp->max_occ <= 0) { b200::set_error("seed_extend: max_occ must be positive"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(p->device));
+    p->b_packed = dev_packed; p->b_woff = dev_word_off; p->b_len = dev_read_len; p->b_n = n_reads; p->b_maxlen = max_read_len;
+    p->b_sp = *sp; p->b_ep = *ep; p->b_out = dev_out;
+    if (n_reads == 0) return BWA_B200_OK;
+    return pipe_enqueue(p);
+}
+
+// wait for the batch; if the seed arrays overflowed, they have been grown: run the batch again
+extern "C" int bwa_b200_pipeline_sync(bwa_b200_pipeline_t *p)
+{
+    if (!p) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(p->device));
+    if (p->b_n == 0) return BWA_B200_OK;
+    uint64_t cap_before = p->seeder->seed_cap;
+    int rc = b200_seeder_finish(p->seeder);
+    if (rc) return rc;
+    if (p->seeder->last_total > cap_before) {
+        rc = pipe_enqueue(p);
+        if (rc) return rc;
+        rc = b200_seeder_finish(p->seeder);
+        if (rc) return rc;
+    }
+    B200_CUDA(cudaStreamSynchronize(p->stream));
+    return bwa_b200_extend_wait(p->ext);
+}
+
+extern "C" int bwa_b200_seed_extend_host(bwa_b200_pipeline_t *p, const uint32_t *packed, const uint64_t *word_off,
+                                         const uint32_t *read_len, uint64_t n_reads, const bwa_b200_seed_params_t *sp,
+                                         const bwa_b200_ext_params_t *ep, bwa_b200_read_result_t *host_out)
+{
+    if (!p || !sp || !ep || (n_reads && (!packed || !word_off || !read_len || !host_out))) { b200::set_error("seed_extend_host: bad argument"); return BWA_B200_ERR_ARG; }
+    if (n_reads == 0) return BWA_B200_OK;
+    bwa_b200_seeder *s = p->seeder;
+    if (n_reads > p->max_reads || word_off[n_reads] > s->max_words) { b200::set_error("seed_extend_host: batch exceeds the pipeline capacity"); return BWA_B200_ERR_CAPACITY; }
+    B200_CUDA(cudaSetDevice(p->device));
+    uint32_t max_len = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) max_len = read_len[r] > max_len ? read_len[r] : max_len;
+    cudaStream_t st = p->stream;
+    B200_CUDA(cudaMemcpyAsync(s->d_packed, packed, word_off[n_reads] * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(s->d_woff, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(s->d_len, read_len, n_reads * 4, cudaMemcpyHostToDevice, st));
+    int rc = bwa_b200_seed_extend_device(p, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, sp, ep, p->d_out);
+    if (rc) return rc;
+    rc = bwa_b200_pipeline_sync(p);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(host_out, p->d_out, n_reads * sizeof(bwa_b200_read_result_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return BWA_B200_OK;
+}
+
+extern "C" void *bwa_b200_pipeline_stream(bwa_b200_pipeline_t *p) { return p ? (void *)p->stream : nullptr; }
+extern "C" uint64_t bwa_b200_pipeline_launches(const bwa_b200_pipeline_t *p)
+{
+    return p ? p->launches + p->seeder->launches + p->ext->launches : 0;
+}
+
+extern "C" int bwa_b200_pipeline_totals(bwa_b200_pipeline_t *p, uint64_t out[3])
+{
+    if (!p || !out) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(p->device));
+    B200_CUDA(cudaMemcpyAsync(p->h_tot, p->d_live, 8, cudaMemcpyDeviceToHost, p->stream));
+    B200_CUDA(cudaMemcpyAsync(p->h_tot + 1, p->ext->d_cells, 8, cudaMemcpyDeviceToHost, p->stream));
+    B200_CUDA(cudaStreamSynchronize(p->stream));
+    out[0] = p->seeder->last_total; out[1] = p->h_tot[0]; out[2] = p->h_tot[1];
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_pipeline_profile(bwa_b200_pipeline_t *p, int enable)
+{
+    if (!p) return BWA_B200_ERR_ARG;
+    p->profiling = enable != 0;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_pipeline_kernel_times(bwa_b200_pipeline_t *p, const char **names, float *ms, int cap)
+{
+    if (!p) return BWA_B200_ERR_ARG;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    int n = 0;
+    for (size_t i = 0; i < p->prof.used && n < cap; ++i, ++n) {
+        float t = 0;
+        cudaEventElapsedTime(&t, p->prof.recs[i].a, p->prof.recs[i].b);
+        names[n] = p->prof.recs[i].name; ms[n] = t;
+    }
+    return n;
+}

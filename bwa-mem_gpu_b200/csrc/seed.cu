@@ -23,7 +23,7 @@
 //
 // HBM traffic per read is dominated by random 32-byte sectors of the bucket array (one sector per
 // occurrence lookup); candidates cost 16 B written + read once per size change.
-#include "common.h"
+#include "internal.h"
 #include <cub/cub.cuh>
 
 using b200::IndexView;
@@ -35,12 +35,7 @@ constexpr int BACK_THREADS = 128;
 constexpr int ENV_SMEM = 24;          // envelope entries kept in shared memory per lane
 constexpr int LOC_THREADS = 128;
 
-struct __align__(16) Cand {           // one forward candidate / (after back_kernel) one SMEM
-    uint64_t k;                       // x[0]: first SA row
-    uint32_t s;                       // x[2]: interval size; 0 after back_kernel = not an SMEM
-    uint16_t x;                       // segment start (candidate) / SMEM begin (after back_kernel)
-    uint16_t end;                     // exclusive end on the read
-};
+using b200::Cand;
 
 // ----------------------------------------------------------------------------- bucket access
 struct Bkt { uint32_t c[4]; uint32_t w[4]; };
@@ -369,36 +364,6 @@ struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { re
 } // namespace
 
 // =============================================================================== host side
-struct bwa_b200_seeder {
-    const bwa_b200_index *idx = nullptr;
-    int device = 0, n_sm = 0;
-    cudaStream_t stream = nullptr;
-    uint64_t max_reads = 0, max_words = 0;
-    uint32_t max_read_len = 0, cand_stride = 0, env_stride = 0;
-    // inputs (host API)
-    uint32_t *d_packed = nullptr, *d_len = nullptr;
-    uint64_t *d_woff = nullptr;
-    // workspace
-    Cand *d_cand = nullptr;
-    uint64_t cand_cap = 0;
-    uint32_t *d_ncand = nullptr, *d_nsmems = nullptr, *d_nseeds = nullptr, *d_env = nullptr;
-    uint64_t *d_seed_off = nullptr, *d_smem_off = nullptr;
-    unsigned long long *d_counters = nullptr;     // [0] next_read, [1] next_seed, [2] total seeds, [3] total smems
-    void *d_cub = nullptr;
-    size_t cub_bytes = 0;
-    // outputs
-    uint64_t *d_rbeg = nullptr;
-    int2 *d_qq = nullptr;
-    uint32_t *d_score = nullptr;
-    uint64_t seed_cap = 0;
-    uint64_t last_n_reads = 0, last_total = 0;
-    int back_grid = 0, loc_grid = 0;
-    uint64_t launches = 0;
-    bwa_b200_seed_params_t last_p{19, 500};
-    // pinned staging for the scalar read-backs
-    unsigned long long *h_counters = nullptr;
-};
-
 static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, int min_seed_len)
 {
     uint32_t stride = max_len >= (uint32_t)min_seed_len ? max_len - (uint32_t)min_seed_len + 2 : 2;
@@ -464,6 +429,8 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, it, s->d_seed_off, (int)max_reads, s->stream));
     B200_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes + 16));
+    int rc = seeder_ensure_out(s, max_reads * 4);
+    if (rc) return rc;
     *out = s;
     return BWA_B200_OK;
 }
@@ -484,55 +451,77 @@ extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
 extern "C" void *bwa_b200_seeder_stream(bwa_b200_seeder_t *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s) { return s ? s->launches : 0; }
 
-// enqueue fwd -> back -> scan -> (total) ; then fill + locate once the output capacity is known
-static int seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t *d_woff, const uint32_t *d_len,
-                      uint64_t n_reads, uint32_t max_len, const bwa_b200_seed_params_t *p)
+static int seeder_fill_locate(bwa_b200_seeder *s)
+{
+    const IndexView &ix = s->idx->v;
+    const uint32_t n = (uint32_t)s->last_n_reads;
+    cudaStream_t st = s->stream;
+    B200_LAUNCH(s->prof, "fill_kernel", st,
+        (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
+                                                       s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
+    B200_LAUNCH(s->prof, "locate_kernel", st,
+        (locate_kernel<<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
+    s->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+// enqueue fwd -> back -> scan -> total -> fill -> locate on s->stream; no host synchronisation
+int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t *d_woff, const uint32_t *d_len,
+                    uint64_t n_reads, uint32_t max_len, const bwa_b200_seed_params_t *p)
 {
     if (n_reads > s->max_reads) { b200::set_error("seed: %llu reads > capacity %llu", (unsigned long long)n_reads, (unsigned long long)s->max_reads); return BWA_B200_ERR_CAPACITY; }
     if (max_len > 65535) { b200::set_error("seed: reads longer than 65535 bases are not supported"); return BWA_B200_ERR_ARG; }
     if (p->min_seed_len < 1) { b200::set_error("seed: min_seed_len < 1"); return BWA_B200_ERR_ARG; }
     B200_CUDA(cudaSetDevice(s->device));
-    s->last_n_reads = n_reads; s->last_total = 0; s->last_p = *p;
+    s->last_n_reads = n_reads; s->last_total = 0; s->last_p = *p; s->filled = false;
     if (n_reads == 0) return BWA_B200_OK;
+    if (!s->idx->v.sa) { b200::set_error("seed: index has no suffix array samples"); return BWA_B200_ERR_ARG; }
     int rc = seeder_ensure_cand(s, n_reads, max_len, p->min_seed_len);
     if (rc) return rc;
     const IndexView &ix = s->idx->v;
     const uint32_t n = (uint32_t)n_reads;
-    B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
-    fwd_kernel<<<(n + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, s->stream>>>(
-        ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand);
-    back_kernel<<<s->back_grid, BACK_THREADS, 0, s->stream>>>(
-        ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride, s->d_cand, s->d_ncand,
-        s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0);
+    cudaStream_t st = s->stream;
+    B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    B200_LAUNCH(s->prof, "fwd_kernel", st,
+        (fwd_kernel<<<(n + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, st>>>(
+            ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+    B200_LAUNCH(s->prof, "back_kernel", st,
+        (back_kernel<<<s->back_grid, BACK_THREADS, 0, st>>>(
+            ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride, s->d_cand, s->d_ncand,
+            s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     size_t tmp = s->cub_bytes;
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_seed_off, (int)n, s->stream));
-    total_kernel<<<1, 1, 0, s->stream>>>(s->d_nseeds, s->d_seed_off, n, s->d_counters + 2);
+    if (s->prof) s->prof->begin("scan", st);
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_seed_off, (int)n, st));
+    total_kernel<<<1, 1, 0, st>>>(s->d_nseeds, s->d_seed_off, n, s->d_counters + 2);
+    if (s->prof) s->prof->end(st);
     s->launches += 4;
     B200_CUDA(cudaGetLastError());
+    if (s->seed_cap > 0) {                 // output arrays exist: keep going without a host round trip
+        rc = seeder_fill_locate(s);
+        if (rc) return rc;
+        s->filled = true;
+    }
     return BWA_B200_OK;
 }
 
-static int seeder_finish(bwa_b200_seeder *s, bool need_total_on_host)
+// read the seed total back; if the arrays were too small (or absent) grow them and redo fill+locate
+int b200_seeder_finish(bwa_b200_seeder *s)
 {
     if (s->last_n_reads == 0) return BWA_B200_OK;
-    const IndexView &ix = s->idx->v;
-    const uint32_t n = (uint32_t)s->last_n_reads;
-    // the seed total sizes the output arrays: one 8-byte read-back
     B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
     s->last_total = s->h_counters[2];
+    if (s->filled && s->last_total <= s->seed_cap) return BWA_B200_OK;
     int rc = seeder_ensure_out(s, s->last_total);
     if (rc) return rc;
     if (s->last_total) {
-        if (!ix.sa) { b200::set_error("seed: index has no suffix array samples"); return BWA_B200_ERR_ARG; }
-        fill_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
-                                                             s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap);
-        locate_kernel<<<s->loc_grid, LOC_THREADS, 0, s->stream>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1);
-        s->launches += 2;
-        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemsetAsync(s->d_counters + 1, 0, sizeof(unsigned long long), s->stream));
+        rc = seeder_fill_locate(s);
+        if (rc) return rc;
     }
-    (void)need_total_on_host;
+    s->filled = true;
     return BWA_B200_OK;
 }
 
@@ -554,9 +543,9 @@ extern "C" int bwa_b200_seed_device(bwa_b200_seeder_t *s, const uint32_t *dev_pa
         max_len = *(uint32_t *)(s->h_counters + 3);
         s->launches += 1;
     }
-    int rc = seeder_run(s, dev_packed, dev_word_off, dev_read_len, n_reads, max_len, p);
+    int rc = b200_seeder_run(s, dev_packed, dev_word_off, dev_read_len, n_reads, max_len, p);
     if (rc) return rc;
-    return seeder_finish(s, false);
+    return b200_seeder_finish(s);
 }
 
 extern "C" int bwa_b200_seed_device_result(bwa_b200_seeder_t *s, bwa_b200_seeds_t *v)
@@ -588,9 +577,9 @@ extern "C" int bwa_b200_seed_host(bwa_b200_seeder_t *s, const uint32_t *packed, 
         B200_CUDA(cudaMemcpyAsync(s->d_woff, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s->stream));
         B200_CUDA(cudaMemcpyAsync(s->d_len, read_len, n_reads * 4, cudaMemcpyHostToDevice, s->stream));
     }
-    int rc = seeder_run(s, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, p);
+    int rc = b200_seeder_run(s, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, p);
     if (rc) return rc;
-    rc = seeder_finish(s, true);
+    rc = b200_seeder_finish(s);
     if (rc) return rc;
     const uint64_t tot = s->last_total;
     out->n_seeds = tot;

@@ -196,6 +196,49 @@ uint64_t bwa_b200_extender_launches(const bwa_b200_extender_t *e);
 /* cells evaluated by the last batch (sum over rows of end-beg), counted on device */
 uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e);
 
+/* ------------------------------------------------- fused seed -> extend pipeline */
+/* B200-first entry point for the headline metric (reads/s, seed + extend): reads go in once,
+ * SMEM seeds stay in HBM, the extension jobs of each read are cut on the device from a resident
+ * 2-bit copy of the reference (the .pac content) and extended, and one fixed-size record per read
+ * comes back.  Job shapes follow mem_chain2aln for a one-seed chain (cal_max_gap / rmax window,
+ * src/bwamem.c:996-1002,1180-1201; left and right both start from h0 = seed_len * a as in the fork,
+ * src/bwamem.c:1360,1384).  The seed extended is the longest located seed of the read (first on
+ * ties) that does not bridge the forward/reverse boundary; chaining proper stays with the caller
+ * (it is not on the hot path).  The two-boundary flow (bwa_b200_seed_host, then
+ * bwa_b200_extend_async) remains available and returns the same numbers. */
+int  bwa_b200_index_attach_ref(bwa_b200_index_t *idx, const uint8_t *fwd_codes, uint64_t l_pac);
+
+typedef struct {
+    int64_t seed_rbeg;              /* -1 when the read has no usable seed */
+    int32_t seed_qbeg, seed_qend;
+    int32_t n_seeds;                /* located seeds of the read           */
+    int32_t h0;
+    bwa_b200_ext_result_t left, right;   /* score = h0 and gscore = -1 where no extension was needed */
+} bwa_b200_read_result_t;
+
+typedef struct bwa_b200_pipeline bwa_b200_pipeline_t;
+int  bwa_b200_pipeline_create(const bwa_b200_index_t *idx, uint64_t max_reads, uint64_t max_words,
+                              uint32_t max_read_len, bwa_b200_pipeline_t **out);
+void bwa_b200_pipeline_destroy(bwa_b200_pipeline_t *p);
+/* host buffers in and out: H2D, kernels, D2H, synchronised on return */
+int  bwa_b200_seed_extend_host(bwa_b200_pipeline_t *p, const uint32_t *packed, const uint64_t *word_off,
+                               const uint32_t *read_len, uint64_t n_reads, const bwa_b200_seed_params_t *sp,
+                               const bwa_b200_ext_params_t *ep, bwa_b200_read_result_t *host_out);
+/* device buffers in and out, asynchronous on the pipeline stream; call _sync before reading */
+int  bwa_b200_seed_extend_device(bwa_b200_pipeline_t *p, const uint32_t *dev_packed, const uint64_t *dev_word_off,
+                                 const uint32_t *dev_read_len, uint64_t n_reads, uint32_t max_read_len,
+                                 const bwa_b200_seed_params_t *sp, const bwa_b200_ext_params_t *ep,
+                                 bwa_b200_read_result_t *dev_out);
+int  bwa_b200_pipeline_sync(bwa_b200_pipeline_t *p);
+void *bwa_b200_pipeline_stream(bwa_b200_pipeline_t *p);
+uint64_t bwa_b200_pipeline_launches(const bwa_b200_pipeline_t *p);
+/* totals of the last batch: [0] seeds, [1] extension jobs with qlen > 0, [2] DP cells evaluated */
+int  bwa_b200_pipeline_totals(bwa_b200_pipeline_t *p, uint64_t out[3]);
+/* per-kernel device time of the last batch, measured with CUDA events on the pipeline stream:
+ * enable, run a batch, sync, then read (name, milliseconds) pairs; returns the number of records */
+int  bwa_b200_pipeline_profile(bwa_b200_pipeline_t *p, int enable);
+int  bwa_b200_pipeline_kernel_times(bwa_b200_pipeline_t *p, const char **names, float *ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

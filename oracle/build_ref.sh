@@ -33,7 +33,7 @@ for shift in 7 6; do
     gcc $CFLAGS $objs -o "$OUT/bwa$shift" -lm -lz -lpthread -lrt
     if [ "$shift" = 7 ]; then
       lobjs=""; for o in $LOBJS; do lobjs="$lobjs $o.o"; done
-      gcc -c $CFLAGS -fopenmp -I. "$HERE/ref_shim.c" -o ref_shim.o
+      gcc -c $CFLAGS -fopenmp -I. -I"$HERE" "$HERE/ref_shim.c" -o ref_shim.o
       gcc -shared $CFLAGS -fopenmp $lobjs ref_shim.o -o "$OUT/libbwaref.so" -lm -lz -lpthread -lrt
     fi )
 done

@@ -182,7 +182,9 @@ int fmd_smem1(const fmd_index_t *idx, int len, const uint8_t *q, int x, int min_
     for (i = x + 1; i < len; ++i) {
         if (q[i] < 4) {
             int cb = 3 - q[i];
+            uint64_t b_before = c ? c->n_bucket : 0;
             fmd_extend(idx, &ik, ok, 0, c);
+            if (c) { c->n_extend_fwd++; c->n_bucket_fwd += c->n_bucket - b_before; }
             if (ok[cb].s != ik.s) {
                 curr[n_curr++] = ik;
                 if (ok[cb].s < (uint64_t)min_intv) break;
@@ -351,7 +353,7 @@ int64_t fmd_seed_batch(const fmd_index_t *idx, const uint8_t *reads, const uint6
         }
     }
     for (int t = 0; t < n_threads; ++t) {
-        if (cnt) { cnt->n_extend += tc[t].n_extend; cnt->n_bucket += tc[t].n_bucket; cnt->n_lf += tc[t].n_lf; cnt->n_located += tc[t].n_located; cnt->n_smem += tc[t].n_smem; }
+        if (cnt) { cnt->n_extend += tc[t].n_extend; cnt->n_bucket += tc[t].n_bucket; cnt->n_lf += tc[t].n_lf; cnt->n_located += tc[t].n_located; cnt->n_smem += tc[t].n_smem; cnt->n_extend_fwd += tc[t].n_extend_fwd; cnt->n_bucket_fwd += tc[t].n_bucket_fwd; }
         free(tv[t].a);
     }
     free(tv); free(tc); free(where); free(who);

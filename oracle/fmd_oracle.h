@@ -44,6 +44,8 @@ typedef struct {           /* instrumentation: roofline numerators *
     uint64_t n_lf;         /* LF steps inside SA lookups                        */
     uint64_t n_located;    /* SA lookups                                        */
     uint64_t n_smem;       /* SMEMs kept (len >= min_seed_len)                  */
+    uint64_t n_extend_fwd; /* subset of n_extend done by forward phases         */
+    uint64_t n_bucket_fwd; /* subset of n_bucket touched by forward phases      */
 } fmd_counters_t;
 
 /* loaders for the reference file formats (bwa_index/bwt.c:461-487 writers,

@@ -31,7 +31,8 @@ class FmdIndex(C.Structure):
 
 class FmdCounters(C.Structure):
     _fields_ = [("n_extend", C.c_uint64), ("n_bucket", C.c_uint64), ("n_lf", C.c_uint64),
-                ("n_located", C.c_uint64), ("n_smem", C.c_uint64)]
+                ("n_located", C.c_uint64), ("n_smem", C.c_uint64),
+                ("n_extend_fwd", C.c_uint64), ("n_bucket_fwd", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -50,7 +51,7 @@ class KswCounters(C.Structure):
 def build_oracle() -> str:
     """(Re)build oracle/liboracle.so if missing or stale; returns its path."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "fmd_oracle.h", "ksw_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -78,8 +79,26 @@ def lib():
         L.ksw_fill_mat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.ksw_extend_batch_oracle.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p,
                                               C.POINTER(KswParams), i32p, C.c_int, C.POINTER(KswCounters)]
+        L.pipeline_oracle.argtypes = [C.POINTER(FmdIndex), u8p, C.c_int64, u8p, u64p, C.c_int64, C.c_int, C.c_int,
+                                      C.POINTER(KswParams), C.c_int, C.c_void_p, C.c_int, C.POINTER(FmdCounters), C.POINTER(KswCounters)]
         _lib = L
     return _lib
+
+
+READ_RESULT_DTYPE = np.dtype([("seed_rbeg", "<i8"), ("seed_qbeg", "<i4"), ("seed_qend", "<i4"), ("n_seeds", "<i4"), ("h0", "<i4"),
+                              ("left", "<i4", (6,)), ("right", "<i4", (6,))])
+
+
+def pipeline(oi, fwd: np.ndarray, reads: np.ndarray, read_off: np.ndarray, params, min_seed_len=19, max_occ=500, n_threads=None):
+    """CPU statement of the fused seed -> extend pass.  Returns (records, fmd counters, ksw counters)."""
+    n = read_off.size - 1
+    out = np.zeros(max(n, 1), READ_RESULT_DTYPE)
+    fc, kc = FmdCounters(), KswCounters()
+    a = int(params.mat[0])
+    lib().pipeline_oracle(C.byref(oi.idx), np.ascontiguousarray(fwd), fwd.size, np.ascontiguousarray(reads),
+                          np.ascontiguousarray(read_off), n, min_seed_len, max_occ, C.byref(params), a,
+                          out.ctypes.data, n_threads or default_threads(), C.byref(fc), C.byref(kc))
+    return out[:n], fc.as_dict(), dict(cells=int(kc.cells), rows=int(kc.rows), rect=int(kc.rect))
 
 
 def default_threads() -> int:
@@ -204,8 +223,21 @@ def ref_lib():
         L.ref_seed_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.ref_seed_batch.restype = C.c_int64
         L.ref_ksw_batch.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p, i8p] + [C.c_int] * 7 + [i32p, C.c_int]
+        L.ref_pipeline_batch.argtypes = [C.c_void_p, u8p, C.c_int64, u8p, u64p, C.c_int64, C.c_int, C.c_int, i8p] + [C.c_int] * 8 + [C.c_void_p, C.c_int]
         _ref = L
     return _ref
+
+
+def ref_pipeline(handle, fwd, reads, read_off, params, min_seed_len=19, max_occ=500, n_threads=None):
+    """the fused seed -> extend pass run with the REFERENCE's own bwt_smem1 / bwt_sa / ksw_extend2"""
+    n = read_off.size - 1
+    out = np.zeros(max(n, 1), READ_RESULT_DTYPE)
+    mat = np.frombuffer(bytes(params.mat), dtype=np.int8).copy()
+    ref_lib().ref_pipeline_batch(handle, np.ascontiguousarray(fwd), fwd.size, np.ascontiguousarray(reads),
+                                 np.ascontiguousarray(read_off), n, min_seed_len, max_occ, mat,
+                                 params.o_del, params.e_del, params.o_ins, params.e_ins, params.w, params.end_bonus,
+                                 params.zdrop, int(params.mat[0]), out.ctypes.data, n_threads or default_threads())
+    return out[:n]
 
 
 def fork_lib():

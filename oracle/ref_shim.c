@@ -20,6 +20,7 @@
 #include "bwt.h"
 #include "ksw.h"
 #include "bwa.h"
+#include "jobs_common.h"
 
 void *ref_load(const char *bwt128_path, const char *sa_path)
 {
@@ -140,4 +141,69 @@ void ref_ksw_batch(int64_t n, const uint8_t *qseq, const uint32_t *qoff, const u
     for (int64_t a = 0; a < n; ++a)
         ref_ksw_extend2((int)qlen[a], qseq + qoff[a], (int)tlen[a], tseq + toff[a], mat, o_del, e_del, o_ins, e_ins,
                         w, end_bonus, zdrop, (int)h0[a], out6 + 6 * a);
+}
+
+/* fused seed -> extend pass (same record layout as bwa_b200_read_result_t) computed with the
+ * reference's bwt_smem1 / bwt_sa / ksw_extend2; job shapes from oracle/jobs_common.h */
+typedef struct { int64_t seed_rbeg; int32_t seed_qbeg, seed_qend, n_seeds, h0; int32_t left[6], right[6]; } ref_read_result_t;
+
+void ref_pipeline_batch(void *h, const uint8_t *fwd, int64_t l_pac, const uint8_t *reads, const uint64_t *read_off,
+                        int64_t n_reads, int min_seed_len, int max_occ, const int8_t *mat,
+                        int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int a,
+                        ref_read_result_t *out, int n_threads)
+{
+    bwt_t *bwt = (bwt_t *)h;
+    job_rules_t rules = {a, o_del, e_del, o_ins, e_ins, w};
+#pragma omp parallel num_threads(n_threads)
+    {
+        bwtintv_v mem = {0, 0, 0}, t0 = {0, 0, 0}, t1 = {0, 0, 0};
+        bwtintv_v *tmpv[2] = {&t0, &t1};
+        uint64_t *rb = NULL; int32_t *qb = NULL, *qe = NULL; size_t sc = 0;
+        uint8_t *qbuf = NULL, *tbuf = NULL; size_t qcap = 0, tcap = 0;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const uint8_t *q = reads + read_off[r];
+            int len = (int)(read_off[r + 1] - read_off[r]), x = 0;
+            ref_read_result_t *o = &out[r];
+            memset(o, 0, sizeof(*o));
+            o->seed_qbeg = -1; o->seed_rbeg = -1; o->seed_qend = -1;
+            size_t ns = 0;
+            while (len >= min_seed_len && x < len) {
+                if (q[x] < 4) {
+                    x = bwt_smem1(bwt, len, q, x, 1, &mem, tmpv);
+                    for (size_t i = 0; i < mem.n; ++i) {
+                        bwtintv_t *p = &mem.a[i];
+                        int beg = (int)(p->info >> 32), end = (int)(uint32_t)p->info;
+                        if (end - beg < min_seed_len) continue;
+                        int64_t step = p->x[2] > (uint64_t)max_occ ? p->x[2] / max_occ : 1, k, count;
+                        for (k = count = 0; k < (int64_t)p->x[2] && count < max_occ; k += step, ++count) {
+                            if (ns == sc) { sc = sc * 2 + 64; rb = (uint64_t *)realloc(rb, sc * 8); qb = (int32_t *)realloc(qb, sc * 4); qe = (int32_t *)realloc(qe, sc * 4); }
+                            rb[ns] = bwt_sa(bwt, p->x[0] + k); qb[ns] = beg; qe[ns] = end; ++ns;
+                        }
+                    }
+                } else ++x;
+            }
+            o->n_seeds = (int32_t)ns;
+            int64_t best = jc_choose(rb, qb, qe, (int64_t)ns, l_pac);
+            if (best < 0) continue;
+            job_pair_t j;
+            jc_shape(&rules, l_pac, len, (int64_t)rb[best], qb[best], qe[best], &j);
+            o->seed_rbeg = j.rbeg; o->seed_qbeg = j.qbeg; o->seed_qend = j.qend; o->h0 = j.h0;
+            if ((size_t)len + 8 > qcap) { qcap = (size_t)len + 8; qbuf = (uint8_t *)realloc(qbuf, qcap); }
+            size_t tneed = (size_t)(j.lt > j.rt ? j.lt : j.rt) + 8;
+            if (tneed > tcap) { tcap = tneed; tbuf = (uint8_t *)realloc(tbuf, tcap); }
+            int32_t none[6] = {j.h0, 0, 0, 0, -1, 0};
+            memcpy(o->left, none, sizeof(none)); memcpy(o->right, none, sizeof(none));
+            if (j.lq > 0) {
+                for (int i = 0; i < j.lq; ++i) qbuf[i] = q[j.qbeg - 1 - i];
+                for (int i = 0; i < j.lt; ++i) tbuf[i] = jc_text(fwd, l_pac, j.lt_start - 1 - i);
+                ref_ksw_extend2(j.lq, qbuf, j.lt, tbuf, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, j.h0, o->left);
+            }
+            if (j.rq > 0) {
+                for (int i = 0; i < j.rt; ++i) tbuf[i] = jc_text(fwd, l_pac, j.rt_start + i);
+                ref_ksw_extend2(j.rq, q + j.qend, j.rt, tbuf, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, j.h0, o->right);
+            }
+        }
+        free(mem.a); free(t0.a); free(t1.a); free(rb); free(qb); free(qe); free(qbuf); free(tbuf);
+    }
 }

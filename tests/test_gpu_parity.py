@@ -226,3 +226,30 @@ def test_extension_rejects_bad_jobs(gpu):
                                                   jobs["qlen"].ctypes.data, jobs["tseq"].ctypes.data, 8, jobs["toff"].ctypes.data,
                                                   jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data, None, None, None, None))
     ex.destroy()
+
+
+# -------------------------------------------------------------------------- fused pipeline
+
+@pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=300, zdrop=0, use_band=0), dict(w=10, zdrop=50)])
+def test_pipeline_matches_oracle(gpu, oracle, dev_index, kw):
+    g, idx, oi = dev_index
+    idx.attach_ref(g)
+    reads, _, _ = synth.make_reads(g, 6000, 150, seed=55, sub_rate=0.02, n_rate=0.001)
+    edge = np.stack([g[:150], synth.revcomp(g[:150]), g[-150:], synth.revcomp(g[-150:])])   # windows clipped at the ends
+    reads = np.concatenate([reads, edge, np.full((2, 150), 4, np.uint8)])
+    n = reads.shape[0]
+    f = reads.reshape(-1).copy()
+    off = (np.arange(n + 1) * 150).astype(np.uint64)
+    want, fc, kc = oracle.pipeline(oi, g, f, off, oracle.make_params(**kw), 19, 500, n_threads=4)
+    packed, woff, rl = gpu.pack_codes(f, off)
+    pl = gpu.Pipeline(idx, n, packed.size, 150)
+    got = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params(**kw))
+    for key in ("seed_rbeg", "seed_qbeg", "seed_qend", "n_seeds", "h0", "left", "right"):
+        bad = np.nonzero((got[key] != want[key]).reshape(n, -1).any(axis=1))[0]
+        assert bad.size == 0, (key, bad[:5], got[key][bad[:5]], want[key][bad[:5]])
+    tot = pl.totals()
+    assert tot["cells"] == kc["cells"] and tot["seeds"] == fc["n_located"]
+    # a second batch through the same pipeline (no reallocation, no stale state)
+    got2 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params(**kw))
+    assert got2.tobytes() == got.tobytes()
+    pl.destroy()
