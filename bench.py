@@ -143,7 +143,7 @@ def run_reference(args, rank, world, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--reads", type=int, default=1_000_000)
@@ -195,14 +195,14 @@ def main():
         pl.run_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
 
     pl.profile(True)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
         pl.sync()
     torch.cuda.synchronize()
     if dref:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = pl.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ktimes = {}
@@ -230,7 +230,6 @@ def main():
     value = world * n * args.steps / (total_ms / 1e3)
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step)
-    h_packed = torch.from_numpy(packed).pin_memory() if False else None
     pin = {}
     for name, arr in (("packed", packed), ("woff", woff), ("rl", rl)):
         tns = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()

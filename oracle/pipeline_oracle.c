@@ -40,6 +40,7 @@ void pipeline_oracle(const fmd_index_t *idx, const uint8_t *fwd, int64_t l_pac,
             read_result_t *o = &out[r];
             memset(o, 0, sizeof(*o));
             o->seed_qbeg = -1; o->seed_rbeg = -1; o->seed_qend = -1;
+            o->left.gscore = -1; o->right.gscore = -1;      /* no extension ran: score = h0 = 0, gscore = -1 */
             if ((size_t)len + 2 > mem_cap) { mem_cap = (size_t)len + 2; mem = (fmd_intv_t *)realloc(mem, mem_cap * sizeof(*mem)); }
             int n = len >= min_seed_len ? fmd_collect_pass1(idx, len, q, min_seed_len, mem, &c) : 0;
             size_t ns = 0;

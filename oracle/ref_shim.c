@@ -167,6 +167,7 @@ void ref_pipeline_batch(void *h, const uint8_t *fwd, int64_t l_pac, const uint8_
             ref_read_result_t *o = &out[r];
             memset(o, 0, sizeof(*o));
             o->seed_qbeg = -1; o->seed_rbeg = -1; o->seed_qend = -1;
+            o->left[4] = -1; o->right[4] = -1;
             size_t ns = 0;
             while (len >= min_seed_len && x < len) {
                 if (q[x] < 4) {
