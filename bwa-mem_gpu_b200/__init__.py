@@ -91,7 +91,7 @@ SYMBOLS = [
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
     "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
-    "bwa_b200_extend_wait", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
+    "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
     "bwa_b200_index_attach_ref", "bwa_b200_pipeline_create", "bwa_b200_pipeline_destroy", "bwa_b200_seed_extend_host",
     "bwa_b200_seed_extend_device", "bwa_b200_pipeline_sync", "bwa_b200_pipeline_stream", "bwa_b200_pipeline_launches",

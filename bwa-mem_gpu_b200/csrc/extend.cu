@@ -27,6 +27,7 @@ struct ExtParams {
     int8_t  mat[32];
     int32_t o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, use_band, pen_clip;
     int32_t max_score;           // max entry of mat (band clamp, src/ksw.c:886-887)
+    int32_t bias;                // -min(mat, 0): scores are kept as unsigned bytes score + bias
 };
 
 constexpr int N_BINS = 7;
@@ -38,14 +39,14 @@ struct JobView {
     const uint32_t *qoff, *qlen, *toff, *tlen, *h0;
 };
 
-// sort key: query length, with jobs whose scores could overflow 16 bits pushed behind bit 20
+// sort key: query length, with jobs whose scores could reach 2^15 pushed behind bit 20
 __global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, uint32_t *keys, uint32_t *vals)
 {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     uint32_t q = qlen[a];
     uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
-    keys[a] = (q > 0xfffffu ? 0xfffffu : q) | (bound >= 65535ull ? (1u << 20) : 0u);
+    keys[a] = (q > 0xfffffu ? 0xfffffu : q) | (bound >= 32767ull ? (1u << 20) : 0u);
     vals[a] = a;
 }
 
@@ -64,27 +65,55 @@ __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *
     if (b == N_BINS && lo < n) atomicExch(err_flag, 2);
 }
 
-__device__ __forceinline__ int sext8(uint32_t lo, uint32_t hi, int qb)
-{ // entry qb (0..4) of a packed 5 x int8 matrix row
-    uint32_t v = qb < 4 ? (lo >> (8 * qb)) : hi;
-    return (int)(int8_t)(v & 0xffu);
-}
+// One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
+// (src/ksw.c:924) is computed as min(H + s, H << 16): for H > 0 the second term is huge, for H == 0
+// it is 0 and M <= 0, which every later use treats exactly like 0 (h = max(M,e,f) with e,f >= 0;
+// t = max(M - oe, 0)).  Scores come from a row of the matrix kept as biased bytes (score + bias) in
+// {mlo, mhi} and are picked with one PRMT whose selector nibble is the query code (the other
+// selector nibbles are neighbouring codes, all < 8, and their bytes are masked off).
+#define EXT_CELL(J, PE)                                                                          \
+    {                                                                                            \
+        const uint32_t p_ = *(PE);                                                               \
+        const int x_ = (int)(p_ << 16);                                                          \
+        const int hh_ = (int)(p_ & 0xffffu), e_ = (int)(p_ >> 16);                               \
+        qw = __funnelshift_l(qw, qw, 4);                                                         \
+        const int scb_ = (int)(__byte_perm(mlo, mhi, qw) & 0xffu);                               \
+        const int M_ = __viaddmin_s32(hh_ + scb_, nbias, x_);                                    \
+        const int h_ = __vimax3_s32(M_, e_, f);                                                  \
+        const uint32_t kj_ = ((uint32_t)h_ << 16) + (uint32_t)(J);                               \
+        key = key > kj_ ? key : kj_;                                                             \
+        const int t1_ = __viaddmax_s32(M_, noe_del, 0);                                          \
+        const int en_ = __viaddmax_s32(e_, ne_del, t1_);                                         \
+        const int t2_ = __viaddmax_s32(M_, noe_ins, 0);                                          \
+        f = __viaddmax_s32(f, ne_ins, t2_);                                                      \
+        *(PE) = (uint32_t)h1 + ((uint32_t)en_ << 16);                                            \
+        h1 = h_;                                                                                 \
+    }
 
-template <bool BYTES>
-__global__ void __launch_bounds__(128)
+template <bool BYTES, int NT>
+__global__ void __launch_bounds__(NT)
 ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
                  int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
                  int *__restrict__ err_flag)
 {
     extern __shared__ uint32_t smem[];
-    const int nt = blockDim.x, tid = threadIdx.x;
-    uint32_t *eh = smem;                                   // [(max_q + 1)][nt]   h | e << 16
-    uint32_t *qs = smem + (size_t)(max_q + 1) * nt;        // [ceil(max_q / 8)][nt] 4-bit codes
+    __shared__ uint32_t smat[10];                          // biased matrix rows: [t] = bytes q0..q3, [5 + t] = byte q4
+    const int tid = threadIdx.x;
+    uint32_t *const ehp = smem + tid;                      // eh[j] = ehp[j * NT]   (h | e << 16)
+    uint32_t *const qsp = smem + (size_t)(max_q + 1) * NT + tid;   // 4-bit query codes, 8 per word
     const uint32_t lo = range[bin], hi = range[bin + 1];
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const int noe_del = -oe_del, noe_ins = -oe_ins, ne_del = -P.e_del, ne_ins = -P.e_ins, nbias = -P.bias;
     unsigned long long my_cells = 0;
+    if (tid < 5) {
+        uint32_t w = 0;
+        for (int q = 0; q < 4; ++q) w |= (uint32_t)(uint8_t)(P.mat[tid * 5 + q] + P.bias) << (8 * q);
+        smat[tid] = w;
+        smat[5 + tid] = (uint32_t)(uint8_t)(P.mat[tid * 5 + 4] + P.bias);
+    }
+    __syncthreads();
 
-    for (uint32_t base = lo + blockIdx.x * nt; base < hi; base += gridDim.x * nt) {
+    for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
         const uint32_t pos = base + tid;
         if (pos < hi) {
             const uint32_t a = order[pos];
@@ -103,16 +132,18 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
                 if (BYTES) {
                     wv = 0;
                     for (int u = 0; u < 8; ++u) { uint32_t c = j8 + u < qlen ? J.qb[qo + j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
-                } else wv = J.qp[(qo + j8) >> 3];
-                qs[(j8 >> 3) * nt + tid] = wv;
+                } else {
+                    wv = J.qp[(qo + j8) >> 3];        // device-packed input: codes 0..4 (bwa_b200_pack_device)
+                }
+                qsp[(j8 >> 3) * NT] = wv;
             }
             // first row: H(-1,-1) = h0, then one gap open, then extensions (src/ksw.c:880-883)
             {
                 int v = h0;
-                eh[tid] = (uint32_t)v;
+                ehp[0] = (uint32_t)v;
                 v = h0 > oe_ins ? h0 - oe_ins : 0;
                 for (int j = 1; j <= qlen; ++j) {
-                    eh[j * nt + tid] = (uint32_t)v;
+                    ehp[j * NT] = (uint32_t)v;
                     v = v > P.e_ins ? v - P.e_ins : 0;
                 }
             }
@@ -137,9 +168,7 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
                     tbv = (int)((tword >> (28 - 4 * (i & 7))) & 15u);
                     tbv = tbv > 4 ? 4 : tbv;
                 }
-                const int8_t *mr = P.mat + tbv * 5;
-                const uint32_t mlo = (uint32_t)(uint8_t)mr[0] | (uint32_t)(uint8_t)mr[1] << 8 | (uint32_t)(uint8_t)mr[2] << 16 | (uint32_t)(uint8_t)mr[3] << 24;
-                const uint32_t mhi = (uint32_t)(uint8_t)mr[4];
+                const uint32_t mlo = smat[tbv], mhi = smat[5 + tbv];
                 if (P.use_band) {
                     if (beg < i - w) beg = i - w;
                     if (end > i + w + 1) end = i + w + 1;
@@ -147,27 +176,30 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
                 }
                 int h1 = 0, f = 0;
                 if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 < 0 ? 0 : h1; }
-                uint32_t key = 0;                      // (row max << 16) | column, last column wins ties
-                uint32_t qw = beg < end ? qs[(beg >> 3) * nt + tid] : 0u;
-                for (int j = beg; j < end; ++j) {
-                    if ((j & 7) == 0) qw = qs[(j >> 3) * nt + tid];
-                    const uint32_t p = eh[j * nt + tid];
-                    int M = (int)(p & 0xffffu), e = (int)(p >> 16);
-                    const int qb = (int)((qw >> (28 - 4 * (j & 7))) & 7u);
-                    const int sc = sext8(mlo, mhi, qb);
-                    M = M ? M + sc : 0;
-                    int h = __vimax3_s32(M, e, f);
-                    const uint32_t kj = ((uint32_t)h << 16) | (uint32_t)j;
-                    key = key > kj ? key : kj;
-                    const int t1 = __viaddmax_s32(M, -oe_del, 0);
-                    const int en = __viaddmax_s32(e, -P.e_del, t1);
-                    const int t2 = __viaddmax_s32(M, -oe_ins, 0);
-                    f = __viaddmax_s32(f, -P.e_ins, t2);
-                    eh[j * nt + tid] = (uint32_t)h1 | ((uint32_t)en << 16);
-                    h1 = h;
+                uint32_t key = 0;                      // (row max << 16) + column, last column wins ties
+                uint32_t qw = 0;
+                int j = beg;
+                uint32_t *pe = ehp + j * NT;
+                // head: up to the next multiple of 8
+                if ((j & 7) && j < end) {
+                    qw = qsp[(j >> 3) * NT];
+                    qw = __funnelshift_l(qw, qw, 4 * (j & 7));
+                    const int stop = min(end, (j | 7) + 1);
+                    for (; j < stop; ++j, pe += NT) EXT_CELL(j, pe)
+                }
+                // whole words of the query: 8 cells per iteration, no bounds checks
+                for (; j + 8 <= end; j += 8, pe += 8 * NT) {
+                    qw = qsp[(j >> 3) * NT];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) EXT_CELL(j + u, pe + u * NT)
+                }
+                // tail
+                if (j < end) {
+                    qw = qsp[(j >> 3) * NT];
+                    for (; j < end; ++j, pe += NT) EXT_CELL(j, pe)
                 }
                 my_cells += (unsigned long long)(end > beg ? end - beg : 0);
-                eh[end * nt + tid] = (uint32_t)h1;     // H(i, end-1); E = 0
+                ehp[end * NT] = (uint32_t)h1;          // H(i, end-1); E = 0
                 const int m = (int)(key >> 16), mj = beg < end ? (int)(key & 0xffffu) : -1;
                 if (end == qlen && beg < end) {        // `j == qlen` after the column loop
                     best_ie = gscore > h1 ? best_ie : i;
@@ -183,11 +215,11 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
                     if (di > dj) { if (best - m - (di - dj) * P.e_del > P.zdrop) break; }
                     else         { if (best - m - (dj - di) * P.e_ins > P.zdrop) break; }
                 }
-                int j = beg;
-                while (j < end && eh[j * nt + tid] == 0u) ++j;
+                j = beg;
+                while (j < end && ehp[j * NT] == 0u) ++j;
                 beg = j;
                 j = end;
-                while (j >= beg && eh[j * nt + tid] == 0u) --j;
+                while (j >= beg && ehp[j * NT] == 0u) --j;
                 end = j + 2 < qlen ? j + 2 : qlen;
             }
             bwa_b200_ext_result_t r;
@@ -291,8 +323,12 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
     B200_CUDA(cudaHostAlloc(&e->h_err, 4, cudaHostAllocDefault));
     *e->h_cells = 0; *e->h_err = 0;
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
     if (rc) return rc;
     rc = ext_grow_seq(e, max_query_bytes ? max_query_bytes : 1024, max_target_bytes ? max_target_bytes : 1024);
@@ -326,6 +362,9 @@ static void to_dev_params(const bwa_b200_ext_params_t *p, ExtParams *d)
     int mx = 0;
     for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
     d->max_score = mx;
+    int mn = 0;
+    for (int i = 0; i < 25; ++i) mn = mn < p->mat[i] ? mn : p->mat[i];
+    d->bias = -mn;
 }
 
 // sort by query length, derive bin ranges, launch one kernel per bin (empty bins exit at once)
@@ -350,32 +389,35 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     for (int b = 0; b < N_BINS; ++b) {
         const int L = bin_hi[b];
         const size_t per_thread = ((size_t)(L + 1) + (size_t)(L + 7) / 8) * 4;
-        int nt = 128;
-        while (nt > 32 && per_thread * nt > (size_t)e->smem_optin / 2) nt -= 32;
+        const int nt = L <= 128 ? 128 : (L <= 256 ? 64 : 32);
         size_t smem = per_thread * nt;
         if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
+        auto kern = nt == 128 ? ext_inter_kernel<BYTES, 128> : (nt == 64 ? ext_inter_kernel<BYTES, 64> : ext_inter_kernel<BYTES, 32>);
         int occ = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ext_inter_kernel<BYTES>, nt, smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
         if (occ < 1) occ = 1;
         uint32_t max_blocks = (n + nt - 1) / nt;
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
         B200_LAUNCH(e->prof, bin_name[b], e->stream,
-            (ext_inter_kernel<BYTES><<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     B200_CUDA(cudaGetLastError());
     return BWA_B200_OK;
 }
 
-extern "C" int bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
-                                     const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
-                                     const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
-                                     const uint32_t *h0, bwa_b200_ext_result_t *res6,
-                                     int32_t *aln_score, int32_t *query_end, int32_t *target_end)
+// host pages -> device, kernels, results -> host; everything asynchronous on e->stream
+extern "C" int bwa_b200_extend_async_paged(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                           const bwa_b200_host_page_t *qpages, int n_qpages, uint64_t q_bytes,
+                                           const uint32_t *qoff, const uint32_t *qlen,
+                                           const bwa_b200_host_page_t *tpages, int n_tpages, uint64_t t_bytes,
+                                           const uint32_t *toff, const uint32_t *tlen,
+                                           const uint32_t *h0, bwa_b200_ext_result_t *res6,
+                                           int32_t *aln_score, int32_t *query_end, int32_t *target_end)
 {
-    if (!e || !p || !qseq || !tseq || !qoff || !qlen || !toff || !tlen || !h0) { b200::set_error("extend_async: null argument"); return BWA_B200_ERR_ARG; }
+    if (!e || !p || !qpages || !tpages || !qoff || !qlen || !toff || !tlen || !h0) { b200::set_error("extend_async: null argument"); return BWA_B200_ERR_ARG; }
     if (n_jobs == 0) { b200::set_error("extend_async: n_jobs == 0"); return BWA_B200_ERR_ARG; }      // gasal_align.cu:32-35
     if (q_bytes == 0 || t_bytes == 0) { b200::set_error("extend_async: empty batch"); return BWA_B200_ERR_ARG; }
     if (n_jobs >= 0x7fffffffull) { b200::set_error("extend_async: too many jobs"); return BWA_B200_ERR_ARG; }
@@ -386,8 +428,16 @@ extern "C" int bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_
     if (rc) return rc;
     const uint32_t n = (uint32_t)n_jobs;
     cudaStream_t st = e->stream;
-    B200_CUDA(cudaMemcpyAsync(e->d_q, qseq, q_bytes, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(e->d_t, tseq, t_bytes, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n_qpages; ++i) {
+        if (!qpages[i].bytes) continue;
+        if (qpages[i].offset + qpages[i].bytes > q_bytes) { b200::set_error("extend_async: query page %d exceeds the batch", i); return BWA_B200_ERR_ARG; }
+        B200_CUDA(cudaMemcpyAsync(e->d_q + qpages[i].offset, qpages[i].data, qpages[i].bytes, cudaMemcpyHostToDevice, st));
+    }
+    for (int i = 0; i < n_tpages; ++i) {
+        if (!tpages[i].bytes) continue;
+        if (tpages[i].offset + tpages[i].bytes > t_bytes) { b200::set_error("extend_async: target page %d exceeds the batch", i); return BWA_B200_ERR_ARG; }
+        B200_CUDA(cudaMemcpyAsync(e->d_t + tpages[i].offset, tpages[i].data, tpages[i].bytes, cudaMemcpyHostToDevice, st));
+    }
     B200_CUDA(cudaMemcpyAsync(e->d_qoff, qoff, n * 4ull, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(e->d_qlen, qlen, n * 4ull, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(e->d_toff, toff, n * 4ull, cudaMemcpyHostToDevice, st));
@@ -408,6 +458,18 @@ extern "C" int bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_
     B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, st));
     e->pending = true;
     return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                     const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                                     const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                                     const uint32_t *h0, bwa_b200_ext_result_t *res6,
+                                     int32_t *aln_score, int32_t *query_end, int32_t *target_end)
+{
+    if (!qseq || !tseq) { b200::set_error("extend_async: null argument"); return BWA_B200_ERR_ARG; }
+    bwa_b200_host_page_t qp{qseq, 0, q_bytes}, tp{tseq, 0, t_bytes};
+    return bwa_b200_extend_async_paged(e, p, n_jobs, &qp, 1, q_bytes, qoff, qlen, &tp, 1, t_bytes, toff, tlen, h0, res6,
+                                       aln_score, query_end, target_end);
 }
 
 extern "C" int bwa_b200_extend_query(bwa_b200_extender_t *e)

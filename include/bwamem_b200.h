@@ -179,6 +179,17 @@ int  bwa_b200_extend_async(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *
                            const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
                            const uint32_t *h0, bwa_b200_ext_result_t *res6,
                            int32_t *aln_score, int32_t *query_end, int32_t *target_end);
+/* same with each sequence buffer given as a list of host pages (the linked pinned pages of
+ * GASAL2's host_batch_t, GASAL2/src/gasal_align.cu:146-169): page i covers batch bytes
+ * [offset, offset + bytes) */
+typedef struct { const uint8_t *data; uint64_t offset, bytes; } bwa_b200_host_page_t;
+int  bwa_b200_extend_async_paged(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                 const bwa_b200_host_page_t *qpages, int n_qpages, uint64_t q_bytes,
+                                 const uint32_t *qoff, const uint32_t *qlen,
+                                 const bwa_b200_host_page_t *tpages, int n_tpages, uint64_t t_bytes,
+                                 const uint32_t *toff, const uint32_t *tlen,
+                                 const uint32_t *h0, bwa_b200_ext_result_t *res6,
+                                 int32_t *aln_score, int32_t *query_end, int32_t *target_end);
 /* 0 = done, 1 = still running (gasal_is_aln_async_done returns 0 / -1) */
 int  bwa_b200_extend_query(bwa_b200_extender_t *e);
 int  bwa_b200_extend_wait(bwa_b200_extender_t *e);
