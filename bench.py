@@ -48,36 +48,62 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """samples SM clock and throttle reasons through NVML while the timed region runs"""
 
     def __init__(self, dev):
-        self.dev, self.rows, self.proc = dev, [], None
+        self.dev, self.rows, self.stop_flag, self.thr = dev, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                for cand in ("GPU-" + uuid, uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.dev)
+            self.nv, self.h = pynvml, h
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception as ex:  # noqa: BLE001
+            log("clock sampler unavailable:", ex)
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        self.stop_flag = True
+        if self.thr:
+            self.thr.join(timeout=1)
+        sm = sorted(r[0] for r in self.rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         for r in self.rows:
-            for i, nm in enumerate(names):
-                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+            for bit, nm in bits.items():
+                if r[2] & bit:
                     reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in self.rows), default=None),
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
@@ -195,14 +221,14 @@ def main():
         pl.run_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
 
     pl.profile(True)
-    sampler = ClockSampler(local)
-    sampler.start()
     for _ in range(args.warmup):
         step_device()
         pl.sync()
     torch.cuda.synchronize()
     if dref:
         dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
     launches0 = pl.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ktimes = {}
@@ -289,6 +315,12 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
                     "algorithmic_bytes_per_read": alg[dom], "ms_per_launch": seed_k[dom], "share_of_step": seed_k[dom] / step_kernel_ms}
+    rs_hbm = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 8 << 30, 64, 3))
+    rs_l2 = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 64 << 20, 64, 3))
+    if roofline:
+        roofline["random_sector_peak_hbm_gbs"] = rs_hbm
+        roofline["random_sector_peak_l2_gbs"] = rs_l2
+        roofline["frac_of_random_sector_hbm"] = roofline["achieved"] / rs_hbm if rs_hbm else None
     ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel"))
     gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
     seed_ms = sum(seed_k.values())

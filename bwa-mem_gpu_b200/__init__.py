@@ -89,7 +89,7 @@ SYMBOLS = [
     "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
     "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
-    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
+    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_measure_random_sector_gbs", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
@@ -135,6 +135,8 @@ def lib():
         L.bwa_b200_seed_device_smems.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         L.bwa_b200_seeder_launches.argtypes = [vp]
         L.bwa_b200_seeder_launches.restype = C.c_uint64
+        L.bwa_b200_measure_random_sector_gbs.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
+        L.bwa_b200_measure_random_sector_gbs.restype = C.c_double
         L.bwa_b200_ext_params_default.argtypes = [C.POINTER(ExtParams)]
         L.bwa_b200_fill_scmat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.bwa_b200_extender_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]

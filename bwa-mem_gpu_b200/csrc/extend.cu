@@ -323,12 +323,15 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
     B200_CUDA(cudaHostAlloc(&e->h_err, 4, cudaHostAllocDefault));
     *e->h_cells = 0; *e->h_err = 0;
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-    B200_CUDA(cudaFuncSetAttribute(ext_inter_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    {   // dynamic shared memory opt-in: device limit minus the kernels' static shared memory
+        cudaFuncAttributes fa;
+        B200_CUDA(cudaFuncGetAttributes(&fa, ext_inter_kernel<true, 128>));
+        e->smem_optin -= (int)fa.sharedSizeBytes + 16;
+        const void *ks[6] = {(const void *)ext_inter_kernel<true, 128>, (const void *)ext_inter_kernel<false, 128>,
+                             (const void *)ext_inter_kernel<true, 64>, (const void *)ext_inter_kernel<false, 64>,
+                             (const void *)ext_inter_kernel<true, 32>, (const void *)ext_inter_kernel<false, 32>};
+        for (const void *k : ks) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+    }
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
     if (rc) return rc;
     rc = ext_grow_seq(e, max_query_bytes ? max_query_bytes : 1024, max_target_bytes ? max_target_bytes : 1024);

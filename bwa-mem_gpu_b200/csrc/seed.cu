@@ -44,7 +44,11 @@ __device__ __forceinline__ Bkt ld_bucket(const uint32_t *bkt, uint64_t b)
 { // one 32-byte sector, one LDG.256 on sm_100
     Bkt r;
     const uint32_t *p = bkt + b * 8;
+#ifdef BKT_LOAD_L1
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
                  : "=r"(r.c[0]), "=r"(r.c[1]), "=r"(r.c[2]), "=r"(r.c[3]), "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
                  : "l"(p));
     return r;
@@ -101,7 +105,14 @@ __device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, ui
 }
 
 // ------------------------------------------------------------------------------- fwd_kernel
-__global__ void __launch_bounds__(FWD_THREADS)
+#ifndef FWD_MIN_BLOCKS
+#define FWD_MIN_BLOCKS 10
+#endif
+#ifndef BACK_MIN_BLOCKS
+#define BACK_MIN_BLOCKS 10
+#endif
+template <typename RowT>
+__global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS)
 fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, uint32_t cand_stride,
            Cand *__restrict__ cand, uint32_t *__restrict__ n_cand)
@@ -114,7 +125,8 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
     uint32_t n_out = 0;
     if (len < min_seed_len) { n_cand[r] = 0; return; }   // mem_chain: read shorter than a seed
 
-    uint64_t k = 0, l = 0;
+    RowT k = 0, l = 0;
+    const RowT primary = (RowT)ix.primary;
     uint32_t s = 0;
     int x = -1, i = 0;
     uint32_t word = 0;
@@ -123,7 +135,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
         if (end >= min_seed_len) { Cand c; c.k = k; c.s = s; c.x = (uint16_t)x; c.end = (uint16_t)end; out[n_out++] = c; }
     };
     auto start_at = [&](int b, int p) {
-        k = L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = L2_at(ix, 3 - b) + 1; x = p; active = true;
+        k = (RowT)L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = (RowT)L2_at(ix, 3 - b) + 1; x = p; active = true;
     };
 
     word = __ldg(packed + woff);
@@ -144,17 +156,18 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
         }
         // forward extension by complement(b): bwt_extend(ik, ok, 0)  (src/bwt.c:455-470)
         const int cb = 3 - b;
-        uint64_t p0 = l - 1, p1 = l - 1 + s;                 // rows; both >= 0
-        uint64_t j0 = p0 - (p0 >= ix.primary), j1 = p1 - (p1 >= ix.primary);
+        RowT p0 = l - 1, p1 = l - 1 + s;                     // rows; both >= 0
+        RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
         Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
-        Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);
+        Bkt b1 = b0;                                         // both ends in one bucket: one sector (src/bwt.c:369)
+        if ((j1 >> 6) != (j0 >> 6)) b1 = ld_bucket(ix.bkt, j1 >> 6);
         uint32_t tk[4], tl[4];
         bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
         bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
         uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
         uint32_t ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
         uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
-        uint64_t nk = k + (uint64_t)(l <= ix.primary && l + s - 1 >= ix.primary);
+        RowT nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
         if (cb < 3) nk += s3;
         if (cb < 2) nk += s2;
         if (cb < 1) nk += s1;
@@ -167,7 +180,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
                 continue;
             }
         }
-        k = nk; l = L2_at(ix, cb) + 1 + tkc; s = ns;
+        k = nk; l = (RowT)L2_at(ix, cb) + 1 + tkc; s = ns;
         ++i;
         if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
     }
@@ -184,7 +197,8 @@ __device__ __forceinline__ uint32_t seeds_of(uint32_t s, int max_occ)
     return cnt < (uint32_t)max_occ ? cnt : (uint32_t)max_occ;
 }
 
-__global__ void __launch_bounds__(BACK_THREADS)
+template <typename RowT>
+__global__ void __launch_bounds__(BACK_THREADS, BACK_MIN_BLOCKS)
 back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
             const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_occ,
             uint32_t cand_stride, Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
@@ -199,7 +213,9 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     bool finished = false, has_read = false, need_cand = true, first = true;
     uint32_t r = 0;
     int slot = -1, cur_x = -1, t = 0, t_head = 0, env_len = 0, x = 0, end = 0;
-    uint64_t woff = 0, ck = 0;
+    uint64_t woff = 0;
+    RowT ck = 0;
+    const RowT primary = (RowT)ix.primary;
     uint32_t cs = 0, acc_smems = 0, acc_seeds = 0;
     Cand *rc = nullptr;
 
@@ -217,7 +233,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 }
                 if (slot < 0) { n_smems[r] = acc_smems; n_seeds[r] = acc_seeds; has_read = false; continue; }
                 Cand c = rc[slot];
-                ck = c.k; cs = c.s; x = c.x; end = c.end;
+                ck = (RowT)c.k; cs = c.s; x = c.x; end = c.end;
                 if (x != cur_x) { cur_x = x; first = true; t_head = 0; env_len = 0; }
                 t = 0;
                 need_cand = false;
@@ -230,17 +246,17 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             int b = 4;
             if (i >= 0) b = read_base(packed, woff, i);
             bool fail = true;
-            uint64_t nk = 0;
+            RowT nk = 0;
             uint32_t ns = 0;
             if (b < 4) {       // backward extension by b: only x[0], x[2] are needed downstream
-                uint64_t p0 = ck - 1, p1 = ck - 1 + cs;
-                uint64_t j0 = p0 - (p0 >= ix.primary), j1 = p1 - (p1 >= ix.primary);
+                RowT p0 = ck - 1, p1 = ck - 1 + cs;
+                RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
                 Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
-                Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);
+                Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);       // unconditional: a same-bucket branch measured slower here
                 uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b);
                 uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b);
                 ns = ol - ok;
-                nk = L2_at(ix, b) + 1 + ok;
+                nk = (RowT)L2_at(ix, b) + 1 + ok;
                 fail = ns == 0;
             }
             if (fail) {
@@ -311,25 +327,28 @@ __global__ void smem_dump_kernel(uint32_t n_reads, uint32_t cand_stride, const C
 }
 
 // ---------------------------------------------------------------------------- locate_kernel
+template <typename RowT>
 __global__ void __launch_bounds__(LOC_THREADS)
 locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long long *__restrict__ total_p,
               uint64_t cap, unsigned long long *__restrict__ next_seed)
 {
     const uint64_t total = min((uint64_t)*total_p, cap);
-    const uint64_t mask = (1ull << ix.sa_shift) - 1;
+    const RowT mask = (RowT)((1ull << ix.sa_shift) - 1), primary = (RowT)ix.primary;
     bool finished = false, need = true;
-    uint64_t idx = 0, k = 0, steps = 0;
+    uint64_t idx = 0;
+    RowT k = 0;
+    uint32_t steps = 0;
     for (;;) {
         if (!finished && need) {
             idx = atomicAdd(next_seed, 1ull);
             if (idx >= total) finished = true;
-            else { k = rbeg[idx]; steps = 0; need = false; }
+            else { k = (RowT)rbeg[idx]; steps = 0; need = false; }
         }
         if (__all_sync(0xffffffffu, finished)) break;
         if (!finished) {
             if ((k & mask) == 0) {
-                uint64_t j = k >> ix.sa_shift, pos;
-                if (j == 0) pos = steps - 1;                         // sa[0] == -1 (bwa_index/bwt.c:160-163)
+                uint64_t j = (uint64_t)(k >> ix.sa_shift), pos;
+                if (j == 0) pos = (uint64_t)steps - 1;                      // sa[0] == -1 (bwa_index/bwt.c:160-163)
                 else {
                     uint64_t hi = 0;
                     if (ix.pack_mask) {
@@ -340,18 +359,34 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
                 }
                 rbeg[idx] = pos;
                 need = true;
-            } else if (k == ix.primary) {                            // bwt_invPsi: row of '$'
+            } else if (k == primary) {                               // bwt_invPsi: row of '$'
                 k = 0; ++steps;
             } else {
-                uint64_t j = k - (k > ix.primary);
+                RowT j = k - (RowT)(k > primary);
                 Bkt b = ld_bucket(ix.bkt, j >> 6);
                 int off = (int)(j & 63);
                 int sym = (int)((b.w[off >> 4] >> ((~off & 15) << 1)) & 3u);
-                k = L2_at(ix, sym) + bucket_occ1(b, off + 1, sym);
+                k = (RowT)L2_at(ix, sym) + bucket_occ1(b, off + 1, sym);
                 ++steps;
             }
         }
     }
+}
+
+// Random 32-byte-sector gather: the roofline denominator for the seeding kernels.
+// Every lane issues `iters` independent 256-bit loads at hashed sector addresses of a buffer.
+__global__ void __launch_bounds__(256)
+random_sector_kernel(const uint32_t *__restrict__ buf, uint64_t n_sectors, int iters, uint32_t *__restrict__ sink)
+{
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        Bkt b = ld_bucket(buf, x % n_sectors);
+        acc += b.c[0] ^ b.w[3];
+    }
+    if (acc == 0x7fffffffu) sink[0] = acc;
 }
 
 __global__ void total_kernel(const uint32_t *n_per, const uint64_t *off, uint32_t n, unsigned long long *total)
@@ -411,11 +446,31 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     B200_CUDA(cudaGetDeviceProperties(&prop, idx->device));
     s->n_sm = prop.multiProcessorCount;
     int occ_b = 0, occ_l = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_kernel, BACK_THREADS, 0));
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel, LOC_THREADS, 0));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_kernel<uint64_t>, BACK_THREADS, 0));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel<uint64_t>, LOC_THREADS, 0));
     s->back_grid = s->n_sm * (occ_b > 0 ? occ_b : 1);
     s->loc_grid = s->n_sm * (occ_l > 0 ? occ_l : 1);
     B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    if (const char *pv = getenv("BWA_B200_L2_PERSIST")) {
+        // keep the occurrence buckets resident in L2 (set-aside + access policy window on this stream)
+        double ratio = atof(pv);
+        if (ratio > 0 && prop.persistingL2CacheMaxSize > 0) {
+            size_t bytes = ((idx->n_words + 7) / 8 * 8 + 8) * 4;
+            size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = (void *)idx->d_bkt;
+            av.accessPolicyWindow.num_bytes = win;
+            double fit = (double)prop.persistingL2CacheMaxSize / (double)win;
+            av.accessPolicyWindow.hitRatio = (float)(ratio * (fit < 1.0 ? fit : 1.0));
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaError_t er = cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            fprintf(stderr, "[b200] L2 persist: window %zu MB, set-aside %d MB, hitRatio %.2f (%s)\n", win >> 20,
+                    prop.persistingL2CacheMaxSize >> 20, av.accessPolicyWindow.hitRatio, cudaGetErrorString(er));
+        }
+    }
     B200_CUDA(cudaMalloc(&s->d_packed, (max_words ? max_words : 1) * 4));
     B200_CUDA(cudaMalloc(&s->d_len, max_reads * 4));
     B200_CUDA(cudaMalloc(&s->d_woff, (max_reads + 1) * 8));
@@ -459,8 +514,12 @@ static int seeder_fill_locate(bwa_b200_seeder *s)
     B200_LAUNCH(s->prof, "fill_kernel", st,
         (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
                                                        s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
-    B200_LAUNCH(s->prof, "locate_kernel", st,
-        (locate_kernel<<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
+    if (ix.seq_len < 0xfffffff0ull)
+        B200_LAUNCH(s->prof, "locate_kernel", st,
+            (locate_kernel<uint32_t><<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
+    else
+        B200_LAUNCH(s->prof, "locate_kernel", st,
+            (locate_kernel<uint64_t><<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
     s->launches += 2;
     B200_CUDA(cudaGetLastError());
     return BWA_B200_OK;
@@ -483,13 +542,22 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     const uint32_t n = (uint32_t)n_reads;
     cudaStream_t st = s->stream;
     B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
-    B200_LAUNCH(s->prof, "fwd_kernel", st,
-        (fwd_kernel<<<(n + FWD_THREADS - 1) / FWD_THREADS, FWD_THREADS, 0, st>>>(
-            ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
-    B200_LAUNCH(s->prof, "back_kernel", st,
-        (back_kernel<<<s->back_grid, BACK_THREADS, 0, st>>>(
-            ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride, s->d_cand, s->d_ncand,
-            s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
+    // 32-bit row arithmetic when every BWT row fits (seq_len < 2^32), 64-bit otherwise (human-sized)
+    const bool narrow = ix.seq_len < 0xfffffff0ull;
+    const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
+    if (narrow) {
+        B200_LAUNCH(s->prof, "fwd_kernel", st,
+            (fwd_kernel<uint32_t><<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+        B200_LAUNCH(s->prof, "back_kernel", st,
+            (back_kernel<uint32_t><<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride,
+                                                                          s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
+    } else {
+        B200_LAUNCH(s->prof, "fwd_kernel", st,
+            (fwd_kernel<uint64_t><<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+        B200_LAUNCH(s->prof, "back_kernel", st,
+            (back_kernel<uint64_t><<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride,
+                                                                          s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
+    }
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     size_t tmp = s->cub_bytes;
     if (s->prof) s->prof->begin("scan", st);
@@ -639,4 +707,33 @@ extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads
     B200_CUDA(cudaMemcpy(host_s, d_s, tot * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_qb); cudaFree(d_qe); cudaFree(d_k); cudaFree(d_s);
     return BWA_B200_OK;
+}
+
+// measured random-sector read throughput in GB/s over a buffer of `bytes` (0 on failure)
+extern "C" double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return 0;
+    uint32_t *buf = nullptr, *sink = nullptr;
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaMalloc(&sink, 4);
+    cudaMemset(buf, 1, bytes);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    int blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+        cudaEventRecord(a);
+        random_sector_kernel<<<blocks, 256>>>(buf, bytes / 32, iters, sink);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double gbs = (double)blocks * 256 * iters * 32.0 / (ms * 1e-3) / 1e9;
+        if (r > 0 && gbs > best) best = gbs;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    return best;
 }

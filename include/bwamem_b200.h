@@ -141,6 +141,9 @@ int  bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads, uint32_t
                                 int32_t *host_qbeg, int32_t *host_qend, uint64_t *host_k, uint64_t *host_s,
                                 uint64_t cap, uint64_t *total);
 uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s);
+/* random 32-byte-sector gather throughput (GB/s) over a scratch buffer of `bytes`: the measured
+ * denominator for the seeding roofline; > L2-sized buffers measure HBM, small ones measure L2 */
+double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps);
 
 /* ----------------------------------------------------------------- extension */
 typedef struct bwa_b200_extender bwa_b200_extender_t;
