@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...);
 
 // Device view of the FMD index, passed by value to kernels (lives in the constant bank).
 struct IndexView {
-    const uint32_t *bkt;     // 32-byte buckets: {cnt[4], sym[4]} per 64 BWT symbols
+    const uint32_t *bkt;     // 32-byte buckets per 64 BWT symbols: {cnt[4], L_lo, L_hi, H_lo, H_hi} (bit planes, see index.cu)
     const uint32_t *sa;      // low 32 bits of the sampled suffix array
     const uint32_t *sa_hi;   // packed high bits
     uint64_t primary, seq_len;

@@ -1,9 +1,11 @@
 // index.cu -- FMD index: file loader, HBM upload, peer replication, host-side builder.
 //
 // File formats are the reference's (bwa_index/bwt.c:461-487 writers; seed_gen.cu:1386-1468
-// readers; bwa_index/bwtindex.c:174-197 bucket layout).  In HBM the bucket array is kept
-// exactly as on disk: 32 bytes = one DRAM/L2 sector per 64 BWT symbols, so every occurrence
-// lookup costs one sector.
+// readers; bwa_index/bwtindex.c:174-197 bucket layout).  In HBM a bucket keeps the file's size and
+// position -- 32 bytes = one DRAM/L2 sector per 64 BWT symbols, so every occurrence lookup costs
+// one sector -- but its 2-bit symbols are re-arranged once, at upload, into two 64-bit bit planes
+// {cnt[4], L_lo, L_hi, H_lo, H_hi}: bit p of L/H = low/high bit of symbol p.  "Occurrences among the
+// first n symbols" then needs one 64-bit mask and 2 POPC per base instead of 4 masked words.
 #include "common.h"
 #include <algorithm>
 #include <cstdarg>
@@ -40,6 +42,22 @@ extern "C" void *bwa_b200_host_alloc(size_t bytes)
 }
 extern "C" void bwa_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// in place: {cnt[4], sym[4]} (symbol i at bits (15-(i&15))*2 of word i>>4) -> {cnt[4], L_lo, L_hi, H_lo, H_hi}
+__global__ void planes_kernel(uint32_t *bkt, uint64_t n_buckets)
+{
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t *w = bkt + b * 8 + 4;
+    uint32_t s[4] = {w[0], w[1], w[2], w[3]};
+    uint32_t L[2] = {0, 0}, H[2] = {0, 0};
+    for (int p = 0; p < 64; ++p) {
+        uint32_t v = (s[p >> 4] >> ((15 - (p & 15)) * 2)) & 3u;
+        L[p >> 5] |= (v & 1u) << (p & 31);
+        H[p >> 5] |= (v >> 1) << (p & 31);
+    }
+    w[0] = L[0]; w[1] = L[1]; w[2] = H[0]; w[3] = H[1];
+}
+
 static int ilog2(uint64_t x) { int r = 0; while ((1ull << r) < x) ++r; return r; }
 
 extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], const uint32_t *bwt_words, uint64_t n_words,
@@ -61,6 +79,12 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
     B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
     B200_CUDA(cudaMemset(idx->d_bkt, 0, padded * 4));
     B200_CUDA(cudaMemcpy(idx->d_bkt, bwt_words, n_words * 4, cudaMemcpyHostToDevice));
+    {
+        uint64_t n_buckets = (seq_len + 63) / 64;
+        planes_kernel<<<(unsigned)((n_buckets + 255) / 256), 256>>>(idx->d_bkt, n_buckets);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaDeviceSynchronize());
+    }
     if (sa) {
         B200_CUDA(cudaMalloc(&idx->d_sa, n_sa * 4));
         B200_CUDA(cudaMemcpy(idx->d_sa, sa, n_sa * 4, cudaMemcpyHostToDevice));

@@ -62,7 +62,7 @@ struct bwa_b200_seeder {
     uint32_t *d_score = nullptr;
     uint64_t seed_cap = 0;
     uint64_t last_n_reads = 0, last_total = 0;
-    int back_grid = 0, loc_grid = 0;
+    int back_grid = 0, loc_grid = 0, fwd_minb = 10, back_minb = 10;
     uint64_t launches = 0;
     bwa_b200_seed_params_t last_p{19, 500};
     b200::Prof *prof = nullptr;

@@ -10,7 +10,8 @@
 //                  (x0 = 0, x_{i+1} = ret(x_i)) as one loop over the read: one bidirectional
 //                  extension (two 32-byte buckets, fetched with one 256-bit load each) per base.
 //                  Every change of interval size is recorded as a candidate (x, end, k, s).
-//   back_kernel    persistent lanes, one read at a time per lane, fetched dynamically.  For each
+//   back_kernel    persistent lanes, one read at a time per lane, claimed per warp and streamed
+//                  through shared memory with cp.async (see the kernel).  For each
 //                  forward segment the candidates are walked backwards longest-first; a per-lane
 //                  "envelope" of the interval sizes of the previous (longer) candidate reproduces
 //                  the `ok[c].x[2] != curr->a[curr->n-1].x[2]` merge test and the
@@ -32,62 +33,78 @@ namespace {
 
 constexpr int FWD_THREADS = 128;
 constexpr int BACK_THREADS = 128;
-constexpr int ENV_SMEM = 24;          // envelope entries kept in shared memory per lane
+constexpr int ENV_SMEM = 12;          // envelope entries kept in shared memory per lane
 constexpr int LOC_THREADS = 128;
 
 using b200::Cand;
 
 // ----------------------------------------------------------------------------- bucket access
-struct Bkt { uint32_t c[4]; uint32_t w[4]; };
+// A bucket is one 32-byte sector: counters of A,C,G,T before its first symbol, then two 64-bit bit
+// planes (bit p of L / H = low / high bit of symbol p), see index.cu.
+struct Bkt { uint32_t c[4]; uint32_t w[4]; };   // w = {L_lo, L_hi, H_lo, H_hi}
 
-__device__ __forceinline__ Bkt ld_bucket(const uint32_t *bkt, uint64_t b)
+// L2 policy for the bucket array: evict_last, so that the streaming traffic of a batch (candidates,
+// reads, seeds) does not push occurrence buckets out of L2 when the index is of the order of the L2 size
+__device__ __forceinline__ uint64_t bucket_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ Bkt ld_bucket(const uint32_t *bkt, uint64_t b, uint64_t pol)
 { // one 32-byte sector, one LDG.256 on sm_100
     Bkt r;
     const uint32_t *p = bkt + b * 8;
-#ifdef BKT_LOAD_L1
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#else
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#endif
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(r.c[0]), "=r"(r.c[1]), "=r"(r.c[2]), "=r"(r.c[3]), "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return r;
 }
 
-// even-bit mask selecting the first n (0..16) symbols of word `wi` when the bucket keeps n_tot
-// symbols; symbol i of a word sits at bits (15-i)*2
-__device__ __forceinline__ uint32_t keep_mask(int n_tot, int wi)
+// second bucket of a lookup pair: loaded under a predicate (no branch, no request when both ends
+// share a bucket) into registers that do not depend on the first load, then selected, so the two
+// sectors of a pair are in flight together
+__device__ __forceinline__ Bkt ld_bucket_or(bool doit, const Bkt &other, const uint32_t *bkt, uint64_t b, uint64_t pol)
 {
-    int sh = 2 * n_tot - 32 * wi;
-    sh = sh < 0 ? 0 : sh;
-    return __funnelshift_rc(0u, 0xffffffffu, (uint32_t)sh) & 0x55555555u;
+    Bkt r;
+    const uint32_t *p = bkt + b * 8;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+                 "mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0; mov.u32 %4, 0; mov.u32 %5, 0; mov.u32 %6, 0; mov.u32 %7, 0;\n\t"
+                 "@q ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %10;\n\t}"
+                 : "=&r"(r.c[0]), "=&r"(r.c[1]), "=&r"(r.c[2]), "=&r"(r.c[3]), "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3])
+                 : "l"(p), "r"((uint32_t)doit), "l"(pol));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r.c[i] = doit ? r.c[i] : other.c[i]; r.w[i] = doit ? r.w[i] : other.w[i]; }
+    return r;
+}
+
+// masks selecting the first n (0..64) symbols of a bucket in the low / high plane words
+__device__ __forceinline__ void first_n(int n, uint32_t &mlo, uint32_t &mhi)
+{
+    mlo = ~__funnelshift_lc(0u, 0xffffffffu, (uint32_t)n);          // n >= 32: all ones
+    mhi = __funnelshift_rc(0xffffffffu, 0u, (uint32_t)(64 - n));    // n <= 32: zero
 }
 
 // occurrences of all four bases among the first n (1..64) symbols of a bucket, plus its counters
 __device__ __forceinline__ void bucket_occ4(const Bkt &b, int n, uint32_t cnt[4])
 {
-    uint32_t a = 0, c = 0, g = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t w = b.w[i], h = w >> 1, m = keep_mask(n, i);
-        a += __popc(~w & ~h & m);
-        c += __popc(w & ~h & m);
-        g += __popc(~w & h & m);
-    }
-    cnt[0] = b.c[0] + a; cnt[1] = b.c[1] + c; cnt[2] = b.c[2] + g;
-    cnt[3] = b.c[3] + ((uint32_t)n - a - c - g);
+    uint32_t mlo, mhi;
+    first_n(n, mlo, mhi);
+    const uint32_t t = __popc(b.w[0] & b.w[2] & mlo) + __popc(b.w[1] & b.w[3] & mhi);
+    const uint32_t g = __popc(~b.w[0] & b.w[2] & mlo) + __popc(~b.w[1] & b.w[3] & mhi);
+    const uint32_t c = __popc(b.w[0] & ~b.w[2] & mlo) + __popc(b.w[1] & ~b.w[3] & mhi);
+    cnt[0] = b.c[0] + ((uint32_t)n - c - g - t); cnt[1] = b.c[1] + c; cnt[2] = b.c[2] + g; cnt[3] = b.c[3] + t;
 }
 
-// occurrences of one base among the first n symbols
-__device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base)
+// occurrences of one base among the first n symbols; nl / nh = all ones where the base's low / high
+// bit is ZERO (so plane ^ mask has a one wherever the plane bit matches the base)
+__device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base, uint32_t nl, uint32_t nh)
 {
-    uint32_t pat = (uint32_t)base * 0x55555555u, r = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t y = b.w[i] ^ pat;
-        r += __popc(~y & ~(y >> 1) & keep_mask(n, i));
-    }
-    uint32_t base_cnt = base == 0 ? b.c[0] : (base == 1 ? b.c[1] : (base == 2 ? b.c[2] : b.c[3]));
+    uint32_t mlo, mhi;
+    first_n(n, mlo, mhi);
+    const uint32_t r = __popc((b.w[0] ^ nl) & ((b.w[2] ^ nh) & mlo)) + __popc((b.w[1] ^ nl) & ((b.w[3] ^ nh) & mhi));
+    const uint32_t base_cnt = base == 0 ? b.c[0] : (base == 1 ? b.c[1] : (base == 2 ? b.c[2] : b.c[3]));
     return base_cnt + r;
 }
 
@@ -98,21 +115,12 @@ __device__ __forceinline__ uint64_t L2_at(const IndexView &ix, int b)
     return b == 0 ? ix.L2[0] : (b == 1 ? ix.L2[1] : (b == 2 ? ix.L2[2] : (b == 3 ? ix.L2[3] : ix.L2[4])));
 }
 
-__device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, uint64_t woff, int i)
-{
-    uint32_t w = __ldg(packed + woff + (uint32_t)(i >> 3));
-    return (int)((w >> (28 - 4 * (i & 7))) & 15u);
-}
-
 // ------------------------------------------------------------------------------- fwd_kernel
 #ifndef FWD_MIN_BLOCKS
-#define FWD_MIN_BLOCKS 10
+#define FWD_MIN_BLOCKS 8        // measured on B200 (C2): 8 -> 1.41 ms, 10 -> 1.64 ms, 16 -> 2.05 ms (spills)
 #endif
-#ifndef BACK_MIN_BLOCKS
-#define BACK_MIN_BLOCKS 10
-#endif
-template <typename RowT>
-__global__ void __launch_bounds__(FWD_THREADS, FWD_MIN_BLOCKS)
+template <typename RowT, int MINB>
+__global__ void __launch_bounds__(FWD_THREADS, MINB)
 fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, uint32_t cand_stride,
            Cand *__restrict__ cand, uint32_t *__restrict__ n_cand)
@@ -127,12 +135,14 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
 
     RowT k = 0, l = 0;
     const RowT primary = (RowT)ix.primary;
+    const uint64_t pol = bucket_policy();
     uint32_t s = 0;
     int x = -1, i = 0;
     uint32_t word = 0;
     bool active = false;
     auto push = [&](int end) {
-        if (end >= min_seed_len) { Cand c; c.k = k; c.s = s; c.x = (uint16_t)x; c.end = (uint16_t)end; out[n_out++] = c; }
+        if (end >= min_seed_len)     // streaming store: candidates are read back once, by back_kernel
+            __stcs(reinterpret_cast<uint4 *>(out + n_out++), make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)x | (uint32_t)end << 16));
     };
     auto start_at = [&](int b, int p) {
         k = (RowT)L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = (RowT)L2_at(ix, 3 - b) + 1; x = p; active = true;
@@ -158,9 +168,8 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
         const int cb = 3 - b;
         RowT p0 = l - 1, p1 = l - 1 + s;                     // rows; both >= 0
         RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-        Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
-        Bkt b1 = b0;                                         // both ends in one bucket: one sector (src/bwt.c:369)
-        if ((j1 >> 6) != (j0 >> 6)) b1 = ld_bucket(ix.bkt, j1 >> 6);
+        Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
+        const Bkt b1 = ld_bucket_or((j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
         uint32_t tk[4], tl[4];
         bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
         bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
@@ -197,87 +206,170 @@ __device__ __forceinline__ uint32_t seeds_of(uint32_t s, int max_occ)
     return cnt < (uint32_t)max_occ ? cnt : (uint32_t)max_occ;
 }
 
-template <typename RowT>
-__global__ void __launch_bounds__(BACK_THREADS, BACK_MIN_BLOCKS)
+__device__ __forceinline__ uint4 ld_cand(const Cand *p)
+{ // {k.lo, k.hi, s, x | end << 16}
+    return *reinterpret_cast<const uint4 *>(p);       // plain load: the array is rewritten in place by this kernel
+}
+
+#ifndef BACK_MIN_BLOCKS
+#define BACK_MIN_BLOCKS 10
+#endif
+// Work distribution.  A read has one candidate per change of interval size (~30 for a 150 bp read)
+// and each is walked only a few steps, so a lane moves to its next candidate every few iterations.
+// None of those moves may wait on global memory:
+//  * per lane, candidates stream through a 4-entry shared-memory ring filled by cp.async four
+//    candidates ahead of use (cp.async has no destination register, so nothing is waited for
+//    until cp.async.wait_group, by which time the copy has long landed);
+//  * per warp, reads are claimed QG at a time in converged code (one queue atomic per claim) and their
+//    n_cand, word_off and last four candidates are staged in a second ring, so a lane that runs out
+//    of work finds its next read on chip;
+//  * the read word under the pivot is kept per segment (all candidates of a segment start there).
+constexpr int QS = 32;                // claimed reads per warp (ring of {r, n_cand, word_off})
+constexpr int QG = 16;                // reads claimed per refill
+constexpr int KC = 4;                 // per-lane candidate ring / prefetch distance
+constexpr int POP_DELAY = 2;          // iterations a lane sits out after taking a read, while its first candidates land
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");   // .cg: no L1 allocation
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename RowT, int MINB>
+__global__ void __launch_bounds__(BACK_THREADS, MINB)
 back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
-            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_occ,
+            uint32_t n_reads, int min_seed_len, int max_occ,
             uint32_t cand_stride, Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
             uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds,
             uint32_t *__restrict__ env_spill, uint32_t env_stride, unsigned long long *__restrict__ next_read)
 {
     __shared__ uint32_t env_s[ENV_SMEM][BACK_THREADS];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + tid;
-    uint32_t *env_g = env_spill + gtid * env_stride;     // steps >= ENV_SMEM (rare)
+    __shared__ uint4 ring[BACK_THREADS / 32][QS];        // {r, n_cand, word_off, -}
+    __shared__ uint4 mine[KC][BACK_THREADS];             // candidate ring of each lane, entry = slot & (KC-1)
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t gtid = blockIdx.x * blockDim.x + tid;
+    uint4 *const q = ring[tid >> 5];
+    const RowT primary = (RowT)ix.primary;
+    const uint64_t pol = bucket_policy();
+
+    // warp-uniform queue state: slots [head, tail) hold claimed reads
+    uint32_t head = 0, tail = 0;
+    bool exhausted = false;
 
     bool finished = false, has_read = false, need_cand = true, first = true;
-    uint32_t r = 0;
-    int slot = -1, cur_x = -1, t = 0, t_head = 0, env_len = 0, x = 0, end = 0;
-    uint64_t woff = 0;
+    uint32_t r = 0, woff = 0;
+    int slot = -1, cur_x = -1, t = 0, t_head = 0, x = 0, end = 0, delay = 0;
     RowT ck = 0;
-    const RowT primary = (RowT)ix.primary;
-    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0;
-    Cand *rc = nullptr;
+    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0, bw = 0, bw0 = 0;
 
     for (;;) {
-        if (!finished && need_cand) {
-            for (;;) {
-                if (!has_read) {
-                    r = (uint32_t)atomicAdd(next_read, 1ull);
-                    if (r >= n_reads) { finished = true; break; }
-                    slot = (int)n_cand[r] - 1;
-                    cur_x = -1; acc_smems = 0; acc_seeds = 0;
-                    woff = word_off[r];
-                    rc = cand + (uint64_t)r * cand_stride;
-                    has_read = true;
-                }
-                if (slot < 0) { n_smems[r] = acc_smems; n_seeds[r] = acc_seeds; has_read = false; continue; }
-                Cand c = rc[slot];
-                ck = (RowT)c.k; cs = c.s; x = c.x; end = c.end;
-                if (x != cur_x) { cur_x = x; first = true; t_head = 0; env_len = 0; }
-                t = 0;
-                need_cand = false;
-                break;
+        // ---------------- converged: claim reads for the warp, hand them to the lanes that need one
+        if (!exhausted && tail - head <= (uint32_t)(QS - QG)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next_read, (unsigned long long)QG);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < QG) {
+                const unsigned long long rr = base + lane;
+                uint4 m = make_uint4(0xffffffffu, 0, 0, 0);
+                if (rr < n_reads) m = make_uint4((uint32_t)rr, n_cand[rr], (uint32_t)word_off[rr], 0);
+                q[(tail + lane) & (QS - 1)] = m;
+            }
+            tail += QG;
+            if (base + QG >= n_reads) exhausted = true;
+            __syncwarp();
+        }
+        {
+            const bool need = !finished && !has_read;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, need);
+            if (ballot) {
+                const uint32_t cnt = __popc(ballot), avail = tail - head, rank = __popc(ballot & ((1u << lane) - 1u));
+                if (need && rank < avail) {
+                    const uint4 m = q[(head + rank) & (QS - 1)];
+                    r = m.x;
+                    if (r == 0xffffffffu) finished = true;
+                    else {
+                        woff = m.z;
+                        slot = (int)m.y - 1;
+                        const Cand *src = cand + (uint64_t)r * cand_stride;
+#pragma unroll
+                        for (int j = 0; j < KC; ++j)
+                            if (slot - j >= 0) cp_async16(&mine[(slot - j) & (KC - 1)][tid], src + (slot - j));
+                        cp_async_commit();
+#pragma unroll
+                        for (int j = 1; j < KC; ++j) cp_async_commit();   // empty groups: this one is now KC groups old
+                        cur_x = -1; acc_smems = 0; acc_seeds = 0;
+                        has_read = true; need_cand = true; delay = POP_DELAY;
+                    }
+                } else if (need && exhausted) finished = true;   // nothing claimed, nothing coming
+                head += cnt < avail ? cnt : avail;
+                __syncwarp();                             // ring slots are read before a later claim rewrites them
             }
         }
         if (__all_sync(0xffffffffu, finished)) break;
-        if (!finished) {
+        if (delay > 0) { --delay; continue; }
+
+        // ---------------- per lane: next candidate of the current read
+        if (has_read && need_cand) {
+            if (slot < 0) { n_smems[r] = acc_smems; n_seeds[r] = acc_seeds; has_read = false; }
+            else {
+                cp_async_wait_group<KC - 1>();            // the copy for `slot` is at least KC groups old (or the read's first group)
+                uint4 *const m = &mine[slot & (KC - 1)][tid];
+                const uint4 c = *m;
+                if (slot >= KC) cp_async16(m, cand + (uint64_t)r * cand_stride + (slot - KC));
+                cp_async_commit();
+                ck = (RowT)(((uint64_t)c.y << 32) | c.x); cs = c.z; x = (int)(c.w & 0xffffu); end = (int)(c.w >> 16);
+                if (x != cur_x) {
+                    cur_x = x; first = true; t_head = 0;
+                    if (x > 0) bw0 = __ldg(packed + ((uint64_t)woff + ((uint32_t)(x - 1) >> 3)));
+                }
+                t = 0; bw = bw0;
+                need_cand = false;
+            }
+        }
+        // ---------------- per lane: one backward extension
+        if (has_read && !need_cand) {
             const int i = x - 1 - t;
             int b = 4;
-            if (i >= 0) b = read_base(packed, woff, i);
+            if (i >= 0) b = (int)((bw >> (28 - 4 * (i & 7))) & 15u);
             bool fail = true;
             RowT nk = 0;
             uint32_t ns = 0;
             if (b < 4) {       // backward extension by b: only x[0], x[2] are needed downstream
-                RowT p0 = ck - 1, p1 = ck - 1 + cs;
-                RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-                Bkt b0 = ld_bucket(ix.bkt, j0 >> 6);
-                Bkt b1 = ld_bucket(ix.bkt, j1 >> 6);       // unconditional: a same-bucket branch measured slower here
-                uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b);
-                uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b);
+                const RowT p0 = ck - 1, p1 = ck - 1 + cs;
+                const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+                const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
+                const Bkt b0 = ld_bucket_or((j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
+                const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
+                const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
+                const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
                 ns = ol - ok;
                 nk = (RowT)L2_at(ix, b) + 1 + ok;
                 fail = ns == 0;
             }
+            Cand *const rcs = cand + (uint64_t)r * cand_stride + slot;
+            uint32_t *const env_g = env_spill + (uint64_t)gtid * env_stride;     // steps >= ENV_SMEM (rare)
             if (fail) {
                 // candidate stops after t steps: SMEM iff no longer match of this segment stopped here
-                Cand o; o.k = ck; o.s = 0; o.x = (uint16_t)(x - t); o.end = (uint16_t)end;
+                uint32_t os = 0;
                 if (first || t > t_head) {
-                    if (end - (x - t) >= min_seed_len) { o.s = cs; ++acc_smems; acc_seeds += seeds_of(cs, max_occ); }
-                    t_head = t; env_len = t; first = false;
+                    if (end - (x - t) >= min_seed_len) { os = cs; ++acc_smems; acc_seeds += seeds_of(cs, max_occ); }
+                    t_head = t; first = false;           // the envelope now covers steps [0, t)
                 }
-                rc[slot] = o;
+                __stcs(reinterpret_cast<uint4 *>(rcs), make_uint4((uint32_t)ck, (uint32_t)((uint64_t)ck >> 32), os, (uint32_t)(x - t) | (uint32_t)end << 16));
                 --slot; need_cand = true;
             } else {
                 uint32_t prev = 0;
-                if (t < env_len) prev = t < ENV_SMEM ? env_s[t][tid] : env_g[t - ENV_SMEM];
-                if (t < env_len && prev == ns) {        // same interval as the longer match: contained
-                    Cand o; o.k = ck; o.s = 0; o.x = (uint16_t)x; o.end = (uint16_t)end;
-                    rc[slot] = o;
+                if (t < t_head) prev = t < ENV_SMEM ? env_s[t][tid] : env_g[t - ENV_SMEM];
+                if (t < t_head && prev == ns) {         // same interval as the longer match: contained
+                    __stcs(reinterpret_cast<uint4 *>(rcs), make_uint4((uint32_t)ck, (uint32_t)((uint64_t)ck >> 32), 0u, (uint32_t)x | (uint32_t)end << 16));
                     --slot; need_cand = true;
                 } else {
                     if (t < ENV_SMEM) env_s[t][tid] = ns; else env_g[t - ENV_SMEM] = ns;
                     ck = nk; cs = ns; ++t;
+                    if ((i & 7) == 0 && i > 0) bw = __ldg(packed + ((uint64_t)woff + ((uint32_t)(i - 1) >> 3)));   // previous word of the read
                 }
             }
         }
@@ -334,6 +426,7 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
 {
     const uint64_t total = min((uint64_t)*total_p, cap);
     const RowT mask = (RowT)((1ull << ix.sa_shift) - 1), primary = (RowT)ix.primary;
+    const uint64_t pol = bucket_policy();
     bool finished = false, need = true;
     uint64_t idx = 0;
     RowT k = 0;
@@ -363,10 +456,11 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
                 k = 0; ++steps;
             } else {
                 RowT j = k - (RowT)(k > primary);
-                Bkt b = ld_bucket(ix.bkt, j >> 6);
-                int off = (int)(j & 63);
-                int sym = (int)((b.w[off >> 4] >> ((~off & 15) << 1)) & 3u);
-                k = (RowT)L2_at(ix, sym) + bucket_occ1(b, off + 1, sym);
+                Bkt b = ld_bucket(ix.bkt, j >> 6, pol);
+                const int off = (int)(j & 63);
+                const uint32_t lw = off < 32 ? b.w[0] : b.w[1], hw = off < 32 ? b.w[2] : b.w[3];
+                const int sym = (int)(((lw >> (off & 31)) & 1u) | (((hw >> (off & 31)) & 1u) << 1));
+                k = (RowT)L2_at(ix, sym) + bucket_occ1(b, off + 1, sym, (sym & 1) ? 0u : 0xffffffffu, (sym & 2) ? 0u : 0xffffffffu);
                 ++steps;
             }
         }
@@ -380,10 +474,11 @@ random_sector_kernel(const uint32_t *__restrict__ buf, uint64_t n_sectors, int i
 {
     uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
+    const uint64_t pol = bucket_policy();
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
         x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-        Bkt b = ld_bucket(buf, x % n_sectors);
+        Bkt b = ld_bucket(buf, x % n_sectors, pol);
         acc += b.c[0] ^ b.w[3];
     }
     if (acc == 0x7fffffffu) sink[0] = acc;
@@ -395,6 +490,21 @@ __global__ void total_kernel(const uint32_t *n_per, const uint64_t *off, uint32_
 }
 
 struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
+
+using FwdFn = void (*)(IndexView, const uint32_t *, const uint64_t *, const uint32_t *, uint32_t, int, uint32_t, Cand *, uint32_t *);
+using BackFn = void (*)(IndexView, const uint32_t *, const uint64_t *, uint32_t, int, int, uint32_t, Cand *, const uint32_t *, uint32_t *,
+                        uint32_t *, uint32_t *, uint32_t, unsigned long long *);
+// register budget variants (blocks of 128 lanes per SM): more resident lanes = more sectors in flight
+FwdFn fwd_variant(bool narrow, int minb)
+{
+    if (narrow) return minb >= 16 ? fwd_kernel<uint32_t, 16> : (minb >= 12 ? fwd_kernel<uint32_t, 12> : (minb >= 10 ? fwd_kernel<uint32_t, 10> : fwd_kernel<uint32_t, 8>));
+    return minb >= 16 ? fwd_kernel<uint64_t, 16> : (minb >= 12 ? fwd_kernel<uint64_t, 12> : (minb >= 10 ? fwd_kernel<uint64_t, 10> : fwd_kernel<uint64_t, 8>));
+}
+BackFn back_variant(bool narrow, int minb)
+{
+    if (narrow) return minb >= 16 ? back_kernel<uint32_t, 16> : (minb >= 12 ? back_kernel<uint32_t, 12> : (minb >= 10 ? back_kernel<uint32_t, 10> : back_kernel<uint32_t, 8>));
+    return minb >= 16 ? back_kernel<uint64_t, 16> : (minb >= 12 ? back_kernel<uint64_t, 12> : (minb >= 10 ? back_kernel<uint64_t, 10> : back_kernel<uint64_t, 8>));
+}
 
 } // namespace
 
@@ -437,7 +547,8 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
                                       bwa_b200_seeder_t **out)
 {
     if (!idx || !out || max_reads == 0) { b200::set_error("seeder_create: bad argument"); return BWA_B200_ERR_ARG; }
-    if (max_reads >= 0xffffffffull) { b200::set_error("seeder_create: at most 2^32-2 reads per batch"); return BWA_B200_ERR_ARG; }
+    if (max_reads > 0x80000000ull) { b200::set_error("seeder_create: at most 2^31 reads per batch"); return BWA_B200_ERR_ARG; }
+    if (max_words >= 0xffffffffull) { b200::set_error("seeder_create: at most 2^32-2 packed words (32 G bases) per batch"); return BWA_B200_ERR_ARG; }
     B200_CUDA(cudaSetDevice(idx->device));
     bwa_b200_seeder *s = new bwa_b200_seeder();
     s->idx = idx; s->device = idx->device;
@@ -446,7 +557,10 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     B200_CUDA(cudaGetDeviceProperties(&prop, idx->device));
     s->n_sm = prop.multiProcessorCount;
     int occ_b = 0, occ_l = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_kernel<uint64_t>, BACK_THREADS, 0));
+    s->fwd_minb = getenv("BWA_B200_FWD_MINB") ? atoi(getenv("BWA_B200_FWD_MINB")) : FWD_MIN_BLOCKS;
+    s->back_minb = getenv("BWA_B200_BACK_MINB") ? atoi(getenv("BWA_B200_BACK_MINB")) : BACK_MIN_BLOCKS;
+    const bool narrow_rows = idx->v.seq_len < 0xfffffff0ull;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_variant(narrow_rows, s->back_minb), BACK_THREADS, 0));
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel<uint64_t>, LOC_THREADS, 0));
     s->back_grid = s->n_sm * (occ_b > 0 ? occ_b : 1);
     s->loc_grid = s->n_sm * (occ_l > 0 ? occ_l : 1);
@@ -545,19 +659,11 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     // 32-bit row arithmetic when every BWT row fits (seq_len < 2^32), 64-bit otherwise (human-sized)
     const bool narrow = ix.seq_len < 0xfffffff0ull;
     const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
-    if (narrow) {
-        B200_LAUNCH(s->prof, "fwd_kernel", st,
-            (fwd_kernel<uint32_t><<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
-        B200_LAUNCH(s->prof, "back_kernel", st,
-            (back_kernel<uint32_t><<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride,
-                                                                          s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
-    } else {
-        B200_LAUNCH(s->prof, "fwd_kernel", st,
-            (fwd_kernel<uint64_t><<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
-        B200_LAUNCH(s->prof, "back_kernel", st,
-            (back_kernel<uint64_t><<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, p->max_occ, s->cand_stride,
-                                                                          s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
-    }
+    B200_LAUNCH(s->prof, "fwd_kernel", st,
+        (fwd_variant(narrow, s->fwd_minb)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+    B200_LAUNCH(s->prof, "back_kernel", st,
+        (back_variant(narrow, s->back_minb)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, n, p->min_seed_len, p->max_occ, s->cand_stride,
+                                                                                  s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     size_t tmp = s->cub_bytes;
     if (s->prof) s->prof->begin("scan", st);
