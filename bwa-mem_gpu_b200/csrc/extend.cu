@@ -19,50 +19,49 @@
 // memory, no band, zdrop = 0, fixed clip penalty): band, z-drop, end bonus and separate
 // insertion/deletion penalties are honoured, and all six outputs are returned.
 #include "internal.h"
+#include "ext_simd_core.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
-struct ExtParams {
-    int8_t  mat[32];
-    int32_t o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, use_band, pen_clip;
-    int32_t max_score;           // max entry of mat (band clamp, src/ksw.c:886-887)
-    int32_t bias;                // -min(mat, 0): scores are kept as unsigned bytes score + bias
-};
-
 constexpr int N_BINS = 7;
 __constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
 
-struct JobView {
-    const uint8_t  *qb, *tb;     // byte-per-base sequences (BYTES) ...
-    const uint32_t *qp, *tp;     // ... or 4-bit packed (offsets in bases, multiples of 8)
-    const uint32_t *qoff, *qlen, *toff, *tlen, *h0;
-};
+constexpr int SIMD_MAX_Q = 512;          // longest query the two-row kernel stages (shared memory)
+constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
+constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
 
-// sort key: query length, with jobs whose scores could reach 2^15 pushed behind bit 20
-__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, uint32_t *keys, uint32_t *vals)
+// sort key: query length; bit 19 = not eligible for the two-row s16x2 kernel (score bound above 1023, query too
+// long, or a matrix that is not match/mismatch/N shaped); bit 20 = scores could reach 2^15
+__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, int simd_ok, uint32_t *keys, uint32_t *vals)
 {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     uint32_t q = qlen[a];
     uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
-    keys[a] = (q > 0xfffffu ? 0xfffffu : q) | (bound >= 32767ull ? (1u << 20) : 0u);
+    uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
+    if (!simd_ok || bound > 1023ull || q > (uint32_t)SIMD_MAX_Q) k |= CLS_BIT;
+    if (bound >= 32767ull) k |= BAD_BIT;
+    keys[a] = k;
     vals[a] = a;
 }
 
-// bin b of the narrow class covers sorted positions [range[b], range[b+1]); range[N_BINS+1] = n
+// Sorted positions of the bin boundaries.  range[0..N_BINS] bound the bins of the two-row kernel (bin b =
+// [range[b], range[b+1])), range[N_BINS+1 .. 2*N_BINS+1] those of the 32-bit kernel.
 __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag)
 {
-    int b = threadIdx.x;
-    if (b > N_BINS + 1) return;
-    // first position whose key exceeds the bin's upper bound
-    uint32_t bound = b == 0 ? 0u : (b <= N_BINS ? (uint32_t)c_bin_hi[b - 1] : 0xffffffffu);
+    const int k = threadIdx.x;
+    if (k > 2 * N_BINS + 1) return;
+    // first position whose key is >= thr
+    uint32_t thr;
+    if (k <= N_BINS) thr = k == 0 ? 0u : (uint32_t)c_bin_hi[k - 1] + 1u;
+    else thr = CLS_BIT | (k == N_BINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_BINS - 2] + 1u);
     uint32_t lo = 0, hi = n;
-    if (b == 0) { range[0] = 0; return; }
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] <= bound) lo = mid + 1; else hi = mid; }
-    range[b] = lo;
-    // anything past the last bin (query > 1024 or scores beyond 16 bits) is not handled by this kernel
-    if (b == N_BINS && lo < n) atomicExch(err_flag, 2);
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < thr) lo = mid + 1; else hi = mid; }
+    range[k] = lo;
+    // anything between the last bin of a class and the next class (query > 1024), or with the bad bit, is not handled
+    if (k == N_BINS) { uint32_t l2 = 0, h2 = n; while (l2 < h2) { uint32_t mid = (l2 + h2) >> 1; if (sorted_keys[mid] < CLS_BIT) l2 = mid + 1; else h2 = mid; } if (lo < l2) atomicExch(err_flag, 2); }
+    if (k == 2 * N_BINS + 1 && lo < n) atomicExch(err_flag, 2);
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -232,6 +231,41 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     if ((tid & 31) == 0 && my_cells) atomicAdd(cells_total, my_cells);
 }
 
+// ext_simd_kernel: two target rows per lane in the halves of s16x2 registers (ext_simd_core.cuh); one warp per block
+template <bool BYTES>
+__global__ void __launch_bounds__(32)
+ext_simd_kernel(ExtParams P, SimdParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
+                int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
+                int *__restrict__ err_flag)
+{
+    constexpr int NT = 32;
+    extern __shared__ uint32_t smem[];
+    const int tid = threadIdx.x;
+    uint32_t *const Bp = smem + tid;                                   // B[j] = Bp[j * NT]
+    uint32_t *const Ap = smem + (size_t)(max_q + 1) * NT + tid;        // A[j]
+    uint8_t *const Qp = reinterpret_cast<uint8_t *>(smem + (size_t)2 * (max_q + 1) * NT) + tid;   // shaped query bytes
+    const uint32_t lo = range[bin], hi = range[bin + 1];
+    unsigned long long my_cells = 0;
+    for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
+        const uint32_t pos = base + tid;
+        if (pos < hi) {
+            const uint32_t a = order[pos];
+            const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
+            bwa_b200_ext_result_t r;
+            if (qlen == 0) {               // absent job (pipeline slots): ksw_extend2 is never called, score stays h0
+                r.score = h0; r.qle = 0; r.tle = 0; r.gtle = 0; r.gscore = -1; r.max_off = 0;
+                res[a] = r;
+                continue;
+            }
+            if (qlen > max_q || h0 < 1) { atomicExch(err_flag, 1); continue; }
+            simd_job<BYTES, NT>(P, S, J, a, qlen, tlen, h0, Bp, Ap, Qp, r, my_cells);
+            res[a] = r;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, o);
+    if ((tid & 31) == 0 && my_cells) atomicAdd(cells_total, my_cells);
+}
+
 // (score, qend, tend) after the local-vs-to-end rule (src/bwamem.c:1892-1901)
 __global__ void triple_kernel(uint32_t n, const bwa_b200_ext_result_t *res, const uint32_t *qlen, int pen_clip,
                               int32_t *score, int32_t *qend, int32_t *tend)
@@ -315,7 +349,7 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     e->n_sm = prop.multiProcessorCount;
     e->smem_optin = (int)prop.sharedMemPerBlockOptin;
     B200_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaMalloc(&e->d_range, (N_BINS + 2) * 4));
+    B200_CUDA(cudaMalloc(&e->d_range, (2 * N_BINS + 2) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
     B200_CUDA(cudaMemset(e->d_cells, 0, 8));
@@ -331,6 +365,8 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
                              (const void *)ext_inter_kernel<true, 64>, (const void *)ext_inter_kernel<false, 64>,
                              (const void *)ext_inter_kernel<true, 32>, (const void *)ext_inter_kernel<false, 32>};
         for (const void *k : ks) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+        B200_CUDA(cudaFuncSetAttribute((const void *)ext_simd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+        B200_CUDA(cudaFuncSetAttribute((const void *)ext_simd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
     }
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
     if (rc) return rc;
@@ -380,7 +416,13 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     to_dev_params(p, &P);
     B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
     if (e->prof) e->prof->begin("ext_sort", e->stream);
-    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, e->d_keys, e->d_vals);
+    // the two-row s16x2 kernel needs a matrix of the form {a on the diagonal, one mismatch score, one score for N}
+    // (bwa_fill_scmat, src/bwa.c) with 0 < a <= 31; any other matrix runs entirely in the 32-bit kernel
+    SimdParams S;
+    memset(&S, 0, sizeof(S));
+    int simd_ok = simd_params_from(p, &S);
+    if (getenv("BWA_B200_EXT_NO_SIMD")) simd_ok = 0;
+    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, e->d_keys, e->d_vals);
     size_t tmp = e->cub_bytes;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
     range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err);
@@ -389,6 +431,26 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
     static const char *bin_name[N_BINS] = {"ext_inter_kernel_q16", "ext_inter_kernel_q32", "ext_inter_kernel_q64", "ext_inter_kernel_q128",
                                            "ext_inter_kernel_q256", "ext_inter_kernel_q512", "ext_inter_kernel_q1024"};
+    static const char *simd_name[N_BINS] = {"ext_simd_kernel_q16", "ext_simd_kernel_q32", "ext_simd_kernel_q64", "ext_simd_kernel_q128",
+                                            "ext_simd_kernel_q256", "ext_simd_kernel_q512", ""};
+    // two-row s16x2 kernel: one warp per block, bins up to SIMD_MAX_Q
+    for (int b = 0; b < N_BINS && simd_ok && bin_hi[b] <= SIMD_MAX_Q; ++b) {
+        const int L = bin_hi[b];
+        const size_t smem = ((size_t)2 * (L + 1) * 4 + (size_t)(L + 4)) * 32;
+        if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
+        auto kern = ext_simd_kernel<BYTES>;
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+        if (occ < 1) occ = 1;
+        uint32_t max_blocks = (n + 31) / 32;
+        uint32_t grid = (uint32_t)(e->n_sm * occ);
+        if (grid > max_blocks) grid = max_blocks;
+        if (grid < 1) grid = 1;
+        B200_LAUNCH(e->prof, simd_name[b], e->stream,
+            (kern<<<grid, 32, smem, e->stream>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        e->launches += 1;
+    }
+    // 32-bit kernel for everything else
     for (int b = 0; b < N_BINS; ++b) {
         const int L = bin_hi[b];
         const size_t per_thread = ((size_t)(L + 1) + (size_t)(L + 7) / 8) * 4;
@@ -404,7 +466,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
         B200_LAUNCH(e->prof, bin_name[b], e->stream,
-            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range + (N_BINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     B200_CUDA(cudaGetLastError());

@@ -1,0 +1,72 @@
+// Host build of the two-row s16x2 extension (bwa-mem_gpu_b200/csrc/ext_simd_core.cuh) with the five
+// integer intrinsics it uses emulated in plain C++.  TEST INFRASTRUCTURE: lets the exact kernel
+// source be fuzzed against the oracle on the CPU box (tests/test_ext_simd_host.py); never shipped
+// and never used as a compute path.
+//   g++ -O2 -shared -fPIC -I include -I bwa-mem_gpu_b200/csrc tests/host_emul/ext_simd_host.cpp -o tests/host_emul/libextsimd_host.so
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+// prmt.b32, generic mode (PTX ISA): selector bit 3 replicates the sign of the selected byte
+static inline uint32_t b200_prmt(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t v = (uint64_t)y << 32 | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xfu;
+        uint32_t b = (uint32_t)(v >> (8 * (sel & 7u))) & 0xffu;
+        if (sel & 8u) b = (b & 0x80u) ? 0xffu : 0u;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+// __byte_perm (CUDA math API): only bits 2:0 of each selector nibble are used
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) { return b200_prmt(x, y, s & 0x7777u); }
+static inline int16_t lo16(uint32_t v) { return (int16_t)(v & 0xffffu); }
+static inline int16_t hi16(uint32_t v) { return (int16_t)(v >> 16); }
+static inline uint32_t pk(int lo, int hi) { return (uint32_t)(uint16_t)(int16_t)lo | (uint32_t)(uint16_t)(int16_t)hi << 16; }
+static inline int mn(int a, int b) { return a < b ? a : b; }
+static inline int mx(int a, int b) { return a > b ? a : b; }
+static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{ return pk(mn((int16_t)(lo16(a) + lo16(b)), lo16(c)), mn((int16_t)(hi16(a) + hi16(b)), hi16(c))); }
+static inline uint32_t __viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{ return pk(mx((int16_t)(lo16(a) + lo16(b)), lo16(c)), mx((int16_t)(hi16(a) + hi16(b)), hi16(c))); }
+static inline uint32_t __vimax3_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{ return pk(mx(mx(lo16(a), lo16(b)), lo16(c)), mx(mx(hi16(a), hi16(b)), hi16(c))); }
+static inline uint32_t __vibmax_s16x2(uint32_t a, uint32_t b, bool *ph, bool *pl)
+{ *pl = lo16(a) >= lo16(b); *ph = hi16(a) >= hi16(b); return pk(mx(lo16(a), lo16(b)), mx(hi16(a), hi16(b))); }
+
+#include "ext_simd_core.cuh"
+
+// jobs in the GASAL byte layout; res6 = n x 6 int32; returns the number of evaluated cells, or -1 if the parameters
+// are not eligible for the two-row kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > 512)
+extern "C" long long ext_simd_host_run(const bwa_b200_ext_params_t *p, uint64_t n, const uint8_t *qseq, const uint32_t *qoff, const uint32_t *qlen,
+                                       const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen, const uint32_t *h0,
+                                       int32_t *res6, uint8_t *skipped)
+{
+    SimdParams S;
+    if (!simd_params_from(p, &S)) return -1;
+    ExtParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(P.mat, p->mat, 25);
+    P.o_del = p->o_del; P.e_del = p->e_del; P.o_ins = p->o_ins; P.e_ins = p->e_ins;
+    P.w = p->w; P.end_bonus = p->end_bonus; P.zdrop = p->zdrop; P.use_band = p->use_band; P.pen_clip = p->pen_clip;
+    int mxs = 0;
+    for (int i = 0; i < 25; ++i) mxs = mxs > p->mat[i] ? mxs : p->mat[i];
+    P.max_score = mxs;
+    JobView J{qseq, tseq, nullptr, nullptr, qoff, qlen, toff, tlen, h0};
+    unsigned long long cells = 0;
+    std::vector<uint32_t> A, B;
+    std::vector<uint8_t> Q;
+    for (uint64_t a = 0; a < n; ++a) {
+        const int ql = (int)qlen[a], tl = (int)tlen[a], h = (int)h0[a];
+        const uint64_t bound = (uint64_t)h + (uint64_t)ql * (uint64_t)mxs;
+        skipped[a] = (bound > 1023 || ql > 512 || ql < 1 || h < 1) ? 1 : 0;
+        if (skipped[a]) continue;
+        A.assign(ql + 2, 0xdeadbeefu); B.assign(ql + 2, 0xdeadbeefu); Q.assign(ql + 8, 0);
+        bwa_b200_ext_result_t r;
+        simd_job<true, 1>(P, S, J, (uint32_t)a, ql, tl, h, B.data(), A.data(), Q.data(), r, cells);
+        memcpy(res6 + a * 6, &r, 24);
+    }
+    return (long long)cells;
+}
