@@ -559,7 +559,10 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     int occ_b = 0, occ_l = 0;
     s->fwd_minb = getenv("BWA_B200_FWD_MINB") ? atoi(getenv("BWA_B200_FWD_MINB")) : FWD_MIN_BLOCKS;
     s->back_minb = getenv("BWA_B200_BACK_MINB") ? atoi(getenv("BWA_B200_BACK_MINB")) : BACK_MIN_BLOCKS;
-    const bool narrow_rows = idx->v.seq_len < 0xfffffff0ull;
+    // 32-bit row arithmetic when every BWT row fits; BWA_B200_WIDE_ROWS forces the 64-bit kernels (human-sized
+    // indexes) so that tests can cover them on small genomes
+    const bool narrow_rows = idx->v.seq_len < 0xfffffff0ull && !getenv("BWA_B200_WIDE_ROWS");
+    s->narrow_rows = narrow_rows;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_variant(narrow_rows, s->back_minb), BACK_THREADS, 0));
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel<uint64_t>, LOC_THREADS, 0));
     s->back_grid = s->n_sm * (occ_b > 0 ? occ_b : 1);
@@ -628,7 +631,7 @@ static int seeder_fill_locate(bwa_b200_seeder *s)
     B200_LAUNCH(s->prof, "fill_kernel", st,
         (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
                                                        s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
-    if (ix.seq_len < 0xfffffff0ull)
+    if (s->narrow_rows)
         B200_LAUNCH(s->prof, "locate_kernel", st,
             (locate_kernel<uint32_t><<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
     else
@@ -657,7 +660,7 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     cudaStream_t st = s->stream;
     B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
     // 32-bit row arithmetic when every BWT row fits (seq_len < 2^32), 64-bit otherwise (human-sized)
-    const bool narrow = ix.seq_len < 0xfffffff0ull;
+    const bool narrow = s->narrow_rows;
     const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
     B200_LAUNCH(s->prof, "fwd_kernel", st,
         (fwd_variant(narrow, s->fwd_minb)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));

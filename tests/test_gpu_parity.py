@@ -90,6 +90,16 @@ def test_seeding_ragged_and_edge_reads(gpu, dev_index):
     seed_compare(gpu, idx, oi, f, off, 30, 500)
 
 
+def test_seeding_wide_rows_path(gpu, dev_index, monkeypatch):
+    """the 64-bit row kernels (selected for indexes of 2^32 rows and more, i.e. human-sized) forced on a small index"""
+    g, idx, oi = dev_index
+    monkeypatch.setenv("BWA_B200_WIDE_ROWS", "1")
+    reads, _, _ = synth.make_reads(g, 3000, 150, seed=15, n_rate=0.002)
+    seed_compare(gpu, idx, oi, reads.reshape(-1).copy(), (np.arange(3001) * 150).astype(np.uint64), 19, 500)
+    long_reads, _, _ = synth.make_reads(g, 500, 250, seed=16, sub_rate=0.02)
+    seed_compare(gpu, idx, oi, long_reads.reshape(-1).copy(), (np.arange(501) * 250).astype(np.uint64), 19, 20)
+
+
 def test_seeding_empty_batch(gpu, dev_index):
     _, idx, _ = dev_index
     sd = gpu.Seeder(idx, 16, 16)
