@@ -321,13 +321,15 @@ def main():
         roofline["random_sector_peak_hbm_gbs"] = rs_hbm
         roofline["random_sector_peak_l2_gbs"] = rs_l2
         roofline["frac_of_random_sector_hbm"] = roofline["achieved"] / rs_hbm if rs_hbm else None
-    ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel"))
+    ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel") or k.startswith("ext_pair_kernel"))
     gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
     seed_ms = sum(seed_k.values())
     # INT-ALU roofline of the extension kernel: 15 integer ops per cell, 64 int lanes/clk/SM on the ALU pipe
     int_peak_gops = 148 * 64 * (pk.get("sm_max_mhz", 1965.0) / 1e3)
     ext_roof = {"bound": "int_alu", "achieved_gcups": gcups, "peak_gcups_int32": int_peak_gops / 15.0,
-                "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None, "ops_per_cell": 15,
+                "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None,
+                "peak_gcups_s16x2": 2 * int_peak_gops / 15.0, "frac_s16x2": gcups / (2 * int_peak_gops / 15.0) if gcups else None,
+                "ops_per_cell": 15,
                 "cells_per_step": tot["cells"], "ms_per_step": ext_ms}
 
     cpu_baseline = None

@@ -7,19 +7,26 @@
 // whatever an earlier row (or the initial row) left there.  Those semantics are row-sequential,
 // so the inter-query kernel below keeps rows in order per job and never speculates across rows.
 //
-//   ext_inter_kernel   one job per lane.  The per-column state {H(i-1,j-1), E(i,j)} lives in
-//                      shared memory as one 32-bit word per column (two 16-bit fields), laid out
-//                      [column][lane] so lanes never conflict; the query is staged next to it
-//                      as 4-bit codes.  DPX min/max instructions (VIADDMNMX / VIMNMX3) implement
-//                      the recurrences.  Jobs are sorted by query length on the device and
-//                      launched per length bin, so lanes of a warp run similar trip counts and
-//                      each bin gets exactly the shared memory its longest query needs.
+//   ext_pair_kernel    one job per lane, two query columns per s16x2 register (ext_pair_core.cuh):
+//                      M, E and the gap-open terms of a row are data-parallel along the row, only F
+//                      carries from column to column, so a column pair costs ~11 packed ALU
+//                      instructions (VIADDMNMX / VIMNMX3 / PRMT) instead of ~2 x 15 scalar ones.
+//                      State {H(i-1,j-1), E(i,j)} of a column pair is one uint2 in shared memory,
+//                      laid out [pair][lane].  Takes every job whose score bound h0 + qlen * max(mat)
+//                      is at most 1023 and whose query is at most 512 bases.
+//   ext_inter_kernel   one job per lane, one column per step in 32-bit arithmetic: the general
+//                      fallback (scores up to 2^15, queries up to 1024, any matrix).  The per-column
+//                      state lives in shared memory as one 32-bit word per column, [column][lane];
+//                      the query is staged next to it as 4-bit codes.
+//   Jobs are sorted by (class, query length) on the device and launched per length bin, so lanes
+//   of a warp run similar trip counts and each bin gets exactly the shared memory its longest
+//   query needs.
 //
 // This is not a port of GASAL2's KSW kernel (one thread per alignment with eh[] in local
 // memory, no band, zdrop = 0, fixed clip penalty): band, z-drop, end bonus and separate
 // insertion/deletion penalties are honoured, and all six outputs are returned.
 #include "internal.h"
-#include "ext_simd_core.cuh"
+#include "ext_pair_core.cuh"
 #include <cub/cub.cuh>
 
 namespace {
@@ -27,12 +34,16 @@ namespace {
 constexpr int N_BINS = 7;
 __constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
 
-constexpr int SIMD_MAX_Q = 512;          // longest query the two-row kernel stages (shared memory)
+constexpr int N_PBINS = 12;              // bins of the column-pair kernel; the first N_KEYED use the 16-bit (score, pair) key
+constexpr int N_KEYED = 8;
+__constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 192, 256, 384, 512};
+constexpr int PAIR_MAX_Q = 512;          // longest query the column-pair kernel stages (shared memory)
+constexpr int PAIR_NT = 64;              // lanes per block of the column-pair kernel
 constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
 constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
 
-// sort key: query length; bit 19 = not eligible for the two-row s16x2 kernel (score bound above 1023, query too
-// long, or a matrix that is not match/mismatch/N shaped); bit 20 = scores could reach 2^15
+// sort key: query length; bit 19 = not eligible for the column-pair s16x2 kernel (score bound above 1023, query
+// too long, or ineligible matrix / penalties); bit 20 = scores could reach 2^15
 __global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, int simd_ok, uint32_t *keys, uint32_t *vals)
 {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,28 +51,32 @@ __global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0,
     uint32_t q = qlen[a];
     uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
     uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
-    if (!simd_ok || bound > 1023ull || q > (uint32_t)SIMD_MAX_Q) k |= CLS_BIT;
+    if (!simd_ok || bound > (uint64_t)PAIR_MAX_SCORE || q > (uint32_t)PAIR_MAX_Q) k |= CLS_BIT;
     if (bound >= 32767ull) k |= BAD_BIT;
     keys[a] = k;
     vals[a] = a;
 }
 
-// Sorted positions of the bin boundaries.  range[0..N_BINS] bound the bins of the two-row kernel (bin b =
-// [range[b], range[b+1])), range[N_BINS+1 .. 2*N_BINS+1] those of the 32-bit kernel.
+// Sorted positions of the bin boundaries.  range[0..N_PBINS] bound the bins of the column-pair kernel (bin b =
+// [range[b], range[b+1])), range[N_PBINS+1 .. N_PBINS+1+N_BINS] those of the 32-bit kernel.
+__device__ __forceinline__ uint32_t lower_bound_key(const uint32_t *sorted_keys, uint32_t n, uint32_t thr)
+{ // first position whose key is >= thr
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < thr) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag)
 {
     const int k = threadIdx.x;
-    if (k > 2 * N_BINS + 1) return;
-    // first position whose key is >= thr
+    if (k > N_PBINS + N_BINS + 1) return;
     uint32_t thr;
-    if (k <= N_BINS) thr = k == 0 ? 0u : (uint32_t)c_bin_hi[k - 1] + 1u;
-    else thr = CLS_BIT | (k == N_BINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_BINS - 2] + 1u);
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < thr) lo = mid + 1; else hi = mid; }
+    if (k <= N_PBINS) thr = k == 0 ? 0u : (uint32_t)c_pbin_hi[k - 1] + 1u;
+    else thr = CLS_BIT | (k == N_PBINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_PBINS - 2] + 1u);
+    const uint32_t lo = lower_bound_key(sorted_keys, n, thr);
     range[k] = lo;
-    // anything between the last bin of a class and the next class (query > 1024), or with the bad bit, is not handled
-    if (k == N_BINS) { uint32_t l2 = 0, h2 = n; while (l2 < h2) { uint32_t mid = (l2 + h2) >> 1; if (sorted_keys[mid] < CLS_BIT) l2 = mid + 1; else h2 = mid; } if (lo < l2) atomicExch(err_flag, 2); }
-    if (k == 2 * N_BINS + 1 && lo < n) atomicExch(err_flag, 2);
+    // anything between the last bin of a class and the next class, or with the bad bit, is not handled
+    if (k == N_PBINS && lo < lower_bound_key(sorted_keys, n, CLS_BIT)) atomicExch(err_flag, 2);
+    if (k == N_PBINS + N_BINS + 1 && lo < n) atomicExch(err_flag, 2);
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -231,19 +246,18 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     if ((tid & 31) == 0 && my_cells) atomicAdd(cells_total, my_cells);
 }
 
-// ext_simd_kernel: two target rows per lane in the halves of s16x2 registers (ext_simd_core.cuh); one warp per block
-template <bool BYTES>
-__global__ void __launch_bounds__(32)
-ext_simd_kernel(ExtParams P, SimdParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
+// ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh)
+template <bool BYTES, bool KEYED>
+__global__ void __launch_bounds__(PAIR_NT)
+ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
                 int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
                 int *__restrict__ err_flag)
 {
-    constexpr int NT = 32;
-    extern __shared__ uint32_t smem[];
+    constexpr int NT = PAIR_NT;
+    extern __shared__ uint2 smem2[];
     const int tid = threadIdx.x;
-    uint32_t *const Bp = smem + tid;                                   // B[j] = Bp[j * NT]
-    uint32_t *const Ap = smem + (size_t)(max_q + 1) * NT + tid;        // A[j]
-    uint8_t *const Qp = reinterpret_cast<uint8_t *>(smem + (size_t)2 * (max_q + 1) * NT) + tid;   // shaped query bytes
+    uint2 *const HEp = smem2 + tid;                                                              // HE[p] = HEp[p * NT]
+    uint32_t *const QSp = reinterpret_cast<uint32_t *>(smem2 + (size_t)(max_q / 2 + 1) * NT) + tid;   // QS[g] = QSp[g * NT]
     const uint32_t lo = range[bin], hi = range[bin + 1];
     unsigned long long my_cells = 0;
     for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
@@ -258,7 +272,7 @@ ext_simd_kernel(ExtParams P, SimdParams S, JobView J, const uint32_t *__restrict
                 continue;
             }
             if (qlen > max_q || h0 < 1) { atomicExch(err_flag, 1); continue; }
-            simd_job<BYTES, NT>(P, S, J, a, qlen, tlen, h0, Bp, Ap, Qp, r, my_cells);
+            pair_job<BYTES, NT, KEYED>(P, S, J, a, qlen, tlen, h0, HEp, QSp, r, my_cells);
             res[a] = r;
         }
     }
@@ -349,7 +363,7 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     e->n_sm = prop.multiProcessorCount;
     e->smem_optin = (int)prop.sharedMemPerBlockOptin;
     B200_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaMalloc(&e->d_range, (2 * N_BINS + 2) * 4));
+    B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 2) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
     B200_CUDA(cudaMemset(e->d_cells, 0, 8));
@@ -365,8 +379,9 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
                              (const void *)ext_inter_kernel<true, 64>, (const void *)ext_inter_kernel<false, 64>,
                              (const void *)ext_inter_kernel<true, 32>, (const void *)ext_inter_kernel<false, 32>};
         for (const void *k : ks) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-        B200_CUDA(cudaFuncSetAttribute((const void *)ext_simd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-        B200_CUDA(cudaFuncSetAttribute((const void *)ext_simd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+        const void *kp[4] = {(const void *)ext_pair_kernel<true, true>, (const void *)ext_pair_kernel<true, false>,
+                             (const void *)ext_pair_kernel<false, true>, (const void *)ext_pair_kernel<false, false>};
+        for (const void *k : kp) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
     }
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
     if (rc) return rc;
@@ -416,11 +431,11 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     to_dev_params(p, &P);
     B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
     if (e->prof) e->prof->begin("ext_sort", e->stream);
-    // the two-row s16x2 kernel needs a matrix of the form {a on the diagonal, one mismatch score, one score for N}
-    // (bwa_fill_scmat, src/bwa.c) with 0 < a <= 31; any other matrix runs entirely in the 32-bit kernel
-    SimdParams S;
+    // the column-pair s16x2 kernel takes any matrix with 0 < max <= 31 and one score for a query N
+    // (bwa_fill_scmat, src/bwa.c, is of that form); any other matrix runs entirely in the 32-bit kernel
+    PairParams S;
     memset(&S, 0, sizeof(S));
-    int simd_ok = simd_params_from(p, &S);
+    int simd_ok = pair_params_from(p, &S);
     if (getenv("BWA_B200_EXT_NO_SIMD")) simd_ok = 0;
     key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, e->d_keys, e->d_vals);
     size_t tmp = e->cub_bytes;
@@ -431,23 +446,25 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
     static const char *bin_name[N_BINS] = {"ext_inter_kernel_q16", "ext_inter_kernel_q32", "ext_inter_kernel_q64", "ext_inter_kernel_q128",
                                            "ext_inter_kernel_q256", "ext_inter_kernel_q512", "ext_inter_kernel_q1024"};
-    static const char *simd_name[N_BINS] = {"ext_simd_kernel_q16", "ext_simd_kernel_q32", "ext_simd_kernel_q64", "ext_simd_kernel_q128",
-                                            "ext_simd_kernel_q256", "ext_simd_kernel_q512", ""};
-    // two-row s16x2 kernel: one warp per block, bins up to SIMD_MAX_Q
-    for (int b = 0; b < N_BINS && simd_ok && bin_hi[b] <= SIMD_MAX_Q; ++b) {
-        const int L = bin_hi[b];
-        const size_t smem = ((size_t)2 * (L + 1) * 4 + (size_t)(L + 4)) * 32;
+    static const int pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 192, 256, 384, 512};
+    static const char *pbin_name[N_PBINS] = {"ext_pair_kernel_q16", "ext_pair_kernel_q32", "ext_pair_kernel_q48", "ext_pair_kernel_q64",
+                                             "ext_pair_kernel_q80", "ext_pair_kernel_q96", "ext_pair_kernel_q112", "ext_pair_kernel_q128",
+                                             "ext_pair_kernel_q192", "ext_pair_kernel_q256", "ext_pair_kernel_q384", "ext_pair_kernel_q512"};
+    // column-pair s16x2 kernel
+    for (int b = 0; b < N_PBINS && simd_ok; ++b) {
+        const int L = pbin_hi[b];
+        const size_t smem = ((size_t)(L / 2 + 1) * 8 + (size_t)((L + 3) / 4 + 1) * 4) * PAIR_NT;
         if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
-        auto kern = ext_simd_kernel<BYTES>;
+        auto kern = b < N_KEYED ? ext_pair_kernel<BYTES, true> : ext_pair_kernel<BYTES, false>;
         int occ = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PAIR_NT, smem));
         if (occ < 1) occ = 1;
-        uint32_t max_blocks = (n + 31) / 32;
+        uint32_t max_blocks = (n + PAIR_NT - 1) / PAIR_NT;
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
-        B200_LAUNCH(e->prof, simd_name[b], e->stream,
-            (kern<<<grid, 32, smem, e->stream>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        B200_LAUNCH(e->prof, pbin_name[b], e->stream,
+            (kern<<<grid, PAIR_NT, smem, e->stream>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     // 32-bit kernel for everything else
@@ -466,7 +483,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
         B200_LAUNCH(e->prof, bin_name[b], e->stream,
-            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range + (N_BINS + 1), b, L, d_res, e->d_cells, e->d_err)));
+            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     B200_CUDA(cudaGetLastError());

@@ -1,13 +1,13 @@
-// Host build of the two-row s16x2 extension (bwa-mem_gpu_b200/csrc/ext_simd_core.cuh) with the five
+// Host build of the column-pair s16x2 extension (bwa-mem_gpu_b200/csrc/ext_pair_core.cuh) with the
 // integer intrinsics it uses emulated in plain C++.  TEST INFRASTRUCTURE: lets the exact kernel
-// source be fuzzed against the oracle on the CPU box (tests/test_ext_simd_host.py); never shipped
+// source be fuzzed against the oracle on the CPU box (tests/test_ext_pair_host.py); never shipped
 // and never used as a compute path.
-//   g++ -O2 -shared -fPIC -I include -I bwa-mem_gpu_b200/csrc tests/host_emul/ext_simd_host.cpp -o tests/host_emul/libextsimd_host.so
+//   g++ -O2 -shared -fPIC -I include -I bwa-mem_gpu_b200/csrc tests/host_emul/ext_pair_host.cpp -o tests/host_emul/libextpair_host.so
 #include <stdint.h>
 #include <string.h>
 #include <vector>
 
-// prmt.b32, generic mode (PTX ISA): selector bit 3 replicates the sign of the selected byte
+// prmt.b32, generic mode (PTX ISA): selector bit 3 replicates the sign of the selected byte; only c[15:0] is used
 static inline uint32_t b200_prmt(uint32_t x, uint32_t y, uint32_t s)
 {
     const uint64_t v = (uint64_t)y << 32 | x;
@@ -31,21 +31,28 @@ static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c)
 { return pk(mn((int16_t)(lo16(a) + lo16(b)), lo16(c)), mn((int16_t)(hi16(a) + hi16(b)), hi16(c))); }
 static inline uint32_t __viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c)
 { return pk(mx((int16_t)(lo16(a) + lo16(b)), lo16(c)), mx((int16_t)(hi16(a) + hi16(b)), hi16(c))); }
+static inline uint32_t __viaddmax_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)
+{ return pk(mx(mx((int16_t)(lo16(a) + lo16(b)), lo16(c)), 0), mx(mx((int16_t)(hi16(a) + hi16(b)), hi16(c)), 0)); }
 static inline uint32_t __vimax3_s16x2(uint32_t a, uint32_t b, uint32_t c)
 { return pk(mx(mx(lo16(a), lo16(b)), lo16(c)), mx(mx(hi16(a), hi16(b)), hi16(c))); }
 static inline uint32_t __vibmax_s16x2(uint32_t a, uint32_t b, bool *ph, bool *pl)
 { *pl = lo16(a) >= lo16(b); *ph = hi16(a) >= hi16(b); return pk(mx(lo16(a), lo16(b)), mx(hi16(a), hi16(b))); }
+static inline uint32_t umx(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
+{ return umx(a & 0xffffu, b & 0xffffu) | umx(a >> 16, b >> 16) << 16; }
+static inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{ return umx((a + b) & 0xffffu, c & 0xffffu) | umx(((a >> 16) + (b >> 16)) & 0xffffu, c >> 16) << 16; }
 
-#include "ext_simd_core.cuh"
+#include "ext_pair_core.cuh"
 
 // jobs in the GASAL byte layout; res6 = n x 6 int32; returns the number of evaluated cells, or -1 if the parameters
-// are not eligible for the two-row kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > 512)
-extern "C" long long ext_simd_host_run(const bwa_b200_ext_params_t *p, uint64_t n, const uint8_t *qseq, const uint32_t *qoff, const uint32_t *qlen,
-                                       const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen, const uint32_t *h0,
-                                       int32_t *res6, uint8_t *skipped)
+// are not eligible for the pair kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > max_q)
+extern "C" long long ext_pair_host_run(const bwa_b200_ext_params_t *p, int keyed, uint64_t n, const uint8_t *qseq, const uint32_t *qoff,
+                                       const uint32_t *qlen, const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen,
+                                       const uint32_t *h0, int32_t *res6, uint8_t *skipped)
 {
-    SimdParams S;
-    if (!simd_params_from(p, &S)) return -1;
+    PairParams S;
+    if (!pair_params_from(p, &S)) return -1;
     ExtParams P;
     memset(&P, 0, sizeof(P));
     memcpy(P.mat, p->mat, 25);
@@ -56,16 +63,17 @@ extern "C" long long ext_simd_host_run(const bwa_b200_ext_params_t *p, uint64_t 
     P.max_score = mxs;
     JobView J{qseq, tseq, nullptr, nullptr, qoff, qlen, toff, tlen, h0};
     unsigned long long cells = 0;
-    std::vector<uint32_t> A, B;
-    std::vector<uint8_t> Q;
+    std::vector<uint2> HE;
+    std::vector<uint32_t> QS;
     for (uint64_t a = 0; a < n; ++a) {
         const int ql = (int)qlen[a], tl = (int)tlen[a], h = (int)h0[a];
         const uint64_t bound = (uint64_t)h + (uint64_t)ql * (uint64_t)mxs;
-        skipped[a] = (bound > 1023 || ql > 512 || ql < 1 || h < 1) ? 1 : 0;
+        skipped[a] = (bound > (uint64_t)PAIR_MAX_SCORE || ql > (keyed ? PAIR_KEYED_MAX_Q : 512) || ql < 1 || h < 1) ? 1 : 0;
         if (skipped[a]) continue;
-        A.assign(ql + 2, 0xdeadbeefu); B.assign(ql + 2, 0xdeadbeefu); Q.assign(ql + 8, 0);
+        HE.assign(ql / 2 + 1, uint2{0xdeadbeefu, 0xdeadbeefu}); QS.assign((ql + 3) / 4 + 1, 0xdeadbeefu);
         bwa_b200_ext_result_t r;
-        simd_job<true, 1>(P, S, J, (uint32_t)a, ql, tl, h, B.data(), A.data(), Q.data(), r, cells);
+        if (keyed) pair_job<true, 1, true>(P, S, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
+        else pair_job<true, 1, false>(P, S, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
         memcpy(res6 + a * 6, &r, 24);
     }
     return (long long)cells;

@@ -203,10 +203,10 @@ def test_extension_matches_oracle(gpu, oracle, kw):
 
 @pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=16, zdrop=100), dict(w=8, zdrop=0), dict(w=50, zdrop=30, end_bonus=5),
                                 dict(w=300, zdrop=0, use_band=0), dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=3, b=2)])
-def test_extension_two_row_kernel_stress(gpu, oracle, kw):
-    """the s16x2 two-row kernel (rows i / i+1 in the register halves, speculative second row) on many
+def test_extension_pair_kernel_stress(gpu, oracle, kw):
+    """the s16x2 column-pair kernel (two query columns per register, keyed and predicate row maxima) on many
     shapes: long seeds against short bands (right band clamp binds), noisy jobs (windows shrink from
-    both sides), N bases, odd and even target lengths; and the same jobs through the 32-bit kernel"""
+    both sides, odd/even window edges), N bases; and the same jobs through the 32-bit kernel"""
     ex = gpu.Extender(0)
     for seed, extra in ((61, dict(qlen_range=(1, 260), h0_range=(1, 250))),
                         (62, dict(qlen_range=(1, 120), sub_rate=0.25, indel_rate=0.08, n_job_frac=0.3, h0_range=(1, 40))),
@@ -227,8 +227,8 @@ def test_extension_two_row_kernel_stress(gpu, oracle, kw):
     ex.destroy()
 
 
-def test_extension_general_matrix_uses_32bit_kernel(gpu, oracle):
-    """a substitution matrix that is not match/mismatch/N shaped cannot use the PRMT score table"""
+def test_extension_general_matrix(gpu, oracle):
+    """a general substitution matrix (transitions cheaper than transversions): PRMT score rows in the pair kernel"""
     jobs = synth.make_ext_jobs(3000, w=100, seed=71, qlen_range=(1, 200), h0_range=(1, 150))
     P = oracle.make_params(w=100, zdrop=100)
     mat = np.array([[2, -3, -1, -3, -1], [-3, 2, -3, -1, -1], [-1, -3, 2, -3, -1], [-3, -1, -3, 2, -1], [-1, -1, -1, -1, -1]], np.int8)
@@ -239,6 +239,12 @@ def test_extension_general_matrix_uses_32bit_kernel(gpu, oracle):
     for i in range(25):
         ep.mat[i] = int(mat.reshape(-1)[i])
     ex = gpu.Extender(0)
+    res, _ = ex.extend_host(jobs, ep)
+    assert (res == want).all()
+    # a matrix whose "query is N" column is not uniform is not eligible for the pair kernel: 32-bit kernel
+    P.mat[4] = -2
+    ep.mat[4] = -2
+    want, _ = oracle.ksw_batch(jobs, P, n_threads=4)
     res, _ = ex.extend_host(jobs, ep)
     assert (res == want).all()
     ex.destroy()
