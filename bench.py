@@ -220,7 +220,7 @@ def main():
     def step_device():
         pl.run_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
 
-    pl.profile(True)
+    pl.profile(False)
     for _ in range(args.warmup):
         step_device()
         pl.sync()
@@ -231,7 +231,6 @@ def main():
     sampler.start()
     launches0 = pl.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ktimes = {}
     torch.cuda.synchronize()
     for k in range(args.steps):
         with torch.cuda.stream(stream):
@@ -240,13 +239,23 @@ def main():
         step_device()
         ev[k][1].record(stream)
         pl.sync()
-        for name, ms in pl.kernel_times():
-            ktimes.setdefault(name, []).append(ms)
     torch.cuda.synchronize()
     if dref:
         dist.barrier()
     clocks = sampler.stop()
     gpu_launches = pl.launches - launches0
+    # per-kernel durations: the same steps again with a CUDA-event pair around every launch (kernels of a step then
+    # run back to back on one stream; in the timed steps above the extension bins overlap on side streams)
+    pl.profile(True)
+    ktimes = {}
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step_device()
+        pl.sync()
+        for name, ms in pl.kernel_times():
+            ktimes.setdefault(name, []).append(ms)
+    torch.cuda.synchronize()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     tot = pl.totals()
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")

@@ -8,9 +8,10 @@
 // F(i,j+1) = max(F(i,j) - e_ins, max(M(i,j) - oe_ins, 0)) carries from column to column.  For the
 // column pair (j, j+1) that carry is two dependent VIADDMNMX on a chain register whose HIGH half is
 // F(i,j); everything else is one packed instruction for both columns.  Rows stay in the reference's
-// order with the reference's window [beg, end): an odd first / even last column of the window is a
-// scalar cell, so no cell outside the window is ever read or written (src/ksw.c:909-970 semantics
-// are kept exactly; nothing is speculated).
+// order with the reference's window [beg, end): when the window starts at an odd / ends at an even
+// column, the outside half of the first / last pair is masked (inputs zeroed, stored state kept,
+// excluded from the row maximum), so the state of a cell outside the window is never changed
+// (src/ksw.c:909-970 semantics are kept exactly; nothing is speculated).
 //
 // Per-lane state (lane stride NT elements, conflict-free):
 //   HE[p] = uint2 { H(i-1, 2p-1) | H(i-1, 2p) << 16 ,  E(i, 2p) | E(i, 2p+1) << 16 }     p = 0 .. qlen/2
@@ -87,26 +88,56 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
 //   max(x - pen, 0) is the RELU form of VIADDMNMX with the (negative) penalty as its own third operand
 //   key  = h * 64 + p (KEYED): unsigned max keeps the LAST column among equal maxima (src/ksw.c:928);
 //          pp = {p0, p0} for the loop iteration's first pair, KOFF the pair's offset from it
-#define PAIR_STEP(HP, PIDX, SEL, KOFF)                                                           \
-    {                                                                                            \
-        const uint2 he_ = *(HP);                                                                 \
+#define PAIR_CORE(HE, SEL)                                                                       \
         const uint32_t S_ = b200_prmt(tlo, tab_n, (SEL));                                        \
-        const uint32_t M_ = __viaddmin_s16x2(he_.x, S_, he_.x * 32u);                            \
+        const uint32_t M_ = __viaddmin_s16x2((HE).x, S_, (HE).x * 32u);                          \
         const uint32_t t2_ = __viaddmax_s16x2_relu(M_, noe_ins2, noe_ins2);                      \
         const uint32_t Fh_ = __viaddmax_s16x2(c, ne_ins2, t2_ << 16);                            \
         const uint32_t F_ = __byte_perm(c, Fh_, 0x7632);                                         \
         c = __viaddmax_s16x2(Fh_, ne_ins2, t2_);                                                 \
-        const uint32_t h_ = __vimax3_s16x2(M_, he_.y, F_);                                       \
-        if (KEYED) m2 = (KOFF) ? __viaddmax_u16x2(h_ * 64u + pp, (KOFF), m2) : __vmaxu2(m2, h_ * 64u + pp); \
+        const uint32_t h_ = __vimax3_s16x2(M_, (HE).y, F_);                                      \
+        const uint32_t t1_ = __viaddmax_s16x2_relu(M_, noe_del2, noe_del2);                      \
+        const uint32_t En_ = __viaddmax_s16x2((HE).y, ne_del2, t1_);
+
+#define PAIR_MAX(HK, PIDX, KOFF)                                                                 \
+        if (KEYED) m2 = (KOFF) ? __viaddmax_u16x2((HK) * 64u + pp, (KOFF), m2) : __vmaxu2(m2, (HK) * 64u + pp); \
         else {                                                                                   \
             bool pH_, pL_;                                                                       \
-            m2 = __vibmax_s16x2(h_, m2, &pH_, &pL_);                                             \
+            m2 = __vibmax_s16x2((HK), m2, &pH_, &pL_);                                           \
             pjL = pL_ ? (PIDX) : pjL;                                                            \
             pjH = pH_ ? (PIDX) : pjH;                                                            \
-        }                                                                                        \
-        const uint32_t t1_ = __viaddmax_s16x2_relu(M_, noe_del2, noe_del2);                      \
+        }
+
+// a pair wholly inside the window
+#define PAIR_STEP(HP, PIDX, SEL, KOFF)                                                           \
+    {                                                                                            \
+        const uint2 he_ = *(HP);                                                                 \
+        PAIR_CORE(he_, SEL)                                                                      \
+        PAIR_MAX(h_, PIDX, KOFF)                                                                 \
         uint2 o_;                                                                                \
-        o_.y = __viaddmax_s16x2(he_.y, ne_del2, t1_);                                            \
+        o_.y = En_;                                                                              \
+        o_.x = __byte_perm(hprev, h_, 0x5432);                                                   \
+        *(HP) = o_;                                                                              \
+        hprev = h_;                                                                              \
+    }
+
+// the first / last pair of the window.  LO_OUT: the low column (beg - 1) lies outside: its inputs are zeroed, which
+// makes its H, F and gap-open terms 0 = the reference's initial h1 and f of the row, and its stored state is kept.
+// HI_OUT: the high column (end) lies outside: it is computed and discarded, except that eh[end] = {H(i,end-1), 0}
+// (src/ksw.c:940) is exactly what the pair store leaves there.
+#define PAIR_STEP_EDGE(HP, PIDX, SEL, LO_OUT, HI_OUT)                                            \
+    {                                                                                            \
+        const uint2 old_ = *(HP);                                                                \
+        const uint32_t inm_ = (LO_OUT) ? 0xffff0000u : 0xffffffffu;                              \
+        const uint32_t outm_ = (HI_OUT) ? (inm_ & 0x0000ffffu) : inm_;                           \
+        uint2 he_;                                                                               \
+        he_.x = old_.x & inm_; he_.y = old_.y & inm_;                                            \
+        if (LO_OUT) hprev = old_.x << 16;                                                        \
+        PAIR_CORE(he_, SEL)                                                                      \
+        const uint32_t hk_ = (HI_OUT) ? (h_ & 0x0000ffffu) : h_;                                 \
+        PAIR_MAX(hk_, PIDX, 0u)                                                                  \
+        uint2 o_;                                                                                \
+        o_.y = (En_ & outm_) | (old_.y & ~inm_);                                                 \
         o_.x = __byte_perm(hprev, h_, 0x5432);                                                   \
         *(HP) = o_;                                                                              \
         hprev = h_;                                                                              \
@@ -118,14 +149,15 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
                        uint2 *const HEp, uint32_t *const QSp, bwa_b200_ext_result_t &r, unsigned long long &my_cells)
 {
     const uint32_t qo = J.qoff[a], to = J.toff[a];
-    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const int oe_ins = P.o_ins + P.e_ins;
     uint16_t *const hw = reinterpret_cast<uint16_t *>(HEp);
 #define H16(j) hw[((j) >> 1) * (NT * 4) + ((j) & 1)]
 #define E16(j) hw[((j) >> 1) * (NT * 4) + 2 + ((j) & 1)]
-    // stage the query as PRMT selector bytes, four columns per word (columns >= qlen: N, never evaluated)
-    for (int j8 = 0; j8 < qlen; j8 += 8) {
+    const uint16_t *const qs16 = reinterpret_cast<const uint16_t *>(QSp);   // selector pair of column pair p: qs16[(p >> 1) * (NT * 2) + (p & 1)]
+    // stage the query as PRMT selector bytes, four columns per word, through column qlen (columns >= qlen: N)
+    for (int j8 = 0; j8 <= qlen; j8 += 8) {
         uint32_t wv = 0;
-        if (!BYTES) wv = J.qp[(qo + j8) >> 3];
+        if (!BYTES && j8 < qlen) wv = J.qp[(qo + j8) >> 3];
         uint32_t s0 = 0, s1 = 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -135,7 +167,7 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
             if (u < 4) s0 |= sb << (8 * u); else s1 |= sb << (8 * (u - 4));
         }
         QSp[(j8 >> 2) * NT] = s0;
-        if (j8 + 4 < qlen) QSp[((j8 >> 2) + 1) * NT] = s1;
+        if (j8 + 4 <= qlen) QSp[((j8 >> 2) + 1) * NT] = s1;
     }
     // first row: H(-1,-1) = h0, then one gap open, then extensions (src/ksw.c:880-883); E = 0
     {
@@ -182,48 +214,35 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
             if (end > qlen) end = qlen;
         }
         const uint32_t tlo = tbv == 0 ? S.tab[0] : (tbv == 1 ? S.tab[1] : (tbv == 2 ? S.tab[2] : (tbv == 3 ? S.tab[3] : S.tab[4])));
-        int h1 = 0, f = 0, m = 0, mj = -1;
+        int h1 = 0, m = 0, mj = -1;
         if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 < 0 ? 0 : h1; }
-        // one cell, plain integers (src/ksw.c:921-938): the odd first / even last column of the window
-#define PAIR_SCALAR_CELL(COL)                                                                    \
-        {                                                                                        \
-            const int j_ = (COL);                                                                \
-            const int hd_ = (int)H16(j_), e0_ = (int)E16(j_);                                    \
-            const uint32_t qs_ = (QSp[(j_ >> 2) * NT] >> (8 * (j_ & 3))) & 0xffu;                \
-            const int sc_ = (int)(int16_t)(uint16_t)b200_prmt(tlo, tab_n, qs_);                \
-            H16(j_) = (uint16_t)h1;                                                              \
-            const int M_ = hd_ ? hd_ + sc_ : 0;                                                  \
-            int h_ = M_ > e0_ ? M_ : e0_;                                                        \
-            h_ = h_ > f ? h_ : f;                                                                \
-            h1 = h_;                                                                             \
-            mj = m > h_ ? mj : j_;                                                               \
-            m = m > h_ ? m : h_;                                                                 \
-            int t_ = M_ - oe_del; t_ = t_ > 0 ? t_ : 0;                                          \
-            int en_ = e0_ - P.e_del; en_ = en_ > t_ ? en_ : t_;                                  \
-            E16(j_) = (uint16_t)en_;                                                             \
-            t_ = M_ - oe_ins; t_ = t_ > 0 ? t_ : 0;                                              \
-            f -= P.e_ins; f = f > t_ ? f : t_;                                                   \
-        }
-        int j = beg;
-        if ((j & 1) && j < end) { PAIR_SCALAR_CELL(j) ++j; }
-        const int p_end = end >> 1;                      // pairs [j/2, end/2) lie wholly inside the window
-        if ((j >> 1) < p_end) {
-            uint32_t hprev = (uint32_t)h1 << 16, c = (uint32_t)f << 16, m2 = 0u;
-            int p = j >> 1;
-            uint32_t pp = (uint32_t)p * 0x00010001u;
-            int pjL = p, pjH = p;
-            uint2 *hp = HEp + p * NT;
-            const uint32_t *qp = QSp + (p >> 1) * NT;
-            if (p & 1) { const uint32_t qw = *qp; PAIR_STEP(hp, p, qw >> 16, 0u) ++p; pp += 0x00010001u; hp += NT; qp += NT; }
-#pragma unroll 2
-            for (; p + 2 <= p_end; p += 2, pp += 0x00020002u, hp += 2 * NT, qp += NT) {
-                const uint32_t qw = *qp;
-                PAIR_STEP(hp, p, qw, 0u)
-                PAIR_STEP(hp + NT, p + 1, qw >> 16, 0x00010001u)
+        if (beg < end) {
+            const int p0 = beg >> 1, p1 = (end - 1) >> 1;          // first and last column pair of the window
+            const bool lo_out = (beg & 1) != 0, hi_out = (end & 1) != 0;
+            uint32_t hprev = (uint32_t)h1 << 16, c = 0u, m2 = 0u;   // c.hi = F(i, beg) = 0
+            uint32_t pp = (uint32_t)p0 * 0x00010001u;
+            int pjL = p0, pjH = p0;
+            uint2 *hp = HEp + p0 * NT;
+            const uint16_t *qp = qs16 + (p0 >> 1) * (NT * 2) + (p0 & 1);
+            PAIR_STEP_EDGE(hp, p0, (uint32_t)*qp, lo_out, hi_out && p0 == p1)
+            int p = p0 + 1;
+            pp += 0x00010001u; hp += NT; qp += (p0 & 1) ? (NT * 2 - 1) : 1;
+            for (; p + 4 <= p1; p += 4, pp += 0x00040004u, hp += 4 * NT, qp += 2 * (NT * 2)) {
+                const int o1 = (p & 1) ? (NT * 2 - 1) : 1;          // selectors of pairs p .. p+3 (two per word, words NT apart)
+                const uint32_t s0 = qp[0], s1 = qp[o1], s2 = qp[NT * 2], s3 = qp[NT * 2 + o1];
+                PAIR_STEP(hp, p, s0, 0u)
+                PAIR_STEP(hp + NT, p + 1, s1, 0x00010001u)
+                PAIR_STEP(hp + 2 * NT, p + 2, s2, 0x00020002u)
+                PAIR_STEP(hp + 3 * NT, p + 3, s3, 0x00030003u)
             }
-            if (p < p_end) { const uint32_t qw = *qp; PAIR_STEP(hp, p, qw, 0u) ++p; }
-            h1 = (int)(hprev >> 16); f = (int)(c >> 16);
-            // row maximum of the paired columns; among equal maxima the last column wins (src/ksw.c:928)
+            for (; p < p1; ++p, pp += 0x00010001u, hp += NT) {
+                const uint32_t s0 = *qp;
+                qp += (p & 1) ? (NT * 2 - 1) : 1;
+                PAIR_STEP(hp, p, s0, 0u)
+            }
+            if (p1 > p0) { PAIR_STEP_EDGE(hp, p1, (uint32_t)*qp, false, hi_out) }
+            h1 = hi_out ? (int)(hprev & 0xffffu) : (int)(hprev >> 16);
+            // row maximum; among equal maxima the last column wins (src/ksw.c:928)
             int sL, cL, sH, cH;
             if (KEYED) {
                 const uint32_t kl = m2 & 0xffffu, kh = m2 >> 16;
@@ -232,11 +251,8 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
                 sL = (int)(m2 & 0xffffu); cL = pjL * 2; sH = (int)(m2 >> 16); cH = pjH * 2 + 1;
             }
             const bool hi_wins = sH > sL || (sH == sL && cH > cL);
-            const int sP = hi_wins ? sH : sL, cP = hi_wins ? cH : cL;
-            if (sP >= m) { m = sP; mj = cP; }            // every paired column lies right of the scalar head cell
-            j = p << 1;
+            m = hi_wins ? sH : sL; mj = hi_wins ? cH : cL;
         }
-        if (j < end) { PAIR_SCALAR_CELL(j) ++j; }
         // ---- row i is complete (src/ksw.c:940-959)
         H16(end) = (uint16_t)h1; E16(end) = 0;           // eh[end] = {h1, 0}
         my_cells += (unsigned long long)(end > beg ? end - beg : 0);
@@ -255,14 +271,13 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
             else         { if (best - m - (dj - di) * P.e_ins > P.zdrop) break; }
         }
         // window of the next row (src/ksw.c:965-970)
-        j = beg;
+        int j = beg;
         while (j < end && H16(j) == 0 && E16(j) == 0) ++j;
         beg = j;
         j = end;
         while (j >= beg && H16(j) == 0 && E16(j) == 0) --j;
         end = j + 2 < qlen ? j + 2 : qlen;
     }
-#undef PAIR_SCALAR_CELL
 #undef H16
 #undef E16
     r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = best_ie + 1; r.gscore = gscore; r.max_off = max_off;

@@ -130,7 +130,7 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
         const uint32_t pos = base + tid;
         if (pos < hi) {
-            const uint32_t a = order[pos];
+            const uint32_t a = order[hi - 1u - (pos - lo)];       // longest queries of the bin first: a short tail
             const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
             const uint32_t qo = J.qoff[a], to = J.toff[a];
             if (qlen == 0) {               // absent job (pipeline slots): ksw_extend2 is never called, score stays h0
@@ -263,7 +263,7 @@ ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict
     for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
         const uint32_t pos = base + tid;
         if (pos < hi) {
-            const uint32_t a = order[pos];
+            const uint32_t a = order[hi - 1u - (pos - lo)];       // longest queries of the bin first: a short tail
             const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
             bwa_b200_ext_result_t r;
             if (qlen == 0) {               // absent job (pipeline slots): ksw_extend2 is never called, score stays h0
@@ -363,6 +363,14 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     e->n_sm = prop.multiProcessorCount;
     e->smem_optin = (int)prop.sharedMemPerBlockOptin;
     B200_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->n_side = getenv("BWA_B200_EXT_SIDE_STREAMS") ? atoi(getenv("BWA_B200_EXT_SIDE_STREAMS")) : 4;
+    if (e->n_side < 0) e->n_side = 0;
+    if (e->n_side > 8) e->n_side = 8;
+    for (int k = 0; k < e->n_side; ++k) {
+        B200_CUDA(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
+    }
+    B200_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 2) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
@@ -400,6 +408,8 @@ extern "C" void bwa_b200_extender_destroy(bwa_b200_extender_t *e)
     cudaFree(e->d_h0); cudaFree(e->d_keys); cudaFree(e->d_keys2); cudaFree(e->d_vals); cudaFree(e->d_order); cudaFree(e->d_range);
     cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cells); cudaFree(e->d_err); cudaFree(e->d_cub);
     cudaFreeHost(e->h_cells); cudaFreeHost(e->h_err);
+    for (int k = 0; k < e->n_side; ++k) { cudaStreamSynchronize(e->side[k]); cudaStreamDestroy(e->side[k]); cudaEventDestroy(e->ev_join[k]); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -450,8 +460,17 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     static const char *pbin_name[N_PBINS] = {"ext_pair_kernel_q16", "ext_pair_kernel_q32", "ext_pair_kernel_q48", "ext_pair_kernel_q64",
                                              "ext_pair_kernel_q80", "ext_pair_kernel_q96", "ext_pair_kernel_q112", "ext_pair_kernel_q128",
                                              "ext_pair_kernel_q192", "ext_pair_kernel_q256", "ext_pair_kernel_q384", "ext_pair_kernel_q512"};
-    // column-pair s16x2 kernel
-    for (int b = 0; b < N_PBINS && simd_ok; ++b) {
+    // Bins are independent: outside profiling they go to side streams (forked from and joined to e->stream with
+    // events), so that the tail of one bin -- a few long jobs on a few SMs -- overlaps the next bins.
+    const bool fan = e->prof == nullptr && e->n_side > 0;
+    int next_side = 0;
+    if (fan) {
+        B200_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+        for (int k = 0; k < e->n_side; ++k) B200_CUDA(cudaStreamWaitEvent(e->side[k], e->ev_fork, 0));
+    }
+    auto bin_stream = [&]() -> cudaStream_t { if (!fan) return e->stream; cudaStream_t st = e->side[next_side]; next_side = (next_side + 1) % e->n_side; return st; };
+    // column-pair s16x2 kernel, longest bins first
+    for (int b = N_PBINS - 1; b >= 0 && simd_ok; --b) {
         const int L = pbin_hi[b];
         const size_t smem = ((size_t)(L / 2 + 1) * 8 + (size_t)((L + 3) / 4 + 1) * 4) * PAIR_NT;
         if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
@@ -463,8 +482,9 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
-        B200_LAUNCH(e->prof, pbin_name[b], e->stream,
-            (kern<<<grid, PAIR_NT, smem, e->stream>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        cudaStream_t st = bin_stream();
+        B200_LAUNCH(e->prof, pbin_name[b], st,
+            (kern<<<grid, PAIR_NT, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     // 32-bit kernel for everything else
@@ -482,10 +502,16 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
-        B200_LAUNCH(e->prof, bin_name[b], e->stream,
-            (kern<<<grid, nt, smem, e->stream>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
+        cudaStream_t st = bin_stream();
+        B200_LAUNCH(e->prof, bin_name[b], st,
+            (kern<<<grid, nt, smem, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
+    if (fan)
+        for (int k = 0; k < e->n_side; ++k) {
+            B200_CUDA(cudaEventRecord(e->ev_join[k], e->side[k]));
+            B200_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join[k], 0));
+        }
     B200_CUDA(cudaGetLastError());
     return BWA_B200_OK;
 }

@@ -76,6 +76,9 @@ struct bwa_b200_seeder {
 struct bwa_b200_extender {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[8] = {};            // bins of one batch run concurrently on these (forked from / joined to `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+    int n_side = 0;
     uint64_t max_jobs = 0, max_q = 0, max_t = 0;
     uint8_t *d_q = nullptr, *d_t = nullptr;
     uint32_t *d_qoff = nullptr, *d_qlen = nullptr, *d_toff = nullptr, *d_tlen = nullptr, *d_h0 = nullptr;

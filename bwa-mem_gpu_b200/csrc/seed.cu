@@ -35,6 +35,7 @@ constexpr int FWD_THREADS = 128;
 constexpr int BACK_THREADS = 128;
 constexpr int ENV_SMEM = 12;          // envelope entries kept in shared memory per lane
 constexpr int LOC_THREADS = 128;
+constexpr uint32_t LOC_CLAIM = 128;    // seeds a warp of locate_kernel claims per queue atomic
 
 using b200::Cand;
 
@@ -431,11 +432,39 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
     uint64_t idx = 0;
     RowT k = 0;
     uint32_t steps = 0;
+    // seeds are claimed per warp, LOC_CLAIM at a time (one queue atomic per claim instead of one per seed:
+    // two million same-address atomics serialise in L2), and handed to the lanes that need one
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t pool = 0;
+    uint32_t pool_left = 0;
+    bool exhausted = false;
     for (;;) {
-        if (!finished && need) {
-            idx = atomicAdd(next_seed, 1ull);
-            if (idx >= total) finished = true;
-            else { k = (RowT)rbeg[idx]; steps = 0; need = false; }
+        {
+            const bool want = !finished && need;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, want);
+            if (ballot) {
+                const uint32_t cnt = __popc(ballot);
+                if (pool_left < cnt && !exhausted) {          // refill: the few seeds left in the old pool are handed out first
+                    // (pool, pool_left) is a contiguous range, so a refill must not strand seeds: take them now
+                    const uint32_t rank0 = __popc(ballot & ((1u << lane) - 1u));
+                    if (want && rank0 < pool_left) { idx = pool + rank0; k = (RowT)rbeg[idx]; steps = 0; need = false; }
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(next_seed, (unsigned long long)LOC_CLAIM);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    pool = base;
+                    pool_left = base < total ? (uint32_t)(total - base < (uint64_t)LOC_CLAIM ? total - base : (uint64_t)LOC_CLAIM) : 0u;
+                    if (base + LOC_CLAIM >= total) exhausted = true;
+                }
+                const bool want2 = !finished && need;
+                const uint32_t ballot2 = __ballot_sync(0xffffffffu, want2);
+                const uint32_t rank = __popc(ballot2 & ((1u << lane) - 1u)), cnt2 = __popc(ballot2);
+                if (want2) {
+                    if (rank < pool_left) { idx = pool + rank; k = (RowT)rbeg[idx]; steps = 0; need = false; }
+                    else if (exhausted) finished = true;
+                }
+                const uint32_t take = cnt2 < pool_left ? cnt2 : pool_left;
+                pool += take; pool_left -= take;
+            }
         }
         if (__all_sync(0xffffffffu, finished)) break;
         if (!finished) {
