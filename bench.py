@@ -326,10 +326,25 @@ def main():
                     "algorithmic_bytes_per_read": alg[dom], "ms_per_launch": seed_k[dom], "share_of_step": seed_k[dom] / step_kernel_ms}
     rs_hbm = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 8 << 30, 64, 3))
     rs_l2 = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 64 << 20, 64, 3))
+    rs_mid = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 1 << 30, 64, 3))
     if roofline:
+        # random 32-byte-sector gather rates measured live (seed.cu random_sector_kernel): 8 GB buffer (HBM, beyond the
+        # TLB reach), 1 GB buffer (HBM, inside the TLB reach: the regime of a 100 Mb .. 1 Gb index) and 64 MB (L2)
         roofline["random_sector_peak_hbm_gbs"] = rs_hbm
+        roofline["random_sector_peak_hbm_1gb_gbs"] = rs_mid
         roofline["random_sector_peak_l2_gbs"] = rs_l2
         roofline["frac_of_random_sector_hbm"] = roofline["achieved"] / rs_hbm if rs_hbm else None
+        roofline["frac_of_random_sector_hbm_1gb"] = roofline["achieved"] / rs_mid if rs_mid else None
+        try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if (n, L, args.genome) == (1_000_000, 150, 100_000_000) and dom in tr["bytes_per_launch"]:
+                roofline["traffic"] = tr["bytes_per_launch"][dom]
+                roofline["traffic_unit"] = "bytes/launch (dram read+write, ncu)"
+                roofline["traffic_gbs"] = tr["bytes_per_launch"][dom] / (seed_k[dom] / 1e3) / 1e9
+                roofline["algorithmic_bytes_per_launch"] = alg[dom] * n
+                roofline["traffic_source"] = tr["source"]
+        except Exception as ex:  # noqa: BLE001
+            log("no ncu traffic figure:", ex)
     ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel") or k.startswith("ext_pair_kernel"))
     gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
     seed_ms = sum(seed_k.values())
