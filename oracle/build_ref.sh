@@ -45,3 +45,25 @@ cp "$REF"/src/ksw.c "$REF"/src/ksw.h "$F"/
   gcc -c $CFLAGS -I. "$HERE/fork_ksw_shim.c" -o shim.o
   gcc -shared $CFLAGS ksw.o shim.o -o "$OUT/libforkksw.so" -lm )
 echo "[build_ref] built: $(ls "$OUT")"
+# ---- fork host code (chaining, chain filter, extension-job construction): src/*.c compiled as C++ exactly
+# like the reference Makefile:14 (-std=c++11 -fpermissive), on a scratch copy laid out like the reference
+# tree (src/ + GASAL2/include/ = GASAL2/src/*.h, which is what GASAL2's own Makefile installs); the one
+# edit is the hard-coded CUDA include path of gasal.h, the same line GASAL2/configure.sh rewrites.
+M="$TMP/forkmem"; mkdir -p "$M/src" "$M/GASAL2/include"
+cp "$REF"/src/*.c "$REF"/src/*.h "$M/src/"
+cp -r "$REF/src/GPUSeed" "$M/src/"
+cp "$REF"/GASAL2/src/*.h "$M/GASAL2/include/"
+sed -i 's,#include "/usr/local/cuda[^"]*cuda_runtime.h",#include <cuda_runtime.h>,' "$M"/GASAL2/include/*.h
+CUDA_INC="${CUDA_HOME:-/usr/local/cuda}/include"
+if [ -f "$CUDA_INC/cuda_runtime.h" ]; then
+( cd "$M/src"
+  CXXF="-O2 -g -std=c++11 -fpermissive -fPIC -w -DHAVE_PTHREAD -I$CUDA_INC -IGPUSeed"
+  FOBJS="bwamem bntseq bwa utils kstring ksw bwt bwamem_pair bwamem_extra kthread malloc_wrap"
+  for o in $FOBJS; do g++ -c $CXXF $o.c -o $o.o & done; wait
+  g++ -c $CXXF -I. "$HERE/fork_mem_shim.cpp" -o fork_mem_shim.o
+  objs=""; for o in $FOBJS; do objs="$objs $o.o"; done
+  g++ -shared $CXXF $objs fork_mem_shim.o -o "$OUT/libforkmem.so" -lm -lz -lpthread )
+else
+  echo "[build_ref] no CUDA headers: libforkmem.so not built" >&2
+fi
+echo "[build_ref] built: $(ls "$OUT")"

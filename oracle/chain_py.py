@@ -1,0 +1,187 @@
+"""ctypes bindings for the chaining / extension-job oracle (oracle/chain_oracle.c) and for the
+reference fork's own host code compiled into oracle/_ref/libforkmem.so (oracle/fork_mem_shim.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import oracle_py as O
+
+CHAIN_DT = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("n", "<i4"), ("w", "<i4"), ("kept", "<i4"), ("first", "<i4"),
+                     ("is_alt", "<i4"), ("frac_rep", "<f4"), ("seed_off", "<i4")], align=True)
+CSEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("pad", "<i4")], align=True)
+REG_DT = np.dtype([("rb_est", "<i8"), ("re_est", "<i8"), ("target_seed_begin", "<i8"), ("qb_est", "<i4"), ("qe_est", "<i4"),
+                   ("rid", "<i4"), ("score", "<i4"), ("truesc", "<i4"), ("align_sides", "<i4"), ("where_is_long", "<i4"),
+                   ("query_seed_begin", "<i4"), ("seedlen0", "<i4"), ("seedcov", "<i4"), ("w", "<i4"), ("frac_rep", "<f4")], align=True)
+JOB_DT = np.dtype([("qoff", "<u4"), ("qlen", "<u4"), ("toff", "<u4"), ("tlen", "<u4"), ("h0", "<u4")], align=True)
+ALN_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4")], align=True)
+assert CHAIN_DT.itemsize == 40 and CSEED_DT.itemsize == 24 and REG_DT.itemsize == 72 and JOB_DT.itemsize == 20 and ALN_DT.itemsize == 32
+
+
+class ChainOpt(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "w", "min_seed_len", "max_occ",
+                                         "max_chain_gap", "min_chain_weight", "max_chain_extend")] + \
+               [("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+def default_opt(**kw) -> ChainOpt:
+    o = ChainOpt()
+    O.lib().chain_opt_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Contigs:
+    """offsets / lengths / is_alt of the reference sequences (bntseq_t anns)"""
+
+    def __init__(self, lens, alt=None):
+        self.len = np.ascontiguousarray(lens, dtype=np.int32)
+        self.off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(self.len[:-1], dtype=np.int64)]), dtype=np.int64)
+        self.alt = np.ascontiguousarray(alt if alt is not None else np.zeros(len(self.len)), dtype=np.int32)
+        self.n = len(self.len)
+        self.l_pac = int(self.len.astype(np.int64).sum())
+
+
+_vp = C.c_void_p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _bind_oracle():
+    L = O.lib()
+    if getattr(L, "_chain_bound", False):
+        return L
+    L.chain_opt_default.argtypes = [C.POINTER(ChainOpt)]
+    L.chain_oracle_read.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, C.c_uint32, _vp, _vp, _vp, C.c_int,
+                                    C.POINTER(C.c_int32), _vp, _vp]
+    L.chain_oracle_read.restype = C.c_int
+    L.chain2aln_oracle_read.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp,
+                                        C.POINTER(C.c_int32), _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_uint64]
+    L.chain2aln_oracle_read.restype = C.c_int
+    L.chain_regs_finish.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, _vp]
+    L._chain_bound = True
+    return L
+
+
+def oracle_chains(opt, ctg: Contigs, l_query, rbeg, qq, score, layout_all):
+    """mem_chain + mem_chain_flt of one read -> (chains[CHAIN_DT], seeds[CSEED_DT])"""
+    L = _bind_oracle()
+    n = len(rbeg)
+    rbeg = np.ascontiguousarray(rbeg, dtype=np.uint64); qq = np.ascontiguousarray(qq, dtype=np.int32); score = np.ascontiguousarray(score, dtype=np.uint32)
+    chains = np.zeros(max(n, 1), dtype=CHAIN_DT); cs = np.zeros(max(n, 1), dtype=CSEED_DT)
+    nc = C.c_int32(0)
+    rc = L.chain_oracle_read(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(ctg.alt), l_query, n, _ptr(rbeg), _ptr(qq),
+                             _ptr(score), int(layout_all), C.byref(nc), _ptr(chains), _ptr(cs))
+    if rc:
+        raise RuntimeError(f"chain_oracle_read rc={rc}")
+    chains = chains[:nc.value]
+    ns = int(chains["n"].sum()) if nc.value else 0
+    return chains, cs[:ns]
+
+
+def oracle_chain2aln(opt, ctg: Contigs, fwd, query, chains, cseeds, cap=4096, cap_bytes=1 << 22):
+    """mem_chain2aln over the chains of one read -> (regs[REG_DT], [jobs_short, jobs_long], [(q, t) bytes per side])"""
+    L = _bind_oracle()
+    regs = np.zeros(cap, dtype=REG_DT)
+    jobs = [np.zeros(cap, dtype=JOB_DT), np.zeros(cap, dtype=JOB_DT)]
+    qb = [np.zeros(cap_bytes, dtype=np.uint8), np.zeros(cap_bytes, dtype=np.uint8)]
+    tb = [np.zeros(cap_bytes, dtype=np.uint8), np.zeros(cap_bytes, dtype=np.uint8)]
+    qpp = (_vp * 2)(_ptr(qb[0]), _ptr(qb[1])); tpp = (_vp * 2)(_ptr(tb[0]), _ptr(tb[1]))
+    nr = C.c_int32(0); nj = (C.c_int32 * 2)(0, 0)
+    chains = np.ascontiguousarray(chains); cseeds = np.ascontiguousarray(cseeds)
+    query = np.ascontiguousarray(query, dtype=np.uint8)
+    rc = L.chain2aln_oracle_read(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(fwd), len(query), _ptr(query),
+                                 len(chains), _ptr(chains), _ptr(cseeds), C.byref(nr), _ptr(regs), cap, nj, _ptr(jobs[0]), _ptr(jobs[1]), cap,
+                                 qpp, tpp, cap_bytes)
+    if rc:
+        raise RuntimeError(f"chain2aln_oracle_read rc={rc}")
+    out_jobs = [jobs[s][:nj[s]] for s in (0, 1)]
+    seqs = []
+    for s in (0, 1):
+        j = out_jobs[s]
+        nq = int(j["qoff"][-1] + (j["qlen"][-1] + 7) // 8 * 8) if len(j) else 0
+        nt = int(j["toff"][-1] + (j["tlen"][-1] + 7) // 8 * 8) if len(j) else 0
+        seqs.append((qb[s][:nq].copy(), tb[s][:nt].copy()))
+    return regs[:nr.value], out_jobs, seqs
+
+
+def oracle_regs_finish(l_query, regs, short_triples, long_triples):
+    L = _bind_oracle()
+    out = np.zeros(max(len(regs), 1), dtype=ALN_DT)
+    st = np.ascontiguousarray(short_triples, dtype=np.int32).reshape(-1); lt = np.ascontiguousarray(long_triples, dtype=np.int32).reshape(-1)
+    if st.size == 0:
+        st = np.zeros(3, np.int32)
+    if lt.size == 0:
+        lt = np.zeros(3, np.int32)
+    regs = np.ascontiguousarray(regs)
+    L.chain_regs_finish(l_query, len(regs), _ptr(regs), _ptr(st), _ptr(lt), _ptr(out))
+    return out[:len(regs)]
+
+
+# ------------------------------------------------------------------ the reference fork's own code
+_fork = None
+
+
+def have_fork() -> bool:
+    return os.path.exists(os.path.join(O.REF_DIR, "libforkmem.so"))
+
+
+def fork_lib():
+    global _fork
+    if _fork is None:
+        L = C.CDLL(os.path.join(O.REF_DIR, "libforkmem.so"))
+        L.fork_mem_read.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_uint32, _vp, _vp, _vp,
+                                    C.POINTER(C.c_int32), _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int32), _vp, C.c_int,
+                                    C.POINTER(C.c_int32), _vp, _vp, C.c_int]
+        L.fork_mem_read.restype = C.c_int
+        L.fork_mem_seq.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        L.fork_mem_seq.restype = C.POINTER(C.c_uint8)
+        _fork = L
+    return _fork
+
+
+def make_pac(fwd) -> np.ndarray:
+    """the reference's .pac packing: 4 bases per byte, base l at bits ((~l & 3) << 1) (src/bntseq.c _set_pac)"""
+    fwd = np.asarray(fwd, dtype=np.uint8)
+    n = len(fwd)
+    pad = (-n) % 4
+    f = np.concatenate([fwd, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+    return np.ascontiguousarray((f[:, 0] << 6) | (f[:, 1] << 4) | (f[:, 2] << 2) | f[:, 3]).astype(np.uint8)
+
+
+def fork_read(opt, ctg: Contigs, pac, query, rbeg, qq, score, cap=4096):
+    """the unmodified fork: mem_chain -> mem_chain_flt -> mem_flt_chained_seeds -> mem_chain2aln per chain.
+    Seeds in the reference's full layout (every SMEM group holds all `score` rows)."""
+    L = fork_lib()
+    n = len(rbeg)
+    rbeg = np.ascontiguousarray(rbeg, dtype=np.uint64); qq = np.ascontiguousarray(qq, dtype=np.int32); score = np.ascontiguousarray(score, dtype=np.uint32)
+    query = np.ascontiguousarray(query, dtype=np.uint8)
+    chains = np.zeros(max(n, 1), dtype=CHAIN_DT); cs = np.zeros(max(n, 1), dtype=CSEED_DT)
+    regs = np.zeros(cap, dtype=REG_DT)
+    jobs = [np.zeros(cap, dtype=JOB_DT), np.zeros(cap, dtype=JOB_DT)]
+    nc = C.c_int32(0); nr = C.c_int32(0); nj = (C.c_int32 * 2)(0, 0)
+    rc = L.fork_mem_read(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(ctg.alt), _ptr(pac), len(query), _ptr(query),
+                         n, _ptr(rbeg), _ptr(qq), _ptr(score), C.byref(nc), _ptr(chains), len(chains), _ptr(cs), len(cs),
+                         C.byref(nr), _ptr(regs), cap, nj, _ptr(jobs[0]), _ptr(jobs[1]), cap)
+    if rc:
+        raise RuntimeError(f"fork_mem_read rc={rc}")
+    chains = chains[:nc.value]
+    ns = int(chains["n"].sum()) if nc.value else 0
+    seqs = []
+    for s in (0, 1):
+        pair = []
+        for which in (0, 1):
+            nb = C.c_uint64(0)
+            p = L.fork_mem_seq(s, which, C.byref(nb))
+            pair.append(np.ctypeslib.as_array(p, shape=(nb.value,)).copy() if nb.value else np.zeros(0, np.uint8))
+        seqs.append(tuple(pair))
+    return chains, cs[:ns], regs[:nr.value], [jobs[s][:nj[s]] for s in (0, 1)], seqs

@@ -1,0 +1,218 @@
+/*
+ * oracle/fork_mem_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+ * Entry point around the UNMODIFIED host code of the reference fork (src/bwamem.c compiled as
+ * C++ exactly like the reference Makefile:14 does), built by oracle/build_ref.sh from the sources
+ * where they lie into oracle/_ref/libforkmem.so.  It calls, per read and in the order of the
+ * reference worker (src/bwamem.c:2055-2093):
+ *     mem_chain -> mem_chain_flt -> mem_flt_chained_seeds -> mem_chain2aln for every chain
+ * and returns the chains, the alignment-region records and the extension jobs that
+ * fill_extension handed to the SHORT / LONG batches.  This file contains no reference code.
+ *
+ * What it has to provide because the fork's host code cannot run without a GPU:
+ *   - gasal_host_batch_fill / gasal_host_alns_resize / Parameters: GASAL2's versions sit on
+ *     cudaHostAlloc'ed pages (GASAL2/src/host_batch.cpp:79-153, interfaces.cpp:26-78); here the
+ *     same contract (append `size` bytes at `idx`, pad to a multiple of 8 with N_CODE = 4, return
+ *     the new running offset) over one malloc'ed buffer per side.
+ *   - the timing / statistics globals that src/bwamem.c declares extern (src/fastmap.c:138-160).
+ * mem_chain_t and mem_chain_v are private to src/bwamem.c (:318-329); their layout is declared
+ * again here so the chains can be read back.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <vector>
+#include "bwamem.h"
+#include "bntseq.h"
+#include "utils.h"
+#include "GPUSeed/seed_gen.h"
+
+/* ---- globals the fork's bwamem.c / kthread.c expect from fastmap.c ---- */
+time_struct *extension_time = NULL;
+uint64_t *no_of_extensions = NULL;
+double *load_balance_waste_time = NULL;
+double total_load_balance_waste_time = 0;
+gasal_gpu_storage_v *gpu_storage_vec_arr = NULL;
+
+/* ---- private types of src/bwamem.c:318-329 ---- */
+typedef struct {
+    int n, m, first, rid;
+    uint32_t w : 29, kept : 2, is_alt : 1;
+    float frac_rep;
+    int64_t pos;
+    mem_seed_t *seeds;
+} mem_chain_t;
+typedef struct { size_t n, m; mem_chain_t *a; } mem_chain_v;
+
+mem_chain_v mem_chain(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, int len, const uint8_t *seq, mem_seed_v_gpu *gpu_results, int j);
+int mem_chain_flt(const mem_opt_t *opt, int n_chn, mem_chain_t *a);
+void mem_flt_chained_seeds(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, int n_chn, mem_chain_t *a);
+void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, const mem_chain_t *c,
+                   mem_alnreg_v *regs, int *curr_read_offset, int *curr_ref_offset, gpu_batch *curr_gpu_batch_short, gpu_batch *curr_gpu_batch_long);
+
+/* ---- GASAL2 host-side contract over plain memory ---- */
+struct SideBuf { std::vector<uint8_t> q, t; };
+static SideBuf g_buf[2];
+static gasal_gpu_storage_t *g_sto[2] = {NULL, NULL};
+
+Parameters::Parameters(int argc_, char **argv_) : sa(1), sb(4), gapo(6), gape(1), print_out(0), n_threads(1), k_band(0), isPacked(false), isReverseComplement(false), argc(argc_), argv(argv_) {}
+Parameters::~Parameters() {}
+
+uint32_t gasal_host_batch_fill(gasal_gpu_storage_t *sto, uint32_t idx, const char *data, uint32_t size, data_source SRC)
+{
+    int side = sto == g_sto[0] ? 0 : 1;
+    std::vector<uint8_t> &v = SRC == QUERY ? g_buf[side].q : g_buf[side].t;
+    uint32_t pad = (8 - size % 8) % 8;
+    if (v.size() < (size_t)idx + size + pad) v.resize((size_t)idx + size + pad);
+    memcpy(v.data() + idx, data, size);
+    memset(v.data() + idx + size, 4 /* N_CODE */, pad);
+    return idx + size + pad;
+}
+uint32_t gasal_host_batch_addbase(gasal_gpu_storage_t *sto, uint32_t idx, const char base, data_source SRC)
+{ /* GASAL2/src/host_batch.cpp:156-159: one byte, no padding (only bns_get_seq_gpu uses it; not on this path) */
+    int side = sto == g_sto[0] ? 0 : 1;
+    std::vector<uint8_t> &v = SRC == QUERY ? g_buf[side].q : g_buf[side].t;
+    if (v.size() < (size_t)idx + 1) v.resize((size_t)idx + 1);
+    v[idx] = (uint8_t)base;
+    return idx + 1;
+}
+void gasal_host_alns_resize(gasal_gpu_storage_t *sto, int new_max, Parameters *)
+{
+    sto->host_query_batch_offsets = (uint32_t *)realloc(sto->host_query_batch_offsets, (size_t)new_max * 4);
+    sto->host_target_batch_offsets = (uint32_t *)realloc(sto->host_target_batch_offsets, (size_t)new_max * 4);
+    sto->host_query_batch_lens = (uint32_t *)realloc(sto->host_query_batch_lens, (size_t)new_max * 4);
+    sto->host_target_batch_lens = (uint32_t *)realloc(sto->host_target_batch_lens, (size_t)new_max * 4);
+    sto->host_seed_scores = (uint32_t *)realloc(sto->host_seed_scores, (size_t)new_max * 4);
+    sto->host_max_n_alns = (uint32_t)new_max;
+}
+void gasal_aln_async(gasal_gpu_storage_t *, uint32_t, uint32_t, uint32_t, Parameters *) { fprintf(stderr, "fork_mem_shim: gasal_aln_async is not available\n"); abort(); }
+int gasal_is_aln_async_done(gasal_gpu_storage_t *) { return -2; }
+extern "C" int bit_vec_filter_sse1(char *, char *, int, int) { fprintf(stderr, "fork_mem_shim: the SHD filter is not built\n"); abort(); return 0; }
+
+static gasal_gpu_storage_t *new_storage(void)
+{
+    gasal_gpu_storage_t *s = (gasal_gpu_storage_t *)calloc(1, sizeof(*s));
+    gasal_host_alns_resize(s, 1024, NULL);
+    s->host_max_query_batch_bytes = s->host_max_target_batch_bytes = 0x7fffffff;
+    return s;
+}
+
+/* ---- flat records handed back to Python ---- */
+extern "C" {
+
+typedef struct {
+    int32_t a, b, o_del, e_del, o_ins, e_ins, w, min_seed_len, max_occ, max_chain_gap, min_chain_weight, max_chain_extend;
+    float mask_level, drop_ratio;
+} fork_opt_t;
+
+typedef struct { int64_t pos; int32_t rid, n, w, kept, first, is_alt; float frac_rep; int32_t seed_off; } fork_chain_t;
+typedef struct { int64_t rbeg; int32_t qbeg, len, score, pad; } fork_seed_t;
+typedef struct {
+    int64_t rb_est, re_est, target_seed_begin;
+    int32_t qb_est, qe_est, rid, score, truesc, align_sides, where_is_long, query_seed_begin, seedlen0, seedcov, w;
+    float frac_rep;
+} fork_reg_t;
+typedef struct { uint32_t qoff, qlen, toff, tlen, h0; } fork_job_t;
+
+/* seeds in the reference layout of mem_seed_v_gpu (seed_gen.h:68-75): every SMEM group holds all `score` rows.
+ * Returns 0, or -1 when an output capacity is too small.  Job sequences of side s (0 SHORT, 1 LONG) can be read
+ * with fork_mem_seq() until the next call. */
+int fork_mem_read(const fork_opt_t *fo, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                  const uint8_t *pac, int l_query, const uint8_t *query,
+                  uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qbeg_qend, const uint32_t *score,
+                  int32_t *n_chains, fork_chain_t *chains, int cap_chains, fork_seed_t *cseeds, int cap_cseeds,
+                  int32_t *n_regs, fork_reg_t *regs_out, int cap_regs,
+                  int32_t n_jobs[2], fork_job_t *jobs_short, fork_job_t *jobs_long, int cap_jobs)
+{
+    mem_opt_t *opt = mem_opt_init();
+    opt->a = fo->a; opt->b = fo->b; opt->o_del = fo->o_del; opt->e_del = fo->e_del; opt->o_ins = fo->o_ins; opt->e_ins = fo->e_ins;
+    opt->w = fo->w; opt->min_seed_len = fo->min_seed_len; opt->max_occ = fo->max_occ; opt->max_chain_gap = fo->max_chain_gap;
+    opt->min_chain_weight = fo->min_chain_weight; opt->max_chain_extend = fo->max_chain_extend;
+    opt->mask_level = fo->mask_level; opt->drop_ratio = fo->drop_ratio;
+    bwa_fill_scmat(opt->a, opt->b, opt->mat);
+
+    bntseq_t bns;
+    memset(&bns, 0, sizeof(bns));
+    bns.l_pac = l_pac; bns.n_seqs = n_ctg;
+    std::vector<bntann1_t> anns(n_ctg);
+    char nm[] = "ctg";
+    for (int i = 0; i < n_ctg; ++i) { memset(&anns[i], 0, sizeof(bntann1_t)); anns[i].offset = ctg_off[i]; anns[i].len = ctg_len[i]; anns[i].is_alt = ctg_alt ? ctg_alt[i] : 0; anns[i].name = nm; anns[i].anno = nm; }
+    bns.anns = anns.data();
+
+    mem_seed_v_gpu gr;
+    memset(&gr, 0, sizeof(gr));
+    uint32_t zero = 0;
+    gr.rbeg = (bwtint_t_gpu *)rbeg; gr.qbeg = (int2 *)qbeg_qend; gr.score = (uint32_t *)score;
+    gr.n_ref_pos_fow_rev_results = &n_seeds; gr.n_ref_pos_fow_rev_prefix_sums = &zero;
+
+    if (!g_sto[0]) { g_sto[0] = new_storage(); g_sto[1] = new_storage(); }
+    gpu_batch gb[2];
+    for (int s = 0; s < 2; ++s) {
+        memset(&gb[s], 0, sizeof(gpu_batch));
+        gb[s].gpu_storage = g_sto[s];
+        g_sto[s]->current_n_alns = 0;
+        g_buf[s].q.clear(); g_buf[s].t.clear();
+    }
+    int cur_read_off[2] = {0, 0}, cur_ref_off[2] = {0, 0};
+
+    std::vector<uint8_t> q(query, query + l_query);
+    mem_chain_v chn = mem_chain(opt, NULL, &bns, l_query, q.data(), &gr, 0);
+    chn.n = mem_chain_flt(opt, (int)chn.n, chn.a);
+    mem_flt_chained_seeds(opt, &bns, pac, l_query, q.data(), (int)chn.n, chn.a);
+
+    int rc = 0, so = 0;
+    *n_chains = (int32_t)chn.n;
+    for (size_t i = 0; i < chn.n; ++i) {
+        const mem_chain_t *c = &chn.a[i];
+        if ((int)i < cap_chains) {
+            fork_chain_t *o = &chains[i];
+            o->pos = c->pos; o->rid = c->rid; o->n = c->n; o->w = (int32_t)c->w; o->kept = (int32_t)c->kept; o->first = c->first;
+            o->is_alt = (int32_t)c->is_alt; o->frac_rep = c->frac_rep; o->seed_off = so;
+        } else rc = -1;
+        for (int k = 0; k < c->n; ++k, ++so) {
+            if (so < cap_cseeds) { cseeds[so].rbeg = c->seeds[k].rbeg; cseeds[so].qbeg = c->seeds[k].qbeg; cseeds[so].len = c->seeds[k].len; cseeds[so].score = c->seeds[k].score; cseeds[so].pad = 0; }
+            else rc = -1;
+        }
+    }
+
+    mem_alnreg_v regs;
+    regs.n = regs.m = 0; regs.a = NULL;
+    for (size_t i = 0; i < chn.n; ++i) {
+        mem_chain2aln(opt, &bns, pac, l_query, q.data(), &chn.a[i], &regs, cur_read_off, cur_ref_off, &gb[SHORT], &gb[LONG]);
+        free(chn.a[i].seeds);
+    }
+    free(chn.a);
+    *n_regs = (int32_t)regs.n;
+    for (size_t i = 0; i < regs.n; ++i) {
+        if ((int)i >= cap_regs) { rc = -1; break; }
+        const mem_alnreg_t *a = &regs.a[i];
+        fork_reg_t *o = &regs_out[i];
+        o->rb_est = a->rb_est; o->re_est = a->re_est; o->target_seed_begin = a->target_seed_begin;
+        o->qb_est = a->qb_est; o->qe_est = a->qe_est; o->rid = a->rid; o->score = a->score; o->truesc = a->truesc;
+        o->align_sides = a->align_sides; o->where_is_long = a->where_is_long; o->query_seed_begin = a->query_seed_begin;
+        o->seedlen0 = a->seedlen0; o->seedcov = a->seedcov; o->w = a->w; o->frac_rep = a->frac_rep;
+    }
+    free(regs.a);
+    for (int s = 0; s < 2; ++s) {
+        n_jobs[s] = gb[s].n_seqs;
+        fork_job_t *jo = s == 0 ? jobs_short : jobs_long;
+        for (int k = 0; k < gb[s].n_seqs; ++k) {
+            if (k >= cap_jobs) { rc = -1; break; }
+            jo[k].qoff = g_sto[s]->host_query_batch_offsets[k]; jo[k].qlen = g_sto[s]->host_query_batch_lens[k];
+            jo[k].toff = g_sto[s]->host_target_batch_offsets[k]; jo[k].tlen = g_sto[s]->host_target_batch_lens[k];
+            jo[k].h0 = g_sto[s]->host_seed_scores[k];
+        }
+    }
+    free(opt);
+    return rc;
+}
+
+/* byte buffers of the last call: side 0 SHORT / 1 LONG, which 0 query / 1 target */
+const uint8_t *fork_mem_seq(int side, int which, uint64_t *n_bytes)
+{
+    std::vector<uint8_t> &v = which == 0 ? g_buf[side].q : g_buf[side].t;
+    *n_bytes = v.size();
+    return v.data();
+}
+
+} /* extern "C" */
