@@ -253,6 +253,87 @@ int  bwa_b200_pipeline_totals(bwa_b200_pipeline_t *p, uint64_t out[3]);
 int  bwa_b200_pipeline_profile(bwa_b200_pipeline_t *p, int enable);
 int  bwa_b200_pipeline_kernel_times(bwa_b200_pipeline_t *p, const char **names, float *ms, int cap);
 
+/* ------------------------------------- seeds -> chains -> extension jobs -> alignment regions */
+/* The step between the two hot paths in the reference worker (src/bwamem.c:2055-2093 and :2286-2306), on the
+ * device, so that a read batch goes seeds -> chains -> jobs -> extension -> regions without leaving HBM
+ * (SURVEY.md 8f row 1).  Bit-exact with the fork's host code:
+ *   mem_chain (:404-476, test_and_merge :337-359, the chain kbtree of src/kbtree.h), mem_chain_flt (:488-560),
+ *   mem_chain2aln (:1170-1479: rmax window per chain, seeds by descending score, the estimated-extent test that
+ *   skips seeds inside an earlier region, left / right jobs with h0 = seed length, SHORT / LONG batch choice),
+ *   the local-vs-to-end rule (:1892-1901) and the region arithmetic (:2286-2306).
+ * mem_flt_chained_seeds (:970-990) only acts on reads longer than about 700 bases (it runs mem_seed_sw);
+ * such reads are refused with BWA_B200_ERR_ARG.  Re-seeding, mem_sort_dedup_patch and everything after it
+ * stay with the caller. */
+typedef struct {               /* the mem_opt_t fields this stage reads (src/bwamem.h:34-73) */
+    int32_t a, b, o_del, e_del, o_ins, e_ins, w;
+    int32_t min_seed_len, max_occ, max_chain_gap, min_chain_weight, max_chain_extend;
+    float   mask_level, drop_ratio;
+} bwa_b200_chain_params_t;
+void bwa_b200_chain_params_default(bwa_b200_chain_params_t *p);      /* mem_opt_init, src/bwamem.c:107-150 */
+
+typedef struct {               /* mem_chain_t after mem_chain_flt (src/bwamem.c:318-324) */
+    int64_t pos;               /* rbeg of the first seed (the kbtree key)              */
+    int32_t rid, n, w, kept, first, is_alt;
+    float   frac_rep;
+    int32_t seed_off;          /* first seed of the chain within the read's chain seeds */
+} bwa_b200_chain_t;
+typedef struct { int64_t rbeg; int32_t qbeg, len, score, pad; } bwa_b200_chain_seed_t;      /* mem_seed_t */
+
+typedef struct {               /* one mem_alnreg_t (src/bwamem.h:82-112), the fields this stage sets */
+    int64_t rb, re;            /* [rb, re) on the reference, after extension            */
+    int64_t rb_est, re_est, target_seed_begin;
+    int32_t qb, qe, score, truesc;
+    int32_t qb_est, qe_est, rid, align_sides, where_is_long, query_seed_begin, seedlen0, seedcov, w;
+    float   frac_rep;
+    int32_t left_tlen, right_tlen;   /* target window lengths of the left / right extension job    */
+    int32_t job_short, job_long;     /* index of the region's job in the SHORT / LONG batch, or -1 */
+} bwa_b200_region_t;
+
+typedef struct { uint32_t qoff, qlen, toff, tlen, h0; } bwa_b200_job_t;   /* offsets in bases, multiples of 8 */
+
+/* flat result of a batch; arrays are malloc'ed by the call and released with bwa_b200_alignments_free.
+ * Regions of read r are regions[region_off[r] .. + n_regions_per_read[r]), in the order mem_chain2aln creates
+ * them.  With want_detail != 0 the chains and the extension jobs are returned as well: jobs[0 .. n_jobs_short)
+ * are the SHORT batch in the reference's order, the LONG batch follows; job sequences are 4-bit packed. */
+typedef struct {
+    uint64_t n_reads, n_regions, n_chains, n_chain_seeds, n_jobs_short, n_jobs_long, q_words, t_words;
+    uint32_t *n_regions_per_read; uint64_t *region_off; bwa_b200_region_t *regions;
+    uint32_t *n_chains_per_read;  uint64_t *chain_off;  bwa_b200_chain_t *chains;
+    uint64_t *chain_seed_off;     bwa_b200_chain_seed_t *chain_seeds;
+    bwa_b200_job_t *jobs; uint32_t *qpacked, *tpacked; bwa_b200_ext_result_t *job_res;
+} bwa_b200_alignments_t;
+void bwa_b200_alignments_free(bwa_b200_alignments_t *a);
+
+typedef struct bwa_b200_aligner bwa_b200_aligner_t;
+/* idx must have the forward reference attached (bwa_b200_index_attach_ref).  Contigs default to one sequence
+ * [0, l_pac); set the reference's bntann1_t offsets / lengths / is_alt flags for a multi-sequence index. */
+int  bwa_b200_aligner_create(const bwa_b200_index_t *idx, uint64_t max_reads, uint64_t max_words, bwa_b200_aligner_t **out);
+int  bwa_b200_aligner_set_contigs(bwa_b200_aligner_t *a, int32_t n, const int64_t *offset, const int32_t *len, const int32_t *is_alt);
+void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a);
+/* reads in, regions out: seeding (as bwa_b200_seed_host) then chains, jobs, extension, regions */
+int  bwa_b200_align_host(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,
+                         uint64_t n_reads, const bwa_b200_seed_params_t *sp, const bwa_b200_chain_params_t *cp,
+                         const bwa_b200_ext_params_t *ep, int want_detail, bwa_b200_alignments_t *out);
+/* the same from given seeds (host arrays in the layout of bwa_b200_seeds_t).  layout_all != 0: every SMEM group
+ * holds all `score` rows and is sampled with step score / max_occ, the reference's mem_seed_v_gpu
+ * (src/bwamem.c:419-431); 0: a group holds only the sampled rows (bwa_b200_seed_* with max_occ > 0). */
+int  bwa_b200_align_seeds_host(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,
+                               uint64_t n_reads, const bwa_b200_seeds_t *seeds, int layout_all, const bwa_b200_chain_params_t *cp,
+                               const bwa_b200_ext_params_t *ep, int want_detail, bwa_b200_alignments_t *out);
+/* device-resident batch: reads in HBM, regions left in HBM (bwa_b200_align_device_view); returns when done */
+int  bwa_b200_align_device(bwa_b200_aligner_t *a, const uint32_t *dev_packed, const uint64_t *dev_word_off, const uint32_t *dev_read_len,
+                           uint64_t n_reads, uint32_t max_read_len, const bwa_b200_seed_params_t *sp,
+                           const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep);
+typedef struct {
+    uint64_t n_reads, n_regions, n_jobs_short, n_jobs_long, n_seeds, cells;
+    const uint32_t *n_regions_per_read; const uint64_t *region_off; const bwa_b200_region_t *regions;   /* device pointers */
+} bwa_b200_align_view_t;
+int  bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v);
+void *bwa_b200_aligner_stream(bwa_b200_aligner_t *a);
+uint64_t bwa_b200_aligner_launches(const bwa_b200_aligner_t *a);
+int  bwa_b200_aligner_profile(bwa_b200_aligner_t *a, int enable);
+int  bwa_b200_aligner_kernel_times(bwa_b200_aligner_t *a, const char **names, float *ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif
