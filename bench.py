@@ -166,6 +166,75 @@ def run_reference(args, rank, world, dist):
     print(json.dumps(line), flush=True)
 
 
+def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world):
+    """The same batch through bwa_b200_align_*: seeding, then mem_chain / mem_chain_flt / mem_chain2aln on the device, every
+    extension job of every kept chain (not just the longest seed's), the region arithmetic -- SURVEY 8f row 1.  Extension runs
+    with the same band / z-drop as the headline step.  Reported under sub_metrics.chained, timed like the headline."""
+    import torch
+    import torch.distributed as dist
+    al = pkg.Aligner(idx, n, int(d_packed.numel()))
+    sp, cp, ep = pkg.SeedParams(19, 500), pkg.chain_params(w=100), pkg.ext_params()
+    stream = torch.cuda.ExternalStream(al.stream)
+
+    def step():
+        al.align_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, cp, ep)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dref:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = al.launches
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ev[k][0].record(stream)
+        step()                       # returns when the regions are in HBM (one host round trip inside: the job count)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = al.launches - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dref:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    v = al.view()
+    al.profile(True)
+    kt = {}
+    for k in range(min(args.steps, 5)):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step()
+        for name, x in al.kernel_times():
+            kt.setdefault(name, []).append(x)
+    al.profile(False)
+    # host buffers in, malloc'ed regions out
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps, 5))
+    n_reg = 0
+    for _ in range(reps):
+        out = pkg.Alignments()
+        pkg.check(pkg.lib().bwa_b200_align_host(al.h, pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, 0, out))
+        n_reg = int(out.n_regions)
+        pkg.lib().bwa_b200_alignments_free(out)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dref:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    kavg = {k: float(np.mean(x)) for k, x in kt.items()}
+    ext_ms = sum(x for k, x in kavg.items() if k.startswith("ext_"))
+    res = {"reads_per_s": world * n * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps,
+           "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_d2h_bytes_per_step": int(n_reg * 112 + n * 12),
+           "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
+           "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
+           "gpu_launches": int(launches), "kernel_ms": kavg,
+           "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"}
+    al.destroy()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,6 +246,7 @@ def main():
     ap.add_argument("--genome", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="skip the seeds -> chains -> jobs -> extension -> regions stage (sub_metrics.chained)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -295,6 +365,10 @@ def main():
     d2h = int(n * 72)
     mapped = int((out_np["seed_qbeg"] >= 0).sum())
 
+    chained = None
+    if not args.no_chain:
+        chained = run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world)
+
     if rank != 0:
         if dref:
             dist.destroy_process_group()
@@ -390,7 +464,7 @@ def main():
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
         "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
                         "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
-                        "kernel_ms": kavg, "oracle_work_per_read": per_read},
+                        "kernel_ms": kavg, "oracle_work_per_read": per_read, "chained": chained},
     }
     print(json.dumps(line), flush=True)
     if dref:

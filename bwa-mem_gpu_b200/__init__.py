@@ -96,7 +96,42 @@ SYMBOLS = [
     "bwa_b200_index_attach_ref", "bwa_b200_pipeline_create", "bwa_b200_pipeline_destroy", "bwa_b200_seed_extend_host",
     "bwa_b200_seed_extend_device", "bwa_b200_pipeline_sync", "bwa_b200_pipeline_stream", "bwa_b200_pipeline_launches",
     "bwa_b200_pipeline_totals", "bwa_b200_pipeline_profile", "bwa_b200_pipeline_kernel_times",
+    "bwa_b200_chain_params_default", "bwa_b200_alignments_free", "bwa_b200_aligner_create", "bwa_b200_aligner_set_contigs",
+    "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
+    "bwa_b200_align_device_view", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
+    "bwa_b200_aligner_kernel_times",
 ]
+
+
+class ChainParams(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "w", "min_seed_len", "max_occ",
+                                         "max_chain_gap", "min_chain_weight", "max_chain_extend")] + \
+               [("mask_level", C.c_float), ("drop_ratio", C.c_float)]
+
+
+CHAIN_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("n", "<i4"), ("w", "<i4"), ("kept", "<i4"), ("first", "<i4"),
+                        ("is_alt", "<i4"), ("frac_rep", "<f4"), ("seed_off", "<i4")], align=True)
+CHAIN_SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4"), ("score", "<i4"), ("pad", "<i4")], align=True)
+REGION_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("rb_est", "<i8"), ("re_est", "<i8"), ("target_seed_begin", "<i8"),
+                         ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                         ("qb_est", "<i4"), ("qe_est", "<i4"), ("rid", "<i4"), ("align_sides", "<i4"), ("where_is_long", "<i4"),
+                         ("query_seed_begin", "<i4"), ("seedlen0", "<i4"), ("seedcov", "<i4"), ("w", "<i4"), ("frac_rep", "<f4"),
+                         ("left_tlen", "<i4"), ("right_tlen", "<i4"), ("job_short", "<i4"), ("job_long", "<i4")], align=True)
+JOB_DTYPE = np.dtype([("qoff", "<u4"), ("qlen", "<u4"), ("toff", "<u4"), ("tlen", "<u4"), ("h0", "<u4")], align=True)
+assert CHAIN_DTYPE.itemsize == 40 and CHAIN_SEED_DTYPE.itemsize == 24 and REGION_DTYPE.itemsize == 112 and JOB_DTYPE.itemsize == 20
+
+
+class Alignments(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_reads", "n_regions", "n_chains", "n_chain_seeds", "n_jobs_short", "n_jobs_long",
+                                          "q_words", "t_words")] + \
+               [(k, C.c_void_p) for k in ("n_regions_per_read", "region_off", "regions", "n_chains_per_read", "chain_off", "chains",
+                                          "chain_seed_off", "chain_seeds", "jobs", "qpacked", "tpacked", "job_res")]
+
+
+class AlignView(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_reads", "n_regions", "n_jobs_short", "n_jobs_long", "n_seeds", "cells")] + \
+               [(k, C.c_void_p) for k in ("n_regions_per_read", "region_off", "regions")]
+
 
 _lib = None
 vp = C.c_void_p
@@ -166,6 +201,24 @@ def lib():
         L.bwa_b200_pipeline_totals.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.bwa_b200_pipeline_profile.argtypes = [vp, C.c_int]
         L.bwa_b200_pipeline_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+        L.bwa_b200_chain_params_default.argtypes = [C.POINTER(ChainParams)]
+        L.bwa_b200_alignments_free.argtypes = [C.POINTER(Alignments)]
+        L.bwa_b200_aligner_create.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+        L.bwa_b200_aligner_set_contigs.argtypes = [vp, C.c_int32, vp, vp, vp]
+        L.bwa_b200_aligner_destroy.argtypes = [vp]
+        L.bwa_b200_align_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams), C.POINTER(ExtParams),
+                                          C.c_int, C.POINTER(Alignments)]
+        L.bwa_b200_align_seeds_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(Seeds), C.c_int, C.POINTER(ChainParams),
+                                                C.POINTER(ExtParams), C.c_int, C.POINTER(Alignments)]
+        L.bwa_b200_align_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(SeedParams), C.POINTER(ChainParams),
+                                            C.POINTER(ExtParams)]
+        L.bwa_b200_align_device_view.argtypes = [vp, C.POINTER(AlignView)]
+        L.bwa_b200_aligner_stream.argtypes = [vp]
+        L.bwa_b200_aligner_stream.restype = vp
+        L.bwa_b200_aligner_launches.argtypes = [vp]
+        L.bwa_b200_aligner_launches.restype = C.c_uint64
+        L.bwa_b200_aligner_profile.argtypes = [vp, C.c_int]
+        L.bwa_b200_aligner_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
         _lib = L
     return _lib
 
@@ -413,4 +466,96 @@ class Pipeline:
     def destroy(self):
         if self.h:
             lib().bwa_b200_pipeline_destroy(self.h)
+            self.h = None
+
+
+def chain_params(**kw) -> ChainParams:
+    p = ChainParams()
+    lib().bwa_b200_chain_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _take(ptr, n, dtype):
+    """copy n records out of a malloc'ed C array"""
+    dtype = np.dtype(dtype)
+    if not ptr or n == 0:
+        return np.zeros(0, dtype)
+    return np.frombuffer(C.string_at(ptr, int(n) * dtype.itemsize), dtype=dtype).copy()
+
+
+class Aligner:
+    """seeds -> chains -> extension jobs -> extension -> alignment regions on the device (bwa_b200_align_*)."""
+
+    def __init__(self, index: Index, max_reads: int, max_words: int):
+        self.h = vp()
+        self.index = index
+        check(lib().bwa_b200_aligner_create(index.h, max_reads, max_words, C.byref(self.h)))
+
+    def set_contigs(self, offset, length, is_alt=None):
+        off = np.ascontiguousarray(offset, dtype=np.int64); ln = np.ascontiguousarray(length, dtype=np.int32)
+        alt = np.ascontiguousarray(is_alt, dtype=np.int32) if is_alt is not None else None
+        check(lib().bwa_b200_aligner_set_contigs(self.h, ln.size, _p(off), _p(ln), _p(alt)))
+
+    @staticmethod
+    def _unpack(out: Alignments, detail: bool):
+        n = int(out.n_reads)
+        r = dict(n_regions=_take(out.n_regions_per_read, n, np.uint32), region_off=_take(out.region_off, n, np.uint64),
+                 regions=_take(out.regions, out.n_regions, REGION_DTYPE))
+        if detail:
+            nj = int(out.n_jobs_short + out.n_jobs_long)
+            r.update(n_chains=_take(out.n_chains_per_read, n, np.uint32), chain_off=_take(out.chain_off, n, np.uint64),
+                     chain_seed_off=_take(out.chain_seed_off, n, np.uint64), chains=_take(out.chains, out.n_chains, CHAIN_DTYPE),
+                     chain_seeds=_take(out.chain_seeds, out.n_chain_seeds, CHAIN_SEED_DTYPE), jobs=_take(out.jobs, nj, JOB_DTYPE),
+                     qpacked=_take(out.qpacked, out.q_words, np.uint32), tpacked=_take(out.tpacked, out.t_words, np.uint32),
+                     job_res=_take(out.job_res, nj * 6, np.int32).reshape(-1, 6), n_jobs_short=int(out.n_jobs_short),
+                     n_jobs_long=int(out.n_jobs_long))
+        lib().bwa_b200_alignments_free(C.byref(out))
+        return r
+
+    def align_host(self, packed, word_off, read_len, seed_p: SeedParams, chain_p: ChainParams, ext_p: ExtParams, detail=False):
+        out = Alignments()
+        check(lib().bwa_b200_align_host(self.h, _p(packed), _p(word_off), _p(read_len), read_len.size, C.byref(seed_p), C.byref(chain_p),
+                                        C.byref(ext_p), int(detail), C.byref(out)))
+        return self._unpack(out, detail)
+
+    def align_seeds_host(self, packed, word_off, read_len, rbeg, qq, score, n_seeds, seed_off, layout_all, chain_p, ext_p, detail=False):
+        rbeg = np.ascontiguousarray(rbeg, np.uint64); qq = np.ascontiguousarray(qq, np.int32); score = np.ascontiguousarray(score, np.uint32)
+        n_seeds = np.ascontiguousarray(n_seeds, np.uint32); seed_off = np.ascontiguousarray(seed_off, np.uint64)
+        sd = Seeds(read_len.size, rbeg.size, C.cast(_p(rbeg), C.POINTER(C.c_uint64)), C.cast(_p(qq), C.POINTER(C.c_int32)),
+                   C.cast(_p(score), C.POINTER(C.c_uint32)), C.cast(_p(n_seeds), C.POINTER(C.c_uint32)), C.cast(_p(seed_off), C.POINTER(C.c_uint64)))
+        out = Alignments()
+        check(lib().bwa_b200_align_seeds_host(self.h, _p(packed), _p(word_off), _p(read_len), read_len.size, C.byref(sd), int(layout_all),
+                                              C.byref(chain_p), C.byref(ext_p), int(detail), C.byref(out)))
+        return self._unpack(out, detail)
+
+    def align_device(self, d_packed, d_woff, d_len, n, max_read_len, seed_p, chain_p, ext_p):
+        check(lib().bwa_b200_align_device(self.h, d_packed, d_woff, d_len, n, max_read_len, C.byref(seed_p), C.byref(chain_p), C.byref(ext_p)))
+
+    def view(self) -> AlignView:
+        v = AlignView()
+        check(lib().bwa_b200_align_device_view(self.h, C.byref(v)))
+        return v
+
+    def profile(self, on: bool):
+        check(lib().bwa_b200_aligner_profile(self.h, int(on)))
+
+    def kernel_times(self):
+        names = (C.c_char_p * 96)()
+        ms = (C.c_float * 96)()
+        n = lib().bwa_b200_aligner_kernel_times(self.h, names, ms, 96)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    @property
+    def stream(self) -> int:
+        return int(lib().bwa_b200_aligner_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_aligner_launches(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_aligner_destroy(self.h)
             self.h = None

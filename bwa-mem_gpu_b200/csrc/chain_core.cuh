@@ -553,4 +553,98 @@ CH_FN void region_finish(bwa_b200_region_t &a, int l_query, const int32_t *long3
     }
 }
 
+
+// ------------------------------------------------------------------------------------ job sequences
+// Sequences of an extension job, cut eight bases (one 4-bit packed word, first base in the high nibble) at a time:
+// fill_extension's copies (src/bwamem.c:1102-1167) of the read slice and of bns_fetch_seq's window, reversed for a left
+// job (src/bwamem.c:1356-1372), padded with N (code 4) to the word boundary as gasal_host_batch_fill pads to 8
+// (GASAL2/src/host_batch.cpp:100-102).  The reference text is T = fwd + revcomp(fwd) over the 2-bit forward strand
+// (16 bases per word, base 0 in the top two bits); a job's window never crosses l_pac (the rmax clamp above).
+struct JobAux { int64_t start; int32_t qfrom; uint32_t read_flags; };   // flags: bit 31 left job, bit 30 reverse strand
+constexpr uint32_t AUX_LEFT = 1u << 31, AUX_REV = 1u << 30, AUX_READ = AUX_REV - 1;
+
+CH_FN uint32_t ld_word(const uint32_t *a, int64_t i, int64_t n) { return (i >= 0 && i < n) ? a[i] : 0u; }
+CH_FN uint32_t pac8(const uint32_t *pac, int64_t n_words, int64_t f)
+{   // fwd[f .. f+8) as 16 bits, fwd[f] in the top two
+    const int64_t wi = f >> 4;
+    const uint64_t w = (uint64_t)ld_word(pac, wi, n_words) << 32 | ld_word(pac, wi + 1, n_words);
+    return (uint32_t)((w << ((f & 15) << 1)) >> 48);
+}
+CH_FN uint32_t read8(const uint32_t *rd, int64_t n_words, int64_t p)
+{   // read[p .. p+8) as eight nibbles
+    const int64_t wi = p >> 3;
+    const uint64_t w = (uint64_t)ld_word(rd, wi, n_words) << 32 | ld_word(rd, wi + 1, n_words);
+    return (uint32_t)((w << ((p & 7) << 2)) >> 32);
+}
+CH_FN uint32_t rev8x2(uint32_t x)
+{   // eight 2-bit fields of the low 16 bits in reverse order
+    x = ((x & 0x00ffu) << 8) | ((x >> 8) & 0x00ffu);
+    x = ((x & 0x0f0fu) << 4) | ((x >> 4) & 0x0f0fu);
+    return ((x & 0x3333u) << 2) | ((x >> 2) & 0x3333u);
+}
+CH_FN uint32_t rev8x4(uint32_t x)
+{   // eight nibbles in reverse order
+    x = (x << 16) | (x >> 16);
+    x = ((x & 0x00ff00ffu) << 8) | ((x >> 8) & 0x00ff00ffu);
+    return ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+}
+CH_FN uint32_t spread2to4(uint32_t x)
+{   // 8 x 2 bits -> 8 nibbles, order kept
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    return (x | (x << 2)) & 0x33333333u;
+}
+CH_FN uint32_t pad_n(uint32_t w, int64_t valid)
+{   // the first `valid` nibbles of w, N in the others
+    if (valid >= 8) return w;
+    const uint32_t m = valid <= 0 ? 0u : 0xffffffffu << ((8 - (int)valid) << 2);
+    return (w & m) | (0x44444444u & ~m);
+}
+CH_FN uint32_t cut_target_word(const uint32_t *pac, int64_t pac_words, int64_t l_pac, const JobAux &a, uint32_t wi, uint32_t tlen)
+{
+    const int64_t i0 = (int64_t)wi << 3;
+    const bool left = a.read_flags & AUX_LEFT, rev = a.read_flags & AUX_REV;
+    uint32_t x;
+    if (!left) x = !rev ? pac8(pac, pac_words, a.start + i0) : rev8x2(pac8(pac, pac_words, (l_pac << 1) - 8 - (a.start + i0))) ^ 0xffffu;
+    else x = !rev ? rev8x2(pac8(pac, pac_words, a.start - 8 - i0)) : pac8(pac, pac_words, (l_pac << 1) - a.start + i0) ^ 0xffffu;
+    return pad_n(spread2to4(x), (int64_t)tlen - i0);
+}
+CH_FN uint32_t cut_query_word(const uint32_t *rd, int64_t rd_words, const JobAux &a, uint32_t wi, uint32_t qlen)
+{
+    const int64_t i0 = (int64_t)wi << 3;
+    const uint32_t x = !(a.read_flags & AUX_LEFT) ? read8(rd, rd_words, a.qfrom + i0) : rev8x4(read8(rd, rd_words, a.qfrom - 8 - i0));
+    return pad_n(x, (int64_t)qlen - i0);
+}
+
+// the two jobs of a region: side 0 = left, 1 = right -> {qlen, tlen}; which one is the LONG batch's: where_is_long
+CH_FN void region_job(const bwa_b200_region_t &a, int l_query, int side, uint32_t *qlen, uint32_t *tlen, JobAux *aux, uint32_t read, int64_t l_pac)
+{
+    const uint32_t rev = a.target_seed_begin >= l_pac ? AUX_REV : 0u;
+    if (side == 0) { *qlen = (uint32_t)a.query_seed_begin; *tlen = (uint32_t)a.left_tlen; aux->start = a.target_seed_begin; aux->qfrom = a.query_seed_begin; aux->read_flags = read | AUX_LEFT | rev; }
+    else { *qlen = (uint32_t)(l_query - a.query_seed_begin - a.seedlen0); *tlen = (uint32_t)a.right_tlen; aux->start = a.target_seed_begin + a.seedlen0; aux->qfrom = a.query_seed_begin + a.seedlen0; aux->read_flags = read | rev; }
+}
+
+// every job of a read in the order fill_extension receives them: emit(region index, is_long, qlen, tlen, h0, aux)
+template <class F>
+CH_FN void read_jobs(const bwa_b200_region_t *regs, int n_regs, int l_query, uint32_t read, int64_t l_pac, F &&emit)
+{
+    for (int i = 0; i < n_regs; ++i) {
+        const bwa_b200_region_t &a = regs[i];
+        if (a.align_sides <= 0) continue;
+        uint32_t ql, tl;
+        JobAux aux;
+        const int long_side = a.where_is_long ? 1 : 0;
+        if (a.align_sides == 2) { region_job(a, l_query, 1 - long_side, &ql, &tl, &aux, read, l_pac); emit(i, 0, ql, tl, (uint32_t)a.seedlen0, aux); }
+        region_job(a, l_query, long_side, &ql, &tl, &aux, read, l_pac);
+        emit(i, 1, ql, tl, (uint32_t)a.seedlen0, aux);
+    }
+}
+
+// (aln_score, query_batch_end, target_batch_end) of a job: the local-vs-to-end rule, src/bwamem.c:1892-1901
+CH_FN void ext_triple(const bwa_b200_ext_result_t &r, int qlen, int pen_clip, int32_t out[3])
+{
+    if (r.gscore <= 0 || r.gscore <= r.score - pen_clip) { out[0] = r.score; out[1] = r.qle; out[2] = r.tle; }
+    else { out[0] = r.gscore; out[1] = qlen; out[2] = r.gtle; }
+}
+
 } // namespace b200chain

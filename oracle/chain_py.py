@@ -185,3 +185,51 @@ def fork_read(opt, ctg: Contigs, pac, query, rbeg, qq, score, cap=4096):
             pair.append(np.ctypeslib.as_array(p, shape=(nb.value,)).copy() if nb.value else np.zeros(0, np.uint8))
         seqs.append(tuple(pair))
     return chains, cs[:ns], regs[:nr.value], [jobs[s][:nj[s]] for s in (0, 1)], seqs
+
+
+def oracle_align_batch(opt, ctg: Contigs, fwd, reads, rbeg, qq, score, n_seeds, seed_off, layout_all, ksw_params, n_threads=2):
+    """The whole seeds -> chains -> jobs -> ksw_extend2 -> regions stage of a read batch on the CPU (the checker of
+    bwa_b200_align_*): per read mem_chain / mem_chain_flt / mem_chain2aln, then every job of the batch through the
+    ksw oracle in the reference's batch order (SHORT batch, then LONG batch), the local-vs-to-end rule and the
+    region arithmetic."""
+    per = []
+    for r, query in enumerate(reads):
+        so, ns = int(seed_off[r]), int(n_seeds[r])
+        oc, osd = oracle_chains(opt, ctg, len(query), rbeg[so:so + ns], qq[so:so + ns], score[so:so + ns], layout_all)
+        regs, jobs, seqs = oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
+        per.append((oc, osd, regs, jobs, seqs))
+    out = dict(n_chains=np.array([len(p[0]) for p in per], np.uint32), n_regions=np.array([len(p[2]) for p in per], np.uint32),
+               chains=np.concatenate([p[0] for p in per]) if per else np.zeros(0, CHAIN_DT),
+               chain_seeds=np.concatenate([p[1] for p in per]) if per else np.zeros(0, CSEED_DT),
+               regs=np.concatenate([p[2] for p in per]) if per else np.zeros(0, REG_DT))
+    # batch-level job arrays: SHORT batch of every read in read order, then the LONG batch
+    jl, ql, tl = [], [], []
+    nq = nt = 0
+    for side in (0, 1):
+        for p in per:
+            j = p[3][side].copy()
+            j["qoff"] += nq; j["toff"] += nt
+            jl.append(j); ql.append(p[4][side][0]); tl.append(p[4][side][1])
+            nq += len(p[4][side][0]); nt += len(p[4][side][1])
+    jobs = np.concatenate(jl) if jl else np.zeros(0, JOB_DT)
+    qseq = np.concatenate(ql) if ql else np.zeros(0, np.uint8)
+    tseq = np.concatenate(tl) if tl else np.zeros(0, np.uint8)
+    n_short = int(sum(len(p[3][0]) for p in per))
+    out.update(jobs=jobs, qseq=qseq, tseq=tseq, n_jobs_short=n_short, n_jobs_long=len(jobs) - n_short)
+    if len(jobs):
+        jd = dict(qseq=np.ascontiguousarray(qseq if len(qseq) else np.zeros(8, np.uint8)), tseq=np.ascontiguousarray(tseq if len(tseq) else np.zeros(8, np.uint8)),
+                  qoff=np.ascontiguousarray(jobs["qoff"]), toff=np.ascontiguousarray(jobs["toff"]),
+                  qlen=np.ascontiguousarray(jobs["qlen"]), tlen=np.ascontiguousarray(jobs["tlen"]), h0=np.ascontiguousarray(jobs["h0"]))
+        res, cnt = O.ksw_batch(jd, ksw_params, n_threads=n_threads)
+        tri = np.stack(O.gasal_triple(res, jobs["qlen"], ksw_params.pen_clip), axis=1).astype(np.int32)
+    else:
+        res, cnt, tri = np.zeros((0, 6), np.int32), dict(cells=0, rows=0, rect=0), np.zeros((0, 3), np.int32)
+    out.update(job_res=res, cells=cnt["cells"])
+    alns = []
+    i_s, i_l = 0, n_short
+    for r, p in enumerate(per):
+        ns_, nl_ = len(p[3][0]), len(p[3][1])
+        alns.append(oracle_regs_finish(len(reads[r]), p[2], tri[i_s:i_s + ns_], tri[i_l:i_l + nl_]))
+        i_s += ns_; i_l += nl_
+    out["aln"] = np.concatenate(alns) if alns else np.zeros(0, ALN_DT)
+    return out

@@ -35,3 +35,21 @@ extern "C" int chain_host_read(const bwa_b200_chain_params_t *P, int n_ctg, cons
             region_finish(regs[i], l_query, regs[i].job_long >= 0 ? long3 + 3 * regs[i].job_long : long3, regs[i].job_short >= 0 ? short3 + 3 * regs[i].job_short : short3);
     return nc;
 }
+
+// job sequences of one read's regions for one batch (0 SHORT, 1 LONG), cut with the kernels' word functions;
+// outputs the jobs' {qlen, tlen, h0} and their packed words back to back.  Returns the job count.
+extern "C" int chain_host_cut(const uint32_t *pac, int64_t pac_words, int64_t l_pac, const uint32_t *rd, int64_t rd_words, int l_query,
+                              int n_regs, const bwa_b200_region_t *regs, int batch, uint32_t *lens3, uint32_t *qwords, uint32_t *twords,
+                              uint32_t *n_qw, uint32_t *n_tw)
+{
+    int n = 0;
+    uint32_t nq = 0, nt = 0;
+    read_jobs(regs, n_regs, l_query, 7u, l_pac, [&](int, int is_long, uint32_t ql, uint32_t tl, uint32_t h0, const JobAux &aux) {
+        if (is_long != batch) return;
+        lens3[3 * n] = ql; lens3[3 * n + 1] = tl; lens3[3 * n + 2] = h0; ++n;
+        for (uint32_t w = 0; w < (ql + 7) / 8; ++w) qwords[nq++] = cut_query_word(rd, rd_words, aux, w, ql);
+        for (uint32_t w = 0; w < (tl + 7) / 8; ++w) twords[nt++] = cut_target_word(pac, pac_words, l_pac, aux, w, tl);
+    });
+    *n_qw = nq; *n_tw = nt;
+    return n;
+}

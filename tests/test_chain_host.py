@@ -49,7 +49,40 @@ def emul():
         assert nc >= 0, nc
         chains = chains[:nc]
         return chains, cs[:int(chains["n"].sum()) if nc else 0], regs[:counts[0]], counts
+    L.chain_host_cut.restype = C.c_int
+    L.chain_host_cut.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    run.lib = L
     return run
+
+
+def pack2(fwd):
+    """2-bit forward reference as the device holds it: 16 bases per word, base 0 in the top two bits, one spare word"""
+    n = len(fwd)
+    f = np.zeros((n + 15) // 16 * 16 + 16, np.uint32)
+    f[:n] = fwd & 3
+    f = f.reshape(-1, 16)
+    return np.ascontiguousarray((f << (2 * (15 - np.arange(16, dtype=np.uint32)))[None, :]).sum(axis=1).astype(np.uint32))
+
+
+def pack4(codes):
+    """4-bit packing of one sequence: 8 bases per word, base 0 in the high nibble; a partial last word is N-padded"""
+    n = len(codes)
+    f = np.full((n + 7) // 8 * 8, 4, np.uint32)
+    f[:n] = codes
+    f = f.reshape(-1, 8)
+    return np.ascontiguousarray((f << (4 * (7 - np.arange(8, dtype=np.uint32)))[None, :]).sum(axis=1).astype(np.uint32))
+
+
+def host_cut(emul, pac2, l_pac, query, regs, batch):
+    rd = pack4(query)
+    rd[-1] &= np.uint32((0xffffffff << (4 * ((-len(query)) % 8))) & 0xffffffff)      # the read's own padding is zero, as pack_codes leaves it
+    cap = max(1, len(regs)) * 2
+    lens3 = np.zeros(3 * cap, np.uint32); qw = np.zeros(cap * 64, np.uint32); tw = np.zeros(cap * 128, np.uint32)
+    nq = C.c_uint32(0); nt = C.c_uint32(0)
+    regs = np.ascontiguousarray(regs)
+    n = emul.lib.chain_host_cut(pac2.ctypes.data, len(pac2), l_pac, rd.ctypes.data, len(rd), len(query), len(regs), regs.ctypes.data, batch,
+                                lens3.ctypes.data, qw.ctypes.data, tw.ctypes.data, C.addressof(nq), C.addressof(nt))
+    return lens3[:3 * n].reshape(-1, 3), qw[:nq.value], tw[:nt.value]
 
 
 def test_region_struct_layout():
@@ -61,13 +94,14 @@ def test_chain_source_matches_oracle(emul, lens, max_occ, seed):
     ctg = CP.Contigs(lens, alt=[0, 1, 0][:len(lens)])
     opt = CP.default_opt(max_occ=max_occ)
     fwd, cases = CC.make_cases(seed, 300, lens, max_occ)
+    pac2 = pack2(fwd)
     rng = np.random.default_rng(seed)
     n_multi = 0
     for query, rb, qq, sc in cases:
         for layout_all in (1, 0):
             a = (rb, qq, sc) if layout_all else CC.to_compact(rb, qq, sc, max_occ)
             oc, osd = CP.oracle_chains(opt, ctg, len(query), a[0], a[1], a[2], layout_all)
-            oregs, ojobs, _ = CP.oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
+            oregs, ojobs, oseqs = CP.oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
             # made-up extension results: the region arithmetic must agree too
             s3 = rng.integers(0, 200, size=(max(len(ojobs[0]), 1), 3)).astype(np.int32)
             l3 = rng.integers(0, 200, size=(max(len(ojobs[1]), 1), 3)).astype(np.int32)
@@ -88,6 +122,12 @@ def test_chain_source_matches_oracle(emul, lens, max_occ, seed):
             assert (long_q == ojobs[1]["qlen"]).all() and (long_t == ojobs[1]["tlen"]).all()
             assert (short_q == ojobs[0]["qlen"]).all() and (short_t == ojobs[0]["tlen"]).all()
             assert (regs["seedlen0"][any_] == ojobs[1]["h0"]).all()
+            # job sequences, cut a word at a time from the 2-bit reference and the packed read
+            for batch in (0, 1):
+                lens3, qw, tw = host_cut(emul, pac2, ctg.l_pac, query, regs, batch)
+                oj = ojobs[batch]
+                assert (lens3[:, 0] == oj["qlen"]).all() and (lens3[:, 1] == oj["tlen"]).all() and (lens3[:, 2] == oj["h0"]).all()
+                assert qw.tobytes() == pack4(oseqs[batch][0]).tobytes() and tw.tobytes() == pack4(oseqs[batch][1]).tobytes()
             aln = CP.oracle_regs_finish(len(query), oregs, s3, l3)
             for f in ("rb", "re", "qb", "qe", "score", "truesc"):
                 assert (regs[f] == aln[f]).all(), f

