@@ -200,7 +200,7 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     v = al.view()
-    al.profile(True)
+    al.profile(2)
     kt = {}
     for k in range(min(args.steps, 5)):
         with torch.cuda.stream(stream):
@@ -224,7 +224,7 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     kavg = {k: float(np.mean(x)) for k, x in kt.items()}
-    ext_ms = sum(x for k, x in kavg.items() if k.startswith("ext_"))
+    ext_ms = kavg.get("ext_phase", 0.0)
     res = {"reads_per_s": world * n * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps,
            "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_d2h_bytes_per_step": int(n_reg * 112 + n * 12),
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
@@ -314,17 +314,20 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
     gpu_launches = pl.launches - launches0
-    # per-kernel durations: the same steps again with a CUDA-event pair around every launch (kernels of a step then
-    # run back to back on one stream; in the timed steps above the extension bins overlap on side streams)
-    pl.profile(True)
-    ktimes = {}
-    for k in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        step_device()
-        pl.sync()
-        for name, ms in pl.kernel_times():
-            ktimes.setdefault(name, []).append(ms)
+    # per-kernel durations: the same steps again with CUDA events on the pipeline stream.  Mode 2 = an event pair around
+    # every seeding / glue kernel and ONE pair around the extension launch set, whose length bins overlap on side streams
+    # exactly as in the timed steps above; mode 1 = a pair around every launch, which runs the bins one after another
+    # (the per-bin breakdown).
+    ktimes, ktimes_bins = {}, {}
+    for mode, dst in ((2, ktimes), (1, ktimes_bins)):
+        pl.profile(mode)
+        for k in range(args.steps if mode == 2 else min(args.steps, 5)):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            step_device()
+            pl.sync()
+            for name, ms in pl.kernel_times():
+                dst.setdefault(name, []).append(ms)
     torch.cuda.synchronize()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     tot = pl.totals()
@@ -419,7 +422,9 @@ def main():
                 roofline["traffic_source"] = tr["source"]
         except Exception as ex:  # noqa: BLE001
             log("no ncu traffic figure:", ex)
-    ext_ms = sum(v for k, v in kavg.items() if k.startswith("ext_inter_kernel") or k.startswith("ext_pair_kernel"))
+    kbins = {k: float(np.mean(v)) for k, v in ktimes_bins.items()}
+    ext_ms = kavg.get("ext_phase", 0.0)          # sort + every bin, bins overlapping: what the extension costs inside a step
+    ext_ms_serial = sum(v for k, v in kbins.items() if k.startswith("ext_inter_kernel") or k.startswith("ext_pair_kernel"))
     gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
     seed_ms = sum(seed_k.values())
     # INT-ALU roofline of the extension kernel: 15 integer ops per cell, 64 int lanes/clk/SM on the ALU pipe
@@ -428,7 +433,10 @@ def main():
                 "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None,
                 "peak_gcups_s16x2": 2 * int_peak_gops / 15.0, "frac_s16x2": gcups / (2 * int_peak_gops / 15.0) if gcups else None,
                 "ops_per_cell": 15,
-                "cells_per_step": tot["cells"], "ms_per_step": ext_ms}
+                "cells_per_step": tot["cells"], "ms_per_step": ext_ms,
+                "timing": "CUDA events around the whole extension launch set (sort + all length bins, overlapping on side streams)",
+                "gcups_bins_serialised": tot["cells"] / (ext_ms_serial / 1e3) / 1e9 if ext_ms_serial > 0 else None,
+                "ms_bins_serialised": ext_ms_serial}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -464,7 +472,7 @@ def main():
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
         "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
                         "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
-                        "kernel_ms": kavg, "oracle_work_per_read": per_read, "chained": chained},
+                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained},
     }
     print(json.dumps(line), flush=True)
     if dref:

@@ -186,7 +186,7 @@ struct bwa_b200_aligner {
     Cnt b_tot{};
     bool b_detail = false;
     uint64_t launches = 0;
-    b200::Prof prof; bool profiling = false;
+    b200::Prof prof; int profiling = 0;
 };
 
 extern "C" void bwa_b200_chain_params_default(bwa_b200_chain_params_t *p)
@@ -268,7 +268,7 @@ extern "C" void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a)
     if (!a) return;
     cudaSetDevice(a->device);
     cudaStreamSynchronize(a->stream);
-    a->seeder->prof = nullptr; a->ext->prof = nullptr;
+    a->seeder->prof = nullptr; a->ext->prof = nullptr; a->ext->phase_prof = nullptr;
     bwa_b200_extender_destroy(a->ext);
     bwa_b200_seeder_destroy(a->seeder);
     cudaFree(a->d_ctg_off); cudaFree(a->d_ctg_len); cudaFree(a->d_ctg_alt);
@@ -305,7 +305,7 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
 {
     cudaStream_t st = a->stream;
     b200::Prof *prof = a->profiling ? &a->prof : nullptr;
-    a->ext->prof = prof;
+    a->ext->prof = a->profiling == 1 ? prof : nullptr; a->ext->phase_prof = a->profiling == 2 ? prof : nullptr;
     const uint32_t n = (uint32_t)n_reads;
     if (a->n_ctg < 1) { b200::set_error("align: the reference is longer than 2^31; set the contigs first (bwa_b200_aligner_set_contigs)"); return BWA_B200_ERR_ARG; }
     if (cp->e_del <= 0 || cp->e_ins <= 0 || cp->max_occ < 1) { b200::set_error("align: bad chain parameters"); return BWA_B200_ERR_ARG; }
@@ -546,7 +546,7 @@ extern "C" uint64_t bwa_b200_aligner_launches(const bwa_b200_aligner_t *a) { ret
 extern "C" int bwa_b200_aligner_profile(bwa_b200_aligner_t *a, int enable)
 {
     if (!a) return BWA_B200_ERR_ARG;
-    a->profiling = enable != 0;
+    a->profiling = enable == 2 ? 2 : (enable != 0);
     return BWA_B200_OK;
 }
 extern "C" int bwa_b200_aligner_kernel_times(bwa_b200_aligner_t *a, const char **names, float *ms, int cap)

@@ -439,6 +439,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     if (p->e_del <= 0 || p->e_ins <= 0) { b200::set_error("extend: gap extension penalties must be positive"); return BWA_B200_ERR_ARG; }
     ExtParams P;
     to_dev_params(p, &P);
+    if (e->phase_prof) e->phase_prof->begin("ext_phase", e->stream);
     B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
     if (e->prof) e->prof->begin("ext_sort", e->stream);
     // the column-pair s16x2 kernel takes any matrix with 0 < max <= 31 and one score for a query N
@@ -512,6 +513,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
             B200_CUDA(cudaEventRecord(e->ev_join[k], e->side[k]));
             B200_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join[k], 0));
         }
+    if (e->phase_prof) e->phase_prof->end(e->stream);
     B200_CUDA(cudaGetLastError());
     return BWA_B200_OK;
 }

@@ -94,7 +94,8 @@ struct bwa_b200_extender {
     uint64_t launches = 0;
     bool pending = false;
     int smem_optin = 0;
-    b200::Prof *prof = nullptr;
+    b200::Prof *prof = nullptr;          // an event pair around every launch (bins then run one after another)
+    b200::Prof *phase_prof = nullptr;    // one event pair around the whole launch set (bins overlap on the side streams)
     bool own_stream = true;
 };
 

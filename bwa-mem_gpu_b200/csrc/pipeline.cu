@@ -7,6 +7,7 @@
 // claimed.  Kernels here are plumbing around the two hot kernels (seed.cu, extend.cu): a
 // per-read selection, a word-parallel sequence cutter and a gather.
 #include "internal.h"
+#include "chain_core.cuh"
 
 namespace {
 
@@ -21,7 +22,9 @@ __device__ __forceinline__ int max_gap(const Rules &r, int qlen)
     return l < (r.w << 1) ? l : (r.w << 1);
 }
 
-struct JobAux { int64_t start; int32_t qfrom; int32_t dir; };   // dir -1: left job (reversed), +1: right job
+using b200chain::JobAux;          // {start, qfrom, read | AUX_LEFT | AUX_REV}: shared with the chaining stage (chain_core.cuh)
+using b200chain::AUX_LEFT;
+using b200chain::AUX_REV;
 
 // one lane per read: choose the seed, shape both jobs
 __global__ void choose_kernel(uint32_t n_reads, int64_t l_pac, Rules R, const uint32_t *__restrict__ read_len,
@@ -50,7 +53,7 @@ __global__ void choose_kernel(uint32_t n_reads, int64_t l_pac, Rules R, const ui
     o.seed_rbeg = -1; o.seed_qbeg = -1; o.seed_qend = -1; o.n_seeds = (int32_t)ns; o.h0 = 0;
     o.left = bwa_b200_ext_result_t{0, 0, 0, 0, 0, 0}; o.right = o.left;
     uint32_t lq = 0, lt = 0, rq = 0, rt = 0, h0 = 0;
-    JobAux la{0, 0, -1}, ra{0, 0, 1};
+    JobAux la{0, 0, r | AUX_LEFT}, ra{0, 0, r};
     if (best >= 0) {
         int2 q = qq[so + best];
         int64_t rb = (int64_t)rbeg[so + best];
@@ -64,7 +67,8 @@ __global__ void choose_kernel(uint32_t n_reads, int64_t l_pac, Rules R, const ui
         o.seed_rbeg = rb; o.seed_qbeg = q.x; o.seed_qend = q.y; o.h0 = (int32_t)h0;
         lq = (uint32_t)q.x; lt = q.x > 0 ? (uint32_t)(rb - rmax0) : 0u;
         rq = (uint32_t)(len - q.y); rt = q.y < len ? (uint32_t)(rmax1 - (rb + slen)) : 0u;
-        la.start = rb; la.qfrom = q.x; ra.start = rb + slen; ra.qfrom = q.y;
+        const uint32_t rev = rb >= l_pac ? AUX_REV : 0u;
+        la.start = rb; la.qfrom = q.x; la.read_flags |= rev; ra.start = rb + slen; ra.qfrom = q.y; ra.read_flags |= rev;
     }
     out[r] = o;
     const uint32_t jl = 2 * r, jr = 2 * r + 1;
@@ -72,50 +76,28 @@ __global__ void choose_kernel(uint32_t n_reads, int64_t l_pac, Rules R, const ui
     jq_len[jr] = rq; jt_len[jr] = rt; j_h0[jr] = h0; jq_off[jr] = jr * qstride * 8; jt_off[jr] = jr * tstride * 8; aux[jr] = ra;
 }
 
-__device__ __forceinline__ uint32_t text_base(const uint32_t *__restrict__ pac, int64_t l_pac, int64_t p)
-{ // T = fwd + revcomp(fwd); pac: 16 bases per word, base i at bits (15 - i%16)*2
-    bool rev = p >= l_pac;
-    int64_t q = rev ? 2 * l_pac - 1 - p : p;
-    uint32_t b = (pac[q >> 4] >> ((~q & 15) << 1)) & 3u;
-    return rev ? 3u - b : b;
-}
-
-// one lane per output word (8 bases) of every job's query and target slot
-__global__ void cut_kernel(uint32_t n_jobs, int64_t l_pac, const uint32_t *__restrict__ pac,
-                           const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off,
-                           const uint32_t *__restrict__ jq_len, const uint32_t *__restrict__ jt_len,
-                           const JobAux *__restrict__ aux, uint32_t qstride, uint32_t tstride,
-                           uint32_t *__restrict__ qp, uint32_t *__restrict__ tp)
+// one lane per output word (8 bases) of every job's query and target slot; a word is cut with one funnel shift of the
+// packed read / 2-bit reference plus bit spreading (chain_core.cuh), not base by base
+__global__ void __launch_bounds__(256)
+cut_kernel(uint32_t n_jobs, int64_t l_pac, const uint32_t *__restrict__ pac, int64_t pac_words,
+           const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off,
+           const uint32_t *__restrict__ jq_len, const uint32_t *__restrict__ jt_len,
+           const JobAux *__restrict__ aux, uint32_t qstride, uint32_t tstride,
+           uint32_t *__restrict__ qp, uint32_t *__restrict__ tp)
 {
     const uint32_t per_job = qstride + tstride;
     const uint64_t total = (uint64_t)n_jobs * per_job;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(g / per_job), wi = (uint32_t)(g % per_job);
-        const JobAux a = aux[j];
         if (wi < qstride) {
             const uint32_t ql = jq_len[j];
             if (wi * 8 >= ql) continue;
             const uint64_t wo = word_off[j >> 1];
-            uint32_t wv = 0;
-            for (uint32_t u = 0; u < 8; ++u) {
-                uint32_t i = wi * 8 + u, c = 4;
-                if (i < ql) {
-                    int pos = a.dir < 0 ? a.qfrom - 1 - (int)i : a.qfrom + (int)i;
-                    c = (packed_reads[wo + (uint32_t)(pos >> 3)] >> (28 - 4 * (pos & 7))) & 15u;
-                }
-                wv |= c << (28 - 4 * u);
-            }
-            qp[(uint64_t)j * qstride + wi] = wv;
+            qp[(uint64_t)j * qstride + wi] = b200chain::cut_query_word(packed_reads + wo, (int64_t)(word_off[(j >> 1) + 1] - wo), aux[j], wi, ql);
         } else {
             const uint32_t ti = wi - qstride, tl = jt_len[j];
             if (ti * 8 >= tl) continue;
-            uint32_t wv = 0;
-            for (uint32_t u = 0; u < 8; ++u) {
-                uint32_t i = ti * 8 + u, c = 4;
-                if (i < tl) c = text_base(pac, l_pac, a.dir < 0 ? a.start - 1 - (int64_t)i : a.start + (int64_t)i);
-                wv |= c << (28 - 4 * u);
-            }
-            tp[(uint64_t)j * tstride + ti] = wv;
+            tp[(uint64_t)j * tstride + ti] = b200chain::cut_target_word(pac, pac_words, l_pac, aux[j], ti, tl);
         }
     }
 }
@@ -153,7 +135,7 @@ struct bwa_b200_pipeline {
     unsigned long long *d_live = nullptr, *h_tot = nullptr;
     uint64_t launches = 0;
     b200::Prof prof;
-    bool profiling = false;
+    int profiling = 0;            // 0 off, 1 per kernel, 2 per phase (extension bins overlap as in an unprofiled step)
     // state of the batch in flight (for overflow repair)
     const uint32_t *b_packed = nullptr; const uint64_t *b_woff = nullptr; const uint32_t *b_len = nullptr;
     uint64_t b_n = 0; uint32_t b_maxlen = 0;
@@ -233,7 +215,7 @@ extern "C" void bwa_b200_pipeline_destroy(bwa_b200_pipeline_t *p)
     if (!p) return;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
-    p->seeder->prof = nullptr; p->ext->prof = nullptr;
+    p->seeder->prof = nullptr; p->ext->prof = nullptr; p->ext->phase_prof = nullptr;
     bwa_b200_extender_destroy(p->ext);
     bwa_b200_seeder_destroy(p->seeder);
     cudaFree(p->d_jq_len); cudaFree(p->d_jt_len); cudaFree(p->d_j_h0); cudaFree(p->d_jq_off); cudaFree(p->d_jt_off); cudaFree(p->d_aux);
@@ -247,7 +229,7 @@ static int pipe_enqueue(bwa_b200_pipeline *p)
     const uint32_t n = (uint32_t)p->b_n;
     cudaStream_t st = p->stream;
     b200::Prof *prof = p->profiling ? &p->prof : nullptr;
-    p->seeder->prof = prof; p->ext->prof = prof;
+    p->seeder->prof = prof; p->ext->prof = p->profiling == 1 ? prof : nullptr; p->ext->phase_prof = p->profiling == 2 ? prof : nullptr;
     if (prof) prof->reset();
     int rc = pipe_alloc_jobs(p, p->b_maxlen, &p->b_ep);
     if (rc) return rc;
@@ -261,7 +243,7 @@ static int pipe_enqueue(bwa_b200_pipeline *p)
                                                        s->d_qq, s->seed_cap, p->qstride, p->tstride, p->b_out, p->d_jq_len, p->d_jt_len,
                                                        p->d_j_h0, p->d_jq_off, p->d_jt_off, p->d_aux)));
     B200_LAUNCH(prof, "cut_kernel", st,
-        (cut_kernel<<<p->n_sm * 16, 256, 0, st>>>(2 * n, (int64_t)p->idx->l_pac, p->idx->d_pac, p->b_packed, p->b_woff, p->d_jq_len,
+        (cut_kernel<<<p->n_sm * 16, 256, 0, st>>>(2 * n, (int64_t)p->idx->l_pac, p->idx->d_pac, (int64_t)((p->idx->l_pac + 15) / 16 + 1), p->b_packed, p->b_woff, p->d_jq_len,
                                                  p->d_jt_len, p->d_aux, p->qstride, p->tstride, p->d_qp, p->d_tp)));
     rc = b200_ext_run_packed(p->ext, &p->b_ep, 2 * n, p->d_qp, p->d_jq_off, p->d_jq_len, p->d_tp, p->d_jt_off, p->d_jt_len, p->d_j_h0, p->d_res);
     if (rc) return rc;
@@ -350,7 +332,7 @@ extern "C" int bwa_b200_pipeline_totals(bwa_b200_pipeline_t *p, uint64_t out[3])
 extern "C" int bwa_b200_pipeline_profile(bwa_b200_pipeline_t *p, int enable)
 {
     if (!p) return BWA_B200_ERR_ARG;
-    p->profiling = enable != 0;
+    p->profiling = enable == 2 ? 2 : (enable != 0);
     return BWA_B200_OK;
 }
 
