@@ -171,6 +171,35 @@ uint32_t gasal_host_batch_fill(gasal_gpu_storage_t *gpu_storage, uint32_t idx, c
     return idx + need;
 }
 
+// unpadded append of `size` bases at running offset idx (GASAL2/src/host_batch.cpp:156-236); same page rules as fill
+uint32_t gasal_host_batch_add(gasal_gpu_storage_t *gpu_storage, uint32_t idx, const char *data, uint32_t size, data_source SRC)
+{
+    host_batch_t *page = NULL;
+    uint32_t *total = NULL;
+    if (SRC == QUERY) { page = gpu_storage->extensible_host_unpacked_query_batch; total = &gpu_storage->host_max_query_batch_bytes; }
+    else if (SRC == TARGET) { page = gpu_storage->extensible_host_unpacked_target_batch; total = &gpu_storage->host_max_target_batch_bytes; }
+    else { fprintf(stderr, "[GASAL ERROR:] gasal_host_batch_add: SRC must be QUERY or TARGET\n"); exit(EXIT_FAILURE); }
+    while (page->is_locked) page = page->next;
+    if (page->page_size - page->data_size < size) {
+        if (page->next == NULL) {
+            uint32_t grow = page->page_size * 2;
+            while (grow < size) grow *= 2;
+            page->next = gasal_host_batch_new(grow, page->offset + page->data_size);
+            *total += grow;
+        } else page->next->offset = page->offset + page->data_size;
+        page->is_locked = 1;
+        page = page->next;
+    }
+    memcpy(page->data + (idx - page->offset), data, size);
+    page->data_size += size;
+    return idx + size;
+}
+
+uint32_t gasal_host_batch_addbase(gasal_gpu_storage_t *gpu_storage, uint32_t idx, const char base, data_source SRC)
+{
+    return gasal_host_batch_add(gpu_storage, idx, &base, 1, SRC);
+}
+
 void gasal_host_batch_print(host_batch_t *res)
 {
     fprintf(stderr, "[GASAL PRINT] Page data: offset=%d, next_offset=%d, data size=%d, page size=%d\n", res->offset,

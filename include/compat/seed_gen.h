@@ -16,6 +16,7 @@
 #ifndef B200_COMPAT_SEED_GEN_H
 #define B200_COMPAT_SEED_GEN_H
 
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -49,6 +50,42 @@ typedef struct {
     uint32_t     *sa_upper_bits;
     uint8_t       pack_size;
 } bwt_t_gpu;
+
+/* Host-side types the fork's driver takes from this header although GPUSeed itself never touches them
+ * (seed_gen.h:35-66): the per-read seed record / vector used by mem_chain (src/bwamem.c:323-431) and the
+ * bntseq mirror structs. */
+typedef struct {
+    int64_t  offset;
+    int32_t  len;
+    int32_t  n_ambs;
+    uint32_t gi;
+    int32_t  is_alt;
+    char    *name, *anno;
+} bntann2_t;
+
+typedef struct {
+    int64_t offset;
+    int32_t len;
+    char    amb;
+} bntamb2_t;
+
+typedef struct {
+    int64_t    l_pac;
+    int32_t    n_seqs;
+    uint32_t   seed;
+    bntann2_t *anns;
+    int32_t    n_holes;
+    bntamb2_t *ambs;
+    FILE      *fp_pac;
+} bntseq2_t;
+
+typedef struct {
+    int64_t rbeg;
+    int32_t qbeg, len;
+    int     score;
+} mem_seed_t;
+
+typedef struct { size_t n, m; mem_seed_t *a; int seed_counter; } mem_seed_v;
 
 /* flat per-file seed table consumed by mem_chain (seed_gen.h:68-75, src/bwamem.c:415-431) */
 typedef struct {
