@@ -97,7 +97,7 @@ SYMBOLS = [
     "bwa_b200_seed_extend_device", "bwa_b200_pipeline_sync", "bwa_b200_pipeline_stream", "bwa_b200_pipeline_launches",
     "bwa_b200_pipeline_totals", "bwa_b200_pipeline_profile", "bwa_b200_pipeline_kernel_times",
     "bwa_b200_chain_params_default", "bwa_b200_alignments_free", "bwa_b200_aligner_create", "bwa_b200_aligner_set_contigs",
-    "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
+    "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_host_view", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
     "bwa_b200_align_device_view", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
     "bwa_b200_aligner_kernel_times",
 ]
@@ -208,6 +208,8 @@ def lib():
         L.bwa_b200_aligner_destroy.argtypes = [vp]
         L.bwa_b200_align_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams), C.POINTER(ExtParams),
                                           C.c_int, C.POINTER(Alignments)]
+        L.bwa_b200_align_host_view.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams), C.POINTER(ExtParams),
+                                               C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.bwa_b200_align_seeds_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(Seeds), C.c_int, C.POINTER(ChainParams),
                                                 C.POINTER(ExtParams), C.c_int, C.POINTER(Alignments)]
         L.bwa_b200_align_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(SeedParams), C.POINTER(ChainParams),
@@ -519,6 +521,21 @@ class Aligner:
         check(lib().bwa_b200_align_host(self.h, _p(packed), _p(word_off), _p(read_len), read_len.size, C.byref(seed_p), C.byref(chain_p),
                                         C.byref(ext_p), int(detail), C.byref(out)))
         return self._unpack(out, detail)
+
+    def align_host_view(self, packed_ptr, woff_ptr, len_ptr, n, seed_p, chain_p, ext_p, copy=True):
+        """regions only, through the aligner's pinned result buffers (bwa_b200_align_host_view).  copy=False returns
+        numpy views of those buffers, valid until the aligner's next call."""
+        nr, a, b, c = C.c_uint64(0), vp(), vp(), vp()
+        check(lib().bwa_b200_align_host_view(self.h, packed_ptr, woff_ptr, len_ptr, n, C.byref(seed_p), C.byref(chain_p), C.byref(ext_p),
+                                             C.byref(nr), C.byref(a), C.byref(b), C.byref(c)))
+
+        def arr(ptr, cnt, dt):
+            dt = np.dtype(dt)
+            if not ptr.value or cnt == 0:
+                return np.zeros(0, dt)
+            v = np.frombuffer((C.c_char * (int(cnt) * dt.itemsize)).from_address(ptr.value), dtype=dt)
+            return v.copy() if copy else v
+        return dict(n_regions=arr(a, n, np.uint32), region_off=arr(b, n, np.uint64), regions=arr(c, nr.value, REGION_DTYPE))
 
     def align_seeds_host(self, packed, word_off, read_len, rbeg, qq, score, n_seeds, seed_off, layout_all, chain_p, ext_p, detail=False):
         rbeg = np.ascontiguousarray(rbeg, np.uint64); qq = np.ascontiguousarray(qq, np.int32); score = np.ascontiguousarray(score, np.uint32)

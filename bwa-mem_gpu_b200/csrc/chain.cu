@@ -187,6 +187,9 @@ struct bwa_b200_aligner {
     bool b_detail = false;
     uint64_t launches = 0;
     b200::Prof prof; int profiling = 0;
+    // pinned host result buffers of bwa_b200_align_host_view (grown geometrically, reused batch after batch)
+    uint32_t *p_nregs = nullptr; uint64_t *p_region_off = nullptr; uint64_t p_reads = 0;
+    bwa_b200_region_t *p_regions = nullptr; uint64_t p_region_cap = 0;
 };
 
 extern "C" void bwa_b200_chain_params_default(bwa_b200_chain_params_t *p)
@@ -281,6 +284,7 @@ extern "C" void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a)
     cudaFree(a->J.qoff); cudaFree(a->J.qlen); cudaFree(a->J.toff); cudaFree(a->J.tlen); cudaFree(a->J.h0); cudaFree(a->J.aux);
     cudaFree(a->d_res); cudaFree(a->d_qp); cudaFree(a->d_tp);
     cudaFree(a->g_rbeg); cudaFree(a->g_seed_off); cudaFree(a->g_qq); cudaFree(a->g_score); cudaFree(a->g_nseeds);
+    cudaFreeHost(a->p_nregs); cudaFreeHost(a->p_region_off); cudaFreeHost(a->p_regions);
     delete a;
 }
 
@@ -491,6 +495,48 @@ extern "C" int bwa_b200_align_host(bwa_b200_aligner_t *a, const uint32_t *packed
     a->b_detail = false;
     if (rc) return rc;
     return aligner_download(a, want_detail, out);
+}
+
+// regions into pinned buffers owned by the aligner: no allocation and no pageable staging per batch (the reference's
+// gasal_res_t arrays are pinned for the same reason, GASAL2/src/res.cpp)
+extern "C" int bwa_b200_align_host_view(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,
+                                        uint64_t n_reads, const bwa_b200_seed_params_t *sp, const bwa_b200_chain_params_t *cp,
+                                        const bwa_b200_ext_params_t *ep, uint64_t *n_regions, const uint32_t **n_regions_per_read,
+                                        const uint64_t **region_off, const bwa_b200_region_t **regions)
+{
+    if (!a || !sp || !cp || !ep || !n_regions || !n_regions_per_read || !region_off || !regions || (n_reads && (!packed || !word_off || !read_len))) {
+        b200::set_error("align_host_view: bad argument"); return BWA_B200_ERR_ARG;
+    }
+    *n_regions = 0; *n_regions_per_read = nullptr; *region_off = nullptr; *regions = nullptr;
+    if (n_reads == 0) return BWA_B200_OK;
+    B200_CUDA(cudaSetDevice(a->device));
+    uint32_t max_len = 0;
+    int rc = aligner_upload_reads(a, packed, word_off, read_len, n_reads, &max_len);
+    if (rc) return rc;
+    bwa_b200_seeder *s = a->seeder;
+    rc = bwa_b200_align_device(a, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, sp, cp, ep);
+    if (rc) return rc;
+    const uint64_t nr = a->b_tot.regs;
+    if (n_reads > a->p_reads) {
+        cudaFreeHost(a->p_nregs); cudaFreeHost(a->p_region_off); a->p_nregs = nullptr; a->p_region_off = nullptr; a->p_reads = 0;
+        const uint64_t c = std::max<uint64_t>(n_reads, a->max_reads);
+        B200_CUDA(cudaHostAlloc(&a->p_nregs, c * 4, cudaHostAllocDefault));
+        B200_CUDA(cudaHostAlloc(&a->p_region_off, c * 8, cudaHostAllocDefault));
+        a->p_reads = c;
+    }
+    if (nr > a->p_region_cap) {
+        cudaFreeHost(a->p_regions); a->p_regions = nullptr; a->p_region_cap = 0;
+        const uint64_t c = nr + nr / 4 + 1024;
+        B200_CUDA(cudaHostAlloc(&a->p_regions, c * sizeof(bwa_b200_region_t), cudaHostAllocDefault));
+        a->p_region_cap = c;
+    }
+    cudaStream_t st = a->stream;
+    B200_CUDA(cudaMemcpyAsync(a->p_nregs, a->d_nregs, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(a->p_region_off, a->d_region_off, n_reads * 8, cudaMemcpyDeviceToHost, st));
+    if (nr) B200_CUDA(cudaMemcpyAsync(a->p_regions, a->d_regions, nr * sizeof(bwa_b200_region_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    *n_regions = nr; *n_regions_per_read = a->p_nregs; *region_off = a->p_region_off; *regions = a->p_regions;
+    return BWA_B200_OK;
 }
 
 extern "C" int bwa_b200_align_seeds_host(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,

@@ -314,6 +314,13 @@ void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a);
 int  bwa_b200_align_host(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,
                          uint64_t n_reads, const bwa_b200_seed_params_t *sp, const bwa_b200_chain_params_t *cp,
                          const bwa_b200_ext_params_t *ep, int want_detail, bwa_b200_alignments_t *out);
+/* the same, regions only, into pinned host buffers owned by the aligner (valid until its next call or its
+ * destruction; not to be freed): the per-batch path of a driver, no allocation and no pageable staging.  The
+ * reference keeps its result arrays pinned for the same reason (GASAL2/src/res.cpp:10-60). */
+int  bwa_b200_align_host_view(bwa_b200_aligner_t *a, const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len,
+                              uint64_t n_reads, const bwa_b200_seed_params_t *sp, const bwa_b200_chain_params_t *cp,
+                              const bwa_b200_ext_params_t *ep, uint64_t *n_regions, const uint32_t **n_regions_per_read,
+                              const uint64_t **region_off, const bwa_b200_region_t **regions);
 /* the same from given seeds (host arrays in the layout of bwa_b200_seeds_t).  layout_all != 0: every SMEM group
  * holds all `score` rows and is sampled with step score / max_occ, the reference's mem_seed_v_gpu
  * (src/bwamem.c:419-431); 0: a group holds only the sampled rows (bwa_b200_seed_* with max_occ > 0). */

@@ -128,6 +128,12 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
         assert len(want["regs"]) > 2500
         v = al.view()
         assert v.n_regions == len(want["regs"]) and v.cells == want["cells"] and v.n_seeds == sd["total"]
+        # the same batch through the pinned-buffer entry point (twice: buffers are reused)
+        for _ in range(2):
+            pv = al.align_host_view(packed.ctypes.data, woff.ctypes.data, rl.ctypes.data, rl.size, gpu.SeedParams(19, max_occ),
+                                    gpu.chain_params(max_occ=max_occ, w=100), gpu.ext_params(w=100, zdrop=100, use_band=1))
+            assert pv["regions"].tobytes() == got["regions"].tobytes()
+            assert (pv["n_regions"] == got["n_regions"]).all() and (pv["region_off"] == got["region_off"]).all()
         al.destroy()
     oi.close()
     idx.free()
