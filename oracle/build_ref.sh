@@ -2,7 +2,7 @@
 # oracle/build_ref.sh -- TEST INFRASTRUCTURE ONLY.
 # Compiles the reference's own CPU sources, from where they lie under /root/reference,
 # into oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot):
-#   libbwaref.so   bwa_index/*.c library objects (OCC_INTV_SHIFT 7) + oracle/ref_shim.c
+#   libbwaref.so   bwa_index/*.c library objects (OCC_INTV_SHIFT 7) + oracle/ref_shim.c + oracle/ref_collect_shim.c
 #   libforkksw.so  src/ksw.c + oracle/fork_ksw_shim.c  (fork's ksw_extend2 with opt_ext)
 #   bwa7 / bwa6    the reference's index builder compiled with OCC_INTV_SHIFT 7 / 6,
 #                  i.e. the two passes of the reference's build_index.sh:46-66
@@ -32,9 +32,11 @@ for shift in 7 6; do
     objs=""; for o in $LOBJS $AOBJS; do objs="$objs $o.o"; done
     gcc $CFLAGS $objs -o "$OUT/bwa$shift" -lm -lz -lpthread -lrt
     if [ "$shift" = 7 ]; then
-      lobjs=""; for o in $LOBJS; do lobjs="$lobjs $o.o"; done
+      # ref_collect_shim.c #includes the unmodified bwamem.c (to reach its static mem_collect_intv) and so stands in for bwamem.o
+      lobjs=""; for o in $LOBJS; do [ "$o" = bwamem ] || lobjs="$lobjs $o.o"; done
       gcc -c $CFLAGS -fopenmp -I. -I"$HERE" "$HERE/ref_shim.c" -o ref_shim.o
-      gcc -shared $CFLAGS -fopenmp $lobjs ref_shim.o -o "$OUT/libbwaref.so" -lm -lz -lpthread -lrt
+      gcc -c $CFLAGS -I. -I"$HERE" "$HERE/ref_collect_shim.c" -o ref_collect_shim.o
+      gcc -shared $CFLAGS -fopenmp $lobjs ref_shim.o ref_collect_shim.o -o "$OUT/libbwaref.so" -lm -lz -lpthread -lrt
     fi )
 done
 F="$TMP/fork"; mkdir -p "$F"

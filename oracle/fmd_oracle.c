@@ -250,6 +250,84 @@ int fmd_collect_pass1(const fmd_index_t *idx, int len, const uint8_t *q, int min
     return n;
 }
 
+/* bwa_index/bwt.c:434-455 bwt_seed_strategy1: forward extension from x until the interval is smaller than max_intv
+ * and the match longer than min_len; *m gets s == 0 when nothing is found.  Returns the next x. */
+int fmd_seed_strategy1(const fmd_index_t *idx, int len, const uint8_t *q, int x, int min_len, int max_intv,
+                       fmd_intv_t *m, fmd_counters_t *c)
+{
+    fmd_intv_t ik, ok[4];
+    int i;
+    memset(m, 0, sizeof(*m));
+    if (q[x] > 3) return x + 1;
+    set_intv(idx, q[x], &ik);
+    for (i = x + 1; i < len; ++i) {
+        if (q[i] < 4) {
+            int cb = 3 - q[i];
+            uint64_t b_before = c ? c->n_bucket : 0;
+            fmd_extend(idx, &ik, ok, 0, c);
+            if (c) { c->n_extend_fwd++; c->n_bucket_fwd += c->n_bucket - b_before; }
+            if (ok[cb].s < (uint64_t)max_intv && i - x >= min_len) {
+                *m = ok[cb];
+                m->beg = x; m->end = i + 1;
+                return i + 1;
+            }
+            ik = ok[cb];
+        } else return i + 1;
+    }
+    return len;
+}
+
+static int intv_cmp(const void *pa, const void *pb)
+{ /* intv_lt: by info = start << 32 | end (bwa_index/bwamem.c:82-83); equal info means equal interval */
+    const fmd_intv_t *a = (const fmd_intv_t *)pa, *b = (const fmd_intv_t *)pb;
+    if (a->beg != b->beg) return a->beg < b->beg ? -1 : 1;
+    if (a->end != b->end) return a->end < b->end ? -1 : 1;
+    return 0;
+}
+
+/* bwa_index/bwamem.c:114-162 mem_collect_intv, all three passes and the final sort. */
+int fmd_collect_intv(const fmd_index_t *idx, int len, const uint8_t *q, int min_seed_len, const fmd_reseed_t *rs,
+                     fmd_intv_t **out, size_t *out_cap, fmd_counters_t *c)
+{
+    size_t n = 0;
+    int x = 0, m, i;
+    fmd_intv_t *tmp = (fmd_intv_t *)malloc(sizeof(fmd_intv_t) * (size_t)(len + 2));
+#define PUSH(v) do { if (n == *out_cap) { *out_cap = *out_cap ? *out_cap * 2 : 64; *out = (fmd_intv_t *)realloc(*out, *out_cap * sizeof(fmd_intv_t)); } (*out)[n++] = (v); } while (0)
+    while (x < len) {                                        /* pass 1: all SMEMs */
+        if (q[x] < 4) {
+            x = fmd_smem1(idx, len, q, x, 1, tmp, &m, c);
+            for (i = 0; i < m; ++i)
+                if (tmp[i].end - tmp[i].beg >= min_seed_len) PUSH(tmp[i]);
+        } else ++x;
+    }
+    if (rs && rs->enable) {
+        const int split_len = (int)(min_seed_len * rs->split_factor + .499);
+        const size_t old_n = n;
+        for (size_t k = 0; k < old_n; ++k) {                 /* pass 2: MEMs inside a long, rare SMEM */
+            const fmd_intv_t p = (*out)[k];
+            if (p.end - p.beg < split_len || p.s > (uint64_t)rs->split_width) continue;
+            fmd_smem1(idx, len, q, (p.beg + p.end) >> 1, (int)p.s + 1, tmp, &m, c);
+            for (i = 0; i < m; ++i)
+                if (tmp[i].end - tmp[i].beg >= min_seed_len) PUSH(tmp[i]);
+        }
+        if (rs->max_mem_intv > 0) {                          /* pass 3: LAST-like */
+            x = 0;
+            while (x < len) {
+                if (q[x] < 4) {
+                    fmd_intv_t mm;
+                    x = fmd_seed_strategy1(idx, len, q, x, min_seed_len, rs->max_mem_intv, &mm, c);
+                    if (mm.s > 0) PUSH(mm);
+                } else ++x;
+            }
+        }
+        qsort(*out, n, sizeof(fmd_intv_t), intv_cmp);
+    }
+#undef PUSH
+    free(tmp);
+    if (c) c->n_smem += (uint64_t)n;
+    return (int)n;
+}
+
 /* -------------------------------------------------------------------- SA */
 
 static inline int bwt_sym(const fmd_index_t *idx, uint64_t j) /* j: index in the '$'-less string */
@@ -302,6 +380,16 @@ int64_t fmd_seed_batch(const fmd_index_t *idx, const uint8_t *reads, const uint6
                        uint64_t *rbeg, int32_t *qbeg, int32_t *qend, uint32_t *score,
                        int64_t cap, int n_threads, fmd_counters_t *cnt)
 {
+    return fmd_seed_batch_rs(idx, reads, read_off, n_reads, min_seed_len, max_occ, NULL, n_seeds, seed_off, rbeg, qbeg, qend, score,
+                             cap, n_threads, cnt);
+}
+
+int64_t fmd_seed_batch_rs(const fmd_index_t *idx, const uint8_t *reads, const uint64_t *read_off,
+                          int64_t n_reads, int min_seed_len, int max_occ, const fmd_reseed_t *rs,
+                          uint32_t *n_seeds, uint64_t *seed_off,
+                          uint64_t *rbeg, int32_t *qbeg, int32_t *qend, uint32_t *score,
+                          int64_t cap, int n_threads, fmd_counters_t *cnt)
+{
     if (n_threads < 1) n_threads = 1;
     seed_vec_t *tv = (seed_vec_t *)calloc((size_t)n_threads, sizeof(seed_vec_t));
     fmd_counters_t *tc = (fmd_counters_t *)calloc((size_t)n_threads, sizeof(fmd_counters_t));
@@ -318,8 +406,7 @@ int64_t fmd_seed_batch(const fmd_index_t *idx, const uint8_t *reads, const uint6
 #pragma omp for schedule(dynamic, 64)
         for (int64_t r = 0; r < n_reads; ++r) {
             int len = (int)(read_off[r + 1] - read_off[r]);
-            if ((size_t)len + 2 > mem_cap) { mem_cap = (size_t)len + 2; mem = (fmd_intv_t *)realloc(mem, mem_cap * sizeof(fmd_intv_t)); }
-            int n = len >= min_seed_len ? fmd_collect_pass1(idx, len, reads + read_off[r], min_seed_len, mem, &tc[tid]) : 0;
+            int n = len >= min_seed_len ? fmd_collect_intv(idx, len, reads + read_off[r], min_seed_len, rs, &mem, &mem_cap, &tc[tid]) : 0;
             where[r] = tv[tid].n; who16[r] = (uint16_t)tid;
             uint32_t ns = 0;
             for (int i = 0; i < n; ++i) {
@@ -365,14 +452,21 @@ int64_t fmd_smem_batch(const fmd_index_t *idx, const uint8_t *reads, const uint6
                        uint32_t *n_smems, int32_t *qbeg, int32_t *qend, uint64_t *k, uint64_t *s,
                        int64_t cap, int n_threads, fmd_counters_t *cnt)
 {
+    return fmd_smem_batch_rs(idx, reads, read_off, n_reads, min_seed_len, NULL, n_smems, qbeg, qend, k, s, cap, n_threads, cnt);
+}
+
+int64_t fmd_smem_batch_rs(const fmd_index_t *idx, const uint8_t *reads, const uint64_t *read_off,
+                          int64_t n_reads, int min_seed_len, const fmd_reseed_t *rs,
+                          uint32_t *n_smems, int32_t *qbeg, int32_t *qend, uint64_t *k, uint64_t *s,
+                          int64_t cap, int n_threads, fmd_counters_t *cnt)
+{
     /* serial per-read fill; offsets are the running sum (small inputs only) */
     (void)n_threads;
     int64_t tot = 0;
     fmd_intv_t *mem = NULL; size_t mem_cap = 0;
     for (int64_t r = 0; r < n_reads; ++r) {
         int len = (int)(read_off[r + 1] - read_off[r]);
-        if ((size_t)len + 2 > mem_cap) { mem_cap = (size_t)len + 2; mem = (fmd_intv_t *)realloc(mem, mem_cap * sizeof(fmd_intv_t)); }
-        int n = len >= min_seed_len ? fmd_collect_pass1(idx, len, reads + read_off[r], min_seed_len, mem, cnt) : 0;
+        int n = len >= min_seed_len ? fmd_collect_intv(idx, len, reads + read_off[r], min_seed_len, rs, &mem, &mem_cap, cnt) : 0;
         n_smems[r] = (uint32_t)n;
         if (tot + n > cap) { free(mem); return -1; }
         for (int i = 0; i < n; ++i) {

@@ -70,6 +70,26 @@ uint64_t fmd_sa(const fmd_index_t *idx, uint64_t k, fmd_counters_t *c);
 int  fmd_collect_pass1(const fmd_index_t *idx, int len, const uint8_t *q, int min_seed_len,
                        fmd_intv_t *out, fmd_counters_t *c);
 
+/* re-seeding parameters of mem_collect_intv (mem_opt_t split_factor 1.5, split_width 10, max_mem_intv 20,
+ * bwa_index/bwamem.c:60-62); enable == 0 (or a NULL pointer) = pass 1 only, which is all the reference GPU path does */
+typedef struct { int32_t enable; float split_factor; int32_t split_width, max_mem_intv; } fmd_reseed_t;
+/* bwa_index/bwt.c:434-455 */
+int  fmd_seed_strategy1(const fmd_index_t *idx, int len, const uint8_t *q, int x, int min_len, int max_intv,
+                        fmd_intv_t *m, fmd_counters_t *c);
+/* bwa_index/bwamem.c:114-162: pass 1, then (rs->enable) passes 2 and 3 and the sort by (start, end).
+ * *out is a growable malloc'ed array (capacity *out_cap entries). */
+int  fmd_collect_intv(const fmd_index_t *idx, int len, const uint8_t *q, int min_seed_len, const fmd_reseed_t *rs,
+                      fmd_intv_t **out, size_t *out_cap, fmd_counters_t *c);
+int64_t fmd_seed_batch_rs(const fmd_index_t *idx, const uint8_t *reads, const uint64_t *read_off,
+                          int64_t n_reads, int min_seed_len, int max_occ, const fmd_reseed_t *rs,
+                          uint32_t *n_seeds, uint64_t *seed_off,
+                          uint64_t *rbeg, int32_t *qbeg, int32_t *qend, uint32_t *score,
+                          int64_t cap, int n_threads, fmd_counters_t *c);
+int64_t fmd_smem_batch_rs(const fmd_index_t *idx, const uint8_t *reads, const uint64_t *read_off,
+                          int64_t n_reads, int min_seed_len, const fmd_reseed_t *rs,
+                          uint32_t *n_smems, int32_t *qbeg, int32_t *qend, uint64_t *k, uint64_t *s,
+                          int64_t cap, int n_threads, fmd_counters_t *c);
+
 /* Whole-batch driver mirroring the result layout of seed_gpu() (seed_gen.h:68-75) but
  * locating only the rows mem_chain consumes (bwa_index/bwamem.c:278-283 sampling rule):
  *   per read r:  n_seeds[r]; seeds [off[r], off[r]+n_seeds[r]) : rbeg, qbeg, qend, and

@@ -38,6 +38,15 @@ class FmdCounters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class Reseed(C.Structure):
+    """fmd_reseed_t: re-seeding passes 2 and 3 of mem_collect_intv (stock defaults 1.5 / 10 / 20)"""
+    _fields_ = [("enable", C.c_int32), ("split_factor", C.c_float), ("split_width", C.c_int32), ("max_mem_intv", C.c_int32)]
+
+
+def reseed(split_factor=1.5, split_width=10, max_mem_intv=20):
+    return Reseed(1, split_factor, split_width, max_mem_intv)
+
+
 class KswParams(C.Structure):
     _fields_ = [("mat", C.c_int8 * 25), ("o_del", C.c_int32), ("e_del", C.c_int32), ("o_ins", C.c_int32),
                 ("e_ins", C.c_int32), ("w", C.c_int32), ("end_bonus", C.c_int32), ("zdrop", C.c_int32),
@@ -76,6 +85,12 @@ def lib():
         L.fmd_smem_batch.argtypes = [C.POINTER(FmdIndex), u8p, u64p, C.c_int64, C.c_int,
                                      u32p, i32p, i32p, u64p, u64p, C.c_int64, C.c_int, C.POINTER(FmdCounters)]
         L.fmd_smem_batch.restype = C.c_int64
+        L.fmd_seed_batch_rs.argtypes = [C.POINTER(FmdIndex), u8p, u64p, C.c_int64, C.c_int, C.c_int, C.POINTER(Reseed),
+                                        u32p, u64p, u64p, i32p, i32p, u32p, C.c_int64, C.c_int, C.POINTER(FmdCounters)]
+        L.fmd_seed_batch_rs.restype = C.c_int64
+        L.fmd_smem_batch_rs.argtypes = [C.POINTER(FmdIndex), u8p, u64p, C.c_int64, C.c_int, C.POINTER(Reseed),
+                                        u32p, i32p, i32p, u64p, u64p, C.c_int64, C.c_int, C.POINTER(FmdCounters)]
+        L.fmd_smem_batch_rs.restype = C.c_int64
         L.ksw_fill_mat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.ksw_extend_batch_oracle.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p,
                                               C.POINTER(KswParams), i32p, C.c_int, C.POINTER(KswCounters)]
@@ -137,7 +152,7 @@ class OracleIndex:
         return out
 
     def seed_batch(self, reads: np.ndarray, read_off: np.ndarray, min_seed_len=19, max_occ=500,
-                   n_threads=None, cap=None):
+                   n_threads=None, cap=None, rs=None):
         """reads: flat uint8 codes; read_off: uint64[n+1].  Returns dict of arrays + counters."""
         n = read_off.size - 1
         n_threads = n_threads or default_threads()
@@ -150,26 +165,26 @@ class OracleIndex:
             qend = np.zeros(cap, np.int32)
             score = np.zeros(cap, np.uint32)
             cnt = FmdCounters()
-            tot = lib().fmd_seed_batch(C.byref(self.idx), np.ascontiguousarray(reads), np.ascontiguousarray(read_off),
-                                       n, min_seed_len, max_occ, n_seeds, off, rbeg, qbeg, qend, score, cap,
-                                       n_threads, C.byref(cnt))
+            tot = lib().fmd_seed_batch_rs(C.byref(self.idx), np.ascontiguousarray(reads), np.ascontiguousarray(read_off),
+                                          n, min_seed_len, max_occ, C.byref(rs) if rs is not None else None,
+                                          n_seeds, off, rbeg, qbeg, qend, score, cap, n_threads, C.byref(cnt))
             if tot >= 0:
                 break
             cap *= 4
         return dict(n_seeds=n_seeds[:n], seed_off=off[:n], rbeg=rbeg[:tot], qbeg=qbeg[:tot], qend=qend[:tot],
                     score=score[:tot], total=int(tot), counters=cnt.as_dict())
 
-    def smem_batch(self, reads: np.ndarray, read_off: np.ndarray, min_seed_len=19, cap=None):
+    def smem_batch(self, reads: np.ndarray, read_off: np.ndarray, min_seed_len=19, cap=None, rs=None):
         n = read_off.size - 1
-        cap = cap or max(1024, int(reads.size))
+        cap = cap or max(1024, int(reads.size) * (4 if rs is not None else 1))
         n_smems = np.zeros(max(n, 1), np.uint32)
         qbeg = np.zeros(cap, np.int32)
         qend = np.zeros(cap, np.int32)
         k = np.zeros(cap, np.uint64)
         s = np.zeros(cap, np.uint64)
         cnt = FmdCounters()
-        tot = lib().fmd_smem_batch(C.byref(self.idx), np.ascontiguousarray(reads), np.ascontiguousarray(read_off), n,
-                                   min_seed_len, n_smems, qbeg, qend, k, s, cap, 1, C.byref(cnt))
+        tot = lib().fmd_smem_batch_rs(C.byref(self.idx), np.ascontiguousarray(reads), np.ascontiguousarray(read_off), n,
+                                      min_seed_len, C.byref(rs) if rs is not None else None, n_smems, qbeg, qend, k, s, cap, 1, C.byref(cnt))
         assert tot >= 0
         return dict(n_smems=n_smems[:n], qbeg=qbeg[:tot], qend=qend[:tot], k=k[:tot], s=s[:tot],
                     counters=cnt.as_dict())
@@ -222,10 +237,27 @@ def ref_lib():
         L.ref_ksw_extend2.restype = C.c_int
         L.ref_seed_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.ref_seed_batch.restype = C.c_int64
+        L.ref_collect_intv.argtypes = [C.c_void_p, C.c_int, u8p, C.c_int, C.c_float, C.c_int, C.c_int, u64p, C.c_int]
+        L.ref_collect_intv.restype = C.c_int
+        L.ref_collect_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, u32p, u64p, C.c_int64]
+        L.ref_collect_batch.restype = C.c_int64
         L.ref_ksw_batch.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p, i8p] + [C.c_int] * 7 + [i32p, C.c_int]
         L.ref_pipeline_batch.argtypes = [C.c_void_p, u8p, C.c_int64, u8p, u64p, C.c_int64, C.c_int, C.c_int, i8p] + [C.c_int] * 8 + [C.c_void_p, C.c_int]
         _ref = L
     return _ref
+
+
+def ref_collect_batch(handle, reads, read_off, min_seed_len=19, split_factor=1.5, split_width=10, max_mem_intv=20, cap=None):
+    """the reference's own mem_collect_intv (bwa_index/bwamem.c:114-162) over a batch: (n_smems[n], intervals[tot, 5] = x0 x1 x2 start end).
+    split_width < 0 and max_mem_intv = 0 reduce it to pass 1."""
+    n = read_off.size - 1
+    cap = cap or max(1024, int(reads.size) * 4)
+    n_smems = np.zeros(max(n, 1), np.uint32)
+    out = np.zeros(cap * 5, np.uint64)
+    tot = ref_lib().ref_collect_batch(handle, np.ascontiguousarray(reads), np.ascontiguousarray(read_off), n, min_seed_len, split_factor,
+                                      split_width, max_mem_intv, n_smems, out, cap)
+    assert tot >= 0
+    return n_smems[:n], out[:tot * 5].reshape(-1, 5)
 
 
 def ref_pipeline(handle, fwd, reads, read_off, params, min_seed_len=19, max_occ=500, n_threads=None):
