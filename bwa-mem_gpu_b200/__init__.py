@@ -52,7 +52,13 @@ class IndexInfo(C.Structure):
 
 
 class SeedParams(C.Structure):
-    _fields_ = [("min_seed_len", C.c_int32), ("max_occ", C.c_int32)]
+    """bwa_b200_seed_params_t; SeedParams(19, 500) = pass 1 only, SeedParams(19, 500, 1, 1.5, 10, 20) = stock re-seeding too"""
+    _fields_ = [("min_seed_len", C.c_int32), ("max_occ", C.c_int32), ("reseed", C.c_int32), ("split_factor", C.c_float),
+                ("split_width", C.c_int32), ("max_mem_intv", C.c_int32)]
+
+
+def seed_params(min_seed_len=19, max_occ=500, reseed=False, split_factor=1.5, split_width=10, max_mem_intv=20):
+    return SeedParams(min_seed_len, max_occ, int(bool(reseed)), split_factor, split_width, max_mem_intv)
 
 
 class Seeds(C.Structure):
@@ -89,7 +95,7 @@ SYMBOLS = [
     "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
     "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
-    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_measure_random_sector_gbs", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
+    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
@@ -309,10 +315,10 @@ class Seeder:
         self.index = index
         check(lib().bwa_b200_seeder_create(index.h, max_reads, max_words, C.byref(self.h)))
 
-    def seed_host(self, packed, word_off, read_len, min_seed_len=19, max_occ=500):
+    def seed_host(self, packed, word_off, read_len, min_seed_len=19, max_occ=500, params: SeedParams = None):
         """host arrays in, numpy arrays out (copies of the malloc'ed result)."""
         n = read_len.size
-        p = SeedParams(min_seed_len, max_occ)
+        p = params if params is not None else SeedParams(min_seed_len, max_occ)
         out = Seeds()
         check(lib().bwa_b200_seed_host(self.h, _p(packed), _p(word_off), _p(read_len), n, C.byref(p), C.byref(out)))
         tot = int(out.n_seeds)
@@ -327,8 +333,8 @@ class Seeder:
         lib().bwa_b200_seeds_free(C.byref(out))
         return res
 
-    def seed_device(self, d_packed: int, d_word_off: int, d_read_len: int, n_reads: int, min_seed_len=19, max_occ=500):
-        p = SeedParams(min_seed_len, max_occ)
+    def seed_device(self, d_packed: int, d_word_off: int, d_read_len: int, n_reads: int, min_seed_len=19, max_occ=500, params: SeedParams = None):
+        p = params if params is not None else SeedParams(min_seed_len, max_occ)
         check(lib().bwa_b200_seed_device(self.h, d_packed, d_word_off, d_read_len, n_reads, C.byref(p)))
 
     def device_result(self) -> Seeds:

@@ -377,6 +377,213 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     }
 }
 
+// ------------------------------------------------------------- re-seeding (passes 2 and 3)
+// mem_collect_intv after its first pass (bwa_index/bwamem.c:132-161), which the reference GPU path leaves out
+// (README.md:93) and stock `bwa mem` performs:
+//   pass 2  for every pass-1 SMEM of length >= split_len with at most split_width occurrences:
+//           bwt_smem1(x = middle, min_intv = occurrences + 1), keep length >= min_seed_len
+//   pass 3  bwt_seed_strategy1 from x = 0: forward extension until the interval is smaller than max_mem_intv and the
+//           match at least min_seed_len + 1 long; restart behind it
+//   sort    by (start, end)  -- entries with equal (start, end) are equal intervals, so any sort gives the CPU's list
+// The merged list of read r is written to row r of a second candidate array (xstride entries per read); a read
+// that needs more reports its count through *max_need and the host re-runs the two kernels with a wider row.
+
+// forward extension of the bidirectional interval (k, l, s) by base complement cb: bwt_extend(ik, ok, 0), ok[cb]
+template <typename RowT>
+__device__ __forceinline__ void fwd_extend(const IndexView &ix, uint64_t pol, RowT primary, RowT k, RowT l, uint32_t s, int cb,
+                                           RowT &nk, RowT &nl, uint32_t &ns)
+{
+    const RowT p0 = l - 1, p1 = l - 1 + s;
+    const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+    const Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
+    const Bkt b1 = ld_bucket_or((j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);
+    uint32_t tk[4], tl[4];
+    bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
+    bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
+    const uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
+    ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
+    const uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
+    nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
+    if (cb < 3) nk += s3;
+    if (cb < 2) nk += s2;
+    if (cb < 1) nk += s1;
+    nl = (RowT)L2_at(ix, cb) + 1 + tkc;
+}
+
+// backward extension of (k, s) by base b: x[0] and x[2] of bwt_extend(ik, ok, 1), ok[b]
+template <typename RowT>
+__device__ __forceinline__ void back_extend(const IndexView &ix, uint64_t pol, RowT primary, RowT k, uint32_t s, int b, RowT &nk, uint32_t &ns)
+{
+    const RowT p0 = k - 1, p1 = k - 1 + s;
+    const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+    const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
+    const Bkt b0 = ld_bucket_or((j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);
+    const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
+    const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
+    const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
+    ns = ol - ok;
+    nk = (RowT)L2_at(ix, b) + 1 + ok;
+}
+
+__device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, uint64_t woff, int i)
+{
+    return (int)((__ldg(packed + woff + (uint32_t)(i >> 3)) >> (28 - 4 * (i & 7))) & 15u);
+}
+
+constexpr int RS_THREADS = 128;
+
+// pass 3, one lane per read: the loop of bwa_index/bwamem.c:145-158 with bwt_seed_strategy1 (bwa_index/bwt.c:434-455) unrolled
+// into one forward extension per iteration, like fwd_kernel.  Entries go to the front of the read's row.
+template <typename RowT>
+__global__ void __launch_bounds__(RS_THREADS)
+reseed3_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+               const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_intv,
+               uint32_t xstride, Cand *__restrict__ cand2, uint32_t *__restrict__ n_cand2)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int len = (int)read_len[r];
+    uint32_t n_out = 0;
+    if (len >= min_seed_len && max_intv > 0) {
+        const uint64_t woff = word_off[r];
+        Cand *out = cand2 + (uint64_t)r * xstride;
+        const RowT primary = (RowT)ix.primary;
+        const uint64_t pol = bucket_policy();
+        RowT k = 0, l = 0;
+        uint32_t s = 0, word = __ldg(packed + woff);
+        int x = 0;
+        bool active = false;
+        for (int i = 0; i < len; ++i) {
+            if ((i & 7) == 0 && i) word = __ldg(packed + woff + (uint32_t)(i >> 3));
+            const int b = (int)((word >> (28 - 4 * (i & 7))) & 15u);
+            if (!active) {
+                if (b < 4) { k = (RowT)L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = (RowT)L2_at(ix, 3 - b) + 1; x = i; active = true; }
+                continue;
+            }
+            if (b > 3) { active = false; continue; }           // `else return i + 1`: the next call starts behind the N
+            RowT nk = 0, nl = 0;
+            uint32_t ns = 0;
+            if (s) fwd_extend<RowT>(ix, pol, primary, k, l, s, 3 - b, nk, nl, ns);    // an empty interval stays empty
+            if (ns < (uint32_t)max_intv && i - x >= min_seed_len) {
+                if (ns > 0) {                                   // `if (m.x[2] > 0) kv_push`
+                    if (n_out < xstride) out[n_out] = Cand{(uint64_t)nk, ns, (uint16_t)x, (uint16_t)(i + 1)};
+                    ++n_out;
+                }
+                active = false;                                 // returns i + 1
+                continue;
+            }
+            k = nk; l = nl; s = ns;
+        }
+    }
+    n_cand2[r] = n_out;                                        // may exceed xstride: reseed2_kernel reports it
+}
+
+// pass 2 + merge, lanes stride over the reads.  Per-lane scratch in global memory: the forward candidates of one
+// bwt_smem1 call (cl, at most max_len) and the envelope of interval sizes of the backward walk (env, see back_kernel).
+template <typename RowT>
+__global__ void __launch_bounds__(RS_THREADS)
+reseed2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+               const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_occ, int split_len, int split_width,
+               uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
+               uint32_t xstride, Cand *__restrict__ cand2, uint32_t *__restrict__ n_cand2,
+               uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds,
+               uint4 *__restrict__ cl_all, uint32_t *__restrict__ env_all, uint32_t scratch_stride, unsigned long long *__restrict__ max_need)
+{
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, n_lanes = gridDim.x * blockDim.x;
+    uint4 *const cl = cl_all + (uint64_t)gtid * scratch_stride;
+    uint32_t *const env = env_all + (uint64_t)gtid * scratch_stride;
+    const RowT primary = (RowT)ix.primary;
+    const uint64_t pol = bucket_policy();
+    for (uint32_t r = gtid; r < n_reads; r += n_lanes) {
+        const int len = (int)read_len[r];
+        const uint64_t woff = word_off[r];
+        const Cand *row1 = cand + (uint64_t)r * cand_stride;
+        Cand *row2 = cand2 + (uint64_t)r * xstride;
+        const uint32_t n1 = len >= min_seed_len ? n_cand[r] : 0u;
+        uint32_t n_out = n_cand2[r];                           // pass-3 entries already in the row
+        auto emit = [&](uint64_t k, uint32_t s, int beg, int end) {
+            if (n_out < xstride) row2[n_out] = Cand{k, s, (uint16_t)beg, (uint16_t)end};
+            ++n_out;
+        };
+        for (uint32_t j = 0; j < n1; ++j) {
+            const Cand c = row1[j];
+            if (c.s == 0) continue;                            // not an SMEM (or shorter than min_seed_len)
+            emit(c.k, c.s, c.x, c.end);                        // pass 1
+            if ((int)c.end - (int)c.x < split_len || c.s > (uint32_t)split_width) continue;
+            // ---- bwt_smem1(x, min_intv), bwa_index/bwt.c:365-432
+            const int x = ((int)c.x + (int)c.end) >> 1;
+            const uint32_t min_intv = c.s + 1;
+            int nc = 0;
+            {   // forward phase: a candidate at every change of the interval size
+                const int b0 = read_base(packed, woff, x);      // inside an SMEM: never ambiguous
+                RowT k = (RowT)L2_at(ix, b0) + 1, l = (RowT)L2_at(ix, 3 - b0) + 1;
+                uint32_t s = (uint32_t)(L2_at(ix, b0 + 1) - L2_at(ix, b0));
+                int i = x + 1;
+                for (; i < len; ++i) {
+                    const int b = read_base(packed, woff, i);
+                    if (b > 3) { cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)i); break; }
+                    RowT nk, nl;
+                    uint32_t ns;
+                    fwd_extend<RowT>(ix, pol, primary, k, l, s, 3 - b, nk, nl, ns);
+                    if (ns != s) {
+                        cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)i);
+                        if (ns < min_intv) break;
+                    }
+                    k = nk; l = nl; s = ns;
+                }
+                if (i == len) cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)len);
+            }
+            // backward phase: candidates longest first, each walked back on its own; env[t] = interval size of the last
+            // candidate that survived step t, valid for t < t_head (the merge / containment tests of bwt.c:405-421)
+            int t_head = 0;
+            bool first = true;
+            for (int q = nc - 1; q >= 0; --q) {
+                const uint4 e = cl[q];
+                RowT ck = (RowT)(((uint64_t)e.y << 32) | e.x);
+                uint32_t cs = e.z;
+                const int end = (int)e.w;
+                for (int t = 0;; ++t) {
+                    const int i = x - 1 - t;
+                    const int b = i >= 0 ? read_base(packed, woff, i) : 4;
+                    RowT nk = 0;
+                    uint32_t ns = 0;
+                    if (b < 4) back_extend<RowT>(ix, pol, primary, ck, cs, b, nk, ns);
+                    if (b > 3 || ns < min_intv) {              // the match stops here
+                        if (first || t > t_head) {
+                            if (end - (x - t) >= min_seed_len) emit((uint64_t)ck, cs, x - t, end);
+                            t_head = t; first = false;
+                        }
+                        break;
+                    }
+                    if (t < t_head && env[t] == ns) break;      // same interval as a longer match: contained
+                    env[t] = ns;
+                    ck = nk; cs = ns;
+                }
+            }
+        }
+        uint32_t seeds = 0;
+        if (n_out <= xstride) {
+            // sort by (start, end): insertion sort, a dozen entries
+            for (uint32_t a = 1; a < n_out; ++a) {
+                const Cand v = row2[a];
+                const uint32_t key = (uint32_t)v.x << 16 | v.end;
+                uint32_t b = a;
+                while (b > 0) {
+                    const Cand u = row2[b - 1];
+                    if (((uint32_t)u.x << 16 | u.end) <= key) break;
+                    row2[b] = u; --b;
+                }
+                if (b != a) row2[b] = v;
+            }
+            for (uint32_t a = 0; a < n_out; ++a) seeds += seeds_of(row2[a].s, max_occ);
+            n_cand2[r] = n_out; n_smems[r] = n_out; n_seeds[r] = seeds;
+        } else {
+            atomicMax(max_need, (unsigned long long)n_out);
+            n_cand2[r] = 0; n_smems[r] = 0; n_seeds[r] = 0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ fill_kernel
 __global__ void __launch_bounds__(128)
 fill_kernel(uint32_t n_reads, int max_occ, uint32_t cand_stride, const Cand *__restrict__ cand,
@@ -559,6 +766,30 @@ static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max
     return BWA_B200_OK;
 }
 
+static int seeder_ensure_reseed(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, uint32_t want_stride)
+{
+    uint32_t stride = std::max<uint32_t>(std::max<uint32_t>(24u, max_len / 4), want_stride);
+    if (stride < s->xstride) stride = s->xstride;
+    const uint64_t need = n_reads * (uint64_t)stride;
+    if (need > s->cand2_cap) {
+        if (s->d_cand2) B200_CUDA(cudaFree(s->d_cand2));
+        s->d_cand2 = nullptr; s->cand2_cap = 0;
+        B200_CUDA(cudaMalloc(&s->d_cand2, need * sizeof(Cand)));
+        s->cand2_cap = need;
+    }
+    s->xstride = stride;
+    if (max_len + 1 > s->rs_scratch_stride) {
+        if (s->d_rs_cl) B200_CUDA(cudaFree(s->d_rs_cl));
+        if (s->d_rs_env) B200_CUDA(cudaFree(s->d_rs_env));
+        s->d_rs_cl = nullptr; s->d_rs_env = nullptr; s->rs_scratch_stride = 0;
+        const uint64_t lanes = (uint64_t)s->rs_grid * RS_THREADS;
+        B200_CUDA(cudaMalloc(&s->d_rs_cl, lanes * (max_len + 1) * sizeof(uint4)));
+        B200_CUDA(cudaMalloc(&s->d_rs_env, lanes * (max_len + 1) * 4));
+        s->rs_scratch_stride = max_len + 1;
+    }
+    return BWA_B200_OK;
+}
+
 static int seeder_ensure_out(bwa_b200_seeder *s, uint64_t n_seeds)
 {
     if (n_seeds <= s->seed_cap) return BWA_B200_OK;
@@ -625,8 +856,15 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     B200_CUDA(cudaMalloc(&s->d_nseeds, max_reads * 4));
     B200_CUDA(cudaMalloc(&s->d_seed_off, max_reads * 8));
     B200_CUDA(cudaMalloc(&s->d_smem_off, max_reads * 8));
-    B200_CUDA(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
-    B200_CUDA(cudaHostAlloc(&s->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    B200_CUDA(cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long)));
+    B200_CUDA(cudaHostAlloc(&s->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    B200_CUDA(cudaMalloc(&s->d_ncand2, max_reads * 4));
+    {
+        int occ_r = 0;
+        if (narrow_rows) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, reseed2_kernel<uint32_t>, RS_THREADS, 0));
+        else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, reseed2_kernel<uint64_t>, RS_THREADS, 0));
+        s->rs_grid = s->n_sm * (occ_r > 0 ? occ_r : 1);
+    }
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, it, s->d_seed_off, (int)max_reads, s->stream));
     B200_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes + 16));
@@ -644,9 +882,16 @@ extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
     cudaFree(s->d_packed); cudaFree(s->d_len); cudaFree(s->d_woff); cudaFree(s->d_cand); cudaFree(s->d_ncand);
     cudaFree(s->d_nsmems); cudaFree(s->d_nseeds); cudaFree(s->d_env); cudaFree(s->d_seed_off); cudaFree(s->d_smem_off);
     cudaFree(s->d_counters); cudaFree(s->d_cub); cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score);
+    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_rs_cl); cudaFree(s->d_rs_env);
     cudaFreeHost(s->h_counters);
     cudaStreamDestroy(s->stream);
     delete s;
+}
+
+extern "C" void bwa_b200_seed_params_default(bwa_b200_seed_params_t *p)
+{ // mem_opt_init, bwa_index/bwamem.c:56-62
+    if (!p) return;
+    p->min_seed_len = 19; p->max_occ = 500; p->reseed = 0; p->split_factor = 1.5f; p->split_width = 10; p->max_mem_intv = 20;
 }
 
 extern "C" void *bwa_b200_seeder_stream(bwa_b200_seeder_t *s) { return s ? (void *)s->stream : nullptr; }
@@ -657,9 +902,10 @@ static int seeder_fill_locate(bwa_b200_seeder *s)
     const IndexView &ix = s->idx->v;
     const uint32_t n = (uint32_t)s->last_n_reads;
     cudaStream_t st = s->stream;
+    const bool rs = s->last_p.reseed != 0;
     B200_LAUNCH(s->prof, "fill_kernel", st,
-        (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, s->cand_stride, s->d_cand, s->d_ncand,
-                                                       s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
+        (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, rs ? s->xstride : s->cand_stride, rs ? s->d_cand2 : s->d_cand,
+                                                       rs ? s->d_ncand2 : s->d_ncand, s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
     if (s->narrow_rows)
         B200_LAUNCH(s->prof, "locate_kernel", st,
             (locate_kernel<uint32_t><<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
@@ -671,7 +917,54 @@ static int seeder_fill_locate(bwa_b200_seeder *s)
     return BWA_B200_OK;
 }
 
-// enqueue fwd -> back -> scan -> total -> fill -> locate on s->stream; no host synchronisation
+// passes 2 and 3 of mem_collect_intv over the current batch: the merged, sorted interval rows and the per-read counts
+static int seeder_reseed(bwa_b200_seeder *s)
+{
+    const IndexView &ix = s->idx->v;
+    const uint32_t n = (uint32_t)s->last_n_reads;
+    const bwa_b200_seed_params_t &p = s->last_p;
+    cudaStream_t st = s->stream;
+    const int split_len = (int)(p.min_seed_len * p.split_factor + .499f);      // bwa_index/bwamem.c:118
+    B200_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));
+    if (s->narrow_rows) {
+        B200_LAUNCH(s->prof, "reseed3_kernel", st,
+            (reseed3_kernel<uint32_t><<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len,
+                                                                                                 p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
+        B200_LAUNCH(s->prof, "reseed2_kernel", st,
+            (reseed2_kernel<uint32_t><<<s->rs_grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_occ, split_len,
+                                                                         p.split_width, s->cand_stride, s->d_cand, s->d_ncand, s->xstride, s->d_cand2, s->d_ncand2,
+                                                                         s->d_nsmems, s->d_nseeds, s->d_rs_cl, s->d_rs_env, s->rs_scratch_stride, s->d_counters + 4)));
+    } else {
+        B200_LAUNCH(s->prof, "reseed3_kernel", st,
+            (reseed3_kernel<uint64_t><<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len,
+                                                                                                 p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
+        B200_LAUNCH(s->prof, "reseed2_kernel", st,
+            (reseed2_kernel<uint64_t><<<s->rs_grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_occ, split_len,
+                                                                         p.split_width, s->cand_stride, s->d_cand, s->d_ncand, s->xstride, s->d_cand2, s->d_ncand2,
+                                                                         s->d_nsmems, s->d_nseeds, s->d_rs_cl, s->d_rs_env, s->rs_scratch_stride, s->d_counters + 4)));
+    }
+    s->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+// per-read seed offsets and the seed total
+static int seeder_scan(bwa_b200_seeder *s)
+{
+    const uint32_t n = (uint32_t)s->last_n_reads;
+    cudaStream_t st = s->stream;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
+    size_t tmp = s->cub_bytes;
+    if (s->prof) s->prof->begin("scan", st);
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_seed_off, (int)n, st));
+    total_kernel<<<1, 1, 0, st>>>(s->d_nseeds, s->d_seed_off, n, s->d_counters + 2);
+    if (s->prof) s->prof->end(st);
+    s->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+// enqueue fwd -> back -> [re-seeding] -> scan -> total -> fill -> locate on s->stream; no host synchronisation
 int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t *d_woff, const uint32_t *d_len,
                     uint64_t n_reads, uint32_t max_len, const bwa_b200_seed_params_t *p)
 {
@@ -687,7 +980,7 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     const IndexView &ix = s->idx->v;
     const uint32_t n = (uint32_t)n_reads;
     cudaStream_t st = s->stream;
-    B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), st));
     // 32-bit row arithmetic when every BWT row fits (seq_len < 2^32), 64-bit otherwise (human-sized)
     const bool narrow = s->narrow_rows;
     const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
@@ -696,14 +989,16 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     B200_LAUNCH(s->prof, "back_kernel", st,
         (back_variant(narrow, s->back_minb)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, n, p->min_seed_len, p->max_occ, s->cand_stride,
                                                                                   s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
-    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
-    size_t tmp = s->cub_bytes;
-    if (s->prof) s->prof->begin("scan", st);
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tmp, it, s->d_seed_off, (int)n, st));
-    total_kernel<<<1, 1, 0, st>>>(s->d_nseeds, s->d_seed_off, n, s->d_counters + 2);
-    if (s->prof) s->prof->end(st);
-    s->launches += 4;
-    B200_CUDA(cudaGetLastError());
+    s->launches += 2;
+    s->cur_packed = d_packed; s->cur_woff = d_woff; s->cur_len = d_len; s->cur_max_len = max_len;
+    if (p->reseed) {
+        rc = seeder_ensure_reseed(s, n_reads, max_len, 0);
+        if (rc) return rc;
+        rc = seeder_reseed(s);
+        if (rc) return rc;
+    }
+    rc = seeder_scan(s);
+    if (rc) return rc;
     if (s->seed_cap > 0) {                 // output arrays exist: keep going without a host round trip
         rc = seeder_fill_locate(s);
         if (rc) return rc;
@@ -716,8 +1011,20 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
 int b200_seeder_finish(bwa_b200_seeder *s)
 {
     if (s->last_n_reads == 0) return BWA_B200_OK;
-    B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
+    while (s->last_p.reseed && s->h_counters[4] > s->xstride) {
+        // a read produced more intervals than a row holds: widen the rows and redo the re-seeding passes (rare)
+        int rc = seeder_ensure_reseed(s, s->last_n_reads, s->cur_max_len, (uint32_t)s->h_counters[4] + 8);
+        if (rc) return rc;
+        rc = seeder_reseed(s);
+        if (rc) return rc;
+        rc = seeder_scan(s);
+        if (rc) return rc;
+        s->filled = false;
+        B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+    }
     s->last_total = s->h_counters[2];
     if (s->filled && s->last_total <= s->seed_cap) return BWA_B200_OK;
     int rc = seeder_ensure_out(s, s->last_total);
@@ -837,7 +1144,9 @@ extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads
     int32_t *d_qb, *d_qe; uint64_t *d_k, *d_s;
     B200_CUDA(cudaMalloc(&d_qb, tot * 4)); B200_CUDA(cudaMalloc(&d_qe, tot * 4));
     B200_CUDA(cudaMalloc(&d_k, tot * 8)); B200_CUDA(cudaMalloc(&d_s, tot * 8));
-    smem_dump_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, s->cand_stride, s->d_cand, s->d_ncand, s->d_smem_off, d_qb, d_qe, d_k, d_s, tot);
+    const bool rs = s->last_p.reseed != 0;
+    smem_dump_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, rs ? s->xstride : s->cand_stride, rs ? s->d_cand2 : s->d_cand, rs ? s->d_ncand2 : s->d_ncand,
+                                                             s->d_smem_off, d_qb, d_qe, d_k, d_s, tot);
     B200_CUDA(cudaStreamSynchronize(s->stream));
     B200_CUDA(cudaMemcpy(host_qbeg, d_qb, tot * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(host_qend, d_qe, tot * 4, cudaMemcpyDeviceToHost));

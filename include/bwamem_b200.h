@@ -104,7 +104,16 @@ typedef struct {
                                   count = min(s, max_occ) rows k + t*step, step = s > max_occ ? s/max_occ : 1.
                                   <= 0: locate all s rows of every SMEM (reference GPU layout,
                                   seed_gen.cu:520-545)                                       */
+    int32_t reseed;            /* 0: SMEM pass 1 only -- what the reference GPU path does (README.md:93, the
+                                  "no re-seeding" limitation).  != 0: also passes 2 and 3 of mem_collect_intv
+                                  (bwa_index/bwamem.c:132-161), i.e. the seed set of stock `bwa mem`; the four
+                                  fields below are then read                                 */
+    float   split_factor;      /* opt->split_factor  (1.5): pass 2 splits SMEMs of length >= min_seed_len * this */
+    int32_t split_width;       /* opt->split_width   (10):  ... that have at most this many occurrences          */
+    int32_t max_mem_intv;      /* opt->max_mem_intv  (20):  pass 3 (bwt_seed_strategy1) threshold; <= 0 skips it */
 } bwa_b200_seed_params_t;
+/* min_seed_len 19, max_occ 500, reseed off; split_factor 1.5, split_width 10, max_mem_intv 20 (bwa_index/bwamem.c:56-62) */
+void bwa_b200_seed_params_default(bwa_b200_seed_params_t *p);
 
 /* flat result, layout of mem_seed_v_gpu (seed_gen.h:68-75): seeds of read r are
  * [seed_off[r], seed_off[r] + n_seeds[r]), ordered by SMEM (ascending query start) then SA row;
