@@ -166,14 +166,15 @@ def run_reference(args, rank, world, dist):
     print(json.dumps(line), flush=True)
 
 
-def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world):
+def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world, reseed=False):
     """The same batch through bwa_b200_align_*: seeding, then mem_chain / mem_chain_flt / mem_chain2aln on the device, every
     extension job of every kept chain (not just the longest seed's), the region arithmetic -- SURVEY 8f row 1.  Extension runs
     with the same band / z-drop as the headline step.  Reported under sub_metrics.chained, timed like the headline."""
     import torch
     import torch.distributed as dist
     al = pkg.Aligner(idx, n, int(d_packed.numel()))
-    sp, cp, ep = pkg.SeedParams(19, 500), pkg.chain_params(w=100), pkg.ext_params()
+    # reseed: seeding also runs passes 2 and 3 of mem_collect_intv (the seed set of stock `bwa mem`; SURVEY 8f row 3)
+    sp, cp, ep = pkg.seed_params(19, 500, reseed), pkg.chain_params(w=100), pkg.ext_params()
     stream = torch.cuda.ExternalStream(al.stream)
 
     def step():
@@ -230,7 +231,8 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
            "gpu_launches": int(launches), "kernel_ms": kavg,
-           "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"}
+           "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"
+                     + ("; re-seeding split_factor 1.5 split_width 10 max_mem_intv 20" if reseed else "; SMEM pass 1 only")}
     al.destroy()
     return res
 
@@ -368,9 +370,10 @@ def main():
     d2h = int(n * 72)
     mapped = int((out_np["seed_qbeg"] >= 0).sum())
 
-    chained = None
+    chained = chained_rs = None
     if not args.no_chain:
         chained = run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world)
+        chained_rs = run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world, reseed=True)
 
     if rank != 0:
         if dref:
@@ -472,7 +475,7 @@ def main():
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
         "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
                         "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
-                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained},
+                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained, "chained_reseed": chained_rs},
     }
     print(json.dumps(line), flush=True)
     if dref:

@@ -54,12 +54,11 @@ struct bwa_b200_seeder {
     uint32_t *d_ncand = nullptr, *d_nsmems = nullptr, *d_nseeds = nullptr, *d_env = nullptr;
     uint64_t *d_seed_off = nullptr, *d_smem_off = nullptr;
     unsigned long long *d_counters = nullptr;     // [0] next_read, [1] next_seed, [2] total seeds, [3] total smems, [4] widest re-seeding row needed
-    // re-seeding (passes 2 and 3 of mem_collect_intv): merged interval list per read, lane scratch of reseed2_kernel
-    b200::Cand *d_cand2 = nullptr;
-    uint64_t cand2_cap = 0;
-    uint32_t xstride = 0, rs_scratch_stride = 0, *d_ncand2 = nullptr, *d_rs_env = nullptr;
-    uint4 *d_rs_cl = nullptr;
-    int rs_grid = 0;
+    // re-seeding (passes 2 and 3 of mem_collect_intv): merged interval list per read (cand2, xstride per read) and the
+    // pass-2 candidates (cand3, stride3 per read); [4] / [5] of d_counters = widest row a read needed in either
+    b200::Cand *d_cand2 = nullptr, *d_cand3 = nullptr;
+    uint64_t cand2_cap = 0, cand3_cap = 0;
+    uint32_t xstride = 0, stride3 = 0, *d_ncand2 = nullptr, *d_ncand3 = nullptr, *d_rs_dummy = nullptr;
     // inputs of the current batch (re-seeding is re-run from them when a read overflows its row)
     const uint32_t *cur_packed = nullptr, *cur_len = nullptr; const uint64_t *cur_woff = nullptr; uint32_t cur_max_len = 0;
     void *d_cub = nullptr;

@@ -239,7 +239,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename RowT, int MINB>
+// RESEED: the candidates come from fwd2_kernel (pass 2 of mem_collect_intv): bits 48..63 of a candidate's k hold min_intv - 1 of its
+// bwt_smem1 call, and a backward extension fails when the interval gets smaller than min_intv (bwa_index/bwt.c:407) instead of empty.
+template <typename RowT, int MINB, bool RESEED>
 __global__ void __launch_bounds__(BACK_THREADS, MINB)
 back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
             uint32_t n_reads, int min_seed_len, int max_occ,
@@ -264,7 +266,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     uint32_t r = 0, woff = 0;
     int slot = -1, cur_x = -1, t = 0, t_head = 0, x = 0, end = 0, delay = 0;
     RowT ck = 0;
-    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0, bw = 0, bw0 = 0;
+    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0, bw = 0, bw0 = 0, mi1 = 0;
 
     for (;;) {
         // ---------------- converged: claim reads for the warp, hand them to the lanes that need one
@@ -321,7 +323,8 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 const uint4 c = *m;
                 if (slot >= KC) cp_async16(m, cand + (uint64_t)r * cand_stride + (slot - KC));
                 cp_async_commit();
-                ck = (RowT)(((uint64_t)c.y << 32) | c.x); cs = c.z; x = (int)(c.w & 0xffffu); end = (int)(c.w >> 16);
+                ck = (RowT)(((uint64_t)(RESEED ? c.y & 0xffffu : c.y) << 32) | c.x); cs = c.z; x = (int)(c.w & 0xffffu); end = (int)(c.w >> 16);
+                if (RESEED) mi1 = c.y >> 16;
                 if (x != cur_x) {
                     cur_x = x; first = true; t_head = 0;
                     if (x > 0) bw0 = __ldg(packed + ((uint64_t)woff + ((uint32_t)(x - 1) >> 3)));
@@ -348,7 +351,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
                 ns = ol - ok;
                 nk = (RowT)L2_at(ix, b) + 1 + ok;
-                fail = ns == 0;
+                fail = RESEED ? ns <= mi1 : ns == 0;
             }
             Cand *const rcs = cand + (uint64_t)r * cand_stride + slot;
             uint32_t *const env_g = env_spill + (uint64_t)gtid * env_stride;     // steps >= ENV_SMEM (rare)
@@ -475,112 +478,120 @@ reseed3_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t
             k = nk; l = nl; s = ns;
         }
     }
-    n_cand2[r] = n_out;                                        // may exceed xstride: reseed2_kernel reports it
+    n_cand2[r] = n_out;                                        // may exceed xstride: merge_kernel reports it
 }
 
-// pass 2 + merge, lanes stride over the reads.  Per-lane scratch in global memory: the forward candidates of one
-// bwt_smem1 call (cl, at most max_len) and the envelope of interval sizes of the backward walk (env, see back_kernel).
+// pass 2, forward phases: one lane per read walks its pass-1 SMEMs; for every long, rare one (bwa_index/bwamem.c:136-137) it runs
+// the forward phase of bwt_smem1(x = middle, min_intv = occurrences + 1) -- one forward extension per loop iteration, whatever the
+// lane's SMEM -- and writes the candidates to the read's row of a third candidate array.  back_kernel<RESEED> then does the
+// backward phases exactly as for pass 1.  Rows hold stride3 candidates; a read that needs more reports it through *max_need.
 template <typename RowT>
 __global__ void __launch_bounds__(RS_THREADS)
-reseed2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
-               const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int max_occ, int split_len, int split_width,
-               uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
-               uint32_t xstride, Cand *__restrict__ cand2, uint32_t *__restrict__ n_cand2,
-               uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds,
-               uint4 *__restrict__ cl_all, uint32_t *__restrict__ env_all, uint32_t scratch_stride, unsigned long long *__restrict__ max_need)
+fwd2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int split_len, int split_width,
+            uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
+            uint32_t stride3, Cand *__restrict__ cand3, uint32_t *__restrict__ n_cand3, unsigned long long *__restrict__ max_need)
 {
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, n_lanes = gridDim.x * blockDim.x;
-    uint4 *const cl = cl_all + (uint64_t)gtid * scratch_stride;
-    uint32_t *const env = env_all + (uint64_t)gtid * scratch_stride;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int len = (int)read_len[r];
+    const uint64_t woff = word_off[r];
+    const Cand *row1 = cand + (uint64_t)r * cand_stride;
+    Cand *out = cand3 + (uint64_t)r * stride3;
+    const uint32_t n1 = len >= min_seed_len ? n_cand[r] : 0u;
     const RowT primary = (RowT)ix.primary;
     const uint64_t pol = bucket_policy();
-    for (uint32_t r = gtid; r < n_reads; r += n_lanes) {
-        const int len = (int)read_len[r];
-        const uint64_t woff = word_off[r];
-        const Cand *row1 = cand + (uint64_t)r * cand_stride;
-        Cand *row2 = cand2 + (uint64_t)r * xstride;
-        const uint32_t n1 = len >= min_seed_len ? n_cand[r] : 0u;
-        uint32_t n_out = n_cand2[r];                           // pass-3 entries already in the row
-        auto emit = [&](uint64_t k, uint32_t s, int beg, int end) {
-            if (n_out < xstride) row2[n_out] = Cand{k, s, (uint16_t)beg, (uint16_t)end};
+    uint32_t n_out = 0, j = 0, s = 0, mi1 = 0;
+    RowT k = 0, l = 0;
+    int x = 0, i = 0;
+    bool have = false;
+    auto push = [&](int end) {
+        if (end >= min_seed_len) {                              // as fwd_kernel: a match ending before min_seed_len cannot become a seed
+            if (n_out < stride3)
+                __stcs(reinterpret_cast<uint4 *>(out + n_out), make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32) | mi1 << 16, s, (uint32_t)x | (uint32_t)end << 16));
             ++n_out;
-        };
+        }
+    };
+    for (;;) {
+        if (!have) {
+            bool found = false;
+            while (j < n1) {
+                const Cand c = row1[j++];
+                if (c.s == 0 || (int)c.end - (int)c.x < split_len || c.s > (uint32_t)split_width) continue;
+                x = ((int)c.x + (int)c.end) >> 1; mi1 = c.s;     // min_intv - 1
+                found = true;
+                break;
+            }
+            if (!found) break;
+            const int b0 = read_base(packed, woff, x);           // inside an SMEM: never ambiguous
+            k = (RowT)L2_at(ix, b0) + 1; l = (RowT)L2_at(ix, 3 - b0) + 1; s = (uint32_t)(L2_at(ix, b0 + 1) - L2_at(ix, b0));
+            i = x + 1; have = true;
+            if (i >= len) { push(len); have = false; }
+            continue;
+        }
+        const int b = read_base(packed, woff, i);
+        if (b > 3) { push(i); have = false; continue; }
+        RowT nk, nl;
+        uint32_t ns;
+        fwd_extend<RowT>(ix, pol, primary, k, l, s, 3 - b, nk, nl, ns);
+        if (ns != s) {
+            push(i);
+            if (ns <= mi1) { have = false; continue; }           // ok[c].x[2] < min_intv: stop
+        }
+        k = nk; l = nl; s = ns; ++i;
+        if (i == len) { push(len); have = false; }
+    }
+    n_cand3[r] = n_out <= stride3 ? n_out : 0u;
+    if (n_out > stride3) atomicMax(max_need + 1, (unsigned long long)n_out);
+}
+
+// merge: pass-1 SMEMs (cand), pass-2 SMEMs (cand3, after back_kernel<RESEED>) and the pass-3 entries already at the front of the
+// read's cand2 row; sort by (start, end); per-read interval and seed counts.
+__global__ void __launch_bounds__(RS_THREADS)
+merge_kernel(uint32_t n_reads, const uint32_t *__restrict__ read_len, int min_seed_len, int max_occ,
+             uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
+             uint32_t stride3, const Cand *__restrict__ cand3, const uint32_t *__restrict__ n_cand3,
+             uint32_t xstride, Cand *__restrict__ cand2, uint32_t *__restrict__ n_cand2,
+             uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds, unsigned long long *__restrict__ max_need)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    Cand *row2 = cand2 + (uint64_t)r * xstride;
+    uint32_t n_out = n_cand2[r];                               // pass-3 entries (reseed3_kernel); may already exceed the row
+    if ((int)read_len[r] >= min_seed_len) {
+        const Cand *row1 = cand + (uint64_t)r * cand_stride, *row3 = cand3 + (uint64_t)r * stride3;
+        const uint32_t n1 = n_cand[r], n3 = n_cand3[r];
         for (uint32_t j = 0; j < n1; ++j) {
             const Cand c = row1[j];
-            if (c.s == 0) continue;                            // not an SMEM (or shorter than min_seed_len)
-            emit(c.k, c.s, c.x, c.end);                        // pass 1
-            if ((int)c.end - (int)c.x < split_len || c.s > (uint32_t)split_width) continue;
-            // ---- bwt_smem1(x, min_intv), bwa_index/bwt.c:365-432
-            const int x = ((int)c.x + (int)c.end) >> 1;
-            const uint32_t min_intv = c.s + 1;
-            int nc = 0;
-            {   // forward phase: a candidate at every change of the interval size
-                const int b0 = read_base(packed, woff, x);      // inside an SMEM: never ambiguous
-                RowT k = (RowT)L2_at(ix, b0) + 1, l = (RowT)L2_at(ix, 3 - b0) + 1;
-                uint32_t s = (uint32_t)(L2_at(ix, b0 + 1) - L2_at(ix, b0));
-                int i = x + 1;
-                for (; i < len; ++i) {
-                    const int b = read_base(packed, woff, i);
-                    if (b > 3) { cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)i); break; }
-                    RowT nk, nl;
-                    uint32_t ns;
-                    fwd_extend<RowT>(ix, pol, primary, k, l, s, 3 - b, nk, nl, ns);
-                    if (ns != s) {
-                        cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)i);
-                        if (ns < min_intv) break;
-                    }
-                    k = nk; l = nl; s = ns;
-                }
-                if (i == len) cl[nc++] = make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)len);
-            }
-            // backward phase: candidates longest first, each walked back on its own; env[t] = interval size of the last
-            // candidate that survived step t, valid for t < t_head (the merge / containment tests of bwt.c:405-421)
-            int t_head = 0;
-            bool first = true;
-            for (int q = nc - 1; q >= 0; --q) {
-                const uint4 e = cl[q];
-                RowT ck = (RowT)(((uint64_t)e.y << 32) | e.x);
-                uint32_t cs = e.z;
-                const int end = (int)e.w;
-                for (int t = 0;; ++t) {
-                    const int i = x - 1 - t;
-                    const int b = i >= 0 ? read_base(packed, woff, i) : 4;
-                    RowT nk = 0;
-                    uint32_t ns = 0;
-                    if (b < 4) back_extend<RowT>(ix, pol, primary, ck, cs, b, nk, ns);
-                    if (b > 3 || ns < min_intv) {              // the match stops here
-                        if (first || t > t_head) {
-                            if (end - (x - t) >= min_seed_len) emit((uint64_t)ck, cs, x - t, end);
-                            t_head = t; first = false;
-                        }
-                        break;
-                    }
-                    if (t < t_head && env[t] == ns) break;      // same interval as a longer match: contained
-                    env[t] = ns;
-                    ck = nk; cs = ns;
-                }
-            }
+            if (c.s == 0) continue;
+            if (n_out < xstride) row2[n_out] = c;
+            ++n_out;
         }
-        uint32_t seeds = 0;
-        if (n_out <= xstride) {
-            // sort by (start, end): insertion sort, a dozen entries
-            for (uint32_t a = 1; a < n_out; ++a) {
-                const Cand v = row2[a];
-                const uint32_t key = (uint32_t)v.x << 16 | v.end;
-                uint32_t b = a;
-                while (b > 0) {
-                    const Cand u = row2[b - 1];
-                    if (((uint32_t)u.x << 16 | u.end) <= key) break;
-                    row2[b] = u; --b;
-                }
-                if (b != a) row2[b] = v;
-            }
-            for (uint32_t a = 0; a < n_out; ++a) seeds += seeds_of(row2[a].s, max_occ);
-            n_cand2[r] = n_out; n_smems[r] = n_out; n_seeds[r] = seeds;
-        } else {
-            atomicMax(max_need, (unsigned long long)n_out);
-            n_cand2[r] = 0; n_smems[r] = 0; n_seeds[r] = 0;
+        for (uint32_t j = 0; j < n3; ++j) {
+            const Cand c = row3[j];
+            if (c.s == 0) continue;
+            if (n_out < xstride) row2[n_out] = c;
+            ++n_out;
         }
+    }
+    uint32_t seeds = 0;
+    if (n_out <= xstride) {
+        for (uint32_t a = 1; a < n_out; ++a) {                 // insertion sort, a dozen entries
+            const Cand v = row2[a];
+            const uint32_t key = (uint32_t)v.x << 16 | v.end;
+            uint32_t b = a;
+            while (b > 0) {
+                const Cand u = row2[b - 1];
+                if (((uint32_t)u.x << 16 | u.end) <= key) break;
+                row2[b] = u; --b;
+            }
+            if (b != a) row2[b] = v;
+        }
+        for (uint32_t a = 0; a < n_out; ++a) seeds += seeds_of(row2[a].s, max_occ);
+        n_cand2[r] = n_out; n_smems[r] = n_out; n_seeds[r] = seeds;
+    } else {
+        atomicMax(max_need, (unsigned long long)n_out);
+        n_cand2[r] = 0; n_smems[r] = 0; n_seeds[r] = 0;
     }
 }
 
@@ -736,11 +747,12 @@ FwdFn fwd_variant(bool narrow, int minb)
     if (narrow) return minb >= 16 ? fwd_kernel<uint32_t, 16> : (minb >= 12 ? fwd_kernel<uint32_t, 12> : (minb >= 10 ? fwd_kernel<uint32_t, 10> : fwd_kernel<uint32_t, 8>));
     return minb >= 16 ? fwd_kernel<uint64_t, 16> : (minb >= 12 ? fwd_kernel<uint64_t, 12> : (minb >= 10 ? fwd_kernel<uint64_t, 10> : fwd_kernel<uint64_t, 8>));
 }
-BackFn back_variant(bool narrow, int minb)
+template <bool RESEED> BackFn back_variant_t(bool narrow, int minb)
 {
-    if (narrow) return minb >= 16 ? back_kernel<uint32_t, 16> : (minb >= 12 ? back_kernel<uint32_t, 12> : (minb >= 10 ? back_kernel<uint32_t, 10> : back_kernel<uint32_t, 8>));
-    return minb >= 16 ? back_kernel<uint64_t, 16> : (minb >= 12 ? back_kernel<uint64_t, 12> : (minb >= 10 ? back_kernel<uint64_t, 10> : back_kernel<uint64_t, 8>));
+    if (narrow) return minb >= 16 ? back_kernel<uint32_t, 16, RESEED> : (minb >= 12 ? back_kernel<uint32_t, 12, RESEED> : (minb >= 10 ? back_kernel<uint32_t, 10, RESEED> : back_kernel<uint32_t, 8, RESEED>));
+    return minb >= 16 ? back_kernel<uint64_t, 16, RESEED> : (minb >= 12 ? back_kernel<uint64_t, 12, RESEED> : (minb >= 10 ? back_kernel<uint64_t, 10, RESEED> : back_kernel<uint64_t, 8, RESEED>));
 }
+BackFn back_variant(bool narrow, int minb, bool reseed = false) { return reseed ? back_variant_t<true>(narrow, minb) : back_variant_t<false>(narrow, minb); }
 
 } // namespace
 
@@ -766,27 +778,23 @@ static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max
     return BWA_B200_OK;
 }
 
-static int seeder_ensure_reseed(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, uint32_t want_stride)
+static int seeder_ensure_reseed(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, uint32_t want_x, uint32_t want_3)
 {
-    uint32_t stride = std::max<uint32_t>(std::max<uint32_t>(24u, max_len / 4), want_stride);
-    if (stride < s->xstride) stride = s->xstride;
-    const uint64_t need = n_reads * (uint64_t)stride;
-    if (need > s->cand2_cap) {
+    uint32_t xs = std::max<uint32_t>(std::max<uint32_t>(24u, max_len / 4), std::max(want_x, s->xstride));
+    uint32_t s3 = std::max<uint32_t>(std::max<uint32_t>(48u, max_len / 2), std::max(want_3, s->stride3));
+    if (n_reads * (uint64_t)xs > s->cand2_cap) {
         if (s->d_cand2) B200_CUDA(cudaFree(s->d_cand2));
         s->d_cand2 = nullptr; s->cand2_cap = 0;
-        B200_CUDA(cudaMalloc(&s->d_cand2, need * sizeof(Cand)));
-        s->cand2_cap = need;
+        B200_CUDA(cudaMalloc(&s->d_cand2, n_reads * (uint64_t)xs * sizeof(Cand)));
+        s->cand2_cap = n_reads * (uint64_t)xs;
     }
-    s->xstride = stride;
-    if (max_len + 1 > s->rs_scratch_stride) {
-        if (s->d_rs_cl) B200_CUDA(cudaFree(s->d_rs_cl));
-        if (s->d_rs_env) B200_CUDA(cudaFree(s->d_rs_env));
-        s->d_rs_cl = nullptr; s->d_rs_env = nullptr; s->rs_scratch_stride = 0;
-        const uint64_t lanes = (uint64_t)s->rs_grid * RS_THREADS;
-        B200_CUDA(cudaMalloc(&s->d_rs_cl, lanes * (max_len + 1) * sizeof(uint4)));
-        B200_CUDA(cudaMalloc(&s->d_rs_env, lanes * (max_len + 1) * 4));
-        s->rs_scratch_stride = max_len + 1;
+    if (n_reads * (uint64_t)s3 > s->cand3_cap) {
+        if (s->d_cand3) B200_CUDA(cudaFree(s->d_cand3));
+        s->d_cand3 = nullptr; s->cand3_cap = 0;
+        B200_CUDA(cudaMalloc(&s->d_cand3, n_reads * (uint64_t)s3 * sizeof(Cand)));
+        s->cand3_cap = n_reads * (uint64_t)s3;
     }
+    s->xstride = xs; s->stride3 = s3;
     return BWA_B200_OK;
 }
 
@@ -859,12 +867,8 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     B200_CUDA(cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long)));
     B200_CUDA(cudaHostAlloc(&s->h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     B200_CUDA(cudaMalloc(&s->d_ncand2, max_reads * 4));
-    {
-        int occ_r = 0;
-        if (narrow_rows) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, reseed2_kernel<uint32_t>, RS_THREADS, 0));
-        else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, reseed2_kernel<uint64_t>, RS_THREADS, 0));
-        s->rs_grid = s->n_sm * (occ_r > 0 ? occ_r : 1);
-    }
+    B200_CUDA(cudaMalloc(&s->d_ncand3, max_reads * 4));
+    B200_CUDA(cudaMalloc(&s->d_rs_dummy, max_reads * 8));
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, it, s->d_seed_off, (int)max_reads, s->stream));
     B200_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes + 16));
@@ -882,7 +886,7 @@ extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
     cudaFree(s->d_packed); cudaFree(s->d_len); cudaFree(s->d_woff); cudaFree(s->d_cand); cudaFree(s->d_ncand);
     cudaFree(s->d_nsmems); cudaFree(s->d_nseeds); cudaFree(s->d_env); cudaFree(s->d_seed_off); cudaFree(s->d_smem_off);
     cudaFree(s->d_counters); cudaFree(s->d_cub); cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score);
-    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_rs_cl); cudaFree(s->d_rs_env);
+    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_cand3); cudaFree(s->d_ncand3); cudaFree(s->d_rs_dummy);
     cudaFreeHost(s->h_counters);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -925,25 +929,31 @@ static int seeder_reseed(bwa_b200_seeder *s)
     const bwa_b200_seed_params_t &p = s->last_p;
     cudaStream_t st = s->stream;
     const int split_len = (int)(p.min_seed_len * p.split_factor + .499f);      // bwa_index/bwamem.c:118
-    B200_CUDA(cudaMemsetAsync(s->d_counters + 4, 0, sizeof(unsigned long long), st));
+    const unsigned grid = (n + RS_THREADS - 1) / RS_THREADS;
+    unsigned long long *cnt = s->d_counters;
+    B200_CUDA(cudaMemsetAsync(cnt + 4, 0, 3 * sizeof(unsigned long long), st));   // [4] [5] widest rows needed, [6] read queue of the second back_kernel
     if (s->narrow_rows) {
         B200_LAUNCH(s->prof, "reseed3_kernel", st,
-            (reseed3_kernel<uint32_t><<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len,
-                                                                                                 p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
-        B200_LAUNCH(s->prof, "reseed2_kernel", st,
-            (reseed2_kernel<uint32_t><<<s->rs_grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_occ, split_len,
-                                                                         p.split_width, s->cand_stride, s->d_cand, s->d_ncand, s->xstride, s->d_cand2, s->d_ncand2,
-                                                                         s->d_nsmems, s->d_nseeds, s->d_rs_cl, s->d_rs_env, s->rs_scratch_stride, s->d_counters + 4)));
+            (reseed3_kernel<uint32_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
+        B200_LAUNCH(s->prof, "fwd2_kernel", st,
+            (fwd2_kernel<uint32_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, split_len, p.split_width, s->cand_stride, s->d_cand,
+                                                                s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
     } else {
         B200_LAUNCH(s->prof, "reseed3_kernel", st,
-            (reseed3_kernel<uint64_t><<<(n + RS_THREADS - 1) / RS_THREADS, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len,
-                                                                                                 p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
-        B200_LAUNCH(s->prof, "reseed2_kernel", st,
-            (reseed2_kernel<uint64_t><<<s->rs_grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_occ, split_len,
-                                                                         p.split_width, s->cand_stride, s->d_cand, s->d_ncand, s->xstride, s->d_cand2, s->d_ncand2,
-                                                                         s->d_nsmems, s->d_nseeds, s->d_rs_cl, s->d_rs_env, s->rs_scratch_stride, s->d_counters + 4)));
+            (reseed3_kernel<uint64_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
+        B200_LAUNCH(s->prof, "fwd2_kernel", st,
+            (fwd2_kernel<uint64_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, split_len, p.split_width, s->cand_stride, s->d_cand,
+                                                                s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
     }
-    s->launches += 2;
+    // backward phases of the pass-2 calls: the pass-1 kernel, with the per-candidate min_intv (its per-read counts are not used)
+    B200_LAUNCH(s->prof, "back_kernel_pass2", st,
+        (back_variant(s->narrow_rows, s->back_minb, true)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, n, p.min_seed_len, p.max_occ, s->stride3,
+                                                                                                 s->d_cand3, s->d_ncand3, s->d_rs_dummy, s->d_rs_dummy + s->max_reads, s->d_env,
+                                                                                                 s->env_stride, cnt + 6)));
+    B200_LAUNCH(s->prof, "merge_kernel", st,
+        (merge_kernel<<<grid, RS_THREADS, 0, st>>>(n, s->cur_len, p.min_seed_len, p.max_occ, s->cand_stride, s->d_cand, s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3,
+                                                   s->xstride, s->d_cand2, s->d_ncand2, s->d_nsmems, s->d_nseeds, cnt + 4)));
+    s->launches += 4;
     B200_CUDA(cudaGetLastError());
     return BWA_B200_OK;
 }
@@ -992,7 +1002,7 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     s->launches += 2;
     s->cur_packed = d_packed; s->cur_woff = d_woff; s->cur_len = d_len; s->cur_max_len = max_len;
     if (p->reseed) {
-        rc = seeder_ensure_reseed(s, n_reads, max_len, 0);
+        rc = seeder_ensure_reseed(s, n_reads, max_len, 0, 0);
         if (rc) return rc;
         rc = seeder_reseed(s);
         if (rc) return rc;
@@ -1013,9 +1023,9 @@ int b200_seeder_finish(bwa_b200_seeder *s)
     if (s->last_n_reads == 0) return BWA_B200_OK;
     B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
-    while (s->last_p.reseed && s->h_counters[4] > s->xstride) {
-        // a read produced more intervals than a row holds: widen the rows and redo the re-seeding passes (rare)
-        int rc = seeder_ensure_reseed(s, s->last_n_reads, s->cur_max_len, (uint32_t)s->h_counters[4] + 8);
+    while (s->last_p.reseed && (s->h_counters[4] > s->xstride || s->h_counters[5] > s->stride3)) {
+        // a read produced more intervals / pass-2 candidates than a row holds: widen the rows and redo the re-seeding passes (rare)
+        int rc = seeder_ensure_reseed(s, s->last_n_reads, s->cur_max_len, (uint32_t)s->h_counters[4] + 8, (uint32_t)s->h_counters[5] + 8);
         if (rc) return rc;
         rc = seeder_reseed(s);
         if (rc) return rc;

@@ -113,8 +113,9 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
     reads = [base[i, :int(rng.choice([150, 150, 150, 250, 101, 36, 12]))] for i in range(3000)]
     reads.append(np.full(50, 4, np.uint8))
     rf, off = flat(reads)
-    for max_occ in (500, 20):
-        sd = oi.seed_batch(rf, off, 19, max_occ, n_threads=4)
+    for max_occ, reseed in ((500, False), (20, False), (500, True)):
+        # reseed: the seed set of stock `bwa mem` (mem_collect_intv passes 2 and 3) feeding the same chaining stage
+        sd = oi.seed_batch(rf, off, 19, max_occ, n_threads=4, rs=oracle.reseed() if reseed else None)
         ctg = CP.Contigs((g.size,))
         opt = CP.default_opt(max_occ=max_occ, w=100)
         kp = oracle.make_params(w=100, zdrop=100, use_band=1)
@@ -122,7 +123,8 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
         want = CP.oracle_align_batch(opt, ctg, g, reads, sd["rbeg"], qq, sd["score"], sd["n_seeds"], sd["seed_off"], 0, kp)
         packed, woff, rl = gpu.pack_codes(rf, off)
         al = gpu.Aligner(idx, len(reads), packed.size)
-        got = al.align_host(packed, woff, rl, gpu.SeedParams(19, max_occ), gpu.chain_params(max_occ=max_occ, w=100),
+        spar = gpu.seed_params(19, max_occ, reseed)
+        got = al.align_host(packed, woff, rl, spar, gpu.chain_params(max_occ=max_occ, w=100),
                             gpu.ext_params(w=100, zdrop=100, use_band=1), detail=True)
         check_batch(got, want)
         assert len(want["regs"]) > 2500
@@ -130,7 +132,7 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
         assert v.n_regions == len(want["regs"]) and v.cells == want["cells"] and v.n_seeds == sd["total"]
         # the same batch through the pinned-buffer entry point (twice: buffers are reused)
         for _ in range(2):
-            pv = al.align_host_view(packed.ctypes.data, woff.ctypes.data, rl.ctypes.data, rl.size, gpu.SeedParams(19, max_occ),
+            pv = al.align_host_view(packed.ctypes.data, woff.ctypes.data, rl.ctypes.data, rl.size, spar,
                                     gpu.chain_params(max_occ=max_occ, w=100), gpu.ext_params(w=100, zdrop=100, use_band=1))
             assert pv["regions"].tobytes() == got["regions"].tobytes()
             assert (pv["n_regions"] == got["n_regions"]).all() and (pv["region_off"] == got["region_off"]).all()
