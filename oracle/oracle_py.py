@@ -60,7 +60,7 @@ class KswCounters(C.Structure):
 def build_oracle() -> str:
     """(Re)build oracle/liboracle.so if missing or stale; returns its path."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "global_oracle.c", "global_oracle.h", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -91,6 +91,13 @@ def lib():
         L.fmd_smem_batch_rs.argtypes = [C.POINTER(FmdIndex), u8p, u64p, C.c_int64, C.c_int, C.POINTER(Reseed),
                                         u32p, i32p, i32p, u64p, u64p, C.c_int64, C.c_int, C.POINTER(FmdCounters)]
         L.fmd_smem_batch_rs.restype = C.c_int64
+        L.glb_batch.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p, i8p] + [C.c_int] * 4 + [i32p, i32p, u32p, u32p, C.c_int, C.c_int,
+                                C.POINTER(C.c_uint64)]
+        L.glb_band.argtypes = [i8p] + [C.c_int] * 6 + [C.c_int64]
+        L.glb_band.restype = C.c_int
+        L.glb_gen_cigar2.argtypes = [i8p] + [C.c_int] * 5 + [C.c_int64, u8p, C.c_int, u8p, C.c_int64, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     u32p, C.c_int]
+        L.glb_gen_cigar2.restype = C.c_int
         L.ksw_fill_mat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.ksw_extend_batch_oracle.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p,
                                               C.POINTER(KswParams), i32p, C.c_int, C.POINTER(KswCounters)]
@@ -190,6 +197,39 @@ class OracleIndex:
                     counters=cnt.as_dict())
 
 
+def _mat(params):
+    return np.frombuffer(bytes(params.mat), dtype=np.int8).copy()
+
+
+def global_batch(jobs: dict, params: KswParams, cig_stride=64, n_threads=None):
+    """ksw_global2 + NM over a batch (oracle/global_oracle.c).  jobs: qseq tseq qoff toff qlen tlen w.  Returns dict(score, nm,
+    n_cigar, cigar[n, cig_stride], cells)."""
+    n = jobs["qlen"].size
+    score = np.zeros(n, np.int32); nm = np.zeros(n, np.int32); nc = np.zeros(n, np.uint32)
+    cig = np.zeros(max(n, 1) * cig_stride, np.uint32)
+    cells = C.c_uint64(0)
+    lib().glb_batch(n, jobs["qseq"], jobs["qoff"], jobs["qlen"], jobs["tseq"], jobs["toff"], jobs["tlen"], np.ascontiguousarray(jobs["w"], np.uint32),
+                    _mat(params), params.o_del, params.e_del, params.o_ins, params.e_ins, score, nm, nc, cig, cig_stride,
+                    n_threads or default_threads(), C.byref(cells))
+    return dict(score=score, nm=nm, n_cigar=nc, cigar=cig.reshape(-1, cig_stride)[:n], cells=int(cells.value))
+
+
+def global_band(params: KswParams, w_, l_query, rlen):
+    return int(lib().glb_band(_mat(params), params.o_del, params.e_del, params.o_ins, params.e_ins, int(w_), int(l_query), int(rlen)))
+
+
+def gen_cigar2(params: KswParams, w_, fwd, query, rb, re, cap=256):
+    """bwa_gen_cigar2 restated over forward reference codes: (score, nm, cigar[n_cigar]) or None when rejected"""
+    sc, nm = C.c_int(0), C.c_int(0)
+    cig = np.zeros(cap, np.uint32)
+    q = np.ascontiguousarray(query, np.uint8)
+    n = lib().glb_gen_cigar2(_mat(params), params.o_del, params.e_del, params.o_ins, params.e_ins, int(w_), fwd.size, fwd, q.size, q, int(rb), int(re),
+                             C.byref(sc), C.byref(nm), cig, cap)
+    if n < 0:
+        return None
+    return int(sc.value), int(nm.value), cig[:n].copy()
+
+
 def ksw_batch(jobs: dict, params: KswParams, n_threads=None):
     """jobs: dict from tools.synth.make_ext_jobs.  Returns (res[n,6] int32, counters dict).
     Columns: score, qle, tle, gtle, gscore, max_off."""
@@ -237,6 +277,11 @@ def ref_lib():
         L.ref_ksw_extend2.restype = C.c_int
         L.ref_seed_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.ref_seed_batch.restype = C.c_int64
+        L.ref_ksw_global2.argtypes = [C.c_int, u8p, C.c_int, u8p, i8p] + [C.c_int] * 5 + [C.POINTER(C.c_int), u32p, C.c_int]
+        L.ref_ksw_global2.restype = C.c_int
+        L.ref_gen_cigar2.argtypes = [i8p] + [C.c_int] * 5 + [C.c_int64, u8p, C.c_int, u8p, C.c_int64, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     u32p, C.c_int]
+        L.ref_gen_cigar2.restype = C.c_int
         L.ref_collect_intv.argtypes = [C.c_void_p, C.c_int, u8p, C.c_int, C.c_float, C.c_int, C.c_int, u64p, C.c_int]
         L.ref_collect_intv.restype = C.c_int
         L.ref_collect_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_int, u32p, u64p, C.c_int64]

@@ -208,3 +208,30 @@ void ref_pipeline_batch(void *h, const uint8_t *fwd, int64_t l_pac, const uint8_
         free(mem.a); free(t0.a); free(t1.a); free(rb); free(qb); free(qe); free(qbuf); free(tbuf);
     }
 }
+
+/* ---- CIGAR path: the reference's ksw_global2 (bwa_index/ksw.c:504) and bwa_gen_cigar2
+ * (bwa_index/bwa.c:121).  The CIGAR is copied out (first `cap` operations) and the reference's buffer freed. */
+int ref_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                    int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t *cigar_out, int cap)
+{
+    uint32_t *cigar = NULL;
+    int sc = ksw_global2(qlen, query, tlen, target, 5, mat, o_del, e_del, o_ins, e_ins, w, n_cigar, &cigar);
+    for (int i = 0; i < *n_cigar && i < cap; ++i) cigar_out[i] = cigar[i];
+    free(cigar);
+    return sc;
+}
+
+/* pac: 2-bit packed forward reference (4 bases per byte, bntseq.c _get_pac).  Returns n_cigar (0 when the reference
+ * rejects the job and returns NULL). */
+int ref_gen_cigar2(const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac, const uint8_t *pac,
+                   int l_query, const uint8_t *query, int64_t rb, int64_t re, int *score, int *nm, uint32_t *cigar_out, int cap)
+{
+    int n_cigar = 0;
+    uint8_t *q = (uint8_t *)malloc(l_query > 0 ? l_query : 1);
+    memcpy(q, query, l_query > 0 ? l_query : 0);
+    *score = 0; *nm = -1;
+    uint32_t *cigar = bwa_gen_cigar2(mat, o_del, e_del, o_ins, e_ins, w_, l_pac, pac, l_query, q, rb, re, score, &n_cigar, nm);
+    for (int i = 0; cigar && i < n_cigar && i < cap; ++i) cigar_out[i] = cigar[i];
+    free(cigar); free(q);
+    return n_cigar;
+}

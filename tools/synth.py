@@ -179,3 +179,45 @@ def make_ext_jobs(n_jobs: int, qlen_choices=(100, 150, 200, 250, 300), w: int = 
         tseq[toff[a]:toff[a] + tl] = t
     return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff,
                 qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
+
+
+def make_global_jobs(n_jobs: int, qlen_range=(30, 150), seed: int = 991, sub_rate: float = 0.03, indel_rate: float = 0.01,
+                     w_extra=(0, 0), n_frac: float = 0.01, w_cap: int = 100):
+    """End-to-end alignment jobs for ksw_global2 / bwa_gen_cigar2: target = query with substitutions and short indels (no
+    tail: both ends are fixed).  Band per job = |tlen - qlen| + 3 + U[w_extra], capped at w_cap but never below the
+    feasible minimum |tlen - qlen| + 1.  Byte codes 0..4, sequences padded to a multiple of 8 with code 4."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    qs, ts = [], []
+    for _ in range(n_jobs):
+        ql = int(rng.integers(qlen_range[0], qlen_range[1] + 1))
+        q = rng.integers(0, 4, size=ql, dtype=np.uint8)
+        if rng.random() < n_frac:
+            q[int(rng.integers(0, ql))] = 4
+        t = q.copy()
+        sm = rng.random(ql) < sub_rate
+        t[sm] = (t[sm] + rng.integers(1, 4, size=int(sm.sum()), dtype=np.uint8)) & 3
+        ev = np.nonzero(rng.random(ql) < indel_rate)[0]
+        if ev.size:
+            parts, last = [], 0
+            for p in ev:
+                parts.append(t[last:p])
+                if rng.random() < 0.5:
+                    parts.append(rng.integers(0, 4, size=int(rng.integers(1, 5)), dtype=np.uint8)); last = p
+                else:
+                    last = min(ql, p + int(rng.integers(1, 5)))
+            parts.append(t[last:])
+            t = np.concatenate(parts)
+        if t.size == 0:
+            t = q[:1].copy()
+        qs.append(q); ts.append(t)
+    qlen = np.array([x.size for x in qs], np.uint32); tlen = np.array([x.size for x in ts], np.uint32)
+    qp = (qlen.astype(np.int64) + 7) // 8 * 8; tp = (tlen.astype(np.int64) + 7) // 8 * 8
+    qoff = np.zeros(n_jobs, np.uint32); toff = np.zeros(n_jobs, np.uint32)
+    qoff[1:] = np.cumsum(qp)[:-1]; toff[1:] = np.cumsum(tp)[:-1]
+    qseq = np.full(int(qp.sum()), 4, np.uint8); tseq = np.full(int(tp.sum()), 4, np.uint8)
+    for a in range(n_jobs):
+        qseq[qoff[a]:qoff[a] + qlen[a]] = qs[a]; tseq[toff[a]:toff[a] + tlen[a]] = ts[a]
+    diff = np.abs(tlen.astype(np.int64) - qlen.astype(np.int64))
+    w = diff + 3 + rng.integers(w_extra[0], w_extra[1] + 1, size=n_jobs)
+    w = np.maximum(np.minimum(w, w_cap), diff + 1).astype(np.uint32)
+    return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlen, tlen=tlen, w=w)
