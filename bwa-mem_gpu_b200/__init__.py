@@ -106,7 +106,15 @@ SYMBOLS = [
     "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_host_view", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
     "bwa_b200_align_device_view", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
     "bwa_b200_aligner_kernel_times",
+    "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_cigars_free",
+    "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
+    "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times",
 ]
+
+
+class Cigars(C.Structure):
+    _fields_ = [("n_jobs", C.c_uint64), ("n_ops", C.c_uint64), ("score", C.POINTER(C.c_int32)), ("nm", C.POINTER(C.c_int32)),
+                ("n_cigar", C.POINTER(C.c_uint32)), ("cigar_off", C.POINTER(C.c_uint64)), ("cigar", C.POINTER(C.c_uint32))]
 
 
 class ChainParams(C.Structure):
@@ -227,6 +235,21 @@ def lib():
         L.bwa_b200_aligner_launches.restype = C.c_uint64
         L.bwa_b200_aligner_profile.argtypes = [vp, C.c_int]
         L.bwa_b200_aligner_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+        L.bwa_b200_cigar_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.bwa_b200_cigar_destroy.argtypes = [vp]
+        L.bwa_b200_cigar_band.argtypes = [C.POINTER(ExtParams), C.c_int, C.c_int, C.c_int64]
+        L.bwa_b200_global_host.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.POINTER(Cigars)]
+        L.bwa_b200_cigars_free.argtypes = [C.POINTER(Cigars)]
+        L.bwa_b200_global_device.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.bwa_b200_global_device_view.argtypes = [vp, C.POINTER(Cigars)]
+        L.bwa_b200_cigar_stream.argtypes = [vp]
+        L.bwa_b200_cigar_stream.restype = vp
+        L.bwa_b200_cigar_launches.argtypes = [vp]
+        L.bwa_b200_cigar_launches.restype = C.c_uint64
+        L.bwa_b200_cigar_last_cells.argtypes = [vp]
+        L.bwa_b200_cigar_last_cells.restype = C.c_uint64
+        L.bwa_b200_cigar_profile.argtypes = [vp, C.c_int]
+        L.bwa_b200_cigar_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
         _lib = L
     return _lib
 
@@ -581,4 +604,62 @@ class Aligner:
     def destroy(self):
         if self.h:
             lib().bwa_b200_aligner_destroy(self.h)
+            self.h = None
+
+
+class Cigar:
+    """banded global alignment with backtrack on the device: CIGAR, score and NM per job (bwa_b200_global_*)."""
+
+    def __init__(self, device: int = 0):
+        self.h = vp()
+        check(lib().bwa_b200_cigar_create(device, C.byref(self.h)))
+
+    @staticmethod
+    def band(ext_p: ExtParams, w_, l_query, rlen) -> int:
+        return int(lib().bwa_b200_cigar_band(C.byref(ext_p), int(w_), int(l_query), int(rlen)))
+
+    def global_host(self, jobs: dict, ext_p: ExtParams):
+        """jobs: qseq tseq (uint8 codes) qoff toff qlen tlen w (uint32).  Returns dict(score, nm, n_cigar, cigar_off, cigar)."""
+        n = jobs["qlen"].size
+        arr = {k: np.ascontiguousarray(jobs[k], np.uint8 if k in ("qseq", "tseq") else np.uint32) for k in ("qseq", "tseq", "qoff", "toff", "qlen", "tlen", "w")}
+        out = Cigars()
+        check(lib().bwa_b200_global_host(self.h, C.byref(ext_p), n, _p(arr["qseq"]), arr["qseq"].size, _p(arr["qoff"]), _p(arr["qlen"]),
+                                         _p(arr["tseq"]), arr["tseq"].size, _p(arr["toff"]), _p(arr["tlen"]), _p(arr["w"]), C.byref(out)))
+        res = dict(score=_take(out.score, n, np.int32), nm=_take(out.nm, n, np.int32), n_cigar=_take(out.n_cigar, n, np.uint32),
+                   cigar_off=_take(out.cigar_off, n, np.uint64), cigar=_take(out.cigar, out.n_ops, np.uint32))
+        lib().bwa_b200_cigars_free(C.byref(out))
+        return res
+
+    def global_device(self, ext_p, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_tlen, h_w):
+        check(lib().bwa_b200_global_device(self.h, C.byref(ext_p), n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, _p(h_tlen), _p(h_w)))
+
+    def view(self) -> Cigars:
+        v = Cigars()
+        check(lib().bwa_b200_global_device_view(self.h, C.byref(v)))
+        return v
+
+    def profile(self, on: bool):
+        check(lib().bwa_b200_cigar_profile(self.h, int(on)))
+
+    def kernel_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        n = lib().bwa_b200_cigar_kernel_times(self.h, names, ms, 16)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    @property
+    def stream(self) -> int:
+        return int(lib().bwa_b200_cigar_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_cigar_launches(self.h))
+
+    @property
+    def last_cells(self) -> int:
+        return int(lib().bwa_b200_cigar_last_cells(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_cigar_destroy(self.h)
             self.h = None

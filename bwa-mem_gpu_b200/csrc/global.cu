@@ -1,0 +1,450 @@
+// global.cu -- banded global alignment with backtrack -> CIGAR, score and NM, sm_100a  (SURVEY 8f row 4).
+//
+// Parity target: the reference's CPU path  mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2  (src/bwa.c:111-216,
+// src/ksw.c:1120-1241 = bwa_index/ksw.c:504-606): the remaining dynamic programming of the reference's worker2.
+//
+//   global_kernel<R, BLOCK>   one job per lane, 32 jobs of similar band width per warp, rows in order (the recurrence of
+//                             ksw_global2 cell for cell, int32).  Per-column state {H(i-1,j-1), E(i,j)} lives in a ring of R
+//                             slots in shared memory, [slot][lane] (a row touches columns [i-w, i+w+1), so 2w+2 slots are
+//                             live).  The backtrack matrix keeps 4 bits per cell -- the three direction fields of the
+//                             reference's byte (h: 2 bits, e: 1, f: 1) -- eight cells per word, written [row][word][lane] so
+//                             that the 32 lanes of a warp store one 128-byte line; warps are persistent and reuse their
+//                             slab, which therefore stays in L2 for the backtrack that follows immediately.
+//                             The backtrack walks (i, k) exactly as the reference, merges operations like push_cigar, counts
+//                             mismatches for NM on the way, and writes the operations right-aligned into the job's row.
+//   compact_kernel            rows -> flat CIGAR array at scanned offsets.
+//
+// Bound: INT ALU (about 20 integer operations per cell plus one 64-bit shared-memory load and store); HBM traffic is the
+// sequences once and 0.5 byte per cell of backtrack state that mostly stays in L2.
+#include "internal.h"
+#include <algorithm>
+#include <vector>
+#include <cub/cub.cuh>
+
+namespace {
+
+constexpr int32_t MINF = -0x40000000;      // MINUS_INF, src/ksw.c
+
+struct GArgs {
+    const uint8_t *qseq, *tseq;
+    const uint32_t *qoff, *qlen, *toff, *tlen, *w;
+    int8_t mat[25];
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t *score, *nm;
+    uint32_t *n_cigar, *rows;               // rows: cig_stride operations per job, right-aligned
+    uint32_t cig_stride;
+    unsigned long long *counters;           // [0] cells, [1] widest CIGAR row needed
+};
+
+template <int R, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t tlen_max, uint32_t *__restrict__ z_all)
+{
+    extern __shared__ int2 eh_ring[];                   // [R][BLOCK]
+    __shared__ int8_t smat[32];
+    int2 (*eh)[BLOCK] = reinterpret_cast<int2 (*)[BLOCK]>(eh_ring);
+    constexpr int WPR = R / 8;              // backtrack words per row
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (tid < 25) smat[tid] = a.mat[tid];
+    __syncthreads();
+    const uint32_t gwarp = blockIdx.x * (BLOCK / 32) + (tid >> 5), n_warps = gridDim.x * (BLOCK / 32);
+    uint32_t *const z = z_all + (uint64_t)gwarp * tlen_max * WPR * 32;
+    const int oe_del = a.o_del + a.e_del, oe_ins = a.o_ins + a.e_ins;
+    unsigned long long cells = 0;
+
+    for (uint32_t chunk = gwarp; (uint64_t)chunk * 32 < n; chunk += n_warps) {
+        const uint32_t idx = chunk * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t job = valid ? perm[idx] : 0u;
+        const int qlen = valid ? (int)a.qlen[job] : 0, tlen = valid ? (int)a.tlen[job] : 0, w = valid ? (int)a.w[job] : 0;
+        const uint8_t *q = a.qseq + (valid ? a.qoff[job] : 0u), *t = a.tseq + (valid ? a.toff[job] : 0u);
+        // first row (src/ksw.c:1141-1147); only columns 0 .. min(w + 1, qlen) can be read before they are rewritten
+        eh[0][tid] = make_int2(0, MINF);
+        {
+            const int top = w + 1 < qlen ? w + 1 : qlen;
+            for (int j = 1; j <= top; ++j) eh[j & (R - 1)][tid] = j <= w ? make_int2(-(a.o_ins + a.e_ins * j), MINF) : make_int2(MINF, MINF);
+        }
+        int warp_tl = tlen;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) warp_tl = max(warp_tl, __shfl_xor_sync(0xffffffffu, warp_tl, o));
+        for (int i = 0; i < warp_tl; ++i) {
+            const bool act = i < tlen;
+            const int beg = i > w ? i - w : 0;
+            const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+            const int ncol = act && end > beg ? end - beg : 0;
+            int warp_nc = ncol;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) warp_nc = max(warp_nc, __shfl_xor_sync(0xffffffffu, warp_nc, o));
+            const int8_t *srow = smat + (act ? (int)t[i] : 0) * 5;
+            int32_t f = MINF, h1 = beg == 0 ? -(a.o_del + a.e_del * (i + 1)) : MINF;
+            uint32_t zw = 0;
+            uint32_t *zrow = z + (uint64_t)i * WPR * 32 + lane;
+            for (int c = 0; c < warp_nc; ++c) {
+                if (c < ncol) {
+                    const int j = beg + c;
+                    int2 *p = &eh[j & (R - 1)][tid];
+                    const int2 pe = *p;
+                    int32_t m = pe.x + srow[q[j]], e = pe.y, h, tt;
+                    uint32_t d;
+                    d = m >= e ? 0u : 1u;
+                    h = m >= e ? m : e;
+                    d = h >= f ? d : 2u;
+                    h = h >= f ? h : f;
+                    tt = m - oe_del;
+                    e -= a.e_del;
+                    d |= e > tt ? 4u : 0u;
+                    e = e > tt ? e : tt;
+                    *p = make_int2(h1, e);
+                    h1 = h;
+                    tt = m - oe_ins;
+                    f -= a.e_ins;
+                    d |= f > tt ? 8u : 0u;
+                    f = f > tt ? f : tt;
+                    zw |= d << (4 * (c & 7));
+                }
+                if ((c & 7) == 7) { zrow[(c >> 3) * 32] = zw; zw = 0; }
+            }
+            if (warp_nc & 7) zrow[(warp_nc >> 3) * 32] = zw;
+            if (act) eh[end & (R - 1)][tid] = make_int2(h1, MINF);
+            cells += (unsigned long long)ncol;
+        }
+        if (!valid) continue;
+        // score = eh[qlen].h (src/ksw.c:1207).  When the last row does not reach column qlen the reference reads the
+        // value of the first-row initialisation, which is MINUS_INF there (qlen > w), or was never in the ring (tlen == 0)
+        int32_t score;
+        if (tlen == 0) score = qlen == 0 ? 0 : (qlen <= w ? -(a.o_ins + a.e_ins * qlen) : MINF);
+        else score = tlen + w >= qlen ? eh[qlen & (R - 1)][tid].x : MINF;
+        // backtrack (src/ksw.c:1208-1231)
+        int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+        uint32_t which = 0, n_ops = 0, cur_op = 0, cur_len = 0, nmm = 0, gap = 0, edge_del = 0;
+        uint32_t *row = a.rows + (uint64_t)job * a.cig_stride;
+        auto flush = [&]() {                 // the operation is complete: store it (right-aligned, the list is built backwards)
+            if (cur_len == 0) return;
+            if (n_ops < a.cig_stride) row[a.cig_stride - 1 - n_ops] = cur_len << 4 | cur_op;
+            if (cur_op) gap += cur_len;
+            if (cur_op == 2 && n_ops == 0) edge_del += cur_len;        // will be the last operation of the CIGAR
+            ++n_ops;
+        };
+        auto push = [&](uint32_t op, uint32_t len) {                   // push_cigar
+            if (cur_len && op == cur_op) cur_len += len;
+            else { flush(); cur_op = op; cur_len = len; }
+        };
+        while (i >= 0 && k >= 0) {
+            int c = k - (i > w ? i - w : 0);
+            c = c < 0 ? 0 : (c > R - 1 ? R - 1 : c);        // never outside the row's words (the reference would read out of bounds)
+            const uint32_t code = (z[((uint64_t)i * WPR + (c >> 3)) * 32 + lane] >> (4 * (c & 7))) & 15u;
+            which = which == 0 ? (code & 3u) : (which == 1 ? ((code >> 2) & 1u) : ((code >> 3) & 1u) * 2u);
+            if (which == 0) { nmm += q[k] != t[i]; push(0, 1); --i; --k; }
+            else if (which == 1) { push(2, 1); --i; }
+            else { push(1, 1); --k; }
+        }
+        if (i >= 0) push(2, (uint32_t)(i + 1));
+        if (k >= 0) push(1, (uint32_t)(k + 1));
+        if (cur_len && cur_op == 2 && n_ops > 0) edge_del += cur_len;   // the first operation of the CIGAR (and not also the last)
+        flush();
+        a.score[job] = score;
+        a.n_cigar[job] = n_ops;
+        a.nm[job] = (int32_t)(nmm + gap - edge_del);                    // src/bwa.c:178-205
+        if (n_ops > a.cig_stride) atomicMax(a.counters + 1, (unsigned long long)n_ops);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if (lane == 0 && cells) atomicAdd(a.counters, cells);
+}
+
+__global__ void __launch_bounds__(128)
+compact_kernel(uint32_t n, const uint32_t *__restrict__ n_cigar, const uint64_t *__restrict__ off, const uint32_t *__restrict__ rows,
+               uint32_t stride, uint32_t *__restrict__ flat)
+{
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t m = n_cigar[a];
+    if (m > stride) return;
+    const uint32_t *src = rows + (uint64_t)a * stride + (stride - m);
+    uint32_t *dst = flat + off[a];
+    for (uint32_t i = 0; i < m; ++i) dst[i] = src[i];
+}
+
+__global__ void total32_kernel(const uint32_t *n_per, const uint64_t *off, uint32_t n, unsigned long long *total)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = n ? off[n - 1] + n_per[n - 1] : 0ull;
+}
+
+struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
+
+template <typename T> int grow_dev(T *&p, uint64_t &cap, uint64_t need)
+{
+    if (need <= cap && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    uint64_t c = need + need / 4 + 64;
+    if (cudaMalloc(&p, c * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return 1; }
+    cap = c;
+    return 0;
+}
+
+struct ClassCfg { int R, block; uint32_t wmax; };
+const ClassCfg CLASSES[5] = {{16, 128, 7}, {32, 128, 15}, {64, 64, 31}, {128, 32, 63}, {256, 32, 127}};
+
+} // namespace
+
+struct bwa_b200_cigar {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    // inputs (host API)
+    uint8_t *d_q = nullptr, *d_t = nullptr; uint64_t q_cap = 0, t_cap = 0;
+    uint32_t *d_qoff = nullptr, *d_qlen = nullptr, *d_toff = nullptr, *d_tlen = nullptr; uint64_t qoff_cap = 0, qlen_cap = 0, toff_cap = 0, tlen_cap = 0;
+    // per job
+    uint32_t *d_w = nullptr, *d_perm = nullptr, *d_ncig = nullptr; uint64_t w_cap = 0, perm_cap = 0, ncig_cap = 0;
+    int32_t *d_score = nullptr, *d_nm = nullptr; uint64_t score_cap = 0, nm_cap = 0;
+    uint64_t *d_off = nullptr; uint64_t off_cap = 0;
+    uint32_t *d_rows = nullptr; uint64_t rows_cap = 0; uint32_t cig_stride = 16;
+    uint32_t *d_flat = nullptr; uint64_t flat_cap = 0;
+    uint32_t *d_z = nullptr; uint64_t z_cap = 0;
+    void *d_cub = nullptr; uint64_t cub_cap = 0;
+    unsigned long long *d_counters = nullptr, *h_counters = nullptr;   // [0] cells [1] widest row needed [2] total operations
+    int grid[5] = {0, 0, 0, 0, 0};
+    std::vector<uint32_t> perm; uint32_t cls_n[5] = {}, cls_tl[5] = {};
+    uint64_t last_n = 0, last_ops = 0, last_cells = 0, launches = 0;
+    b200::Prof prof; int profiling = 0;
+};
+
+template <int R, int BLOCK> static int class_grid(int n_sm, int *grid)
+{
+    int occ = 0;
+    const size_t smem = (size_t)R * BLOCK * sizeof(int2);
+    B200_CUDA(cudaFuncSetAttribute(global_kernel<R, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, global_kernel<R, BLOCK>, BLOCK, smem));
+    if (occ < 1) occ = 1;
+    int warps = occ * (BLOCK / 32);
+    if (warps > 24) occ = std::max(1, 24 / (BLOCK / 32));      // bound the backtrack slabs (L2 residency)
+    *grid = n_sm * occ;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_cigar_create(int device, bwa_b200_cigar_t **out)
+{
+    if (!out) { b200::set_error("cigar_create: bad argument"); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(device));
+    bwa_b200_cigar *c = new bwa_b200_cigar();
+    c->device = device;
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+    B200_CUDA(cudaHostAlloc(&c->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    int rc = class_grid<16, 128>(c->n_sm, &c->grid[0]); if (rc) return rc;
+    rc = class_grid<32, 128>(c->n_sm, &c->grid[1]); if (rc) return rc;
+    rc = class_grid<64, 64>(c->n_sm, &c->grid[2]); if (rc) return rc;
+    rc = class_grid<128, 32>(c->n_sm, &c->grid[3]); if (rc) return rc;
+    rc = class_grid<256, 32>(c->n_sm, &c->grid[4]); if (rc) return rc;
+    *out = c;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_cigar_destroy(bwa_b200_cigar_t *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_qoff); cudaFree(c->d_qlen); cudaFree(c->d_toff); cudaFree(c->d_tlen);
+    cudaFree(c->d_w); cudaFree(c->d_perm); cudaFree(c->d_ncig); cudaFree(c->d_score); cudaFree(c->d_nm); cudaFree(c->d_off);
+    cudaFree(c->d_rows); cudaFree(c->d_flat); cudaFree(c->d_z); cudaFree(c->d_cub); cudaFree(c->d_counters);
+    cudaFreeHost(c->h_counters);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int bwa_b200_cigar_band(const bwa_b200_ext_params_t *p, int w_, int l_query, int64_t rlen)
+{ // src/bwa.c:161-169
+    if (!p) return -1;
+    int max_ins = (int)((double)(((l_query + 1) >> 1) * p->mat[0] - p->o_ins) / p->e_ins + 1.);
+    int max_del = (int)((double)(((l_query + 1) >> 1) * p->mat[0] - p->o_del) / p->e_del + 1.);
+    int max_gap = max_ins > max_del ? max_ins : max_del;
+    max_gap = max_gap > 1 ? max_gap : 1;
+    int diff = (int)(rlen - l_query); if (diff < 0) diff = -diff;
+    int w = (max_gap + diff + 1) >> 1;
+    w = w < w_ ? w : w_;
+    int min_w = diff + 3;
+    return w > min_w ? w : min_w;
+}
+
+template <int R, int BLOCK>
+static void launch_class(bwa_b200_cigar *c, const GArgs &ga, int cls, uint32_t first, const char *name)
+{
+    b200::Prof *prof = c->profiling ? &c->prof : nullptr;
+    B200_LAUNCH(prof, name, c->stream,
+        (global_kernel<R, BLOCK><<<c->grid[cls], BLOCK, (size_t)R * BLOCK * sizeof(int2), c->stream>>>(ga, c->d_perm + first, c->cls_n[cls], c->cls_tl[cls], c->d_z)));
+    ++c->launches;
+}
+
+// jobs already on the device (byte per base); host copies of tlen and w drive the binning
+static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs, const uint8_t *d_q, const uint32_t *d_qoff,
+                     const uint32_t *d_qlen, const uint8_t *d_t, const uint32_t *d_toff, const uint32_t *d_tlen, const uint32_t *d_w,
+                     const uint32_t *h_tlen, const uint32_t *h_w)
+{
+    c->last_n = n_jobs; c->last_ops = 0; c->last_cells = 0;
+    if (n_jobs == 0) return BWA_B200_OK;
+    if (n_jobs > 0xfffffff0ull) { b200::set_error("global: at most 2^32-16 jobs per batch"); return BWA_B200_ERR_ARG; }
+    const uint32_t n = (uint32_t)n_jobs;
+    // bin the jobs by band-width class
+    uint32_t cnt[5] = {0, 0, 0, 0, 0}, tl[5] = {0, 0, 0, 0, 0};
+    for (uint32_t a = 0; a < n; ++a) {
+        const uint32_t w = h_w[a];
+        int k = 0;
+        while (k < 5 && w > CLASSES[k].wmax) ++k;
+        if (k == 5) { b200::set_error("global: band %u of job %u is wider than 127", w, a); return BWA_B200_ERR_ARG; }
+        ++cnt[k]; tl[k] = std::max(tl[k], h_tlen[a]);
+    }
+    uint32_t first[6] = {0, 0, 0, 0, 0, 0}, cur[5];
+    for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; cur[k] = first[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; }
+    c->perm.resize(n);
+    for (uint32_t a = 0; a < n; ++a) {
+        int k = 0;
+        while (h_w[a] > CLASSES[k].wmax) ++k;
+        c->perm[cur[k]++] = a;
+    }
+    uint64_t z_need = 1;
+    for (int k = 0; k < 5; ++k)
+        if (cnt[k]) z_need = std::max<uint64_t>(z_need, (uint64_t)c->grid[k] * (CLASSES[k].block / 32) * c->cls_tl[k] * (CLASSES[k].R / 8) * 32);
+    int bad = 0;
+    bad |= grow_dev(c->d_perm, c->perm_cap, n); bad |= grow_dev(c->d_ncig, c->ncig_cap, n); bad |= grow_dev(c->d_score, c->score_cap, n);
+    bad |= grow_dev(c->d_nm, c->nm_cap, n); bad |= grow_dev(c->d_off, c->off_cap, n); bad |= grow_dev(c->d_z, c->z_cap, z_need);
+    bad |= grow_dev(c->d_rows, c->rows_cap, (uint64_t)n * c->cig_stride);
+    size_t cub_bytes = 0;
+    cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(c->d_ncig, U32ToU64());
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, it, c->d_off, (int)n, c->stream));
+    uint8_t *cubp = (uint8_t *)c->d_cub;
+    bad |= grow_dev(cubp, c->cub_cap, cub_bytes + 16);
+    c->d_cub = cubp;
+    if (bad) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
+    cudaStream_t st = c->stream;
+    B200_CUDA(cudaMemcpyAsync(c->d_perm, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (c->profiling) c->prof.reset();
+    for (;;) {
+        B200_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+        GArgs ga;
+        ga.qseq = d_q; ga.tseq = d_t; ga.qoff = d_qoff; ga.qlen = d_qlen; ga.toff = d_toff; ga.tlen = d_tlen; ga.w = d_w;
+        memcpy(ga.mat, p->mat, 25);
+        ga.o_del = p->o_del; ga.e_del = p->e_del; ga.o_ins = p->o_ins; ga.e_ins = p->e_ins;
+        ga.score = c->d_score; ga.nm = c->d_nm; ga.n_cigar = c->d_ncig; ga.rows = c->d_rows; ga.cig_stride = c->cig_stride;
+        ga.counters = c->d_counters;
+        if (cnt[0]) launch_class<16, 128>(c, ga, 0, first[0], "global_kernel_w7");
+        if (cnt[1]) launch_class<32, 128>(c, ga, 1, first[1], "global_kernel_w15");
+        if (cnt[2]) launch_class<64, 64>(c, ga, 2, first[2], "global_kernel_w31");
+        if (cnt[3]) launch_class<128, 32>(c, ga, 3, first[3], "global_kernel_w63");
+        if (cnt[4]) launch_class<256, 32>(c, ga, 4, first[4], "global_kernel_w127");
+        B200_CUDA(cudaGetLastError());
+        size_t tmp = c->cub_cap;
+        B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub, tmp, it, c->d_off, (int)n, st));
+        total32_kernel<<<1, 1, 0, st>>>(c->d_ncig, c->d_off, n, c->d_counters + 2);
+        c->launches += 2;
+        B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        if (c->h_counters[1] <= c->cig_stride) break;
+        // some CIGAR has more operations than a row holds: widen the rows and run the batch again (rare)
+        c->cig_stride = (uint32_t)c->h_counters[1] + 8;
+        if (grow_dev(c->d_rows, c->rows_cap, (uint64_t)n * c->cig_stride)) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
+    }
+    c->last_cells = c->h_counters[0];
+    c->last_ops = c->h_counters[2];
+    if (grow_dev(c->d_flat, c->flat_cap, c->last_ops ? c->last_ops : 1)) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
+    b200::Prof *prof = c->profiling ? &c->prof : nullptr;
+    B200_LAUNCH(prof, "compact_kernel", st,
+        (compact_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, c->d_ncig, c->d_off, c->d_rows, c->cig_stride, c->d_flat)));
+    ++c->launches;
+    B200_CUDA(cudaGetLastError());
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                      const uint8_t *dev_qseq, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
+                                      const uint8_t *dev_tseq, const uint32_t *dev_toff, const uint32_t *dev_tlen,
+                                      const uint32_t *host_tlen, const uint32_t *host_w)
+{
+    if (!c || !p || (n_jobs && (!dev_qseq || !dev_qoff || !dev_qlen || !dev_tseq || !dev_toff || !dev_tlen || !host_tlen || !host_w))) {
+        b200::set_error("global_device: bad argument"); return BWA_B200_ERR_ARG;
+    }
+    B200_CUDA(cudaSetDevice(c->device));
+    if (n_jobs) {
+        if (grow_dev(c->d_w, c->w_cap, n_jobs)) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
+        B200_CUDA(cudaMemcpyAsync(c->d_w, host_w, n_jobs * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    return cigar_run(c, p, n_jobs, dev_qseq, dev_qoff, dev_qlen, dev_tseq, dev_toff, dev_tlen, c->d_w, host_tlen, host_w);
+}
+
+extern "C" int bwa_b200_global_device_view(bwa_b200_cigar_t *c, bwa_b200_cigars_t *v)
+{
+    if (!c || !v) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(c->device));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    v->n_jobs = c->last_n; v->n_ops = c->last_ops; v->score = c->d_score; v->nm = c->d_nm; v->n_cigar = c->d_ncig; v->cigar_off = c->d_off; v->cigar = c->d_flat;
+    return BWA_B200_OK;
+}
+
+extern "C" void bwa_b200_cigars_free(bwa_b200_cigars_t *r)
+{
+    if (!r) return;
+    free(r->score); free(r->nm); free(r->n_cigar); free(r->cigar_off); free(r->cigar);
+    memset(r, 0, sizeof(*r));
+}
+
+extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                    const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                                    const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                                    const uint32_t *w, bwa_b200_cigars_t *out)
+{
+    if (!c || !p || !out || (n_jobs && (!qseq || !qoff || !qlen || !tseq || !toff || !tlen || !w))) { b200::set_error("global_host: bad argument"); return BWA_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    out->n_jobs = n_jobs;
+    if (n_jobs == 0) return BWA_B200_OK;
+    for (uint64_t a = 0; a < n_jobs; ++a)
+        if ((uint64_t)qoff[a] + qlen[a] > q_bytes || (uint64_t)toff[a] + tlen[a] > t_bytes) { b200::set_error("global_host: job %llu reaches past its sequence buffer", (unsigned long long)a); return BWA_B200_ERR_ARG; }
+    B200_CUDA(cudaSetDevice(c->device));
+    int bad = 0;
+    bad |= grow_dev(c->d_q, c->q_cap, q_bytes ? q_bytes : 1); bad |= grow_dev(c->d_t, c->t_cap, t_bytes ? t_bytes : 1);
+    bad |= grow_dev(c->d_qoff, c->qoff_cap, n_jobs); bad |= grow_dev(c->d_qlen, c->qlen_cap, n_jobs);
+    bad |= grow_dev(c->d_toff, c->toff_cap, n_jobs); bad |= grow_dev(c->d_tlen, c->tlen_cap, n_jobs); bad |= grow_dev(c->d_w, c->w_cap, n_jobs);
+    if (bad) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
+    cudaStream_t st = c->stream;
+    if (q_bytes) B200_CUDA(cudaMemcpyAsync(c->d_q, qseq, q_bytes, cudaMemcpyHostToDevice, st));
+    if (t_bytes) B200_CUDA(cudaMemcpyAsync(c->d_t, tseq, t_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(c->d_qoff, qoff, n_jobs * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(c->d_qlen, qlen, n_jobs * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(c->d_toff, toff, n_jobs * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(c->d_tlen, tlen, n_jobs * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(c->d_w, w, n_jobs * 4, cudaMemcpyHostToDevice, st));
+    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, tlen, w);
+    if (rc) return rc;
+    const uint64_t ops = c->last_ops;
+    out->n_ops = ops;
+    out->score = (int32_t *)malloc(n_jobs * 4); out->nm = (int32_t *)malloc(n_jobs * 4); out->n_cigar = (uint32_t *)malloc(n_jobs * 4);
+    out->cigar_off = (uint64_t *)malloc(n_jobs * 8); out->cigar = (uint32_t *)malloc((ops ? ops : 1) * 4);
+    if (!out->score || !out->nm || !out->n_cigar || !out->cigar_off || !out->cigar) { bwa_b200_cigars_free(out); b200::set_error("global_host: out of host memory"); return BWA_B200_ERR_NOMEM; }
+    B200_CUDA(cudaMemcpyAsync(out->score, c->d_score, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(out->nm, c->d_nm, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(out->n_cigar, c->d_ncig, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(out->cigar_off, c->d_off, n_jobs * 8, cudaMemcpyDeviceToHost, st));
+    if (ops) B200_CUDA(cudaMemcpyAsync(out->cigar, c->d_flat, ops * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return BWA_B200_OK;
+}
+
+extern "C" void *bwa_b200_cigar_stream(bwa_b200_cigar_t *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t bwa_b200_cigar_launches(const bwa_b200_cigar_t *c) { return c ? c->launches : 0; }
+extern "C" uint64_t bwa_b200_cigar_last_cells(const bwa_b200_cigar_t *c) { return c ? c->last_cells : 0; }
+extern "C" int bwa_b200_cigar_profile(bwa_b200_cigar_t *c, int enable) { if (!c) return BWA_B200_ERR_ARG; c->profiling = enable != 0; return BWA_B200_OK; }
+extern "C" int bwa_b200_cigar_kernel_times(bwa_b200_cigar_t *c, const char **names, float *ms, int cap)
+{
+    if (!c) return BWA_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    int n = 0;
+    for (size_t i = 0; i < c->prof.used && n < cap; ++i, ++n) {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->prof.recs[i].a, c->prof.recs[i].b);
+        names[n] = c->prof.recs[i].name; ms[n] = t;
+    }
+    return n;
+}

@@ -262,6 +262,48 @@ int  bwa_b200_pipeline_totals(bwa_b200_pipeline_t *p, uint64_t out[3]);
 int  bwa_b200_pipeline_profile(bwa_b200_pipeline_t *p, int enable);
 int  bwa_b200_pipeline_kernel_times(bwa_b200_pipeline_t *p, const char **names, float *ms, int cap);
 
+/* ------------------------------------------- global alignment with backtrack: CIGAR, score, NM */
+/* The dynamic programming of the reference's output stage: mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2
+ * (src/bwamem.c:2344-2438, src/bwa.c:111-216, src/ksw.c:1120-1241).  A job is (query, target, band w): both ends fixed, the
+ * arguments of ksw_global2; mat / o_del / e_del / o_ins / e_ins are the fields of the same name in the extension parameter block; its other fields are ignored.
+ * Per job: the score ksw_global2 returns, the CIGAR (len << 4 | op, op 0 M / 1 I / 2 D, BAM encoding as in the reference) and
+ * the NM of bwa_gen_cigar2 (mismatches + inserted + deleted bases, a deletion at either end of the CIGAR not counted,
+ * src/bwa.c:178-205).  The caller fetches the reference window and reverses both sequences for a reverse-strand hit, as
+ * bwa_gen_cigar2 does (src/bwa.c:139-150), and takes the band from bwa_b200_cigar_band.  The MD string is text formatting and
+ * stays with the caller.  Bands wider than 127 are refused (BWA_B200_ERR_ARG). */
+typedef struct bwa_b200_cigar bwa_b200_cigar_t;
+typedef struct {
+    uint64_t  n_jobs, n_ops;
+    int32_t  *score, *nm;
+    uint32_t *n_cigar;
+    uint64_t *cigar_off;       /* exclusive prefix sum of n_cigar */
+    uint32_t *cigar;           /* n_ops operations, job after job */
+} bwa_b200_cigars_t;
+int  bwa_b200_cigar_create(int device, bwa_b200_cigar_t **out);
+void bwa_b200_cigar_destroy(bwa_b200_cigar_t *c);
+/* the band bwa_gen_cigar2 passes to ksw_global2 for a query of l_query bases against rlen reference bases when it was
+ * called with band w_ (src/bwa.c:161-169) */
+int  bwa_b200_cigar_band(const bwa_b200_ext_params_t *p, int w_, int l_query, int64_t rlen);
+/* host in (byte per base, codes 0..4, as bwa_b200_extend_async), host out: arrays of `out` are malloc'ed, release them with
+ * bwa_b200_cigars_free */
+int  bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                          const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                          const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                          const uint32_t *w, bwa_b200_cigars_t *out);
+void bwa_b200_cigars_free(bwa_b200_cigars_t *r);
+/* sequences and job tables already in HBM; host copies of tlen and w drive the band-width binning.  Results stay on the
+ * device until the next call: bwa_b200_global_device_view synchronises and reports the device pointers. */
+int  bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                            const uint8_t *dev_qseq, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
+                            const uint8_t *dev_tseq, const uint32_t *dev_toff, const uint32_t *dev_tlen,
+                            const uint32_t *host_tlen, const uint32_t *host_w);
+int  bwa_b200_global_device_view(bwa_b200_cigar_t *c, bwa_b200_cigars_t *dev_view);
+void *bwa_b200_cigar_stream(bwa_b200_cigar_t *c);
+uint64_t bwa_b200_cigar_launches(const bwa_b200_cigar_t *c);
+uint64_t bwa_b200_cigar_last_cells(const bwa_b200_cigar_t *c);     /* DP cells of the last batch (sum of end - beg over rows) */
+int  bwa_b200_cigar_profile(bwa_b200_cigar_t *c, int enable);
+int  bwa_b200_cigar_kernel_times(bwa_b200_cigar_t *c, const char **names, float *ms, int cap);
+
 /* ------------------------------------- seeds -> chains -> extension jobs -> alignment regions */
 /* The step between the two hot paths in the reference worker (src/bwamem.c:2055-2093 and :2286-2306), on the
  * device, so that a read batch goes seeds -> chains -> jobs -> extension -> regions without leaving HBM

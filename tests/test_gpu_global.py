@@ -1,0 +1,126 @@
+"""GPU parity tests of the CIGAR path (ksw_global2 with backtrack + NM): the CUDA kernel through the C ABI
+against the oracle and against golden vectors from the reference's own ksw_global2 / bwa_gen_cigar2.  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    assert pkg.lib().bwa_b200_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return pkg
+
+
+def rows_of(res, stride):
+    """flat CIGAR + offsets -> [n, stride] left-aligned rows (the oracle's layout)"""
+    n = res["n_cigar"].size
+    rows = np.zeros((n, stride), np.uint32)
+    for a in range(n):
+        m = int(res["n_cigar"][a]); o = int(res["cigar_off"][a])
+        rows[a, :m] = res["cigar"][o:o + m]
+    return rows
+
+
+def compare(gpu, oracle, cg, jobs, pkw=None, stride=256):
+    pkw = pkw or {}
+    got = cg.global_host(jobs, gpu.ext_params(**pkw))
+    want = oracle.global_batch(jobs, oracle.make_params(**pkw), cig_stride=stride, n_threads=4)
+    assert (want["n_cigar"] <= stride).all()
+    assert (got["score"] == want["score"]).all()
+    assert (got["n_cigar"] == want["n_cigar"]).all()
+    assert (got["nm"] == want["nm"]).all()
+    assert (rows_of(got, stride) == want["cigar"]).all()
+    assert cg.last_cells == want["cells"]
+    off = np.zeros(got["n_cigar"].size, np.uint64)
+    off[1:] = np.cumsum(got["n_cigar"].astype(np.uint64))[:-1]
+    assert (got["cigar_off"] == off).all() and got["cigar"].size == int(got["n_cigar"].sum())
+    return got
+
+
+def test_global_matches_oracle(gpu, oracle):
+    cg = gpu.Cigar(0)
+    compare(gpu, oracle, cg, synth.make_global_jobs(20000, qlen_range=(1, 150), seed=501))
+    compare(gpu, oracle, cg, synth.make_global_jobs(5000, qlen_range=(80, 300), seed=502, sub_rate=0.08, indel_rate=0.03, w_extra=(0, 40)))
+    # every band class up to 127, other scoring
+    compare(gpu, oracle, cg, synth.make_global_jobs(3000, qlen_range=(100, 400), seed=503, sub_rate=0.1, indel_rate=0.04, w_extra=(0, 120), w_cap=127),
+            dict(a=2, b=3, o_del=4, e_del=2, o_ins=5, e_ins=1))
+    # tight bands, many operations per CIGAR (the widen-the-rows path: more than 16 operations)
+    got = compare(gpu, oracle, cg, synth.make_global_jobs(3000, qlen_range=(20, 200), seed=504, sub_rate=0.2, indel_rate=0.08, w_extra=(0, 2)))
+    assert got["n_cigar"].max() > 16
+    assert cg.launches > 0
+    cg.destroy()
+
+
+def test_global_edge_cases(gpu, oracle):
+    """one-base sequences, band narrower than the length difference (the last row misses column qlen: score MINUS_INF), all-N"""
+    cg = gpu.Cigar(0)
+    q = [np.array([2], np.uint8), np.array([0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3], np.uint8), np.full(20, 4, np.uint8), np.array([1, 1, 1, 1, 1, 1, 1, 1, 1, 1], np.uint8),
+         np.array([0, 1, 2, 3, 0, 1, 2, 3], np.uint8)]
+    t = [np.array([2], np.uint8), np.array([0, 1, 2], np.uint8), np.full(18, 4, np.uint8), np.array([1], np.uint8), np.array([0, 1, 2, 3, 0, 1, 2, 3, 3, 3], np.uint8)]
+    # (a target longer than qlen + w would make the reference's backtrack read cells it never wrote: not a defined case)
+    w = np.array([3, 2, 5, 1, 2], np.uint32)
+    qoff = np.zeros(len(q), np.uint32); toff = np.zeros(len(q), np.uint32)
+    qs, ts = [], []
+    for a in range(len(q)):
+        qoff[a] = sum(x.size for x in qs); toff[a] = sum(x.size for x in ts)
+        qs.append(np.concatenate([q[a], np.full(-q[a].size % 8, 4, np.uint8)])); ts.append(np.concatenate([t[a], np.full(-t[a].size % 8, 4, np.uint8)]))
+    jobs = dict(qseq=np.concatenate(qs), tseq=np.concatenate(ts), qoff=qoff, toff=toff, qlen=np.array([x.size for x in q], np.uint32),
+                tlen=np.array([x.size for x in t], np.uint32), w=w)
+    got = compare(gpu, oracle, cg, jobs)
+    assert got["score"][1] == -0x40000000 and got["score"][0] == 1
+    # empty batch; band beyond the supported maximum is refused loudly
+    e = cg.global_host(dict(qseq=np.zeros(0, np.uint8), tseq=np.zeros(0, np.uint8), qoff=np.zeros(0, np.uint32), toff=np.zeros(0, np.uint32),
+                            qlen=np.zeros(0, np.uint32), tlen=np.zeros(0, np.uint32), w=np.zeros(0, np.uint32)), gpu.ext_params())
+    assert e["score"].size == 0 and e["cigar"].size == 0
+    jobs["w"] = np.array([3, 2, 5, 1, 200], np.uint32)
+    with pytest.raises(RuntimeError):
+        cg.global_host(jobs, gpu.ext_params())
+    cg.destroy()
+
+
+def test_global_golden_from_reference(gpu, oracle):
+    gold = np.load(os.path.join(GOLD, "global_golden.npz"))
+    cg = gpu.Cigar(0)
+    p = gpu.ext_params()
+    for si in range(3):
+        jobs = {k: gold[f"s{si}_{k}"] for k in ("qseq", "tseq", "qoff", "toff", "qlen", "tlen", "w")}
+        got = cg.global_host(jobs, p)
+        stride = gold[f"s{si}_cigar"].shape[1]
+        assert (got["score"] == gold[f"s{si}_score"]).all()
+        assert (got["n_cigar"] == gold[f"s{si}_n_cigar"]).all()
+        assert (rows_of(got, stride) == gold[f"s{si}_cigar"]).all()
+    # bwa_gen_cigar2: the caller's part (window fetch, strand reversal, band rule) done here as INTEGRATION.md shows, the DP,
+    # backtrack and NM on the device
+    g = synth.make_genome(int(gold["gc_genome_len"]), seed=int(gold["gc_genome_seed"]))
+    L = g.size
+    qoff_g = gold["gc_qoff"]
+    qs, ts, ws, keep = [], [], [], []
+    for i in range(gold["gc_rb"].size):
+        q = gold["gc_query"][qoff_g[i]:qoff_g[i + 1]].copy()
+        rb, re, w_ = int(gold["gc_rb"][i]), int(gold["gc_re"][i]), int(gold["gc_w"][i])
+        if rb >= L:
+            r = (3 - g[2 * L - re:2 * L - rb])[::-1].copy()          # bns_get_seq on the reverse strand
+            q, r = q[::-1].copy(), r[::-1].copy()                  # then both reversed (src/bwa.c:145-150)
+        else:
+            r = g[rb:re].copy()
+        if q.size == r.size and w_ == 0:
+            continue                                               # the ungapped shortcut needs no DP (src/bwa.c:151-160)
+        keep.append(i); qs.append(q); ts.append(r); ws.append(gpu.Cigar.band(p, w_, q.size, r.size))
+    assert len(keep) > 300
+    qoff = np.zeros(len(qs), np.uint32); toff = np.zeros(len(qs), np.uint32)
+    qoff[1:] = np.cumsum([x.size for x in qs])[:-1]; toff[1:] = np.cumsum([x.size for x in ts])[:-1]
+    jobs = dict(qseq=np.concatenate(qs), tseq=np.concatenate(ts), qoff=qoff, toff=toff, qlen=np.array([x.size for x in qs], np.uint32),
+                tlen=np.array([x.size for x in ts], np.uint32), w=np.array(ws, np.uint32))
+    got = cg.global_host(jobs, p)
+    keep = np.array(keep)
+    assert (got["score"] == gold["gc_score"][keep]).all()
+    assert (got["nm"] == gold["gc_nm"][keep]).all()
+    assert (got["n_cigar"] == gold["gc_n_cigar"][keep]).all()
+    assert (rows_of(got, gold["gc_cigar"].shape[1]) == gold["gc_cigar"][keep]).all()
+    cg.destroy()
