@@ -237,6 +237,66 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
     return res
 
 
+def run_cigar(args, pkg, flush):
+    """CIGAR path: ksw_global2 with backtrack + NM over a batch of end-to-end jobs shaped like the output stage
+    of the C2 workload (150 bp queries, 3 % substitutions, 1 % short indels, band = |tlen - qlen| + 3 as bwa_gen_cigar2 gives).
+    Device-resident timing with CUDA events; the host-to-host call; the oracle on the host cores beside it."""
+    import torch
+    from oracle import oracle_py as O
+    n = 262_144
+    jobs = synth.make_global_jobs(n, qlen_range=(150, 150), seed=2027)
+    ep = pkg.ext_params()
+    cg = pkg.Cigar(torch.cuda.current_device())
+    dev = {k: torch.from_numpy(jobs[k].view(np.uint8 if k in ("qseq", "tseq") else np.int32)).cuda() for k in ("qseq", "tseq", "qoff", "toff", "qlen", "tlen")}
+    stream = torch.cuda.ExternalStream(cg.stream)
+
+    def step():
+        cg.global_device(ep, n, dev["qseq"].data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(), dev["tseq"].data_ptr(), dev["toff"].data_ptr(),
+                         dev["tlen"].data_ptr(), jobs["tlen"], jobs["w"])
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 10))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    l0 = cg.launches
+    for k in range(reps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / reps
+    launches = (cg.launches - l0) // reps
+    cells = cg.last_cells
+    cg.profile(True)
+    step()
+    kt = dict(cg.kernel_times())
+    cg.profile(False)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        got = cg.global_host(jobs, ep)
+    e2e_s = (time.perf_counter() - t0) / 3
+    kms = sum(v for k, v in kt.items() if k.startswith("global_kernel"))
+    res = {"jobs": n, "ms_per_batch": ms, "jobs_per_s": n / (ms / 1e3), "cells": int(cells), "GCUPS": cells / (kms / 1e3) / 1e9 if kms else None,
+           "kernel_ms": kt, "e2e_jobs_per_s": n / e2e_s, "gpu_launches": int(launches), "cigar_ops": int(got["cigar"].size),
+           "workload": "262144 jobs, 150 bp queries, 3% substitutions, 1% indels of 1-4 bases, band |tlen - qlen| + 3"}
+    if not args.no_cpu_baseline:
+        sample = 65_536
+        sj = {k: (v[:sample] if k not in ("qseq", "tseq") else v) for k, v in jobs.items()}
+        threads = O.default_threads()
+        O.global_batch(sj, O.make_params(), cig_stride=64, n_threads=threads)
+        t0 = time.perf_counter()
+        want = O.global_batch(sj, O.make_params(), cig_stride=64, n_threads=threads)
+        cdt = time.perf_counter() - t0
+        same = bool((got["score"][:sample] == want["score"]).all() and (got["nm"][:sample] == want["nm"]).all() and (got["n_cigar"][:sample] == want["n_cigar"]).all())
+        res["cpu_baseline"] = {"value": sample / cdt, "unit": "jobs/s", "cores": threads, "kind": "port", "sample": f"first {sample} jobs",
+                               "gpu_output_identical_on_sample": same}
+    cg.destroy()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -379,6 +439,7 @@ def main():
         if dref:
             dist.destroy_process_group()
         return
+    cigar = run_cigar(args, pkg, flush) if not args.no_chain else None
 
     # ---- roofline of the dominant kernel (CUDA-event time per launch, live, over the timed steps)
     pk, pk_src = peaks()
@@ -475,7 +536,7 @@ def main():
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
         "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
                         "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
-                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained, "chained_reseed": chained_rs},
+                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained, "chained_reseed": chained_rs, "cigar": cigar},
     }
     print(json.dumps(line), flush=True)
     if dref:

@@ -18,6 +18,13 @@
 //                      fallback (scores up to 2^15, queries up to 1024, any matrix).  The per-column
 //                      state lives in shared memory as one 32-bit word per column, [column][lane];
 //                      the query is staged next to it as 4-bit codes.
+//   ext_intra_kernel   one job per WARP, for everything the two kernels above do not take (queries longer than
+//                      1024 bases, scores that do not fit 16 bits): the 32 lanes compute 32 consecutive columns
+//                      of a row at once.  M and E of a row depend on the previous row only; F is the max-plus
+//                      prefix scan F(j+1) = max(F(j) - e_ins, max(M(j) - oe_ins, 0)), done with warp shuffles
+//                      (5 steps per 32 columns) and carried from chunk to chunk.  int32 throughout, {H, E} per
+//                      column in a per-warp slab in global memory (coalesced 256-byte rows), so there is no
+//                      length limit other than the slab size (BWA_B200_EXT_INTRA_MAX_Q, default 32768 bases).
 //   Jobs are sorted by (class, query length) on the device and launched per length bin, so lanes
 //   of a warp run similar trip counts and each bin gets exactly the shared memory its longest
 //   query needs.
@@ -76,7 +83,7 @@ __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *
     range[k] = lo;
     // anything between the last bin of a class and the next class, or with the bad bit, is not handled
     if (k == N_PBINS && lo < lower_bound_key(sorted_keys, n, CLS_BIT)) atomicExch(err_flag, 2);
-    if (k == N_PBINS + N_BINS + 1 && lo < n) atomicExch(err_flag, 2);
+    // keys at or beyond range[N_PBINS + N_BINS + 1] (longer than the last bin, or scores beyond 16 bits) run in ext_intra_kernel
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -246,6 +253,148 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     if ((tid & 31) == 0 && my_cells) atomicAdd(cells_total, my_cells);
 }
 
+// ext_intra_kernel: one job per warp (see the header).  Row-order semantics are those of ext_inter_kernel; the row itself is
+// evaluated 32 columns at a time.  All row-level state (beg, end, best, ...) is kept redundantly in every lane.
+constexpr int INTRA_WARPS = 4;
+template <bool BYTES>
+__global__ void __launch_bounds__(INTRA_WARPS * 32)
+ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ first, uint32_t n,
+                 int max_q, int2 *__restrict__ slab_all, bwa_b200_ext_result_t *__restrict__ res,
+                 unsigned long long *__restrict__ cells_total, int *__restrict__ err_flag)
+{
+    __shared__ int8_t smat[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 25) smat[tid] = P.mat[tid];
+    __syncthreads();
+    const uint32_t gw = blockIdx.x * INTRA_WARPS + (tid >> 5), n_warps = gridDim.x * INTRA_WARPS;
+    int2 *const eh = slab_all + (uint64_t)gw * (uint64_t)(max_q + 1);      // eh[j] = {H(i-1,j-1), E(i,j)}
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    unsigned long long my_cells = 0;
+    for (uint32_t pos = *first + gw; pos < n; pos += n_warps) {
+        const uint32_t a = order[pos];
+        const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
+        const uint32_t qo = J.qoff[a], to = J.toff[a];
+        if (qlen == 0) {
+            if (lane == 0) { bwa_b200_ext_result_t r0; r0.score = h0; r0.qle = 0; r0.tle = 0; r0.gtle = 0; r0.gscore = -1; r0.max_off = 0; res[a] = r0; }
+            continue;
+        }
+        if (qlen > max_q || h0 < 1) { if (lane == 0) atomicExch(err_flag, 1); continue; }
+        auto qcode = [&](int j) -> int {
+            int c;
+            if (BYTES) c = J.qb[qo + j];
+            else c = (int)((J.qp[(qo + j) >> 3] >> (28 - 4 * (j & 7))) & 15u);
+            return c > 4 ? 4 : c;
+        };
+        // first row (src/ksw.c:880-883): H(-1,-1) = h0, one gap open, then extensions, clipped at 0
+        for (int j = lane; j <= qlen; j += 32) {
+            long long v = j == 0 ? (long long)h0 : (long long)h0 - oe_ins - (long long)(j - 1) * P.e_ins;
+            eh[j] = make_int2(v > 0 ? (int)v : 0, 0);
+        }
+        __syncwarp();
+        int w = P.w;
+        {   // band clamp (src/ksw.c:885-893)
+            int max_ins = (int)((double)(qlen * P.max_score + P.end_bonus - P.o_ins) / P.e_ins + 1.);
+            max_ins = max_ins > 1 ? max_ins : 1;
+            w = w < max_ins ? w : max_ins;
+            int max_del = (int)((double)(qlen * P.max_score + P.end_bonus - P.o_del) / P.e_del + 1.);
+            max_del = max_del > 1 ? max_del : 1;
+            w = w < max_del ? w : max_del;
+        }
+        int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
+        int beg = 0, end = qlen;
+        for (int i = 0; i < tlen; ++i) {
+            int tbv;
+            if (BYTES) tbv = J.tb[to + i];
+            else tbv = (int)((J.tp[(to + i) >> 3] >> (28 - 4 * (i & 7))) & 15u);
+            tbv = tbv > 4 ? 4 : tbv;
+            const int8_t *srow = smat + tbv * 5;
+            if (P.use_band) {
+                if (beg < i - w) beg = i - w;
+                if (end > i + w + 1) end = i + w + 1;
+                if (end > qlen) end = qlen;
+            }
+            int hc = 0, fc = 0;                 // carries into the next chunk: H(i, j-1) and F(i, j) of its first column
+            if (beg == 0) { hc = h0 - (P.o_del + P.e_del * (i + 1)); hc = hc < 0 ? 0 : hc; }
+            unsigned long long key = 0;         // (row max << 32) + column, last column wins ties
+            for (int base = beg; base < end; base += 32) {
+                const int j = base + lane;
+                const bool in = j < end;
+                const int2 pe = in ? eh[j] : make_int2(0, 0);
+                const int M = in && pe.x ? pe.x + srow[qcode(j)] : 0;           // M = M ? M + s : 0   (src/ksw.c:924)
+                const int g = M - oe_ins > 0 ? M - oe_ins : 0;
+                int pm = g + lane * P.e_ins;                                    // prefix max of g(k) + k * e_ins
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, pm, o); if (lane >= o) pm = pm > up ? pm : up; }
+                const int pprev = __shfl_up_sync(0xffffffffu, pm, 1);
+                int f = fc - lane * P.e_ins;
+                if (lane > 0) { const int t = pprev - (lane - 1) * P.e_ins; f = f > t ? f : t; }
+                int h = M > pe.y ? M : pe.y;
+                h = h > f ? h : f;
+                int t1 = M - oe_del; t1 = t1 > 0 ? t1 : 0;
+                int e2 = pe.y - P.e_del; e2 = e2 > t1 ? e2 : t1;
+                const int hup = __shfl_up_sync(0xffffffffu, h, 1);
+                if (in) {
+                    eh[j] = make_int2(lane == 0 ? hc : hup, e2);
+                    const unsigned long long kj = ((unsigned long long)(uint32_t)h << 32) | (uint32_t)j;
+                    key = key > kj ? key : kj;
+                }
+                const int last = end - 1 - base < 31 ? end - 1 - base : 31;        // last column of this chunk
+                hc = __shfl_sync(0xffffffffu, h, last);
+                const int p31 = __shfl_sync(0xffffffffu, pm, 31);
+                const int c1 = p31 - 31 * P.e_ins, c2 = fc - 32 * P.e_ins;
+                fc = c1 > c2 ? c1 : c2;
+            }
+            if (lane == 0) eh[end] = make_int2(hc, 0);       // H(i, end-1); E = 0
+            __syncwarp();
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = key > ok ? key : ok; }
+            if (lane == 0) my_cells += (unsigned long long)(end > beg ? end - beg : 0);
+            const int m = (int)(key >> 32), mj = beg < end ? (int)(uint32_t)key : -1;
+            if (end == qlen && beg < end) {        // `j == qlen` after the column loop
+                best_ie = gscore > hc ? best_ie : i;
+                gscore = gscore > hc ? gscore : hc;
+            }
+            if (m == 0) break;
+            if (m > best) {
+                best = m; best_i = i; best_j = mj;
+                const int d = mj > i ? mj - i : i - mj;
+                max_off = max_off > d ? max_off : d;
+            } else if (P.zdrop > 0) {
+                const int di = i - best_i, dj = mj - best_j;
+                if (di > dj) { if (best - m - (di - dj) * P.e_del > P.zdrop) break; }
+                else         { if (best - m - (dj - di) * P.e_ins > P.zdrop) break; }
+            }
+            // shrink the window to the non-zero part of the row (src/ksw.c:965-970)
+            int nb = end;
+            for (int base = beg; base < end; base += 32) {
+                const int j = base + lane;
+                int2 v = make_int2(0, 0);
+                if (j < end) v = eh[j];
+                const uint32_t bal = __ballot_sync(0xffffffffu, (v.x | v.y) != 0);
+                if (bal) { nb = base + __ffs(bal) - 1; break; }
+            }
+            int jj = nb - 1;
+            for (int top = end; top >= nb; top -= 32) {
+                const int j = top - lane;
+                int2 v = make_int2(0, 0);
+                if (j >= nb) v = eh[j];
+                const uint32_t bal = __ballot_sync(0xffffffffu, (v.x | v.y) != 0);
+                if (bal) { jj = top - (__ffs(bal) - 1); break; }
+            }
+            beg = nb;
+            end = jj + 2 < qlen ? jj + 2 : qlen;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            bwa_b200_ext_result_t r;
+            r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = best_ie + 1; r.gscore = gscore; r.max_off = max_off;
+            res[a] = r;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && my_cells) atomicAdd(cells_total, my_cells);
+}
+
 // ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh)
 template <bool BYTES, bool KEYED>
 __global__ void __launch_bounds__(PAIR_NT)
@@ -374,6 +523,10 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 2) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
+    e->intra_max_q = getenv("BWA_B200_EXT_INTRA_MAX_Q") ? atoi(getenv("BWA_B200_EXT_INTRA_MAX_Q")) : 32768;
+    if (e->intra_max_q < 1024) e->intra_max_q = 1024;
+    e->intra_grid = e->n_sm;
+    B200_CUDA(cudaMalloc(&e->d_intra, (size_t)e->intra_grid * INTRA_WARPS * ((size_t)e->intra_max_q + 1) * sizeof(int2)));
     B200_CUDA(cudaMemset(e->d_cells, 0, 8));
     B200_CUDA(cudaMemset(e->d_err, 0, 4));
     B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
@@ -406,7 +559,7 @@ extern "C" void bwa_b200_extender_destroy(bwa_b200_extender_t *e)
     cudaStreamSynchronize(e->stream);
     cudaFree(e->d_q); cudaFree(e->d_t); cudaFree(e->d_qoff); cudaFree(e->d_qlen); cudaFree(e->d_toff); cudaFree(e->d_tlen);
     cudaFree(e->d_h0); cudaFree(e->d_keys); cudaFree(e->d_keys2); cudaFree(e->d_vals); cudaFree(e->d_order); cudaFree(e->d_range);
-    cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cells); cudaFree(e->d_err); cudaFree(e->d_cub);
+    cudaFree(e->d_res); cudaFree(e->d_tri); cudaFree(e->d_cells); cudaFree(e->d_err); cudaFree(e->d_cub); cudaFree(e->d_intra);
     cudaFreeHost(e->h_cells); cudaFreeHost(e->h_err);
     for (int k = 0; k < e->n_side; ++k) { cudaStreamSynchronize(e->side[k]); cudaStreamDestroy(e->side[k]); cudaEventDestroy(e->ev_join[k]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -508,6 +661,13 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
             (kern<<<grid, nt, smem, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
+    {   // one warp per job for what is left (queries beyond the last bin, scores beyond 16 bits); exits at once when there is none
+        cudaStream_t st = bin_stream();
+        B200_LAUNCH(e->prof, "ext_intra_kernel", st,
+            (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), n, e->intra_max_q,
+                                                                                e->d_intra, d_res, e->d_cells, e->d_err)));
+        e->launches += 1;
+    }
     if (fan)
         for (int k = 0; k < e->n_side; ++k) {
             B200_CUDA(cudaEventRecord(e->ev_join[k], e->side[k]));
@@ -600,7 +760,7 @@ extern "C" int bwa_b200_extend_wait(bwa_b200_extender_t *e)
     if (*e->h_err) {
         *e->h_err = 0;
         cudaMemsetAsync(e->d_err, 0, 4, e->stream);
-        b200::set_error("extend: a job had qlen > 1024, scores beyond 16 bits, or h0 < 1 (ksw_extend2 asserts h0 > 0, src/ksw.c:869)");
+        b200::set_error("extend: a job had h0 < 1 (ksw_extend2 asserts h0 > 0, src/ksw.c:869) or a query beyond BWA_B200_EXT_INTRA_MAX_Q bases");
         return BWA_B200_ERR_ARG;
     }
     return BWA_B200_OK;

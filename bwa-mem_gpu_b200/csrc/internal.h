@@ -104,6 +104,8 @@ struct bwa_b200_extender {
     b200::Prof *prof = nullptr;          // an event pair around every launch (bins then run one after another)
     b200::Prof *phase_prof = nullptr;    // one event pair around the whole launch set (bins overlap on the side streams)
     bool own_stream = true;
+    int2 *d_intra = nullptr;             // {H, E} column slabs of ext_intra_kernel, one per resident warp
+    int intra_grid = 0, intra_max_q = 0;
 };
 
 

@@ -271,6 +271,36 @@ def test_extension_device_packed_path(gpu, oracle):
     ex.destroy()
 
 
+def test_extension_long_queries_and_wide_scores_intra_kernel(gpu, oracle):
+    """jobs the per-lane kernels do not take -- queries beyond 1024 bases, scores beyond 16 bits -- run one per warp in
+    ext_intra_kernel (32 columns of a row at once, F by a warp max-plus scan); mixed with ordinary jobs in one batch"""
+    ex = gpu.Extender(0)
+    for kw in (dict(w=100, zdrop=100), dict(w=300, zdrop=0, use_band=0), dict(w=20, zdrop=50)):
+        longj = synth.make_ext_jobs(300, w=kw["w"], seed=91, qlen_range=(1000, 3000), h0_range=(1, 200), sub_rate=0.08, indel_rate=0.02)
+        want, cnt = oracle.ksw_batch(longj, oracle.make_params(**kw), n_threads=4)
+        res, _ = ex.extend_host(longj, gpu.ext_params(**kw))
+        assert (res == want).all()
+        assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == cnt["cells"]
+    # one very long query (and a target that diverges half way: z-drop / window shrink on a long row)
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 4, 20000, dtype=np.uint8)
+    t = q.copy(); t[12000:] = rng.integers(0, 4, 8000, dtype=np.uint8)
+    pad = lambda x: np.concatenate([x, np.full(-x.size % 8, 4, np.uint8)])
+    one = dict(qseq=pad(q), tseq=pad(t), qoff=np.zeros(1, np.uint32), toff=np.zeros(1, np.uint32), qlen=np.array([q.size], np.uint32),
+               tlen=np.array([t.size], np.uint32), h0=np.array([30], np.uint32))
+    for kw in (dict(w=100, zdrop=100), dict(w=100, zdrop=0)):
+        want, _ = oracle.ksw_batch(one, oracle.make_params(**kw), n_threads=1)
+        res, _ = ex.extend_host(one, gpu.ext_params(**kw))
+        assert (res == want).all() and res[0, 0] > 10000
+    # scores beyond 16 bits with ordinary lengths: a = 60, h0 large; mixed with short jobs of the per-lane kernels
+    mixed = synth.make_ext_jobs(2000, w=100, seed=92, qlen_range=(1, 1100), h0_range=(1, 150))
+    kw = dict(a=60, b=90, o_del=100, e_del=20, o_ins=120, e_ins=30, w=100, zdrop=2000)
+    want, _ = oracle.ksw_batch(mixed, oracle.make_params(**kw), n_threads=4)
+    res, _ = ex.extend_host(mixed, gpu.ext_params(**kw))
+    assert (res == want).all() and res[:, 0].max() > 40000
+    ex.destroy()
+
+
 def test_extension_rejects_bad_jobs(gpu):
     jobs = synth.make_ext_jobs(8, w=100, seed=1, qlen_range=(10, 20))
     jobs["h0"][3] = 0                                  # ksw_extend2 asserts h0 > 0
