@@ -38,15 +38,30 @@ struct GArgs {
 
 template <int R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t tlen_max, uint32_t *__restrict__ z_all)
+global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t tlen_max, uint32_t qw_max, uint32_t tw_max, uint32_t *__restrict__ z_all)
 {
-    extern __shared__ int2 eh_ring[];                   // [R][BLOCK]
-    __shared__ int8_t smat[32];
+    // dynamic shared memory: eh ring [R][BLOCK] of int2, then the staged sequences as 4-bit codes, 8 per word, first base in
+    // the high nibble: query [qw_max][BLOCK], target [tw_max][BLOCK]
+    extern __shared__ int2 eh_ring[];
+    __shared__ uint32_t smat_lo[5], smat_hi[5];            // biased score bytes of matrix row t: lo = query codes 0..3, hi = code 4
+    __shared__ int s_bias;
     int2 (*eh)[BLOCK] = reinterpret_cast<int2 (*)[BLOCK]>(eh_ring);
+    uint32_t *const qs = reinterpret_cast<uint32_t *>(eh_ring + (size_t)R * BLOCK) + threadIdx.x;       // qs[g * BLOCK]
+    uint32_t *const ts = qs + (size_t)qw_max * BLOCK;                                                   // ts[g * BLOCK]
     constexpr int WPR = R / 8;              // backtrack words per row
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    if (tid < 25) smat[tid] = a.mat[tid];
+    if (tid == 0) {
+        int mn = 0;
+        for (int i = 0; i < 25; ++i) mn = mn < a.mat[i] ? mn : a.mat[i];
+        s_bias = -mn;
+        for (int t = 0; t < 5; ++t) {
+            uint32_t lo = 0;
+            for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)(a.mat[t * 5 + q] - mn) << (8 * q);
+            smat_lo[t] = lo; smat_hi[t] = (uint32_t)(uint8_t)(a.mat[t * 5 + 4] - mn);
+        }
+    }
     __syncthreads();
+    const int bias = s_bias;
     const uint32_t gwarp = blockIdx.x * (BLOCK / 32) + (tid >> 5), n_warps = gridDim.x * (BLOCK / 32);
     uint32_t *const z = z_all + (uint64_t)gwarp * tlen_max * WPR * 32;
     const int oe_del = a.o_del + a.e_del, oe_ins = a.o_ins + a.e_ins;
@@ -58,33 +73,50 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
         const uint32_t job = valid ? perm[idx] : 0u;
         const int qlen = valid ? (int)a.qlen[job] : 0, tlen = valid ? (int)a.tlen[job] : 0, w = valid ? (int)a.w[job] : 0;
         const uint8_t *q = a.qseq + (valid ? a.qoff[job] : 0u), *t = a.tseq + (valid ? a.toff[job] : 0u);
+        // stage both sequences (codes above 4 are read as 4)
+        for (int j8 = 0; j8 < qlen; j8 += 8) {
+            uint32_t wv = 0;
+            for (int u = 0; u < 8; ++u) { const uint32_t c = j8 + u < qlen ? q[j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+            qs[(j8 >> 3) * BLOCK] = wv;
+        }
+        for (int i8 = 0; i8 < tlen; i8 += 8) {
+            uint32_t wv = 0;
+            for (int u = 0; u < 8; ++u) { const uint32_t c = i8 + u < tlen ? t[i8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+            ts[(i8 >> 3) * BLOCK] = wv;
+        }
         // first row (src/ksw.c:1141-1147); only columns 0 .. min(w + 1, qlen) can be read before they are rewritten
         eh[0][tid] = make_int2(0, MINF);
         {
             const int top = w + 1 < qlen ? w + 1 : qlen;
             for (int j = 1; j <= top; ++j) eh[j & (R - 1)][tid] = j <= w ? make_int2(-(a.o_ins + a.e_ins * j), MINF) : make_int2(MINF, MINF);
         }
-        int warp_tl = tlen;
+        int warp_tl = tlen, warp_w = w;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) warp_tl = max(warp_tl, __shfl_xor_sync(0xffffffffu, warp_tl, o));
+        for (int o = 16; o; o >>= 1) {
+            warp_tl = max(warp_tl, __shfl_xor_sync(0xffffffffu, warp_tl, o));
+            warp_w = max(warp_w, __shfl_xor_sync(0xffffffffu, warp_w, o));
+        }
+        const int warp_nc = 2 * warp_w + 1;          // no row of any lane has more columns
+        uint32_t tword = 0;
         for (int i = 0; i < warp_tl; ++i) {
             const bool act = i < tlen;
             const int beg = i > w ? i - w : 0;
             const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
             const int ncol = act && end > beg ? end - beg : 0;
-            int warp_nc = ncol;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) warp_nc = max(warp_nc, __shfl_xor_sync(0xffffffffu, warp_nc, o));
-            const int8_t *srow = smat + (act ? (int)t[i] : 0) * 5;
+            if ((i & 7) == 0 && act) tword = ts[(i >> 3) * BLOCK];
+            const int tb = act ? (int)((tword >> (28 - 4 * (i & 7))) & 15u) : 4;
+            const uint32_t mlo = smat_lo[tb], mhi = smat_hi[tb];
             int32_t f = MINF, h1 = beg == 0 ? -(a.o_del + a.e_del * (i + 1)) : MINF;
-            uint32_t zw = 0;
+            uint32_t zw = 0, qw = ncol ? qs[(beg >> 3) * BLOCK] : 0u;
             uint32_t *zrow = z + (uint64_t)i * WPR * 32 + lane;
             for (int c = 0; c < warp_nc; ++c) {
                 if (c < ncol) {
                     const int j = beg + c;
+                    if ((j & 7) == 0 && c) qw = qs[(j >> 3) * BLOCK];
+                    const uint32_t qc = (qw >> (28 - 4 * (j & 7))) & 15u;
                     int2 *p = &eh[j & (R - 1)][tid];
                     const int2 pe = *p;
-                    int32_t m = pe.x + srow[q[j]], e = pe.y, h, tt;
+                    int32_t m = pe.x + (int)(__byte_perm(mlo, mhi, qc) & 0xffu) - bias, e = pe.y, h, tt;
                     uint32_t d;
                     d = m >= e ? 0u : 1u;
                     h = m >= e ? m : e;
@@ -134,7 +166,10 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
             c = c < 0 ? 0 : (c > R - 1 ? R - 1 : c);        // never outside the row's words (the reference would read out of bounds)
             const uint32_t code = (z[((uint64_t)i * WPR + (c >> 3)) * 32 + lane] >> (4 * (c & 7))) & 15u;
             which = which == 0 ? (code & 3u) : (which == 1 ? ((code >> 2) & 1u) : ((code >> 3) & 1u) * 2u);
-            if (which == 0) { nmm += q[k] != t[i]; push(0, 1); --i; --k; }
+            if (which == 0) {
+                const uint32_t qc = (qs[(k >> 3) * BLOCK] >> (28 - 4 * (k & 7))) & 15u, tc = (ts[(i >> 3) * BLOCK] >> (28 - 4 * (i & 7))) & 15u;
+                nmm += qc != tc; push(0, 1); --i; --k;
+            }
             else if (which == 1) { push(2, 1); --i; }
             else { push(1, 1); --k; }
         }
@@ -204,20 +239,24 @@ struct bwa_b200_cigar {
     void *d_cub = nullptr; uint64_t cub_cap = 0;
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;   // [0] cells [1] widest row needed [2] total operations
     int grid[5] = {0, 0, 0, 0, 0};
-    std::vector<uint32_t> perm; uint32_t cls_n[5] = {}, cls_tl[5] = {};
+    cudaStream_t side[5] = {};              // band classes of one batch run concurrently (forked from / joined to `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
+    std::vector<uint32_t> perm; uint32_t cls_n[5] = {}, cls_tl[5] = {}, cls_ql[5] = {};
+    int smem_optin = 0;
+    uint64_t z_off[5] = {};
     uint64_t last_n = 0, last_ops = 0, last_cells = 0, launches = 0;
     b200::Prof prof; int profiling = 0;
 };
 
-template <int R, int BLOCK> static int class_grid(int n_sm, int *grid)
+// resident blocks of one class for the shared memory its longest sequences need: at most 24 warps per SM, so that the backtrack
+// slabs of the resident warps stay of the order of the L2 size
+template <int R, int BLOCK> static int class_grid(int n_sm, size_t smem, int *grid)
 {
     int occ = 0;
-    const size_t smem = (size_t)R * BLOCK * sizeof(int2);
     B200_CUDA(cudaFuncSetAttribute(global_kernel<R, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, global_kernel<R, BLOCK>, BLOCK, smem));
     if (occ < 1) occ = 1;
-    int warps = occ * (BLOCK / 32);
-    if (warps > 24) occ = std::max(1, 24 / (BLOCK / 32));      // bound the backtrack slabs (L2 residency)
+    if (occ * (BLOCK / 32) > 24) occ = std::max(1, 24 / (BLOCK / 32));
     *grid = n_sm * occ;
     return BWA_B200_OK;
 }
@@ -234,11 +273,12 @@ extern "C" int bwa_b200_cigar_create(int device, bwa_b200_cigar_t **out)
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     B200_CUDA(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
     B200_CUDA(cudaHostAlloc(&c->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
-    int rc = class_grid<16, 128>(c->n_sm, &c->grid[0]); if (rc) return rc;
-    rc = class_grid<32, 128>(c->n_sm, &c->grid[1]); if (rc) return rc;
-    rc = class_grid<64, 64>(c->n_sm, &c->grid[2]); if (rc) return rc;
-    rc = class_grid<128, 32>(c->n_sm, &c->grid[3]); if (rc) return rc;
-    rc = class_grid<256, 32>(c->n_sm, &c->grid[4]); if (rc) return rc;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < 5; ++k) {
+        B200_CUDA(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
     *out = c;
     return BWA_B200_OK;
 }
@@ -252,6 +292,8 @@ extern "C" void bwa_b200_cigar_destroy(bwa_b200_cigar_t *c)
     cudaFree(c->d_w); cudaFree(c->d_perm); cudaFree(c->d_ncig); cudaFree(c->d_score); cudaFree(c->d_nm); cudaFree(c->d_off);
     cudaFree(c->d_rows); cudaFree(c->d_flat); cudaFree(c->d_z); cudaFree(c->d_cub); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
+    for (int k = 0; k < 5; ++k) { if (c->side[k]) cudaStreamDestroy(c->side[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -270,44 +312,64 @@ extern "C" int bwa_b200_cigar_band(const bwa_b200_ext_params_t *p, int w_, int l
     return w > min_w ? w : min_w;
 }
 
+template <int R, int BLOCK> static size_t class_smem(const bwa_b200_cigar *c, int cls)
+{
+    return (size_t)R * BLOCK * sizeof(int2) + ((size_t)(c->cls_ql[cls] + 7) / 8 + (size_t)(c->cls_tl[cls] + 7) / 8) * BLOCK * 4;
+}
 template <int R, int BLOCK>
 static void launch_class(bwa_b200_cigar *c, const GArgs &ga, int cls, uint32_t first, const char *name)
 {
     b200::Prof *prof = c->profiling ? &c->prof : nullptr;
-    B200_LAUNCH(prof, name, c->stream,
-        (global_kernel<R, BLOCK><<<c->grid[cls], BLOCK, (size_t)R * BLOCK * sizeof(int2), c->stream>>>(ga, c->d_perm + first, c->cls_n[cls], c->cls_tl[cls], c->d_z)));
+    cudaStream_t st = prof ? c->stream : c->side[cls];      // profiled: one after another on the main stream
+    B200_LAUNCH(prof, name, st,
+        (global_kernel<R, BLOCK><<<c->grid[cls], BLOCK, class_smem<R, BLOCK>(c, cls), st>>>(ga, c->d_perm + first, c->cls_n[cls], c->cls_tl[cls],
+                                                                                                 (c->cls_ql[cls] + 7) / 8, (c->cls_tl[cls] + 7) / 8, c->d_z + c->z_off[cls])));
     ++c->launches;
 }
 
 // jobs already on the device (byte per base); host copies of tlen and w drive the binning
 static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs, const uint8_t *d_q, const uint32_t *d_qoff,
                      const uint32_t *d_qlen, const uint8_t *d_t, const uint32_t *d_toff, const uint32_t *d_tlen, const uint32_t *d_w,
-                     const uint32_t *h_tlen, const uint32_t *h_w)
+                     const uint32_t *h_qlen, const uint32_t *h_tlen, const uint32_t *h_w)
 {
     c->last_n = n_jobs; c->last_ops = 0; c->last_cells = 0;
     if (n_jobs == 0) return BWA_B200_OK;
     if (n_jobs > 0xfffffff0ull) { b200::set_error("global: at most 2^32-16 jobs per batch"); return BWA_B200_ERR_ARG; }
     const uint32_t n = (uint32_t)n_jobs;
     // bin the jobs by band-width class
-    uint32_t cnt[5] = {0, 0, 0, 0, 0}, tl[5] = {0, 0, 0, 0, 0};
+    uint32_t cnt[5] = {0, 0, 0, 0, 0}, tl[5] = {0, 0, 0, 0, 0}, ql[5] = {0, 0, 0, 0, 0};
     for (uint32_t a = 0; a < n; ++a) {
         const uint32_t w = h_w[a];
         int k = 0;
         while (k < 5 && w > CLASSES[k].wmax) ++k;
         if (k == 5) { b200::set_error("global: band %u of job %u is wider than 127", w, a); return BWA_B200_ERR_ARG; }
-        ++cnt[k]; tl[k] = std::max(tl[k], h_tlen[a]);
+        ++cnt[k]; tl[k] = std::max(tl[k], h_tlen[a]); ql[k] = std::max(ql[k], h_qlen[a]);
     }
     uint32_t first[6] = {0, 0, 0, 0, 0, 0}, cur[5];
-    for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; cur[k] = first[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; }
+    for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; cur[k] = first[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; c->cls_ql[k] = ql[k] ? ql[k] : 1; }
+    {   // shared memory of a class = ring + its longest query and target; the grid follows from the occupancy at that size
+        const size_t sm[5] = {class_smem<16, 128>(c, 0), class_smem<32, 128>(c, 1), class_smem<64, 64>(c, 2), class_smem<128, 32>(c, 3), class_smem<256, 32>(c, 4)};
+        for (int k = 0; k < 5; ++k)
+            if (cnt[k] && sm[k] > (size_t)c->smem_optin) { b200::set_error("global: sequences of %u / %u bases in band class %d do not fit shared memory", ql[k], tl[k], k); return BWA_B200_ERR_CAPACITY; }
+        int rc = 0;
+        if (cnt[0]) rc |= class_grid<16, 128>(c->n_sm, sm[0], &c->grid[0]);
+        if (cnt[1]) rc |= class_grid<32, 128>(c->n_sm, sm[1], &c->grid[1]);
+        if (cnt[2]) rc |= class_grid<64, 64>(c->n_sm, sm[2], &c->grid[2]);
+        if (cnt[3]) rc |= class_grid<128, 32>(c->n_sm, sm[3], &c->grid[3]);
+        if (cnt[4]) rc |= class_grid<256, 32>(c->n_sm, sm[4], &c->grid[4]);
+        if (rc) return BWA_B200_ERR_CUDA;
+    }
     c->perm.resize(n);
     for (uint32_t a = 0; a < n; ++a) {
         int k = 0;
         while (h_w[a] > CLASSES[k].wmax) ++k;
         c->perm[cur[k]++] = a;
     }
-    uint64_t z_need = 1;
-    for (int k = 0; k < 5; ++k)
-        if (cnt[k]) z_need = std::max<uint64_t>(z_need, (uint64_t)c->grid[k] * (CLASSES[k].block / 32) * c->cls_tl[k] * (CLASSES[k].R / 8) * 32);
+    uint64_t z_need = 1;                    // the classes run concurrently: each has its own region of backtrack slabs
+    for (int k = 0; k < 5; ++k) {
+        c->z_off[k] = z_need;
+        if (cnt[k]) z_need += (uint64_t)c->grid[k] * (CLASSES[k].block / 32) * c->cls_tl[k] * (CLASSES[k].R / 8) * 32;
+    }
     int bad = 0;
     bad |= grow_dev(c->d_perm, c->perm_cap, n); bad |= grow_dev(c->d_ncig, c->ncig_cap, n); bad |= grow_dev(c->d_score, c->score_cap, n);
     bad |= grow_dev(c->d_nm, c->nm_cap, n); bad |= grow_dev(c->d_off, c->off_cap, n); bad |= grow_dev(c->d_z, c->z_cap, z_need);
@@ -330,11 +392,18 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
         ga.o_del = p->o_del; ga.e_del = p->e_del; ga.o_ins = p->o_ins; ga.e_ins = p->e_ins;
         ga.score = c->d_score; ga.nm = c->d_nm; ga.n_cigar = c->d_ncig; ga.rows = c->d_rows; ga.cig_stride = c->cig_stride;
         ga.counters = c->d_counters;
+        const bool fan = !c->profiling;
+        if (fan) {
+            B200_CUDA(cudaEventRecord(c->ev_fork, st));
+            for (int k = 0; k < 5; ++k) if (cnt[k]) B200_CUDA(cudaStreamWaitEvent(c->side[k], c->ev_fork, 0));
+        }
         if (cnt[0]) launch_class<16, 128>(c, ga, 0, first[0], "global_kernel_w7");
         if (cnt[1]) launch_class<32, 128>(c, ga, 1, first[1], "global_kernel_w15");
         if (cnt[2]) launch_class<64, 64>(c, ga, 2, first[2], "global_kernel_w31");
         if (cnt[3]) launch_class<128, 32>(c, ga, 3, first[3], "global_kernel_w63");
         if (cnt[4]) launch_class<256, 32>(c, ga, 4, first[4], "global_kernel_w127");
+        if (fan)
+            for (int k = 0; k < 5; ++k) if (cnt[k]) { B200_CUDA(cudaEventRecord(c->ev_join[k], c->side[k])); B200_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0)); }
         B200_CUDA(cudaGetLastError());
         size_t tmp = c->cub_cap;
         B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub, tmp, it, c->d_off, (int)n, st));
@@ -361,9 +430,9 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
 extern "C" int bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
                                       const uint8_t *dev_qseq, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
                                       const uint8_t *dev_tseq, const uint32_t *dev_toff, const uint32_t *dev_tlen,
-                                      const uint32_t *host_tlen, const uint32_t *host_w)
+                                      const uint32_t *host_qlen, const uint32_t *host_tlen, const uint32_t *host_w)
 {
-    if (!c || !p || (n_jobs && (!dev_qseq || !dev_qoff || !dev_qlen || !dev_tseq || !dev_toff || !dev_tlen || !host_tlen || !host_w))) {
+    if (!c || !p || (n_jobs && (!dev_qseq || !dev_qoff || !dev_qlen || !dev_tseq || !dev_toff || !dev_tlen || !host_qlen || !host_tlen || !host_w))) {
         b200::set_error("global_device: bad argument"); return BWA_B200_ERR_ARG;
     }
     B200_CUDA(cudaSetDevice(c->device));
@@ -371,7 +440,7 @@ extern "C" int bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_pa
         if (grow_dev(c->d_w, c->w_cap, n_jobs)) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
         B200_CUDA(cudaMemcpyAsync(c->d_w, host_w, n_jobs * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    return cigar_run(c, p, n_jobs, dev_qseq, dev_qoff, dev_qlen, dev_tseq, dev_toff, dev_tlen, c->d_w, host_tlen, host_w);
+    return cigar_run(c, p, n_jobs, dev_qseq, dev_qoff, dev_qlen, dev_tseq, dev_toff, dev_tlen, c->d_w, host_qlen, host_tlen, host_w);
 }
 
 extern "C" int bwa_b200_global_device_view(bwa_b200_cigar_t *c, bwa_b200_cigars_t *v)
@@ -415,7 +484,7 @@ extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_para
     B200_CUDA(cudaMemcpyAsync(c->d_toff, toff, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_tlen, tlen, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_w, w, n_jobs * 4, cudaMemcpyHostToDevice, st));
-    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, tlen, w);
+    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, qlen, tlen, w);
     if (rc) return rc;
     const uint64_t ops = c->last_ops;
     out->n_ops = ops;
