@@ -140,6 +140,9 @@ struct bwa_b200_pipeline {
     const uint32_t *b_packed = nullptr; const uint64_t *b_woff = nullptr; const uint32_t *b_len = nullptr;
     uint64_t b_n = 0; uint32_t b_maxlen = 0;
     bwa_b200_seed_params_t b_sp{19, 500}; bwa_b200_ext_params_t b_ep{}; bwa_b200_read_result_t *b_out = nullptr;
+    // host-buffer path: copy streams so that the H2D of the next slice and the D2H of the previous one overlap the kernels
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[16] = {};
 };
 
 extern "C" int bwa_b200_index_attach_ref(bwa_b200_index_t *idx, const uint8_t *fwd, uint64_t l_pac)
@@ -221,6 +224,9 @@ extern "C" void bwa_b200_pipeline_destroy(bwa_b200_pipeline_t *p)
     cudaFree(p->d_jq_len); cudaFree(p->d_jt_len); cudaFree(p->d_j_h0); cudaFree(p->d_jq_off); cudaFree(p->d_jt_off); cudaFree(p->d_aux);
     cudaFree(p->d_qp); cudaFree(p->d_tp); cudaFree(p->d_res); cudaFree(p->d_out); cudaFree(p->d_live);
     cudaFreeHost(p->h_tot);
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+    for (int k = 0; k < 16; ++k) if (p->ev_in[k]) cudaEventDestroy(p->ev_in[k]);
     delete p;
 }
 
@@ -299,16 +305,41 @@ extern "C" int bwa_b200_seed_extend_host(bwa_b200_pipeline_t *p, const uint32_t 
     B200_CUDA(cudaSetDevice(p->device));
     uint32_t max_len = 0;
     for (uint64_t r = 0; r < n_reads; ++r) max_len = read_len[r] > max_len ? read_len[r] : max_len;
-    cudaStream_t st = p->stream;
-    B200_CUDA(cudaMemcpyAsync(s->d_packed, packed, word_off[n_reads] * 4, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(s->d_woff, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(s->d_len, read_len, n_reads * 4, cudaMemcpyHostToDevice, st));
-    int rc = bwa_b200_seed_extend_device(p, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, sp, ep, p->d_out);
-    if (rc) return rc;
-    rc = bwa_b200_pipeline_sync(p);
-    if (rc) return rc;
-    B200_CUDA(cudaMemcpyAsync(host_out, p->d_out, n_reads * sizeof(bwa_b200_read_result_t), cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    // The batch is cut into slices of whole reads: every H2D copy is queued up front on a copy stream, the kernels of slice k
+    // wait for its copy only, and its results go back on a third stream while slice k + 1 computes.  Offsets stay absolute
+    // (one packed buffer, one output array), so a slice is just a sub-range of the batch.
+    // Measured on B200 / C2 (tools/gpu_slices.sh): 1 slice 76.9, 2 slices 77.5, 4 slices 65.4, 8 slices 46.9 M reads/s -- at
+    // PCIe 5 rates the copies are 2.9 ms of a 13 ms call and the fixed cost of a slice (about 30 launches, the host round
+    // trip for the seed total, the tails of the extension bins) eats the overlap, so the default is one slice.
+    int n_slices = getenv("BWA_B200_HOST_SLICES") ? atoi(getenv("BWA_B200_HOST_SLICES")) : 1;
+    if (n_slices > 16) n_slices = 16;
+    if (n_slices < 1 || n_reads < (uint64_t)n_slices * 32768) n_slices = 1;
+    if (!p->s_h2d) {
+        B200_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+        for (int k = 0; k < 16; ++k) B200_CUDA(cudaEventCreateWithFlags(&p->ev_in[k], cudaEventDisableTiming));
+    }
+    const uint64_t per = (n_reads + n_slices - 1) / n_slices;
+    for (int k = 0; k < n_slices; ++k) {
+        const uint64_t r0 = std::min<uint64_t>(n_reads, k * per), r1 = std::min<uint64_t>(n_reads, r0 + per);
+        if (r1 > r0) {
+            B200_CUDA(cudaMemcpyAsync(s->d_packed + word_off[r0], packed + word_off[r0], (word_off[r1] - word_off[r0]) * 4, cudaMemcpyHostToDevice, p->s_h2d));
+            B200_CUDA(cudaMemcpyAsync(s->d_woff + r0, word_off + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, p->s_h2d));
+            B200_CUDA(cudaMemcpyAsync(s->d_len + r0, read_len + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, p->s_h2d));
+        }
+        B200_CUDA(cudaEventRecord(p->ev_in[k], p->s_h2d));
+    }
+    for (int k = 0; k < n_slices; ++k) {
+        const uint64_t r0 = std::min<uint64_t>(n_reads, k * per), r1 = std::min<uint64_t>(n_reads, r0 + per);
+        if (r1 == r0) continue;
+        B200_CUDA(cudaStreamWaitEvent(p->stream, p->ev_in[k], 0));
+        int rc = bwa_b200_seed_extend_device(p, s->d_packed, s->d_woff + r0, s->d_len + r0, r1 - r0, max_len, sp, ep, p->d_out + r0);
+        if (rc) return rc;
+        rc = bwa_b200_pipeline_sync(p);          // slice k is complete (and its seed arrays were large enough, or it was re-run)
+        if (rc) return rc;
+        B200_CUDA(cudaMemcpyAsync(host_out + r0, p->d_out + r0, (r1 - r0) * sizeof(bwa_b200_read_result_t), cudaMemcpyDeviceToHost, p->s_d2h));
+    }
+    B200_CUDA(cudaStreamSynchronize(p->s_d2h));
     return BWA_B200_OK;
 }
 

@@ -342,3 +342,26 @@ def test_pipeline_matches_oracle(gpu, oracle, dev_index, kw):
     got2 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params(**kw))
     assert got2.tobytes() == got.tobytes()
     pl.destroy()
+
+
+def test_pipeline_host_call_in_slices(gpu, oracle, dev_index, monkeypatch):
+    """the host-buffer call cuts a large batch into slices whose copies overlap the kernels: same records as one pass, ragged
+    read lengths so that slice boundaries fall at arbitrary word offsets"""
+    g, idx, oi = dev_index
+    idx.attach_ref(g)
+    n = 3 * 32768 + 1234
+    base, _, _ = synth.make_reads(g, n, 150, seed=77, sub_rate=0.02, n_rate=0.001)
+    rng = np.random.default_rng(7)
+    lens = rng.choice([150, 150, 149, 101, 75, 36], size=n)
+    reads = [base[i, :lens[i]] for i in range(n)]
+    f, off = flat(reads)
+    want, _, _ = oracle.pipeline(oi, g, f, off, oracle.make_params(), 19, 500, n_threads=4)
+    packed, woff, rl = gpu.pack_codes(f, off)
+    pl = gpu.Pipeline(idx, n, packed.size, 150)
+    monkeypatch.setenv("BWA_B200_HOST_SLICES", "3")
+    got = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params())
+    assert got.tobytes() == want.tobytes()
+    monkeypatch.setenv("BWA_B200_HOST_SLICES", "1")
+    got1 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params())
+    assert got1.tobytes() == want.tobytes()
+    pl.destroy()
