@@ -145,6 +145,9 @@ def fork_lib():
         L.fork_mem_read.restype = C.c_int
         L.fork_mem_seq.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         L.fork_mem_seq.restype = C.POINTER(C.c_uint8)
+        L.fork_reg2aln.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                   C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]
+        L.fork_reg2aln.restype = C.c_int
         _fork = L
     return _fork
 
@@ -233,3 +236,37 @@ def oracle_align_batch(opt, ctg: Contigs, fwd, reads, rbeg, qq, score, n_seeds, 
         i_s += ns_; i_l += nl_
     out["aln"] = np.concatenate(alns) if alns else np.zeros(0, ALN_DT)
     return out
+
+
+# ------------------------------------------------------------------ mem_reg2aln (CIGAR stage at the call-site level)
+ALN_DT = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("band", "<i4"),
+                   ("n_waves", "<i4")], align=True)
+
+
+def fork_reg2aln(opt, ctg: Contigs, pac, query, qb, qe, rb, re, truesc, ar_w, cap=512):
+    """the unmodified fork's mem_reg2aln: dict(pos, rid, is_rev, nm, n_cigar, cigar)"""
+    out8 = np.zeros(8, np.int64)
+    cig = np.zeros(cap, np.uint32)
+    query = np.ascontiguousarray(query, dtype=np.uint8)
+    n = fork_lib().fork_reg2aln(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(pac), len(query), _ptr(query), int(qb), int(qe),
+                                int(rb), int(re), int(truesc), int(ar_w), 0, _ptr(out8), _ptr(cig), cap)
+    assert n <= cap
+    return dict(pos=int(out8[0]), rid=int(out8[1]), is_rev=int(out8[2]), nm=int(out8[4]), n_cigar=int(out8[5]), cigar=cig[:n].copy())
+
+
+def oracle_reg2aln(opt, kp, ctg: Contigs, fwd, query, qb, qe, rb, re, truesc, ar_w, cap=512):
+    """oracle/global_oracle.c glb_reg2aln: (ALN_DT record, cigar)"""
+    L = O.lib()
+    if not getattr(L, "_r2a", False):
+        L.glb_reg2aln.argtypes = [_vp] + [C.c_int] * 6 + [C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                  _vp, _vp, C.c_int]
+        L.glb_reg2aln.restype = C.c_int
+        L._r2a = True
+    mat = np.frombuffer(bytes(kp.mat), dtype=np.int8).copy()
+    out = np.zeros(1, ALN_DT)
+    cig = np.zeros(cap, np.uint32)
+    query = np.ascontiguousarray(query, dtype=np.uint8); fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
+    n = L.glb_reg2aln(_ptr(mat), opt.a, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, opt.w, ctg.l_pac, _ptr(fwd), ctg.n, _ptr(ctg.off), len(query), _ptr(query),
+                      int(qb), int(qe), int(rb), int(re), int(truesc), int(ar_w), _ptr(out), _ptr(cig), cap)
+    assert n >= 0
+    return out[0], cig[:n].copy()

@@ -215,4 +215,37 @@ const uint8_t *fork_mem_seq(int side, int which, uint64_t *n_bytes)
     return v.data();
 }
 
+/* the fork's own mem_reg2aln (src/bwamem.c:2344-2438) on one alignment region.  pac: 2-bit packed forward reference; query: codes
+ * 0..4 of the whole read.  out8 = pos, rid, is_rev, score (the mem_aln_t one = ar->score), NM, n_cigar, flag, mapq; the CIGAR
+ * (soft clips included) is copied to cigar_out.  Returns n_cigar. */
+int fork_reg2aln(const fork_opt_t *fo, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const uint8_t *pac,
+                 int l_query, const uint8_t *query, int qb, int qe, int64_t rb, int64_t re, int truesc, int ar_w, int ar_score,
+                 int64_t out8[8], uint32_t *cigar_out, int cap)
+{
+    mem_opt_t *opt = mem_opt_init();
+    opt->a = fo->a; opt->b = fo->b; opt->o_del = fo->o_del; opt->e_del = fo->e_del; opt->o_ins = fo->o_ins; opt->e_ins = fo->e_ins; opt->w = fo->w;
+    bwa_fill_scmat(opt->a, opt->b, opt->mat);
+    bntseq_t bns;
+    memset(&bns, 0, sizeof(bns));
+    bns.l_pac = l_pac; bns.n_seqs = n_ctg;
+    std::vector<bntann1_t> anns(n_ctg);
+    char nm[] = "ctg";
+    for (int i = 0; i < n_ctg; ++i) { memset(&anns[i], 0, sizeof(bntann1_t)); anns[i].offset = ctg_off[i]; anns[i].len = ctg_len[i]; anns[i].name = nm; anns[i].anno = nm; }
+    bns.anns = anns.data();
+    mem_alnreg_t ar;
+    memset(&ar, 0, sizeof(ar));
+    ar.rb = rb; ar.re = re; ar.qb = qb; ar.qe = qe; ar.truesc = truesc; ar.w = ar_w; ar.score = ar_score; ar.secondary = -1;
+    if (rb >= 0 && re >= 0) {
+        int is_rev;
+        ar.rid = bns_pos2rid(&bns, bns_depos(&bns, rb < l_pac ? rb : re - 1, &is_rev));     /* mem_reg2aln asserts a.rid == ar->rid */
+    }
+    mem_aln_t a = mem_reg2aln(opt, &bns, pac, l_query, (const char *)query, &ar);
+    out8[0] = a.pos; out8[1] = a.rid; out8[2] = a.is_rev; out8[3] = a.score; out8[4] = a.NM; out8[5] = a.n_cigar; out8[6] = a.flag; out8[7] = a.mapq;
+    for (int i = 0; i < a.n_cigar && i < cap; ++i) cigar_out[i] = a.cigar[i];
+    int n = a.n_cigar;
+    free(a.cigar);
+    free(opt);
+    return n;
+}
+
 } /* extern "C" */

@@ -169,3 +169,72 @@ int glb_gen_cigar2(const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins
     free(rseq); free(query);
     return n_cigar;
 }
+
+/* ---- mem_reg2aln (src/bwamem.c:2344-2438): band inference, bwa_gen_cigar2 with the band-doubling retry, squeeze of a
+ * leading / trailing deletion, soft clips, position.  The MD string, mapq and the flags stay out (text / other inputs). */
+static int infer_bw(int l1, int l2, int score, int a, int q, int r)
+{ /* src/bwamem.c:1486-1494 */
+    int w;
+    if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+    w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+    if (w < abs(l1 - l2)) w = abs(l1 - l2);
+    return w;
+}
+
+static int pos2rid(int n_ctg, const int64_t *ctg_off, int64_t l_pac, int64_t pos_f)
+{ /* bns_pos2rid, src/bntseq.c:349-363 */
+    int left = 0, mid = 0, right = n_ctg;
+    if (pos_f >= l_pac) return -1;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pos_f >= ctg_off[mid]) {
+            if (mid == n_ctg - 1) break;
+            if (pos_f < ctg_off[mid + 1]) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    return mid;
+}
+
+int glb_reg2aln(const int8_t *mat, int a, int o_del, int e_del, int o_ins, int e_ins, int opt_w, int64_t l_pac, const uint8_t *fwd,
+                int n_ctg, const int64_t *ctg_off, int l_query, const uint8_t *query, int qb, int qe, int64_t rb, int64_t re,
+                int truesc, int ar_w, glb_aln_t *out, uint32_t *cigar, int cap)
+{
+    int i, w2, tmp, NM = -1, score = 0, last_sc = -(1 << 30), n_cigar = 0, is_rev, n_waves = 0;
+    int64_t pos;
+    memset(out, 0, sizeof(*out));
+    if (rb < 0 || re < 0) { out->rid = -1; out->pos = -1; return 0; }
+    tmp = infer_bw(qe - qb, (int)(re - rb), truesc, a, o_del, e_del);
+    w2 = infer_bw(qe - qb, (int)(re - rb), truesc, a, o_ins, e_ins);
+    w2 = w2 > tmp ? w2 : tmp;
+    if (w2 > opt_w) w2 = w2 < ar_w ? w2 : ar_w;
+    i = 0;
+    do {
+        w2 = w2 < opt_w << 2 ? w2 : opt_w << 2;
+        int sc = 0, nm = -1;
+        int n = glb_gen_cigar2(mat, o_del, e_del, o_ins, e_ins, w2, l_pac, fwd, qe - qb, query + qb, rb, re, &sc, &nm, cigar, cap);
+        ++n_waves;
+        if (n >= 0) { n_cigar = n; score = sc; NM = nm; } else { n_cigar = 0; NM = -1; }   /* a rejected job leaves score as it was */
+        if (score == last_sc || w2 == opt_w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < truesc - a);
+    if (n_cigar > cap) return -1;
+    pos = rb < l_pac ? rb : re - 1;
+    is_rev = pos >= l_pac;
+    if (is_rev) pos = (l_pac << 1) - 1 - pos;
+    if (n_cigar > 0) {
+        if ((cigar[0] & 0xf) == 2) { pos += cigar[0] >> 4; --n_cigar; memmove(cigar, cigar + 1, (size_t)n_cigar * 4); }
+        else if ((cigar[n_cigar - 1] & 0xf) == 2) --n_cigar;
+    }
+    if (qb != 0 || qe != l_query) {
+        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+        if (n_cigar + 2 > cap) return -1;
+        if (clip5) { memmove(cigar + 1, cigar, (size_t)n_cigar * 4); cigar[0] = (uint32_t)clip5 << 4 | 3; ++n_cigar; }
+        if (clip3) cigar[n_cigar++] = (uint32_t)clip3 << 4 | 3;
+    }
+    out->rid = pos2rid(n_ctg, ctg_off, l_pac, pos);
+    out->pos = pos - (out->rid >= 0 ? ctg_off[out->rid] : 0);
+    out->is_rev = is_rev; out->score = score; out->nm = NM; out->n_cigar = n_cigar; out->band = w2; out->n_waves = n_waves;
+    return n_cigar;
+}

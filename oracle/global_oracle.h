@@ -34,6 +34,13 @@ void glb_batch(int64_t n, const uint8_t *qseq, const uint32_t *qoff, const uint3
  * shortcut when l_query == re - rb and w_ == 0), NM.  Returns n_cigar, or -1 when the reference rejects the job. */
 int glb_gen_cigar2(const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac, const uint8_t *fwd,
                    int l_query, const uint8_t *query, int64_t rb, int64_t re, int *score, int *nm, uint32_t *cigar, int cap);
+/* mem_reg2aln (src/bwamem.c:2344-2438) without the text parts: the fields of mem_aln_t it computes from the DP */
+typedef struct { int64_t pos; int32_t rid, is_rev, score, nm, n_cigar, band, n_waves; } glb_aln_t;
+/* score = the last global score, band = the last w2 handed to bwa_gen_cigar2, n_waves = calls of bwa_gen_cigar2; the CIGAR has
+ * the leading / trailing deletion squeezed out and the soft clips added.  Returns n_cigar, -1 when cap is too small. */
+int glb_reg2aln(const int8_t *mat, int a, int o_del, int e_del, int o_ins, int e_ins, int opt_w, int64_t l_pac, const uint8_t *fwd,
+                int n_ctg, const int64_t *ctg_off, int l_query, const uint8_t *query, int qb, int qe, int64_t rb, int64_t re,
+                int truesc, int ar_w, glb_aln_t *out, uint32_t *cigar, int cap);
 #ifdef __cplusplus
 }
 #endif
