@@ -108,8 +108,12 @@ SYMBOLS = [
     "bwa_b200_aligner_kernel_times",
     "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_cigars_free",
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
-    "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times",
+    "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
 ]
+
+ALN_IN_DTYPE = np.dtype([("read", "<u4"), ("qb", "<i4"), ("qe", "<i4"), ("rb", "<i8"), ("re", "<i8"), ("truesc", "<i4"), ("w", "<i4")], align=True)
+ALN_OUT_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("band", "<i4"),
+                          ("n_waves", "<i4"), ("cigar_off", "<u8")], align=True)
 
 
 class Cigars(C.Structure):
@@ -250,6 +254,8 @@ def lib():
         L.bwa_b200_cigar_last_cells.restype = C.c_uint64
         L.bwa_b200_cigar_profile.argtypes = [vp, C.c_int]
         L.bwa_b200_cigar_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+        L.bwa_b200_reg2aln_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(ExtParams), C.c_int32, vp,
+                                            C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -629,6 +635,19 @@ class Cigar:
                    cigar_off=_take(out.cigar_off, n, np.uint64), cigar=_take(out.cigar, out.n_ops, np.uint32))
         lib().bwa_b200_cigars_free(C.byref(out))
         return res
+
+    def reg2aln_host(self, index, ctg_off, packed, word_off, read_len, alns, ext_p: ExtParams, match_score: int):
+        """mem_reg2aln over a batch (bwa_b200_reg2aln_host).  alns: ALN_IN_DTYPE records.  Returns (ALN_OUT_DTYPE records, flat cigar)."""
+        alns = np.ascontiguousarray(alns, dtype=ALN_IN_DTYPE)
+        ctg_off = np.ascontiguousarray(ctg_off, dtype=np.int64)
+        out = np.zeros(alns.size, ALN_OUT_DTYPE)
+        cig = C.POINTER(C.c_uint32)()
+        n_ops = C.c_uint64(0)
+        check(lib().bwa_b200_reg2aln_host(self.h, index.h, ctg_off.size, _p(ctg_off), _p(packed), _p(word_off), _p(read_len), read_len.size, _p(alns),
+                                          alns.size, C.byref(ext_p), int(match_score), _p(out), C.byref(cig), C.byref(n_ops)))
+        flat = np.ctypeslib.as_array(cig, shape=(max(int(n_ops.value), 1),))[:int(n_ops.value)].copy()
+        C.CDLL(None).free(cig)
+        return out, flat
 
     def global_device(self, ext_p, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_qlen, h_tlen, h_w):
         check(lib().bwa_b200_global_device(self.h, C.byref(ext_p), n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, _p(h_qlen), _p(h_tlen), _p(h_w)))

@@ -242,6 +242,9 @@ struct bwa_b200_cigar {
     cudaStream_t side[5] = {};              // band classes of one batch run concurrently (forked from / joined to `stream`)
     cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
     std::vector<uint32_t> perm; uint32_t cls_n[5] = {}, cls_tl[5] = {}, cls_ql[5] = {};
+    // bwa_b200_reg2aln_host: the batch's reads and region table on the device
+    uint32_t *r_packed = nullptr; uint64_t r_packed_cap = 0; uint64_t *r_woff = nullptr; uint64_t r_woff_cap = 0;
+    void *r_jobs = nullptr; uint64_t r_jobs_cap = 0;
     int smem_optin = 0;
     uint64_t z_off[5] = {};
     uint64_t last_n = 0, last_ops = 0, last_cells = 0, launches = 0;
@@ -291,6 +294,7 @@ extern "C" void bwa_b200_cigar_destroy(bwa_b200_cigar_t *c)
     cudaFree(c->d_q); cudaFree(c->d_t); cudaFree(c->d_qoff); cudaFree(c->d_qlen); cudaFree(c->d_toff); cudaFree(c->d_tlen);
     cudaFree(c->d_w); cudaFree(c->d_perm); cudaFree(c->d_ncig); cudaFree(c->d_score); cudaFree(c->d_nm); cudaFree(c->d_off);
     cudaFree(c->d_rows); cudaFree(c->d_flat); cudaFree(c->d_z); cudaFree(c->d_cub); cudaFree(c->d_counters);
+    cudaFree(c->r_packed); cudaFree(c->r_woff); cudaFree(c->r_jobs);
     cudaFreeHost(c->h_counters);
     for (int k = 0; k < 5; ++k) { if (c->side[k]) cudaStreamDestroy(c->side[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -516,4 +520,207 @@ extern "C" int bwa_b200_cigar_kernel_times(bwa_b200_cigar_t *c, const char **nam
         names[n] = c->prof.recs[i].name; ms[n] = t;
     }
     return n;
+}
+
+// ============================================================================ mem_reg2aln, batched
+// The caller of the CIGAR path (src/bwamem.c:2344-2438).  Per alignment region: band inference (infer_bw), bwa_gen_cigar2 with up to
+// three band-doubling retries, squeeze of a leading / trailing deletion, soft clips, forward position and contig.  Here a retry is a
+// wave: every region still improving goes through global_kernel again with a doubled band.  Sequences never come from the host:
+// r2a_cut_kernel cuts query and reference window of every region from the packed reads and the resident 2-bit reference, in the
+// orientation bwa_gen_cigar2 aligns them (both reversed for a reverse-strand hit, src/bwa.c:145-150).
+namespace {
+
+struct R2AJob { uint32_t read; int32_t qb, qe; int64_t rb, re; uint32_t qoff, toff; };
+
+__global__ void __launch_bounds__(128)
+r2a_cut_kernel(uint32_t n, const R2AJob *__restrict__ jobs, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
+               const uint32_t *__restrict__ pac, uint64_t l_pac, uint8_t *__restrict__ qout, uint8_t *__restrict__ tout)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= n) return;
+    const R2AJob J = jobs[warp];
+    const int ql = J.qe - J.qb, tl = (int)(J.re - J.rb);
+    const bool rev = J.rb >= (int64_t)l_pac;
+    const uint64_t wo = word_off[J.read];
+    for (int j = (int)lane; j < ql; j += 32) {
+        const int pos = rev ? J.qe - 1 - j : J.qb + j;
+        uint32_t c = (packed[wo + ((uint32_t)pos >> 3)] >> (28 - 4 * (pos & 7))) & 15u;
+        qout[J.qoff + j] = (uint8_t)(c > 4u ? 4u : c);
+    }
+    const uint64_t t0 = rev ? 2 * l_pac - (uint64_t)J.re : (uint64_t)J.rb;      // forward-strand start of the window
+    for (int j = (int)lane; j < tl; j += 32) {
+        const uint64_t g = t0 + (uint64_t)j;
+        const uint32_t b = (pac[g >> 4] >> ((~g & 15u) << 1)) & 3u;
+        tout[J.toff + j] = (uint8_t)(rev ? 3u - b : b);
+    }
+}
+
+int infer_bw(int l1, int l2, int score, int a, int q, int r)
+{ // src/bwamem.c:1486-1494
+    if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+    int w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+    const int d = l1 > l2 ? l1 - l2 : l2 - l1;
+    return w < d ? d : w;
+}
+
+} // namespace
+
+extern "C" int bwa_b200_reg2aln_host(bwa_b200_cigar_t *c, const bwa_b200_index_t *idx, int32_t n_ctg, const int64_t *ctg_off,
+                                     const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len, uint64_t n_reads,
+                                     const bwa_b200_aln_in_t *alns, uint64_t n_alns, const bwa_b200_ext_params_t *p, int32_t match_score,
+                                     bwa_b200_aln_out_t *out, uint32_t **cigar, uint64_t *n_ops)
+{
+    if (!c || !idx || !p || !out || !cigar || !n_ops || n_ctg < 1 || !ctg_off || (n_alns && (!alns || !packed || !word_off || !read_len))) {
+        b200::set_error("reg2aln: bad argument"); return BWA_B200_ERR_ARG;
+    }
+    *cigar = nullptr; *n_ops = 0;
+    if (!idx->d_pac) { b200::set_error("reg2aln: the index has no reference attached (bwa_b200_index_attach_ref)"); return BWA_B200_ERR_ARG; }
+    if (idx->device != c->device) { b200::set_error("reg2aln: index and CIGAR handle live on different devices"); return BWA_B200_ERR_ARG; }
+    if (n_alns > 0x7ffffff0ull) { b200::set_error("reg2aln: too many regions"); return BWA_B200_ERR_ARG; }
+    const int64_t l_pac = (int64_t)idx->l_pac;
+    const int opt_w = p->w, a_sc = match_score;
+    // ---- jobs: every mapped region the reference would hand to ksw_global2
+    struct St { int w2, last_sc, iter, score, nm, n_waves; bool job, done; std::vector<uint32_t> cig; };
+    std::vector<St> st(n_alns);
+    std::vector<R2AJob> jobs; std::vector<uint32_t> job_aln;
+    uint64_t qbytes = 0, tbytes = 0;
+    for (uint64_t k = 0; k < n_alns; ++k) {
+        const bwa_b200_aln_in_t &r = alns[k];
+        St &s = st[k];
+        s.w2 = 0; s.last_sc = -(1 << 30); s.iter = 0; s.score = 0; s.nm = -1; s.n_waves = 0; s.job = false; s.done = true;
+        if (r.rb < 0 || r.re < 0) continue;                                   // unmapped record
+        if (r.read >= n_reads || r.qb < 0 || r.qe > (int32_t)read_len[r.read]) { b200::set_error("reg2aln: region %llu does not lie on its read", (unsigned long long)k); return BWA_B200_ERR_ARG; }
+        if (r.re > 2 * l_pac) { b200::set_error("reg2aln: region %llu reaches past the reference", (unsigned long long)k); return BWA_B200_ERR_ARG; }
+        const int lq = r.qe - r.qb; const int64_t rl = r.re - r.rb;
+        int tmp = infer_bw(lq, (int)rl, r.truesc, a_sc, p->o_del, p->e_del);
+        int w2 = infer_bw(lq, (int)rl, r.truesc, a_sc, p->o_ins, p->e_ins);
+        w2 = w2 > tmp ? w2 : tmp;
+        if (w2 > opt_w) w2 = w2 < r.w ? w2 : r.w;
+        s.w2 = w2; s.done = false;
+        if (lq <= 0 || r.rb >= r.re || (r.rb < l_pac && r.re > l_pac)) continue;   // bwa_gen_cigar2 rejects it (src/bwa.c:124): no DP, score stays 0
+        s.job = true;
+        R2AJob j; j.read = r.read; j.qb = r.qb; j.qe = r.qe; j.rb = r.rb; j.re = r.re; j.qoff = (uint32_t)qbytes; j.toff = (uint32_t)tbytes;
+        qbytes += ((uint64_t)lq + 7) / 8 * 8; tbytes += ((uint64_t)rl + 7) / 8 * 8;
+        if (qbytes > 0xfffffff0ull || tbytes > 0xfffffff0ull) { b200::set_error("reg2aln: more than 4 GB of sequence in one batch"); return BWA_B200_ERR_CAPACITY; }
+        jobs.push_back(j); job_aln.push_back((uint32_t)k);
+    }
+    B200_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stq = c->stream;
+    const uint64_t nj = jobs.size();
+    if (nj) {
+        // reads + job table up, sequences cut on the device
+        const uint64_t n_words = word_off[n_reads];
+        int bad = 0;
+        bad |= grow_dev(c->r_packed, c->r_packed_cap, n_words ? n_words : 1); bad |= grow_dev(c->r_woff, c->r_woff_cap, n_reads + 1);
+        bad |= grow_dev(c->d_q, c->q_cap, qbytes ? qbytes : 1); bad |= grow_dev(c->d_t, c->t_cap, tbytes ? tbytes : 1);
+        uint8_t *jb = (uint8_t *)c->r_jobs;
+        bad |= grow_dev(jb, c->r_jobs_cap, nj * sizeof(R2AJob));
+        c->r_jobs = jb;
+        bad |= grow_dev(c->d_qoff, c->qoff_cap, nj); bad |= grow_dev(c->d_qlen, c->qlen_cap, nj); bad |= grow_dev(c->d_toff, c->toff_cap, nj);
+        bad |= grow_dev(c->d_tlen, c->tlen_cap, nj); bad |= grow_dev(c->d_w, c->w_cap, nj);
+        if (bad) { b200::set_error("reg2aln: out of device memory"); return BWA_B200_ERR_NOMEM; }
+        B200_CUDA(cudaMemcpyAsync(c->r_packed, packed, n_words * 4, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->r_woff, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->r_jobs, jobs.data(), nj * sizeof(R2AJob), cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemsetAsync(c->d_q, 4, qbytes ? qbytes : 1, stq));
+        B200_CUDA(cudaMemsetAsync(c->d_t, 4, tbytes ? tbytes : 1, stq));
+        r2a_cut_kernel<<<(unsigned)((nj * 32 + 127) / 128), 128, 0, stq>>>((uint32_t)nj, (const R2AJob *)c->r_jobs, c->r_packed, c->r_woff, idx->d_pac,
+                                                                          (uint64_t)l_pac, c->d_q, c->d_t);
+        ++c->launches;
+        B200_CUDA(cudaGetLastError());
+    }
+    // ---- waves (the do-while of src/bwamem.c:2375-2392, all regions at once)
+    std::vector<uint32_t> act, h_qoff, h_qlen, h_toff, h_tlen, h_w, h_nc, h_flat;
+    std::vector<int32_t> h_score, h_nm; std::vector<uint64_t> h_off;
+    for (int wave = 0; wave < 3; ++wave) {
+        act.clear(); h_qoff.clear(); h_qlen.clear(); h_toff.clear(); h_tlen.clear(); h_w.clear();
+        for (uint64_t jx = 0; jx < nj; ++jx) {
+            St &s = st[job_aln[jx]];
+            if (s.done) continue;
+            s.w2 = s.w2 < opt_w << 2 ? s.w2 : opt_w << 2;
+            const int lq = jobs[jx].qe - jobs[jx].qb; const int64_t rl = jobs[jx].re - jobs[jx].rb;
+            // ungapped shortcut of bwa_gen_cigar2 (src/bwa.c:151-160) == the DP with a band of 0: one diagonal, all M
+            const int band = (lq == rl && s.w2 == 0) ? 0 : bwa_b200_cigar_band(p, s.w2, lq, rl);
+            act.push_back((uint32_t)jx); h_qoff.push_back(jobs[jx].qoff); h_qlen.push_back((uint32_t)lq); h_toff.push_back(jobs[jx].toff);
+            h_tlen.push_back((uint32_t)rl); h_w.push_back((uint32_t)band);
+        }
+        // regions bwa_gen_cigar2 rejects go through the same control flow with score 0 and no CIGAR
+        for (uint64_t k = 0; k < n_alns; ++k) {
+            St &s = st[k];
+            if (s.done || s.job) continue;
+            s.w2 = s.w2 < opt_w << 2 ? s.w2 : opt_w << 2;
+            ++s.n_waves;
+            if (s.score == s.last_sc || s.w2 == opt_w << 2) { s.done = true; continue; }
+            s.last_sc = s.score; s.w2 <<= 1;
+            if (!(++s.iter < 3 && s.score < alns[k].truesc - a_sc)) s.done = true;
+        }
+        const uint64_t na = act.size();
+        if (na == 0) break;
+        B200_CUDA(cudaMemcpyAsync(c->d_qoff, h_qoff.data(), na * 4, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->d_qlen, h_qlen.data(), na * 4, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->d_toff, h_toff.data(), na * 4, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->d_tlen, h_tlen.data(), na * 4, cudaMemcpyHostToDevice, stq));
+        B200_CUDA(cudaMemcpyAsync(c->d_w, h_w.data(), na * 4, cudaMemcpyHostToDevice, stq));
+        int rc = cigar_run(c, p, na, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, h_qlen.data(), h_tlen.data(), h_w.data());
+        if (rc) return rc;
+        const uint64_t ops = c->last_ops;
+        h_score.resize(na); h_nm.resize(na); h_nc.resize(na); h_off.resize(na); h_flat.resize(ops ? ops : 1);
+        B200_CUDA(cudaMemcpyAsync(h_score.data(), c->d_score, na * 4, cudaMemcpyDeviceToHost, stq));
+        B200_CUDA(cudaMemcpyAsync(h_nm.data(), c->d_nm, na * 4, cudaMemcpyDeviceToHost, stq));
+        B200_CUDA(cudaMemcpyAsync(h_nc.data(), c->d_ncig, na * 4, cudaMemcpyDeviceToHost, stq));
+        B200_CUDA(cudaMemcpyAsync(h_off.data(), c->d_off, na * 8, cudaMemcpyDeviceToHost, stq));
+        if (ops) B200_CUDA(cudaMemcpyAsync(h_flat.data(), c->d_flat, ops * 4, cudaMemcpyDeviceToHost, stq));
+        B200_CUDA(cudaStreamSynchronize(stq));
+        for (uint64_t x = 0; x < na; ++x) {
+            const uint64_t k = job_aln[act[x]];
+            St &s = st[k];
+            s.score = h_score[x]; s.nm = h_nm[x]; ++s.n_waves;
+            s.cig.assign(h_flat.begin() + h_off[x], h_flat.begin() + h_off[x] + h_nc[x]);
+            if (s.score == s.last_sc || s.w2 == opt_w << 2) { s.done = true; continue; }
+            s.last_sc = s.score; s.w2 <<= 1;
+            if (!(++s.iter < 3 && s.score < alns[k].truesc - a_sc)) s.done = true;
+        }
+    }
+    // ---- position, deletion squeeze, soft clips (src/bwamem.c:2402-2432)
+    uint64_t total = 0;
+    for (uint64_t k = 0; k < n_alns; ++k) {
+        const bwa_b200_aln_in_t &r = alns[k];
+        St &s = st[k];
+        bwa_b200_aln_out_t &o = out[k];
+        memset(&o, 0, sizeof(o));
+        if (r.rb < 0 || r.re < 0) { o.rid = -1; o.pos = -1; o.cigar_off = total; continue; }
+        int64_t pos = r.rb < l_pac ? r.rb : r.re - 1;
+        const int is_rev = pos >= l_pac;
+        if (is_rev) pos = (l_pac << 1) - 1 - pos;
+        std::vector<uint32_t> &cg = s.cig;
+        if (!cg.empty()) {
+            if ((cg.front() & 0xf) == 2) { pos += cg.front() >> 4; cg.erase(cg.begin()); }
+            else if ((cg.back() & 0xf) == 2) cg.pop_back();
+        }
+        const int l_query = (int)read_len[r.read];
+        if (r.qb != 0 || r.qe != l_query) {
+            const int clip5 = is_rev ? l_query - r.qe : r.qb, clip3 = is_rev ? r.qb : l_query - r.qe;
+            if (clip5) cg.insert(cg.begin(), (uint32_t)clip5 << 4 | 3u);
+            if (clip3) cg.push_back((uint32_t)clip3 << 4 | 3u);
+        }
+        int rid = -1;
+        if (pos < l_pac) {               // bns_pos2rid, src/bntseq.c:349-363
+            int left = 0, mid = 0, right = n_ctg;
+            while (left < right) {
+                mid = (left + right) >> 1;
+                if (pos >= ctg_off[mid]) { if (mid == n_ctg - 1) break; if (pos < ctg_off[mid + 1]) break; left = mid + 1; }
+                else right = mid;
+            }
+            rid = mid;
+        }
+        o.rid = rid; o.pos = pos - (rid >= 0 ? ctg_off[rid] : 0); o.is_rev = is_rev; o.score = s.score; o.nm = s.nm;
+        o.n_cigar = (int32_t)cg.size(); o.band = s.w2; o.n_waves = s.n_waves; o.cigar_off = total;
+        total += cg.size();
+    }
+    uint32_t *flat = (uint32_t *)malloc((total ? total : 1) * 4);
+    if (!flat) { b200::set_error("reg2aln: out of host memory"); return BWA_B200_ERR_NOMEM; }
+    for (uint64_t k = 0; k < n_alns; ++k)
+        if (!st[k].cig.empty() && out[k].rid != -1) memcpy(flat + out[k].cigar_off, st[k].cig.data(), st[k].cig.size() * 4);
+    *cigar = flat; *n_ops = total;
+    return BWA_B200_OK;
 }

@@ -304,6 +304,26 @@ uint64_t bwa_b200_cigar_last_cells(const bwa_b200_cigar_t *c);     /* DP cells o
 int  bwa_b200_cigar_profile(bwa_b200_cigar_t *c, int enable);
 int  bwa_b200_cigar_kernel_times(bwa_b200_cigar_t *c, const char **names, float *ms, int cap);
 
+/* mem_reg2aln over a batch (src/bwamem.c:2344-2438): per alignment region the band inference (infer_bw), bwa_gen_cigar2 with its
+ * band-doubling retries -- each retry is one more wave of the kernel over the regions still improving --, the squeeze of a leading or
+ * trailing deletion, the soft clips, the forward position and contig.  Query and reference windows are cut on the device from the
+ * packed reads and the reference attached to the index (bwa_b200_index_attach_ref), in the orientation bwa_gen_cigar2 aligns them.
+ * What stays with the caller: mapq, flags, the MD text.  ctg_off = bntann1_t offsets; match_score = opt->a; p->w = opt->w. */
+typedef struct { uint32_t read; int32_t qb, qe; int64_t rb, re; int32_t truesc, w; } bwa_b200_aln_in_t;   /* the mem_alnreg_t fields it reads */
+typedef struct {                   /* the mem_aln_t fields it sets */
+    int64_t  pos;                  /* 0-based position on contig rid, forward strand; -1 for an unmapped record (rb or re < 0) */
+    int32_t  rid, is_rev;
+    int32_t  score;                /* the last global-alignment score (the value mem_reg2aln compares with truesc)             */
+    int32_t  nm, n_cigar;          /* CIGAR in BAM encoding, soft clips (op 3) included                                        */
+    int32_t  band, n_waves;        /* w2 after the retry loop; calls of bwa_gen_cigar2                                          */
+    uint64_t cigar_off;            /* first operation in the flat CIGAR array                                                  */
+} bwa_b200_aln_out_t;
+/* `cigar` is malloc'ed (n_ops operations): release it with free() */
+int  bwa_b200_reg2aln_host(bwa_b200_cigar_t *c, const bwa_b200_index_t *idx, int32_t n_ctg, const int64_t *ctg_off,
+                           const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len, uint64_t n_reads,
+                           const bwa_b200_aln_in_t *alns, uint64_t n_alns, const bwa_b200_ext_params_t *p, int32_t match_score,
+                           bwa_b200_aln_out_t *out, uint32_t **cigar, uint64_t *n_ops);
+
 /* ------------------------------------- seeds -> chains -> extension jobs -> alignment regions */
 /* The step between the two hot paths in the reference worker (src/bwamem.c:2055-2093 and :2286-2306), on the
  * device, so that a read batch goes seeds -> chains -> jobs -> extension -> regions without leaving HBM

@@ -124,3 +124,50 @@ def test_global_golden_from_reference(gpu, oracle):
     assert (got["n_cigar"] == gold["gc_n_cigar"][keep]).all()
     assert (rows_of(got, gold["gc_cigar"].shape[1]) == gold["gc_cigar"][keep]).all()
     cg.destroy()
+
+
+def test_reg2aln_matches_oracle_and_fork_golden(gpu, oracle, tmp_path):
+    """mem_reg2aln over a batch: windows cut on the device, band-doubling retries as waves, squeeze / clips / position on the host --
+    against the fork's own mem_reg2aln (golden) and the oracle (band and number of waves too)"""
+    from oracle import chain_py as CP
+    gold = np.load(os.path.join(GOLD, "reg2aln_golden.npz"))
+    ctg = CP.Contigs(tuple(int(x) for x in gold["contigs"]))
+    g = synth.make_genome(ctg.l_pac, seed=int(gold["genome_seed"]))
+    prefix = str(tmp_path / "g")
+    gpu.build_index(g, prefix, sa_intv=16, n_threads=4)
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(g)
+    reads, regs = gold["reads"], gold["regs"]
+    n, L = reads.shape
+    packed, woff, rl = gpu.pack_codes(reads.reshape(-1).copy(), (np.arange(n + 1) * L).astype(np.uint64))
+    alns = np.zeros(len(regs), gpu.ALN_IN_DTYPE)
+    for k, (i, qb, qe, rb, re, truesc, w) in enumerate(regs):
+        alns[k] = (i, qb, qe, rb, re, truesc, w)
+    cg = gpu.Cigar(0)
+    waves = 0
+    for oi in range(2):
+        v = gold[f"opt_{oi}"]
+        opt = CP.default_opt(a=int(v[0]), b=int(v[1]), o_del=int(v[2]), e_del=int(v[3]), o_ins=int(v[4]), e_ins=int(v[5]), w=int(v[6]))
+        kw = dict(a=opt.a, b=opt.b, o_del=opt.o_del, e_del=opt.e_del, o_ins=opt.o_ins, e_ins=opt.e_ins)
+        got, flat = cg.reg2aln_host(idx, ctg.off, packed, woff, rl, alns, gpu.ext_params(w=opt.w, **kw), opt.a)
+        rec, cig = gold[f"rec_{oi}"], gold[f"cigar_{oi}"]
+        kp = oracle.make_params(**kw)
+        for k, (i, qb, qe, rb, re, truesc, w) in enumerate(regs):
+            o = got[k]
+            assert (int(o["pos"]), int(o["rid"]), int(o["is_rev"])) == tuple(int(x) for x in rec[k, :3]), k
+            if rec[k, 1] < 0:
+                assert o["n_cigar"] == 0
+                continue
+            mine = flat[int(o["cigar_off"]):int(o["cigar_off"]) + int(o["n_cigar"])]
+            assert int(o["nm"]) == rec[k, 3] and int(o["n_cigar"]) == rec[k, 4], k
+            assert (mine == cig[k, :mine.size]).all(), k
+            a, _ = CP.oracle_reg2aln(opt, kp, ctg, g, reads[i], qb, qe, rb, re, truesc, w)
+            assert int(o["score"]) == int(a["score"]) and int(o["band"]) == int(a["band"]) and int(o["n_waves"]) == int(a["n_waves"]), k
+            waves = max(waves, int(o["n_waves"]))
+    assert waves >= 2                                        # the band-doubling retry did run on some region
+    # regions outside the read / the reference are refused
+    bad = alns[:1].copy(); bad["qe"] = L + 5
+    with pytest.raises(RuntimeError):
+        cg.reg2aln_host(idx, ctg.off, packed, woff, rl, bad, gpu.ext_params(), 1)
+    cg.destroy()
+    idx.free()
