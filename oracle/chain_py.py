@@ -239,7 +239,7 @@ def oracle_align_batch(opt, ctg: Contigs, fwd, reads, rbeg, qq, score, n_seeds, 
 
 
 # ------------------------------------------------------------------ mem_reg2aln (CIGAR stage at the call-site level)
-ALN_DT = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("band", "<i4"),
+R2A_DT = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("score", "<i4"), ("nm", "<i4"), ("n_cigar", "<i4"), ("band", "<i4"),
                    ("n_waves", "<i4")], align=True)
 
 
@@ -255,7 +255,7 @@ def fork_reg2aln(opt, ctg: Contigs, pac, query, qb, qe, rb, re, truesc, ar_w, ca
 
 
 def oracle_reg2aln(opt, kp, ctg: Contigs, fwd, query, qb, qe, rb, re, truesc, ar_w, cap=512):
-    """oracle/global_oracle.c glb_reg2aln: (ALN_DT record, cigar)"""
+    """oracle/global_oracle.c glb_reg2aln: (R2A_DT record, cigar)"""
     L = O.lib()
     if not getattr(L, "_r2a", False):
         L.glb_reg2aln.argtypes = [_vp] + [C.c_int] * 6 + [C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
@@ -263,7 +263,7 @@ def oracle_reg2aln(opt, kp, ctg: Contigs, fwd, query, qb, qe, rb, re, truesc, ar
         L.glb_reg2aln.restype = C.c_int
         L._r2a = True
     mat = np.frombuffer(bytes(kp.mat), dtype=np.int8).copy()
-    out = np.zeros(1, ALN_DT)
+    out = np.zeros(1, R2A_DT)
     cig = np.zeros(cap, np.uint32)
     query = np.ascontiguousarray(query, dtype=np.uint8); fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
     n = L.glb_reg2aln(_ptr(mat), opt.a, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, opt.w, ctg.l_pac, _ptr(fwd), ctg.n, _ptr(ctg.off), len(query), _ptr(query),
