@@ -109,6 +109,7 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
             int32_t f = MINF, h1 = beg == 0 ? -(a.o_del + a.e_del * (i + 1)) : MINF;
             uint32_t zw = 0, qw = ncol ? qs[(beg >> 3) * BLOCK] : 0u;
             uint32_t *zrow = z + (uint64_t)i * WPR * 32 + lane;
+#pragma unroll 4
             for (int c = 0; c < warp_nc; ++c) {
                 if (c < ncol) {
                     const int j = beg + c;
@@ -363,12 +364,17 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
         if (cnt[4]) rc |= class_grid<256, 32>(c->n_sm, sm[4], &c->grid[4]);
         if (rc) return BWA_B200_ERR_CUDA;
     }
+    // within a class jobs are ordered by band width (counting sort), so the 32 jobs of a warp have (nearly) the same number of
+    // columns per row and no lane idles through another lane's wider band
     c->perm.resize(n);
-    for (uint32_t a = 0; a < n; ++a) {
-        int k = 0;
-        while (h_w[a] > CLASSES[k].wmax) ++k;
-        c->perm[cur[k]++] = a;
+    {
+        uint32_t hist[129];
+        memset(hist, 0, sizeof(hist));
+        for (uint32_t a = 0; a < n; ++a) ++hist[h_w[a] + 1];
+        for (int v = 0; v < 128; ++v) hist[v + 1] += hist[v];                    // hist[w] = first position of band w (classes are contiguous in w)
+        for (uint32_t a = 0; a < n; ++a) c->perm[hist[h_w[a]]++] = a;
     }
+    (void)cur;
     uint64_t z_need = 1;                    // the classes run concurrently: each has its own region of backtrack slabs
     for (int k = 0; k < 5; ++k) {
         c->z_off[k] = z_need;
