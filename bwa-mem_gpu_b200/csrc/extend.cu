@@ -41,11 +41,11 @@ namespace {
 constexpr int N_BINS = 7;
 __constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
 
-constexpr int N_PBINS = 12;              // bins of the column-pair kernel; the first N_KEYED use the 16-bit (score, pair) key
+constexpr int N_PBINS = 16;              // bins of the column-pair kernel; the first N_KEYED use the 16-bit (score, pair) key
 constexpr int N_KEYED = 8;
-__constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 192, 256, 384, 512};
+__constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512};
 constexpr int PAIR_MAX_Q = 512;          // longest query the column-pair kernel stages (shared memory)
-constexpr int PAIR_NT = 64;              // lanes per block of the column-pair kernel
+constexpr int PAIR_NT = 64;              // lanes per block of the column-pair kernel (32 for the long bins, see ext_launch)
 constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
 constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
 
@@ -396,13 +396,12 @@ ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
 }
 
 // ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh)
-template <bool BYTES, bool KEYED>
-__global__ void __launch_bounds__(PAIR_NT)
+template <bool BYTES, bool KEYED, int NT>
+__global__ void __launch_bounds__(NT)
 ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
                 int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
                 int *__restrict__ err_flag)
 {
-    constexpr int NT = PAIR_NT;
     extern __shared__ uint2 smem2[];
     const int tid = threadIdx.x;
     uint2 *const HEp = smem2 + tid;                                                              // HE[p] = HEp[p * NT]
@@ -540,8 +539,9 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
                              (const void *)ext_inter_kernel<true, 64>, (const void *)ext_inter_kernel<false, 64>,
                              (const void *)ext_inter_kernel<true, 32>, (const void *)ext_inter_kernel<false, 32>};
         for (const void *k : ks) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-        const void *kp[4] = {(const void *)ext_pair_kernel<true, true>, (const void *)ext_pair_kernel<true, false>,
-                             (const void *)ext_pair_kernel<false, true>, (const void *)ext_pair_kernel<false, false>};
+        const void *kp[6] = {(const void *)ext_pair_kernel<true, true, 64>, (const void *)ext_pair_kernel<true, false, 64>,
+                             (const void *)ext_pair_kernel<false, true, 64>, (const void *)ext_pair_kernel<false, false, 64>,
+                             (const void *)ext_pair_kernel<true, false, 32>, (const void *)ext_pair_kernel<false, false, 32>};
         for (const void *k : kp) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
     }
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
@@ -610,10 +610,11 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
     static const char *bin_name[N_BINS] = {"ext_inter_kernel_q16", "ext_inter_kernel_q32", "ext_inter_kernel_q64", "ext_inter_kernel_q128",
                                            "ext_inter_kernel_q256", "ext_inter_kernel_q512", "ext_inter_kernel_q1024"};
-    static const int pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 192, 256, 384, 512};
+    static const int pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512};
     static const char *pbin_name[N_PBINS] = {"ext_pair_kernel_q16", "ext_pair_kernel_q32", "ext_pair_kernel_q48", "ext_pair_kernel_q64",
                                              "ext_pair_kernel_q80", "ext_pair_kernel_q96", "ext_pair_kernel_q112", "ext_pair_kernel_q128",
-                                             "ext_pair_kernel_q192", "ext_pair_kernel_q256", "ext_pair_kernel_q384", "ext_pair_kernel_q512"};
+                                             "ext_pair_kernel_q160", "ext_pair_kernel_q192", "ext_pair_kernel_q224", "ext_pair_kernel_q256",
+                                             "ext_pair_kernel_q320", "ext_pair_kernel_q384", "ext_pair_kernel_q448", "ext_pair_kernel_q512"};
     // Bins are independent: outside profiling they go to side streams (forked from and joined to e->stream with
     // events), so that the tail of one bin -- a few long jobs on a few SMs -- overlaps the next bins.
     const bool fan = e->prof == nullptr && e->n_side > 0;
@@ -626,19 +627,36 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     // column-pair s16x2 kernel, longest bins first
     for (int b = N_PBINS - 1; b >= 0 && simd_ok; --b) {
         const int L = pbin_hi[b];
-        const size_t smem = ((size_t)(L / 2 + 1) * 8 + (size_t)((L + 3) / 4 + 1) * 4) * PAIR_NT;
-        if (smem > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
-        auto kern = b < N_KEYED ? ext_pair_kernel<BYTES, true> : ext_pair_kernel<BYTES, false>;
-        int occ = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PAIR_NT, smem));
+        // The column state of a lane lives in shared memory, so the longest query of a bin bounds the resident lanes per SM.  Blocks
+        // of 64 lanes waste up to 63 lanes' worth of it on the long bins; there, blocks of 32 lanes fit more lanes (q384: 96 vs 64).
+        const size_t per_lane = (size_t)(L / 2 + 1) * 8 + (size_t)((L + 3) / 4 + 1) * 4;
+        if (per_lane * 32 > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
+        int occ64 = 0, occ32 = 0;
+        if (b < N_KEYED) {
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ext_pair_kernel<BYTES, true, 64>, 64, per_lane * 64));
+        } else {
+            if (per_lane * 64 <= (size_t)e->smem_optin) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ext_pair_kernel<BYTES, false, 64>, 64, per_lane * 64));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, ext_pair_kernel<BYTES, false, 32>, 32, per_lane * 32));
+        }
+        const bool use32 = occ32 * 32 > occ64 * 64;
+        const int nt = use32 ? 32 : 64;
+        int occ = use32 ? occ32 : occ64;
         if (occ < 1) occ = 1;
-        uint32_t max_blocks = (n + PAIR_NT - 1) / PAIR_NT;
+        const size_t smem = per_lane * nt;
+        uint32_t max_blocks = (n + nt - 1) / nt;
         uint32_t grid = (uint32_t)(e->n_sm * occ);
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
         cudaStream_t st = bin_stream();
-        B200_LAUNCH(e->prof, pbin_name[b], st,
-            (kern<<<grid, PAIR_NT, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        if (b < N_KEYED)
+            B200_LAUNCH(e->prof, pbin_name[b], st,
+                (ext_pair_kernel<BYTES, true, 64><<<grid, 64, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        else if (use32)
+            B200_LAUNCH(e->prof, pbin_name[b], st,
+                (ext_pair_kernel<BYTES, false, 32><<<grid, 32, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        else
+            B200_LAUNCH(e->prof, pbin_name[b], st,
+                (ext_pair_kernel<BYTES, false, 64><<<grid, 64, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     // 32-bit kernel for everything else
