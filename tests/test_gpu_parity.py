@@ -254,6 +254,10 @@ def test_extension_device_packed_path(gpu, oracle):
     import torch
     kw = dict(w=100, zdrop=100)
     jobs = synth.make_ext_jobs(3000, w=100, seed=41, qlen_range=(1, 200), h0_range=(1, 150))
+    longj = synth.make_ext_jobs(60, w=100, seed=42, qlen_range=(1030, 1600), h0_range=(1, 150))      # one-warp-per-job kernel, packed input
+    jobs = {k: np.concatenate([jobs[k], longj[k]]) for k in ("qseq", "tseq", "qlen", "tlen", "h0")} | \
+           {"qoff": np.concatenate([jobs["qoff"], longj["qoff"] + np.uint32(jobs["qseq"].size)]).astype(np.uint32),
+            "toff": np.concatenate([jobs["toff"], longj["toff"] + np.uint32(jobs["tseq"].size)]).astype(np.uint32)}
     want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
     ex = gpu.Extender(0)
     dq = torch.from_numpy(jobs["qseq"]).cuda()
@@ -263,8 +267,8 @@ def test_extension_device_packed_path(gpu, oracle):
     ex.pack_device(dq.data_ptr(), dq.numel(), qp.data_ptr())
     ex.pack_device(dt.data_ptr(), dt.numel(), tp.data_ptr())
     dev = {k: torch.from_numpy(jobs[k].view(np.int32)).cuda() for k in ("qoff", "toff", "qlen", "tlen", "h0")}
-    out = torch.zeros(3000 * 6, dtype=torch.int32, device="cuda")
-    ex.extend_device(gpu.ext_params(**kw), 3000, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(),
+    out = torch.zeros(3060 * 6, dtype=torch.int32, device="cuda")
+    ex.extend_device(gpu.ext_params(**kw), 3060, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(),
                      tp.data_ptr(), dev["toff"].data_ptr(), dev["tlen"].data_ptr(), dev["h0"].data_ptr(), out.data_ptr())
     ex.wait()
     assert (out.cpu().numpy().reshape(-1, 6) == want).all()

@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  env $cfg timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/try.err | python -c "
+  env $cfg timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-chain 2>gpurun_out/try.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['sub_metrics']['kernel_ms']
