@@ -24,7 +24,7 @@
 //                      prefix scan F(j+1) = max(F(j) - e_ins, max(M(j) - oe_ins, 0)), done with warp shuffles
 //                      (5 steps per 32 columns) and carried from chunk to chunk.  int32 throughout, {H, E} per
 //                      column in a per-warp slab in global memory (coalesced 256-byte rows), so there is no
-//                      length limit other than the slab size (BWA_B200_EXT_INTRA_MAX_Q, default 32768 bases).
+//                      length limit other than the slab size (BWA_B200_EXT_INTRA_MAX_Q, default 16384 bases).
 //   Jobs are sorted by (class, query length) on the device and launched per length bin, so lanes
 //   of a warp run similar trip counts and each bin gets exactly the shared memory its longest
 //   query needs.
@@ -522,9 +522,16 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 2) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
-    e->intra_max_q = getenv("BWA_B200_EXT_INTRA_MAX_Q") ? atoi(getenv("BWA_B200_EXT_INTRA_MAX_Q")) : 32768;
+    e->intra_max_q = getenv("BWA_B200_EXT_INTRA_MAX_Q") ? atoi(getenv("BWA_B200_EXT_INTRA_MAX_Q")) : 16384;
     if (e->intra_max_q < 1024) e->intra_max_q = 1024;
-    e->intra_grid = e->n_sm;
+    {   // a warp's row is one dependent chain of 32-column chunks (loads, scan, carries): with 4 warps per SM the kernel issued 17 % of
+        // the time (ncu, profiles/r01_ncu_full_intra_v9.txt); 24 resident warps per SM hide most of that latency
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ext_intra_kernel<true>, INTRA_WARPS * 32, 0));
+        if (occ < 1) occ = 1;
+        if (occ > 6) occ = 6;
+        e->intra_grid = e->n_sm * occ;
+    }
     B200_CUDA(cudaMalloc(&e->d_intra, (size_t)e->intra_grid * INTRA_WARPS * ((size_t)e->intra_max_q + 1) * sizeof(int2)));
     B200_CUDA(cudaMemset(e->d_cells, 0, 8));
     B200_CUDA(cudaMemset(e->d_err, 0, 4));

@@ -43,10 +43,12 @@ def main():
     ex = pkg.Extender(0)
     st = torch.cuda.ExternalStream(ex.stream)
     base_n = 1 << 14
-    for qlen in (100, 150, 200, 250, 300):
-        for w in (16, 32, 50, 64, 100):
-            base = synth.make_ext_jobs(base_n, w=w, seed=777 + qlen + w, qlen_range=(qlen, qlen), h0_range=(19, 150))
-            t = args.jobs // base_n
+    points = [(q, w, base_n, args.jobs) for q in (100, 150, 200, 250, 300) for w in (16, 32, 50, 64, 100)]
+    points += [(2000, 100, 512, 8192), (10000, 100, 128, 2048)]          # long reads: one job per warp (ext_intra_kernel)
+    for qlen, w, bn, total in points:
+        if True:
+            base = synth.make_ext_jobs(bn, w=w, seed=777 + qlen + w, qlen_range=(qlen, qlen), h0_range=(19, 150))
+            t = total // bn
             jobs = {k: np.tile(base[k], t) for k in ("qseq", "tseq", "qlen", "tlen", "h0")}
             jobs["qoff"] = np.concatenate([base["qoff"] + np.uint32(r * base["qseq"].size) for r in range(t)]).astype(np.uint32)
             jobs["toff"] = np.concatenate([base["toff"] + np.uint32(r * base["tseq"].size) for r in range(t)]).astype(np.uint32)
