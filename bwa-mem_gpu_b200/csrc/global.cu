@@ -117,22 +117,20 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
                     const uint32_t qc = (qw >> (28 - 4 * (j & 7))) & 15u;
                     int2 *p = &eh[j & (R - 1)][tid];
                     const int2 pe = *p;
-                    int32_t m = pe.x + (int)(__byte_perm(mlo, mhi, qc) & 0xffu) - bias, e = pe.y, h, tt;
+                    // max with the "first operand wins ties" predicate in one DPX instruction (VIMNMX with predicate output)
+                    int32_t m = pe.x + (int)(__byte_perm(mlo, mhi, qc) & 0xffu) - bias, e = pe.y, h;
+                    bool m_ge_e, h_ge_f, t_ge_e, t_ge_f;
                     uint32_t d;
-                    d = m >= e ? 0u : 1u;
-                    h = m >= e ? m : e;
-                    d = h >= f ? d : 2u;
-                    h = h >= f ? h : f;
-                    tt = m - oe_del;
-                    e -= a.e_del;
-                    d |= e > tt ? 4u : 0u;
-                    e = e > tt ? e : tt;
+                    h = __vibmax_s32(m, e, &m_ge_e);
+                    d = m_ge_e ? 0u : 1u;
+                    h = __vibmax_s32(h, f, &h_ge_f);
+                    d = h_ge_f ? d : 2u;
+                    e = __vibmax_s32(m - oe_del, e - a.e_del, &t_ge_e);       // E(i+1,j); extension wins only when strictly larger
+                    d |= t_ge_e ? 0u : 4u;
                     *p = make_int2(h1, e);
                     h1 = h;
-                    tt = m - oe_ins;
-                    f -= a.e_ins;
-                    d |= f > tt ? 8u : 0u;
-                    f = f > tt ? f : tt;
+                    f = __vibmax_s32(m - oe_ins, f - a.e_ins, &t_ge_f);
+                    d |= t_ge_f ? 0u : 8u;
                     zw |= d << (4 * (c & 7));
                 }
                 if ((c & 7) == 7) { zrow[(c >> 3) * 32] = zw; zw = 0; }

@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box visit (round 1, pass 7 (final of round 1)): every GPU parity test, smoke, bench (both arms), ncu launch list of one bench run,
+# ncu --set full of the re-seeding and CIGAR kernels.  Outputs in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+nproc >> gpurun_out/gpu.txt; lscpu | grep -E 'Model name|^CPU\(s\)' >> gpurun_out/gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+tail -3 gpurun_out/smoke.log
+STEPS=${STEPS:-10}
+timeout 1500 python bench.py --steps $STEPS --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -c 2500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "${REF:-1}" = 1 ]; then
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
+fi
+if [ "${NCU:-1}" = 1 ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "ncu list rc=$?"
+fi
+ls -la gpurun_out/
