@@ -306,7 +306,7 @@ def run_cigar(args, pkg, flush):
     for _ in range(3):
         got = cg.global_host(jobs, ep)
     e2e_s = (time.perf_counter() - t0) / 3
-    kms = sum(v for k, v in kt.items() if k.startswith("global_kernel"))
+    kms = sum(v for k, v in kt.items() if k.startswith("global_"))
     res = {"jobs": n, "ms_per_batch": ms, "jobs_per_s": n / (ms / 1e3), "cells": int(cells), "GCUPS": cells / (kms / 1e3) / 1e9 if kms else None,
            "kernel_ms": kt, "e2e_jobs_per_s": n / e2e_s, "gpu_launches": int(launches), "cigar_ops": int(got["cigar"].size),
            "workload": "262144 jobs (65536 distinct, tiled 4 x), 150 bp queries, 3% substitutions, 1% indels of 1-4 bases, band |tlen - qlen| + 3"}

@@ -186,6 +186,185 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
     if (lane == 0 && cells) atomicAdd(a.counters, cells);
 }
 
+// global_band_kernel<W, BLOCK>: the same recurrence for the narrow bands (w <= W, W = 7 or 15 -- almost every job of a read-length
+// workload), with the column state in REGISTERS.  In band coordinates c = j - i + w a row's columns are c = 0 .. 2w whatever the row:
+// the diagonal neighbour (i-1, j-1) has the same c, the upper one (i-1, j) has c + 1, so {H(i-1, .), E(i, .)} are two register arrays
+// updated in place by a fully unrolled loop over c -- no shared-memory ring, no index arithmetic; the 4-bit query codes of the
+// row's window sit in a 2 x 64-bit shift register that moves one base per row.  Out-of-range cells (j < 0, j >= qlen) are
+// predicated off and leave the arrays as the reference leaves eh[]; the first-column boundary -(o_del + e_del (i+1)) is planted
+// where the next row reads its diagonal.  Backtrack state is indexed by c.
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+global_band_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t tlen_max, uint32_t qw_max, uint32_t tw_max, uint32_t *__restrict__ z_all)
+{
+    extern __shared__ int2 eh_ring[];                       // only the staged sequences here: query [qw_max][BLOCK], target [tw_max][BLOCK]
+    __shared__ uint32_t smat_lo[5], smat_hi[5];
+    __shared__ int s_bias;
+    constexpr int NC = 2 * W + 1, WPR = (NC + 7) / 8;
+    uint32_t *const qs = reinterpret_cast<uint32_t *>(eh_ring) + threadIdx.x;
+    uint32_t *const ts = qs + (size_t)qw_max * BLOCK;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (tid == 0) {
+        int mn = 0;
+        for (int i = 0; i < 25; ++i) mn = mn < a.mat[i] ? mn : a.mat[i];
+        s_bias = -mn;
+        for (int t = 0; t < 5; ++t) {
+            uint32_t lo = 0;
+            for (int q = 0; q < 4; ++q) lo |= (uint32_t)(uint8_t)(a.mat[t * 5 + q] - mn) << (8 * q);
+            smat_lo[t] = lo; smat_hi[t] = (uint32_t)(uint8_t)(a.mat[t * 5 + 4] - mn);
+        }
+    }
+    __syncthreads();
+    const int bias = s_bias;
+    const uint32_t gwarp = blockIdx.x * (BLOCK / 32) + (tid >> 5), n_warps = gridDim.x * (BLOCK / 32);
+    uint32_t *const z = z_all + (uint64_t)gwarp * tlen_max * WPR * 32;
+    const int oe_del = a.o_del + a.e_del, oe_ins = a.o_ins + a.e_ins;
+    unsigned long long cells = 0;
+
+    for (uint32_t chunk = gwarp; (uint64_t)chunk * 32 < n; chunk += n_warps) {
+        const uint32_t idx = chunk * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t job = valid ? perm[idx] : 0u;
+        const int qlen = valid ? (int)a.qlen[job] : 0, tlen = valid ? (int)a.tlen[job] : 0, w = valid ? (int)a.w[job] : 0;
+        const uint8_t *q = a.qseq + (valid ? a.qoff[job] : 0u), *t = a.tseq + (valid ? a.toff[job] : 0u);
+        for (int j8 = 0; j8 < qlen; j8 += 8) {
+            uint32_t wv = 0;
+            for (int u = 0; u < 8; ++u) { const uint32_t c = j8 + u < qlen ? q[j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+            qs[(j8 >> 3) * BLOCK] = wv;
+        }
+        for (int i8 = 0; i8 < tlen; i8 += 8) {
+            uint32_t wv = 0;
+            for (int u = 0; u < 8; ++u) { const uint32_t c = i8 + u < tlen ? t[i8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+            ts[(i8 >> 3) * BLOCK] = wv;
+        }
+        auto qcode = [&](int j) -> uint32_t { return (qs[(j >> 3) * BLOCK] >> (28 - 4 * (j & 7))) & 15u; };
+        // first row of the reference (src/ksw.c:1141-1147) in band coordinates: row 0 reads H(-1, j-1) at c = j + w
+        int32_t B[NC], E[NC + 1];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { const int j = c - w; B[c] = j == 0 ? 0 : (j > 0 && j <= w ? -(a.o_ins + a.e_ins * j) : MINF); E[c] = MINF; }
+        E[NC] = MINF;
+        // query window: code of column c at bits 4c of {qlo, qhi}; row 0 holds j = 0 .. w at c = w .. 2w
+        uint64_t qlo = 0, qhi = 0;
+        for (int j = 0; j <= w && j < qlen; ++j) {
+            const int c = j + w;
+            if (c < 16) qlo |= (uint64_t)qcode(j) << (4 * c); else qhi |= (uint64_t)qcode(j) << (4 * (c - 16));
+        }
+        int warp_tl = tlen, warp_w = w;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            warp_tl = max(warp_tl, __shfl_xor_sync(0xffffffffu, warp_tl, o));
+            warp_w = max(warp_w, __shfl_xor_sync(0xffffffffu, warp_w, o));
+        }
+        uint32_t tword = 0;
+        for (int i = 0; i < warp_tl; ++i) {
+            const bool act = i < tlen;
+            const int cbeg = w - i > 0 ? w - i : 0;                               // j >= 0
+            int cend = qlen - i + w < 2 * w + 1 ? qlen - i + w : 2 * w + 1;        // j < qlen, c <= 2w
+            if (!act || cend < cbeg) cend = cbeg;
+            if ((i & 7) == 0 && act) tword = ts[(i >> 3) * BLOCK];
+            const int tb = act ? (int)((tword >> (28 - 4 * (i & 7))) & 15u) : 4;
+            const uint32_t mlo = smat_lo[tb], mhi = smat_hi[tb];
+            int32_t f = MINF;
+            uint32_t zw[WPR];
+#pragma unroll
+            for (int k = 0; k < WPR; ++k) zw[k] = 0;
+            const int warp_nc = 2 * warp_w + 1;          // jobs are ordered by band width: a warp's lanes agree on it (almost) always
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c >= warp_nc) break;                 // warp-uniform: the unrolled cells beyond the warp's band are skipped, not predicated
+                if (c >= cbeg && c < cend) {
+                    const uint32_t qc = c < 16 ? (uint32_t)(qlo >> (4 * c)) & 15u : (uint32_t)(qhi >> (4 * (c - 16))) & 15u;
+                    const int32_t m = B[c] + (int)(__byte_perm(mlo, mhi, qc) & 0xffu) - bias;
+                    bool m_ge_e, h_ge_f, t_ge_e, t_ge_f;
+                    int32_t h = __vibmax_s32(m, E[c + 1], &m_ge_e);
+                    uint32_t d = m_ge_e ? 0u : 1u;
+                    h = __vibmax_s32(h, f, &h_ge_f);
+                    d = h_ge_f ? d : 2u;
+                    E[c] = __vibmax_s32(m - oe_del, E[c + 1] - a.e_del, &t_ge_e);
+                    d |= t_ge_e ? 0u : 4u;
+                    f = __vibmax_s32(m - oe_ins, f - a.e_ins, &t_ge_f);
+                    d |= t_ge_f ? 0u : 8u;
+                    B[c] = h;
+                    zw[c >> 3] |= d << (4 * (c & 7));
+                }
+            }
+            // the reference ends a row with eh[end] = {H(i, end-1), MINUS_INF}: the E read by the next row's new last column
+            // (c = 2w there) is E[2w+1], never written, MINUS_INF; a row that stops at qlen needs nothing
+            uint32_t *zrow = z + (uint64_t)i * WPR * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < WPR; ++k) zrow[k * 32] = zw[k];
+            cells += (unsigned long long)(cend - cbeg);
+            if (i < warp_w) {
+                // first-column boundary: the next row's column j = 0 (c = w - i - 1) reads H(i, -1) = -(o_del + e_del (i + 1)) as its diagonal
+                const int cb = w - i - 1;
+                const int32_t bnd = -(a.o_del + a.e_del * (i + 1));
+#pragma unroll
+                for (int c = 0; c < W; ++c) if (act && c == cb) B[c] = bnd;
+            }
+            // the window moves one base: column c takes the code of c + 1, the new base j = i + 1 + w enters at c = 2w
+            qlo = (qlo >> 4) | (qhi << 60); qhi >>= 4;
+            {
+                const int jn = i + 1 + w;
+                if (act && jn < qlen) {
+                    const uint64_t code = qcode(jn);
+                    const int c = 2 * w;
+                    if (c < 16) qlo |= code << (4 * c); else qhi |= code << (4 * (c - 16));
+                }
+            }
+        }
+        if (!valid) continue;
+        // score = eh[qlen].h = H(tlen-1, qlen-1) when the last row reaches column qlen - 1 and is not past it (see global_kernel)
+        int32_t score;
+        if (tlen == 0) score = qlen == 0 ? 0 : (qlen <= w ? -(a.o_ins + a.e_ins * qlen) : MINF);
+        else if (qlen == 0) score = tlen - 1 <= w ? -(a.o_del + a.e_del * tlen) : MINF;     // no column at all: eh[0].h of the last row
+        else if (tlen + w < qlen || tlen > qlen + w) score = MINF;
+        else {
+            const int cs = qlen - tlen + w;
+            score = MINF;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) if (c == cs) score = B[c];
+        }
+        // backtrack (src/ksw.c:1208-1231), cells addressed by c = k - i + w
+        int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+        uint32_t which = 0, n_ops = 0, cur_op = 0, cur_len = 0, nmm = 0, gap = 0, edge_del = 0;
+        uint32_t *row = a.rows + (uint64_t)job * a.cig_stride;
+        auto flush = [&]() {
+            if (cur_len == 0) return;
+            if (n_ops < a.cig_stride) row[a.cig_stride - 1 - n_ops] = cur_len << 4 | cur_op;
+            if (cur_op) gap += cur_len;
+            if (cur_op == 2 && n_ops == 0) edge_del += cur_len;
+            ++n_ops;
+        };
+        auto push = [&](uint32_t op, uint32_t len) {
+            if (cur_len && op == cur_op) cur_len += len;
+            else { flush(); cur_op = op; cur_len = len; }
+        };
+        while (i >= 0 && k >= 0) {
+            int c = k - i + w;
+            c = c < 0 ? 0 : (c > NC - 1 ? NC - 1 : c);
+            const uint32_t code = (z[((uint64_t)i * WPR + (c >> 3)) * 32 + lane] >> (4 * (c & 7))) & 15u;
+            which = which == 0 ? (code & 3u) : (which == 1 ? ((code >> 2) & 1u) : ((code >> 3) & 1u) * 2u);
+            if (which == 0) {
+                const uint32_t qc = qcode(k), tc = (ts[(i >> 3) * BLOCK] >> (28 - 4 * (i & 7))) & 15u;
+                nmm += qc != tc; push(0, 1); --i; --k;
+            }
+            else if (which == 1) { push(2, 1); --i; }
+            else { push(1, 1); --k; }
+        }
+        if (i >= 0) push(2, (uint32_t)(i + 1));
+        if (k >= 0) push(1, (uint32_t)(k + 1));
+        if (cur_len && cur_op == 2 && n_ops > 0) edge_del += cur_len;
+        flush();
+        a.score[job] = score;
+        a.n_cigar[job] = n_ops;
+        a.nm[job] = (int32_t)(nmm + gap - edge_del);
+        if (n_ops > a.cig_stride) atomicMax(a.counters + 1, (unsigned long long)n_ops);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if (lane == 0 && cells) atomicAdd(a.counters, cells);
+}
+
 __global__ void __launch_bounds__(128)
 compact_kernel(uint32_t n, const uint32_t *__restrict__ n_cigar, const uint64_t *__restrict__ off, const uint32_t *__restrict__ rows,
                uint32_t stride, uint32_t *__restrict__ flat)
@@ -245,6 +424,7 @@ struct bwa_b200_cigar {
     uint32_t *r_packed = nullptr; uint64_t r_packed_cap = 0; uint64_t *r_woff = nullptr; uint64_t r_woff_cap = 0;
     void *r_jobs = nullptr; uint64_t r_jobs_cap = 0;
     int smem_optin = 0;
+    bool use_band = true;
     uint64_t z_off[5] = {};
     uint64_t last_n = 0, last_ops = 0, last_cells = 0, launches = 0;
     b200::Prof prof; int profiling = 0;
@@ -319,6 +499,31 @@ template <int R, int BLOCK> static size_t class_smem(const bwa_b200_cigar *c, in
 {
     return (size_t)R * BLOCK * sizeof(int2) + ((size_t)(c->cls_ql[cls] + 7) / 8 + (size_t)(c->cls_tl[cls] + 7) / 8) * BLOCK * 4;
 }
+// the register-resident kernel of the two narrow classes needs the staged sequences only
+template <int BLOCK> static size_t band_smem(const bwa_b200_cigar *c, int cls)
+{
+    return ((size_t)(c->cls_ql[cls] + 7) / 8 + (size_t)(c->cls_tl[cls] + 7) / 8) * BLOCK * 4;
+}
+template <int W, int BLOCK> static int band_grid(int n_sm, size_t smem, int *grid)
+{
+    int occ = 0;
+    B200_CUDA(cudaFuncSetAttribute(global_band_kernel<W, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, global_band_kernel<W, BLOCK>, BLOCK, smem));
+    if (occ < 1) occ = 1;
+    if (occ * (BLOCK / 32) > 24) occ = std::max(1, 24 / (BLOCK / 32));
+    *grid = n_sm * occ;
+    return BWA_B200_OK;
+}
+template <int W, int BLOCK>
+static void launch_band(bwa_b200_cigar *c, const GArgs &ga, int cls, uint32_t first, const char *name)
+{
+    b200::Prof *prof = c->profiling ? &c->prof : nullptr;
+    cudaStream_t st = prof ? c->stream : c->side[cls];
+    B200_LAUNCH(prof, name, st,
+        (global_band_kernel<W, BLOCK><<<c->grid[cls], BLOCK, band_smem<BLOCK>(c, cls), st>>>(ga, c->d_perm + first, c->cls_n[cls], c->cls_tl[cls],
+                                                                                            (c->cls_ql[cls] + 7) / 8, (c->cls_tl[cls] + 7) / 8, c->d_z + c->z_off[cls])));
+    ++c->launches;
+}
 template <int R, int BLOCK>
 static void launch_class(bwa_b200_cigar *c, const GArgs &ga, int cls, uint32_t first, const char *name)
 {
@@ -351,12 +556,16 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
     uint32_t first[6] = {0, 0, 0, 0, 0, 0}, cur[5];
     for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; cur[k] = first[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; c->cls_ql[k] = ql[k] ? ql[k] : 1; }
     {   // shared memory of a class = ring + its longest query and target; the grid follows from the occupancy at that size
-        const size_t sm[5] = {class_smem<16, 128>(c, 0), class_smem<32, 128>(c, 1), class_smem<64, 64>(c, 2), class_smem<128, 32>(c, 3), class_smem<256, 32>(c, 4)};
+        // w <= 15: column state in registers (global_band_kernel); BWA_B200_GLOBAL_RING=1 sends those classes through the shared-memory
+        // ring kernel as well (tests run both)
+        c->use_band = getenv("BWA_B200_GLOBAL_RING") == nullptr;
+        const size_t sm[5] = {c->use_band ? band_smem<128>(c, 0) : class_smem<16, 128>(c, 0), c->use_band ? band_smem<128>(c, 1) : class_smem<32, 128>(c, 1),
+                              class_smem<64, 64>(c, 2), class_smem<128, 32>(c, 3), class_smem<256, 32>(c, 4)};
         for (int k = 0; k < 5; ++k)
             if (cnt[k] && sm[k] > (size_t)c->smem_optin) { b200::set_error("global: sequences of %u / %u bases in band class %d do not fit shared memory", ql[k], tl[k], k); return BWA_B200_ERR_CAPACITY; }
         int rc = 0;
-        if (cnt[0]) rc |= class_grid<16, 128>(c->n_sm, sm[0], &c->grid[0]);
-        if (cnt[1]) rc |= class_grid<32, 128>(c->n_sm, sm[1], &c->grid[1]);
+        if (cnt[0]) rc |= c->use_band ? band_grid<7, 128>(c->n_sm, sm[0], &c->grid[0]) : class_grid<16, 128>(c->n_sm, sm[0], &c->grid[0]);
+        if (cnt[1]) rc |= c->use_band ? band_grid<15, 128>(c->n_sm, sm[1], &c->grid[1]) : class_grid<32, 128>(c->n_sm, sm[1], &c->grid[1]);
         if (cnt[2]) rc |= class_grid<64, 64>(c->n_sm, sm[2], &c->grid[2]);
         if (cnt[3]) rc |= class_grid<128, 32>(c->n_sm, sm[3], &c->grid[3]);
         if (cnt[4]) rc |= class_grid<256, 32>(c->n_sm, sm[4], &c->grid[4]);
@@ -405,8 +614,8 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
             B200_CUDA(cudaEventRecord(c->ev_fork, st));
             for (int k = 0; k < 5; ++k) if (cnt[k]) B200_CUDA(cudaStreamWaitEvent(c->side[k], c->ev_fork, 0));
         }
-        if (cnt[0]) launch_class<16, 128>(c, ga, 0, first[0], "global_kernel_w7");
-        if (cnt[1]) launch_class<32, 128>(c, ga, 1, first[1], "global_kernel_w15");
+        if (cnt[0]) { if (c->use_band) launch_band<7, 128>(c, ga, 0, first[0], "global_band_kernel_w7"); else launch_class<16, 128>(c, ga, 0, first[0], "global_kernel_w7"); }
+        if (cnt[1]) { if (c->use_band) launch_band<15, 128>(c, ga, 1, first[1], "global_band_kernel_w15"); else launch_class<32, 128>(c, ga, 1, first[1], "global_kernel_w15"); }
         if (cnt[2]) launch_class<64, 64>(c, ga, 2, first[2], "global_kernel_w31");
         if (cnt[3]) launch_class<128, 32>(c, ga, 3, first[3], "global_kernel_w63");
         if (cnt[4]) launch_class<256, 32>(c, ga, 4, first[4], "global_kernel_w127");

@@ -171,3 +171,14 @@ def test_reg2aln_matches_oracle_and_fork_golden(gpu, oracle, tmp_path):
         cg.reg2aln_host(idx, ctg.off, packed, woff, rl, bad, gpu.ext_params(), 1)
     cg.destroy()
     idx.free()
+
+
+def test_global_ring_kernel_on_narrow_bands(gpu, oracle, monkeypatch):
+    """bands up to 15 normally run in the register-resident kernel; the shared-memory ring kernel (the one wider bands use) must give
+    the same answers on them"""
+    monkeypatch.setenv("BWA_B200_GLOBAL_RING", "1")
+    cg = gpu.Cigar(0)
+    compare(gpu, oracle, cg, synth.make_global_jobs(8000, qlen_range=(1, 150), seed=601))
+    compare(gpu, oracle, cg, synth.make_global_jobs(3000, qlen_range=(60, 250), seed=602, sub_rate=0.1, indel_rate=0.04, w_extra=(0, 12), w_cap=15),
+            dict(a=2, b=3, o_del=4, e_del=2, o_ins=5, e_ins=1))
+    cg.destroy()
