@@ -280,7 +280,7 @@ def run_cigar(args, pkg, flush):
 
     def step():
         cg.global_device(ep, n, dev["qseq"].data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(), dev["tseq"].data_ptr(), dev["toff"].data_ptr(),
-                         dev["tlen"].data_ptr(), jobs["qlen"], jobs["tlen"], jobs["w"])
+                         dev["tlen"].data_ptr(), jobs["qlen"], jobs["tlen"], jobs["w"], aligned8=True)      # make_global_jobs pads to 8
 
     for _ in range(3):
         step()

@@ -244,7 +244,7 @@ def lib():
         L.bwa_b200_cigar_band.argtypes = [C.POINTER(ExtParams), C.c_int, C.c_int, C.c_int64]
         L.bwa_b200_global_host.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.POINTER(Cigars)]
         L.bwa_b200_cigars_free.argtypes = [C.POINTER(Cigars)]
-        L.bwa_b200_global_device.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.bwa_b200_global_device.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.bwa_b200_global_device_view.argtypes = [vp, C.POINTER(Cigars)]
         L.bwa_b200_cigar_stream.argtypes = [vp]
         L.bwa_b200_cigar_stream.restype = vp
@@ -649,8 +649,9 @@ class Cigar:
         C.CDLL(None).free(cig)
         return out, flat
 
-    def global_device(self, ext_p, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_qlen, h_tlen, h_w):
-        check(lib().bwa_b200_global_device(self.h, C.byref(ext_p), n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, _p(h_qlen), _p(h_tlen), _p(h_w)))
+    def global_device(self, ext_p, n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, h_qlen, h_tlen, h_w, aligned8=False):
+        check(lib().bwa_b200_global_device(self.h, C.byref(ext_p), n, d_qseq, d_qoff, d_qlen, d_tseq, d_toff, d_tlen, _p(h_qlen), _p(h_tlen), _p(h_w),
+                                           int(aligned8)))
 
     def view(self) -> Cigars:
         v = Cigars()

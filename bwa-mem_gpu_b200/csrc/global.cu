@@ -33,8 +33,36 @@ struct GArgs {
     int32_t *score, *nm;
     uint32_t *n_cigar, *rows;               // rows: cig_stride operations per job, right-aligned
     uint32_t cig_stride;
+    uint32_t aligned8;                      // every sequence starts on an 8-byte boundary and is padded to a multiple of 8
     unsigned long long *counters;           // [0] cells, [1] widest CIGAR row needed
 };
+
+// stage a byte-per-base sequence into shared memory as 4-bit codes, 8 per word, first base in the high nibble, words `stride` apart.
+// aligned8: the sequence starts on an 8-byte boundary and is padded to a multiple of 8 (the GASAL host layout) -> one 64-bit load per
+// word and SIMD-in-register packing instead of eight byte loads
+__device__ __forceinline__ uint32_t pack8(uint2 v)
+{
+    const uint32_t a = __vminu4(v.x, 0x04040404u), b = __vminu4(v.y, 0x04040404u);     // codes above 4 are read as 4
+    const uint32_t ta = (a << 4) | (a >> 8), tb = (b << 4) | (b >> 8);                  // byte 0 = b0 b1, byte 2 = b2 b3 (nibbles)
+    return (__byte_perm(ta, 0u, 0x4402u) << 16) | __byte_perm(tb, 0u, 0x4402u);
+}
+__device__ __forceinline__ void stage_seq(uint32_t *dst, int stride, const uint8_t *src, int len, bool aligned8)
+{
+    if (aligned8) {
+        const uint2 *s8 = reinterpret_cast<const uint2 *>(src);
+        for (int j8 = 0; j8 < len; j8 += 8) {
+            uint32_t wv = pack8(s8[j8 >> 3]);
+            if (j8 + 8 > len) wv = (wv & ~(0xffffffffu >> (4 * (len - j8)))) | (0x44444444u >> (4 * (len - j8)));   // past the end: code 4
+            dst[(j8 >> 3) * stride] = wv;
+        }
+    } else {
+        for (int j8 = 0; j8 < len; j8 += 8) {
+            uint32_t wv = 0;
+            for (int u = 0; u < 8; ++u) { const uint32_t c = j8 + u < len ? src[j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
+            dst[(j8 >> 3) * stride] = wv;
+        }
+    }
+}
 
 template <int R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
@@ -74,16 +102,8 @@ global_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint32_t t
         const int qlen = valid ? (int)a.qlen[job] : 0, tlen = valid ? (int)a.tlen[job] : 0, w = valid ? (int)a.w[job] : 0;
         const uint8_t *q = a.qseq + (valid ? a.qoff[job] : 0u), *t = a.tseq + (valid ? a.toff[job] : 0u);
         // stage both sequences (codes above 4 are read as 4)
-        for (int j8 = 0; j8 < qlen; j8 += 8) {
-            uint32_t wv = 0;
-            for (int u = 0; u < 8; ++u) { const uint32_t c = j8 + u < qlen ? q[j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
-            qs[(j8 >> 3) * BLOCK] = wv;
-        }
-        for (int i8 = 0; i8 < tlen; i8 += 8) {
-            uint32_t wv = 0;
-            for (int u = 0; u < 8; ++u) { const uint32_t c = i8 + u < tlen ? t[i8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
-            ts[(i8 >> 3) * BLOCK] = wv;
-        }
+        stage_seq(qs, BLOCK, q, qlen, a.aligned8 != 0);
+        stage_seq(ts, BLOCK, t, tlen, a.aligned8 != 0);
         // first row (src/ksw.c:1141-1147); only columns 0 .. min(w + 1, qlen) can be read before they are rewritten
         eh[0][tid] = make_int2(0, MINF);
         {
@@ -227,16 +247,8 @@ global_band_kernel(GArgs a, const uint32_t *__restrict__ perm, uint32_t n, uint3
         const uint32_t job = valid ? perm[idx] : 0u;
         const int qlen = valid ? (int)a.qlen[job] : 0, tlen = valid ? (int)a.tlen[job] : 0, w = valid ? (int)a.w[job] : 0;
         const uint8_t *q = a.qseq + (valid ? a.qoff[job] : 0u), *t = a.tseq + (valid ? a.toff[job] : 0u);
-        for (int j8 = 0; j8 < qlen; j8 += 8) {
-            uint32_t wv = 0;
-            for (int u = 0; u < 8; ++u) { const uint32_t c = j8 + u < qlen ? q[j8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
-            qs[(j8 >> 3) * BLOCK] = wv;
-        }
-        for (int i8 = 0; i8 < tlen; i8 += 8) {
-            uint32_t wv = 0;
-            for (int u = 0; u < 8; ++u) { const uint32_t c = i8 + u < tlen ? t[i8 + u] : 4u; wv |= (c > 4u ? 4u : c) << (28 - 4 * u); }
-            ts[(i8 >> 3) * BLOCK] = wv;
-        }
+        stage_seq(qs, BLOCK, q, qlen, a.aligned8 != 0);
+        stage_seq(ts, BLOCK, t, tlen, a.aligned8 != 0);
         auto qcode = [&](int j) -> uint32_t { return (qs[(j >> 3) * BLOCK] >> (28 - 4 * (j & 7))) & 15u; };
         // first row of the reference (src/ksw.c:1141-1147) in band coordinates: row 0 reads H(-1, j-1) at c = j + w
         int32_t B[NC], E[NC + 1];
@@ -538,7 +550,7 @@ static void launch_class(bwa_b200_cigar *c, const GArgs &ga, int cls, uint32_t f
 // jobs already on the device (byte per base); host copies of tlen and w drive the binning
 static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs, const uint8_t *d_q, const uint32_t *d_qoff,
                      const uint32_t *d_qlen, const uint8_t *d_t, const uint32_t *d_toff, const uint32_t *d_tlen, const uint32_t *d_w,
-                     const uint32_t *h_qlen, const uint32_t *h_tlen, const uint32_t *h_w)
+                     const uint32_t *h_qlen, const uint32_t *h_tlen, const uint32_t *h_w, bool aligned8)
 {
     c->last_n = n_jobs; c->last_ops = 0; c->last_cells = 0;
     if (n_jobs == 0) return BWA_B200_OK;
@@ -607,7 +619,7 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
         ga.qseq = d_q; ga.tseq = d_t; ga.qoff = d_qoff; ga.qlen = d_qlen; ga.toff = d_toff; ga.tlen = d_tlen; ga.w = d_w;
         memcpy(ga.mat, p->mat, 25);
         ga.o_del = p->o_del; ga.e_del = p->e_del; ga.o_ins = p->o_ins; ga.e_ins = p->e_ins;
-        ga.score = c->d_score; ga.nm = c->d_nm; ga.n_cigar = c->d_ncig; ga.rows = c->d_rows; ga.cig_stride = c->cig_stride;
+        ga.score = c->d_score; ga.nm = c->d_nm; ga.n_cigar = c->d_ncig; ga.rows = c->d_rows; ga.cig_stride = c->cig_stride; ga.aligned8 = aligned8 ? 1u : 0u;
         ga.counters = c->d_counters;
         const bool fan = !c->profiling;
         if (fan) {
@@ -647,7 +659,7 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
 extern "C" int bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
                                       const uint8_t *dev_qseq, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
                                       const uint8_t *dev_tseq, const uint32_t *dev_toff, const uint32_t *dev_tlen,
-                                      const uint32_t *host_qlen, const uint32_t *host_tlen, const uint32_t *host_w)
+                                      const uint32_t *host_qlen, const uint32_t *host_tlen, const uint32_t *host_w, int aligned8)
 {
     if (!c || !p || (n_jobs && (!dev_qseq || !dev_qoff || !dev_qlen || !dev_tseq || !dev_toff || !dev_tlen || !host_qlen || !host_tlen || !host_w))) {
         b200::set_error("global_device: bad argument"); return BWA_B200_ERR_ARG;
@@ -657,7 +669,8 @@ extern "C" int bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_pa
         if (grow_dev(c->d_w, c->w_cap, n_jobs)) { b200::set_error("global: out of device memory"); return BWA_B200_ERR_NOMEM; }
         B200_CUDA(cudaMemcpyAsync(c->d_w, host_w, n_jobs * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    return cigar_run(c, p, n_jobs, dev_qseq, dev_qoff, dev_qlen, dev_tseq, dev_toff, dev_tlen, c->d_w, host_qlen, host_tlen, host_w);
+    const bool al = aligned8 != 0 && ((uintptr_t)dev_qseq & 7) == 0 && ((uintptr_t)dev_tseq & 7) == 0;
+    return cigar_run(c, p, n_jobs, dev_qseq, dev_qoff, dev_qlen, dev_tseq, dev_toff, dev_tlen, c->d_w, host_qlen, host_tlen, host_w, al);
 }
 
 extern "C" int bwa_b200_global_device_view(bwa_b200_cigar_t *c, bwa_b200_cigars_t *v)
@@ -685,8 +698,11 @@ extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_para
     memset(out, 0, sizeof(*out));
     out->n_jobs = n_jobs;
     if (n_jobs == 0) return BWA_B200_OK;
-    for (uint64_t a = 0; a < n_jobs; ++a)
+    bool al = true;                        // the GASAL host layout: 8-byte aligned, padded sequences -> 64-bit loads in the kernel
+    for (uint64_t a = 0; a < n_jobs; ++a) {
         if ((uint64_t)qoff[a] + qlen[a] > q_bytes || (uint64_t)toff[a] + tlen[a] > t_bytes) { b200::set_error("global_host: job %llu reaches past its sequence buffer", (unsigned long long)a); return BWA_B200_ERR_ARG; }
+        if ((qoff[a] & 7) || (toff[a] & 7) || (uint64_t)qoff[a] + ((uint64_t)qlen[a] + 7) / 8 * 8 > q_bytes || (uint64_t)toff[a] + ((uint64_t)tlen[a] + 7) / 8 * 8 > t_bytes) al = false;
+    }
     B200_CUDA(cudaSetDevice(c->device));
     int bad = 0;
     bad |= grow_dev(c->d_q, c->q_cap, q_bytes ? q_bytes : 1); bad |= grow_dev(c->d_t, c->t_cap, t_bytes ? t_bytes : 1);
@@ -701,7 +717,7 @@ extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_para
     B200_CUDA(cudaMemcpyAsync(c->d_toff, toff, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_tlen, tlen, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_w, w, n_jobs * 4, cudaMemcpyHostToDevice, st));
-    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, qlen, tlen, w);
+    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, qlen, tlen, w, al);
     if (rc) return rc;
     const uint64_t ops = c->last_ops;
     out->n_ops = ops;
@@ -874,7 +890,7 @@ extern "C" int bwa_b200_reg2aln_host(bwa_b200_cigar_t *c, const bwa_b200_index_t
         B200_CUDA(cudaMemcpyAsync(c->d_toff, h_toff.data(), na * 4, cudaMemcpyHostToDevice, stq));
         B200_CUDA(cudaMemcpyAsync(c->d_tlen, h_tlen.data(), na * 4, cudaMemcpyHostToDevice, stq));
         B200_CUDA(cudaMemcpyAsync(c->d_w, h_w.data(), na * 4, cudaMemcpyHostToDevice, stq));
-        int rc = cigar_run(c, p, na, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, h_qlen.data(), h_tlen.data(), h_w.data());
+        int rc = cigar_run(c, p, na, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, h_qlen.data(), h_tlen.data(), h_w.data(), true);
         if (rc) return rc;
         const uint64_t ops = c->last_ops;
         h_score.resize(na); h_nm.resize(na); h_nc.resize(na); h_off.resize(na); h_flat.resize(ops ? ops : 1);

@@ -291,12 +291,14 @@ int  bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, u
                           const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
                           const uint32_t *w, bwa_b200_cigars_t *out);
 void bwa_b200_cigars_free(bwa_b200_cigars_t *r);
-/* sequences and job tables already in HBM; host copies of qlen, tlen and w drive the band-width binning and the sizing.  Results stay on the
+/* sequences and job tables already in HBM; host copies of qlen, tlen and w drive the band-width binning and the sizing.
+ * aligned8 != 0: the caller guarantees the GASAL layout -- every offset a multiple of 8 and every sequence padded to a multiple of 8
+ * bytes inside its buffer -- so the kernel loads 8 bases at a time (bwa_b200_global_host checks this itself).  Results stay on the
  * device until the next call: bwa_b200_global_device_view synchronises and reports the device pointers. */
 int  bwa_b200_global_device(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
                             const uint8_t *dev_qseq, const uint32_t *dev_qoff, const uint32_t *dev_qlen,
                             const uint8_t *dev_tseq, const uint32_t *dev_toff, const uint32_t *dev_tlen,
-                            const uint32_t *host_qlen, const uint32_t *host_tlen, const uint32_t *host_w);
+                            const uint32_t *host_qlen, const uint32_t *host_tlen, const uint32_t *host_w, int aligned8);
 int  bwa_b200_global_device_view(bwa_b200_cigar_t *c, bwa_b200_cigars_t *dev_view);
 void *bwa_b200_cigar_stream(bwa_b200_cigar_t *c);
 uint64_t bwa_b200_cigar_launches(const bwa_b200_cigar_t *c);
