@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--reads", type=int, default=500_000)
     ap.add_argument("--genome", type=int, default=100_000_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only-long", action="store_true", help="only the long-read extension points")
     args = ap.parse_args()
     pkg = ge.load_package(); pkg.build()
     torch.cuda.set_device(0)
@@ -45,6 +46,8 @@ def main():
     base_n = 1 << 14
     points = [(q, w, base_n, args.jobs) for q in (100, 150, 200, 250, 300) for w in (16, 32, 50, 64, 100)]
     points += [(2000, 100, 512, 8192), (10000, 100, 128, 2048)]          # long reads: one job per warp (ext_intra_kernel)
+    if args.only_long:
+        points = points[-2:]
     for qlen, w, bn, total in points:
         if True:
             base = synth.make_ext_jobs(bn, w=w, seed=777 + qlen + w, qlen_range=(qlen, qlen), h0_range=(19, 150))
@@ -70,6 +73,9 @@ def main():
             print(out["c4_extension"][-1], file=sys.stderr, flush=True)
             del dq, dt, qp, tp, dev, res
     ex.destroy()
+    if args.only_long:
+        print(json.dumps(out))
+        return
     # ---- C5
     cache = os.environ.get("BWA_B200_CACHE", "/tmp/bwa_b200_bench"); os.makedirs(cache, exist_ok=True)
     prefix = os.path.join(cache, f"g{args.genome}_s{synth.GENOME_SEED}")
