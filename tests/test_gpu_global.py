@@ -182,3 +182,42 @@ def test_global_ring_kernel_on_narrow_bands(gpu, oracle, monkeypatch):
     compare(gpu, oracle, cg, synth.make_global_jobs(3000, qlen_range=(60, 250), seed=602, sub_rate=0.1, indel_rate=0.04, w_extra=(0, 12), w_cap=15),
             dict(a=2, b=3, o_del=4, e_del=2, o_ins=5, e_ins=1))
     cg.destroy()
+
+
+def test_align_regions_through_reg2aln(gpu, oracle, small_index):
+    """the two stages composed on real data: regions produced by bwa_b200_align_host (chaining + extension on the device) go through
+    bwa_b200_reg2aln_host; every alignment equals the oracle's mem_reg2aln on the same region"""
+    from oracle import chain_py as CP
+    g, prefix = small_index
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(g)
+    reads, _, _ = synth.make_reads(g, 2000, 150, seed=123, sub_rate=0.03, ins_rate=0.003, del_rate=0.003)
+    n, L = reads.shape
+    packed, woff, rl = gpu.pack_codes(reads.reshape(-1).copy(), (np.arange(n + 1) * L).astype(np.uint64))
+    al = gpu.Aligner(idx, n, packed.size)
+    res = al.align_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.chain_params(w=100), gpu.ext_params(w=100, zdrop=100, use_band=1))
+    al.destroy()
+    regs = res["regions"]
+    read_of = np.repeat(np.arange(n), res["n_regions"])
+    keep = (regs["qe"] > regs["qb"]) & (regs["re"] > regs["rb"])
+    assert keep.sum() > 1500
+    alns = np.zeros(int(keep.sum()), gpu.ALN_IN_DTYPE)
+    alns["read"] = read_of[keep]; alns["qb"] = regs["qb"][keep]; alns["qe"] = regs["qe"][keep]; alns["rb"] = regs["rb"][keep]; alns["re"] = regs["re"][keep]
+    alns["truesc"] = regs["truesc"][keep]; alns["w"] = regs["w"][keep]
+    cg = gpu.Cigar(0)
+    ctg = CP.Contigs((g.size,))
+    got, flat = cg.reg2aln_host(idx, ctg.off, packed, woff, rl, alns, gpu.ext_params(w=100), 1)
+    cg.destroy()
+    idx.free()
+    opt, kp = CP.default_opt(w=100), oracle.make_params()
+    n_gapped = 0
+    for k in range(alns.size):
+        a = alns[k]
+        want, wc = CP.oracle_reg2aln(opt, kp, ctg, g, reads[int(a["read"])], int(a["qb"]), int(a["qe"]), int(a["rb"]), int(a["re"]), int(a["truesc"]), int(a["w"]))
+        o = got[k]
+        mine = flat[int(o["cigar_off"]):int(o["cigar_off"]) + int(o["n_cigar"])]
+        assert (int(o["pos"]), int(o["rid"]), int(o["is_rev"]), int(o["nm"]), int(o["score"]), int(o["n_waves"])) == \
+               (int(want["pos"]), int(want["rid"]), int(want["is_rev"]), int(want["nm"]), int(want["score"]), int(want["n_waves"])), k
+        assert mine.size == wc.size and (mine == wc).all(), k
+        n_gapped += int(((mine & 0xf) == 1).any() or ((mine & 0xf) == 2).any())
+    assert n_gapped > 20          # some alignments do carry indels
