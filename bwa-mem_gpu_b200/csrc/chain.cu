@@ -336,7 +336,7 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
             rc = b200_seeder_finish(a->seeder);            // synchronises; grows and refills the seed arrays on overflow
             if (rc) return rc;
             a->b_seeds = a->seeder->last_total;
-            if (a->seeder->last_total > cap_before && attempt == 0) continue;
+            if ((a->seeder->last_total > cap_before || a->seeder->redone) && attempt == 0) continue;
         }
         B200_CUDA(cudaStreamSynchronize(st));
         break;

@@ -74,6 +74,8 @@ struct bwa_b200_seeder {
     bwa_b200_seed_params_t last_p{19, 500};
     b200::Prof *prof = nullptr;
     bool filled = false;          // fill + locate already enqueued for the current batch
+    bool redone = false;          // b200_seeder_finish had to redo part of the batch (re-seeding rows widened, or seed arrays grown):
+                                  // whatever a caller enqueued behind b200_seeder_run consumed incomplete seeds and must be re-enqueued
     bool narrow_rows = true;      // every BWT row fits 32 bits (seq_len < 2^32) and BWA_B200_WIDE_ROWS is not set
     // pinned staging for the scalar read-backs
     unsigned long long *h_counters = nullptr;

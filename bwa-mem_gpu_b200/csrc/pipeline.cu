@@ -284,7 +284,7 @@ extern "C" int bwa_b200_pipeline_sync(bwa_b200_pipeline_t *p)
     uint64_t cap_before = p->seeder->seed_cap;
     int rc = b200_seeder_finish(p->seeder);
     if (rc) return rc;
-    if (p->seeder->last_total > cap_before) {
+    if (p->seeder->last_total > cap_before || p->seeder->redone) {
         rc = pipe_enqueue(p);
         if (rc) return rc;
         rc = b200_seeder_finish(p->seeder);

@@ -780,8 +780,12 @@ static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max
 
 static int seeder_ensure_reseed(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, uint32_t want_x, uint32_t want_3)
 {
-    uint32_t xs = std::max<uint32_t>(std::max<uint32_t>(24u, max_len / 4), std::max(want_x, s->xstride));
-    uint32_t s3 = std::max<uint32_t>(std::max<uint32_t>(48u, max_len / 2), std::max(want_3, s->stride3));
+    // BWA_B200_RESEED_ROW0 starts the rows at that width instead (tests use a tiny one to drive every caller through the widen-and-redo path)
+    const char *row0 = getenv("BWA_B200_RESEED_ROW0");
+    uint32_t xs = row0 ? (uint32_t)std::max(1, atoi(row0)) : std::max<uint32_t>(24u, max_len / 4);
+    uint32_t s3 = row0 ? (uint32_t)std::max(1, atoi(row0)) : std::max<uint32_t>(48u, max_len / 2);
+    xs = std::max(xs, std::max(want_x, s->xstride));
+    s3 = std::max(s3, std::max(want_3, s->stride3));
     if (n_reads * (uint64_t)xs > s->cand2_cap) {
         if (s->d_cand2) B200_CUDA(cudaFree(s->d_cand2));
         s->d_cand2 = nullptr; s->cand2_cap = 0;
@@ -1020,6 +1024,7 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
 // read the seed total back; if the arrays were too small (or absent) grow them and redo fill+locate
 int b200_seeder_finish(bwa_b200_seeder *s)
 {
+    s->redone = false;
     if (s->last_n_reads == 0) return BWA_B200_OK;
     B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
@@ -1031,12 +1036,13 @@ int b200_seeder_finish(bwa_b200_seeder *s)
         if (rc) return rc;
         rc = seeder_scan(s);
         if (rc) return rc;
-        s->filled = false;
+        s->filled = false; s->redone = true;
         B200_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
         B200_CUDA(cudaStreamSynchronize(s->stream));
     }
     s->last_total = s->h_counters[2];
     if (s->filled && s->last_total <= s->seed_cap) return BWA_B200_OK;
+    s->redone = true;
     int rc = seeder_ensure_out(s, s->last_total);
     if (rc) return rc;
     if (s->last_total) {

@@ -141,6 +141,43 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
     idx.free()
 
 
+def test_align_with_reseeding_rows_overflow(gpu, oracle, small_index, monkeypatch):
+    """tiny initial re-seeding rows: the seeder widens them and redoes its passes inside b200_seeder_finish, after the chaining kernels
+    were already enqueued on incomplete seeds -- the aligner and the fused pipeline must run their part again"""
+    monkeypatch.setenv("BWA_B200_RESEED_ROW0", "3")
+    g, prefix = small_index
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(g)
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    base, _, _ = synth.make_reads(g, 1500, 150, seed=25, sub_rate=0.02, n_rate=0.002)
+    reads = [base[i] for i in range(1500)]
+    rf, off = flat(reads)
+    sd = oi.seed_batch(rf, off, 19, 500, n_threads=4, rs=oracle.reseed())
+    assert sd["n_seeds"].max() > 3
+    ctg = CP.Contigs((g.size,))
+    qq = np.stack([sd["qbeg"], sd["qend"]], axis=1).astype(np.int32)
+    want = CP.oracle_align_batch(CP.default_opt(max_occ=500, w=100), ctg, g, reads, sd["rbeg"], qq, sd["score"], sd["n_seeds"], sd["seed_off"], 0,
+                                 oracle.make_params(w=100, zdrop=100, use_band=1))
+    packed, woff, rl = gpu.pack_codes(rf, off)
+    for _ in range(2):                       # a fresh aligner each time: the first batch of a handle is the one that overflows
+        al = gpu.Aligner(idx, len(reads), packed.size)
+        got = al.align_host(packed, woff, rl, gpu.seed_params(19, 500, True), gpu.chain_params(max_occ=500, w=100),
+                            gpu.ext_params(w=100, zdrop=100, use_band=1), detail=True)
+        check_batch(got, want)
+        al.destroy()
+    # fused pipeline with re-seeding: same records whether the rows overflowed on the way or not
+    pl = gpu.Pipeline(idx, len(reads), packed.size, 150)
+    a = pl.run_host(packed, woff, rl, gpu.seed_params(19, 500, True), gpu.ext_params())
+    pl.destroy()
+    monkeypatch.delenv("BWA_B200_RESEED_ROW0")
+    pl = gpu.Pipeline(idx, len(reads), packed.size, 150)
+    b = pl.run_host(packed, woff, rl, gpu.seed_params(19, 500, True), gpu.ext_params())
+    pl.destroy()
+    assert a.tobytes() == b.tobytes() and (a["n_seeds"] == sd["n_seeds"]).all()
+    oi.close()
+    idx.free()
+
+
 def test_align_rejects_bad_input(gpu, case_index):
     lens, fwd, cases, idx = case_index
     al = gpu.Aligner(idx, 8, 4096)
