@@ -25,6 +25,12 @@ thread_local int t_max_occ = 0;
 
 extern "C" void gpuseed_b200_set_device(int device) { t_device = device; }
 extern "C" void gpuseed_b200_set_max_occ(int max_occ) { t_max_occ = max_occ; }
+thread_local int t_reseed = 0, t_split_width = 10, t_max_mem_intv = 20;
+thread_local float t_split_factor = 1.5f;
+extern "C" void gpuseed_b200_set_reseed(int enable, float split_factor, int split_width, int max_mem_intv)
+{
+    t_reseed = enable != 0; t_split_factor = split_factor; t_split_width = split_width; t_max_mem_intv = max_mem_intv;
+}
 
 extern "C" bwt_t_gpu *bwt_restore_bwt_gpu(const char *fn)
 {
@@ -135,7 +141,7 @@ extern "C" mem_seed_v_gpu *seed_gpu(gpuseed_storage_vector *d)
     char *line = nullptr;
     size_t line_cap = 0;
     bool done = false;
-    bwa_b200_seed_params_t sp{d->min_seed_size, t_max_occ};
+    bwa_b200_seed_params_t sp{d->min_seed_size, t_max_occ, t_reseed, t_split_factor, t_split_width, t_max_mem_intv};
     while (!done) {
         bases.clear(); off.assign(1, 0);
         while (bases.size() < BATCH_BASES) {

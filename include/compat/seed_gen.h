@@ -127,6 +127,10 @@ mem_seed_v_gpu *seed_gpu(gpuseed_storage_vector *gpuseed_data);
  * contributes all of its occurrences. */
 void            gpuseed_b200_set_device(int device);
 void            gpuseed_b200_set_max_occ(int max_occ);
+/* re-seeding for the next seed_gpu on this thread: enable != 0 adds passes 2 and 3 of mem_collect_intv (bwa_index/bwamem.c:132-161), the
+ * seed set of stock bwa mem, lifting the reference's documented limitation (README.md:93); split_factor 1.5, split_width 10,
+ * max_mem_intv 20 are mem_opt_init's.  Default: off, i.e. exactly what GPUSeed returns.  The layout of mem_seed_v_gpu is unchanged. */
+void            gpuseed_b200_set_reseed(int enable, float split_factor, int split_width, int max_mem_intv);
 
 #ifdef __cplusplus
 }

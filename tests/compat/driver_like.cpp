@@ -53,6 +53,7 @@ int main(int argc, char **argv)
     bwt_restore_sa_gpu((prefix + ".sa").c_str(), gd->bwt);
     gd->bwt_gpu = gpu_cpy_wrapper(gd->bwt);
     gd->pre_calc_seed_len = 13; gd->pre_calc_seed_intervals_flag = 0;
+    if (argc > 6 && atoi(argv[6])) gpuseed_b200_set_reseed(1, 1.5f, 10, 20);      // optional: the seed set of stock bwa mem
     mem_seed_v_gpu *seeds = seed_gpu(gd);
     free_gpuseed_data(gd);
     free(gd);

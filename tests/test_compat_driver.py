@@ -58,6 +58,18 @@ def test_driver_like_flow_matches_oracle(pkg, oracle, small_index, tmp_path):
     assert (per == want["n_seeds"]).all() and (pre == want["seed_off"].astype(np.uint32)).all()
     assert (rbeg == want["rbeg"]).all() and (qq[:, 0] == want["qbeg"]).all() and (qq[:, 1] == want["qend"]).all()
     assert (score == want["score"]).all()
+    # the same driver with re-seeding switched on through the compat layer: stock bwa mem's seed set in GPUSeed's layout
+    out2 = str(tmp_path / "out2.bin")
+    subprocess.check_call([exe, prefix, fa, jb, out2, "19", "1"])
+    b2 = open(out2, "rb").read()
+    n_reads2, n_seeds2 = struct.unpack_from("<QQ", b2, 0)
+    want2 = oi.seed_batch(reads.reshape(-1).copy(), (np.arange(1501) * 150).astype(np.uint64), 19, 0, n_threads=4, rs=oracle.reseed())
+    assert n_reads2 == 1500 and n_seeds2 == want2["total"] > n_seeds
+    o2 = 16
+    per2 = np.frombuffer(b2, np.uint32, n_reads2, o2); o2 += 8 * n_reads2
+    rbeg2 = np.frombuffer(b2, np.uint64, n_seeds2, o2); o2 += 8 * n_seeds2
+    qq2 = np.frombuffer(b2, np.int32, 2 * n_seeds2, o2).reshape(-1, 2)
+    assert (per2 == want2["n_seeds"]).all() and (rbeg2 == want2["rbeg"]).all() and (qq2[:, 0] == want2["qbeg"]).all() and (qq2[:, 1] == want2["qend"]).all()
     (nj,) = struct.unpack_from("<I", buf, o); o += 4
     sc = np.frombuffer(buf, np.int32, nj, o); o += 4 * nj
     qe = np.frombuffer(buf, np.int32, nj, o); o += 4 * nj
