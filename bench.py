@@ -41,7 +41,9 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)), "measured (MEASURED_PEAKS.json)"
+            pk = json.load(open(path))
+            if isinstance(pk, dict) and float(pk.get("hbm_gbs", 0)) > 0:
+                return pk, "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
