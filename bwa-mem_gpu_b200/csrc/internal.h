@@ -59,6 +59,8 @@ struct bwa_b200_seeder {
     b200::Cand *d_cand2 = nullptr, *d_cand3 = nullptr;
     uint64_t cand2_cap = 0, cand3_cap = 0;
     uint32_t xstride = 0, stride3 = 0, *d_ncand2 = nullptr, *d_ncand3 = nullptr, *d_rs_dummy = nullptr;
+    uint32_t *d_nsmems1 = nullptr;       // pass-1 SMEM counts of the batch, kept aside: merge_kernel overwrites d_nsmems and the passes may be re-run
+    bool rs_saved = false;
     // inputs of the current batch (re-seeding is re-run from them when a read overflows its row)
     const uint32_t *cur_packed = nullptr, *cur_len = nullptr; const uint64_t *cur_woff = nullptr; uint32_t cur_max_len = 0;
     void *d_cub = nullptr;

@@ -266,7 +266,8 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     uint32_t r = 0, woff = 0;
     int slot = -1, cur_x = -1, t = 0, t_head = 0, x = 0, end = 0, delay = 0;
     RowT ck = 0;
-    uint32_t cs = 0, acc_smems = 0, acc_seeds = 0, bw = 0, bw0 = 0, mi1 = 0;
+    uint32_t cs = 0, acc_seeds = 0, bw = 0, bw0 = 0, mi1 = 0;
+    int wtop = -1;                       // SMEMs of the read are written downwards from the top of its row: next free slot
 
     for (;;) {
         // ---------------- converged: claim reads for the warp, hand them to the lanes that need one
@@ -303,7 +304,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                         cp_async_commit();
 #pragma unroll
                         for (int j = 1; j < KC; ++j) cp_async_commit();   // empty groups: this one is now KC groups old
-                        cur_x = -1; acc_smems = 0; acc_seeds = 0;
+                        cur_x = -1; wtop = slot; acc_seeds = 0;
                         has_read = true; need_cand = true; delay = POP_DELAY;
                     }
                 } else if (need && exhausted) finished = true;   // nothing claimed, nothing coming
@@ -316,7 +317,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
 
         // ---------------- per lane: next candidate of the current read
         if (has_read && need_cand) {
-            if (slot < 0) { n_smems[r] = acc_smems; n_seeds[r] = acc_seeds; has_read = false; }
+            if (slot < 0) { n_smems[r] = (uint32_t)((int)n_cand[r] - 1 - wtop); n_seeds[r] = acc_seeds; has_read = false; }
             else {
                 cp_async_wait_group<KC - 1>();            // the copy for `slot` is at least KC groups old (or the read's first group)
                 uint4 *const m = &mine[slot & (KC - 1)][tid];
@@ -353,22 +354,25 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 nk = (RowT)L2_at(ix, b) + 1 + ok;
                 fail = RESEED ? ns <= mi1 : ns == 0;
             }
-            Cand *const rcs = cand + (uint64_t)r * cand_stride + slot;
             uint32_t *const env_g = env_spill + (uint64_t)gtid * env_stride;     // steps >= ENV_SMEM (rare)
             if (fail) {
-                // candidate stops after t steps: SMEM iff no longer match of this segment stopped here
-                uint32_t os = 0;
+                // candidate stops after t steps: SMEM iff no longer match of this segment stopped here.  Only SMEMs are written back,
+                // compacted downwards from the top of the read's row (slots at or above the current one have been consumed), so the
+                // row ends with the read's SMEMs in ascending (start, end) order and the consumers never scan the other candidates
                 if (first || t > t_head) {
-                    if (end - (x - t) >= min_seed_len) { os = cs; ++acc_smems; acc_seeds += seeds_of(cs, max_occ); }
+                    if (end - (x - t) >= min_seed_len) {
+                        acc_seeds += seeds_of(cs, max_occ);
+                        __stcs(reinterpret_cast<uint4 *>(cand + (uint64_t)r * cand_stride + wtop),
+                               make_uint4((uint32_t)ck, (uint32_t)((uint64_t)ck >> 32), cs, (uint32_t)(x - t) | (uint32_t)end << 16));
+                        --wtop;
+                    }
                     t_head = t; first = false;           // the envelope now covers steps [0, t)
                 }
-                __stcs(reinterpret_cast<uint4 *>(rcs), make_uint4((uint32_t)ck, (uint32_t)((uint64_t)ck >> 32), os, (uint32_t)(x - t) | (uint32_t)end << 16));
                 --slot; need_cand = true;
             } else {
                 uint32_t prev = 0;
                 if (t < t_head) prev = t < ENV_SMEM ? env_s[t][tid] : env_g[t - ENV_SMEM];
                 if (t < t_head && prev == ns) {         // same interval as the longer match: contained
-                    __stcs(reinterpret_cast<uint4 *>(rcs), make_uint4((uint32_t)ck, (uint32_t)((uint64_t)ck >> 32), 0u, (uint32_t)x | (uint32_t)end << 16));
                     --slot; need_cand = true;
                 } else {
                     if (t < ENV_SMEM) env_s[t][tid] = ns; else env_g[t - ENV_SMEM] = ns;
@@ -489,16 +493,16 @@ template <typename RowT>
 __global__ void __launch_bounds__(RS_THREADS)
 fwd2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
             const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, int split_len, int split_width,
-            uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
+            uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand, const uint32_t *__restrict__ n_smems,
             uint32_t stride3, Cand *__restrict__ cand3, uint32_t *__restrict__ n_cand3, unsigned long long *__restrict__ max_need)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const int len = (int)read_len[r];
     const uint64_t woff = word_off[r];
-    const Cand *row1 = cand + (uint64_t)r * cand_stride;
+    const uint32_t n1 = len >= min_seed_len ? n_smems[r] : 0u;                  // pass-1 SMEMs: the last n1 entries of the read's row
+    const Cand *row1 = cand + (uint64_t)r * cand_stride + (n_cand[r] - n1);
     Cand *out = cand3 + (uint64_t)r * stride3;
-    const uint32_t n1 = len >= min_seed_len ? n_cand[r] : 0u;
     const RowT primary = (RowT)ix.primary;
     const uint64_t pol = bucket_policy();
     uint32_t n_out = 0, j = 0, s = 0, mi1 = 0;
@@ -517,7 +521,7 @@ fwd2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             bool found = false;
             while (j < n1) {
                 const Cand c = row1[j++];
-                if (c.s == 0 || (int)c.end - (int)c.x < split_len || c.s > (uint32_t)split_width) continue;
+                if ((int)c.end - (int)c.x < split_len || c.s > (uint32_t)split_width) continue;
                 x = ((int)c.x + (int)c.end) >> 1; mi1 = c.s;     // min_intv - 1
                 found = true;
                 break;
@@ -549,8 +553,8 @@ fwd2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
 // read's cand2 row; sort by (start, end); per-read interval and seed counts.
 __global__ void __launch_bounds__(RS_THREADS)
 merge_kernel(uint32_t n_reads, const uint32_t *__restrict__ read_len, int min_seed_len, int max_occ,
-             uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
-             uint32_t stride3, const Cand *__restrict__ cand3, const uint32_t *__restrict__ n_cand3,
+             uint32_t cand_stride, const Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand, const uint32_t *__restrict__ n_smems1,
+             uint32_t stride3, const Cand *__restrict__ cand3, const uint32_t *__restrict__ n_cand3, const uint32_t *__restrict__ n_smems3,
              uint32_t xstride, Cand *__restrict__ cand2, uint32_t *__restrict__ n_cand2,
              uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds, unsigned long long *__restrict__ max_need)
 {
@@ -559,18 +563,14 @@ merge_kernel(uint32_t n_reads, const uint32_t *__restrict__ read_len, int min_se
     Cand *row2 = cand2 + (uint64_t)r * xstride;
     uint32_t n_out = n_cand2[r];                               // pass-3 entries (reseed3_kernel); may already exceed the row
     if ((int)read_len[r] >= min_seed_len) {
-        const Cand *row1 = cand + (uint64_t)r * cand_stride, *row3 = cand3 + (uint64_t)r * stride3;
-        const uint32_t n1 = n_cand[r], n3 = n_cand3[r];
+        const uint32_t n1 = n_smems1[r], n3 = n_smems3[r];                      // SMEMs of pass 1 / pass 2 close their rows
+        const Cand *row1 = cand + (uint64_t)r * cand_stride + (n_cand[r] - n1), *row3 = cand3 + (uint64_t)r * stride3 + (n_cand3[r] - n3);
         for (uint32_t j = 0; j < n1; ++j) {
-            const Cand c = row1[j];
-            if (c.s == 0) continue;
-            if (n_out < xstride) row2[n_out] = c;
+            if (n_out < xstride) row2[n_out] = row1[j];
             ++n_out;
         }
         for (uint32_t j = 0; j < n3; ++j) {
-            const Cand c = row3[j];
-            if (c.s == 0) continue;
-            if (n_out < xstride) row2[n_out] = c;
+            if (n_out < xstride) row2[n_out] = row3[j];
             ++n_out;
         }
     }
@@ -598,17 +598,16 @@ merge_kernel(uint32_t n_reads, const uint32_t *__restrict__ read_len, int min_se
 // ------------------------------------------------------------------------------ fill_kernel
 __global__ void __launch_bounds__(128)
 fill_kernel(uint32_t n_reads, int max_occ, uint32_t cand_stride, const Cand *__restrict__ cand,
-            const uint32_t *__restrict__ n_cand, const uint64_t *__restrict__ seed_off,
+            const uint32_t *__restrict__ n_cand, const uint32_t *__restrict__ n_smems, const uint64_t *__restrict__ seed_off,
             uint64_t *__restrict__ rbeg, int2 *__restrict__ qq, uint32_t *__restrict__ score, uint64_t cap)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    const Cand *rc = cand + (uint64_t)r * cand_stride;
-    uint32_t n = n_cand[r];
+    const uint32_t ns = n_smems[r];
+    const Cand *rc = cand + (uint64_t)r * cand_stride + (n_cand[r] - ns);     // the read's SMEMs close its row (back_kernel / merge_kernel)
     uint64_t o = seed_off[r];
-    for (uint32_t j = 0; j < n; ++j) {
+    for (uint32_t j = 0; j < ns; ++j) {
         Cand c = rc[j];
-        if (c.s == 0) continue;
         uint32_t step = (max_occ > 0 && c.s > (uint32_t)max_occ) ? c.s / (uint32_t)max_occ : 1u;
         uint32_t cnt = seeds_of(c.s, max_occ);
         for (uint32_t t = 0; t < cnt; ++t, ++o) {
@@ -622,18 +621,17 @@ fill_kernel(uint32_t n_reads, int max_occ, uint32_t cand_stride, const Cand *__r
 
 // SMEM-only dump used by tests: (qbeg, qend, k, s) per SMEM in read order
 __global__ void smem_dump_kernel(uint32_t n_reads, uint32_t cand_stride, const Cand *__restrict__ cand,
-                                 const uint32_t *__restrict__ n_cand, const uint64_t *__restrict__ smem_off,
+                                 const uint32_t *__restrict__ n_cand, const uint32_t *__restrict__ n_smems, const uint64_t *__restrict__ smem_off,
                                  int32_t *qbeg, int32_t *qend, uint64_t *k, uint64_t *s, uint64_t cap)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    const Cand *rc = cand + (uint64_t)r * cand_stride;
+    const uint32_t ns = n_smems[r];
+    const Cand *rc = cand + (uint64_t)r * cand_stride + (n_cand[r] - ns);
     uint64_t o = smem_off[r];
-    for (uint32_t j = 0; j < n_cand[r]; ++j) {
+    for (uint32_t j = 0; j < ns; ++j, ++o) {
         Cand c = rc[j];
-        if (c.s == 0) continue;
         if (o < cap) { qbeg[o] = c.x; qend[o] = c.end; k[o] = c.k; s[o] = c.s; }
-        ++o;
     }
 }
 
@@ -873,6 +871,7 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     B200_CUDA(cudaMalloc(&s->d_ncand2, max_reads * 4));
     B200_CUDA(cudaMalloc(&s->d_ncand3, max_reads * 4));
     B200_CUDA(cudaMalloc(&s->d_rs_dummy, max_reads * 8));
+    B200_CUDA(cudaMalloc(&s->d_nsmems1, max_reads * 4));
     cub::TransformInputIterator<uint64_t, U32ToU64, const uint32_t *> it(s->d_nseeds, U32ToU64());
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, it, s->d_seed_off, (int)max_reads, s->stream));
     B200_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes + 16));
@@ -890,7 +889,7 @@ extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
     cudaFree(s->d_packed); cudaFree(s->d_len); cudaFree(s->d_woff); cudaFree(s->d_cand); cudaFree(s->d_ncand);
     cudaFree(s->d_nsmems); cudaFree(s->d_nseeds); cudaFree(s->d_env); cudaFree(s->d_seed_off); cudaFree(s->d_smem_off);
     cudaFree(s->d_counters); cudaFree(s->d_cub); cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score);
-    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_cand3); cudaFree(s->d_ncand3); cudaFree(s->d_rs_dummy);
+    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_cand3); cudaFree(s->d_ncand3); cudaFree(s->d_rs_dummy); cudaFree(s->d_nsmems1);
     cudaFreeHost(s->h_counters);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -913,7 +912,7 @@ static int seeder_fill_locate(bwa_b200_seeder *s)
     const bool rs = s->last_p.reseed != 0;
     B200_LAUNCH(s->prof, "fill_kernel", st,
         (fill_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, s->last_p.max_occ, rs ? s->xstride : s->cand_stride, rs ? s->d_cand2 : s->d_cand,
-                                                       rs ? s->d_ncand2 : s->d_ncand, s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
+                                                       rs ? s->d_ncand2 : s->d_ncand, s->d_nsmems, s->d_seed_off, s->d_rbeg, s->d_qq, s->d_score, s->seed_cap)));
     if (s->narrow_rows)
         B200_LAUNCH(s->prof, "locate_kernel", st,
             (locate_kernel<uint32_t><<<s->loc_grid, LOC_THREADS, 0, st>>>(ix, s->d_rbeg, s->d_counters + 2, s->seed_cap, s->d_counters + 1)));
@@ -935,19 +934,23 @@ static int seeder_reseed(bwa_b200_seeder *s)
     const int split_len = (int)(p.min_seed_len * p.split_factor + .499f);      // bwa_index/bwamem.c:118
     const unsigned grid = (n + RS_THREADS - 1) / RS_THREADS;
     unsigned long long *cnt = s->d_counters;
+    if (!s->rs_saved) {                   // first time for this batch: d_nsmems still holds back_kernel's pass-1 counts
+        B200_CUDA(cudaMemcpyAsync(s->d_nsmems1, s->d_nsmems, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        s->rs_saved = true;
+    }
     B200_CUDA(cudaMemsetAsync(cnt + 4, 0, 3 * sizeof(unsigned long long), st));   // [4] [5] widest rows needed, [6] read queue of the second back_kernel
     if (s->narrow_rows) {
         B200_LAUNCH(s->prof, "reseed3_kernel", st,
             (reseed3_kernel<uint32_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
         B200_LAUNCH(s->prof, "fwd2_kernel", st,
             (fwd2_kernel<uint32_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, split_len, p.split_width, s->cand_stride, s->d_cand,
-                                                                s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
+                                                                s->d_ncand, s->d_nsmems1, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
     } else {
         B200_LAUNCH(s->prof, "reseed3_kernel", st,
             (reseed3_kernel<uint64_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, p.max_mem_intv, s->xstride, s->d_cand2, s->d_ncand2)));
         B200_LAUNCH(s->prof, "fwd2_kernel", st,
             (fwd2_kernel<uint64_t><<<grid, RS_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, s->cur_len, n, p.min_seed_len, split_len, p.split_width, s->cand_stride, s->d_cand,
-                                                                s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
+                                                                s->d_ncand, s->d_nsmems1, s->stride3, s->d_cand3, s->d_ncand3, cnt + 4)));
     }
     // backward phases of the pass-2 calls: the pass-1 kernel, with the per-candidate min_intv (its per-read counts are not used)
     B200_LAUNCH(s->prof, "back_kernel_pass2", st,
@@ -955,7 +958,7 @@ static int seeder_reseed(bwa_b200_seeder *s)
                                                                                                  s->d_cand3, s->d_ncand3, s->d_rs_dummy, s->d_rs_dummy + s->max_reads, s->d_env,
                                                                                                  s->env_stride, cnt + 6)));
     B200_LAUNCH(s->prof, "merge_kernel", st,
-        (merge_kernel<<<grid, RS_THREADS, 0, st>>>(n, s->cur_len, p.min_seed_len, p.max_occ, s->cand_stride, s->d_cand, s->d_ncand, s->stride3, s->d_cand3, s->d_ncand3,
+        (merge_kernel<<<grid, RS_THREADS, 0, st>>>(n, s->cur_len, p.min_seed_len, p.max_occ, s->cand_stride, s->d_cand, s->d_ncand, s->d_nsmems1, s->stride3, s->d_cand3, s->d_ncand3, s->d_rs_dummy,
                                                    s->xstride, s->d_cand2, s->d_ncand2, s->d_nsmems, s->d_nseeds, cnt + 4)));
     s->launches += 4;
     B200_CUDA(cudaGetLastError());
@@ -986,7 +989,7 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     if (max_len > 65535) { b200::set_error("seed: reads longer than 65535 bases are not supported"); return BWA_B200_ERR_ARG; }
     if (p->min_seed_len < 1) { b200::set_error("seed: min_seed_len < 1"); return BWA_B200_ERR_ARG; }
     B200_CUDA(cudaSetDevice(s->device));
-    s->last_n_reads = n_reads; s->last_total = 0; s->last_p = *p; s->filled = false;
+    s->last_n_reads = n_reads; s->last_total = 0; s->last_p = *p; s->filled = false; s->rs_saved = false;
     if (n_reads == 0) return BWA_B200_OK;
     if (!s->idx->v.sa) { b200::set_error("seed: index has no suffix array samples"); return BWA_B200_ERR_ARG; }
     int rc = seeder_ensure_cand(s, n_reads, max_len, p->min_seed_len);
@@ -1162,7 +1165,7 @@ extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads
     B200_CUDA(cudaMalloc(&d_k, tot * 8)); B200_CUDA(cudaMalloc(&d_s, tot * 8));
     const bool rs = s->last_p.reseed != 0;
     smem_dump_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, rs ? s->xstride : s->cand_stride, rs ? s->d_cand2 : s->d_cand, rs ? s->d_ncand2 : s->d_ncand,
-                                                             s->d_smem_off, d_qb, d_qe, d_k, d_s, tot);
+                                                             s->d_nsmems, s->d_smem_off, d_qb, d_qe, d_k, d_s, tot);
     B200_CUDA(cudaStreamSynchronize(s->stream));
     B200_CUDA(cudaMemcpy(host_qbeg, d_qb, tot * 4, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemcpy(host_qend, d_qe, tot * 4, cudaMemcpyDeviceToHost));
