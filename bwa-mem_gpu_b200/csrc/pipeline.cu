@@ -85,20 +85,18 @@ cut_kernel(uint32_t n_jobs, int64_t l_pac, const uint32_t *__restrict__ pac, int
            const JobAux *__restrict__ aux, uint32_t qstride, uint32_t tstride,
            uint32_t *__restrict__ qp, uint32_t *__restrict__ tp)
 {
-    const uint32_t per_job = qstride + tstride;
-    const uint64_t total = (uint64_t)n_jobs * per_job;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(g / per_job), wi = (uint32_t)(g % per_job);
-        if (wi < qstride) {
-            const uint32_t ql = jq_len[j];
-            if (wi * 8 >= ql) continue;
-            const uint64_t wo = word_off[j >> 1];
-            qp[(uint64_t)j * qstride + wi] = b200chain::cut_query_word(packed_reads + wo, (int64_t)(word_off[(j >> 1) + 1] - wo), aux[j], wi, ql);
-        } else {
-            const uint32_t ti = wi - qstride, tl = jt_len[j];
-            if (ti * 8 >= tl) continue;
-            tp[(uint64_t)j * tstride + ti] = b200chain::cut_target_word(pac, pac_words, l_pac, aux[j], ti, tl);
-        }
+    // one warp per job, lanes over its words: no division per word, the job's descriptors are warp-uniform loads, and the words a
+    // short job does not have are never visited
+    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_jobs; j += warps) {
+        const uint32_t ql = jq_len[j], tl = jt_len[j];
+        if (ql == 0 && tl == 0) continue;
+        const JobAux ax = aux[j];
+        const uint64_t wo = word_off[j >> 1];
+        const int64_t rw = (int64_t)(word_off[(j >> 1) + 1] - wo);
+        const uint32_t qw = (ql + 7) >> 3, tw = (tl + 7) >> 3;
+        for (uint32_t wi = lane; wi < qw; wi += 32) qp[(uint64_t)j * qstride + wi] = b200chain::cut_query_word(packed_reads + wo, rw, ax, wi, ql);
+        for (uint32_t ti = lane; ti < tw; ti += 32) tp[(uint64_t)j * tstride + ti] = b200chain::cut_target_word(pac, pac_words, l_pac, ax, ti, tl);
     }
 }
 
