@@ -565,8 +565,8 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
         if (k == 5) { b200::set_error("global: band %u of job %u is wider than 127", w, a); return BWA_B200_ERR_ARG; }
         ++cnt[k]; tl[k] = std::max(tl[k], h_tlen[a]); ql[k] = std::max(ql[k], h_qlen[a]);
     }
-    uint32_t first[6] = {0, 0, 0, 0, 0, 0}, cur[5];
-    for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; cur[k] = first[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; c->cls_ql[k] = ql[k] ? ql[k] : 1; }
+    uint32_t first[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 5; ++k) { first[k + 1] = first[k] + cnt[k]; c->cls_n[k] = cnt[k]; c->cls_tl[k] = tl[k] ? tl[k] : 1; c->cls_ql[k] = ql[k] ? ql[k] : 1; }
     {   // shared memory of a class = ring + its longest query and target; the grid follows from the occupancy at that size
         // w <= 15: column state in registers (global_band_kernel); BWA_B200_GLOBAL_RING=1 sends those classes through the shared-memory
         // ring kernel as well (tests run both)
@@ -593,7 +593,6 @@ static int cigar_run(bwa_b200_cigar *c, const bwa_b200_ext_params_t *p, uint64_t
         for (int v = 0; v < 128; ++v) hist[v + 1] += hist[v];                    // hist[w] = first position of band w (classes are contiguous in w)
         for (uint32_t a = 0; a < n; ++a) c->perm[hist[h_w[a]]++] = a;
     }
-    (void)cur;
     uint64_t z_need = 1;                    // the classes run concurrently: each has its own region of backtrack slabs
     for (int k = 0; k < 5; ++k) {
         c->z_off[k] = z_need;
