@@ -8,10 +8,12 @@
 // first n symbols" then needs one 64-bit mask and 2 POPC per base instead of 4 masked words.
 #include "common.h"
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <thread>
 #include <vector>
 #include <atomic>
+#include <chrono>
 
 namespace b200 {
 static thread_local char g_err[512] = "";
@@ -194,9 +196,13 @@ extern "C" void bwa_b200_index_free(bwa_b200_index_t *idx)
 }
 
 // ------------------------------------------------------------------------------------------
-// Host-side index construction.  Suffix array of T = fwd + revcomp(fwd) by a 12-mer counting
-// sort followed by per-bucket comparison sorts on a 2-bit packed copy of T (32 bases per
-// 64-bit window), then BWT, occurrence buckets and SA samples in the reference's formats.
+// Host-side index construction.  Suffix array of T = fwd + revcomp(fwd) by a 7-mer partition
+// followed by per-partition sorts keyed on a 2-bit packed copy of T (32 bases per 64-bit
+// window), then BWT, occurrence buckets and SA samples in the reference's formats.
+// Suffix indexes are 32-bit while 2*l_pac < 2^32 - 1 and 64-bit beyond (human-sized genomes:
+// the SA samples then carry their high bits in the packed array of bwa_index/bwt.c:78-147).
+// Every pass over the rows is spread over the host threads: the BWT pass is one random read of
+// the text per row, which a single thread cannot feed at 6 G rows.
 // ------------------------------------------------------------------------------------------
 namespace {
 
@@ -210,6 +216,7 @@ struct Packed {
         uint64_t lo = r ? (w[q + 1] >> (64 - r)) : 0;
         return hi | lo;
     }
+    inline uint32_t base(uint64_t i) const { return (uint32_t)(w[i >> 5] >> (62 - 2 * (i & 31))) & 3u; }
     // suffix order with an implicit sentinel smaller than every base
     inline bool less(uint64_t a, uint64_t b) const
     {
@@ -222,11 +229,13 @@ struct Packed {
     }
 };
 
-template <class F> void parallel_for(uint64_t n, int n_threads, F f)
+// f(first, last, thread) over [0, n) cut into n_threads pieces whose boundaries are multiples of `align`
+template <class F> void parallel_for(uint64_t n, int n_threads, F f, uint64_t align = 1)
 {
     if (n_threads <= 1 || n < 2) { f(0, n, 0); return; }
     std::vector<std::thread> th;
     uint64_t chunk = (n + n_threads - 1) / n_threads;
+    chunk = (chunk + align - 1) / align * align;
     for (int t = 0; t < n_threads; ++t) {
         uint64_t a = std::min(n, chunk * t), b = std::min(n, a + chunk);
         th.emplace_back([=] { f(a, b, t); });
@@ -244,118 +253,198 @@ int write_file(const std::string &path, const std::vector<std::pair<const void *
     return BWA_B200_OK;
 }
 
+// bucket arrays: `cw` count words (u32 x 4 or u64 x 4 = 8 words) in front of every `sym` BWT symbols, one more set at the end
+// (bwa_index/bwtindex.c:151-197).  raw = 16 symbols per word; pre[t] = counts before thread t's piece.
+template <class CntT>
+void bucket_layout(std::vector<uint32_t> &out, const std::vector<uint32_t> &raw, uint64_t n, uint64_t sym, int n_threads,
+                   const std::vector<std::array<uint64_t, 4>> &pre, uint64_t piece)
+{
+    const uint64_t cw = 4 * sizeof(CntT) / 4, n_raw = (n + 15) / 16, wpb = sym / 16;
+    out.assign(cw * ((n + sym - 1) / sym) + n_raw + cw, 0);
+    parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
+        if (a >= b) return;
+        CntT c[4] = {(CntT)pre[t][0], (CntT)pre[t][1], (CntT)pre[t][2], (CntT)pre[t][3]};
+        for (uint64_t i = a; i < b; i += 16) {                       // a is a multiple of `piece`, itself a multiple of sym
+            uint64_t o = (i / sym) * (cw + wpb) + cw + (i % sym) / 16;
+            if (i % sym == 0) memcpy(&out[o - cw], c, sizeof(c));
+            const uint32_t v = raw[i >> 4];
+            out[o] = v;
+            const int m = (int)std::min<uint64_t>(16, n - i);
+            for (int j = 0; j < m; ++j) ++c[(v >> ((15 - j) << 1)) & 3u];
+        }
+        if (b == n) memcpy(&out[out.size() - cw], c, sizeof(c));
+    }, piece);
+}
+
+template <class IdxT>
+int build_impl(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *prefix, int also_stock_layout, int n_threads)
+{
+    const uint64_t n = 2 * l_pac;
+    const bool verbose = getenv("BWA_B200_BUILD_TIMES") != nullptr;              // phase times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        auto now = std::chrono::steady_clock::now();
+        if (verbose) fprintf(stderr, "[build_index] %-28s %.2f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+    // packed text, validation and base counts in one pass over the forward strand
+    Packed P;
+    P.n = n;
+    P.w.assign(n / 32 + 3, 0);
+    std::vector<std::array<uint64_t, 5>> cnt_t(n_threads, std::array<uint64_t, 5>{0, 0, 0, 0, 0});
+    parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
+        auto &c = cnt_t[t];
+        for (uint64_t i = a; i < b; ++i) {
+            uint32_t v = i < l_pac ? fwd[i] : 3u - fwd[n - 1 - i];
+            if (i < l_pac && v > 3) { if (!c[4]) c[4] = i + 1; v = 0; }
+            v &= 3u;
+            ++c[v];
+            P.w[i >> 5] |= (uint64_t)v << (62 - 2 * (i & 31));
+        }
+    }, 32);
+    uint64_t L2[5] = {0, 0, 0, 0, 0};
+    for (auto &c : cnt_t) {
+        if (c[4]) { b200::set_error("build_index: code %d at %llu (only A,C,G,T)", fwd[c[4] - 1], (unsigned long long)(c[4] - 1)); return BWA_B200_ERR_ARG; }
+        for (int k = 0; k < 4; ++k) L2[k + 1] += c[k];
+    }
+    for (int k = 0; k < 4; ++k)
+        if (L2[k + 1] > 0xffffffffull) { b200::set_error("build_index: %llu occurrences of one base do not fit the 32-bit bucket counts", (unsigned long long)L2[k + 1]); return BWA_B200_ERR_CAPACITY; }
+    for (int c = 1; c <= 4; ++c) L2[c] += L2[c - 1];
+    phase("pack text");
+
+    // Partition by the first K bases (zero padded past the end): per-thread histograms over contiguous pieces of the text, so the
+    // scatter needs no atomics and leaves every partition in text order.  Each partition (n / 4^K suffixes, cache-sized) is then
+    // sorted on its own: the 32 bases behind the shared K-mer travel with each suffix as the sort key, fetched once in text order,
+    // and the text is touched again only on a tie.  Zero padding past the end sorts like the sentinel or like A; a tie falls back to
+    // the full comparison, so the order is the strict suffix order and the result does not depend on the thread count.
+    const int K = 7;
+    const uint64_t NB = 1ull << (2 * K);
+    auto key = [&](uint64_t i) { return P.window(i) >> (64 - 2 * K); };
+    std::vector<uint64_t> start(NB + 1, 0);
+    std::vector<IdxT> sa(n);
+    {
+        std::vector<uint64_t> hist((size_t)n_threads * NB, 0);
+        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
+            uint64_t *h = &hist[(size_t)t * NB];
+            for (uint64_t i = a; i < b; ++i) ++h[key(i)];
+        });
+        uint64_t run = 0;
+        for (uint64_t k = 0; k < NB; ++k) {
+            start[k] = run;
+            for (int t = 0; t < n_threads; ++t) { uint64_t c = hist[(size_t)t * NB + k]; hist[(size_t)t * NB + k] = run; run += c; }
+        }
+        start[NB] = run;
+        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
+            uint64_t *h = &hist[(size_t)t * NB];
+            for (uint64_t i = a; i < b; ++i) sa[h[key(i)]++] = (IdxT)i;
+        });
+        phase("k-mer partition");
+    }
+    {
+        std::atomic<uint64_t> next(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t)
+            th.emplace_back([&] {
+                typedef std::pair<uint64_t, IdxT> KeyIdx;
+                std::vector<KeyIdx> buf;
+                for (;;) {
+                    const uint64_t k = next.fetch_add(1);
+                    if (k >= NB) break;
+                    const uint64_t a = start[k], m = start[k + 1] - a;
+                    if (m < 2) continue;
+                    buf.resize(m);
+                    for (uint64_t e = 0; e < m; ++e) { const IdxT p = sa[a + e]; buf[e] = KeyIdx(P.window((uint64_t)p + K), p); }
+                    std::sort(buf.begin(), buf.end(), [&](const KeyIdx &x, const KeyIdx &y) {
+                        return x.first != y.first ? x.first < y.first : P.less(x.second, y.second);
+                    });
+                    for (uint64_t e = 0; e < m; ++e) sa[a + e] = buf[e].second;
+                }
+            });
+        for (auto &x : th) x.join();
+        phase("partition sorts");
+    }
+    // ---- BWT with '$' removed, primary.  Rows: 0 = empty suffix (char T[n-1]); row r >= 1 = sa[r-1]; the row whose suffix is
+    // the whole text (primary) has no symbol, so symbol j >= 1 belongs to row j + (j >= primary)
+    uint64_t primary = 0;
+    parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) if (sa[r] == 0) primary = r + 1;       // exactly one writer
+    });
+    const uint64_t n_raw = (n + 15) / 16;
+    std::vector<uint32_t> raw(n_raw, 0);
+    const uint64_t piece = 128 * (((n + n_threads - 1) / n_threads + 127) / 128);     // whole buckets of either layout per thread
+    std::vector<std::array<uint64_t, 4>> pre(n_threads + 1, std::array<uint64_t, 4>{0, 0, 0, 0});
+    parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
+        uint64_t c[4] = {0, 0, 0, 0};
+        for (uint64_t j = a; j < b; ++j) {
+            uint32_t v;
+            if (j == 0) v = P.base(n - 1);
+            else v = P.base((uint64_t)sa[j - 1 + (j >= primary)] - 1);
+            ++c[v];
+            raw[j >> 4] |= v << ((~j & 15) << 1);
+        }
+        for (int k = 0; k < 4; ++k) pre[t + 1][k] = c[k];
+    }, piece);
+    for (int t = 1; t <= n_threads; ++t) for (int k = 0; k < 4; ++k) pre[t][k] += pre[t - 1][k];
+    phase("bwt");
+
+    int rc;
+    {   // ---- GPU layout: u32 counts + 4 words per 64 symbols, trailing counts (bwtindex.c:174-197)
+        std::vector<uint32_t> g;
+        bucket_layout<uint32_t>(g, raw, n, 64, n_threads, pre, piece);
+        rc = write_file(std::string(prefix) + ".bwt", {{&primary, 8}, {L2 + 1, 32}, {g.data(), g.size() * 4}});
+        if (rc) return rc;
+    }
+    if (also_stock_layout) { // u64 counts + 8 words per 128 symbols (bwtindex.c:151-172)
+        std::vector<uint32_t> s;
+        bucket_layout<uint64_t>(s, raw, n, 128, n_threads, pre, piece);
+        rc = write_file(std::string(prefix) + ".bwt128", {{&primary, 8}, {L2 + 1, 32}, {s.data(), s.size() * 4}});
+        if (rc) return rc;
+    }
+    std::vector<uint32_t>().swap(raw);
+    phase("bucket layouts + write");
+    // ---- SA samples: low 32 bits, and the high bits packed `pack_size` to a sample (bwa_index/bwt.c:78-147, 472-487)
+    const uint64_t n_sa = (n + (uint64_t)sa_intv) / (uint64_t)sa_intv;
+    uint8_t pack_size = 1;
+    uint32_t pack_mask = 0;
+    {
+        const uint32_t upper = (uint32_t)(n >> 32);
+        int msb = 0;
+        while (msb < 32 && (upper >> msb)) ++msb;                 // position of the highest set bit, 1-based
+        if (msb == 1) { pack_size = 1; pack_mask = 1u; }
+        else if (msb == 2) { pack_size = 2; pack_mask = 3u; }
+        else if (msb > 2 && msb <= 4) { pack_size = 4; pack_mask = 0xfu; }
+        else if (msb > 4 && msb <= 8) { pack_size = 8; pack_mask = 0xffu; }
+        else if (msb > 8 && msb <= 16) { pack_size = 16; pack_mask = 0xffffu; }
+        else if (msb > 16) { pack_size = 32; pack_mask = 0xffffffffu; }
+    }
+    const uint64_t pack_div = 32 / pack_size;
+    std::vector<uint32_t> smp(n_sa);
+    std::vector<uint32_t> hi((uint64_t)pack_size * n_sa / 32 + 1, 0);
+    parallel_for(n_sa, n_threads, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t j = std::max<uint64_t>(a, 1); j < b; ++j) {
+            const uint64_t v = (uint64_t)sa[j * (uint64_t)sa_intv - 1];
+            smp[j] = (uint32_t)v;
+            if (pack_mask) hi[j / pack_div] |= ((uint32_t)(v >> 32) & pack_mask) << ((j % pack_div) * pack_size);
+        }
+    }, 32);
+    smp[0] = 0xffffffffu;
+    hi[0] |= pack_mask;                                            // row 0 reads as -1 (bwa_index/bwt.c:144-146)
+    uint64_t intv64 = (uint64_t)sa_intv, seq_len = n;
+    rc = write_file(std::string(prefix) + ".sa", {{&primary, 8}, {L2 + 1, 32}, {&intv64, 8}, {&seq_len, 8},
+                                                  {smp.data() + 1, (n_sa - 1) * 4}, {&pack_size, 1}, {hi.data(), hi.size() * 4}});
+    phase("sa samples + write");
+    return rc;
+}
+
 } // namespace
 
 extern "C" int bwa_b200_build_index(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *prefix,
                                     int also_stock_layout, int n_threads)
 {
     if (!fwd || !prefix || l_pac == 0 || sa_intv <= 0 || (sa_intv & (sa_intv - 1))) { b200::set_error("build_index: bad argument"); return BWA_B200_ERR_ARG; }
-    const uint64_t n = 2 * l_pac;
-    if (n >= 0xffffffffull) { b200::set_error("build_index: host builder handles 2*l_pac < 2^32 (got %llu)", (unsigned long long)n); return BWA_B200_ERR_CAPACITY; }
     if (n_threads < 1) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    for (uint64_t i = 0; i < l_pac; ++i) if (fwd[i] > 3) { b200::set_error("build_index: code %d at %llu (only A,C,G,T)", fwd[i], (unsigned long long)i); return BWA_B200_ERR_ARG; }
-
-    // text + packed text
-    std::vector<uint8_t> T(n);
-    for (uint64_t i = 0; i < l_pac; ++i) { T[i] = fwd[i]; T[n - 1 - i] = (uint8_t)(3 - fwd[i]); }
-    Packed P;
-    P.n = n;
-    P.w.assign(n / 32 + 3, 0);
-    for (uint64_t i = 0; i < n; ++i) P.w[i >> 5] |= (uint64_t)T[i] << (62 - 2 * (i & 31));
-
-    // counting sort on the first K bases (zero padded past the end); shared atomic histogram
-    const int K = n > (1ull << 26) ? 13 : (n > (1ull << 20) ? 11 : 8);
-    const uint64_t NB = 1ull << (2 * K);
-    auto key = [&](uint64_t i) { return P.window(i) >> (64 - 2 * K); };
-    std::vector<uint32_t> start(NB + 1, 0), cursor(NB, 0);
-    std::vector<uint32_t> sa(n);
-    {
-        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int) {
-            for (uint64_t i = a; i < b; ++i) __atomic_fetch_add(&cursor[key(i)], 1u, __ATOMIC_RELAXED);
-        });
-        uint64_t run = 0;
-        for (uint64_t k = 0; k < NB; ++k) { start[k] = (uint32_t)run; run += cursor[k]; cursor[k] = start[k]; }
-        start[NB] = (uint32_t)run;
-        parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int) {
-            for (uint64_t i = a; i < b; ++i) sa[__atomic_fetch_add(&cursor[key(i)], 1u, __ATOMIC_RELAXED)] = (uint32_t)i;
-        });
-        std::vector<uint32_t>().swap(cursor);
-        // per-bucket sorts, dynamically scheduled (a strict total order: result is unique)
-        std::atomic<uint64_t> next(0);
-        const uint64_t grain = 4096;
-        std::vector<std::thread> th;
-        for (int t = 0; t < n_threads; ++t)
-            th.emplace_back([&] {
-                for (;;) {
-                    uint64_t k0 = next.fetch_add(grain);
-                    if (k0 >= NB) break;
-                    uint64_t k1 = std::min(NB, k0 + grain);
-                    for (uint64_t k = k0; k < k1; ++k) {
-                        uint32_t a = start[k], b = start[k + 1];
-                        if (b - a > 1) std::sort(sa.begin() + a, sa.begin() + b, [&](uint32_t x, uint32_t y) { return P.less(x, y); });
-                    }
-                }
-            });
-        for (auto &x : th) x.join();
-    }
-    {
-        // ---- BWT with '$' removed, primary, L2
-        uint64_t primary = 0, L2[5] = {0, 0, 0, 0, 0};
-        for (uint64_t i = 0; i < n; ++i) ++L2[T[i] + 1];
-        for (int c = 1; c <= 4; ++c) L2[c] += L2[c - 1];
-        std::vector<uint8_t> B(n);
-        // rows: 0 = empty suffix (char T[n-1]); row r>=1 = sa[r-1]
-        {
-            uint64_t j = 0;
-            B[j++] = T[n - 1];
-            for (uint64_t r = 1; r <= n; ++r) {
-                uint32_t p = sa[r - 1];
-                if (p == 0) { primary = r; continue; }
-                B[j++] = T[p - 1];
-            }
-        }
-        const uint64_t n_raw = (n + 15) / 16;
-        std::vector<uint32_t> raw(n_raw, 0);
-        for (uint64_t i = 0; i < n; ++i) raw[i >> 4] |= (uint32_t)B[i] << ((~i & 15) << 1);
-
-        // ---- GPU layout: u32 counts + 4 words per 64 symbols, trailing counts (bwtindex.c:174-197)
-        std::vector<uint32_t> g;
-        g.reserve(4 * ((n + 63) / 64) + n_raw + 4);
-        {
-            uint32_t c[4] = {0, 0, 0, 0};
-            for (uint64_t i = 0; i < n; ++i) {
-                if ((i & 63) == 0) g.insert(g.end(), c, c + 4);
-                if ((i & 15) == 0) g.push_back(raw[i >> 4]);
-                ++c[B[i]];
-            }
-            g.insert(g.end(), c, c + 4);
-        }
-        int rc = write_file(std::string(prefix) + ".bwt", {{&primary, 8}, {L2 + 1, 32}, {g.data(), g.size() * 4}});
-        if (rc) return rc;
-        if (also_stock_layout) { // u64 counts + 8 words per 128 symbols (bwtindex.c:151-172)
-            std::vector<uint32_t> s;
-            s.reserve(8 * ((n + 127) / 128) + n_raw + 8);
-            uint64_t c[4] = {0, 0, 0, 0};
-            for (uint64_t i = 0; i < n; ++i) {
-                if ((i & 127) == 0) { const uint32_t *cw = (const uint32_t *)c; s.insert(s.end(), cw, cw + 8); }
-                if ((i & 15) == 0) s.push_back(raw[i >> 4]);
-                ++c[B[i]];
-            }
-            const uint32_t *cw = (const uint32_t *)c;
-            s.insert(s.end(), cw, cw + 8);
-            rc = write_file(std::string(prefix) + ".bwt128", {{&primary, 8}, {L2 + 1, 32}, {s.data(), s.size() * 4}});
-            if (rc) return rc;
-        }
-        // ---- SA samples (bwa_index/bwt.c:64-148, 472-487)
-        const uint64_t n_sa = (n + (uint64_t)sa_intv) / (uint64_t)sa_intv;
-        std::vector<uint32_t> smp(n_sa);
-        smp[0] = 0xffffffffu;
-        for (uint64_t j = 1; j < n_sa; ++j) smp[j] = sa[j * (uint64_t)sa_intv - 1];
-        uint8_t pack_size = 1;                 // seq_len < 2^32 here: msb == 0 -> pack_size 1, mask 0
-        std::vector<uint32_t> hi((uint64_t)pack_size * n_sa / 32 + 1, 0);
-        uint64_t intv64 = (uint64_t)sa_intv, seq_len = n;
-        rc = write_file(std::string(prefix) + ".sa", {{&primary, 8}, {L2 + 1, 32}, {&intv64, 8}, {&seq_len, 8},
-                                                       {smp.data() + 1, (n_sa - 1) * 4}, {&pack_size, 1}, {hi.data(), hi.size() * 4}});
-        return rc;
-    }
+    const char *wide = getenv("BWA_B200_BUILD_WIDE");              // tests: 64-bit suffix indexes on a small text
+    if (2 * l_pac >= 0xffffffffull || (wide && wide[0] == '1'))
+        return build_impl<uint64_t>(fwd, l_pac, sa_intv, prefix, also_stock_layout, n_threads);
+    return build_impl<uint32_t>(fwd, l_pac, sa_intv, prefix, also_stock_layout, n_threads);
 }

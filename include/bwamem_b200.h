@@ -81,7 +81,11 @@ void bwa_b200_index_free(bwa_b200_index_t *idx);          /* replaces free_gpuse
  * build_index.sh): writes <prefix>.bwt (32-bit occ, 64-symbol buckets) and <prefix>.sa; with
  * also_stock_layout != 0 additionally <prefix>.bwt128 (stock 64-bit occ, 128-symbol buckets) so
  * the unmodified CPU bwa can be timed on the same index.  fwd = forward strand, codes 0..3.
- * Output is byte-identical to the reference's `bwa index -s sa -r R` + `bwa index -s bwt`. */
+ * Output is byte-identical to the reference's `bwa index -s sa -r R` + `bwa index -s bwt`.
+ * Texts of 2^32 - 1 rows and more (2*l_pac; human-sized genomes) are sorted with 64-bit suffix indexes and
+ * their SA samples carry the high bits in the packed array of bwa_index/bwt.c:78-147 (about 10 bytes of
+ * host memory per row); BWA_B200_ERR_CAPACITY if one base occurs 2^32 times or more (the 32-bit bucket counts
+ * of the reference's GPU layout could not hold it). */
 int  bwa_b200_build_index(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *prefix,
                           int also_stock_layout, int n_threads);
 

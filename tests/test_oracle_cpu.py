@@ -15,13 +15,17 @@ def sha(path):
     return hashlib.sha256(open(path, "rb").read()).hexdigest()
 
 
-def test_builder_matches_reference_hashes(pkg, tmp_path):
-    """index files byte-identical to the reference's `bwa index` output (hashes recorded by make_golden.py)"""
+@pytest.mark.parametrize("wide,threads", [("0", 4), ("1", 4), ("1", 7), ("0", 1)])
+def test_builder_matches_reference_hashes(pkg, tmp_path, monkeypatch, wide, threads):
+    """index files byte-identical to the reference's `bwa index` output (hashes recorded by make_golden.py); wide = the builder's
+    64-bit suffix-index instantiation (the one genomes with 2*l_pac >= 2^32 take), forced onto the same small texts; the passes are
+    cut by thread, so odd thread counts move the cuts"""
+    monkeypatch.setenv("BWA_B200_BUILD_WIDE", wide)
     gold = np.load(os.path.join(GOLD, "index_hashes.npz"), allow_pickle=True)
     for n, rep, seed, intv, h_bwt, h_sa, h_128 in gold["rows"]:
         g = synth.make_genome(int(n), seed=int(seed), repeats=bool(int(rep)))
         prefix = str(tmp_path / f"g{n}")
-        pkg.build_index(g, prefix, sa_intv=int(intv), also_stock_layout=True, n_threads=4)
+        pkg.build_index(g, prefix, sa_intv=int(intv), also_stock_layout=True, n_threads=threads)
         assert sha(prefix + ".bwt") == h_bwt
         assert sha(prefix + ".sa") == h_sa
         assert sha(prefix + ".bwt128") == h_128
