@@ -46,6 +46,9 @@ typedef struct { size_t n, m; mem_chain_t *a; } mem_chain_v;
 
 mem_chain_v mem_chain(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, int len, const uint8_t *seq, mem_seed_v_gpu *gpu_results, int j);
 int mem_chain_flt(const mem_opt_t *opt, int n_chn, mem_chain_t *a);
+int mem_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *query, int n, mem_alnreg_t *a);
+int mem_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id);
+int mem_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a);
 void mem_flt_chained_seeds(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, int n_chn, mem_chain_t *a);
 void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, const mem_chain_t *c,
                    mem_alnreg_v *regs, int *curr_read_offset, int *curr_ref_offset, gpu_batch *curr_gpu_batch_short, gpu_batch *curr_gpu_batch_long);
@@ -244,6 +247,63 @@ int fork_reg2aln(const fork_opt_t *fo, int64_t l_pac, int n_ctg, const int64_t *
     for (int i = 0; i < a.n_cigar && i < cap; ++i) cigar_out[i] = a.cigar[i];
     int n = a.n_cigar;
     free(a.cigar);
+    free(opt);
+    return n;
+}
+
+/* the fork's own mem_sort_dedup_patch (src/bwamem.c:620-681), the is_alt marking of its caller (:2321-2325), mem_mark_primary_se
+ * (:715-760) and mem_approx_mapq_se as mem_reg2aln applies it (:1690-1716, :2363) on one read's alignment regions, in place.
+ * The record is oracle/region_oracle.h's region_t.  opt13 = a b o_del e_del o_ins e_ins w min_seed_len max_chain_gap mapQ_coef_fac
+ * then mask_level, mask_level_redun, mapQ_coef_len as floats.  Returns the new count. */
+typedef struct {
+    int64_t rb, re;
+    uint64_t hash;
+    int32_t qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0, n_comp, is_alt;
+    float frac_rep;
+    int32_t mapq;
+} fork_region_t;
+typedef struct {
+    int32_t a, b, o_del, e_del, o_ins, e_ins, w, min_seed_len, max_chain_gap, mapQ_coef_fac;
+    float mask_level, mask_level_redun, mapQ_coef_len;
+} fork_region_opt_t;
+
+int fork_finish_regs(const fork_region_opt_t *fo, int64_t l_pac, int n_ctg, const int32_t *ctg_alt, const uint8_t *pac,
+                     int l_query, const uint8_t *query_in, int n, fork_region_t *r, int64_t id, int *n_pri)
+{
+    mem_opt_t *opt = mem_opt_init();
+    opt->a = fo->a; opt->b = fo->b; opt->o_del = fo->o_del; opt->e_del = fo->e_del; opt->o_ins = fo->o_ins; opt->e_ins = fo->e_ins; opt->w = fo->w;
+    opt->min_seed_len = fo->min_seed_len; opt->max_chain_gap = fo->max_chain_gap; opt->mapQ_coef_fac = fo->mapQ_coef_fac;
+    opt->mask_level = fo->mask_level; opt->mask_level_redun = fo->mask_level_redun; opt->mapQ_coef_len = fo->mapQ_coef_len;
+    bwa_fill_scmat(opt->a, opt->b, opt->mat);
+    bntseq_t bns;
+    memset(&bns, 0, sizeof(bns));
+    bns.l_pac = l_pac; bns.n_seqs = n_ctg;
+    std::vector<bntann1_t> anns(n_ctg > 0 ? n_ctg : 1);
+    char nm[] = "ctg";
+    for (int i = 0; i < n_ctg; ++i) { memset(&anns[i], 0, sizeof(bntann1_t)); anns[i].name = nm; anns[i].anno = nm; anns[i].is_alt = ctg_alt ? ctg_alt[i] : 0; }
+    bns.anns = anns.data();
+    std::vector<uint8_t> query(query_in, query_in + l_query);
+    std::vector<mem_alnreg_t> a(n > 0 ? n : 1);
+    for (int i = 0; i < n; ++i) {
+        mem_alnreg_t &x = a[i];
+        memset(&x, 0, sizeof(x));
+        x.rb = r[i].rb; x.re = r[i].re; x.qb = r[i].qb; x.qe = r[i].qe; x.rid = r[i].rid; x.score = r[i].score; x.truesc = r[i].truesc;
+        x.sub = r[i].sub; x.alt_sc = r[i].alt_sc; x.csub = r[i].csub; x.sub_n = r[i].sub_n; x.w = r[i].w; x.seedcov = r[i].seedcov;
+        x.secondary = r[i].secondary; x.secondary_all = r[i].secondary_all; x.seedlen0 = r[i].seedlen0; x.n_comp = r[i].n_comp;
+        x.is_alt = r[i].is_alt; x.frac_rep = r[i].frac_rep; x.hash = r[i].hash;
+    }
+    n = mem_sort_dedup_patch(opt, &bns, pac, query.data(), n, a.data());
+    for (int i = 0; i < n; ++i)
+        if (a[i].rid >= 0 && bns.anns[a[i].rid].is_alt) a[i].is_alt = 1;
+    *n_pri = mem_mark_primary_se(opt, n, a.data(), id);
+    for (int i = 0; i < n; ++i) {
+        const mem_alnreg_t &x = a[i];
+        r[i].rb = x.rb; r[i].re = x.re; r[i].qb = x.qb; r[i].qe = x.qe; r[i].rid = x.rid; r[i].score = x.score; r[i].truesc = x.truesc;
+        r[i].sub = x.sub; r[i].alt_sc = x.alt_sc; r[i].csub = x.csub; r[i].sub_n = x.sub_n; r[i].w = x.w; r[i].seedcov = x.seedcov;
+        r[i].secondary = x.secondary; r[i].secondary_all = x.secondary_all; r[i].seedlen0 = x.seedlen0; r[i].n_comp = x.n_comp;
+        r[i].is_alt = x.is_alt; r[i].frac_rep = x.frac_rep; r[i].hash = x.hash;
+        r[i].mapq = x.secondary < 0 ? mem_approx_mapq_se(opt, &x) : 0;
+    }
     free(opt);
     return n;
 }

@@ -60,7 +60,7 @@ class KswCounters(C.Structure):
 def build_oracle() -> str:
     """(Re)build oracle/liboracle.so if missing or stale; returns its path."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "global_oracle.c", "global_oracle.h", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "global_oracle.c", "region_oracle.c", "region_oracle.h", "global_oracle.h", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
