@@ -88,6 +88,19 @@ READ_RESULT_DTYPE = np.dtype([("seed_rbeg", "<i8"), ("seed_qbeg", "<i4"), ("seed
 assert READ_RESULT_DTYPE.itemsize == C.sizeof(ReadResult) == 72
 
 
+class RegionOpt(C.Structure):
+    """bwa_b200_region_opt_t"""
+    _fields_ = [(k, C.c_int32) for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "w", "min_seed_len", "max_chain_gap", "mapQ_coef_fac")] + \
+               [("mask_level", C.c_float), ("mask_level_redun", C.c_float), ("mapQ_coef_len", C.c_float)]
+
+
+# bwa_b200_alnreg_t
+ALNREG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("hash", "<u8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"),
+                         ("truesc", "<i4"), ("sub", "<i4"), ("alt_sc", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"),
+                         ("seedcov", "<i4"), ("secondary", "<i4"), ("secondary_all", "<i4"), ("seedlen0", "<i4"), ("n_comp", "<i4"),
+                         ("is_alt", "<i4"), ("frac_rep", "<f4"), ("mapq", "<i4")], align=True)
+assert ALNREG_DTYPE.itemsize == 96
+
 # every symbol include/bwamem_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bwa_b200_last_error", "bwa_b200_version", "bwa_b200_device_count", "bwa_b200_host_alloc", "bwa_b200_host_free",
@@ -109,6 +122,7 @@ SYMBOLS = [
     "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_cigars_free",
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
     "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
+    "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
 ]
 
 ALN_IN_DTYPE = np.dtype([("read", "<u4"), ("qb", "<i4"), ("qe", "<i4"), ("rb", "<i8"), ("re", "<i8"), ("truesc", "<i4"), ("w", "<i4")], align=True)
@@ -256,6 +270,9 @@ def lib():
         L.bwa_b200_cigar_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
         L.bwa_b200_reg2aln_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(ExtParams), C.c_int32, vp,
                                             C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+        L.bwa_b200_region_opt_default.argtypes = [C.POINTER(RegionOpt)]
+        L.bwa_b200_region_opt_default.restype = None
+        L.bwa_b200_finish_regions_host.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_int64, C.POINTER(RegionOpt)]
         _lib = L
     return _lib
 
@@ -683,3 +700,25 @@ class Cigar:
         if self.h:
             lib().bwa_b200_cigar_destroy(self.h)
             self.h = None
+
+
+def region_opt(**kw) -> RegionOpt:
+    o = RegionOpt()
+    lib().bwa_b200_region_opt_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def finish_regions(index: Index, packed, word_off, read_len, regs, region_off, opt: RegionOpt, ctg_alt=None, first_read_id=0):
+    """mem_sort_dedup_patch -> is_alt -> mem_mark_primary_se -> mapq for a batch (bwa_b200_finish_regions_host).
+    regs: ALNREG_DTYPE array, read r's regions at [region_off[r], region_off[r+1]).  Returns (list of per-read arrays, n_pri)."""
+    n = read_len.size
+    a = np.ascontiguousarray(regs, dtype=ALNREG_DTYPE).copy()
+    off = np.ascontiguousarray(region_off, dtype=np.uint64)
+    n_out = np.zeros(max(n, 1), np.uint32)
+    n_pri = np.zeros(max(n, 1), np.int32)
+    alt = np.ascontiguousarray(ctg_alt, dtype=np.int32) if ctg_alt is not None else None
+    check(lib().bwa_b200_finish_regions_host(index.h, 0 if alt is None else alt.size, _p(alt) if alt is not None else None, _p(packed), _p(word_off),
+                                             _p(read_len), n, _p(off), _p(a), _p(n_out), _p(n_pri), first_read_id, C.byref(opt)))
+    return [a[int(off[r]):int(off[r]) + int(n_out[r])] for r in range(n)], n_pri[:n]

@@ -418,6 +418,33 @@ uint64_t bwa_b200_aligner_launches(const bwa_b200_aligner_t *a);
 int  bwa_b200_aligner_profile(bwa_b200_aligner_t *a, int enable);
 int  bwa_b200_aligner_kernel_times(bwa_b200_aligner_t *a, const char **names, float *ms, int cap);
 
+/* ---------------------------------------------------------------- regions -> the records SAM is written from
+ * What the reference does to a read's alignment regions once the extension results are in: mem_sort_dedup_patch (redundant hits
+ * dropped, colinear hits joined when one global alignment of the joint span scores within 10 % of the prediction; src/bwamem.c:
+ * 580-681), the is_alt marking of its caller (:2321-2325), mem_mark_primary_se (:715-760; id = index of the read in the run, it
+ * seeds the tie-breaking hash) and mem_approx_mapq_se as mem_reg2aln applies it (:1690-1716, :2363: 0 for secondary hits).
+ * One GPU lane per read runs the reference's own sequence of comparisons (its introsort is not stable, equal keys are common).
+ * The records carry the mem_alnreg_t fields the stage reads or writes (src/bwamem.h:83-112). */
+typedef struct {
+    int32_t a, b, o_del, e_del, o_ins, e_ins, w, min_seed_len, max_chain_gap, mapQ_coef_fac;   /* mapQ_coef_fac is an int in the reference */
+    float   mask_level, mask_level_redun, mapQ_coef_len;
+} bwa_b200_region_opt_t;
+typedef struct {
+    int64_t  rb, re;
+    uint64_t hash;
+    int32_t  qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0, n_comp, is_alt;
+    float    frac_rep;
+    int32_t  mapq;
+} bwa_b200_alnreg_t;
+void bwa_b200_region_opt_default(bwa_b200_region_opt_t *o);   /* mem_opt_init's values (src/bwamem.c:100-140) */
+/* regs[region_off[r] .. region_off[r+1]) are read r's regions on entry; on return the first n_regs_out[r] of that slice are its
+ * finished regions in the reference's final order, n_pri[r] = mem_mark_primary_se's return value.  The reads are 4-bit packed
+ * (bwa_b200_pack_*), the reference is the one attached to idx; ctg_alt (n_ctg flags, may be NULL) = bntann1_t.is_alt. */
+int  bwa_b200_finish_regions_host(const bwa_b200_index_t *idx, int32_t n_ctg, const int32_t *ctg_alt,
+                                  const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len, uint64_t n_reads,
+                                  const uint64_t *region_off, bwa_b200_alnreg_t *regs, uint32_t *n_regs_out, int32_t *n_pri,
+                                  int64_t first_read_id, const bwa_b200_region_opt_t *opt);
+
 #ifdef __cplusplus
 }
 #endif

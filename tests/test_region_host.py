@@ -1,0 +1,74 @@
+"""The per-read region-finishing source meant for the CUDA kernels (region_core.cuh: sort / dedup / patch, primary marking, mapq),
+built for the host, against the fork's golden vectors and the oracle (oracle/region_oracle.c, itself pinned to the reference fork).
+Runs on the CPU box."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tests", "host_emul")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from oracle import chain_py as CP, region_py as RP
+    so = os.path.join(HERE, "libregion_host.so")
+    srcs = [os.path.join(HERE, "region_host.cpp"), os.path.join(ROOT, "bwa-mem_gpu_b200", "csrc", "region_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "bwa-mem_gpu_b200", "csrc"), srcs[0], "-o", so])
+    L = C.CDLL(so)
+    L.region_host_read.restype = C.c_int
+    L.region_host_read.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int)]
+
+    def run(opt, ctg, fwd, query, regs, rid_id):
+        a = np.ascontiguousarray(regs.copy())
+        q = np.ascontiguousarray(query, dtype=np.uint8)
+        n_pri = C.c_int(0)
+        n = L.region_host_read(C.addressof(opt), ctg.l_pac, ctg.alt.ctypes.data, fwd.ctypes.data, len(q), q.ctypes.data, len(a), a.ctypes.data,
+                               rid_id, C.byref(n_pri))
+        return a[:n], int(n_pri.value)
+    return run
+
+
+def _maker():
+    spec = importlib.util.spec_from_file_location("mkreg", os.path.join(GOLD, "make_region_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    return mk
+
+
+def test_region_core_matches_fork_golden(emul, oracle):
+    from oracle import chain_py as CP, region_py as RP
+    mk = _maker()
+    gold = np.load(os.path.join(GOLD, "region_golden.npz"))
+    ctg = CP.Contigs(tuple(int(x) for x in gold["contigs"]), alt=tuple(int(x) for x in gold["alt"]))
+    g = synth.make_genome(ctg.l_pac, seed=int(gold["genome_seed"]))
+    reads, regs_in, in_off = gold["reads"], gold["regs_in"], gold["in_off"]
+    for oi, kw in enumerate(mk.OPTS):
+        opt = RP.default_opt(**kw)
+        want, woff, wpri = gold[f"out_{oi}"], gold[f"out_off_{oi}"], gold[f"n_pri_{oi}"]
+        for i in range(len(reads)):
+            a, n_pri = emul(opt, ctg, g, reads[i], regs_in[in_off[i]:in_off[i + 1]], i)
+            assert n_pri == wpri[i] and RP.equal(a, want[woff[i]:woff[i + 1]]), (oi, i)
+
+
+def test_region_core_matches_oracle_fresh_cases(emul, oracle):
+    from oracle import region_py as RP
+    mk = _maker()
+    ctg, g, reads, cases = mk.make_inputs(n_reads=1500, seed=909)
+    merged = 0
+    for kw in mk.OPTS + (dict(w=5, mask_level=0.9), dict(mapQ_coef_len=100, mapQ_coef_fac=4)):
+        opt = RP.default_opt(**kw)
+        for i, regs in enumerate(cases):
+            a, pa = emul(opt, ctg, g, reads[i], regs, 5000 + i)
+            b, pb = RP.oracle_finish(opt, ctg, g, reads[i], regs, 5000 + i)
+            assert pa == pb and RP.equal(a, b), (kw, i)
+            merged += int((a["n_comp"] > 1).sum())
+    assert merged > 100
