@@ -72,3 +72,53 @@ def test_region_core_matches_oracle_fresh_cases(emul, oracle):
             assert pa == pb and RP.equal(a, b), (kw, i)
             merged += int((a["n_comp"] > 1).sum())
     assert merged > 100
+
+
+def _tie_heavy_case(g, ctg, rng, n_regs, L=150):
+    """many regions with few distinct ends / scores: the sorts run far beyond their insertion-sort range and meet equal keys all the time"""
+    from oracle import region_py as RP
+    l = ctg.l_pac
+    regs = np.zeros(n_regs, RP.REGION_DT)
+    ends = rng.integers(200, l - 200, max(4, n_regs // 40))
+    for k in range(n_regs):
+        qb = int(rng.integers(0, 60)); qe = int(rng.integers(qb + 30, L + 1))
+        re = int(rng.choice(ends)) + (l if k & 1 else 0)
+        ln = qe - qb + int(rng.integers(-2, 3))
+        rb = re - ln
+        if rb < 0 or (rb < l < re):
+            rb, re = 300, 300 + ln
+        regs[k]["rb"], regs[k]["re"], regs[k]["qb"], regs[k]["qe"] = rb, re, qb, qe
+        regs[k]["score"] = regs[k]["truesc"] = int(rng.choice([30, 31, 45, 60]))
+        regs[k]["rid"] = RP._rid(ctg, rb, re)
+        regs[k]["w"] = int(rng.choice([0, 10, 100])); regs[k]["seedcov"] = int(rng.integers(19, 100)); regs[k]["secondary"] = -1
+    return regs
+
+
+def test_region_core_ties_ambiguous_bases_and_large_sets(emul, oracle):
+    """N bases in the read (scored -1 by the patch alignment) and thousands of regions per read with equal keys everywhere;
+    the fork itself is compared when oracle/_ref is present"""
+    from oracle import chain_py as CP, region_py as RP
+    mk = _maker()
+    ctg, g, reads, cases = mk.make_inputs(n_reads=400, seed=31)
+    rng = np.random.default_rng(8)
+    reads = reads.copy()
+    reads[rng.random(reads.shape) < 0.02] = 4
+    pac = CP.make_pac(g) if CP.have_fork() else None
+    opt = RP.default_opt()
+    for i, regs in enumerate(cases):
+        a, pa = emul(opt, ctg, g, reads[i], regs, i)
+        b, pb = RP.oracle_finish(opt, ctg, g, reads[i], regs, i)
+        assert pa == pb and RP.equal(a, b), i
+        if pac is not None:
+            c, pc = RP.fork_finish(opt, ctg, pac, reads[i], regs, i)
+            assert pc == pb and RP.equal(c, b), i
+    for n_regs in (17, 64, 700, 3000):
+        regs = _tie_heavy_case(g, ctg, rng, n_regs)
+        for kw in (dict(), dict(max_chain_gap=50, mask_level_redun=0.5)):
+            opt = RP.default_opt(**kw)
+            a, pa = emul(opt, ctg, g, reads[0], regs, 77)
+            b, pb = RP.oracle_finish(opt, ctg, g, reads[0], regs, 77)
+            assert pa == pb and RP.equal(a, b), (n_regs, kw)
+            if pac is not None:
+                c, pc = RP.fork_finish(opt, ctg, pac, reads[0], regs, 77)
+                assert pc == pb and RP.equal(c, b), (n_regs, kw)
