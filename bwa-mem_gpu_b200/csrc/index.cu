@@ -336,7 +336,7 @@ int build_impl(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *pref
         start[NB] = run;
         parallel_for(n, n_threads, [&](uint64_t a, uint64_t b, int t) {
             uint64_t *h = &hist[(size_t)t * NB];
-            for (uint64_t i = a; i < b; ++i) sa[h[key(i)]++] = (IdxT)i;
+            for (uint64_t i = a; i < b; ++i) sa[h[key(i)]++] = (IdxT)i;      // (gathering a cache line per partition first: no gain measured)
         });
         phase("k-mer partition");
     }
@@ -346,7 +346,10 @@ int build_impl(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *pref
         for (int t = 0; t < n_threads; ++t)
             th.emplace_back([&] {
                 typedef std::pair<uint64_t, IdxT> KeyIdx;
-                std::vector<KeyIdx> buf;
+                std::vector<KeyIdx> buf, buf2;
+                constexpr int RB = 12;                       // large partitions: one counting pass on the key's top 12 bits first
+                std::vector<uint32_t> cnt((1u << RB) + 1);
+                auto lt = [&](const KeyIdx &x, const KeyIdx &y) { return x.first != y.first ? x.first < y.first : P.less(x.second, y.second); };
                 for (;;) {
                     const uint64_t k = next.fetch_add(1);
                     if (k >= NB) break;
@@ -354,10 +357,23 @@ int build_impl(const uint8_t *fwd, uint64_t l_pac, int sa_intv, const char *pref
                     if (m < 2) continue;
                     buf.resize(m);
                     for (uint64_t e = 0; e < m; ++e) { const IdxT p = sa[a + e]; buf[e] = KeyIdx(P.window((uint64_t)p + K), p); }
-                    std::sort(buf.begin(), buf.end(), [&](const KeyIdx &x, const KeyIdx &y) {
-                        return x.first != y.first ? x.first < y.first : P.less(x.second, y.second);
-                    });
-                    for (uint64_t e = 0; e < m; ++e) sa[a + e] = buf[e].second;
+                    if (m < 4096 || m > 0xffffffffull) {
+                        std::sort(buf.begin(), buf.end(), lt);
+                        for (uint64_t e = 0; e < m; ++e) sa[a + e] = buf[e].second;
+                        continue;
+                    }
+                    std::fill(cnt.begin(), cnt.end(), 0u);
+                    for (uint64_t e = 0; e < m; ++e) ++cnt[(buf[e].first >> (64 - RB)) + 1];
+                    for (uint32_t d = 0; d < (1u << RB); ++d) cnt[d + 1] += cnt[d];
+                    buf2.resize(m);
+                    for (uint64_t e = 0; e < m; ++e) buf2[cnt[buf[e].first >> (64 - RB)]++] = buf[e];      // cnt[d] is now the END of digit d
+                    uint32_t b0 = 0;
+                    for (uint32_t d = 0; d < (1u << RB); ++d) {
+                        const uint32_t b1 = cnt[d];
+                        if (b1 - b0 > 1) std::sort(buf2.begin() + b0, buf2.begin() + b1, lt);
+                        b0 = b1;
+                    }
+                    for (uint64_t e = 0; e < m; ++e) sa[a + e] = buf2[e].second;
                 }
             });
         for (auto &x : th) x.join();
