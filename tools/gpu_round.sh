@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list. Outputs in gpurun_out/.
+# One GPU-box visit (all tiers): every GPU parity test, smoke, bench (both arms), ncu launch list of one bench run,
+# ncu --set full of the re-seeding and CIGAR kernels.  Outputs in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
@@ -10,8 +11,12 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 tail -3 gpurun_out/smoke.log
 STEPS=${STEPS:-10}
 timeout 1500 python bench.py --steps $STEPS --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -c 6000 gpurun_out/bench.json
+tail -c 2500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "${REF:-1}" = 1 ]; then
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
-cat gpurun_out/bench_ref.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "ncu rc=$?"
+fi
+if [ "${NCU:-1}" = 1 ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "ncu list rc=$?"
+fi
+ls -la gpurun_out/
