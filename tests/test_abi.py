@@ -47,3 +47,17 @@ def test_index_load_rejects_stock_layout(pkg, small_index, tmp_path):
         assert b"OCC_INTV_SHIFT 6" in L.bwa_b200_last_error()
     rc = L.bwa_b200_index_load(str(tmp_path / "missing.bwt").encode(), None, 0, ctypes.byref(h))
     assert rc == -2
+
+
+def test_finish_regions_argument_checks_and_no_fallback(pkg):
+    """bad arguments are refused before any device work; with good ones and no device the call fails loudly (no CPU path)"""
+    import numpy as np
+    L = pkg.lib()
+    opt = pkg.region_opt()
+    one = np.zeros(1, np.uint64)
+    rc = L.bwa_b200_finish_regions_host(None, 0, None, None, one.ctypes.data, one.ctypes.data, 0, one.ctypes.data, None, one.ctypes.data,
+                                        one.ctypes.data, 0, ctypes.byref(opt))
+    assert rc == -1 and b"bad argument" in L.bwa_b200_last_error()          # BWA_B200_ERR_ARG: no index
+    assert (opt.a, opt.b, opt.w, opt.min_seed_len, opt.max_chain_gap, opt.mapQ_coef_fac) == (1, 4, 100, 19, 10000, 3)
+    assert abs(opt.mask_level_redun - 0.95) < 1e-6 and opt.mapQ_coef_len == 50.0
+    assert pkg.ALNREG_DTYPE.itemsize == 96
