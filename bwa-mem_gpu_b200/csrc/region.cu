@@ -65,14 +65,24 @@ extern "C" int bwa_b200_finish_regions_host(const bwa_b200_index_t *idx, int32_t
     if (!idx || !opt || !word_off || !read_len || !region_off || !n_regs_out || !n_pri || (n_reads && (!packed || !regs && region_off[n_reads])))
         { b200::set_error("finish_regions: bad argument"); return BWA_B200_ERR_ARG; }
     if (opt->e_del <= 0 || opt->e_ins <= 0 || opt->a <= 0) { b200::set_error("finish_regions: a, e_del and e_ins must be positive"); return BWA_B200_ERR_ARG; }
+    // everything the lanes index with is checked here, before any device work: a region outside its read or outside the text would
+    // send the patch alignment out of bounds
+    const uint64_t n_regs = n_reads ? region_off[n_reads] : 0, n_words = n_reads ? word_off[n_reads] : 0;
+    uint32_t max_len = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        max_len = std::max(max_len, read_len[r]);
+        if (region_off[r + 1] < region_off[r] || word_off[r + 1] < word_off[r] + (read_len[r] + 7) / 8)
+            { b200::set_error("finish_regions: offsets of read %llu are not increasing / its words do not hold %u bases", (unsigned long long)r, read_len[r]); return BWA_B200_ERR_ARG; }
+        for (uint64_t a = region_off[r]; a < region_off[r + 1]; ++a) {
+            const bwa_b200_alnreg_t &x = regs[a];
+            if (x.qb < 0 || x.qe < x.qb || (uint32_t)x.qe > read_len[r] || x.rb < 0 || x.re < x.rb || (idx->l_pac && (uint64_t)x.re > 2 * idx->l_pac) ||
+                (n_ctg > 0 && x.rid >= n_ctg))
+                { b200::set_error("finish_regions: region %llu of read %llu lies outside its read, the reference or the contig table", (unsigned long long)(a - region_off[r]), (unsigned long long)r); return BWA_B200_ERR_ARG; }
+        }
+    }
     B200_CUDA(cudaSetDevice(idx->device));
     if (!idx->d_pac) { b200::set_error("finish_regions: the index has no reference attached (bwa_b200_index_attach_ref)"); return BWA_B200_ERR_ARG; }
     if (n_reads == 0) return BWA_B200_OK;
-    const uint64_t n_regs = region_off[n_reads], n_words = word_off[n_reads];
-    uint32_t max_len = 0;
-    for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_len[r]);
-    for (uint64_t a = 0; a < n_regs; ++a)
-        if (n_ctg > 0 && regs[a].rid >= n_ctg) { b200::set_error("finish_regions: region %llu has rid %d of %d contigs", (unsigned long long)a, regs[a].rid, n_ctg); return BWA_B200_ERR_ARG; }
     int sm = 0;
     B200_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, idx->device));
     const unsigned grid = (unsigned)std::min<uint64_t>((n_reads + FIN_THREADS - 1) / FIN_THREADS, (uint64_t)sm * 8);

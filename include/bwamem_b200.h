@@ -439,7 +439,9 @@ typedef struct {
 void bwa_b200_region_opt_default(bwa_b200_region_opt_t *o);   /* mem_opt_init's values (src/bwamem.c:100-140) */
 /* regs[region_off[r] .. region_off[r+1]) are read r's regions on entry; on return the first n_regs_out[r] of that slice are its
  * finished regions in the reference's final order, n_pri[r] = mem_mark_primary_se's return value.  The reads are 4-bit packed
- * (bwa_b200_pack_*), the reference is the one attached to idx; ctg_alt (n_ctg flags, may be NULL) = bntann1_t.is_alt. */
+ * (bwa_b200_pack_*), the reference is the one attached to idx; ctg_alt (n_ctg flags, may be NULL) = bntann1_t.is_alt.
+ * BWA_B200_ERR_ARG when a region lies outside its read ([qb, qe) within read_len), outside the text ([rb, re) within 2*l_pac) or names
+ * a contig beyond n_ctg: checked on the host before any device work. */
 int  bwa_b200_finish_regions_host(const bwa_b200_index_t *idx, int32_t n_ctg, const int32_t *ctg_alt,
                                   const uint32_t *packed, const uint64_t *word_off, const uint32_t *read_len, uint64_t n_reads,
                                   const uint64_t *region_off, bwa_b200_alnreg_t *regs, uint32_t *n_regs_out, int32_t *n_pri,
