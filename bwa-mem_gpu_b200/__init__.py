@@ -710,6 +710,18 @@ def region_opt(**kw) -> RegionOpt:
     return o
 
 
+def alnregs_from_regions(regions: np.ndarray) -> np.ndarray:
+    """the regions bwa_b200_align_* returns (REGION_DTYPE) as the records bwa_b200_finish_regions_host takes: the mem_alnreg_t fields
+    mem_chain2aln and the extension results have filled by then (src/bwamem.c:1263-1472, 2297-2306); sub / csub / sub_n stay 0 as in the
+    fork, which never fills them before this stage; secondary = -1"""
+    a = np.zeros(regions.size, ALNREG_DTYPE)
+    for k in ("rb", "re", "qb", "qe", "rid", "score", "truesc", "w", "seedcov", "seedlen0", "frac_rep"):
+        a[k] = regions[k]
+    a["secondary"] = -1
+    a["secondary_all"] = -1
+    return a
+
+
 def finish_regions(index: Index, packed, word_off, read_len, regs, region_off, opt: RegionOpt, ctg_alt=None, first_read_id=0):
     """mem_sort_dedup_patch -> is_alt -> mem_mark_primary_se -> mapq for a batch (bwa_b200_finish_regions_host).
     regs: ALNREG_DTYPE array, read r's regions at [region_off[r], region_off[r+1]).  Returns (list of per-read arrays, n_pri)."""

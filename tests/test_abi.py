@@ -61,3 +61,15 @@ def test_finish_regions_argument_checks_and_no_fallback(pkg):
     assert (opt.a, opt.b, opt.w, opt.min_seed_len, opt.max_chain_gap, opt.mapQ_coef_fac) == (1, 4, 100, 19, 10000, 3)
     assert abs(opt.mask_level_redun - 0.95) < 1e-6 and opt.mapQ_coef_len == 50.0
     assert pkg.ALNREG_DTYPE.itemsize == 96
+
+
+def test_alnregs_from_regions_maps_the_alnreg_fields(pkg):
+    import numpy as np
+    r = np.zeros(3, pkg.REGION_DTYPE)
+    r["rb"], r["re"], r["qb"], r["qe"] = [10, 2000, 5], [160, 2150, 90], [0, 3, 1], [150, 150, 86]
+    r["rid"], r["score"], r["truesc"], r["w"], r["seedcov"], r["seedlen0"], r["frac_rep"] = [0, 1, 0], [140, 120, 60], [140, 118, 60], 100, [150, 80, 40], [19, 33, 25], [0, .5, 0]
+    a = pkg.alnregs_from_regions(r)
+    assert a.dtype == pkg.ALNREG_DTYPE and a.size == 3
+    for k in ("rb", "re", "qb", "qe", "rid", "score", "truesc", "w", "seedcov", "seedlen0", "frac_rep"):
+        assert (a[k] == r[k]).all(), k
+    assert (a["secondary"] == -1).all() and (a["sub"] == 0).all() and (a["csub"] == 0).all() and (a["n_comp"] == 0).all() and (a["is_alt"] == 0).all()
