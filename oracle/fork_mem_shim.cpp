@@ -49,6 +49,14 @@ int mem_chain_flt(const mem_opt_t *opt, int n_chn, mem_chain_t *a);
 int mem_sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *query, int n, mem_alnreg_t *a);
 int mem_mark_primary_se(const mem_opt_t *opt, int n, mem_alnreg_t *a, int64_t id);
 int mem_approx_mapq_se(const mem_opt_t *opt, const mem_alnreg_t *a);
+void ks_combsort_mem_ars2(size_t n, mem_alnreg_t a[]);      /* KSORT_INIT instances of src/bwamem.c:565-575 */
+void ks_combsort_mem_ars(size_t n, mem_alnreg_t a[]);
+void ks_combsort_mem_ars_hash(size_t n, mem_alnreg_t a[]);
+void ks_combsort_mem_ars_hash2(size_t n, mem_alnreg_t a[]);
+void ks_introsort_mem_ars2(size_t n, mem_alnreg_t a[]);
+void ks_introsort_mem_ars(size_t n, mem_alnreg_t a[]);
+void ks_introsort_mem_ars_hash(size_t n, mem_alnreg_t a[]);
+void ks_introsort_mem_ars_hash2(size_t n, mem_alnreg_t a[]);
 void mem_flt_chained_seeds(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, int n_chn, mem_chain_t *a);
 void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const uint8_t *query, const mem_chain_t *c,
                    mem_alnreg_v *regs, int *curr_read_offset, int *curr_ref_offset, gpu_batch *curr_gpu_batch_short, gpu_batch *curr_gpu_batch_long);
@@ -306,6 +314,31 @@ int fork_finish_regs(const fork_region_opt_t *fo, int64_t l_pac, int n_ctg, cons
     }
     free(opt);
     return n;
+}
+
+/* the fork's own sort instances on the same records: comb != 0 -> ks_combsort, else ks_introsort; which = 0 mem_ars2 (end), 1 mem_ars
+ * (score), 2 mem_ars_hash, 3 mem_ars_hash2.  Only the fields the comparators read and an identity (seedlen0) travel. */
+void fork_sort_regs(int comb, int which, int n, fork_region_t *r)
+{
+    std::vector<mem_alnreg_t> a(n > 0 ? n : 1);
+    for (int i = 0; i < n; ++i) {
+        memset(&a[i], 0, sizeof(mem_alnreg_t));
+        a[i].rb = r[i].rb; a[i].re = r[i].re; a[i].qb = r[i].qb; a[i].qe = r[i].qe; a[i].score = r[i].score; a[i].is_alt = r[i].is_alt;
+        a[i].hash = r[i].hash; a[i].seedlen0 = r[i].seedlen0;
+    }
+    if (n > 0) {
+        if (comb) {
+            if (which == 0) ks_combsort_mem_ars2(n, a.data()); else if (which == 1) ks_combsort_mem_ars(n, a.data());
+            else if (which == 2) ks_combsort_mem_ars_hash(n, a.data()); else ks_combsort_mem_ars_hash2(n, a.data());
+        } else {
+            if (which == 0) ks_introsort_mem_ars2(n, a.data()); else if (which == 1) ks_introsort_mem_ars(n, a.data());
+            else if (which == 2) ks_introsort_mem_ars_hash(n, a.data()); else ks_introsort_mem_ars_hash2(n, a.data());
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        r[i].rb = a[i].rb; r[i].re = a[i].re; r[i].qb = a[i].qb; r[i].qe = a[i].qe; r[i].score = a[i].score; r[i].is_alt = a[i].is_alt;
+        r[i].hash = a[i].hash; r[i].seedlen0 = a[i].seedlen0;
+    }
 }
 
 } /* extern "C" */

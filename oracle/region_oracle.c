@@ -94,6 +94,19 @@ static void introsort(lt_fn lt, size_t n, region_t *a)
     }
 }
 
+/* the comb-sort fallback of the introsort runs only when quicksort degenerates (depth 2 log2 n), which random inputs never reach:
+ * exported so that the tests can drive it directly.  which: 0 end, 1 score, 2 hash, 3 hash2 */
+void region_combsort(int which, int n, region_t *a)
+{
+    static const lt_fn f[4] = {lt_end, lt_score, lt_hash, lt_hash2};
+    if (n > 0) combsort(f[which & 3], (size_t)n, a);
+}
+void region_introsort(int which, int n, region_t *a)
+{
+    static const lt_fn f[4] = {lt_end, lt_score, lt_hash, lt_hash2};
+    introsort(f[which & 3], (size_t)n, a);
+}
+
 /* ---- mem_patch_reg, src/bwamem.c:580-618: can hit a (upstream) be joined with hit b by one global alignment? ---- */
 #define PATCH_MAX_R_BW 0.05f
 #define PATCH_MIN_SC_RATIO 0.90f

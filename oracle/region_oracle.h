@@ -38,6 +38,9 @@ int region_approx_mapq_se(const region_opt_t *o, const region_t *a);
  * (ctg_alt may be NULL), primary marking with id = index of the read in the run, mapq.  Returns the new count; *n_pri as above. */
 int region_finish_read(const region_opt_t *o, int64_t l_pac, const int32_t *ctg_alt, const uint8_t *fwd, const uint8_t *query,
                        int n, region_t *a, int64_t id, int *n_pri);
+/* the sorts alone (src/ksort.h:146-226 with the comparators of src/bwamem.c:565-575): which = 0 end, 1 score, 2 hash, 3 hash2 */
+void region_combsort(int which, int n, region_t *a);
+void region_introsort(int which, int n, region_t *a);
 #ifdef __cplusplus
 }
 #endif

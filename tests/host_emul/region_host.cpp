@@ -14,3 +14,16 @@ extern "C" int region_host_read(const Opt *o, int64_t l_pac, const int32_t *ctg_
     std::vector<int32_t> z((size_t)(n > 0 ? n : 1));
     return finish_read(*o, l_pac, ctg_alt, ByteRef{fwd}, ByteQuery{query}, n, a, id, n_pri, eh.data(), z.data());
 }
+
+// the sorts alone; which = 0 end, 1 score, 2 hash, 3 hash2
+extern "C" void region_host_sort(int comb, int which, int n, Reg *a)
+{
+    if (n <= 0) return;
+    if (comb) {
+        if (which == 0) combsort(LtEnd(), n, a); else if (which == 1) combsort(LtScore(), n, a);
+        else if (which == 2) combsort(LtHash(), n, a); else combsort(LtHash2(), n, a);
+    } else {
+        if (which == 0) introsort(LtEnd(), n, a); else if (which == 1) introsort(LtScore(), n, a);
+        else if (which == 2) introsort(LtHash(), n, a); else introsort(LtHash2(), n, a);
+    }
+}

@@ -122,3 +122,38 @@ def test_region_core_ties_ambiguous_bases_and_large_sets(emul, oracle):
             if pac is not None:
                 c, pc = RP.fork_finish(opt, ctg, pac, reads[0], regs, 77)
                 assert pc == pb and RP.equal(c, b), (n_regs, kw)
+
+
+def test_region_sorts_alone_incl_comb_sort_fallback(emul, oracle):
+    """ks_introsort's comb-sort fallback only runs when quicksort degenerates, which the stage tests never cause: the four sort
+    instances (and the comb sort by itself) of the device source, of the oracle and -- when oracle/_ref is present -- of the fork, on
+    arrays full of equal keys; seedlen0 carries each record's identity so that the permutation itself is compared"""
+    import ctypes as C
+    from oracle import chain_py as CP, region_py as RP, oracle_py as O
+    L = C.CDLL(os.path.join(HERE, "libregion_host.so"))
+    L.region_host_sort.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    OL = O.lib()
+    OL.region_combsort.argtypes = OL.region_introsort.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    OL.region_combsort.restype = OL.region_introsort.restype = None
+    FL = None
+    if CP.have_fork():
+        FL = CP.fork_lib()
+        FL.fork_sort_regs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        FL.fork_sort_regs.restype = None
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 3, 9, 10, 11, 16, 17, 18, 40, 129, 1000, 5000):
+        for distinct in (2, 7, 10 ** 6):
+            a = np.zeros(n, RP.REGION_DT)
+            a["re"] = rng.integers(0, distinct, n); a["rb"] = rng.integers(0, distinct, n); a["qb"] = rng.integers(0, distinct, n)
+            a["score"] = rng.integers(0, distinct, n); a["is_alt"] = rng.integers(0, 2, n); a["hash"] = rng.integers(0, distinct, n).astype(np.uint64)
+            a["seedlen0"] = np.arange(n)
+            for comb in (0, 1):
+                for which in range(4):
+                    x, y = a.copy(), a.copy()
+                    L.region_host_sort(comb, which, n, x.ctypes.data)
+                    (OL.region_combsort if comb else OL.region_introsort)(which, n, y.ctypes.data)
+                    assert (x["seedlen0"] == y["seedlen0"]).all(), (n, distinct, comb, which)
+                    if FL is not None:
+                        z = a.copy()
+                        FL.fork_sort_regs(comb, which, n, z.ctypes.data)
+                        assert (x["seedlen0"] == z["seedlen0"]).all(), (n, distinct, comb, which, "fork")
