@@ -45,7 +45,6 @@ constexpr int N_PBINS = 16;              // bins of the column-pair kernel; the 
 constexpr int N_KEYED = 8;
 __constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512};
 constexpr int PAIR_MAX_Q = 512;          // longest query the column-pair kernel stages (shared memory)
-constexpr int PAIR_NT = 64;              // lanes per block of the column-pair kernel (32 for the long bins, see ext_launch)
 constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
 constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
 

@@ -207,11 +207,6 @@ __device__ __forceinline__ uint32_t seeds_of(uint32_t s, int max_occ)
     return cnt < (uint32_t)max_occ ? cnt : (uint32_t)max_occ;
 }
 
-__device__ __forceinline__ uint4 ld_cand(const Cand *p)
-{ // {k.lo, k.hi, s, x | end << 16}
-    return *reinterpret_cast<const uint4 *>(p);       // plain load: the array is rewritten in place by this kernel
-}
-
 #ifndef BACK_MIN_BLOCKS
 #define BACK_MIN_BLOCKS 10
 #endif
@@ -236,7 +231,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");   // .cg: no L1 allocation
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // RESEED: the candidates come from fwd2_kernel (pass 2 of mem_collect_intv): bits 48..63 of a candidate's k hold min_intv - 1 of its
