@@ -72,3 +72,19 @@ def test_oracle_edge_cases(oracle):
     assert list(res[0]) == [5, 0, 0, 0, -1, 0]          # no target rows: score = h0
     assert res[1][0] == 1                                # all-N query never beats h0
     assert res[2][0] == 30
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_builder_and_oracle_locate_reads_at_their_true_place(pkg, oracle, tmp_path, wide):
+    """ground truth instead of a hash: error-free reads cut from known places of both strands come back as one seed at that place
+    (tools/check_wide_index.py at a small size; the same tool checks an index beyond 2^32 rows)"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, BWA_B200_BUILD_WIDE=wide, WIDE_PREFIX=str(tmp_path / "w"))
+    env.pop("WIDE_GPU", None)
+    out = subprocess.run([sys.executable, os.path.join(pkg.ROOT, "tools", "check_wide_index.py"), "2500000", "300"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    assert info["all_located_at_truth"] and info["rows"] == 5000000 and info["noisy_seeds"] > 300
