@@ -157,3 +157,44 @@ def test_region_sorts_alone_incl_comb_sort_fallback(emul, oracle):
                         z = a.copy()
                         FL.fork_sort_regs(comb, which, n, z.ctypes.data)
                         assert (x["seedlen0"] == z["seedlen0"]).all(), (n, distinct, comb, which, "fork")
+
+
+def test_region_core_on_regions_of_real_reads(emul, oracle, small_index):
+    """the stage's real input distribution: regions that seeding -> chaining -> extension (the oracle pipeline, itself pinned to the
+    reference) produce for reads with errors on a genome with repeats, re-seeding on (more chains, more overlapping regions);
+    device source == oracle (== the fork when oracle/_ref is present)"""
+    from oracle import chain_py as CP, region_py as RP
+    g, prefix = small_index
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    reads, _, _ = synth.make_reads(g, 1500, 150, seed=77, sub_rate=0.03, ins_rate=0.004, del_rate=0.004)
+    n, L = reads.shape
+    rf = reads.reshape(-1).copy()
+    off = (np.arange(n + 1) * L).astype(np.uint64)
+    sd = oi.seed_batch(rf, off, 19, 500, n_threads=4, rs=oracle.reseed())
+    oi.close()
+    ctg = CP.Contigs((g.size,))
+    kp = oracle.make_params(w=100, zdrop=100, use_band=1)
+    qq = np.stack([sd["qbeg"], sd["qend"]], axis=1).astype(np.int32)
+    want = CP.oracle_align_batch(CP.default_opt(max_occ=500, w=100), ctg, g, list(reads), sd["rbeg"], qq, sd["score"], sd["n_seeds"], sd["seed_off"], 0, kp)
+    regs, aln, nr = want["regs"], want["aln"], want["n_regions"]
+    a = np.zeros(len(regs), RP.REGION_DT)
+    for k in ("rb", "re", "qb", "qe", "score", "truesc"):
+        a[k] = aln[k]
+    for k in ("rid", "w", "seedcov", "seedlen0", "frac_rep"):
+        a[k] = regs[k]
+    a["secondary"] = a["secondary_all"] = -1
+    ro = np.concatenate([[0], np.cumsum(nr)]).astype(np.int64)
+    pac = CP.make_pac(g) if CP.have_fork() else None
+    opt = RP.default_opt()
+    multi = dropped = secondary = 0
+    for i in range(n):
+        mine = a[ro[i]:ro[i + 1]]
+        keep = mine[(mine["qe"] > mine["qb"]) & (mine["re"] > mine["rb"])]
+        x, px = emul(opt, ctg, g, reads[i], keep, i)
+        y, py = RP.oracle_finish(opt, ctg, g, reads[i], keep, i)
+        assert px == py and RP.equal(x, y), i
+        if pac is not None:
+            z, pz = RP.fork_finish(opt, ctg, pac, reads[i], keep, i)
+            assert pz == py and RP.equal(z, y), i
+        multi += int(len(keep) > 1); dropped += len(keep) - len(y); secondary += int((y["secondary"] >= 0).sum())
+    assert multi > 50 and dropped > 20 and secondary > 10
