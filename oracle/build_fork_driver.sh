@@ -7,6 +7,8 @@
 #                                looks for GASAL2's and GPUSeed's headers: ../GASAL2/include/ and src/GPUSeed/) and linked
 #                                to bwa-mem_gpu_b200/libbwamem_b200.so instead of libgasal.a + libseed.a.  This is the
 #                                drop-in of INTEGRATION.md section A, exercised for real.
+#   oracle/_ref/bwa-gasal2-cpu  the same objects linked to oracle/cpu_compat.cpp instead: both boundaries on the CPU with the reference's
+#                                own bwt_smem1 / bwt_sa / ksw_extend2 -- the SAM-level checker of tests/test_gpu_sam.py.
 #   oracle/_ref/bwa-gasal2-ref   the same driver with the reference's own GPU libraries (GPUSeed seed_gen.cu, GASAL2
 #                                *.cpp + gasal_align.cu; flags of GASAL2/run_all.sh: MAX_SEQ_LEN=153 N_CODE=4 N_PENALTY=1)
 #                                compiled for sm_100 -- the reference GPU path, to diff SAM against on the GPU box.
@@ -41,7 +43,11 @@ cp "$ROOT"/include/compat/seed_gen.h "$A/src/GPUSeed/seed_gen.h"
 compile_host "$A"
 ( cd "$A/src"; objs=""; for o in $OBJS; do objs="$objs $o.o"; done
   g++ $objs shd_stub.o -o "$OUT/bwa-gasal2-b200" -L"$ROOT/bwa-mem_gpu_b200" -lbwamem_b200 \
-      -Wl,-rpath,'$ORIGIN/../../bwa-mem_gpu_b200' -L"$CUDA/lib64" -lcudart -lm -lz -ldl -lpthread -lrt )
+      -Wl,-rpath,'$ORIGIN/../../bwa-mem_gpu_b200' -L"$CUDA/lib64" -lcudart -lm -lz -ldl -lpthread -lrt
+  # the same objects over the CPU checker (oracle/cpu_compat.cpp: the reference's bwt_smem1 / bwt_sa from libbwaref.so and the
+  # driver's own ksw_extend2): the SAM this binary writes is what the B200 one must reproduce byte for byte
+  g++ -c -O2 -g -std=c++11 -w -I../GASAL2/include -IGPUSeed -I"$CUDA/include" "$HERE/cpu_compat.cpp" -o cpu_compat.o
+  g++ $objs shd_stub.o cpu_compat.o -o "$OUT/bwa-gasal2-cpu" -lm -lz -ldl -lpthread -lrt )
 
 # ---- (2) the driver over the reference's own GPU libraries, sm_100
 B="$TMP/ref"; mkdir -p "$B/src" "$B/GASAL2/include" "$B/GASAL2/src"
@@ -58,7 +64,7 @@ ARCH="-gencode arch=compute_100,code=sm_100"
   "$CUDA/bin/nvcc" -c -O3 -std=c++11 -w -Xcompiler -w $GDEF $ARCH -lineinfo --default-stream per-thread gasal_align.cu -o gasal_align.o &
   wait )
 ( cd "$B/src/GPUSeed"
-  "$CUDA/bin/nvcc" -c --device-c -O3 -std=c++14 -w -Xcompiler -w $ARCH -lineinfo --default-stream per-thread -I.. seed_gen.cu -o seed_gen.o
+  "$CUDA/bin/nvcc" -c --device-c -O3 -std=c++14 -w -Xcompiler -w $ARCH -lineinfo --default-stream per-thread -I.. -I"$CUDA/include/nvtx3" seed_gen.cu -o seed_gen.o
   "$CUDA/bin/nvcc" $ARCH -dlink seed_gen.o -o dlink.o )
 ( cd "$B/src"; objs=""; for o in $OBJS; do objs="$objs $o.o"; done
   g++ $objs shd_stub.o GPUSeed/seed_gen.o GPUSeed/dlink.o ../GASAL2/src/*.o -o "$OUT/bwa-gasal2-ref" \

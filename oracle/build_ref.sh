@@ -6,6 +6,7 @@
 #   libforkksw.so  src/ksw.c + oracle/fork_ksw_shim.c  (fork's ksw_extend2 with opt_ext)
 #   bwa7 / bwa6    the reference's index builder compiled with OCC_INTV_SHIFT 7 / 6,
 #                  i.e. the two passes of the reference's build_index.sh:46-66
+#   bwa7p          bwa7 with the broken .sa reader replaced (oracle/ref_sa_shim.c): runs `bwa mem` / `bwa fastmap`
 # The reference's bwt.h hard-codes OCC_INTV_SHIFT and its own build script rewrites that
 # line with sed between the two passes; we do the same on a scratch copy under $TMPDIR.
 # Nothing from /root/reference is copied into the repository.
@@ -31,6 +32,14 @@ for shift in 7 6; do
     for o in $LOBJS $AOBJS; do gcc -c $CFLAGS $o.c -o $o.o & done; wait
     objs=""; for o in $LOBJS $AOBJS; do objs="$objs $o.o"; done
     gcc $CFLAGS $objs -o "$OUT/bwa$shift" -lm -lz -lpthread -lrt
+    if [ "$shift" = 7 ]; then
+      # bwa7p: the same program with the one loader that cannot read the reference's own .sa replaced (oracle/ref_sa_shim.c):
+      # the CPU `bwa mem` / `bwa fastmap` that bench.py and tools/sam_check.py time and diff against
+      gcc -c $CFLAGS -Dbwt_restore_sa=bwt_restore_sa_as_shipped bwt.c -o bwt_p.o
+      gcc -c $CFLAGS -I. "$HERE/ref_sa_shim.c" -o ref_sa_shim.o
+      pobjs=""; for o in $LOBJS $AOBJS; do if [ "$o" = bwt ]; then pobjs="$pobjs bwt_p.o"; else pobjs="$pobjs $o.o"; fi; done
+      gcc $CFLAGS $pobjs ref_sa_shim.o -o "$OUT/bwa7p" -lm -lz -lpthread -lrt
+    fi
     if [ "$shift" = 7 ]; then
       # ref_collect_shim.c #includes the unmodified bwamem.c (to reach its static mem_collect_intv) and so stands in for bwamem.o
       lobjs=""; for o in $LOBJS; do [ "$o" = bwamem ] || lobjs="$lobjs $o.o"; done
