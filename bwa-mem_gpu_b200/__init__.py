@@ -108,7 +108,7 @@ SYMBOLS = [
     "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
     "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
-    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
+    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_measure_int_alu", "bwa_b200_int_alu_op_name", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
@@ -204,6 +204,9 @@ def lib():
         L.bwa_b200_seeder_launches.restype = C.c_uint64
         L.bwa_b200_measure_random_sector_gbs.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.bwa_b200_measure_random_sector_gbs.restype = C.c_double
+        L.bwa_b200_measure_int_alu.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.bwa_b200_int_alu_op_name.argtypes = [C.c_int]
+        L.bwa_b200_int_alu_op_name.restype = C.c_char_p
         L.bwa_b200_ext_params_default.argtypes = [C.POINTER(ExtParams)]
         L.bwa_b200_fill_scmat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.bwa_b200_extender_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]
@@ -734,3 +737,14 @@ def finish_regions(index: Index, packed, word_off, read_len, regs, region_off, o
     check(lib().bwa_b200_finish_regions_host(index.h, 0 if alt is None else alt.size, _p(alt) if alt is not None else None, _p(packed), _p(word_off),
                                              _p(read_len), n, _p(off), _p(a), _p(n_out), _p(n_pri), first_read_id, C.byref(opt)))
     return [a[int(off[r]):int(off[r]) + int(n_out[r])] for r in range(n)], n_pri[:n]
+
+
+def measure_int_alu(device: int = 0) -> dict:
+    """issue rates of the extension kernels' integer instructions (warp-instructions per clock per SM), measured on the device"""
+    rates = (C.c_double * 16)()
+    mhz, n_sm = C.c_double(0), C.c_int(0)
+    n = lib().bwa_b200_measure_int_alu(device, rates, 16, C.byref(mhz), C.byref(n_sm))
+    if n < 0:
+        check(n)
+    return {"sm_mhz": mhz.value, "n_sm": n_sm.value,
+            "warp_inst_per_clk_per_sm": {lib().bwa_b200_int_alu_op_name(i).decode(): rates[i] for i in range(n)}}

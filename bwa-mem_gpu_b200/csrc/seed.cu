@@ -707,18 +707,25 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
 }
 
 // Random 32-byte-sector gather: the roofline denominator for the seeding kernels.
-// Every lane issues `iters` independent 256-bit loads at hashed sector addresses of a buffer.
+// Every lane issues `iters` independent 256-bit loads at hashed sector addresses of a buffer, RS_UNROLL of them in flight
+// at a time (2048 resident lanes per SM x 8 = 16 K sectors in flight per SM: the memory system, not the issue rate, is the limit;
+// the range reduction is a multiply-high, not a 64-bit modulo).
+constexpr int RS_UNROLL = 8;
 __global__ void __launch_bounds__(256)
 random_sector_kernel(const uint32_t *__restrict__ buf, uint64_t n_sectors, int iters, uint32_t *__restrict__ sink)
 {
     uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
     const uint64_t pol = bucket_policy();
-#pragma unroll 4
-    for (int i = 0; i < iters; ++i) {
-        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-        Bkt b = ld_bucket(buf, x % n_sectors, pol);
-        acc += b.c[0] ^ b.w[3];
+    for (int i = 0; i < iters; i += RS_UNROLL) {
+        Bkt b[RS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RS_UNROLL; ++u) {
+            x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+            b[u] = ld_bucket(buf, __umul64hi(x * 0x94D049BB133111EBull, n_sectors), pol);
+        }
+#pragma unroll
+        for (int u = 0; u < RS_UNROLL; ++u) acc += b[u].c[0] ^ b[u].w[3];
     }
     if (acc == 0x7fffffffu) sink[0] = acc;
 }
@@ -1169,17 +1176,19 @@ extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads
     return BWA_B200_OK;
 }
 
-// measured random-sector read throughput in GB/s over a buffer of `bytes` (0 on failure)
+// measured random-sector read throughput in GB/s over a buffer of `bytes` (0 on failure): best of `reps` launches after one
+// warm-up launch; `iters` loads per lane (rounded up to a multiple of 8) -- 2048 gives about 40 GB of traffic per launch
 extern "C" double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps)
 {
     if (cudaSetDevice(device) != cudaSuccess) return 0;
     uint32_t *buf = nullptr, *sink = nullptr;
-    if (cudaMalloc(&buf, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (bytes < 4096 || cudaMalloc(&buf, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaMalloc(&sink, 4);
     cudaMemset(buf, 1, bytes);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     int blocks = prop.multiProcessorCount * 8;
+    iters = (iters + RS_UNROLL - 1) / RS_UNROLL * RS_UNROLL;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     double best = 0;

@@ -157,6 +157,12 @@ uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s);
 /* random 32-byte-sector gather throughput (GB/s) over a scratch buffer of `bytes`: the measured
  * denominator for the seeding roofline; > L2-sized buffers measure HBM, small ones measure L2 */
 double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps);
+/* measured denominator for the extension roofline: issue rate, in warp-instructions per clock per SM, of the integer instructions
+ * the extension kernels are made of (op i is named by bwa_b200_int_alu_op_name(i): IADD3, LOP3, PRMT, VIMNMX.S32, VIADDMNMX.S32,
+ * VIMNMX3.S32, VIADDMNMX.S16x2, VIMNMX3.S16x2, IMAD), at full occupancy with independent chains; *sm_mhz = the SM clock measured
+ * under that load, *n_sm = the SM count.  Returns the number of rates written (9) or a negative error code. */
+int  bwa_b200_measure_int_alu(int device, double *rates, int cap, double *sm_mhz, int *n_sm);
+const char *bwa_b200_int_alu_op_name(int i);
 
 /* ----------------------------------------------------------------- extension */
 typedef struct bwa_b200_extender bwa_b200_extender_t;

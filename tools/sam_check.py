@@ -55,7 +55,10 @@ def stock_prefix(prefix):
 def run(cmd, out_path, cwd):
     t0 = time.time()
     with open(out_path, "wb") as fo, open(out_path + ".log", "wb") as fe:
-        rc = subprocess.call(cmd, stdout=fo, stderr=fe, cwd=cwd)
+        try:
+            rc = subprocess.call(cmd, stdout=fo, stderr=fe, cwd=cwd, timeout=600)
+        except subprocess.TimeoutExpired:
+            rc = -999
     return rc, time.time() - t0
 
 
