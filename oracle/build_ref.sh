@@ -71,9 +71,9 @@ if [ -f "$CUDA_INC/cuda_runtime.h" ]; then
   CXXF="-O2 -g -std=c++11 -fpermissive -fPIC -w -DHAVE_PTHREAD -I$CUDA_INC -IGPUSeed"
   FOBJS="bwamem bntseq bwa utils kstring ksw bwt bwamem_pair bwamem_extra kthread malloc_wrap"
   for o in $FOBJS; do g++ -c $CXXF $o.c -o $o.o & done; wait
-  g++ -c $CXXF -I. "$HERE/fork_mem_shim.cpp" -o fork_mem_shim.o
+  g++ -c $CXXF -fopenmp -I. "$HERE/fork_mem_shim.cpp" -o fork_mem_shim.o
   objs=""; for o in $FOBJS; do objs="$objs $o.o"; done
-  g++ -shared $CXXF $objs fork_mem_shim.o -o "$OUT/libforkmem.so" -lm -lz -lpthread )
+  g++ -shared $CXXF -fopenmp $objs fork_mem_shim.o -o "$OUT/libforkmem.so" -lm -lz -lpthread )
 else
   echo "[build_ref] no CUDA headers: libforkmem.so not built" >&2
 fi

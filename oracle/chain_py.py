@@ -270,3 +270,70 @@ def oracle_reg2aln(opt, kp, ctg: Contigs, fwd, query, qb, qe, rb, re, truesc, ar
                       int(qb), int(qe), int(rb), int(re), int(truesc), int(ar_w), _ptr(out), _ptr(cig), cap)
     assert n >= 0
     return out[0], cig[:n].copy()
+
+
+# ------------------------------------------------------------------ CPU arm of the chained step (bench.py, kind "reference")
+FORK_ALN_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"), ("rid", "<i4"),
+                        ("seedcov", "<i4"), ("seedlen0", "<i4"), ("w", "<i4"), ("frac_rep", "<f4"), ("pad", "<i4")], align=True)
+assert FORK_ALN_DT.itemsize == 56
+
+
+def ref_seed_arrays(handle, reads, read_off, min_seed_len=19, max_occ=0, n_threads=None):
+    """pass-1 SMEM seeds of a batch from the REFERENCE's own bwt_smem1 / bwt_sa (oracle/_ref/libbwaref.so), layout of mem_seed_v_gpu"""
+    L = O.ref_lib()
+    if not getattr(L, "_seed_arrays", False):
+        L.ref_seed_arrays.argtypes = [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64]
+        L.ref_seed_arrays.restype = C.c_int64
+        L._seed_arrays = True
+    n = read_off.size - 1
+    reads = np.ascontiguousarray(reads, dtype=np.uint8); read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+    n_seeds = np.zeros(max(n, 1), np.uint32); seed_off = np.zeros(max(n, 1), np.uint64)
+    cap = max(1024, 8 * n)
+    while True:
+        rbeg = np.empty(cap, np.uint64); qq = np.empty(2 * cap, np.int32); score = np.empty(cap, np.uint32)
+        tot = L.ref_seed_arrays(handle, _ptr(reads), _ptr(read_off), n, min_seed_len, max_occ, n_threads or O.default_threads(),
+                                _ptr(n_seeds), _ptr(seed_off), _ptr(rbeg), _ptr(qq), _ptr(score), cap)
+        if tot >= 0:
+            break
+        cap = -tot + 1024
+    return dict(total=int(tot), n_seeds=n_seeds[:n], seed_off=seed_off[:n], rbeg=rbeg[:tot], qq=qq[:2 * tot].reshape(-1, 2), score=score[:tot])
+
+
+def fork_align_batch(opt, ctg: Contigs, pac, reads, read_off, seeds, ksw_params, n_threads=None):
+    """seeds -> chains -> jobs -> ksw_extend2 -> regions of a whole batch with the FORK's own host functions (oracle/_ref/libforkmem.so,
+    fork_mem_shim.cpp fork_align_batch).  seeds: dict from ref_seed_arrays (all rows of every SMEM group).  Returns dict(n_regs, reg_off,
+    regs[FORK_ALN_DT], n_jobs)."""
+    L = fork_lib()
+    if not getattr(L, "_align_batch", False):
+        L.fork_align_batch.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]
+        L.fork_align_batch.restype = C.c_int64
+        L._align_batch = True
+    n = read_off.size - 1
+    reads = np.ascontiguousarray(reads, dtype=np.uint8); read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+    rbeg = np.ascontiguousarray(seeds["rbeg"], dtype=np.uint64); qq = np.ascontiguousarray(seeds["qq"], dtype=np.int32).reshape(-1)
+    score = np.ascontiguousarray(seeds["score"], dtype=np.uint32)
+    ns = np.ascontiguousarray(seeds["n_seeds"], dtype=np.uint32); so = np.ascontiguousarray(seeds["seed_off"], dtype=np.uint64)
+    if rbeg.size == 0:
+        rbeg = np.zeros(1, np.uint64); qq = np.zeros(2, np.int32); score = np.zeros(1, np.uint32)
+    n_regs = np.zeros(max(n, 1), np.uint32); reg_off = np.zeros(max(n, 1), np.uint64)
+    cap = max(1024, 3 * n)
+    nj = C.c_uint64(0)
+    while True:
+        regs = np.zeros(cap, FORK_ALN_DT)
+        tot = L.fork_align_batch(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(ctg.alt), _ptr(pac), n, _ptr(reads), _ptr(read_off),
+                                 _ptr(rbeg), _ptr(qq), _ptr(score), _ptr(ns), _ptr(so), ksw_params.w, ksw_params.zdrop, ksw_params.end_bonus,
+                                 ksw_params.use_band, ksw_params.pen_clip, _ptr(n_regs), _ptr(reg_off), _ptr(regs), cap, n_threads or O.default_threads(), C.byref(nj))
+        if tot >= 0:
+            break
+        cap = int(n_regs.sum()) + 16
+    return dict(n_regs=n_regs[:n], reg_off=reg_off[:n], regs=regs[:tot], n_jobs=int(nj.value))
+
+
+def ref_chained_pipeline(handle, opt, ctg: Contigs, pac, reads, read_off, ksw_params, min_seed_len=19, n_threads=None):
+    """the CPU reference of bwa_b200_align_*: the reference's bwt_smem1 / bwt_sa for the seeds, the fork's mem_chain ... mem_chain2aln and
+    ksw_extend2 for everything after, all host threads"""
+    seeds = ref_seed_arrays(handle, reads, read_off, min_seed_len, 0, n_threads)
+    out = fork_align_batch(opt, ctg, pac, reads, read_off, seeds, ksw_params, n_threads)
+    out["n_seeds"] = seeds["total"]
+    return out

@@ -24,6 +24,7 @@
 #include <vector>
 #include "bwamem.h"
 #include "bntseq.h"
+#include "ksw.h"
 #include "utils.h"
 #include "GPUSeed/seed_gen.h"
 
@@ -63,8 +64,8 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 
 /* ---- GASAL2 host-side contract over plain memory ---- */
 struct SideBuf { std::vector<uint8_t> q, t; };
-static SideBuf g_buf[2];
-static gasal_gpu_storage_t *g_sto[2] = {NULL, NULL};
+static thread_local SideBuf g_buf[2];                       /* per thread: fork_align_batch runs reads on several threads */
+static thread_local gasal_gpu_storage_t *g_sto[2] = {NULL, NULL};
 
 Parameters::Parameters(int argc_, char **argv_) : sa(1), sb(4), gapo(6), gape(1), print_out(0), n_threads(1), k_band(0), isPacked(false), isReverseComplement(false), argc(argc_), argv(argv_) {}
 Parameters::~Parameters() {}
@@ -339,6 +340,120 @@ void fork_sort_regs(int comb, int which, int n, fork_region_t *r)
         r[i].rb = a[i].rb; r[i].re = a[i].re; r[i].qb = a[i].qb; r[i].qe = a[i].qe; r[i].score = a[i].score; r[i].is_alt = a[i].is_alt;
         r[i].hash = a[i].hash; r[i].seedlen0 = a[i].seedlen0;
     }
+}
+
+/* ---- the CPU arm of bench.py's chained step: a whole read batch through the fork's own host code, on n_threads threads ----
+ * Per read, in the order of the reference worker (src/bwamem.c:2055-2093, :2286-2306):
+ *   mem_chain -> mem_chain_flt -> mem_flt_chained_seeds -> mem_chain2aln per kept chain   (the fork's functions, unmodified)
+ *   every extension job of the read's SHORT then LONG batch through the fork's ksw_extend2 (src/ksw.c:864) with the given band /
+ *   z-drop / end bonus, the local-vs-to-end rule of decoy_cpu_align (src/bwamem.c:1892-1901),
+ *   the result gathering of the worker (src/bwamem.c:2286-2306; restated here, it is inline code of the worker).
+ * Seeds arrive in the reference layout of mem_seed_v_gpu for the whole batch (seed_off = exclusive prefix sums, every SMEM group
+ * holding all its rows).  Output: n_regs[r] and, at reg_off[r] (exclusive prefix sums, computed here), one fork_aln_t per region in
+ * the order mem_chain2aln created them.  Returns the total number of regions, or -1 when cap_regs is too small (n_regs is still
+ * filled).  cells_out (may be NULL) receives nothing: the fork's ksw_extend2 has no cell counter. */
+typedef struct { int64_t rb, re; int32_t qb, qe, score, truesc, rid, seedcov, seedlen0, w; float frac_rep; int32_t pad; } fork_aln_t;
+
+int64_t fork_align_batch(const fork_opt_t *fo, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                         const uint8_t *pac, int64_t n_reads, const uint8_t *reads, const uint64_t *read_off,
+                         const uint64_t *rbeg, const int32_t *qbeg_qend, const uint32_t *score, const uint32_t *n_seeds, const uint64_t *seed_off,
+                         int ext_w, int ext_zdrop, int ext_end_bonus, int ext_use_band, int pen_clip,
+                         uint32_t *n_regs, uint64_t *reg_off, fork_aln_t *regs_out, int64_t cap_regs, int n_threads, uint64_t *n_jobs_out)
+{
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::vector<fork_aln_t> > per_read((size_t)n_reads);
+    uint64_t n_jobs_total = 0;
+#pragma omp parallel num_threads(n_threads) reduction(+:n_jobs_total)
+    {
+        mem_opt_t *opt = mem_opt_init();
+        opt->a = fo->a; opt->b = fo->b; opt->o_del = fo->o_del; opt->e_del = fo->e_del; opt->o_ins = fo->o_ins; opt->e_ins = fo->e_ins;
+        opt->w = fo->w; opt->min_seed_len = fo->min_seed_len; opt->max_occ = fo->max_occ; opt->max_chain_gap = fo->max_chain_gap;
+        opt->min_chain_weight = fo->min_chain_weight; opt->max_chain_extend = fo->max_chain_extend;
+        opt->mask_level = fo->mask_level; opt->drop_ratio = fo->drop_ratio;
+        bwa_fill_scmat(opt->a, opt->b, opt->mat);
+        bntseq_t bns;
+        memset(&bns, 0, sizeof(bns));
+        bns.l_pac = l_pac; bns.n_seqs = n_ctg;
+        std::vector<bntann1_t> anns(n_ctg);
+        char nm[] = "ctg";
+        for (int i = 0; i < n_ctg; ++i) { memset(&anns[i], 0, sizeof(bntann1_t)); anns[i].offset = ctg_off[i]; anns[i].len = ctg_len[i]; anns[i].is_alt = ctg_alt ? ctg_alt[i] : 0; anns[i].name = nm; anns[i].anno = nm; }
+        bns.anns = anns.data();
+        if (!g_sto[0]) { g_sto[0] = new_storage(); g_sto[1] = new_storage(); }
+        std::vector<uint8_t> q;
+        std::vector<int32_t> tri[2];
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const int l_query = (int)(read_off[r + 1] - read_off[r]);
+            q.assign(reads + read_off[r], reads + read_off[r + 1]);
+            mem_seed_v_gpu gr;
+            memset(&gr, 0, sizeof(gr));
+            uint32_t ns = n_seeds[r], zero = 0;
+            gr.rbeg = (bwtint_t_gpu *)(rbeg + seed_off[r]); gr.qbeg = (int2 *)(qbeg_qend + 2 * seed_off[r]); gr.score = (uint32_t *)(score + seed_off[r]);
+            gr.n_ref_pos_fow_rev_results = &ns; gr.n_ref_pos_fow_rev_prefix_sums = &zero;
+            gpu_batch gb[2];
+            for (int s = 0; s < 2; ++s) {
+                memset(&gb[s], 0, sizeof(gpu_batch));
+                gb[s].gpu_storage = g_sto[s];
+                g_sto[s]->current_n_alns = 0;
+                g_buf[s].q.clear(); g_buf[s].t.clear();
+            }
+            int cur_read_off[2] = {0, 0}, cur_ref_off[2] = {0, 0};
+            mem_chain_v chn = mem_chain(opt, NULL, &bns, l_query, q.data(), &gr, 0);
+            chn.n = mem_chain_flt(opt, (int)chn.n, chn.a);
+            mem_flt_chained_seeds(opt, &bns, pac, l_query, q.data(), (int)chn.n, chn.a);
+            mem_alnreg_v regs;
+            regs.n = regs.m = 0; regs.a = NULL;
+            for (size_t i = 0; i < chn.n; ++i) {
+                mem_chain2aln(opt, &bns, pac, l_query, q.data(), &chn.a[i], &regs, cur_read_off, cur_ref_off, &gb[SHORT], &gb[LONG]);
+                free(chn.a[i].seeds);
+            }
+            free(chn.a);
+            for (int s = 0; s < 2; ++s) {                      /* the extension jobs of this read */
+                tri[s].resize((size_t)gb[s].n_seqs * 3 + 3);
+                n_jobs_total += (uint64_t)gb[s].n_seqs;
+                for (int k = 0; k < gb[s].n_seqs; ++k) {
+                    const uint32_t ql = g_sto[s]->host_query_batch_lens[k], tl = g_sto[s]->host_target_batch_lens[k];
+                    const uint8_t *qs = g_buf[s].q.data() + g_sto[s]->host_query_batch_offsets[k], *ts = g_buf[s].t.data() + g_sto[s]->host_target_batch_offsets[k];
+                    int qle, tle, gtle, gscore, max_off;
+                    const int sc = ksw_extend2((int)ql, qs, (int)tl, ts, 5, opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, ext_w, ext_end_bonus, ext_zdrop,
+                                               (int)g_sto[s]->host_seed_scores[k], &qle, &tle, &gtle, &gscore, &max_off, ext_use_band);
+                    int32_t *t3 = &tri[s][(size_t)k * 3];
+                    if (gscore <= 0 || gscore <= sc - pen_clip) { t3[0] = sc; t3[1] = qle; t3[2] = tle; }
+                    else { t3[0] = gscore; t3[1] = (int)ql; t3[2] = gtle; }
+                }
+            }
+            std::vector<fork_aln_t> &out = per_read[(size_t)r];
+            out.resize(regs.n);
+            int is = 0, il = 0;
+            for (size_t i = 0; i < regs.n; ++i) {              /* src/bwamem.c:2217-2306 */
+                const mem_alnreg_t *a = &regs.a[i];
+                fork_aln_t *o = &out[i];
+                int32_t part[2][3] = {{0, 0, 0}, {0, 0, 0}};
+                if (a->seedlen0 != l_query && a->align_sides > 0) {
+                    memcpy(part[a->where_is_long ? 1 : 0], &tri[LONG][(size_t)3 * il++], sizeof(int32_t) * 3);
+                    if (a->align_sides == 2) memcpy(part[a->where_is_long ? 0 : 1], &tri[SHORT][(size_t)3 * is++], sizeof(int32_t) * 3);
+                    o->score = part[0][0] + part[1][0] - (a->align_sides == 2 ? a->seedlen0 : 0);
+                    o->qb = a->query_seed_begin - part[0][1];
+                    o->qe = a->query_seed_begin + a->seedlen0 + part[1][1];
+                    o->rb = a->target_seed_begin - part[0][2];
+                    o->re = a->target_seed_begin + a->seedlen0 + part[1][2];
+                    o->truesc = o->score;
+                } else {
+                    o->score = o->truesc = a->score; o->qb = 0; o->qe = l_query; o->rb = a->target_seed_begin; o->re = a->target_seed_begin + a->seedlen0;
+                }
+                o->rid = a->rid; o->seedcov = a->seedcov; o->seedlen0 = a->seedlen0; o->w = a->w; o->frac_rep = a->frac_rep; o->pad = 0;
+            }
+            free(regs.a);
+        }
+        free(opt);
+    }
+    uint64_t tot = 0;
+    for (int64_t r = 0; r < n_reads; ++r) { n_regs[r] = (uint32_t)per_read[(size_t)r].size(); reg_off[r] = tot; tot += n_regs[r]; }
+    if (n_jobs_out) *n_jobs_out = n_jobs_total;
+    if ((int64_t)tot > cap_regs) return -1;
+    for (int64_t r = 0; r < n_reads; ++r)
+        if (n_regs[r]) memcpy(regs_out + reg_off[r], per_read[(size_t)r].data(), sizeof(fork_aln_t) * n_regs[r]);
+    return (int64_t)tot;
 }
 
 } /* extern "C" */

@@ -132,6 +132,73 @@ int64_t ref_seed_batch(void *h, const uint8_t *reads, const uint64_t *read_off, 
     return total;
 }
 
+/* the seeds themselves, in the layout of mem_seed_v_gpu (seed_gen.h:68-75): pass-1 SMEMs of length >= min_seed_len in query
+ * order, rows k + t*step for t < count (max_occ <= 0: all rows), `score` = occurrence count on the first row of a group.
+ * n_seeds[r] / seed_off[r] per read; returns the total, or -(total) when `cap` was too small (nothing past cap written). */
+typedef struct { uint64_t rbeg; int32_t qb, qe; uint32_t score; } ref_seed_rec_t;
+int64_t ref_seed_arrays(void *h, const uint8_t *reads, const uint64_t *read_off, int64_t n_reads, int min_seed_len, int max_occ, int n_threads,
+                        uint32_t *n_seeds, uint64_t *seed_off, uint64_t *rbeg, int32_t *qbeg_qend, uint32_t *score, int64_t cap)
+{
+    bwt_t *bwt = (bwt_t *)h;
+    if (n_threads < 1) n_threads = 1;
+    ref_seed_rec_t **tv = (ref_seed_rec_t **)calloc((size_t)n_threads, sizeof(*tv));
+    size_t *tn = (size_t *)calloc((size_t)n_threads, sizeof(size_t)), *tm = (size_t *)calloc((size_t)n_threads, sizeof(size_t));
+    uint64_t *where = (uint64_t *)malloc(8 * (size_t)(n_reads ? n_reads : 1));
+    uint16_t *who = (uint16_t *)malloc(2 * (size_t)(n_reads ? n_reads : 1));
+#pragma omp parallel num_threads(n_threads)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        bwtintv_v mem = {0, 0, 0}, t0 = {0, 0, 0}, t1 = {0, 0, 0};
+        bwtintv_v *tmpv[2] = {&t0, &t1};
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const uint8_t *q = reads + read_off[r];
+            int len = (int)(read_off[r + 1] - read_off[r]), x = 0;
+            where[r] = tn[tid]; who[r] = (uint16_t)tid;
+            uint32_t ns = 0;
+            while (len >= min_seed_len && x < len) {
+                if (q[x] < 4) {
+                    x = bwt_smem1(bwt, len, q, x, 1, &mem, tmpv);
+                    for (size_t i = 0; i < mem.n; ++i) {
+                        bwtintv_t *p = &mem.a[i];
+                        int qb = (int)(p->info >> 32), qe = (int)(uint32_t)p->info;
+                        if (qe - qb < min_seed_len) continue;
+                        uint64_t s = p->x[2], step = 1, count = s;
+                        if (max_occ > 0) { step = s > (uint64_t)max_occ ? s / (uint64_t)max_occ : 1; count = (s + step - 1) / step; if (count > (uint64_t)max_occ) count = (uint64_t)max_occ; }
+                        for (uint64_t t = 0; t < count; ++t) {
+                            if (tn[tid] == tm[tid]) { tm[tid] = tm[tid] ? tm[tid] * 2 : 4096; tv[tid] = (ref_seed_rec_t *)realloc(tv[tid], tm[tid] * sizeof(ref_seed_rec_t)); }
+                            ref_seed_rec_t *o = &tv[tid][tn[tid]++];
+                            o->rbeg = bwt_sa(bwt, p->x[0] + t * step); o->qb = qb; o->qe = qe; o->score = t == 0 ? (uint32_t)s : 0u;
+                            ++ns;
+                        }
+                    }
+                } else ++x;
+            }
+            n_seeds[r] = ns;
+        }
+        free(mem.a); free(t0.a); free(t1.a);
+    }
+    uint64_t tot = 0;
+    for (int64_t r = 0; r < n_reads; ++r) { seed_off[r] = tot; tot += n_seeds[r]; }
+    int over = (int64_t)tot > cap;
+    if (!over) {
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const ref_seed_rec_t *src = tv[who[r]] + where[r];
+            for (uint32_t i = 0; i < n_seeds[r]; ++i) {
+                uint64_t o = seed_off[r] + i;
+                rbeg[o] = src[i].rbeg; qbeg_qend[2 * o] = src[i].qb; qbeg_qend[2 * o + 1] = src[i].qe; score[o] = src[i].score;
+            }
+        }
+    }
+    for (int t = 0; t < n_threads; ++t) free(tv[t]);
+    free(tv); free(tn); free(tm); free(where); free(who);
+    return over ? -(int64_t)tot : (int64_t)tot;
+}
+
 void ref_ksw_batch(int64_t n, const uint8_t *qseq, const uint32_t *qoff, const uint32_t *qlen,
                    const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen, const uint32_t *h0,
                    const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop,

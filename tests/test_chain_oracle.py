@@ -89,3 +89,32 @@ def test_regs_finish_arithmetic():
     assert (out["score"][0], out["qb"][0], out["qe"][0], out["rb"][0], out["re"][0]) == (55 + 60 - 30, 0, 150, 1000 - 49, 1000 + 30 + 72)
     assert (out["score"][1], out["qb"][1], out["qe"][1], out["rb"][1], out["re"][1]) == (90, 0, 150, 2000 - 111, 2040)
     assert (out["score"][2], out["qb"][2], out["qe"][2], out["rb"][2], out["re"][2]) == (150, 0, 150, 3000, 3150)
+
+
+@pytest.mark.skipif(not (CP.have_fork() and CP.O.have_ref()), reason="oracle/_ref not built")
+def test_reference_chained_pipeline_equals_oracle_batch(pkg, small_index):
+    """bench.py's CPU arm for the chained step (the reference's bwt_smem1 / bwt_sa, the fork's mem_chain .. mem_chain2aln and
+    ksw_extend2, multi-threaded) gives the oracle's regions, read by read"""
+    from oracle import oracle_py as O
+    from tools import synth
+    g, prefix = small_index
+    n, L = 600, 150
+    reads, _, _ = synth.make_reads(g, n, L, seed=91, sub_rate=0.02, n_rate=0.002)
+    flat = reads.reshape(-1).copy()
+    off = (np.arange(n + 1) * L).astype(np.uint64)
+    ctg = CP.Contigs((g.size,))
+    opt = CP.default_opt(w=100)
+    kp = O.make_params()
+    h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+    assert h
+    got = CP.ref_chained_pipeline(h, opt, ctg, CP.make_pac(g), flat, off, kp, 19, n_threads=3)
+    oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    sd = oi.seed_batch(flat, off, 19, 0, n_threads=2)            # all rows of every SMEM group
+    assert sd["total"] == got["n_seeds"]
+    want = CP.oracle_align_batch(opt, ctg, g, reads, sd["rbeg"], np.stack([sd["qbeg"], sd["qend"]], axis=1).astype(np.int32), sd["score"],
+                                 sd["n_seeds"], sd["seed_off"], 1, kp, n_threads=2)
+    assert (got["n_regs"] == want["n_regions"]).all() and got["n_jobs"] == len(want["jobs"])
+    assert len(got["regs"]) == len(want["aln"]) > n
+    for f in ("rb", "re", "qb", "qe", "score", "truesc"):
+        assert (got["regs"][f] == want["aln"][f]).all(), f
+    assert (got["regs"]["seedcov"] == want["regs"]["seedcov"]).all() and (got["regs"]["rid"] == want["regs"]["rid"]).all()
