@@ -104,7 +104,7 @@ assert ALNREG_DTYPE.itemsize == 96
 # every symbol include/bwamem_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "bwa_b200_last_error", "bwa_b200_version", "bwa_b200_device_count", "bwa_b200_host_alloc", "bwa_b200_host_free",
-    "bwa_b200_index_load", "bwa_b200_index_from_host", "bwa_b200_index_clone_to", "bwa_b200_index_info",
+    "bwa_b200_index_load", "bwa_b200_index_from_host", "bwa_b200_index_clone_to", "bwa_b200_index_info", "bwa_b200_index_set_kmer_table",
     "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
     "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
@@ -186,6 +186,7 @@ def lib():
         L.bwa_b200_index_clone_to.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.bwa_b200_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
         L.bwa_b200_index_free.argtypes = [vp]
+        L.bwa_b200_index_set_kmer_table.argtypes = [vp, C.c_int]
         L.bwa_b200_build_index.argtypes = [vp, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int]
         L.bwa_b200_packed_words.argtypes = [vp, C.c_uint64]
         L.bwa_b200_packed_words.restype = C.c_size_t
@@ -347,6 +348,10 @@ class Index:
         info = IndexInfo()
         check(lib().bwa_b200_index_info(self.h, C.byref(info)))
         return info
+
+    def set_kmer_table(self, K: int):
+        """rebuild the k-mer interval table with another K (0 drops it)"""
+        check(lib().bwa_b200_index_set_kmer_table(self.h, int(K)))
 
     def attach_ref(self, fwd_codes: np.ndarray):
         fwd = np.ascontiguousarray(fwd_codes, dtype=np.uint8)

@@ -103,8 +103,23 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
     v.pack_size = (uint32_t)pack_size;
     // bwa_index/bwt.c:82-112: no high bits are kept when seq_len < 2^32
     v.pack_mask = (seq_len >> 32) == 0 ? 0u : (pack_size >= 32 ? 0xffffffffu : ((1u << pack_size) - 1));
+    // bucket loads keep evict_last only while the bucket array is of the order of the L2 size; beyond, that priority goes to the k-mer table
+    v.bkt_evict_last = padded * 4 <= (192ull << 20) ? 1u : 0u;
+    {   // k-mer interval table (seed.cu): K = 11 by default, BWA_B200_KMER_K = 0 .. 14 overrides, 0 = none
+        const char *ev = getenv("BWA_B200_KMER_K");
+        int K = ev ? atoi(ev) : 11;
+        while (K > 0 && (1ull << (2 * K)) > seq_len) --K;        // a tiny text does not need 4^K patterns
+        int rc = b200_index_build_kmer_table(idx, K);
+        if (rc) { bwa_b200_index_free(idx); return rc; }
+    }
     *out = idx;
     return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_index_set_kmer_table(bwa_b200_index_t *idx, int K)
+{
+    if (!idx || K < 0) { b200::set_error("index_set_kmer_table: bad argument"); return BWA_B200_ERR_ARG; }
+    return b200_index_build_kmer_table(idx, K);
 }
 
 extern "C" int bwa_b200_index_load(const char *bwt_path, const char *sa_path, int device, bwa_b200_index_t **out)
@@ -161,6 +176,7 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
     idx->device = device;
     idx->d_bkt = idx->d_sa = idx->d_sa_hi = nullptr;
     idx->d_pac = nullptr; idx->l_pac = 0;
+    idx->d_kt = nullptr; idx->v.kt = nullptr;
     uint64_t padded = (src->n_words + 7) / 8 * 8 + 8;
     B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
     B200_CUDA(cudaMemcpyPeer(idx->d_bkt, device, src->d_bkt, src->device, padded * 4));
@@ -171,6 +187,12 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
         B200_CUDA(cudaMemcpyPeer(idx->d_sa_hi, device, src->d_sa_hi, src->device, src->n_hi * 4));
     }
     idx->v.bkt = idx->d_bkt; idx->v.sa = idx->d_sa; idx->v.sa_hi = idx->d_sa_hi;
+    if (src->d_kt) {
+        const uint64_t bytes = (((1ull << (2 * (src->kt_K + 1))) - 4) / 3) * 8;
+        B200_CUDA(cudaMalloc(&idx->d_kt, bytes));
+        B200_CUDA(cudaMemcpyPeer(idx->d_kt, device, src->d_kt, src->device, bytes));
+        idx->v.kt = idx->d_kt;
+    }
     *out = idx;
     return BWA_B200_OK;
 }
@@ -183,7 +205,7 @@ extern "C" int bwa_b200_index_info(const bwa_b200_index_t *idx, bwa_b200_index_i
     info->n_buckets = (idx->v.seq_len + 63) / 64;
     info->n_sa = idx->n_sa; info->sa_intv = idx->sa_intv; info->pack_size = idx->pack_size;
     info->device = idx->device;
-    info->hbm_bytes = ((idx->n_words + 7) / 8 * 8 + 8) * 4 + idx->n_sa * 4 + idx->n_hi * 4;
+    info->hbm_bytes = ((idx->n_words + 7) / 8 * 8 + 8) * 4 + idx->n_sa * 4 + idx->n_hi * 4 + (idx->kt_K ? (((1ull << (2 * (idx->kt_K + 1))) - 4) / 3) * 8 : 0);
     return BWA_B200_OK;
 }
 
@@ -191,7 +213,7 @@ extern "C" void bwa_b200_index_free(bwa_b200_index_t *idx)
 {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    cudaFree(idx->d_bkt); cudaFree(idx->d_sa); cudaFree(idx->d_sa_hi); cudaFree(idx->d_pac);
+    cudaFree(idx->d_bkt); cudaFree(idx->d_sa); cudaFree(idx->d_sa_hi); cudaFree(idx->d_pac); cudaFree(idx->d_kt);
     delete idx;
 }
 

@@ -46,11 +46,43 @@ struct Bkt { uint32_t c[4]; uint32_t w[4]; };   // w = {L_lo, L_hi, H_lo, H_hi}
 
 // L2 policy for the bucket array: evict_last, so that the streaming traffic of a batch (candidates,
 // reads, seeds) does not push occurrence buckets out of L2 when the index is of the order of the L2 size
-__device__ __forceinline__ uint64_t bucket_policy()
+// With an index far beyond L2 the buckets get the normal priority instead, and evict_last goes to the k-mer table.
+__device__ __forceinline__ uint64_t evict_last_policy()
 {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+__device__ __forceinline__ uint64_t bucket_policy(const IndexView &ix)
+{
+    uint64_t pol;
+    if (ix.bkt_evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// ---------------------------------------------------------------------------- k-mer table
+// The suffix-array interval of every pattern of up to K bases, as the chain of bwt_extend calls of the reference would compute it
+// (kt_level_kernel below IS that chain, run once per pattern at load time).  A lookup replaces one backward or forward extension whose
+// result is a pattern of at most K bases: one 8-byte load from a table that stays in L2 (45 MB for K = 11) instead of two dependent
+// 32-byte sectors of the bucket array, which for a human-sized index come from HBM.  An entry whose size does not fit 24 bits
+// (the shortest patterns of a large genome) says so and the caller takes the bucket path for that step; those few hundred buckets
+// are L2-hot anyway.  The reference has a hook for the same idea that it leaves switched off (pre_calc_seed_intervals,
+// src/GPUSeed/seed_gen.cu:1169, src/fastmap.c:455).
+constexpr uint32_t KT_SAT = 0xffffffu;
+__device__ __host__ __forceinline__ uint64_t kt_off(int m) { return ((1ull << (2 * m)) - 4) / 3; }   // entries of levels 1 .. m-1
+__device__ __forceinline__ uint64_t ld_kt(const uint64_t *kt, int m, uint32_t val, uint64_t pol)
+{
+    uint64_t e;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(e) : "l"(kt + kt_off(m) + val), "l"(pol));
+    return e;
+}
+// reverse complement of a pattern of m bases (2 bits each, first base most significant)
+__device__ __forceinline__ uint32_t kt_revcomp(uint32_t val, int m)
+{
+    uint32_t r = __brev(val);
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    return (r >> (32 - 2 * m)) ^ ((1u << (2 * m)) - 1u);
 }
 
 __device__ __forceinline__ Bkt ld_bucket(const uint32_t *bkt, uint64_t b, uint64_t pol)
@@ -120,7 +152,7 @@ __device__ __forceinline__ uint64_t L2_at(const IndexView &ix, int b)
 #ifndef FWD_MIN_BLOCKS
 #define FWD_MIN_BLOCKS 8        // measured on B200 (C2): 8 -> 1.41 ms, 10 -> 1.64 ms, 16 -> 2.05 ms (spills)
 #endif
-template <typename RowT, int MINB>
+template <typename RowT, int MINB, bool KT>
 __global__ void __launch_bounds__(FWD_THREADS, MINB)
 fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, uint32_t cand_stride,
@@ -136,17 +168,20 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
 
     RowT k = 0, l = 0;
     const RowT primary = (RowT)ix.primary;
-    const uint64_t pol = bucket_policy();
+    const uint64_t pol = bucket_policy(ix), tpol = evict_last_policy();
+    const int K = KT ? (int)ix.kt_K : 0;
     uint32_t s = 0;
     int x = -1, i = 0;
     uint32_t word = 0;
-    bool active = false;
+    uint32_t val = 0;                    // KT: the match read[x, i) as a pattern, while it has at most K bases
+    bool active = false, l_ok = true;    // KT: l is not tracked through table steps; it is looked up when a bucket step needs it
     auto push = [&](int end) {
         if (end >= min_seed_len)     // streaming store: candidates are read back once, by back_kernel
             __stcs(reinterpret_cast<uint4 *>(out + n_out++), make_uint4((uint32_t)k, (uint32_t)((uint64_t)k >> 32), s, (uint32_t)x | (uint32_t)end << 16));
     };
     auto start_at = [&](int b, int p) {
         k = (RowT)L2_at(ix, b) + 1; s = (uint32_t)(L2_at(ix, b + 1) - L2_at(ix, b)); l = (RowT)L2_at(ix, 3 - b) + 1; x = p; active = true;
+        val = (uint32_t)b; l_ok = true;
     };
 
     word = __ldg(packed + woff);
@@ -167,20 +202,37 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
         }
         // forward extension by complement(b): bwt_extend(ik, ok, 0)  (src/bwt.c:455-470)
         const int cb = 3 - b;
-        RowT p0 = l - 1, p1 = l - 1 + s;                     // rows; both >= 0
-        RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-        Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
-        const Bkt b1 = ld_bucket_or((j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
-        uint32_t tk[4], tl[4];
-        bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
-        bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
-        uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
-        uint32_t ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
-        uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
-        RowT nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
-        if (cb < 3) nk += s3;
-        if (cb < 2) nk += s2;
-        if (cb < 1) nk += s1;
+        RowT nk = 0, nl = 0;
+        uint32_t ns = 0;
+        bool by_table = false;
+        const int m = i - x + 1;             // bases of the match after this extension
+        if (KT && m <= K) {
+            val = (val << 2) | (uint32_t)b;
+            const uint64_t e = ld_kt(ix.kt, m, val, tpol);
+            if ((uint32_t)(e & KT_SAT) != KT_SAT) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); by_table = true; }
+        }
+        if (!by_table) {
+            if (KT && !l_ok) {               // x[1] of the current match = first row of its reverse complement
+                const int m0 = m - 1;
+                const uint32_t cur = m <= K ? val >> 2 : val;
+                l = (RowT)(ld_kt(ix.kt, m0, kt_revcomp(cur, m0), tpol) >> 24);
+            }
+            RowT p0 = l - 1, p1 = l - 1 + s;                     // rows; both >= 0
+            RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+            Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
+            const Bkt b1 = ld_bucket_or((j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
+            uint32_t tk[4], tl[4];
+            bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
+            bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
+            uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
+            ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
+            uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
+            nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
+            if (cb < 3) nk += s3;
+            if (cb < 2) nk += s2;
+            if (cb < 1) nk += s1;
+            nl = (RowT)L2_at(ix, cb) + 1 + tkc;
+        }
         if (ns != s) {
             push(i);
             if (ns == 0) {                   // cannot extend: next bwt_smem1 call starts here
@@ -190,7 +242,9 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
                 continue;
             }
         }
-        k = nk; l = (RowT)L2_at(ix, cb) + 1 + tkc; s = ns;
+        k = nk; s = ns;
+        if (!by_table) l = nl;
+        l_ok = !by_table;
         ++i;
         if ((i & 7) == 0 && i < len) word = __ldg(packed + woff + (uint32_t)(i >> 3));
     }
@@ -235,7 +289,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm vol
 
 // RESEED: the candidates come from fwd2_kernel (pass 2 of mem_collect_intv): bits 48..63 of a candidate's k hold min_intv - 1 of its
 // bwt_smem1 call, and a backward extension fails when the interval gets smaller than min_intv (bwa_index/bwt.c:407) instead of empty.
-template <typename RowT, int MINB, bool RESEED>
+template <typename RowT, int MINB, bool RESEED, bool KT>
 __global__ void __launch_bounds__(BACK_THREADS, MINB)
 back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
             uint32_t n_reads, int min_seed_len, int max_occ,
@@ -250,7 +304,9 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     const uint32_t gtid = blockIdx.x * blockDim.x + tid;
     uint4 *const q = ring[tid >> 5];
     const RowT primary = (RowT)ix.primary;
-    const uint64_t pol = bucket_policy();
+    const uint64_t pol = bucket_policy(ix), tpol = evict_last_policy();
+    const int K = KT ? (int)ix.kt_K : 0;
+    uint32_t win = 0, val = 0;           // KT: the first K bases behind the pivot / the current match, as patterns (first base most significant)
 
     // warp-uniform queue state: slots [head, tail) hold claimed reads
     uint32_t head = 0, tail = 0;
@@ -323,8 +379,21 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 if (x != cur_x) {
                     cur_x = x; first = true; t_head = 0;
                     if (x > 0) bw0 = __ldg(packed + ((uint64_t)woff + ((uint32_t)(x - 1) >> 3)));
+                    if (KT) {            // read[x, x + K) as a pattern; words behind the segment's longest candidate (this one) are not touched
+                        const uint32_t w_first = (uint32_t)x >> 3, w_last = (uint32_t)(end - 1) >> 3;
+                        uint32_t wd[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) wd[j] = __ldg(packed + ((uint64_t)woff + min(w_first + (uint32_t)j, w_last)));
+                        win = 0;
+                        for (int qq = 0; qq < K; ++qq) {
+                            const uint32_t p = (uint32_t)x + (uint32_t)qq, wi = (p >> 3) - w_first;
+                            const uint32_t w = wi == 0 ? wd[0] : (wi == 1 ? wd[1] : wd[2]);
+                            win = (win << 2) | ((w >> (28 - 4 * (p & 7u))) & 3u);
+                        }
+                    }
                 }
                 t = 0; bw = bw0;
+                if (KT) { const int l0 = end - x; val = l0 <= K ? win >> (2 * (K - l0)) : 0u; }
                 need_cand = false;
             }
         }
@@ -336,16 +405,26 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             bool fail = true;
             RowT nk = 0;
             uint32_t ns = 0;
+            uint32_t nval = 0;
             if (b < 4) {       // backward extension by b: only x[0], x[2] are needed downstream
-                const RowT p0 = ck - 1, p1 = ck - 1 + cs;
-                const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-                const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
-                const Bkt b0 = ld_bucket_or((j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
-                const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
-                const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
-                const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
-                ns = ol - ok;
-                nk = (RowT)L2_at(ix, b) + 1 + ok;
+                bool by_table = false;
+                const int m = end - x + t + 1;            // bases of the match after this extension
+                if (KT && m <= K) {
+                    nval = val | (uint32_t)b << (2 * (m - 1));
+                    const uint64_t e = ld_kt(ix.kt, m, nval, tpol);
+                    if ((uint32_t)(e & KT_SAT) != KT_SAT) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); by_table = true; }
+                }
+                if (!by_table) {
+                    const RowT p0 = ck - 1, p1 = ck - 1 + cs;
+                    const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+                    const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
+                    const Bkt b0 = ld_bucket_or((j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
+                    const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
+                    const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
+                    const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
+                    ns = ol - ok;
+                    nk = (RowT)L2_at(ix, b) + 1 + ok;
+                }
                 fail = RESEED ? ns <= mi1 : ns == 0;
             }
             uint32_t *const env_g = env_spill + (uint64_t)gtid * env_stride;     // steps >= ENV_SMEM (rare)
@@ -371,6 +450,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 } else {
                     if (t < ENV_SMEM) env_s[t][tid] = ns; else env_g[t - ENV_SMEM] = ns;
                     ck = nk; cs = ns; ++t;
+                    if (KT) val = nval;
                     if ((i & 7) == 0 && i > 0) bw = __ldg(packed + ((uint64_t)woff + ((uint32_t)(i - 1) >> 3)));   // previous word of the read
                 }
             }
@@ -449,7 +529,7 @@ reseed3_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t
         const uint64_t woff = word_off[r];
         Cand *out = cand2 + (uint64_t)r * xstride;
         const RowT primary = (RowT)ix.primary;
-        const uint64_t pol = bucket_policy();
+        const uint64_t pol = bucket_policy(ix);
         RowT k = 0, l = 0;
         uint32_t s = 0, word = __ldg(packed + woff);
         int x = 0;
@@ -498,7 +578,7 @@ fwd2_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     const Cand *row1 = cand + (uint64_t)r * cand_stride + (n_cand[r] - n1);
     Cand *out = cand3 + (uint64_t)r * stride3;
     const RowT primary = (RowT)ix.primary;
-    const uint64_t pol = bucket_policy();
+    const uint64_t pol = bucket_policy(ix);
     uint32_t n_out = 0, j = 0, s = 0, mi1 = 0;
     RowT k = 0, l = 0;
     int x = 0, i = 0;
@@ -637,7 +717,7 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
 {
     const uint64_t total = min((uint64_t)*total_p, cap);
     const RowT mask = (RowT)((1ull << ix.sa_shift) - 1), primary = (RowT)ix.primary;
-    const uint64_t pol = bucket_policy();
+    const uint64_t pol = bucket_policy(ix);
     bool finished = false, need = true;
     uint64_t idx = 0;
     RowT k = 0;
@@ -716,7 +796,7 @@ random_sector_kernel(const uint32_t *__restrict__ buf, uint64_t n_sectors, int i
 {
     uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
-    const uint64_t pol = bucket_policy();
+    const uint64_t pol = evict_last_policy();
     for (int i = 0; i < iters; i += RS_UNROLL) {
         Bkt b[RS_UNROLL];
 #pragma unroll
@@ -740,20 +820,105 @@ struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { re
 using FwdFn = void (*)(IndexView, const uint32_t *, const uint64_t *, const uint32_t *, uint32_t, int, uint32_t, Cand *, uint32_t *);
 using BackFn = void (*)(IndexView, const uint32_t *, const uint64_t *, uint32_t, int, int, uint32_t, Cand *, const uint32_t *, uint32_t *,
                         uint32_t *, uint32_t *, uint32_t, unsigned long long *);
-// register budget variants (blocks of 128 lanes per SM): more resident lanes = more sectors in flight
-FwdFn fwd_variant(bool narrow, int minb)
+// register budget variants (blocks of 128 lanes per SM): more resident lanes = more sectors in flight; KT = with the k-mer table
+template <typename RowT, bool KT> FwdFn fwd_variant_t(int minb)
 {
-    if (narrow) return minb >= 16 ? fwd_kernel<uint32_t, 16> : (minb >= 12 ? fwd_kernel<uint32_t, 12> : (minb >= 10 ? fwd_kernel<uint32_t, 10> : fwd_kernel<uint32_t, 8>));
-    return minb >= 16 ? fwd_kernel<uint64_t, 16> : (minb >= 12 ? fwd_kernel<uint64_t, 12> : (minb >= 10 ? fwd_kernel<uint64_t, 10> : fwd_kernel<uint64_t, 8>));
+    return minb >= 12 ? fwd_kernel<RowT, 12, KT> : (minb >= 10 ? fwd_kernel<RowT, 10, KT> : fwd_kernel<RowT, 8, KT>);
 }
-template <bool RESEED> BackFn back_variant_t(bool narrow, int minb)
+FwdFn fwd_variant(bool narrow, int minb, bool kt)
 {
-    if (narrow) return minb >= 16 ? back_kernel<uint32_t, 16, RESEED> : (minb >= 12 ? back_kernel<uint32_t, 12, RESEED> : (minb >= 10 ? back_kernel<uint32_t, 10, RESEED> : back_kernel<uint32_t, 8, RESEED>));
-    return minb >= 16 ? back_kernel<uint64_t, 16, RESEED> : (minb >= 12 ? back_kernel<uint64_t, 12, RESEED> : (minb >= 10 ? back_kernel<uint64_t, 10, RESEED> : back_kernel<uint64_t, 8, RESEED>));
+    if (narrow) return kt ? fwd_variant_t<uint32_t, true>(minb) : fwd_variant_t<uint32_t, false>(minb);
+    return kt ? fwd_variant_t<uint64_t, true>(minb) : fwd_variant_t<uint64_t, false>(minb);
 }
-BackFn back_variant(bool narrow, int minb, bool reseed = false) { return reseed ? back_variant_t<true>(narrow, minb) : back_variant_t<false>(narrow, minb); }
+template <typename RowT, bool RESEED, bool KT> BackFn back_variant_t(int minb)
+{
+    return minb >= 12 ? back_kernel<RowT, 12, RESEED, KT> : (minb >= 10 ? back_kernel<RowT, 10, RESEED, KT> : back_kernel<RowT, 8, RESEED, KT>);
+}
+template <bool RESEED> BackFn back_variant_r(bool narrow, int minb, bool kt)
+{
+    if (narrow) return kt ? back_variant_t<uint32_t, RESEED, true>(minb) : back_variant_t<uint32_t, RESEED, false>(minb);
+    return kt ? back_variant_t<uint64_t, RESEED, true>(minb) : back_variant_t<uint64_t, RESEED, false>(minb);
+}
+BackFn back_variant(bool narrow, int minb, bool kt, bool reseed = false) { return reseed ? back_variant_r<true>(narrow, minb, kt) : back_variant_r<false>(narrow, minb, kt); }
+
+// ---- k-mer table construction: level m from level m - 1, one lane per parent pattern P: the four backward extensions c.P of
+// bwt_extend(ik, ok, 1) (src/bwt.c:455-470), exact 64-bit {k, s} kept in scratch arrays, then packed into the table
+template <typename RowT>
+__global__ void __launch_bounds__(256)
+kt_level_kernel(IndexView ix, int m, const uint64_t *__restrict__ pk, const uint64_t *__restrict__ ps, uint64_t *__restrict__ ck, uint64_t *__restrict__ cs)
+{
+    const uint64_t n_parent = 1ull << (2 * (m - 1));
+    const uint64_t P = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= n_parent) return;
+    const RowT primary = (RowT)ix.primary;
+    const uint64_t pol = bucket_policy(ix);
+    const RowT k = (RowT)pk[P], s = (RowT)ps[P];
+    const RowT p0 = k - 1, p1 = k - 1 + s;
+    const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+    const Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
+    const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
+    uint32_t tk[4], tl[4];
+    bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
+    bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint64_t child = ((uint64_t)c << (2 * (m - 1))) | P;
+        ck[child] = L2_at(ix, c) + 1 + tk[c];
+        cs[child] = (uint64_t)(uint32_t)(tl[c] - tk[c]);
+    }
+}
+
+__global__ void kt_level1_kernel(IndexView ix, uint64_t *ck, uint64_t *cs)
+{
+    const int c = threadIdx.x;
+    if (c < 4) { ck[c] = L2_at(ix, c) + 1; cs[c] = L2_at(ix, c + 1) - L2_at(ix, c); }     // bwt_set_intv
+}
+
+__global__ void __launch_bounds__(256)
+kt_pack_kernel(int m, const uint64_t *__restrict__ k, const uint64_t *__restrict__ s, uint64_t *__restrict__ kt, uint64_t sat)
+{
+    const uint64_t n = 1ull << (2 * m);
+    const uint64_t P = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= n) return;
+    const bool fits = s[P] < sat && k[P] < (1ull << 40);
+    kt[kt_off(m) + P] = fits ? (k[P] << 24 | s[P]) : (uint64_t)KT_SAT;
+}
 
 } // namespace
+
+// level sizes beyond a 32-bit occurrence difference cannot arise: the bucket counters are 32-bit (index.cu refuses larger texts)
+int b200_index_build_kmer_table(bwa_b200_index *idx, int K)
+{
+    B200_CUDA(cudaSetDevice(idx->device));
+    if (idx->d_kt) { cudaFree(idx->d_kt); idx->d_kt = nullptr; }
+    idx->kt_K = 0; idx->v.kt = nullptr; idx->v.kt_K = 0;
+    if (K <= 0) return BWA_B200_OK;
+    if (K > 14) K = 14;
+    const uint64_t total = kt_off(K + 1), top = 1ull << (2 * K);
+    uint64_t *d_kt = nullptr, *d_k[2] = {nullptr, nullptr}, *d_s[2] = {nullptr, nullptr};
+    B200_CUDA(cudaMalloc(&d_kt, total * 8));
+    for (int j = 0; j < 2; ++j) { B200_CUDA(cudaMalloc(&d_k[j], top * 8)); B200_CUDA(cudaMalloc(&d_s[j], top * 8)); }
+    const bool narrow = idx->v.seq_len < 0xfffffff0ull;
+    // BWA_B200_KMER_SAT lowers the size from which an entry defers to the bucket path (tests: reach that path on small genomes)
+    uint64_t sat = KT_SAT;
+    if (const char *ev = getenv("BWA_B200_KMER_SAT")) { const long long v = atoll(ev); if (v > 0 && (uint64_t)v < sat) sat = (uint64_t)v; }
+    kt_level1_kernel<<<1, 32>>>(idx->v, d_k[1], d_s[1]);
+    kt_pack_kernel<<<1, 256>>>(1, d_k[1], d_s[1], d_kt, sat);
+    for (int m = 2; m <= K; ++m) {
+        const int src = (m - 1) & 1, dst = m & 1;
+        const uint64_t n_parent = 1ull << (2 * (m - 1));
+        const unsigned grid = (unsigned)((n_parent + 255) / 256);
+        if (narrow) kt_level_kernel<uint32_t><<<grid, 256>>>(idx->v, m, d_k[src], d_s[src], d_k[dst], d_s[dst]);
+        else kt_level_kernel<uint64_t><<<grid, 256>>>(idx->v, m, d_k[src], d_s[src], d_k[dst], d_s[dst]);
+        kt_pack_kernel<<<(unsigned)((4 * n_parent + 255) / 256), 256>>>(m, d_k[dst], d_s[dst], d_kt, sat);
+    }
+    cudaError_t er = cudaDeviceSynchronize();
+    for (int j = 0; j < 2; ++j) { cudaFree(d_k[j]); cudaFree(d_s[j]); }
+    if (er != cudaSuccess || (er = cudaGetLastError()) != cudaSuccess) { cudaFree(d_kt); b200::set_error("k-mer table build failed: %s", cudaGetErrorString(er)); return BWA_B200_ERR_CUDA; }
+    idx->d_kt = d_kt; idx->kt_K = K;
+    idx->v.kt = d_kt; idx->v.kt_K = (uint32_t)K;
+    return BWA_B200_OK;
+}
 
 // =============================================================================== host side
 static int seeder_ensure_cand(bwa_b200_seeder *s, uint64_t n_reads, uint32_t max_len, int min_seed_len)
@@ -834,7 +999,7 @@ extern "C" int bwa_b200_seeder_create(const bwa_b200_index_t *idx, uint64_t max_
     // indexes) so that tests can cover them on small genomes
     const bool narrow_rows = idx->v.seq_len < 0xfffffff0ull && !getenv("BWA_B200_WIDE_ROWS");
     s->narrow_rows = narrow_rows;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_variant(narrow_rows, s->back_minb), BACK_THREADS, 0));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, back_variant(narrow_rows, s->back_minb, idx->v.kt_K > 0), BACK_THREADS, 0));
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, locate_kernel<uint64_t>, LOC_THREADS, 0));
     s->back_grid = s->n_sm * (occ_b > 0 ? occ_b : 1);
     s->loc_grid = s->n_sm * (occ_l > 0 ? occ_l : 1);
@@ -955,7 +1120,7 @@ static int seeder_reseed(bwa_b200_seeder *s)
     }
     // backward phases of the pass-2 calls: the pass-1 kernel, with the per-candidate min_intv (its per-read counts are not used)
     B200_LAUNCH(s->prof, "back_kernel_pass2", st,
-        (back_variant(s->narrow_rows, s->back_minb, true)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, n, p.min_seed_len, p.max_occ, s->stride3,
+        (back_variant(s->narrow_rows, s->back_minb, ix.kt_K > 0, true)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, n, p.min_seed_len, p.max_occ, s->stride3,
                                                                                                  s->d_cand3, s->d_ncand3, s->d_rs_dummy, s->d_rs_dummy + s->max_reads, s->d_env,
                                                                                                  s->env_stride, cnt + 6)));
     B200_LAUNCH(s->prof, "merge_kernel", st,
@@ -1003,9 +1168,9 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     const bool narrow = s->narrow_rows;
     const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
     B200_LAUNCH(s->prof, "fwd_kernel", st,
-        (fwd_variant(narrow, s->fwd_minb)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+        (fwd_variant(narrow, s->fwd_minb, ix.kt_K > 0)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
     B200_LAUNCH(s->prof, "back_kernel", st,
-        (back_variant(narrow, s->back_minb)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, n, p->min_seed_len, p->max_occ, s->cand_stride,
+        (back_variant(narrow, s->back_minb, ix.kt_K > 0)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, n, p->min_seed_len, p->max_occ, s->cand_stride,
                                                                                   s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
     s->launches += 2;
     s->cur_packed = d_packed; s->cur_woff = d_woff; s->cur_len = d_len; s->cur_max_len = max_len;

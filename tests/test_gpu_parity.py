@@ -369,3 +369,27 @@ def test_pipeline_host_call_in_slices(gpu, oracle, dev_index, monkeypatch):
     got1 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params())
     assert got1.tobytes() == want.tobytes()
     pl.destroy()
+
+
+@pytest.mark.parametrize("K,sat", [(0, None), (4, None), (9, None), (9, 40), (7, 3000), (6, 2)])
+def test_seeding_kmer_table_variants(gpu, dev_index, monkeypatch, K, sat):
+    """the k-mer interval table (seed.cu): every table size, including none, and every size from which an entry defers to the
+    occurrence buckets, gives the oracle's SMEMs and seeds -- a table step and a bucket step are interchangeable at any point"""
+    g, idx, oi = dev_index
+    if sat is not None:
+        monkeypatch.setenv("BWA_B200_KMER_SAT", str(sat))
+    idx.set_kmer_table(K)
+    try:
+        reads, _, _ = synth.make_reads(g, 2500, 150, seed=25 + K, sub_rate=0.02, n_rate=0.003)
+        seed_compare(gpu, idx, oi, reads.reshape(-1).copy(), (np.arange(2501) * 150).astype(np.uint64), 19, 500)
+        rng = np.random.default_rng(K)
+        rl = [reads[i, :int(rng.integers(1, 151))] for i in range(300)]
+        rl += [np.full(30, 4, np.uint8), np.zeros(200, np.uint8), g[100:130].copy(), synth.revcomp(g[9000:9100].copy()), g[-60:].copy(), synth.revcomp(g[:60].copy())]
+        f, off = flat(rl)
+        seed_compare(gpu, idx, oi, f, off, 12, 50)
+        monkeypatch.setenv("BWA_B200_WIDE_ROWS", "1")
+        seed_compare(gpu, idx, oi, f, off, 19, 500)
+    finally:
+        monkeypatch.delenv("BWA_B200_KMER_SAT", raising=False)
+        monkeypatch.delenv("BWA_B200_WIDE_ROWS", raising=False)
+        idx.set_kmer_table(9)

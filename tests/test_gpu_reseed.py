@@ -105,3 +105,20 @@ def test_reseed_golden_from_reference(gpu, tmp_path):
             assert (got["n_seeds"] == gold["n_seeds"]).all()
             assert (got["rbeg"] == gold["rbeg"]).all() and (got["score"] == gold["score"]).all()
     idx.free()
+
+
+@pytest.mark.parametrize("K,sat", [(0, None), (5, None), (9, 100)])
+def test_reseed_kmer_table_variants(gpu, oracle, dev_index, monkeypatch, K, sat):
+    """re-seeding (back_kernel<RESEED> takes table steps too) under several k-mer table shapes"""
+    g, idx, oi = dev_index
+    if sat is not None:
+        monkeypatch.setenv("BWA_B200_KMER_SAT", str(sat))
+    idx.set_kmer_table(K)
+    try:
+        reads, _, _ = synth.make_reads(g, 2000, 150, seed=61 + K, n_rate=0.002)
+        flat, off = reads.reshape(-1).copy(), (np.arange(2001) * 150).astype(np.uint64)
+        reseed_compare(gpu, oracle, idx, oi, flat, off, 19, 500)
+        reseed_compare(gpu, oracle, idx, oi, flat, off, 19, 20, sf=2.0, sw=50, mmi=5)
+    finally:
+        monkeypatch.delenv("BWA_B200_KMER_SAT", raising=False)
+        idx.set_kmer_table(9)

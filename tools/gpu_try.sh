@@ -1,9 +1,10 @@
 #!/bin/bash
+# BENCH_ARGS='--genome 1000000000' adds bench.py arguments
 # usage: gpu_try.sh "ENV=.. ENV=.." ...   -> one short bench per env set, kernel times printed
 set -u
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  env $cfg timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-chain 2>gpurun_out/try.err | python -c "
+  env $cfg timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-chain ${BENCH_ARGS:-} 2>gpurun_out/try.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 k=d['sub_metrics']['kernel_ms']
