@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- reads/s end-to-end (seed + extend) on synthetic reads, one process per GPU.
+"""bench.py -- reads/s end-to-end (seed -> chain -> extend) on synthetic reads, one process per GPU.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nproc-per-node N bench.py --gpus N ...
 
-Workload at N=1: BASELINE.json configs[1] -- 1M synthetic 150 bp reads (1 % sub, 0.1 % indel) vs a
-synthetic 100 Mb genome.  A step is one pass of the hot path over the batch: SMEM seeding (+ SA
-locate) of every read, on-device cut of the left/right extension jobs of each read's longest seed,
-and ksw_extend2 on all of them (bwa_b200_seed_extend_*).  Reads shard across ranks (weak scaling:
-every rank owns a full batch and a replica of the index); no data-path collective.
+Headline workload (N = 1): BASELINE.json configs[1] -- 1 M synthetic 150 bp reads (1 % substitutions, 0.1 % indels) against a
+synthetic 100 Mb genome.  A step is one pass of the pipeline the reference's `gase_aln` worker runs over a batch
+(src/bwamem.c:2055-2093, 2286-2306): SMEM seeding (+ SA locate) of every read, mem_chain / mem_chain_flt, mem_chain2aln's
+extension jobs for every kept chain, ksw_extend2 on all of them, the region arithmetic -- bwa_b200_align_*.  Reads shard across
+ranks (weak scaling: every rank owns a full batch and a replica of the index); no data-path collective.
 
-`value` is measured with inputs resident in HBM (CUDA events on the pipeline stream); `e2e` goes
-through the host-buffer C-ABI call with H2D/D2H inside the timed region.  The oracle is used only
-for the cpu_baseline leg and for `--impl reference`.
+`value` is measured with inputs resident in HBM (CUDA events on the aligner's stream); `e2e` goes through the host-buffer C-ABI
+call (bwa_b200_align_host_view) with H2D and D2H inside the timed region.  `--impl reference` times the same step over the
+reference's own CPU functions (oracle/_ref: bwt_smem1 / bwt_sa of bwa_index, the fork's mem_chain .. mem_chain2aln and ksw_extend2)
+on all host threads, in a process that never loads the product library.  The oracle is used only there, for the cpu_baseline legs
+and for the work counters.  Other legs ride in sub_metrics: the fused one-seed step (round 1's headline), the chained step with
+re-seeding, the CIGAR path, BASELINE config 3 (3.1 Gb genome, `c3`) and the reference's CPU `bwa mem` wall time.
 """
 import argparse
 import json
@@ -26,11 +29,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-import __graft_entry__ as ge  # noqa: E402
 from tools import synth  # noqa: E402
 
 METRIC = "reads_per_s_end_to_end_seed_extend"
 UNIT = "reads/s"
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+# contig lengths of GRCh38 chr1..22, X, Y in Mb: the proportions of config 3's 24 contigs
+HG38_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09, 133.28, 114.36, 107.04, 101.99, 90.34,
+           83.26, 80.37, 58.62, 64.44, 46.71, 50.82, 156.04, 57.23]
 
 
 def log(*a):
@@ -47,6 +53,19 @@ def peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(reads, read_len, genome):
+    return f"{reads} synthetic {read_len}bp reads (1% sub, 0.1% indel) vs synthetic {genome} bp genome, per GPU"
+
+
+def contig_lens(genome_bases, n_ctg):
+    if n_ctg <= 1:
+        return [genome_bases]
+    tot = sum(HG38_MB[:n_ctg])
+    lens = [int(genome_bases * x / tot) for x in HG38_MB[:n_ctg]]
+    lens[-1] = genome_bases - sum(lens[:-1])
+    return lens
 
 
 class ClockSampler:
@@ -109,103 +128,237 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def prepare_data(args, rank, world, dist):
-    """genome + index (built once per box, shared through /tmp) and this rank's read batch"""
+# ------------------------------------------------------------------------------------------------------------ data
+BUILD_SNIPPET = """
+import sys, os
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+from tools import synth
+pkg = ge.load_package()
+g = synth.make_genome({genome}, seed=synth.GENOME_SEED)
+pkg.build_index(g, {prefix!r} + ".tmp", sa_intv={sa_intv}, also_stock_layout=True, n_threads=0)
+for ext in (".bwt", ".bwt128", ".sa"):
+    os.replace({prefix!r} + ".tmp" + ext, {prefix!r} + ext)
+"""
+
+
+def index_prefix(genome_bases, sa_intv=16):
     cache = os.environ.get("BWA_B200_CACHE", "/tmp/bwa_b200_bench")
     os.makedirs(cache, exist_ok=True)
-    prefix = os.path.join(cache, f"g{args.genome}_s{synth.GENOME_SEED}")
+    return os.path.join(cache, f"g{genome_bases}_s{synth.GENOME_SEED}" + ("" if sa_intv == 16 else f"_sa{sa_intv}"))
+
+
+def have_index(prefix):
+    return all(os.path.exists(prefix + e) for e in (".sa", ".bwt", ".bwt128"))
+
+
+def prepare_data(genome_bases, n_reads, read_len, rank, dist, in_subprocess=False, sa_intv=16):
+    """genome + index (built once per box by rank 0, shared through /tmp) and this rank's read batch.  in_subprocess: the index is
+    built by a child process, so that the calling process (the reference arm) never maps the product library"""
+    prefix = index_prefix(genome_bases, sa_intv)
     t0 = time.time()
-    genome = synth.make_genome(args.genome, seed=synth.GENOME_SEED)
-    pkg = ge.load_package()
-    if rank == 0 and not (os.path.exists(prefix + ".sa") and os.path.exists(prefix + ".bwt") and os.path.exists(prefix + ".bwt128")):
-        pkg.build_index(genome, prefix + ".tmp", sa_intv=16, also_stock_layout=True, n_threads=0)
-        for ext in (".bwt", ".bwt128", ".sa"):
-            os.replace(prefix + ".tmp" + ext, prefix + ext)
+    genome = synth.make_genome(genome_bases, seed=synth.GENOME_SEED)
+    if rank == 0 and not have_index(prefix):
+        if in_subprocess:
+            subprocess.check_call([sys.executable, "-c", BUILD_SNIPPET.format(root=ROOT, genome=genome_bases, prefix=prefix, sa_intv=sa_intv)])
+        else:
+            import __graft_entry__ as ge
+            pkg = ge.load_package()
+            pkg.build_index(genome, prefix + ".tmp", sa_intv=sa_intv, also_stock_layout=True, n_threads=0)
+            for ext in (".bwt", ".bwt128", ".sa"):
+                os.replace(prefix + ".tmp" + ext, prefix + ext)
     if dist is not None:
         dist.barrier()
     t1 = time.time()
-    reads, pos, strand = synth.make_reads(genome, args.reads, args.read_len, seed=synth.READS_SEED + rank)
-    log(f"[rank {rank}] genome+index {t1 - t0:.1f}s, reads {time.time() - t1:.1f}s")
+    reads, pos, strand = synth.make_reads(genome, n_reads, read_len, seed=synth.READS_SEED + rank)
+    log(f"[rank {rank}] genome {genome_bases} + index {t1 - t0:.1f}s, {n_reads} reads {time.time() - t1:.1f}s")
     return genome, prefix, reads
 
 
-def run_reference(args, rank, world, dist):
-    """CPU arm: the reference's own bwt_smem1 / bwt_sa / ksw_extend2 (oracle/_ref, kind "reference") or,
-    if that library did not travel, the oracle port; all host threads; bounded sample per step."""
-    from oracle import oracle_py as O
+# ----------------------------------------------------------------------------------------------- CPU reference legs
+class CpuChained:
+    """the chained step on the host cores with the reference's own functions (oracle/chain_py.ref_chained_pipeline): bwt_smem1 / bwt_sa of
+    bwa_index through libbwaref.so, mem_chain .. mem_chain2aln and ksw_extend2 of the fork through libforkmem.so"""
+
+    def __init__(self, genome, prefix, lens, w=100):
+        from oracle import chain_py as CP, oracle_py as O
+        self.CP, self.O = CP, O
+        self.kind = "reference" if (O.have_ref() and CP.have_fork()) else None
+        assert self.kind, "oracle/_ref is not built (libbwaref.so / libforkmem.so): run __graft_entry__.build() where /root/reference exists"
+        self.h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+        assert self.h, "ref_load failed"
+        self.ctg = CP.Contigs(tuple(lens))
+        self.opt = CP.default_opt(w=w)
+        self.kp = O.make_params()
+        self.pac = CP.make_pac(genome)
+        self.threads = O.default_threads()
+
+    def run(self, reads2d):
+        n, L = reads2d.shape
+        flat = np.ascontiguousarray(reads2d).reshape(-1)
+        off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+        return self.CP.ref_chained_pipeline(self.h, self.opt, self.ctg, self.pac, flat, off, self.kp, 19, self.threads)
+
+    def close(self):
+        self.O.ref_lib().ref_free(self.h)
+
+
+def same_regions(cpu_out, gpu_out, n):
+    """GPU regions (REGION_DTYPE) of the first n reads == the CPU arm's, field by field"""
+    if not (cpu_out["n_regs"][:n] == gpu_out["n_regions"][:n]).all():
+        return False
+    tot = int(cpu_out["n_regs"][:n].sum())
+    a, b = cpu_out["regs"][:tot], gpu_out["regions"][:tot]
+    return all(bool((a[f] == b[f]).all()) for f in ("rb", "re", "qb", "qe", "score", "truesc", "rid", "seedcov", "seedlen0"))
+
+
+def run_reference(args, rank):
+    """--impl reference: the chained step on the CPU, all host threads, the full batch per step when that fits the time budget"""
     if rank != 0:
         return
-    genome, prefix, reads = prepare_data(args, 0, 1, None)
-    sample = min(args.reads, args.cpu_sample)
-    f = reads[:sample].reshape(-1).copy()
-    off = (np.arange(sample + 1) * args.read_len).astype(np.uint64)
-    params = O.make_params()
-    threads = O.default_threads()
-    if O.have_ref():
-        h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
-        assert h, "ref_load failed"
-        kind = "reference"
-        step = lambda: O.ref_pipeline(h, genome, f, off, params, 19, 500, threads)  # noqa: E731
-    else:
-        oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
-        kind = "port"
-        step = lambda: O.pipeline(oi, genome, f, off, params, 19, 500, threads)  # noqa: E731
+    genome, prefix, reads = prepare_data(args.genome, args.reads, args.read_len, 0, None, in_subprocess=True)
+    cpu = CpuChained(genome, prefix, [args.genome])
+    n = reads.shape[0]
+    probe = min(n, 50_000)
+    cpu.run(reads[:probe])
+    t0 = time.perf_counter()
+    cpu.run(reads[:probe])
+    rate = probe / (time.perf_counter() - t0)
+    budget_s = args.ref_budget
+    sample = n if n * (args.steps + args.warmup) / rate <= budget_s else max(probe, int(rate * budget_s / (args.steps + args.warmup)))
+    sample = min(sample, n)
     for _ in range(args.warmup):
-        step()
+        cpu.run(reads[:sample])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        out = cpu.run(reads[:sample])
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
+    loaded = [ln.split()[-1] for ln in open("/proc/self/maps") if "libbwamem_b200" in ln]
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{args.reads} synthetic {args.read_len}bp reads (1% sub, 0.1% indel) vs synthetic {args.genome} bp genome",
-                       "sample_reads_per_step": sample, "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
-                             "sample": f"first {sample} reads of the batch per step, {threads} host threads"},
+            "config": {"workload": workload_name(args.reads, args.read_len, args.genome), "pipeline": "seed -> chain -> extend (pass-1 SMEMs)",
+                       "reads_per_step": sample, "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100, "sa_intv": 16},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
+                             "sample": f"{'all' if sample == n else 'first'} {sample} reads of the batch per step, {cpu.threads} host threads",
+                             "regions_per_step": int(len(out["regs"])), "product_library_loaded": bool(loaded)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world, reseed=False):
-    """The same batch through bwa_b200_align_*: seeding, then mem_chain / mem_chain_flt / mem_chain2aln on the device, every
-    extension job of every kept chain (not just the longest seed's), the region arithmetic -- SURVEY 8f row 1.  Extension runs
-    with the same band / z-drop as the headline step.  Reported under sub_metrics.chained, timed like the headline."""
+def run_bwa_mem_cpu(genome, prefix, reads, read_len, label, n_sub, threads):
+    """the reference's CPU program `bwa mem -t <all cores>` (oracle/_ref/bwa7p = bwa_index/ with the .sa loader fix) on a FASTA of
+    the first n_sub reads: [M::mem_process_seqs] real seconds and whole-process wall seconds (index load included)"""
+    import re
+    import tempfile
+    exe = os.path.join(REF_DIR, "bwa7p")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/bwa7p not built"}
+    work = tempfile.mkdtemp(prefix="bwamem_")
+    sp = os.path.join(work, "ref")
+    fasta = os.path.join(work, "ref.fa")
+    t0 = time.time()
+    synth.genome_to_fasta(genome, fasta)
+    subprocess.check_call([exe, "fa2pac", "-f", fasta, sp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    os.unlink(fasta)
+    for ext, src in ((".bwt", ".bwt128"), (".sa", ".sa")):
+        os.symlink(prefix + src, sp + ext)
+    prep = time.time() - t0
+    fa = os.path.join(work, "reads.fa")
+    pos = np.zeros(n_sub, np.int64)
+    synth.reads_to_fasta(reads[:n_sub], pos, pos.astype(np.uint8), fa)
+    res = {"reads": n_sub, "workload": label, "fasta_pac_seconds": round(prep, 2)}
+    for t in (threads, 1):
+        n_here = n_sub if t > 1 else min(n_sub, 20_000)
+        if t == 1 and n_here < n_sub:
+            synth.reads_to_fasta(reads[:n_here], pos[:n_here], pos[:n_here].astype(np.uint8), fa)
+        t0 = time.time()
+        p = subprocess.run([exe, "mem", "-t", str(t), sp, fa], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        wall = time.time() - t0
+        real = sum(float(x) for x in re.findall(r"Processed \d+ reads in [\d.]+ CPU sec, ([\d.]+) real sec", p.stderr))
+        key = "all_cores" if t > 1 else "one_core"
+        res[key] = {"threads": t, "reads": n_here, "rc": p.returncode, "wall_seconds": round(wall, 3), "mem_process_seqs_real_seconds": round(real, 3),
+                    "reads_per_s_process_seqs": n_here / real if real > 0 else None, "reads_per_s_wall": n_here / wall}
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    return res
+
+
+# --------------------------------------------------------------------------------------------------- GPU legs
+class Batch:
+    """one rank's read batch: packed on the host, resident on the device, pinned for the host-buffer calls"""
+
+    def __init__(self, pkg, reads):
+        import torch
+        self.n, self.L = reads.shape
+        flat = reads.reshape(-1)
+        off = (np.arange(self.n + 1, dtype=np.uint64) * np.uint64(self.L))
+        self.packed, self.woff, self.rl = pkg.pack_codes(flat, off)
+        self.d_packed = torch.from_numpy(self.packed.view(np.int32)).cuda()
+        self.d_woff = torch.from_numpy(self.woff.view(np.int64)).cuda()
+        self.d_rl = torch.from_numpy(self.rl.view(np.int32)).cuda()
+        self.pin = {}
+        for name, arr in (("packed", self.packed), ("woff", self.woff), ("rl", self.rl)):
+            t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+            t.numpy()[:] = arr.view(np.uint8)
+            self.pin[name] = t
+        self.h2d = int(self.packed.nbytes + self.woff.nbytes + self.rl.nbytes)
+
+
+def max_over_ranks(x, dist):
     import torch
-    import torch.distributed as dist
-    al = pkg.Aligner(idx, n, int(d_packed.numel()))
-    # reseed: seeding also runs passes 2 and 3 of mem_collect_intv (the seed set of stock `bwa mem`; SURVEY 8f row 3)
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, steps=None, sampler=None):
+    """bwa_b200_align_*: seeding, mem_chain / mem_chain_flt / mem_chain2aln on the device, every extension job of every kept chain,
+    the region arithmetic.  Device-resident timing with CUDA events on the aligner's stream, then the host-buffer call with one and
+    with two batches in flight (two aligner handles, two host threads: the reference's NB_STREAMS = 2 pattern, src/fastmap.c:31,473-511)."""
+    import torch
+    steps = steps or args.steps
+    n, L = bt.n, bt.L
+
+    def make():
+        a = pkg.Aligner(idx, n, int(bt.d_packed.numel()))
+        if len(lens) > 1:
+            a.set_contigs(np.concatenate([[0], np.cumsum(lens[:-1])]), lens)
+        return a
+    al = make()
     sp, cp, ep = pkg.seed_params(19, 500, reseed), pkg.chain_params(w=100), pkg.ext_params()
     stream = torch.cuda.ExternalStream(al.stream)
 
     def step():
-        al.align_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, cp, ep)
+        al.align_device(bt.d_packed.data_ptr(), bt.d_woff.data_ptr(), bt.d_rl.data_ptr(), n, L, sp, cp, ep)
 
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if dref:
+    if dist:
         dist.barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     l0 = al.launches
-    for k in range(args.steps):
+    for k in range(steps):
         with torch.cuda.stream(stream):
-            flush.zero_()
+            flush.zero_()                # evict L2 between timed iterations (outside the event pair)
         ev[k][0].record(stream)
-        step()                       # returns when the regions are in HBM (one host round trip inside: the job count)
+        step()                           # returns when the regions are in HBM (one host round trip inside: the job count)
         ev[k][1].record(stream)
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dist)
     launches = al.launches - l0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dref:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     v = al.view()
     al.profile(2)
     kt = {}
-    for k in range(min(args.steps, 5)):
+    for k in range(min(steps, 5)):
         with torch.cuda.stream(stream):
             flush.zero_()
         step()
@@ -213,17 +366,18 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
             kt.setdefault(name, []).append(x)
     al.profile(False)
     # pinned host buffers in, regions out into the aligner's pinned result buffers (bwa_b200_align_host_view)
-    reps = max(1, min(args.steps, 10))
-    n_reg = int(al.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=False)["regions"].size)
+    reps = max(2, min(steps, 10))
+    pin = bt.pin
+    host = al.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=True)
+    n_reg = int(host["regions"].size)
     torch.cuda.synchronize()
-    if dref:
+    if dist:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         al.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=False)
-    e2e_one = world * n * reps / (time.perf_counter() - t0)
-    # two batches in flight: two aligner handles, two host threads (as the headline e2e)
-    al2 = pkg.Aligner(idx, n, int(d_packed.numel()))
+    e2e_one = world * n * reps / max_over_ranks(time.perf_counter() - t0, dist)
+    al2 = make()
     errs = []
 
     def worker(a, k):
@@ -235,7 +389,7 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
 
     worker(al2, 1)
     torch.cuda.synchronize()
-    if dref:
+    if dist:
         dist.barrier()
     th = [threading.Thread(target=worker, args=(al, (reps + 1) // 2)), threading.Thread(target=worker, args=(al2, reps // 2))]
     t0 = time.perf_counter()
@@ -243,30 +397,98 @@ def run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, 
         x.start()
     for x in th:
         x.join()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dist)
     assert not errs, errs
     al2.destroy()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dref:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
     kavg = {k: float(np.mean(x)) for k, x in kt.items()}
     ext_ms = kavg.get("ext_phase", 0.0)
-    res = {"reads_per_s": world * n * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps,
-           "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_one_batch_in_flight": e2e_one, "e2e_d2h_bytes_per_step": int(n_reg * pkg.REGION_DTYPE.itemsize + n * 12),
+    d2h = int(n_reg * pkg.REGION_DTYPE.itemsize + n * 12)
+    res = {"reads_per_s": world * n * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
+           "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_one_batch_in_flight": e2e_one, "e2e_h2d_bytes_per_step": bt.h2d, "e2e_d2h_bytes_per_step": d2h,
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
            "gpu_launches": int(launches), "kernel_ms": kavg,
            "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"
                      + ("; re-seeding split_factor 1.5 split_width 10 max_mem_intv 20" if reseed else "; SMEM pass 1 only")}
     al.destroy()
-    return res
+    return res, host, clocks
+
+
+def run_fused(args, pkg, idx, bt, flush, dist, world):
+    """round 1's headline, kept as a sub-metric: seeding, then the left / right extension of each read's longest seed only
+    (bwa_b200_seed_extend_*), device-resident and through the host-buffer call"""
+    import torch
+    n, L = bt.n, bt.L
+    pl = pkg.Pipeline(idx, n, bt.packed.size, L)
+    sp, ep = pkg.SeedParams(19, 500), pkg.ext_params()
+    d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(pl.stream)
+
+    def step_device():
+        pl.run_device(bt.d_packed.data_ptr(), bt.d_woff.data_ptr(), bt.d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
+
+    pl.profile(False)
+    for _ in range(args.warmup):
+        step_device()
+        pl.sync()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    steps = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    l0 = pl.launches
+    for k in range(steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        pl.sync()
+    torch.cuda.synchronize()
+    launches = pl.launches - l0
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dist)
+    ktimes, kbins = {}, {}
+    for mode, dst in ((2, ktimes), (1, kbins)):      # 2: one event pair around the extension launch set; 1: a pair around every launch
+        pl.profile(mode)
+        for k in range(min(steps, 5)):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            step_device()
+            pl.sync()
+            for name, x in pl.kernel_times():
+                dst.setdefault(name, []).append(x)
+    pl.profile(False)
+    tot = pl.totals()
+    h_out = torch.empty(n * 72, dtype=torch.uint8).pin_memory()
+    pin = bt.pin
+
+    def step_host():
+        pkg.check(pkg.lib().bwa_b200_seed_extend_host(pl.h, pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, ep, h_out.data_ptr()))
+    step_host()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    reps = max(2, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step_host()
+    e2e = world * n * reps / max_over_ranks(time.perf_counter() - t0, dist)
+    out_np = h_out.numpy().view(pkg.READ_RESULT_DTYPE).copy()
+    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
+    ext_ms = kavg.get("ext_phase", 0.0)
+    res = {"reads_per_s": world * n * steps / (ms / 1e3), "ms_per_step": ms / steps, "e2e_reads_per_s_one_batch_in_flight": e2e,
+           "e2e_h2d_bytes_per_step": bt.h2d, "e2e_d2h_bytes_per_step": int(n * 72), "gpu_launches": int(launches),
+           "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "cells_per_step": tot["cells"],
+           "extension_GCUPS": tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None,
+           "reads_with_seed": int((out_np["seed_qbeg"] >= 0).sum()), "kernel_ms": kavg,
+           "kernel_ms_bins_serialised": {k: float(np.mean(v)) for k, v in kbins.items()}}
+    pl.destroy()
+    return res, out_np
 
 
 def run_cigar(args, pkg, flush):
     """CIGAR path: ksw_global2 with backtrack + NM over a batch of end-to-end jobs shaped like the output stage
-    of the C2 workload (150 bp queries, 3 % substitutions, 1 % short indels, band = |tlen - qlen| + 3 as bwa_gen_cigar2 gives).
-    Device-resident timing with CUDA events; the host-to-host call; the oracle on the host cores beside it."""
+    of the C2 workload (150 bp queries, 3 % substitutions, 1 % short indels, band = |tlen - qlen| + 3 as bwa_gen_cigar2 gives)."""
     import torch
     from oracle import oracle_py as O
     base = synth.make_global_jobs(65_536, qlen_range=(150, 150), seed=2027)       # generated once, tiled 4 x (generation is a Python loop)
@@ -321,9 +543,86 @@ def run_cigar(args, pkg, flush):
         want = O.global_batch(sj, O.make_params(), cig_stride=64, n_threads=threads)
         cdt = time.perf_counter() - t0
         same = bool((got["score"][:sample] == want["score"]).all() and (got["nm"][:sample] == want["nm"]).all() and (got["n_cigar"][:sample] == want["n_cigar"]).all())
+        assert same, "CIGAR kernel output differs from the oracle on the bench sample"
         res["cpu_baseline"] = {"value": sample / cdt, "unit": "jobs/s", "cores": threads, "kind": "port", "sample": f"first {sample} jobs",
                                "gpu_output_identical_on_sample": same}
     cg.destroy()
+    return res
+
+
+def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk, pk_src):
+    """roofline block of the dominant seeding kernel: algorithmic bytes = the bucket sectors / LF steps / SA samples the reference's CPU
+    algorithm touches on the same reads (instrumented oracle), over the kernel's live CUDA-event time"""
+    from oracle import oracle_py as O
+    oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    s_n = min(n, 20_000)
+    L = reads.shape[1]
+    sf = reads[:s_n].reshape(-1).copy()
+    soff = (np.arange(s_n + 1) * L).astype(np.uint64)
+    _, fc, _ = O.pipeline(oi, genome, sf, soff, O.make_params(), 19, 500, O.default_threads())
+    oi.close()
+    per_read = {k: v / s_n for k, v in fc.items()}
+    alg = {"fwd_kernel": 32.0 * per_read["n_bucket_fwd"],
+           "back_kernel": 32.0 * (per_read["n_bucket"] - per_read["n_bucket_fwd"] - per_read["n_lf"]),
+           "locate_kernel": 32.0 * per_read["n_lf"] + 4.0 * per_read["n_located"]}
+    seed_k = {k: kavg[k] for k in alg if k in kavg}
+    if not seed_k:
+        return None, per_read
+    dom = max(seed_k, key=seed_k.get)
+    achieved = alg[dom] * n / (seed_k[dom] / 1e3) / 1e9
+    rs = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, int(index_bytes), 2048, 2))
+    all_alg = sum(alg[k] for k in seed_k) * n / (sum(seed_k.values()) / 1e3) / 1e9
+    roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+            "peak_source": pk_src, "algorithmic_bytes_per_read": alg[dom], "algorithmic_bytes_per_launch": alg[dom] * n, "ms_per_launch": seed_k[dom],
+            "share_of_step": seed_k[dom] / sum(kavg.values()) if kavg else None,
+            "random_sector_peak_at_index_footprint_gbs": rs, "index_bucket_bytes": int(index_bytes),
+            "frac_of_random_sector": achieved / rs if rs else None,
+            "all_seeding_kernels": {"algorithmic_gbs": all_alg, "ms": sum(seed_k.values()), "kernel_ms": seed_k,
+                                    "algorithmic_bytes_per_read": {k: alg[k] for k in seed_k}},
+            "note": "achieved = sectors the reference's CPU algorithm touches / kernel time; the k-mer interval table answers the steps on patterns "
+                    "of at most kt_K bases from L2, so fewer sectors than that reach HBM (traffic, from ncu) and frac_of_random_sector may exceed 1"}
+    return roof, per_read
+
+
+def run_c3(args, pkg, local, rank, world, dist, flush, pk, pk_src):
+    """BASELINE config 3: 150 bp reads against a 3.1 Gb genome in 24 contigs (sizes in the proportions of GRCh38), index replicated per GPU.
+    The chained step device-resident and host-to-host, its kernel times, the seeding roofline in the HBM regime, and identity with the
+    CPU reference on a sample."""
+    import torch
+    lens = contig_lens(args.c3_genome, 24)
+    genome, prefix, reads = prepare_data(args.c3_genome, args.c3_reads, args.read_len, rank, dist)
+    t0 = time.time()
+    idx = pkg.Index.load(prefix + ".bwt", prefix + ".sa", local)
+    idx.attach_ref(genome)
+    info = idx.info()
+    load_s = time.time() - t0
+    bt = Batch(pkg, reads)
+    steps = max(3, min(args.steps, 5))
+    res, host, _ = run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, steps=steps)
+    res["workload"] = workload_name(args.c3_reads, args.read_len, args.c3_genome) + ", 24 contigs"
+    res["index_hbm_bytes"] = int(info.hbm_bytes)
+    res["index_load_seconds"] = round(load_s, 1)
+    res["scaling"] = "weak"
+    if rank == 0:
+        bkt_bytes = int(info.n_buckets) * 32
+        roof, per_read = seeding_roofline(pkg, local, genome, prefix, reads, res["kernel_ms"], bt.n, bkt_bytes, pk, pk_src)
+        res["roofline"] = roof
+        res["oracle_work_per_read"] = per_read
+        if not args.no_cpu_baseline:
+            sample = min(bt.n, args.c3_cpu_sample)
+            cpu = CpuChained(genome, prefix, lens)
+            cpu.run(reads[:min(sample, 5000)])
+            t0 = time.perf_counter()
+            out = cpu.run(reads[:sample])
+            cdt = time.perf_counter() - t0
+            same = same_regions(out, host, sample)
+            assert same, "c3: GPU regions differ from the CPU reference on the bench sample"
+            res["cpu_baseline"] = {"value": sample / cdt, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
+                                   "sample": f"first {sample} reads of the batch, {cpu.threads} host threads", "gpu_output_identical_on_sample": same}
+            cpu.close()
+    idx.free()
+    del bt
+    torch.cuda.empty_cache()
     return res
 
 
@@ -337,8 +636,14 @@ def main():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--genome", type=int, default=100_000_000)
     ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--ref-budget", type=float, default=170.0, help="seconds the reference arm may spend in its warm-up + timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-chain", action="store_true", help="skip the seeds -> chains -> jobs -> extension -> regions stage (sub_metrics.chained)")
+    ap.add_argument("--no-chain", action="store_true", help="only the fused one-seed step (kernel A/B runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the re-seeding, CIGAR and bwa-mem sub-metrics")
+    ap.add_argument("--no-c3", action="store_true", help="skip BASELINE config 3 (3.1 Gb genome)")
+    ap.add_argument("--c3-genome", type=int, default=3_100_000_000)
+    ap.add_argument("--c3-reads", type=int, default=1_250_000, help="reads per GPU of config 3 (10 M reads over 8 GPUs)")
+    ap.add_argument("--c3-cpu-sample", type=int, default=50_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -347,11 +652,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world, None)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
+    import __graft_entry__ as ge
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -359,252 +665,136 @@ def main():
 
     pkg = ge.load_package()
     pkg.build()
-    genome, prefix, reads = prepare_data(args, rank, world, dref)
-    n, L = reads.shape
-    flat = reads.reshape(-1)
-    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
-    packed, woff, rl = pkg.pack_codes(flat, off)
-
+    genome, prefix, reads = prepare_data(args.genome, args.reads, args.read_len, rank, dref)
     idx = pkg.Index.load(prefix + ".bwt", prefix + ".sa", local)
     idx.attach_ref(genome)
     info = idx.info()
-    pl = pkg.Pipeline(idx, n, packed.size, L)
-    sp, ep = pkg.SeedParams(19, 500), pkg.ext_params()
-
-    # resident inputs
-    d_packed = torch.from_numpy(packed.view(np.int32)).cuda()
-    d_woff = torch.from_numpy(woff.view(np.int64)).cuda()
-    d_rl = torch.from_numpy(rl.view(np.int32)).cuda()
-    d_out = torch.empty(n * 72, dtype=torch.uint8, device="cuda")
+    bt = Batch(pkg, reads)
+    n, L = bt.n, bt.L
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB)
-    stream = torch.cuda.ExternalStream(pl.stream)
+    pk, pk_src = peaks()
+    lens = [args.genome]
 
-    def step_device():
-        pl.run_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, L, sp, ep, d_out.data_ptr())
+    fused, fused_out = run_fused(args, pkg, idx, bt, flush, dref, world)
+    if args.no_chain:
+        # kernel A/B mode: the fused step only, one line in the old shape
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": fused["reads_per_s"], "unit": UNIT, "n_gpus": world, "ms_per_step": fused["ms_per_step"],
+                              "e2e": {"value": fused["e2e_reads_per_s_one_batch_in_flight"]}, "sub_metrics": {"kernel_ms": fused["kernel_ms"], "fused": fused}}), flush=True)
+        if dref:
+            dist.destroy_process_group()
+        return
 
-    pl.profile(False)
-    for _ in range(args.warmup):
-        step_device()
-        pl.sync()
-    torch.cuda.synchronize()
-    if dref:
-        dist.barrier()
     sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = pl.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    for k in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()                       # evict L2 between timed iterations (outside the event pair)
-        ev[k][0].record(stream)
-        step_device()
-        ev[k][1].record(stream)
-        pl.sync()
-    torch.cuda.synchronize()
-    if dref:
-        dist.barrier()
-    clocks = sampler.stop()
-    gpu_launches = pl.launches - launches0
-    # per-kernel durations: the same steps again with CUDA events on the pipeline stream.  Mode 2 = an event pair around
-    # every seeding / glue kernel and ONE pair around the extension launch set, whose length bins overlap on side streams
-    # exactly as in the timed steps above; mode 1 = a pair around every launch, which runs the bins one after another
-    # (the per-bin breakdown).
-    ktimes, ktimes_bins = {}, {}
-    for mode, dst in ((2, ktimes), (1, ktimes_bins)):
-        pl.profile(mode)
-        for k in range(args.steps if mode == 2 else min(args.steps, 5)):
-            with torch.cuda.stream(stream):
-                flush.zero_()
-            step_device()
-            pl.sync()
-            for name, ms in pl.kernel_times():
-                dst.setdefault(name, []).append(ms)
-    torch.cuda.synchronize()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    tot = pl.totals()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dref:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * n * args.steps / (total_ms / 1e3)
+    chained, host, clocks = run_chained(args, pkg, idx, bt, flush, dref, world, lens, reseed=False, sampler=sampler)
+    chained_rs = cigar = None
+    if not args.no_extras:
+        chained_rs, _, _ = run_chained(args, pkg, idx, bt, flush, dref, world, lens, reseed=True, steps=max(3, min(args.steps, 10)))
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step)
-    pin = {}
-    for name, arr in (("packed", packed), ("woff", woff), ("rl", rl)):
-        tns = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
-        tns.numpy()[:] = arr.view(np.uint8)
-        pin[name] = tns
-    h_out = torch.empty(n * 72, dtype=torch.uint8).pin_memory()
-    out_np = h_out.numpy().view(pkg.READ_RESULT_DTYPE)
-
-    def step_host():
-        pkg.check(pkg.lib().bwa_b200_seed_extend_host(pl.h, pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(),
-                                                     n, sp, ep, h_out.data_ptr()))
-
-    pl.profile(False)
-    step_host()
-    torch.cuda.synchronize()
-    if dref:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dref:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sync = world * n * args.steps / float(t.item())
-    # the same call with two batches in flight -- two pipeline handles driven by two host threads, which is how the reference's
-    # driver uses its own boundary (NB_STREAMS = 2 storages per worker thread, src/fastmap.c:31,473-511): every step still pays
-    # its H2D and D2H inside the timed region, but they overlap the other handle's kernels
-    pl2 = pkg.Pipeline(idx, n, packed.size, L)
-    h_out2 = torch.empty(n * 72, dtype=torch.uint8).pin_memory()
-
-    errs = []
-
-    def worker(handle, out_t, k):
+    c3 = None
+    if not args.no_c3:
         try:
-            for _ in range(k):
-                pkg.check(pkg.lib().bwa_b200_seed_extend_host(handle, pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(),
-                                                             n, sp, ep, out_t.data_ptr()))
-        except Exception as ex:  # noqa: BLE001
-            errs.append(ex)
-
-    worker(pl2.h, h_out2, 1)
-    assert h_out2.numpy().tobytes() == h_out.numpy().tobytes()
-    torch.cuda.synchronize()
-    if dref:
-        dist.barrier()
-    k1, k2 = (args.steps + 1) // 2, args.steps // 2
-    th = [threading.Thread(target=worker, args=(pl.h, h_out, k1)), threading.Thread(target=worker, args=(pl2.h, h_out2, k2))]
-    t0 = time.perf_counter()
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
-    torch.cuda.synchronize()
-    assert not errs, errs
-    e2e_s2 = time.perf_counter() - t0
-    t = torch.tensor([e2e_s2], dtype=torch.float64, device="cuda")
-    if dref:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(t.item())
-    pl2.destroy()
-    h2d = int(packed.nbytes + woff.nbytes + rl.nbytes)
-    d2h = int(n * 72)
-    mapped = int((out_np["seed_qbeg"] >= 0).sum())
-
-    chained = chained_rs = None
-    if not args.no_chain:
-        chained = run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world)
-        chained_rs = run_chained(args, pkg, idx, d_packed, d_woff, d_rl, pin, n, L, flush, dref, world, reseed=True)
+            c3 = run_c3(args, pkg, local, rank, world, dref, flush, pk, pk_src)
+        except AssertionError:
+            raise
+        except Exception as ex:  # noqa: BLE001  (e.g. not enough host memory for the 6.2 G-row index build on a small box)
+            log("c3 leg failed:", repr(ex))
+            c3 = {"unavailable": repr(ex)[:300]}
 
     if rank != 0:
         if dref:
             dist.destroy_process_group()
         return
-    cigar = run_cigar(args, pkg, flush) if not args.no_chain else None
+    if not args.no_extras:
+        cigar = run_cigar(args, pkg, flush)
 
-    # ---- roofline of the dominant kernel (CUDA-event time per launch, live, over the timed steps)
-    pk, pk_src = peaks()
-    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
-    step_kernel_ms = sum(kavg.values())
-    from oracle import oracle_py as O
-    oi = O.OracleIndex(prefix + ".bwt", prefix + ".sa")
-    s_n = min(n, 20_000)
-    sf = reads[:s_n].reshape(-1).copy()
-    soff = (np.arange(s_n + 1) * L).astype(np.uint64)
-    _, fc, kc = O.pipeline(oi, genome, sf, soff, O.make_params(), 19, 500, O.default_threads())
-    per_read = {k: v / s_n for k, v in fc.items()}
-    alg = {   # algorithmic bytes per read of each seeding kernel: 32 B per distinct bucket / LF step, 4 B per SA sample
-        "fwd_kernel": 32.0 * per_read["n_bucket_fwd"],
-        "back_kernel": 32.0 * (per_read["n_bucket"] - per_read["n_bucket_fwd"] - per_read["n_lf"]),
-        "locate_kernel": 32.0 * per_read["n_lf"] + 4.0 * per_read["n_located"],
-    }
-    seed_k = {k: kavg[k] for k in alg if k in kavg}
-    dom = max(seed_k, key=seed_k.get) if seed_k else None
-    roofline = None
-    if dom:
-        achieved = alg[dom] * n / (seed_k[dom] / 1e3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
-                    "algorithmic_bytes_per_read": alg[dom], "ms_per_launch": seed_k[dom], "share_of_step": seed_k[dom] / step_kernel_ms}
-    rs_hbm = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 8 << 30, 64, 3))
-    rs_l2 = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 64 << 20, 64, 3))
-    rs_mid = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, 1 << 30, 64, 3))
+    # ---- rooflines: dominant seeding kernel (HBM sectors) and the extension launch set (INT ALU), both from live CUDA-event times
+    kavg = chained["kernel_ms"]
+    roofline, per_read = seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, int(info.n_buckets) * 32, pk, pk_src)
     if roofline:
-        # random 32-byte-sector gather rates measured live (seed.cu random_sector_kernel): 8 GB buffer (HBM, beyond the
-        # TLB reach), 1 GB buffer (HBM, inside the TLB reach: the regime of a 100 Mb .. 1 Gb index) and 64 MB (L2)
-        roofline["random_sector_peak_hbm_gbs"] = rs_hbm
-        roofline["random_sector_peak_hbm_1gb_gbs"] = rs_mid
-        roofline["random_sector_peak_l2_gbs"] = rs_l2
-        roofline["frac_of_random_sector_hbm"] = roofline["achieved"] / rs_hbm if rs_hbm else None
-        roofline["frac_of_random_sector_hbm_1gb"] = roofline["achieved"] / rs_mid if rs_mid else None
         try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if (n, L, args.genome) == (1_000_000, 150, 100_000_000) and dom in tr["bytes_per_launch"]:
-                roofline["traffic"] = tr["bytes_per_launch"][dom]
+            if (n, L, args.genome) == (1_000_000, 150, 100_000_000) and roofline["kernel"] in tr["bytes_per_launch"]:
+                roofline["traffic"] = tr["bytes_per_launch"][roofline["kernel"]]
                 roofline["traffic_unit"] = "bytes/launch (dram read+write, ncu)"
-                roofline["traffic_gbs"] = tr["bytes_per_launch"][dom] / (seed_k[dom] / 1e3) / 1e9
-                roofline["algorithmic_bytes_per_launch"] = alg[dom] * n
                 roofline["traffic_source"] = tr["source"]
         except Exception as ex:  # noqa: BLE001
             log("no ncu traffic figure:", ex)
-    kbins = {k: float(np.mean(v)) for k, v in ktimes_bins.items()}
-    ext_ms = kavg.get("ext_phase", 0.0)          # sort + every bin, bins overlapping: what the extension costs inside a step
-    ext_ms_serial = sum(v for k, v in kbins.items() if k.startswith("ext_inter_kernel") or k.startswith("ext_pair_kernel"))
-    gcups = tot["cells"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
-    seed_ms = sum(seed_k.values())
-    # INT-ALU roofline of the extension kernel: 15 integer ops per cell, 64 int lanes/clk/SM on the ALU pipe
-    int_peak_gops = 148 * 64 * (pk.get("sm_max_mhz", 1965.0) / 1e3)
-    ext_roof = {"bound": "int_alu", "achieved_gcups": gcups, "peak_gcups_int32": int_peak_gops / 15.0,
-                "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None,
+    ext_ms = kavg.get("ext_phase", 0.0)
+    gcups = chained["cells_per_step"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
+    ia = pkg.measure_int_alu(local)      # measured issue rates (warp-instructions per clock per SM) and the SM clock under load
+    r = ia["warp_inst_per_clk_per_sm"]
+    alu_rate = max(r["IADD3"], r["PRMT"], r["VIADDMNMX.S16x2"], r["VIMNMX3.S16x2"])
+    int_peak_gops = ia["n_sm"] * alu_rate * 32 * ia["sm_mhz"] / 1e3          # thread-level integer ALU operations per second / 1e9
+    ext_roof = {"bound": "int_alu", "achieved_gcups": gcups, "ops_per_cell": 15,
+                "measured": ia, "alu_warp_inst_per_clk_per_sm": alu_rate,
+                "peak_gcups_int32": int_peak_gops / 15.0, "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None,
                 "peak_gcups_s16x2": 2 * int_peak_gops / 15.0, "frac_s16x2": gcups / (2 * int_peak_gops / 15.0) if gcups else None,
-                "ops_per_cell": 15,
-                "cells_per_step": tot["cells"], "ms_per_step": ext_ms,
-                "timing": "CUDA events around the whole extension launch set (sort + all length bins, overlapping on side streams)",
-                "gcups_bins_serialised": tot["cells"] / (ext_ms_serial / 1e3) / 1e9 if ext_ms_serial > 0 else None,
-                "ms_bins_serialised": ext_ms_serial}
+                "frac": gcups / (2 * int_peak_gops / 15.0) if gcups else None,
+                "cells_per_step": chained["cells_per_step"], "ms_per_step": ext_ms,
+                "peak_source": "bwa_b200_measure_int_alu, live: fastest of IADD3 / PRMT / VIADDMNMX.S16x2 / VIMNMX3.S16x2 x 32 lanes x SMs x measured SM clock; "
+                               "x 2 for s16x2, / 15 integer operations per cell (SURVEY 8d)",
+                "timing": "CUDA events around the whole extension launch set of the chained step (sort + all length bins, overlapping on side streams)"}
 
-    cpu_baseline = None
+    cpu_baseline = bwa_mem = None
     if not args.no_cpu_baseline:
         sample = min(n, args.cpu_sample)
-        cf = reads[:sample].reshape(-1).copy()
-        coff = (np.arange(sample + 1) * L).astype(np.uint64)
-        threads = O.default_threads()
-        if O.have_ref():
-            h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
-            kind, fn = "reference", (lambda: O.ref_pipeline(h, genome, cf, coff, O.make_params(), 19, 500, threads))
-        else:
-            kind, fn = "port", (lambda: O.pipeline(oi, genome, cf, coff, O.make_params(), 19, 500, threads))
-        fn()
+        cpu = CpuChained(genome, prefix, lens)
+        cpu.run(reads[:min(sample, 20_000)])
         t0 = time.perf_counter()
-        ref_out = fn()
+        out = cpu.run(reads[:sample])
         cdt = time.perf_counter() - t0
-        ref_out = ref_out[0] if isinstance(ref_out, tuple) else ref_out
-        same = bool(ref_out.tobytes() == out_np[:sample].tobytes())
-        cpu_baseline = {"value": sample / cdt, "unit": UNIT, "cores": threads, "kind": kind,
-                        "sample": f"first {sample} reads of the batch, {threads} host threads, same pipeline on CPU",
+        same = same_regions(out, host, sample)
+        assert same, "GPU regions differ from the CPU reference on the bench sample"
+        cpu_baseline = {"value": sample / cdt, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
+                        "sample": f"first {sample} reads of the batch, {cpu.threads} host threads, same pipeline (seed -> chain -> extend) on the CPU",
                         "gpu_output_identical_on_sample": same}
+        cpu.close()
+        # the fused sub-metric against its own CPU counterpart (the reference's bwt_smem1 / bwt_sa / ksw_extend2 on each read's longest seed)
+        from oracle import oracle_py as O
+        if O.have_ref():
+            s2 = min(n, 100_000)
+            h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+            cf = reads[:s2].reshape(-1).copy()
+            coff = (np.arange(s2 + 1) * L).astype(np.uint64)
+            ref_out = O.ref_pipeline(h, genome, cf, coff, O.make_params(), 19, 500, O.default_threads())
+            same_f = bool(ref_out.tobytes() == fused_out[:s2].tobytes())
+            assert same_f, "fused step output differs from the CPU reference on the bench sample"
+            fused["gpu_output_identical_on_sample"] = same_f
+        if not args.no_extras:
+            threads = os.cpu_count() or 1
+            try:
+                g1 = synth.make_genome(5_000_000, seed=synth.GENOME_SEED)
+                p1 = index_prefix(5_000_000)
+                if not have_index(p1):
+                    pkg.build_index(g1, p1 + ".tmp", sa_intv=16, also_stock_layout=True, n_threads=0)
+                    for ext in (".bwt", ".bwt128", ".sa"):
+                        os.replace(p1 + ".tmp" + ext, p1 + ext)
+                r1, _, _ = synth.make_reads(g1, 10_000, 150, seed=synth.READS_SEED)
+                bwa_mem = {"c1": run_bwa_mem_cpu(g1, p1, r1, 150, "BASELINE config 1: 10k x 150bp vs 5 Mb", 10_000, threads),
+                           "c2_subsample": run_bwa_mem_cpu(genome, prefix, reads, L, "BASELINE config 2 subsample: first 100k reads vs 100 Mb", min(n, 100_000), threads),
+                           "program": "oracle/_ref/bwa7p mem (the reference's bwa_index/ sources, OCC_INTV_SHIFT 7, .sa loader fixed), default options "
+                                      "(re-seeding on, w=100, zdrop=100), SAM to /dev/null"}
+            except Exception as ex:  # noqa: BLE001
+                bwa_mem = {"unavailable": repr(ex)[:300]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": chained["reads_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": chained["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{n} synthetic {L}bp reads (1% sub, 0.1% indel) vs synthetic {args.genome} bp genome, per GPU",
-                   "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100, "sa_intv": 16,
+        "config": {"workload": workload_name(n, L, args.genome), "pipeline": "seed -> chain -> extend (pass-1 SMEMs)",
+                   "reads_per_step": n, "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100, "sa_intv": 16,
+                   "kmer_table_K": int(os.environ.get("BWA_B200_KMER_K", "11")),
                    "index_hbm_bytes": int(info.hbm_bytes), "l2_policy": "512 MB memset between timed steps (L2 flush) and inputs + workspace > L2",
                    "parallelism": f"reads sharded over {world} rank(s), index replicated, no collective"},
-        "clocks": clocks, "gpu_launches": int(gpu_launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "batches_in_flight": 2,
-                "value_one_batch_in_flight": e2e_sync,
-                "how": "bwa_b200_seed_extend_host with pinned host buffers, two handles driven by two host threads (the reference's NB_STREAMS = 2 pattern)"},
+        "clocks": clocks, "gpu_launches": chained["gpu_launches"],
+        "e2e": {"value": chained["e2e_reads_per_s"], "unit": UNIT, "h2d_bytes_per_step": chained["e2e_h2d_bytes_per_step"],
+                "d2h_bytes_per_step": chained["e2e_d2h_bytes_per_step"], "batches_in_flight": 2, "value_one_batch_in_flight": chained["e2e_one_batch_in_flight"],
+                "how": "bwa_b200_align_host_view with pinned host buffers, two aligner handles driven by two host threads (the reference's NB_STREAMS = 2 pattern)"},
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
-        "sub_metrics": {"seeding_Mreads_per_s": n / (seed_ms / 1e3) / 1e6 if seed_ms else None, "extension_GCUPS": gcups,
-                        "seeds_per_step": tot["seeds"], "ext_jobs_per_step": tot["jobs"], "reads_with_seed": mapped,
-                        "kernel_ms": kavg, "kernel_ms_bins_serialised": kbins, "oracle_work_per_read": per_read, "chained": chained, "chained_reseed": chained_rs, "cigar": cigar},
+        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "c3": c3, "bwa_mem_cpu": bwa_mem,
+                        "extension_GCUPS": gcups, "oracle_work_per_read": per_read,
+                        "seeding_Mreads_per_s": n / (sum(kavg[k] for k in ("fwd_kernel", "back_kernel", "fill_kernel", "locate_kernel") if k in kavg) / 1e3) / 1e6},
     }
     print(json.dumps(line), flush=True)
     if dref:

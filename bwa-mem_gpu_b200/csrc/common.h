@@ -33,8 +33,10 @@ struct IndexView {
     // k-mer interval table (seed.cu, "k-mer table"): the suffix-array interval {first row k, size s} of every pattern of 1 .. kt_K
     // bases, one u64 per pattern = k << 24 | min(s, 0xffffff); level m starts at entry (4^m - 4) / 3 and is indexed by the pattern
     // with its first base most significant.  kt_K = 0: no table.  bkt_evict_last: L2 policy of the bucket loads (small indexes only).
+    // Levels below kt_lo hold at least one pattern whose size does not fit the entry; steps landing there take the bucket path (the
+    // choice depends on the level only, never on loaded data, so a warp issues its table loads and its bucket loads together).
     const uint64_t *kt;
-    uint32_t kt_K, bkt_evict_last;
+    uint32_t kt_K, kt_lo, bkt_evict_last;
 };
 
 } // namespace b200
@@ -48,7 +50,7 @@ struct bwa_b200_index {
     uint64_t n_words = 0, n_sa = 0, n_hi = 0;
     int sa_intv = 0, pack_size = 0;
     uint64_t *d_kt = nullptr;       // k-mer interval table (optional)
-    int kt_K = 0;
+    int kt_K = 0, kt_lo = 0;
 };
 
 // seed.cu: (re)build the k-mer interval table of a resident index on its device; K = 0 drops it

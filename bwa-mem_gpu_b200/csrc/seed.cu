@@ -77,6 +77,28 @@ __device__ __forceinline__ uint64_t ld_kt(const uint64_t *kt, int m, uint32_t va
     asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(e) : "l"(kt + kt_off(m) + val), "l"(pol));
     return e;
 }
+// the same under a predicate, without a branch: the load is issued (or not) in line, so that a warp whose lanes are split between
+// table steps and bucket steps has all of its requests in flight before anything is waited for
+__device__ __forceinline__ uint64_t ld_kt_if(bool doit, const uint64_t *kt, int m, uint32_t val, uint64_t pol)
+{
+    uint64_t e;
+    const uint64_t *p = kt + (doit ? kt_off(m) + val : 0ull);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u64 %0, 0;\n\t@q ld.global.nc.L2::cache_hint.u64 %0, [%1], %3;\n\t}"
+                 : "=&l"(e) : "l"(p), "r"((uint32_t)doit), "l"(pol));
+    return e;
+}
+// a bucket under a predicate (zeros when not loaded)
+__device__ __forceinline__ Bkt ld_bucket_if(bool doit, const uint32_t *bkt, uint64_t b, uint64_t pol)
+{
+    Bkt r;
+    const uint32_t *p = bkt + (doit ? b * 8 : 0ull);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %9, 0;\n\t"
+                 "mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0; mov.u32 %4, 0; mov.u32 %5, 0; mov.u32 %6, 0; mov.u32 %7, 0;\n\t"
+                 "@q ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %10;\n\t}"
+                 : "=&r"(r.c[0]), "=&r"(r.c[1]), "=&r"(r.c[2]), "=&r"(r.c[3]), "=&r"(r.w[0]), "=&r"(r.w[1]), "=&r"(r.w[2]), "=&r"(r.w[3])
+                 : "l"(p), "r"((uint32_t)doit), "l"(pol));
+    return r;
+}
 // reverse complement of a pattern of m bases (2 bits each, first base most significant)
 __device__ __forceinline__ uint32_t kt_revcomp(uint32_t val, int m)
 {
@@ -169,7 +191,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
     RowT k = 0, l = 0;
     const RowT primary = (RowT)ix.primary;
     const uint64_t pol = bucket_policy(ix), tpol = evict_last_policy();
-    const int K = KT ? (int)ix.kt_K : 0;
+    const int K = KT ? (int)ix.kt_K : 0, klo = KT ? (int)ix.kt_lo : 0;
     uint32_t s = 0;
     int x = -1, i = 0;
     uint32_t word = 0;
@@ -204,23 +226,20 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
         const int cb = 3 - b;
         RowT nk = 0, nl = 0;
         uint32_t ns = 0;
-        bool by_table = false;
         const int m = i - x + 1;             // bases of the match after this extension
-        if (KT && m <= K) {
-            val = (val << 2) | (uint32_t)b;
-            const uint64_t e = ld_kt(ix.kt, m, val, tpol);
-            if ((uint32_t)(e & KT_SAT) != KT_SAT) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); by_table = true; }
+        const bool by_table = KT && m >= klo && m <= K;
+        if (KT && m <= K) val = (val << 2) | (uint32_t)b;
+        if (KT && !by_table && !l_ok) {      // x[1] of the current match = first row of its reverse complement (once per segment)
+            const int m0 = m - 1;
+            const uint32_t cur = m <= K ? val >> 2 : val;
+            l = (RowT)(ld_kt(ix.kt, m0, kt_revcomp(cur, m0), tpol) >> 24);
         }
-        if (!by_table) {
-            if (KT && !l_ok) {               // x[1] of the current match = first row of its reverse complement
-                const int m0 = m - 1;
-                const uint32_t cur = m <= K ? val >> 2 : val;
-                l = (RowT)(ld_kt(ix.kt, m0, kt_revcomp(cur, m0), tpol) >> 24);
-            }
+        {
+            const uint64_t e = ld_kt_if(by_table, ix.kt, m, val, tpol);
             RowT p0 = l - 1, p1 = l - 1 + s;                     // rows; both >= 0
             RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-            Bkt b0 = ld_bucket(ix.bkt, j0 >> 6, pol);
-            const Bkt b1 = ld_bucket_or((j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
+            Bkt b0 = ld_bucket_if(!by_table, ix.bkt, j0 >> 6, pol);
+            const Bkt b1 = ld_bucket_or(!by_table && (j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
             uint32_t tk[4], tl[4];
             bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
             bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
@@ -232,6 +251,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
             if (cb < 2) nk += s2;
             if (cb < 1) nk += s1;
             nl = (RowT)L2_at(ix, cb) + 1 + tkc;
+            if (by_table) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); }
         }
         if (ns != s) {
             push(i);
@@ -305,7 +325,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     uint4 *const q = ring[tid >> 5];
     const RowT primary = (RowT)ix.primary;
     const uint64_t pol = bucket_policy(ix), tpol = evict_last_policy();
-    const int K = KT ? (int)ix.kt_K : 0;
+    const int K = KT ? (int)ix.kt_K : 0, klo = KT ? (int)ix.kt_lo : 0;
     uint32_t win = 0, val = 0;           // KT: the first K bases behind the pivot / the current match, as patterns (first base most significant)
 
     // warp-uniform queue state: slots [head, tail) hold claimed reads
@@ -407,24 +427,20 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             uint32_t ns = 0;
             uint32_t nval = 0;
             if (b < 4) {       // backward extension by b: only x[0], x[2] are needed downstream
-                bool by_table = false;
                 const int m = end - x + t + 1;            // bases of the match after this extension
-                if (KT && m <= K) {
-                    nval = val | (uint32_t)b << (2 * (m - 1));
-                    const uint64_t e = ld_kt(ix.kt, m, nval, tpol);
-                    if ((uint32_t)(e & KT_SAT) != KT_SAT) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); by_table = true; }
-                }
-                if (!by_table) {
-                    const RowT p0 = ck - 1, p1 = ck - 1 + cs;
-                    const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
-                    const Bkt b1 = ld_bucket(ix.bkt, j1 >> 6, pol);
-                    const Bkt b0 = ld_bucket_or((j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
-                    const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
-                    const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
-                    const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
-                    ns = ol - ok;
-                    nk = (RowT)L2_at(ix, b) + 1 + ok;
-                }
+                const bool by_table = KT && m >= klo && m <= K;
+                if (KT && m <= K) nval = val | (uint32_t)b << (2 * (m - 1));
+                const uint64_t e = ld_kt_if(by_table, ix.kt, m, nval, tpol);
+                const RowT p0 = ck - 1, p1 = ck - 1 + cs;
+                const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
+                const Bkt b1 = ld_bucket_if(!by_table, ix.bkt, j1 >> 6, pol);
+                const Bkt b0 = ld_bucket_or(!by_table && (j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
+                const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
+                const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
+                const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
+                ns = ol - ok;
+                nk = (RowT)L2_at(ix, b) + 1 + ok;
+                if (by_table) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); }
                 fail = RESEED ? ns <= mi1 : ns == 0;
             }
             uint32_t *const env_g = env_spill + (uint64_t)gtid * env_stride;     // steps >= ENV_SMEM (rare)
@@ -875,13 +891,16 @@ __global__ void kt_level1_kernel(IndexView ix, uint64_t *ck, uint64_t *cs)
 }
 
 __global__ void __launch_bounds__(256)
-kt_pack_kernel(int m, const uint64_t *__restrict__ k, const uint64_t *__restrict__ s, uint64_t *__restrict__ kt, uint64_t sat)
+kt_pack_kernel(int m, const uint64_t *__restrict__ k, const uint64_t *__restrict__ s, uint64_t *__restrict__ kt, unsigned long long *__restrict__ level_max)
 {
     const uint64_t n = 1ull << (2 * m);
     const uint64_t P = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (P >= n) return;
-    const bool fits = s[P] < sat && k[P] < (1ull << 40);
+    const bool fits = s[P] < (uint64_t)KT_SAT && k[P] < (1ull << 40);
     kt[kt_off(m) + P] = fits ? (k[P] << 24 | s[P]) : (uint64_t)KT_SAT;
+    unsigned long long v = fits ? s[P] : ~0ull;
+    for (int o = 16; o; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o); v = u > v ? u : v; }
+    if ((threadIdx.x & 31) == 0) atomicMax(level_max + m, v);          // the widest interval of the level (all ones: one does not fit)
 }
 
 } // namespace
@@ -899,22 +918,31 @@ int b200_index_build_kmer_table(bwa_b200_index *idx, int K)
     B200_CUDA(cudaMalloc(&d_kt, total * 8));
     for (int j = 0; j < 2; ++j) { B200_CUDA(cudaMalloc(&d_k[j], top * 8)); B200_CUDA(cudaMalloc(&d_s[j], top * 8)); }
     const bool narrow = idx->v.seq_len < 0xfffffff0ull;
-    // BWA_B200_KMER_SAT lowers the size from which an entry defers to the bucket path (tests: reach that path on small genomes)
-    uint64_t sat = KT_SAT;
-    if (const char *ev = getenv("BWA_B200_KMER_SAT")) { const long long v = atoll(ev); if (v > 0 && (uint64_t)v < sat) sat = (uint64_t)v; }
+    unsigned long long *d_max = nullptr, h_max[16];
+    B200_CUDA(cudaMalloc(&d_max, sizeof(h_max)));
+    B200_CUDA(cudaMemset(d_max, 0, sizeof(h_max)));
     kt_level1_kernel<<<1, 32>>>(idx->v, d_k[1], d_s[1]);
-    kt_pack_kernel<<<1, 256>>>(1, d_k[1], d_s[1], d_kt, sat);
+    kt_pack_kernel<<<1, 256>>>(1, d_k[1], d_s[1], d_kt, d_max);
     for (int m = 2; m <= K; ++m) {
         const int src = (m - 1) & 1, dst = m & 1;
         const uint64_t n_parent = 1ull << (2 * (m - 1));
         const unsigned grid = (unsigned)((n_parent + 255) / 256);
         if (narrow) kt_level_kernel<uint32_t><<<grid, 256>>>(idx->v, m, d_k[src], d_s[src], d_k[dst], d_s[dst]);
         else kt_level_kernel<uint64_t><<<grid, 256>>>(idx->v, m, d_k[src], d_s[src], d_k[dst], d_s[dst]);
-        kt_pack_kernel<<<(unsigned)((4 * n_parent + 255) / 256), 256>>>(m, d_k[dst], d_s[dst], d_kt, sat);
+        kt_pack_kernel<<<(unsigned)((4 * n_parent + 255) / 256), 256>>>(m, d_k[dst], d_s[dst], d_kt, d_max);
     }
-    cudaError_t er = cudaDeviceSynchronize();
+    cudaError_t er = cudaMemcpy(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost);
+    cudaFree(d_max);
     for (int j = 0; j < 2; ++j) { cudaFree(d_k[j]); cudaFree(d_s[j]); }
     if (er != cudaSuccess || (er = cudaGetLastError()) != cudaSuccess) { cudaFree(d_kt); b200::set_error("k-mer table build failed: %s", cudaGetErrorString(er)); return BWA_B200_ERR_CUDA; }
+    // the table serves levels kt_lo .. K: the deepest run of levels in which every interval fits an entry.  BWA_B200_KMER_SAT lowers
+    // the size regarded as fitting (tests: make the short levels defer to the buckets on a small genome)
+    uint64_t sat = KT_SAT;
+    if (const char *ev = getenv("BWA_B200_KMER_SAT")) { const long long v = atoll(ev); if (v > 0 && (uint64_t)v < sat) sat = (uint64_t)v; }
+    int lo = K + 1;
+    while (lo > 1 && h_max[lo - 1] < sat) --lo;
+    if (lo > K) { cudaFree(d_kt); return BWA_B200_OK; }                 // nothing fits: no table
+    idx->kt_lo = lo; idx->v.kt_lo = (uint32_t)lo;
     idx->d_kt = d_kt; idx->kt_K = K;
     idx->v.kt = d_kt; idx->v.kt_K = (uint32_t)K;
     return BWA_B200_OK;
