@@ -70,7 +70,8 @@ __device__ __forceinline__ uint64_t bucket_policy(const IndexView &ix)
 // are L2-hot anyway.  The reference has a hook for the same idea that it leaves switched off (pre_calc_seed_intervals,
 // src/GPUSeed/seed_gen.cu:1169, src/fastmap.c:455).
 constexpr uint32_t KT_SAT = 0xffffffu;
-__device__ __host__ __forceinline__ uint64_t kt_off(int m) { return ((1ull << (2 * m)) - 4) / 3; }   // entries of levels 1 .. m-1
+// entries of levels 1 .. m-1 = (4^m - 4) / 3 = 0b0101..01 (m ones) - 1: a shift, not a 64-bit division in the inner loop
+__device__ __host__ __forceinline__ uint64_t kt_off(int m) { return (uint64_t)(0x55555555u >> (32 - 2 * m)) - 1ull; }
 __device__ __forceinline__ uint64_t ld_kt(const uint64_t *kt, int m, uint32_t val, uint64_t pol)
 {
     uint64_t e;
