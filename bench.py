@@ -784,7 +784,7 @@ def main():
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": workload_name(n, L, args.genome), "pipeline": "seed -> chain -> extend (pass-1 SMEMs)",
                    "reads_per_step": n, "min_seed_len": 19, "max_occ": 500, "band_w": 100, "zdrop": 100, "sa_intv": 16,
-                   "kmer_table_K": int(os.environ.get("BWA_B200_KMER_K", "11")),
+                   "kmer_table_K": os.environ.get("BWA_B200_KMER_K", "auto: none below 256 MB of buckets, 12 below 1 GB, 13 beyond"),
                    "index_hbm_bytes": int(info.hbm_bytes), "l2_policy": "512 MB memset between timed steps (L2 flush) and inputs + workspace > L2",
                    "parallelism": f"reads sharded over {world} rank(s), index replicated, no collective"},
         "clocks": clocks, "gpu_launches": chained["gpu_launches"],

@@ -69,6 +69,11 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
     if (!L2 || !bwt_words || !out || n_words < 8) { b200::set_error("index_from_host: bad argument"); return BWA_B200_ERR_ARG; }
     if (sa && (sa_intv <= 0 || (sa_intv & (sa_intv - 1)))) { b200::set_error("SA interval %d is not a power of two", sa_intv); return BWA_B200_ERR_ARG; }
     B200_CUDA(cudaSetDevice(device));
+    if (const char *ev = getenv("BWA_B200_L2_FETCH")) {      // experiment knob: L2 fetch granularity from DRAM (32 / 64 / 128 bytes)
+        cudaError_t er = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ev));
+        size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[b200] L2 fetch granularity -> %zu (%s)\n", got, cudaGetErrorString(er));
+    }
     bwa_b200_index *idx = new bwa_b200_index();
     idx->device = device;
     idx->n_words = n_words;
@@ -105,9 +110,13 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
     v.pack_mask = (seq_len >> 32) == 0 ? 0u : (pack_size >= 32 ? 0xffffffffu : ((1u << pack_size) - 1));
     // bucket loads keep evict_last only while the bucket array is of the order of the L2 size; beyond, that priority goes to the k-mer table
     v.bkt_evict_last = padded * 4 <= (192ull << 20) ? 1u : 0u;
-    {   // k-mer interval table (seed.cu): K = 11 by default, BWA_B200_KMER_K = 0 .. 14 overrides, 0 = none
+    {   // k-mer interval table (seed.cu).  Measured on B200 (profiles/r02_kmer_table_ab.txt): with an index of the order of the L2 size
+        // the table only adds instructions to kernels that already issue 57 % of their cycles (100 Mb genome: back_kernel 4.0 -> 5.0 ms),
+        // with the buckets in HBM it removes the sectors that bound them (1 Gb genome: 10.7 -> 7.5 ms at K = 13).  BWA_B200_KMER_K = 0 .. 14
+        // overrides.
         const char *ev = getenv("BWA_B200_KMER_K");
-        int K = ev ? atoi(ev) : 11;
+        const uint64_t bkt_bytes = padded * 4;
+        int K = ev ? atoi(ev) : (bkt_bytes <= (256ull << 20) ? 0 : (bkt_bytes < (1ull << 30) ? 12 : 13));
         while (K > 0 && (1ull << (2 * K)) > seq_len) --K;        // a tiny text does not need 4^K patterns
         int rc = b200_index_build_kmer_table(idx, K);
         if (rc) { bwa_b200_index_free(idx); return rc; }

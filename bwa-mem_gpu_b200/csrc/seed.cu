@@ -1375,6 +1375,7 @@ extern "C" int bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads
 extern "C" double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps)
 {
     if (cudaSetDevice(device) != cudaSuccess) return 0;
+    if (const char *ev = getenv("BWA_B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ev));
     uint32_t *buf = nullptr, *sink = nullptr;
     if (bytes < 4096 || cudaMalloc(&buf, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaMalloc(&sink, 4);

@@ -75,9 +75,9 @@ int  bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], const uint
 /* replicate a resident index onto another device with a peer copy over NVLink */
 int  bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, bwa_b200_index_t **out);
 int  bwa_b200_index_info(const bwa_b200_index_t *idx, bwa_b200_index_info_t *info);
-/* k-mer interval table beside the index (built on the device at load time; K = 11 by default, environment BWA_B200_KMER_K
- * overrides): the suffix-array interval of every pattern of up to K bases, so that an extension step whose result has at most K
- * bases is one L2-resident 8-byte load instead of two dependent occurrence-bucket sectors.  Results do not change.  This call
+/* k-mer interval table beside the index (built on the device at load time for indexes beyond 256 MB of buckets, K = 12 or 13;
+ * environment BWA_B200_KMER_K overrides): the suffix-array interval of every pattern of up to K bases, so that an extension step
+ * whose result has at most K bases is one 8-byte table load instead of two dependent occurrence-bucket sectors.  Results do not change.  This call
  * rebuilds it with another K (0 = drop it, at most 14: 8 * (4^(K+1) - 4) / 3 bytes); the reference's unused hook for the same idea is
  * pre_calc_seed_intervals_wrapper (seed_gen.h:101, src/fastmap.c:455). */
 int  bwa_b200_index_set_kmer_table(bwa_b200_index_t *idx, int K);
