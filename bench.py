@@ -550,7 +550,7 @@ def run_cigar(args, pkg, flush):
     return res
 
 
-def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk, pk_src):
+def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk, pk_src, idx=None, bt=None):
     """roofline block of the dominant seeding kernel: algorithmic bytes = the bucket sectors / LF steps / SA samples the reference's CPU
     algorithm touches on the same reads (instrumented oracle), over the kernel's live CUDA-event time"""
     from oracle import oracle_py as O
@@ -572,15 +572,26 @@ def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk
     achieved = alg[dom] * n / (seed_k[dom] / 1e3) / 1e9
     rs = float(pkg.lib().bwa_b200_measure_random_sector_gbs(local, int(index_bytes), 2048, 2))
     all_alg = sum(alg[k] for k in seed_k) * n / (sum(seed_k.values()) / 1e3) / 1e9
+    issued = None
+    if idx is not None and bt is not None:     # what the kernels themselves ask for: one more pass with the request counters on
+        sd = pkg.Seeder(idx, bt.n, int(bt.d_packed.numel()))
+        sd.request_counts(True)
+        sd.seed_device(bt.d_packed.data_ptr(), bt.d_woff.data_ptr(), bt.d_rl.data_ptr(), bt.n, 19, 500)
+        issued = sd.request_counts(False)
+        sd.destroy()
     roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
             "peak_source": pk_src, "algorithmic_bytes_per_read": alg[dom], "algorithmic_bytes_per_launch": alg[dom] * n, "ms_per_launch": seed_k[dom],
             "share_of_step": seed_k[dom] / sum(kavg.values()) if kavg else None,
             "random_sector_peak_at_index_footprint_gbs": rs, "index_bucket_bytes": int(index_bytes),
-            "frac_of_random_sector": achieved / rs if rs else None,
+            "requests_per_launch": issued,
+            "requested_bucket_gbs": (issued[dom.split("_")[0] + "_sectors"] * 32.0 / (seed_k[dom] / 1e3) / 1e9) if issued and dom in ("fwd_kernel", "back_kernel") else None,
+            "frac_of_random_sector": (issued[dom.split("_")[0] + "_sectors"] * 32.0 / (seed_k[dom] / 1e3) / 1e9 / rs) if issued and rs and dom in ("fwd_kernel", "back_kernel") else None,
+            "algorithmic_over_random_sector": achieved / rs if rs else None,
             "all_seeding_kernels": {"algorithmic_gbs": all_alg, "ms": sum(seed_k.values()), "kernel_ms": seed_k,
                                     "algorithmic_bytes_per_read": {k: alg[k] for k in seed_k}},
-            "note": "achieved = sectors the reference's CPU algorithm touches / kernel time; the k-mer interval table answers the steps on patterns "
-                    "of at most kt_K bases from L2, so fewer sectors than that reach HBM (traffic, from ncu) and frac_of_random_sector may exceed 1"}
+            "note": "achieved = sectors the reference's CPU algorithm touches / kernel time (SURVEY 8d); requested_bucket_gbs = 32-byte bucket sectors the "
+                    "kernel itself requested (counted in the kernel) / the same time, and frac_of_random_sector = that over the measured random-sector "
+                    "gather rate at the index's footprint; the k-mer interval table answers the steps on short patterns, so requested < algorithmic"}
     return roof, per_read
 
 
@@ -605,7 +616,7 @@ def run_c3(args, pkg, local, rank, world, dist, flush, pk, pk_src):
     res["scaling"] = "weak"
     if rank == 0:
         bkt_bytes = int(info.n_buckets) * 32
-        roof, per_read = seeding_roofline(pkg, local, genome, prefix, reads, res["kernel_ms"], bt.n, bkt_bytes, pk, pk_src)
+        roof, per_read = seeding_roofline(pkg, local, genome, prefix, reads, res["kernel_ms"], bt.n, bkt_bytes, pk, pk_src, idx, bt)
         res["roofline"] = roof
         res["oracle_work_per_read"] = per_read
         if not args.no_cpu_baseline:
@@ -710,7 +721,7 @@ def main():
 
     # ---- rooflines: dominant seeding kernel (HBM sectors) and the extension launch set (INT ALU), both from live CUDA-event times
     kavg = chained["kernel_ms"]
-    roofline, per_read = seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, int(info.n_buckets) * 32, pk, pk_src)
+    roofline, per_read = seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, int(info.n_buckets) * 32, pk, pk_src, idx, bt)
     if roofline:
         try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))

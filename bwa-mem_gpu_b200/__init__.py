@@ -108,7 +108,7 @@ SYMBOLS = [
     "bwa_b200_index_free", "bwa_b200_build_index", "bwa_b200_packed_words", "bwa_b200_pack_ascii",
     "bwa_b200_pack_codes", "bwa_b200_seeder_create", "bwa_b200_seeder_destroy", "bwa_b200_seed_host",
     "bwa_b200_seeds_free", "bwa_b200_seed_device", "bwa_b200_seed_device_result", "bwa_b200_seeder_stream",
-    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_measure_int_alu", "bwa_b200_int_alu_op_name", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
+    "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seeder_request_counts", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_measure_int_alu", "bwa_b200_int_alu_op_name", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
     "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
@@ -203,6 +203,7 @@ def lib():
         L.bwa_b200_seed_device_smems.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         L.bwa_b200_seeder_launches.argtypes = [vp]
         L.bwa_b200_seeder_launches.restype = C.c_uint64
+        L.bwa_b200_seeder_request_counts.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
         L.bwa_b200_measure_random_sector_gbs.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.bwa_b200_measure_random_sector_gbs.restype = C.c_double
         L.bwa_b200_measure_int_alu.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -406,6 +407,13 @@ class Seeder:
         check(lib().bwa_b200_seed_device_smems(self.h, n_reads, _p(n_smems), _p(qb), _p(qe), _p(k), _p(s), cap, C.byref(tot)))
         t = int(tot.value)
         return dict(n_smems=n_smems[:n_reads], qbeg=qb[:t], qend=qe[:t], k=k[:t], s=s[:t])
+
+    def request_counts(self, enable=True):
+        """switch the request counting of fwd_kernel / back_kernel on or off; returns the last counted batch's
+        dict(fwd_sectors, fwd_table, back_sectors, back_table)"""
+        out = (C.c_uint64 * 4)()
+        check(lib().bwa_b200_seeder_request_counts(self.h, int(enable), out))
+        return dict(fwd_sectors=int(out[0]), fwd_table=int(out[1]), back_sectors=int(out[2]), back_table=int(out[3]))
 
     @property
     def stream(self) -> int:

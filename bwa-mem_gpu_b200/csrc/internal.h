@@ -53,6 +53,7 @@ struct bwa_b200_seeder {
     uint64_t cand_cap = 0;
     uint32_t *d_ncand = nullptr, *d_nsmems = nullptr, *d_nseeds = nullptr, *d_env = nullptr;
     uint64_t *d_seed_off = nullptr, *d_smem_off = nullptr;
+    unsigned long long *d_stats = nullptr;        // optional request counters (bwa_b200_seeder_request_counts)
     unsigned long long *d_counters = nullptr;     // [0] next_read, [1] next_seed, [2] total seeds, [3] total smems, [4] widest re-seeding row needed
     // re-seeding (passes 2 and 3 of mem_collect_intv): merged interval list per read (cand2, xstride per read) and the
     // pass-2 candidates (cand3, stride3 per read); [4] / [5] of d_counters = widest row a read needed in either

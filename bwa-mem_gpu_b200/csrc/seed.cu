@@ -179,7 +179,7 @@ template <typename RowT, int MINB, bool KT>
 __global__ void __launch_bounds__(FWD_THREADS, MINB)
 fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__restrict__ word_off,
            const uint32_t *__restrict__ read_len, uint32_t n_reads, int min_seed_len, uint32_t cand_stride,
-           Cand *__restrict__ cand, uint32_t *__restrict__ n_cand)
+           Cand *__restrict__ cand, uint32_t *__restrict__ n_cand, unsigned long long *__restrict__ stats)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -187,6 +187,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
     const uint64_t woff = word_off[r];
     Cand *out = cand + (uint64_t)r * cand_stride;
     uint32_t n_out = 0;
+    uint32_t n_sect = 0, n_tab = 0;      // bucket sectors / table entries this lane requested (reported through stats, bench.py's roofline)
     if (len < min_seed_len) { n_cand[r] = 0; return; }   // mem_chain: read shorter than a seed
 
     RowT k = 0, l = 0;
@@ -241,6 +242,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
             RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
             Bkt b0 = ld_bucket_if(!by_table, ix.bkt, j0 >> 6, pol);
             const Bkt b1 = ld_bucket_or(!by_table && (j1 >> 6) != (j0 >> 6), b0, ix.bkt, j1 >> 6, pol);   // both ends in one bucket: one sector (src/bwt.c:369)
+            n_tab += by_table; n_sect += by_table ? 0u : 1u + (uint32_t)((j1 >> 6) != (j0 >> 6));
             uint32_t tk[4], tl[4];
             bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
             bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
@@ -271,6 +273,7 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
     }
     if (active) push(len);                   // reached the end of the read (src/bwt.c:521-522)
     n_cand[r] = n_out;
+    if (stats) { atomicAdd(stats + 0, (unsigned long long)n_sect); atomicAdd(stats + 1, (unsigned long long)n_tab); }
 }
 
 // ------------------------------------------------------------------------------ back_kernel
@@ -316,7 +319,8 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             uint32_t n_reads, int min_seed_len, int max_occ,
             uint32_t cand_stride, Cand *__restrict__ cand, const uint32_t *__restrict__ n_cand,
             uint32_t *__restrict__ n_smems, uint32_t *__restrict__ n_seeds,
-            uint32_t *__restrict__ env_spill, uint32_t env_stride, unsigned long long *__restrict__ next_read)
+            uint32_t *__restrict__ env_spill, uint32_t env_stride, unsigned long long *__restrict__ next_read,
+            unsigned long long *__restrict__ stats)
 {
     __shared__ uint32_t env_s[ENV_SMEM][BACK_THREADS];
     __shared__ uint4 ring[BACK_THREADS / 32][QS];        // {r, n_cand, word_off, -}
@@ -328,6 +332,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
     const uint64_t pol = bucket_policy(ix), tpol = evict_last_policy();
     const int K = KT ? (int)ix.kt_K : 0, klo = KT ? (int)ix.kt_lo : 0;
     uint32_t win = 0, val = 0;           // KT: the first K bases behind the pivot / the current match, as patterns (first base most significant)
+    uint32_t n_sect = 0, n_tab = 0;      // bucket sectors / table entries this lane requested
 
     // warp-uniform queue state: slots [head, tail) hold claimed reads
     uint32_t head = 0, tail = 0;
@@ -436,6 +441,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 const RowT j0 = p0 - (RowT)(p0 >= primary), j1 = p1 - (RowT)(p1 >= primary);
                 const Bkt b1 = ld_bucket_if(!by_table, ix.bkt, j1 >> 6, pol);
                 const Bkt b0 = ld_bucket_or(!by_table && (j0 >> 6) != (j1 >> 6), b1, ix.bkt, j0 >> 6, pol);   // one sector when both ends share a bucket (src/bwt.c:312)
+                n_tab += by_table; n_sect += by_table ? 0u : 1u + (uint32_t)((j0 >> 6) != (j1 >> 6));
                 const uint32_t nl = (b & 1) ? 0u : 0xffffffffu, nh = (b & 2) ? 0u : 0xffffffffu;
                 const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
                 const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
@@ -473,6 +479,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
             }
         }
     }
+    if (stats) { atomicAdd(stats + 2, (unsigned long long)n_sect); atomicAdd(stats + 3, (unsigned long long)n_tab); }
 }
 
 // ------------------------------------------------------------- re-seeding (passes 2 and 3)
@@ -834,9 +841,9 @@ __global__ void total_kernel(const uint32_t *n_per, const uint64_t *off, uint32_
 
 struct U32ToU64 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
 
-using FwdFn = void (*)(IndexView, const uint32_t *, const uint64_t *, const uint32_t *, uint32_t, int, uint32_t, Cand *, uint32_t *);
+using FwdFn = void (*)(IndexView, const uint32_t *, const uint64_t *, const uint32_t *, uint32_t, int, uint32_t, Cand *, uint32_t *, unsigned long long *);
 using BackFn = void (*)(IndexView, const uint32_t *, const uint64_t *, uint32_t, int, int, uint32_t, Cand *, const uint32_t *, uint32_t *,
-                        uint32_t *, uint32_t *, uint32_t, unsigned long long *);
+                        uint32_t *, uint32_t *, uint32_t, unsigned long long *, unsigned long long *);
 // register budget variants (blocks of 128 lanes per SM): more resident lanes = more sectors in flight; KT = with the k-mer table
 template <typename RowT, bool KT> FwdFn fwd_variant_t(int minb)
 {
@@ -1084,7 +1091,7 @@ extern "C" void bwa_b200_seeder_destroy(bwa_b200_seeder_t *s)
     cudaFree(s->d_packed); cudaFree(s->d_len); cudaFree(s->d_woff); cudaFree(s->d_cand); cudaFree(s->d_ncand);
     cudaFree(s->d_nsmems); cudaFree(s->d_nseeds); cudaFree(s->d_env); cudaFree(s->d_seed_off); cudaFree(s->d_smem_off);
     cudaFree(s->d_counters); cudaFree(s->d_cub); cudaFree(s->d_rbeg); cudaFree(s->d_qq); cudaFree(s->d_score);
-    cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_cand3); cudaFree(s->d_ncand3); cudaFree(s->d_rs_dummy); cudaFree(s->d_nsmems1);
+    cudaFree(s->d_stats); cudaFree(s->d_cand2); cudaFree(s->d_ncand2); cudaFree(s->d_cand3); cudaFree(s->d_ncand3); cudaFree(s->d_rs_dummy); cudaFree(s->d_nsmems1);
     cudaFreeHost(s->h_counters);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -1097,6 +1104,22 @@ extern "C" void bwa_b200_seed_params_default(bwa_b200_seed_params_t *p)
 }
 
 extern "C" void *bwa_b200_seeder_stream(bwa_b200_seeder_t *s) { return s ? (void *)s->stream : nullptr; }
+
+// request counters of pass 1: enable != 0 makes fwd_kernel / back_kernel count the bucket sectors and k-mer table entries they ask
+// for (one atomic per lane at exit); out = {fwd sectors, fwd table entries, back sectors, back table entries} of the last batch
+extern "C" int bwa_b200_seeder_request_counts(bwa_b200_seeder_t *s, int enable, uint64_t out[4])
+{
+    if (!s) return BWA_B200_ERR_ARG;
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    if (out) {
+        for (int i = 0; i < 4; ++i) out[i] = 0;
+        if (s->d_stats) B200_CUDA(cudaMemcpy(out, s->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !s->d_stats) { B200_CUDA(cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long))); B200_CUDA(cudaMemset(s->d_stats, 0, 4 * sizeof(unsigned long long))); }
+    if (!enable && s->d_stats) { cudaFree(s->d_stats); s->d_stats = nullptr; }
+    return BWA_B200_OK;
+}
 extern "C" uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s) { return s ? s->launches : 0; }
 
 static int seeder_fill_locate(bwa_b200_seeder *s)
@@ -1151,7 +1174,7 @@ static int seeder_reseed(bwa_b200_seeder *s)
     B200_LAUNCH(s->prof, "back_kernel_pass2", st,
         (back_variant(s->narrow_rows, s->back_minb, ix.kt_K > 0, true)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, s->cur_packed, s->cur_woff, n, p.min_seed_len, p.max_occ, s->stride3,
                                                                                                  s->d_cand3, s->d_ncand3, s->d_rs_dummy, s->d_rs_dummy + s->max_reads, s->d_env,
-                                                                                                 s->env_stride, cnt + 6)));
+                                                                                                 s->env_stride, cnt + 6, (unsigned long long *)nullptr)));
     B200_LAUNCH(s->prof, "merge_kernel", st,
         (merge_kernel<<<grid, RS_THREADS, 0, st>>>(n, s->cur_len, p.min_seed_len, p.max_occ, s->cand_stride, s->d_cand, s->d_ncand, s->d_nsmems1, s->stride3, s->d_cand3, s->d_ncand3, s->d_rs_dummy,
                                                    s->xstride, s->d_cand2, s->d_ncand2, s->d_nsmems, s->d_nseeds, cnt + 4)));
@@ -1193,14 +1216,15 @@ int b200_seeder_run(bwa_b200_seeder *s, const uint32_t *d_packed, const uint64_t
     const uint32_t n = (uint32_t)n_reads;
     cudaStream_t st = s->stream;
     B200_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    if (s->d_stats) B200_CUDA(cudaMemsetAsync(s->d_stats, 0, 4 * sizeof(unsigned long long), st));
     // 32-bit row arithmetic when every BWT row fits (seq_len < 2^32), 64-bit otherwise (human-sized)
     const bool narrow = s->narrow_rows;
     const unsigned fwd_grid = (n + FWD_THREADS - 1) / FWD_THREADS;
     B200_LAUNCH(s->prof, "fwd_kernel", st,
-        (fwd_variant(narrow, s->fwd_minb, ix.kt_K > 0)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand)));
+        (fwd_variant(narrow, s->fwd_minb, ix.kt_K > 0)<<<fwd_grid, FWD_THREADS, 0, st>>>(ix, d_packed, d_woff, d_len, n, p->min_seed_len, s->cand_stride, s->d_cand, s->d_ncand, s->d_stats)));
     B200_LAUNCH(s->prof, "back_kernel", st,
         (back_variant(narrow, s->back_minb, ix.kt_K > 0)<<<s->back_grid, BACK_THREADS, 0, st>>>(ix, d_packed, d_woff, n, p->min_seed_len, p->max_occ, s->cand_stride,
-                                                                                  s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0)));
+                                                                                  s->d_cand, s->d_ncand, s->d_nsmems, s->d_nseeds, s->d_env, s->env_stride, s->d_counters + 0, s->d_stats)));
     s->launches += 2;
     s->cur_packed = d_packed; s->cur_woff = d_woff; s->cur_len = d_len; s->cur_max_len = max_len;
     if (p->reseed) {

@@ -160,6 +160,10 @@ int  bwa_b200_seed_device_smems(bwa_b200_seeder_t *s, uint64_t n_reads, uint32_t
                                 int32_t *host_qbeg, int32_t *host_qend, uint64_t *host_k, uint64_t *host_s,
                                 uint64_t cap, uint64_t *total);
 uint64_t bwa_b200_seeder_launches(const bwa_b200_seeder_t *s);
+/* what the pass-1 kernels actually ask the memory system for (bench.py's roofline): enable != 0 switches the counting on for the
+ * following batches; out (may be NULL) receives {fwd_kernel bucket sectors, fwd_kernel k-mer table entries, back_kernel bucket
+ * sectors, back_kernel k-mer table entries} of the last counted batch */
+int  bwa_b200_seeder_request_counts(bwa_b200_seeder_t *s, int enable, uint64_t out[4]);
 /* random 32-byte-sector gather throughput (GB/s) over a scratch buffer of `bytes`: the measured
  * denominator for the seeding roofline; > L2-sized buffers measure HBM, small ones measure L2 */
 double bwa_b200_measure_random_sector_gbs(int device, uint64_t bytes, int iters, int reps);
