@@ -60,7 +60,7 @@ class KswCounters(C.Structure):
 def build_oracle() -> str:
     """(Re)build oracle/liboracle.so if missing or stale; returns its path."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "global_oracle.c", "region_oracle.c", "region_oracle.h", "global_oracle.h", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("fmd_oracle.c", "ksw_oracle.c", "pipeline_oracle.c", "chain_oracle.c", "global_oracle.c", "region_oracle.c", "sw_oracle.c", "sw_oracle.h", "region_oracle.h", "global_oracle.h", "fmd_oracle.h", "ksw_oracle.h", "jobs_common.h", "chain_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -337,3 +337,40 @@ def ref_build_index(fasta: str, prefix: str, sa_intv: int = 16) -> None:
     subprocess.check_call([os.path.join(REF_DIR, "bwa6"), "index", "-s", "bwt", "-p", prefix, fasta],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
     os.remove(prefix + ".bwt1")
+
+
+# ------------------------------------------------------------------ ksw_align2 (mate rescue / mem_seed_sw)
+SW_XBYTE, SW_XSTOP, SW_XSUBO, SW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
+SW_RES_DT = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+
+
+def _sw_args(jobs, params):
+    mat = np.frombuffer(bytes(params.mat), dtype=np.int8).copy()
+    a = [np.ascontiguousarray(jobs[k], dtype=(np.uint8 if k in ("qseq", "tseq") else np.uint32)) for k in ("qseq", "qoff", "qlen", "tseq", "toff", "tlen", "xtra")]
+    return mat, a
+
+
+def sw_align2_batch(jobs: dict, params: KswParams, n_threads=None):
+    """oracle restatement of ksw_align2 over a batch: jobs = dict(qseq, qoff, qlen, tseq, toff, tlen, xtra); returns SW_RES_DT array"""
+    L = lib()
+    if not getattr(L, "_sw", False):
+        L.sw_align2_batch_oracle.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p, C.c_int, i8p] + [C.c_int] * 4 + [C.c_void_p, C.c_int]
+        L._sw = True
+    mat, (qs, qo, ql, ts, to, tl, xt) = _sw_args(jobs, params)
+    n = ql.size
+    res = np.zeros(max(n, 1), SW_RES_DT)
+    L.sw_align2_batch_oracle(n, qs, qo, ql, ts, to, tl, xt, 5, mat, params.o_del, params.e_del, params.o_ins, params.e_ins, res.ctypes.data, n_threads or default_threads())
+    return res[:n]
+
+
+def fork_sw_align2_batch(jobs: dict, params: KswParams):
+    """the fork's own ksw_align2 (SSE2 ksw_u8 / ksw_i16, oracle/_ref/libforkksw.so) over the same batch"""
+    L = fork_lib()
+    if not getattr(L, "_sw", False):
+        L.fork_ksw_align2_batch.argtypes = [C.c_int64, u8p, u32p, u32p, u8p, u32p, u32p, u32p, C.c_int, i8p] + [C.c_int] * 4 + [C.c_void_p]
+        L._sw = True
+    mat, (qs, qo, ql, ts, to, tl, xt) = _sw_args(jobs, params)
+    n = ql.size
+    res = np.zeros(max(n, 1), SW_RES_DT)
+    L.fork_ksw_align2_batch(n, qs, qo, ql, ts, to, tl, xt, 5, mat, params.o_del, params.e_del, params.o_ins, params.e_ins, res.ctypes.data)
+    return res[:n]

@@ -221,3 +221,50 @@ def make_global_jobs(n_jobs: int, qlen_range=(30, 150), seed: int = 991, sub_rat
     w = diff + 3 + rng.integers(w_extra[0], w_extra[1] + 1, size=n_jobs)
     w = np.maximum(np.minimum(w, w_cap), diff + 1).astype(np.uint32)
     return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlen, tlen=tlen, w=w)
+
+
+def make_sw_jobs(n_jobs: int, qlen_range=(30, 150), tlen_range=(100, 700), seed: int = 4242, sub_rate: float = 0.04, indel_rate: float = 0.01,
+                 none_frac: float = 0.1, n_frac: float = 0.05, xtra=None):
+    """Local-alignment jobs shaped like mate rescue (mem_matesw, src/bwamem_pair.c:119-175): a query and a longer target window that
+    holds a diverged copy of it (or of a part of it, or nothing: none_frac) somewhere inside; codes 0..4.  Byte-per-base buffers with
+    per-job offsets, like make_ext_jobs.  xtra: per-job flags of ksw_align2 (array or scalar); default = the mate-rescue value
+    KSW_XSUBO | KSW_XSTART | (qlen < 250 ? KSW_XBYTE : 0) | 19."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    qs, ts, qoff, toff, qlen, tlen = [], [], [], [], [], []
+    qo = to = 0
+    for _ in range(n_jobs):
+        ql = int(rng.integers(qlen_range[0], qlen_range[1] + 1))
+        tl = int(rng.integers(max(tlen_range[0], 1), tlen_range[1] + 1))
+        q = rng.integers(0, 4, size=ql, dtype=np.uint8)
+        t = rng.integers(0, 4, size=tl, dtype=np.uint8)
+        if rng.random() >= none_frac:
+            a = int(rng.integers(0, max(1, ql // 3)))
+            b = int(rng.integers(min(ql, a + 10), ql + 1))
+            part = q[a:b].copy()
+            mut = rng.random(part.size) < sub_rate
+            part[mut] = (part[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+            out = []
+            for c in part:
+                u = rng.random()
+                if u < indel_rate / 2:
+                    continue
+                out.append(c)
+                if u > 1 - indel_rate / 2:
+                    out.extend(rng.integers(0, 4, size=int(rng.integers(1, 4)), dtype=np.uint8))
+            part = np.asarray(out, dtype=np.uint8)
+            if 0 < part.size <= tl:
+                p = int(rng.integers(0, tl - part.size + 1))
+                t[p:p + part.size] = part
+        if rng.random() < n_frac:
+            q[rng.integers(0, ql, size=max(1, ql // 30))] = 4
+        if rng.random() < n_frac:
+            t[rng.integers(0, tl, size=max(1, tl // 40))] = 4
+        qs.append(q); ts.append(t); qoff.append(qo); toff.append(to); qlen.append(ql); tlen.append(tl)
+        qo += ql; to += tl
+    ql_a = np.asarray(qlen, np.uint32)
+    if xtra is None:
+        x = (0x40000 | 0x80000 | 19) | np.where(ql_a < 250, 0x10000, 0).astype(np.uint32)
+    else:
+        x = np.broadcast_to(np.asarray(xtra, np.uint32), ql_a.shape).copy()
+    return dict(qseq=np.concatenate(qs), tseq=np.concatenate(ts), qoff=np.asarray(qoff, np.uint32), toff=np.asarray(toff, np.uint32),
+                qlen=ql_a, tlen=np.asarray(tlen, np.uint32), xtra=x.astype(np.uint32))
