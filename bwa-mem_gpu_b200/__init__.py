@@ -123,6 +123,7 @@ SYMBOLS = [
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
     "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
     "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
+    "bwa_b200_sw_create", "bwa_b200_sw_destroy", "bwa_b200_sw_align2_host", "bwa_b200_sw_launches",
 ]
 
 ALN_IN_DTYPE = np.dtype([("read", "<u4"), ("qb", "<i4"), ("qe", "<i4"), ("rb", "<i8"), ("re", "<i8"), ("truesc", "<i4"), ("w", "<i4")], align=True)
@@ -258,6 +259,11 @@ def lib():
         L.bwa_b200_aligner_launches.restype = C.c_uint64
         L.bwa_b200_aligner_profile.argtypes = [vp, C.c_int]
         L.bwa_b200_aligner_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+        L.bwa_b200_sw_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.bwa_b200_sw_destroy.argtypes = [vp]
+        L.bwa_b200_sw_align2_host.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, vp]
+        L.bwa_b200_sw_launches.argtypes = [vp]
+        L.bwa_b200_sw_launches.restype = C.c_uint64
         L.bwa_b200_cigar_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.bwa_b200_cigar_destroy.argtypes = [vp]
         L.bwa_b200_cigar_band.argtypes = [C.POINTER(ExtParams), C.c_int, C.c_int, C.c_int64]
@@ -761,3 +767,33 @@ def measure_int_alu(device: int = 0) -> dict:
         check(n)
     return {"sm_mhz": mhz.value, "n_sm": n_sm.value,
             "warp_inst_per_clk_per_sm": {lib().bwa_b200_int_alu_op_name(i).decode(): rates[i] for i in range(n)}}
+
+
+SW_RESULT_DTYPE = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4")])
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000
+
+
+class LocalAligner:
+    """ksw_align2 on the device (bwa_b200_sw_*): the Smith-Waterman call of mate rescue and mem_seed_sw"""
+
+    def __init__(self, device: int = 0):
+        self.h = vp()
+        check(lib().bwa_b200_sw_create(device, C.byref(self.h)))
+
+    def align2_host(self, jobs: dict, ext_p: ExtParams) -> np.ndarray:
+        """jobs = dict(qseq, qoff, qlen, tseq, toff, tlen, xtra), byte-per-base codes 0..4; returns SW_RESULT_DTYPE records (kswr_t)"""
+        a = {k: np.ascontiguousarray(jobs[k], dtype=(np.uint8 if k in ("qseq", "tseq") else np.uint32)) for k in ("qseq", "qoff", "qlen", "tseq", "toff", "tlen", "xtra")}
+        n = a["qlen"].size
+        out = np.zeros(max(n, 1), SW_RESULT_DTYPE)
+        check(lib().bwa_b200_sw_align2_host(self.h, C.byref(ext_p), n, _p(a["qseq"]), a["qseq"].size, _p(a["qoff"]), _p(a["qlen"]),
+                                            _p(a["tseq"]), a["tseq"].size, _p(a["toff"]), _p(a["tlen"]), _p(a["xtra"]), _p(out)))
+        return out[:n]
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_sw_launches(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_sw_destroy(self.h)
+            self.h = None

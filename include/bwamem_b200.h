@@ -346,6 +346,25 @@ int  bwa_b200_reg2aln_host(bwa_b200_cigar_t *c, const bwa_b200_index_t *idx, int
                            const bwa_b200_aln_in_t *alns, uint64_t n_alns, const bwa_b200_ext_params_t *p, int32_t match_score,
                            bwa_b200_aln_out_t *out, uint32_t **cigar, uint64_t *n_ops);
 
+/* -------------------------------------------------- local alignment of mate rescue: ksw_align2 */
+/* The Smith-Waterman call of mate rescue (mem_matesw, src/bwamem_pair.c:119-175, call at :159) and of mem_seed_sw (src/bwamem.c:774-830):
+ * ksw_align2 (src/ksw.c:698-736) over the fork's striped kernels ksw_u8 / ksw_i16 (src/ksw.c:440-696, the SSE2 build: opt->use_avx2 = 0).
+ * One job = (query, target, xtra): xtra carries the reference's flags -- KSW_XBYTE 0x10000 (byte kernel), KSW_XSTOP 0x20000, KSW_XSUBO
+ * 0x40000 (second-best above xtra & 0xffff), KSW_XSTART 0x80000 (second pass over the reversed prefixes for the start positions).
+ * The result is kswr_t field for field.  Bit-exact with the reference's SIMD code, whose values differ from the textbook recurrence
+ * (E is not corrected after the lazy-F pass, F restarts at every stripe): the kernel replays the striped order, see csrc/sw_core.cuh.
+ * A byte-kernel overflow reports score 255 and te, as the reference's first pass does (its second pass is undefined there).
+ * mat / o_del / e_del / o_ins / e_ins are read from the extension parameter block; sequences are byte-per-base codes 0..4. */
+typedef struct bwa_b200_sw bwa_b200_sw_t;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb; } bwa_b200_sw_result_t;
+int  bwa_b200_sw_create(int device, bwa_b200_sw_t **out);
+void bwa_b200_sw_destroy(bwa_b200_sw_t *s);
+int  bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                             const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                             const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                             const uint32_t *xtra, bwa_b200_sw_result_t *out);
+uint64_t bwa_b200_sw_launches(const bwa_b200_sw_t *s);
+
 /* ------------------------------------- seeds -> chains -> extension jobs -> alignment regions */
 /* The step between the two hot paths in the reference worker (src/bwamem.c:2055-2093 and :2286-2306), on the
  * device, so that a read batch goes seeds -> chains -> jobs -> extension -> regions without leaving HBM
