@@ -117,7 +117,7 @@ SYMBOLS = [
     "bwa_b200_pipeline_totals", "bwa_b200_pipeline_profile", "bwa_b200_pipeline_kernel_times",
     "bwa_b200_chain_params_default", "bwa_b200_alignments_free", "bwa_b200_aligner_create", "bwa_b200_aligner_set_contigs",
     "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_host_view", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
-    "bwa_b200_align_device_view", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
+    "bwa_b200_align_device_view", "bwa_b200_aligner_skipped_reads", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
     "bwa_b200_aligner_kernel_times",
     "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_cigars_free",
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
@@ -253,6 +253,7 @@ def lib():
         L.bwa_b200_align_device.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.POINTER(SeedParams), C.POINTER(ChainParams),
                                             C.POINTER(ExtParams)]
         L.bwa_b200_align_device_view.argtypes = [vp, C.POINTER(AlignView)]
+        L.bwa_b200_aligner_skipped_reads.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp)]
         L.bwa_b200_aligner_stream.argtypes = [vp]
         L.bwa_b200_aligner_stream.restype = vp
         L.bwa_b200_aligner_launches.argtypes = [vp]
@@ -623,6 +624,14 @@ class Aligner:
 
     def align_device(self, d_packed, d_woff, d_len, n, max_read_len, seed_p, chain_p, ext_p):
         check(lib().bwa_b200_align_device(self.h, d_packed, d_woff, d_len, n, max_read_len, C.byref(seed_p), C.byref(chain_p), C.byref(ext_p)))
+
+    def skipped_reads(self) -> np.ndarray:
+        """indexes of the last batch's reads left to the caller (long reads that need mem_seed_sw)"""
+        n, p = C.c_uint64(0), vp()
+        check(lib().bwa_b200_aligner_skipped_reads(self.h, C.byref(n), C.byref(p)))
+        if not n.value:
+            return np.zeros(0, np.uint32)
+        return np.frombuffer((C.c_char * (int(n.value) * 4)).from_address(p.value), dtype=np.uint32).copy()
 
     def view(self) -> AlignView:
         v = AlignView()

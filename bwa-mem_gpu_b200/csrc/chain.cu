@@ -19,6 +19,8 @@
 #include "internal.h"
 #include "chain_core.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
+#include <vector>
 
 using namespace b200chain;
 
@@ -42,7 +44,7 @@ struct SeedView { const uint64_t *rbeg; const int32_t *qq; const uint32_t *score
 
 __global__ void __launch_bounds__(128)
 chain_kernel(uint32_t n_reads, bwa_b200_chain_params_t P, Contigs ctg, SeedView S, const uint32_t *__restrict__ read_len,
-             Scratch W, Cnt *__restrict__ cnt, int *__restrict__ err)
+             Scratch W, Cnt *__restrict__ cnt, int *__restrict__ err, uint32_t *__restrict__ skipped)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -55,7 +57,9 @@ chain_kernel(uint32_t n_reads, bwa_b200_chain_params_t P, Contigs ctg, SeedView 
                   W.ch + so, W.nxt + so, W.sq + 2 * so, W.ord + so, W.kidx + so, W.nodes + (so / 3 + 4ull * r), nodes_needed(ns),
                   W.chains + so, W.cseeds + so};
         int nc = chain_read(P, ctg, io);
-        if (nc < 0) { atomicMax(err, nc == -2 ? 1 : 2); nc = 0; }
+        if (nc == -2) skipped[atomicAdd(err + 1, 1)] = r;       // the read needs mem_seed_sw: reported to the caller, no regions, the batch goes on
+        else if (nc < 0) atomicMax(err, 2);
+        if (nc < 0) nc = 0;
         AlnIO ao{l_query, nc, W.chains + so, W.cseeds + so, W.srt + so, W.regs + so};
         int n_short = 0, n_long = 0;
         const int nr = chain2aln_read(P, ctg, ao, &n_short, &n_long);
@@ -170,7 +174,9 @@ struct bwa_b200_aligner {
     Cnt *d_cnt = nullptr, *d_off = nullptr, *d_tot = nullptr, *h_tot = nullptr;
     uint32_t *d_nregs = nullptr, *d_nchains = nullptr; uint64_t *d_region_off = nullptr, *d_chain_off = nullptr, *d_cseed_off = nullptr;
     void *d_cub = nullptr; size_t cub_bytes = 0;
-    int *d_err = nullptr, *h_err = nullptr;
+    int *d_err = nullptr, *h_err = nullptr;          // [0] internal error, [1] reads left to the caller (mem_seed_sw)
+    uint32_t *d_skipped = nullptr;
+    std::vector<uint32_t> skipped;                   // their indexes in the last batch, ascending
     // outputs
     bwa_b200_region_t *d_regions = nullptr; uint64_t region_cap = 0;
     bwa_b200_chain_t *d_chains = nullptr; uint64_t chain_cap = 0;
@@ -253,8 +259,9 @@ extern "C" int bwa_b200_aligner_create(const bwa_b200_index_t *idx, uint64_t max
     B200_CUDA(cudaMalloc(&a->d_tot, sizeof(Cnt))); B200_CUDA(cudaHostAlloc(&a->h_tot, sizeof(Cnt), cudaHostAllocDefault));
     B200_CUDA(cudaMalloc(&a->d_nregs, max_reads * 4)); B200_CUDA(cudaMalloc(&a->d_nchains, max_reads * 4));
     B200_CUDA(cudaMalloc(&a->d_region_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_chain_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_cseed_off, max_reads * 8));
-    B200_CUDA(cudaMalloc(&a->d_err, 4)); B200_CUDA(cudaMemset(a->d_err, 0, 4)); B200_CUDA(cudaHostAlloc(&a->h_err, 4, cudaHostAllocDefault));
-    *a->h_err = 0;
+    B200_CUDA(cudaMalloc(&a->d_err, 8)); B200_CUDA(cudaMemset(a->d_err, 0, 8)); B200_CUDA(cudaHostAlloc(&a->h_err, 8, cudaHostAllocDefault));
+    a->h_err[0] = a->h_err[1] = 0;
+    B200_CUDA(cudaMalloc(&a->d_skipped, (max_reads ? max_reads : 1) * 4));
     B200_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, a->cub_bytes, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)max_reads, a->stream));
     B200_CUDA(cudaMalloc(&a->d_cub, a->cub_bytes + 16));
     if (idx->l_pac < 0x7fffffffull) {           // default: one sequence [0, l_pac)
@@ -279,7 +286,7 @@ extern "C" void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a)
     cudaFree(a->W.chains); cudaFree(a->W.cseeds); cudaFree(a->W.regs);
     cudaFree(a->d_cnt); cudaFree(a->d_off); cudaFree(a->d_tot); cudaFreeHost(a->h_tot);
     cudaFree(a->d_nregs); cudaFree(a->d_nchains); cudaFree(a->d_region_off); cudaFree(a->d_chain_off); cudaFree(a->d_cseed_off);
-    cudaFree(a->d_cub); cudaFree(a->d_err); cudaFreeHost(a->h_err);
+    cudaFree(a->d_cub); cudaFree(a->d_err); cudaFree(a->d_skipped); cudaFreeHost(a->h_err);
     cudaFree(a->d_regions); cudaFree(a->d_chains); cudaFree(a->d_cseeds);
     cudaFree(a->J.qoff); cudaFree(a->J.qlen); cudaFree(a->J.toff); cudaFree(a->J.tlen); cudaFree(a->J.h0); cudaFree(a->J.aux);
     cudaFree(a->d_res); cudaFree(a->d_qp); cudaFree(a->d_tp);
@@ -322,7 +329,8 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         }
         int rc = aligner_ensure_slots(a, S.cap);
         if (rc) return rc;
-        B200_LAUNCH(prof, "chain_kernel", st, (chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, *cp, ctg, S, d_len, a->W, a->d_cnt, a->d_err)));
+        B200_CUDA(cudaMemsetAsync(a->d_err, 0, 8, st));      // also before the retry: attempt 0 may have chained incomplete seed arrays
+        B200_LAUNCH(prof, "chain_kernel", st, (chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, *cp, ctg, S, d_len, a->W, a->d_cnt, a->d_err, a->d_skipped)));
         size_t tmp = a->cub_bytes;
         if (prof) prof->begin("chain_scan", st);
         B200_CUDA(cub::DeviceScan::ExclusiveScan(a->d_cub, tmp, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)n, st));
@@ -330,7 +338,7 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         if (prof) prof->end(st);
         a->launches += 3;
         B200_CUDA(cudaMemcpyAsync(a->h_tot, a->d_tot, sizeof(Cnt), cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaMemcpyAsync(a->h_err, a->d_err, 4, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(a->h_err, a->d_err, 8, cudaMemcpyDeviceToHost, st));
         if (seeds_from_seeder) {
             const uint64_t cap_before = a->seeder->seed_cap;
             rc = b200_seeder_finish(a->seeder);            // synchronises; grows and refills the seed arrays on overflow
@@ -341,13 +349,17 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         B200_CUDA(cudaStreamSynchronize(st));
         break;
     }
-    if (*a->h_err) {
-        const int e = *a->h_err;
-        *a->h_err = 0;
-        cudaMemsetAsync(a->d_err, 0, 4, st);
-        b200::set_error(e == 1 ? "align: a read is long enough for mem_flt_chained_seeds to run mem_seed_sw (about 700 bases); not on this path"
-                               : "align: internal capacity exceeded while chaining a read");
-        return e == 1 ? BWA_B200_ERR_ARG : BWA_B200_ERR_CAPACITY;
+    a->skipped.clear();
+    if (a->h_err[0]) {
+        a->h_err[0] = 0;
+        b200::set_error("align: internal capacity exceeded while chaining a read");
+        return BWA_B200_ERR_CAPACITY;
+    }
+    if (a->h_err[1] > 0) {       // reads long enough for mem_flt_chained_seeds to run mem_seed_sw (about 757 bases and more): left to the caller
+        a->skipped.resize((size_t)a->h_err[1]);
+        B200_CUDA(cudaMemcpyAsync(a->skipped.data(), a->d_skipped, a->skipped.size() * 4, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        std::sort(a->skipped.begin(), a->skipped.end());
     }
     const Cnt T = *a->h_tot;
     a->b_tot = T; a->b_n = n_reads; a->b_detail = detail; a->b_cells = 0;
@@ -409,6 +421,14 @@ extern "C" int bwa_b200_align_device(bwa_b200_aligner_t *a, const uint32_t *dev_
     int rc = b200_seeder_run(a->seeder, dev_packed, dev_word_off, dev_read_len, n_reads, max_read_len, sp);
     if (rc) return rc;
     return aligner_run(a, SeedView{}, true, dev_packed, dev_word_off, dev_read_len, n_reads, cp, ep, a->b_detail);
+}
+
+extern "C" int bwa_b200_aligner_skipped_reads(bwa_b200_aligner_t *a, uint64_t *n, const uint32_t **read_idx)
+{
+    if (!a || !n) return BWA_B200_ERR_ARG;
+    *n = a->skipped.size();
+    if (read_idx) *read_idx = a->skipped.empty() ? nullptr : a->skipped.data();
+    return BWA_B200_OK;
 }
 
 extern "C" int bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v)

@@ -373,9 +373,10 @@ uint64_t bwa_b200_sw_launches(const bwa_b200_sw_t *s);
  *   mem_chain2aln (:1170-1479: rmax window per chain, seeds by descending score, the estimated-extent test that
  *   skips seeds inside an earlier region, left / right jobs with h0 = seed length, SHORT / LONG batch choice),
  *   the local-vs-to-end rule (:1892-1901) and the region arithmetic (:2286-2306).
- * mem_flt_chained_seeds (:970-990) only acts on reads longer than about 700 bases (it runs mem_seed_sw);
- * such reads are refused with BWA_B200_ERR_ARG.  Re-seeding, mem_sort_dedup_patch and everything after it
- * stay with the caller. */
+ * mem_flt_chained_seeds (:970-990) only acts on reads of about 757 bases and more (5.5 ln L <= 0.05 L: it then runs mem_seed_sw on
+ * every chained seed).  Such reads do not fail the batch: they come back with no regions and are listed by
+ * bwa_b200_aligner_skipped_reads, so that the caller routes just those through its own path (the local alignment mem_seed_sw needs is
+ * bwa_b200_sw_align2_host).  mem_sort_dedup_patch and everything after it stay with the caller. */
 typedef struct {               /* the mem_opt_t fields this stage reads (src/bwamem.h:34-73) */
     int32_t a, b, o_del, e_del, o_ins, e_ins, w;
     int32_t min_seed_len, max_occ, max_chain_gap, min_chain_weight, max_chain_extend;
@@ -448,6 +449,9 @@ typedef struct {
     const uint32_t *n_regions_per_read; const uint64_t *region_off; const bwa_b200_region_t *regions;   /* device pointers */
 } bwa_b200_align_view_t;
 int  bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v);
+/* reads of the last batch that were not aligned because mem_flt_chained_seeds would run mem_seed_sw on them (see above): *n of them,
+ * indexes ascending in *read_idx (owned by the aligner, valid until its next call; NULL when there are none) */
+int  bwa_b200_aligner_skipped_reads(bwa_b200_aligner_t *a, uint64_t *n, const uint32_t **read_idx);
 void *bwa_b200_aligner_stream(bwa_b200_aligner_t *a);
 uint64_t bwa_b200_aligner_launches(const bwa_b200_aligner_t *a);
 int  bwa_b200_aligner_profile(bwa_b200_aligner_t *a, int enable);

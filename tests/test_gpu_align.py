@@ -184,13 +184,18 @@ def test_align_rejects_bad_input(gpu, case_index):
     # contigs that do not tile the reference
     with pytest.raises(gpu.B200Error):
         al.set_contigs([0, 100], [100, 200])
-    # a read long enough for mem_flt_chained_seeds' mem_seed_sw is refused, not silently mishandled
-    q = np.random.default_rng(1).integers(0, 4, 1200, dtype=np.uint8)
-    rf, off = flat([q])
+    # a read long enough for mem_flt_chained_seeds' mem_seed_sw does not fail the batch: it comes back without regions and is listed, the
+    # short read beside it is aligned as usual
+    rng = np.random.default_rng(1)
+    q_long, q_short = rng.integers(0, 4, 1200, dtype=np.uint8), fwd[500:650].copy()
+    rf, off = flat([q_long, q_short])
     packed, woff, rl = gpu.pack_codes(rf, off)
-    with pytest.raises(gpu.B200Error):
-        al.align_seeds_host(packed, woff, rl, np.array([100], np.uint64), np.array([[0, 30]], np.int32), np.array([1], np.uint32),
-                            np.array([1], np.uint32), np.array([0], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
+    res = al.align_seeds_host(packed, woff, rl, np.array([100, 500], np.uint64), np.array([[0, 30], [0, 150]], np.int32), np.array([1, 1], np.uint32),
+                              np.array([1, 1], np.uint32), np.array([0, 1], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
+    assert list(al.skipped_reads()) == [0] and list(res["n_regions"]) == [0, 1]
+    res = al.align_seeds_host(packed[woff[1]:], woff[1:] - woff[1], rl[1:], np.array([500], np.uint64), np.array([[0, 150]], np.int32), np.array([1], np.uint32),
+                              np.array([1], np.uint32), np.array([0], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
+    assert al.skipped_reads().size == 0 and list(res["n_regions"]) == [1]
     # empty batch
     e = al.align_host(np.zeros(1, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32), gpu.SeedParams(19, 500), gpu.chain_params(),
                       gpu.ext_params())
