@@ -189,6 +189,7 @@ struct bwa_b200_aligner {
     uint64_t g_cap = 0, g_reads = 0;
     // last batch
     uint64_t b_n = 0, b_seeds = 0, b_cells = 0;
+    int64_t b_max_len = -1;          // longest read of the batch when the caller knows it (bounds the extension jobs)
     Cnt b_tot{};
     bool b_detail = false;
     uint64_t launches = 0;
@@ -390,7 +391,7 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
                                                                          d_packed, d_woff, a->J, a->d_qp, a->d_tp)));
         a->launches += 1;
         B200_CUDA(cudaGetLastError());
-        rc = b200_ext_run_packed(a->ext, ep, (uint32_t)n_jobs, a->d_qp, a->J.qoff, a->J.qlen, a->d_tp, a->J.toff, a->J.tlen, a->J.h0, a->d_res);
+        rc = b200_ext_run_packed(a->ext, ep, (uint32_t)n_jobs, a->d_qp, a->J.qoff, a->J.qlen, a->d_tp, a->J.toff, a->J.tlen, a->J.h0, a->d_res, a->b_max_len);
         if (rc) return rc;
     }
     B200_LAUNCH(prof, "finish_kernel", st,
@@ -418,6 +419,7 @@ extern "C" int bwa_b200_align_device(bwa_b200_aligner_t *a, const uint32_t *dev_
     b200::Prof *prof = a->profiling ? &a->prof : nullptr;
     a->seeder->prof = prof;
     if (prof) prof->reset();
+    a->b_max_len = (int64_t)max_read_len;
     int rc = b200_seeder_run(a->seeder, dev_packed, dev_word_off, dev_read_len, n_reads, max_read_len, sp);
     if (rc) return rc;
     return aligner_run(a, SeedView{}, true, dev_packed, dev_word_off, dev_read_len, n_reads, cp, ep, a->b_detail);
@@ -573,6 +575,7 @@ extern "C" int bwa_b200_align_seeds_host(bwa_b200_aligner_t *a, const uint32_t *
     uint32_t max_len = 0;
     int rc = aligner_upload_reads(a, packed, word_off, read_len, n_reads, &max_len);
     if (rc) return rc;
+    a->b_max_len = -1;            // given seeds: a seed's score (h0) is the caller's, not bounded by the read length
     const uint64_t ns = seeds->n_seeds;
     if (ns > a->g_cap || !a->g_rbeg) {
         uint64_t c;

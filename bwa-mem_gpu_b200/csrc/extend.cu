@@ -71,7 +71,7 @@ __device__ __forceinline__ uint32_t lower_bound_key(const uint32_t *sorted_keys,
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < thr) lo = mid + 1; else hi = mid; }
     return lo;
 }
-__global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag)
+__global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag, int intra_ok)
 {
     const int k = threadIdx.x;
     if (k > N_PBINS + N_BINS + 1) return;
@@ -82,7 +82,9 @@ __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *
     range[k] = lo;
     // anything between the last bin of a class and the next class, or with the bad bit, is not handled
     if (k == N_PBINS && lo < lower_bound_key(sorted_keys, n, CLS_BIT)) atomicExch(err_flag, 2);
-    // keys at or beyond range[N_PBINS + N_BINS + 1] (longer than the last bin, or scores beyond 16 bits) run in ext_intra_kernel
+    // keys at or beyond range[N_PBINS + N_BINS + 1] (longer than the last bin, or scores beyond 16 bits) run in ext_intra_kernel; a caller
+    // that ruled such jobs out (no slabs, no launch) and was wrong gets an error, not missing results
+    if (k == N_PBINS + N_BINS + 1 && !intra_ok && lo < n) atomicExch(err_flag, 3);
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -531,7 +533,7 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
         if (occ > 6) occ = 6;
         e->intra_grid = e->n_sm * occ;
     }
-    B200_CUDA(cudaMalloc(&e->d_intra, (size_t)e->intra_grid * INTRA_WARPS * ((size_t)e->intra_max_q + 1) * sizeof(int2)));
+    // the slabs of ext_intra_kernel (0.47 GB on a 148-SM part) are allocated by the first batch that can reach that kernel (ext_launch)
     B200_CUDA(cudaMemset(e->d_cells, 0, 8));
     B200_CUDA(cudaMemset(e->d_err, 0, 4));
     B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
@@ -592,8 +594,10 @@ static void to_dev_params(const bwa_b200_ext_params_t *p, ExtParams *d)
 
 // sort by query length, derive bin ranges, launch one kernel per bin (empty bins exit at once)
 template <bool BYTES>
+// may_intra: some job of the batch may be beyond the per-lane kernels (query longer than 1024 bases or scores beyond 16 bits); callers
+// that know the batch cannot hold one (short reads) pass false and neither the launch nor the slab allocation happens
 static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n, const JobView &J,
-                      bwa_b200_ext_result_t *d_res)
+                      bwa_b200_ext_result_t *d_res, bool may_intra = true)
 {
     if (p->e_del <= 0 || p->e_ins <= 0) { b200::set_error("extend: gap extension penalties must be positive"); return BWA_B200_ERR_ARG; }
     ExtParams P;
@@ -610,7 +614,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, e->d_keys, e->d_vals);
     size_t tmp = e->cub_bytes;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
-    range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err);
+    range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err, may_intra ? 1 : 0);
     if (e->prof) e->prof->end(e->stream);
     e->launches += 3;
     static const int bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};
@@ -685,7 +689,9 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
             (kern<<<grid, nt, smem, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
-    {   // one warp per job for what is left (queries beyond the last bin, scores beyond 16 bits); exits at once when there is none
+    if (may_intra && !e->d_intra)
+        B200_CUDA(cudaMalloc(&e->d_intra, (size_t)e->intra_grid * INTRA_WARPS * ((size_t)e->intra_max_q + 1) * sizeof(int2)));
+    if (may_intra) {   // one warp per job for what is left (queries beyond the last bin, scores beyond 16 bits); exits at once when there is none
         cudaStream_t st = bin_stream();
         B200_LAUNCH(e->prof, "ext_intra_kernel", st,
             (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), n, e->intra_max_q,
@@ -738,7 +744,14 @@ extern "C" int bwa_b200_extend_async_paged(bwa_b200_extender_t *e, const bwa_b20
     B200_CUDA(cudaMemcpyAsync(e->d_tlen, tlen, n * 4ull, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(e->d_h0, h0, n * 4ull, cudaMemcpyHostToDevice, st));
     JobView J{e->d_q, e->d_t, nullptr, nullptr, e->d_qoff, e->d_qlen, e->d_toff, e->d_tlen, e->d_h0};
-    rc = ext_launch<true>(e, p, n, J, e->d_res);
+    bool may_intra = false;                    // host arrays: the exact test of key_kernel / range_kernel
+    {
+        int mx = 0;
+        for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
+        for (uint32_t a = 0; a < n && !may_intra; ++a)
+            may_intra = qlen[a] > 1024u || (uint64_t)h0[a] + (uint64_t)qlen[a] * (uint64_t)mx >= 32767ull;
+    }
+    rc = ext_launch<true>(e, p, n, J, e->d_res, may_intra);
     if (rc) return rc;
     if (res6) B200_CUDA(cudaMemcpyAsync(res6, e->d_res, n * sizeof(bwa_b200_ext_result_t), cudaMemcpyDeviceToHost, st));
     if (aln_score || query_end || target_end) {
@@ -820,12 +833,16 @@ extern "C" int bwa_b200_extend_device(bwa_b200_extender_t *e, const bwa_b200_ext
 int b200_ext_run_packed(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n,
                         const uint32_t *d_qp, const uint32_t *d_qoff, const uint32_t *d_qlen,
                         const uint32_t *d_tp, const uint32_t *d_toff, const uint32_t *d_tlen,
-                        const uint32_t *d_h0, bwa_b200_ext_result_t *d_res)
+                        const uint32_t *d_h0, bwa_b200_ext_result_t *d_res, int64_t max_read_len)
 {
     int rc = ext_grow_jobs(e, n);
     if (rc) return rc;
     JobView J{nullptr, nullptr, d_qp, d_tp, d_qoff, d_qlen, d_toff, d_tlen, d_h0};
-    rc = ext_launch<false>(e, p, n, J, d_res);
+    // queries and seed scores are bounded by the longest read (h0 = seed length * a): short reads never reach ext_intra_kernel
+    int mx = 1;
+    for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
+    const bool may_intra = max_read_len < 0 || max_read_len > 1024 || (uint64_t)max_read_len * (uint64_t)(2 * mx) >= 32767ull;
+    rc = ext_launch<false>(e, p, n, J, d_res, may_intra);
     if (rc) return rc;
     B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
     e->pending = true;

@@ -123,4 +123,4 @@ int b200_seeder_finish(bwa_b200_seeder *s);
 int b200_ext_run_packed(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n,
                         const uint32_t *d_qp, const uint32_t *d_qoff, const uint32_t *d_qlen,
                         const uint32_t *d_tp, const uint32_t *d_toff, const uint32_t *d_tlen,
-                        const uint32_t *d_h0, bwa_b200_ext_result_t *d_res);
+                        const uint32_t *d_h0, bwa_b200_ext_result_t *d_res, int64_t max_read_len = -1);

@@ -249,7 +249,7 @@ static int pipe_enqueue(bwa_b200_pipeline *p)
     B200_LAUNCH(prof, "cut_kernel", st,
         (cut_kernel<<<p->n_sm * 16, 256, 0, st>>>(2 * n, (int64_t)p->idx->l_pac, p->idx->d_pac, (int64_t)((p->idx->l_pac + 15) / 16 + 1), p->b_packed, p->b_woff, p->d_jq_len,
                                                  p->d_jt_len, p->d_aux, p->qstride, p->tstride, p->d_qp, p->d_tp)));
-    rc = b200_ext_run_packed(p->ext, &p->b_ep, 2 * n, p->d_qp, p->d_jq_off, p->d_jq_len, p->d_tp, p->d_jt_off, p->d_jt_len, p->d_j_h0, p->d_res);
+    rc = b200_ext_run_packed(p->ext, &p->b_ep, 2 * n, p->d_qp, p->d_jq_off, p->d_jq_len, p->d_tp, p->d_jt_off, p->d_jt_len, p->d_j_h0, p->d_res, (int64_t)p->b_maxlen);
     if (rc) return rc;
     B200_LAUNCH(prof, "gather_kernel", st,
         (gather_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, p->d_res, p->d_jq_len, p->b_out, p->d_live)));
