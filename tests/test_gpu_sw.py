@@ -43,7 +43,7 @@ def test_sw_align2_larger_batch_and_argument_checks(pkg, oracle, sw):
     assert sw.launches == l0 + 1
     want = O.sw_align2_batch(jobs, O.make_params())
     assert got.tobytes() == want.tobytes()
-    assert (got["qb"] >= 0).mean() > 0.8 and (got["score2"] > 0).sum() > 0
+    assert (got["qb"] >= 0).mean() > 0.5 and (got["score2"] > 0).sum() > 0      # the workload reaches the KSW_XSTART pass and the second-best score
     bad = dict(jobs)
     bad["qlen"] = jobs["qlen"].copy(); bad["qlen"][5] = 0
     with pytest.raises(pkg.B200Error):
