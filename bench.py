@@ -15,7 +15,8 @@ call (bwa_b200_align_host_view) with H2D and D2H inside the timed region.  `--im
 reference's own CPU functions (oracle/_ref: bwt_smem1 / bwt_sa of bwa_index, the fork's mem_chain .. mem_chain2aln and ksw_extend2)
 on all host threads, in a process that never loads the product library.  The oracle is used only there, for the cpu_baseline legs
 and for the work counters.  Other legs ride in sub_metrics: the fused one-seed step (round 1's headline), the chained step with
-re-seeding, the CIGAR path, BASELINE config 3 (3.1 Gb genome, `c3`) and the reference's CPU `bwa mem` wall time.
+re-seeding, the CIGAR path, BASELINE config 3 (3.1 Gb genome, `c3`), config 4 (extension-only sweep, `c4_extension_sweep`), config 5
+(seeding only on the config-3 index, `c5_seeding`) and the reference's CPU `bwa mem` wall time.
 """
 import argparse
 import json
@@ -304,6 +305,14 @@ class Batch:
             t.numpy()[:] = arr.view(np.uint8)
             self.pin[name] = t
         self.h2d = int(self.packed.nbytes + self.woff.nbytes + self.rl.nbytes)
+        # the compact wire layout (2 bits per base, reads of one length: no per-read array crosses the bus)
+        p2, _, nl = pkg.pack2_codes(flat, off, with_lengths=False)
+        self.n_n = int(nl.size)
+        for name, arr in (("packed2", p2), ("nlist", nl if nl.size else np.zeros(1, np.uint64))):
+            t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+            t.numpy()[:] = arr.view(np.uint8)
+            self.pin[name] = t
+        self.h2d_compact = int(p2.nbytes + nl.nbytes)
 
 
 def max_over_ranks(x, dist):
@@ -365,7 +374,9 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
         for name, x in al.kernel_times():
             kt.setdefault(name, []).append(x)
     al.profile(False)
-    # pinned host buffers in, regions out into the aligner's pinned result buffers (bwa_b200_align_host_view)
+    # ---- host buffers in, host buffers out.  (1) the full 112-byte records through bwa_b200_align_host_view, one batch in flight;
+    # (2) the compact boundary through the in-library dispatcher (bwa_b200_multi_align_compact): 2-bit reads in, 40-byte records out,
+    # the batch dealt in chunks to two workers of this rank's device, so that one chunk's copies run under the other's kernels
     reps = max(2, min(steps, 10))
     pin = bt.pin
     host = al.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=True)
@@ -377,40 +388,44 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
     for _ in range(reps):
         al.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=False)
     e2e_one = world * n * reps / max_over_ranks(time.perf_counter() - t0, dist)
-    al2 = make()
-    errs = []
+    al.destroy()
+    al = None
+    chunk = max(1, (n + args.e2e_chunks - 1) // args.e2e_chunks)
+    multi = pkg.MultiAligner(idx, [torch.cuda.current_device()], 2, chunk, L)
+    if len(lens) > 1:
+        multi.set_contigs(np.concatenate([[0], np.cumsum(lens[:-1])]), lens)
 
-    def worker(a, k):
-        try:
-            for _ in range(k):
-                a.align_host_view(pin["packed"].data_ptr(), pin["woff"].data_ptr(), pin["rl"].data_ptr(), n, sp, cp, ep, copy=False)
-        except Exception as ex:  # noqa: BLE001
-            errs.append(ex)
-
-    worker(al2, 1)
+    def step_compact(copy=False):
+        return multi.align_compact(pin["packed2"].data_ptr(), None, L, n, pin["nlist"].data_ptr() if bt.n_n else None, bt.n_n, sp, cp, ep, copy=copy, gather=copy)
+    comp = step_compact(copy=True)
+    step_compact()
+    assert int(comp["regions"].size) == n_reg
+    cu = pkg.unpack_compact(comp)
+    same_c = bool((cu["n_regions"] == host["n_regions"]).all()) and all(bool((cu[f] == host["regions"][f]).all()) for f in ("rb", "re", "qb", "qe", "score", "truesc", "rid", "seedcov", "seedlen0", "w"))
+    assert same_c, "compact boundary returned different regions than the full-record call"
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    th = [threading.Thread(target=worker, args=(al, (reps + 1) // 2)), threading.Thread(target=worker, args=(al2, reps // 2))]
+    l0m = multi.launches
     t0 = time.perf_counter()
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
+    for _ in range(reps):
+        step_compact()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dist)
-    assert not errs, errs
-    al2.destroy()
+    e2e_launches = (multi.launches - l0m) // reps
+    multi.destroy()
     kavg = {k: float(np.mean(x)) for k, x in kt.items()}
     ext_ms = kavg.get("ext_phase", 0.0)
-    d2h = int(n_reg * pkg.REGION_DTYPE.itemsize + n * 12)
+    d2h_full = int(n_reg * pkg.REGION_DTYPE.itemsize + n * 12)
+    d2h = int(n_reg * pkg.REGION_COMPACT_DTYPE.itemsize + n * 4)
     res = {"reads_per_s": world * n * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
-           "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_one_batch_in_flight": e2e_one, "e2e_h2d_bytes_per_step": bt.h2d, "e2e_d2h_bytes_per_step": d2h,
+           "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_h2d_bytes_per_step": bt.h2d_compact, "e2e_d2h_bytes_per_step": d2h,
+           "e2e_chunks_per_step": int((n + chunk - 1) // chunk), "e2e_gpu_launches": int(e2e_launches), "e2e_identical_to_full_records": same_c,
+           "e2e_full_records_one_batch_in_flight": e2e_one, "e2e_full_records_h2d_bytes_per_step": bt.h2d, "e2e_full_records_d2h_bytes_per_step": d2h_full,
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
            "gpu_launches": int(launches), "kernel_ms": kavg,
            "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"
                      + ("; re-seeding split_factor 1.5 split_width 10 max_mem_intv 20" if reseed else "; SMEM pass 1 only")}
-    al.destroy()
     return res, host, clocks
 
 
@@ -595,6 +610,143 @@ def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk
     return roof, per_read
 
 
+def run_c4(args, pkg, local, rank, world, dist, flush, int_peak_gcups_s16x2):
+    """BASELINE config 4: extension-only sweep -- ksw_extend2 batches of one query length and one band each, query 100..300 bp x band
+    16..100, z-drop 100 and 0, end bonus 5, h0 in [19, 150], targets of qlen + min(qlen, 2w) bases.  Every rank runs the
+    whole grid on its own GPU (weak scaling; ms = max over ranks).  Jobs are packed in HBM before the timed region; GCUPS counts the
+    cells ksw_extend2 evaluates (counted on the device, equal to the oracle's count on the checked sample).  Rank 0 also runs the
+    reference's own ksw_extend2 on all host cores over the first 2^14 jobs of every point and asserts the results are identical."""
+    import torch
+    from oracle import oracle_py as O
+    ex = pkg.Extender(local)
+    st = torch.cuda.ExternalStream(ex.stream)
+    bn = 1 << 14
+    t = max(1, args.c4_jobs // bn)
+    n = bn * t
+    rows = []
+    ref_ok = (not args.no_cpu_baseline) and rank == 0 and O.have_ref()
+    for qlen in (100, 150, 200, 250, 300):
+        for w in (16, 32, 50, 64, 100):
+            base = synth.make_ext_jobs(bn, w=w, seed=777 + qlen + w, qlen_range=(qlen, qlen), h0_range=(19, 150))
+            dq = torch.from_numpy(base["qseq"]).cuda().repeat(t)
+            dt = torch.from_numpy(base["tseq"]).cuda().repeat(t)
+            qp = torch.empty((dq.numel() + 7) // 8, dtype=torch.int32, device="cuda")
+            tp = torch.empty((dt.numel() + 7) // 8, dtype=torch.int32, device="cuda")
+            ex.pack_device(dq.data_ptr(), dq.numel(), qp.data_ptr())
+            ex.pack_device(dt.data_ptr(), dt.numel(), tp.data_ptr())
+            rep = torch.arange(t, device="cuda", dtype=torch.int64).repeat_interleave(bn)
+            dev = {k: torch.from_numpy(base[k].astype(np.int64)).cuda().repeat(t) for k in ("qoff", "toff", "qlen", "tlen", "h0")}
+            dev["qoff"] += rep * int(base["qseq"].size)
+            dev["toff"] += rep * int(base["tseq"].size)
+            assert int(dev["qoff"].max()) < 2 ** 32 and int(dev["toff"].max()) < 2 ** 32
+            dev = {k: v.to(torch.int32) if k in ("qlen", "tlen", "h0") else (v & 0xffffffff).to(torch.int64).to(torch.int32) for k, v in dev.items()}
+            res = torch.zeros(n * 6, dtype=torch.int32, device="cuda")
+            del dq, dt, rep
+            for zdrop in (100, 0):
+                ep = pkg.ext_params(w=w, zdrop=zdrop)
+
+                def fn():
+                    ex.extend_device(ep, n, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(), tp.data_ptr(), dev["toff"].data_ptr(),
+                                     dev["tlen"].data_ptr(), dev["h0"].data_ptr(), res.data_ptr())
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                ms = 0.0
+                for _ in range(args.c4_reps):
+                    with torch.cuda.stream(st):
+                        flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(st); fn(); b.record(st)
+                    torch.cuda.synchronize()
+                    ms += a.elapsed_time(b)
+                ex.wait()
+                ms = max_over_ranks(ms / args.c4_reps, dist)
+                cells = int(ex.last_cells())
+                row = {"qlen": qlen, "w": w, "zdrop": zdrop, "jobs": n, "ms": ms, "cells": cells, "GCUPS": world * cells / (ms / 1e3) / 1e9,
+                       "Mjobs_per_s": world * n / (ms / 1e3) / 1e6, "frac_s16x2": (cells / (ms / 1e3) / 1e9) / int_peak_gcups_s16x2 if int_peak_gcups_s16x2 else None}
+                if ref_ok:
+                    got = res[:bn * 6].cpu().numpy().reshape(bn, 6)
+                    kp = O.make_params(w=w, zdrop=zdrop)
+                    want = np.zeros((bn, 6), np.int32)
+                    t0 = time.perf_counter()
+                    O.ref_lib().ref_ksw_batch(bn, base["qseq"], base["qoff"], base["qlen"], base["tseq"], base["toff"], base["tlen"], base["h0"], kp.mat,
+                                              kp.o_del, kp.e_del, kp.o_ins, kp.e_ins, kp.w, kp.end_bonus, kp.zdrop, want.reshape(-1), O.default_threads())
+                    cdt = time.perf_counter() - t0
+                    assert (got == want).all(), f"c4: ksw_extend2 results differ from the reference at qlen {qlen} w {w} zdrop {zdrop}"
+                    row["cpu_reference_GCUPS"] = (cells / t) / cdt / 1e9
+                    row["identical_to_reference_on_sample"] = True
+                rows.append(row)
+            del qp, tp, dev, res
+            torch.cuda.empty_cache()
+    ex.destroy()
+    out = {"workload": f"{n} jobs per point (2^14 distinct, tiled), every rank the whole grid; h0 in [19,150], 5% substitutions, 1% indels, 1% of jobs with N, "
+                       "target = query + min(qlen, 2w) bases, end bonus 5, scoring 1/4/6/1", "scaling": "weak", "points": rows,
+           "min_frac_s16x2": min((r["frac_s16x2"] for r in rows if r["frac_s16x2"]), default=None),
+           "min_GCUPS_per_gpu": min(r["GCUPS"] for r in rows) / world, "max_GCUPS_per_gpu": max(r["GCUPS"] for r in rows) / world}
+    if ref_ok:
+        out["cpu_baseline"] = {"kind": "reference", "cores": O.default_threads(), "unit": "GCUPS",
+                               "value": float(np.median([r["cpu_reference_GCUPS"] for r in rows])),
+                               "sample": "the reference's ksw_extend2 (bwa_index/ksw.c) over the first 2^14 jobs of every point, all host threads; median over the grid",
+                               "gpu_output_identical_on_sample": True}
+    return out
+
+
+def run_c5(args, pkg, idx, genome, prefix, local, rank, world, dist, flush, pk, pk_src):
+    """BASELINE config 5: seeding only -- SMEMs (min_seed_len 19) + SA locate of 250 bp reads against the 3.1 Gb index, reads/s with
+    the reads resident in HBM, pass 1 as the reference's GPU path runs it and with re-seeding; the seeding roofline; identity with the
+    reference's own bwt_smem1 / bwt_sa on a sample and that CPU loop's rate on all host threads."""
+    import torch
+    reads, _, _ = synth.make_reads(genome, args.c5_reads, 250, seed=778 + rank)
+    n, L = reads.shape
+    packed, woff, rl = pkg.pack_codes(reads.reshape(-1), (np.arange(n + 1, dtype=np.uint64) * np.uint64(L)))
+    d_packed = torch.from_numpy(packed.view(np.int32)).cuda(); d_woff = torch.from_numpy(woff.view(np.int64)).cuda(); d_rl = torch.from_numpy(rl.view(np.int32)).cuda()
+    sd = pkg.Seeder(idx, n, packed.size)
+    st = torch.cuda.ExternalStream(sd.stream)
+    out = {"workload": f"{n} synthetic 250bp reads (1% sub, 0.1% indel) per GPU vs the {args.c3_genome} bp genome", "scaling": "weak", "modes": {}}
+    for name, par in (("pass1", pkg.seed_params(19, 500)), ("reseed", pkg.seed_params(19, 500, True))):
+        def fn():
+            sd.seed_device(d_packed.data_ptr(), d_woff.data_ptr(), d_rl.data_ptr(), n, params=par)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        ms = 0.0
+        reps = 3
+        for _ in range(reps):
+            with torch.cuda.stream(st):
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); fn(); b.record(st)
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        ms = max_over_ranks(ms / reps, dist)
+        out["modes"][name] = {"ms": ms, "Mreads_per_s": world * n / (ms / 1e3) / 1e6, "seeds": int(sd.device_result().n_seeds)}
+    sd.destroy()
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import chain_py as CP, oracle_py as O
+        s_n = min(n, args.c5_cpu_sample)
+        flat = reads[:s_n].reshape(-1).copy()
+        off = (np.arange(s_n + 1) * L).astype(np.uint64)
+        h = O.ref_lib().ref_load((prefix + ".bwt128").encode(), (prefix + ".sa").encode())
+        CP.ref_seed_arrays(h, flat[:L * 2000], off[:2001], 19, 500, O.default_threads())
+        t0 = time.perf_counter()
+        want = CP.ref_seed_arrays(h, flat, off, 19, 500, O.default_threads())
+        cdt = time.perf_counter() - t0
+        O.ref_lib().ref_free(h)
+        sp, swoff, srl = pkg.pack_codes(flat, off)
+        sd2 = pkg.Seeder(idx, s_n, sp.size)
+        got = sd2.seed_host(sp, swoff, srl, 19, 500)
+        sd2.destroy()
+        same = bool((got["n_seeds"] == want["n_seeds"]).all() and (got["rbeg"] == want["rbeg"]).all() and (got["qq"] == want["qq"]).all()
+                    and (got["score"] == want["score"]).all())
+        assert same, "c5: seeds differ from the reference's bwt_smem1 / bwt_sa on the bench sample"
+        out["cpu_baseline"] = {"value": s_n / cdt / 1e6, "unit": "Mreads/s", "cores": O.default_threads(), "kind": "reference",
+                               "sample": f"first {s_n} reads, the reference's bwt_smem1 + bwt_sa (pass 1, max_occ 500) on all host threads",
+                               "gpu_output_identical_on_sample": same}
+    return out
+
+
 def run_c3(args, pkg, local, rank, world, dist, flush, pk, pk_src):
     """BASELINE config 3: 150 bp reads against a 3.1 Gb genome in 24 contigs (sizes in the proportions of GRCh38), index replicated per GPU.
     The chained step device-resident and host-to-host, its kernel times, the seeding roofline in the HBM regime, and identity with the
@@ -631,10 +783,14 @@ def run_c3(args, pkg, local, rank, world, dist, flush, pk, pk_src):
             res["cpu_baseline"] = {"value": sample / cdt, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
                                    "sample": f"first {sample} reads of the batch, {cpu.threads} host threads", "gpu_output_identical_on_sample": same}
             cpu.close()
-    idx.free()
     del bt
     torch.cuda.empty_cache()
-    return res
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5(args, pkg, idx, genome, prefix, local, rank, world, dist, flush, pk, pk_src)
+    idx.free()
+    torch.cuda.empty_cache()
+    return res, c5
 
 
 def main():
@@ -652,9 +808,16 @@ def main():
     ap.add_argument("--no-chain", action="store_true", help="only the fused one-seed step (kernel A/B runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the re-seeding, CIGAR and bwa-mem sub-metrics")
     ap.add_argument("--no-c3", action="store_true", help="skip BASELINE config 3 (3.1 Gb genome)")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks the host-to-host step deals its batch in")
     ap.add_argument("--c3-genome", type=int, default=3_100_000_000)
     ap.add_argument("--c3-reads", type=int, default=1_250_000, help="reads per GPU of config 3 (10 M reads over 8 GPUs)")
     ap.add_argument("--c3-cpu-sample", type=int, default=50_000)
+    ap.add_argument("--no-c4", action="store_true", help="skip BASELINE config 4 (extension-only sweep)")
+    ap.add_argument("--c4-jobs", type=int, default=1 << 22, help="jobs per point of the extension sweep")
+    ap.add_argument("--c4-reps", type=int, default=3)
+    ap.add_argument("--no-c5", action="store_true", help="skip BASELINE config 5 (seeding only, 250 bp reads, the config-3 index)")
+    ap.add_argument("--c5-reads", type=int, default=500_000, help="250 bp reads per GPU of config 5 (4 M reads over 8 GPUs)")
+    ap.add_argument("--c5-cpu-sample", type=int, default=20_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -702,10 +865,16 @@ def main():
     if not args.no_extras:
         chained_rs, _, _ = run_chained(args, pkg, idx, bt, flush, dref, world, lens, reseed=True, steps=max(3, min(args.steps, 10)))
 
-    c3 = None
+    c3 = c4 = c5 = None
+    ia = pkg.measure_int_alu(local)      # measured issue rates (warp-instructions per clock per SM) and the SM clock under load
+    r_ = ia["warp_inst_per_clk_per_sm"]
+    alu_rate = max(r_["IADD3"], r_["PRMT"], r_["VIADDMNMX.S16x2"], r_["VIMNMX3.S16x2"])
+    int_peak_gops = ia["n_sm"] * alu_rate * 32 * ia["sm_mhz"] / 1e3          # thread-level integer ALU operations per second / 1e9
+    if not args.no_c4:
+        c4 = run_c4(args, pkg, local, rank, world, dref, flush, 2 * int_peak_gops / 15.0)
     if not args.no_c3:
         try:
-            c3 = run_c3(args, pkg, local, rank, world, dref, flush, pk, pk_src)
+            c3, c5 = run_c3(args, pkg, local, rank, world, dref, flush, pk, pk_src)
         except AssertionError:
             raise
         except Exception as ex:  # noqa: BLE001  (e.g. not enough host memory for the 6.2 G-row index build on a small box)
@@ -733,10 +902,6 @@ def main():
             log("no ncu traffic figure:", ex)
     ext_ms = kavg.get("ext_phase", 0.0)
     gcups = chained["cells_per_step"] / (ext_ms / 1e3) / 1e9 if ext_ms > 0 else None
-    ia = pkg.measure_int_alu(local)      # measured issue rates (warp-instructions per clock per SM) and the SM clock under load
-    r = ia["warp_inst_per_clk_per_sm"]
-    alu_rate = max(r["IADD3"], r["PRMT"], r["VIADDMNMX.S16x2"], r["VIMNMX3.S16x2"])
-    int_peak_gops = ia["n_sm"] * alu_rate * 32 * ia["sm_mhz"] / 1e3          # thread-level integer ALU operations per second / 1e9
     ext_roof = {"bound": "int_alu", "achieved_gcups": gcups, "ops_per_cell": 15,
                 "measured": ia, "alu_warp_inst_per_clk_per_sm": alu_rate,
                 "peak_gcups_int32": int_peak_gops / 15.0, "frac_int32": gcups / (int_peak_gops / 15.0) if gcups else None,
@@ -800,10 +965,13 @@ def main():
                    "parallelism": f"reads sharded over {world} rank(s), index replicated, no collective"},
         "clocks": clocks, "gpu_launches": chained["gpu_launches"],
         "e2e": {"value": chained["e2e_reads_per_s"], "unit": UNIT, "h2d_bytes_per_step": chained["e2e_h2d_bytes_per_step"],
-                "d2h_bytes_per_step": chained["e2e_d2h_bytes_per_step"], "batches_in_flight": 2, "value_one_batch_in_flight": chained["e2e_one_batch_in_flight"],
-                "how": "bwa_b200_align_host_view with pinned host buffers, two aligner handles driven by two host threads (the reference's NB_STREAMS = 2 pattern)"},
+                "d2h_bytes_per_step": chained["e2e_d2h_bytes_per_step"], "chunks_per_step": chained["e2e_chunks_per_step"],
+                "identical_to_full_records": chained["e2e_identical_to_full_records"],
+                "full_records_one_batch_in_flight": chained["e2e_full_records_one_batch_in_flight"],
+                "how": "bwa_b200_multi_align_compact from pinned host buffers: 2-bit reads in, 40-byte region records out, the batch dealt in chunks to "
+                       "two worker threads of the rank's device (the reference's NB_STREAMS = 2 pattern, src/fastmap.c:31), every chunk's H2D and D2H inside the timed region"},
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
-        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "c3": c3, "bwa_mem_cpu": bwa_mem,
+        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,
                         "extension_GCUPS": gcups, "oracle_work_per_read": per_read,
                         "seeding_Mreads_per_s": n / (sum(kavg[k] for k in ("fwd_kernel", "back_kernel", "fill_kernel", "locate_kernel") if k in kavg) / 1e3) / 1e6},
     }

@@ -124,6 +124,9 @@ SYMBOLS = [
     "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
     "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
     "bwa_b200_sw_create", "bwa_b200_sw_destroy", "bwa_b200_sw_align2_host", "bwa_b200_sw_launches",
+    "bwa_b200_packed2_words", "bwa_b200_pack2_codes", "bwa_b200_pack2_ascii", "bwa_b200_align_host_compact",
+    "bwa_b200_multi_create", "bwa_b200_multi_set_contigs", "bwa_b200_multi_align_compact", "bwa_b200_multi_n_workers",
+    "bwa_b200_multi_worker_chunks", "bwa_b200_multi_launches", "bwa_b200_multi_destroy",
 ]
 
 ALN_IN_DTYPE = np.dtype([("read", "<u4"), ("qb", "<i4"), ("qe", "<i4"), ("rb", "<i8"), ("re", "<i8"), ("truesc", "<i4"), ("w", "<i4")], align=True)
@@ -150,6 +153,9 @@ REGION_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("rb_est", "<i8"), ("re_e
                          ("qb_est", "<i4"), ("qe_est", "<i4"), ("rid", "<i4"), ("align_sides", "<i4"), ("where_is_long", "<i4"),
                          ("query_seed_begin", "<i4"), ("seedlen0", "<i4"), ("seedcov", "<i4"), ("w", "<i4"), ("frac_rep", "<f4"),
                          ("left_tlen", "<i4"), ("right_tlen", "<i4"), ("job_short", "<i4"), ("job_long", "<i4")], align=True)
+REGION_COMPACT_DTYPE = np.dtype([("rb", "<i8"), ("rlen", "<i4"), ("qb", "<u2"), ("qe", "<u2"), ("score", "<i4"), ("truesc", "<i4"),
+                                 ("seedcov", "<i4"), ("rid", "<i4"), ("w", "<u2"), ("seedlen0", "<u2"), ("frac_rep", "<f4")], align=True)
+assert REGION_COMPACT_DTYPE.itemsize == 40
 JOB_DTYPE = np.dtype([("qoff", "<u4"), ("qlen", "<u4"), ("toff", "<u4"), ("tlen", "<u4"), ("h0", "<u4")], align=True)
 assert CHAIN_DTYPE.itemsize == 40 and CHAIN_SEED_DTYPE.itemsize == 24 and REGION_DTYPE.itemsize == 112 and JOB_DTYPE.itemsize == 20
 
@@ -210,6 +216,23 @@ def lib():
         L.bwa_b200_measure_int_alu.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.bwa_b200_int_alu_op_name.argtypes = [C.c_int]
         L.bwa_b200_int_alu_op_name.restype = C.c_char_p
+        L.bwa_b200_packed2_words.argtypes = [vp, C.c_uint64, C.c_uint32]
+        L.bwa_b200_packed2_words.restype = C.c_size_t
+        L.bwa_b200_pack2_codes.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+        L.bwa_b200_pack2_ascii.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+        L.bwa_b200_align_host_compact.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams),
+                                                  C.POINTER(ExtParams), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
+        L.bwa_b200_multi_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+        L.bwa_b200_multi_set_contigs.argtypes = [vp, C.c_int32, vp, vp, vp]
+        L.bwa_b200_multi_align_compact.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams),
+                                                   C.POINTER(ExtParams), C.POINTER(MultiResult)]
+        L.bwa_b200_multi_n_workers.argtypes = [vp]
+        L.bwa_b200_multi_worker_chunks.argtypes = [vp, C.c_int]
+        L.bwa_b200_multi_worker_chunks.restype = C.c_uint64
+        L.bwa_b200_multi_launches.argtypes = [vp]
+        L.bwa_b200_multi_launches.restype = C.c_uint64
+        L.bwa_b200_multi_destroy.argtypes = [vp]
+        L.bwa_b200_multi_destroy.restype = None
         L.bwa_b200_ext_params_default.argtypes = [C.POINTER(ExtParams)]
         L.bwa_b200_fill_scmat.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int8)]
         L.bwa_b200_extender_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]
@@ -562,6 +585,94 @@ def _take(ptr, n, dtype):
     return np.frombuffer(C.string_at(ptr, int(n) * dtype.itemsize), dtype=dtype).copy()
 
 
+def _view(ptr, cnt, dt, copy=True):
+    """numpy array over cnt items at a C pointer (a copy, or a view valid as long as the owner keeps the buffer)"""
+    dt = np.dtype(dt)
+    val = ptr.value if hasattr(ptr, "value") else ptr
+    if not val or not cnt:
+        return np.zeros(0, dt)
+    v = np.frombuffer((C.c_char * (int(cnt) * dt.itemsize)).from_address(val), dtype=dt)
+    return v.copy() if copy else v
+
+
+def pack2_codes(codes: np.ndarray, base_off: np.ndarray, with_lengths: bool = True, n_threads: int = 0):
+    """codes (0..3, anything else = N) -> (packed2, read_len or None, n_list): the compact wire layout of bwa_b200_align_host_compact"""
+    codes = np.ascontiguousarray(codes, np.uint8); base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = base_off.size - 1
+    lens = (base_off[1:] - base_off[:-1]).astype(np.uint32)
+    words = int(((lens.astype(np.uint64) + np.uint64(15)) // np.uint64(16)).sum())
+    packed2 = np.zeros(max(words, 1), np.uint32)
+    rl = np.zeros(max(n, 1), np.uint32)
+    cap = int((codes > 3).sum()) + 1
+    nl = np.zeros(cap, np.uint64)
+    nn = C.c_uint64(0)
+    check(lib().bwa_b200_pack2_codes(_p(codes), _p(base_off), n, _p(packed2), _p(rl), _p(nl), cap, C.byref(nn), n_threads))
+    return packed2[:words], (rl[:n] if with_lengths else None), nl[:nn.value].copy()
+
+
+def unpack_compact(res: dict) -> dict:
+    """the compact records with the names of REGION_DTYPE (re = rb + rlen), and exclusive region offsets per read"""
+    r = res["regions"]
+    off = np.zeros(res["n_regions"].size, np.uint64)
+    if off.size:
+        off[1:] = np.cumsum(res["n_regions"][:-1], dtype=np.uint64)
+    return dict(n_regions=res["n_regions"], region_off=off, rb=r["rb"].astype(np.int64), re=r["rb"] + r["rlen"], qb=r["qb"].astype(np.int32), qe=r["qe"].astype(np.int32),
+                score=r["score"], truesc=r["truesc"], seedcov=r["seedcov"], rid=r["rid"], w=r["w"].astype(np.int32), seedlen0=r["seedlen0"].astype(np.int32),
+                frac_rep=r["frac_rep"])
+
+
+class MultiResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_regions", C.c_uint64), ("n_chunks", C.c_uint64), ("chunk_reads", C.c_uint64),
+                ("n_regions_per_read", vp), ("chunk_region_off", vp), ("regions", vp)]
+
+
+class MultiAligner:
+    """every GPU of the box behind one call (bwa_b200_multi_*): chunks of reads dealt to worker threads, the index replicated by peer copies"""
+
+    def __init__(self, index, devices, workers_per_device: int, chunk_reads: int, max_read_len: int):
+        self.h = vp()
+        self.index = index
+        dv = (C.c_int * len(devices))(*devices)
+        check(lib().bwa_b200_multi_create(index.h, dv, len(devices), workers_per_device, chunk_reads, max_read_len, C.byref(self.h)))
+
+    def set_contigs(self, offset, length, is_alt=None):
+        off = np.ascontiguousarray(offset, dtype=np.int64); ln = np.ascontiguousarray(length, dtype=np.int32)
+        alt = np.ascontiguousarray(is_alt, dtype=np.int32) if is_alt is not None else None
+        check(lib().bwa_b200_multi_set_contigs(self.h, ln.size, _p(off), _p(ln), _p(alt)))
+
+    def align_compact(self, packed2_ptr, len_ptr, uniform_len, n, nlist_ptr, n_n, seed_p, chain_p, ext_p, copy=True, gather=True):
+        """regions of the whole batch; gather=True puts the chunks' records in read order (a host copy), False returns them as the chunks landed
+        together with chunk_region_off"""
+        out = MultiResult()
+        check(lib().bwa_b200_multi_align_compact(self.h, packed2_ptr, len_ptr or None, uniform_len, n, nlist_ptr or None, n_n, C.byref(seed_p), C.byref(chain_p),
+                                                 C.byref(ext_p), C.byref(out)))
+        nregs = _view(out.n_regions_per_read, n, np.uint32, copy)
+        coff = _view(out.chunk_region_off, out.n_chunks, np.uint64, True)
+        regs = _view(out.regions, out.n_regions, REGION_COMPACT_DTYPE, copy and not gather)
+        res = dict(n_regions=nregs, chunk_region_off=coff, chunk_reads=int(out.chunk_reads), n_chunks=int(out.n_chunks), regions=regs)
+        if gather and out.n_chunks:
+            cr = int(out.chunk_reads)
+            per_chunk = np.add.reduceat(nregs.astype(np.uint64), np.arange(0, n, cr))
+            res["regions"] = np.concatenate([regs[int(coff[k]):int(coff[k]) + int(per_chunk[k])] for k in range(int(out.n_chunks))]) if out.n_regions else regs.copy()
+        return res
+
+    @property
+    def n_workers(self) -> int:
+        return int(lib().bwa_b200_multi_n_workers(self.h))
+
+    def worker_chunks(self):
+        return [int(lib().bwa_b200_multi_worker_chunks(self.h, i)) for i in range(self.n_workers)]
+
+    @property
+    def launches(self) -> int:
+        return int(lib().bwa_b200_multi_launches(self.h))
+
+    def destroy(self):
+        if self.h:
+            lib().bwa_b200_multi_destroy(self.h)
+            self.h = vp()
+
+
 class Aligner:
     """seeds -> chains -> extension jobs -> extension -> alignment regions on the device (bwa_b200_align_*)."""
 
@@ -611,6 +722,14 @@ class Aligner:
             v = np.frombuffer((C.c_char * (int(cnt) * dt.itemsize)).from_address(ptr.value), dtype=dt)
             return v.copy() if copy else v
         return dict(n_regions=arr(a, n, np.uint32), region_off=arr(b, n, np.uint64), regions=arr(c, nr.value, REGION_DTYPE))
+
+    def align_host_compact(self, packed2_ptr, len_ptr, uniform_len, n, nlist_ptr, n_n, seed_p, chain_p, ext_p, copy=True):
+        """the compact boundary (bwa_b200_align_host_compact): 2-bit reads in (len_ptr None / 0: every read has uniform_len bases), 40-byte region
+        records out, through the aligner's pinned buffers"""
+        nr, a, c = C.c_uint64(0), vp(), vp()
+        check(lib().bwa_b200_align_host_compact(self.h, packed2_ptr, len_ptr or None, uniform_len, n, nlist_ptr or None, n_n, C.byref(seed_p), C.byref(chain_p),
+                                                C.byref(ext_p), C.byref(nr), C.byref(a), C.byref(c)))
+        return dict(n_regions=_view(a, n, np.uint32, copy), regions=_view(c, nr.value, REGION_COMPACT_DTYPE, copy))
 
     def align_seeds_host(self, packed, word_off, read_len, rbeg, qq, score, n_seeds, seed_off, layout_all, chain_p, ext_p, detail=False):
         rbeg = np.ascontiguousarray(rbeg, np.uint64); qq = np.ascontiguousarray(qq, np.int32); score = np.ascontiguousarray(score, np.uint32)

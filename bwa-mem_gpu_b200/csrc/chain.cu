@@ -20,6 +20,7 @@
 #include "chain_core.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <functional>
 #include <vector>
 
 using namespace b200chain;
@@ -145,6 +146,70 @@ finish_kernel(uint32_t n_reads, int pen_clip, const uint32_t *__restrict__ read_
     }
 }
 
+// ---- compact boundary: 2-bit reads -> the 4-bit layout of bwa_b200_pack_codes (padding 4), bases that are not A/C/G/T patched in
+// from a sparse list; regions -> 40-byte records
+__global__ void layout2_kernel(uint32_t n_reads, const uint32_t *len_in, uint32_t uniform_len, uint32_t *len,
+                               uint64_t *__restrict__ w4, uint64_t *__restrict__ w2)
+{ // per-read word counts (slot n_reads = 0, so that the exclusive scans end with the totals)
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    const uint32_t l = r == n_reads ? 0u : (len_in ? len_in[r] : uniform_len);
+    if (r < n_reads) len[r] = l;
+    w4[r] = ((uint64_t)l + 7) >> 3; w2[r] = ((uint64_t)l + 15) >> 4;
+}
+__global__ void layout2_uniform_kernel(uint32_t n_reads, uint32_t uniform_len, uint32_t *__restrict__ len, uint64_t *__restrict__ w4, uint64_t *__restrict__ w2)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_reads) return;
+    if (r < n_reads) len[r] = uniform_len;
+    w4[r] = (uint64_t)r * ((uint64_t)(uniform_len + 7) >> 3); w2[r] = (uint64_t)r * ((uint64_t)(uniform_len + 15) >> 4);
+}
+// one warp per read, one lane per output word: 8 bases = 16 bits of the 2-bit word, each pair of bits spread into a nibble
+__global__ void __launch_bounds__(256)
+expand2_kernel(uint32_t n_reads, const uint32_t *__restrict__ p2, const uint64_t *__restrict__ w2, const uint32_t *__restrict__ len,
+               const uint64_t *__restrict__ w4, uint32_t *__restrict__ p4)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t l = len[r], nw = (l + 7) >> 3;
+        const uint32_t *src = p2 + w2[r];
+        uint32_t *dst = p4 + w4[r];
+        for (uint32_t k = lane; k < nw; k += 32) {
+            uint32_t x = (src[k >> 1] >> (16u * (1u - (k & 1u)))) & 0xffffu;
+            x = (x | (x << 8)) & 0x00ff00ffu;
+            x = (x | (x << 4)) & 0x0f0f0f0fu;
+            x = (x | (x << 2)) & 0x33333333u;
+            const uint32_t valid = l - 8u * k;                     // bases of this word inside the read (>= 1)
+            if (valid < 8u) { const uint32_t pad = 0xffffffffu >> (4u * valid); x = (x & ~pad) | (0x44444444u & pad); }
+            dst[k] = x;
+        }
+    }
+}
+__global__ void npatch_kernel(uint64_t n_n, const uint64_t *__restrict__ list, uint32_t n_reads, const uint32_t *__restrict__ len,
+                              const uint64_t *__restrict__ w4, uint32_t *__restrict__ p4, int *__restrict__ err)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_n) return;
+    const uint32_t r = (uint32_t)(list[k] >> 32), pos = (uint32_t)list[k];
+    if (r >= n_reads || pos >= len[r]) { atomicMax(err, 3); return; }
+    const uint32_t sh = 28u - 4u * (pos & 7u);
+    uint32_t *wd = p4 + w4[r] + (pos >> 3);
+    atomicAnd(wd, ~(0xfu << sh));
+    atomicOr(wd, 4u << sh);
+}
+__global__ void compact_regions_kernel(uint64_t n, const bwa_b200_region_t *__restrict__ in, bwa_b200_region_compact_t *__restrict__ out, int *__restrict__ err)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const bwa_b200_region_t a = in[k];
+    bwa_b200_region_compact_t c;
+    c.rb = a.rb; c.rlen = (int32_t)(a.re - a.rb); c.qb = (uint16_t)a.qb; c.qe = (uint16_t)a.qe;
+    c.score = a.score; c.truesc = a.truesc; c.seedcov = a.seedcov; c.rid = a.rid;
+    c.w = (uint16_t)a.w; c.seedlen0 = (uint16_t)a.seedlen0; c.frac_rep = a.frac_rep;
+    if (a.w < 0 || a.w > 0xffff || a.re - a.rb > 0x7fffffffll || a.re < a.rb) atomicMax(err, 4);
+    out[k] = c;
+}
+
 template <typename T> int grow(T *&p, uint64_t &cap, uint64_t need, uint64_t slack = 0)
 {
     if (need <= cap && p) return BWA_B200_OK;
@@ -174,7 +239,7 @@ struct bwa_b200_aligner {
     Cnt *d_cnt = nullptr, *d_off = nullptr, *d_tot = nullptr, *h_tot = nullptr;
     uint32_t *d_nregs = nullptr, *d_nchains = nullptr; uint64_t *d_region_off = nullptr, *d_chain_off = nullptr, *d_cseed_off = nullptr;
     void *d_cub = nullptr; size_t cub_bytes = 0;
-    int *d_err = nullptr, *h_err = nullptr;          // [0] internal error, [1] reads left to the caller (mem_seed_sw)
+    int *d_err = nullptr, *h_err = nullptr;          // [0] internal error, [1] reads left to the caller (mem_seed_sw), [2] compact boundary
     uint32_t *d_skipped = nullptr;
     std::vector<uint32_t> skipped;                   // their indexes in the last batch, ascending
     // outputs
@@ -197,6 +262,10 @@ struct bwa_b200_aligner {
     // pinned host result buffers of bwa_b200_align_host_view (grown geometrically, reused batch after batch)
     uint32_t *p_nregs = nullptr; uint64_t *p_region_off = nullptr; uint64_t p_reads = 0;
     bwa_b200_region_t *p_regions = nullptr; uint64_t p_region_cap = 0;
+    // compact boundary (bwa_b200_align_host_compact): 2-bit reads in, 40-byte records out
+    uint32_t *d_p2 = nullptr; uint64_t p2_cap = 0; uint64_t *d_woff2 = nullptr; uint64_t *d_nlist = nullptr; uint64_t nlist_cap = 0;
+    bwa_b200_region_compact_t *d_cregions = nullptr; uint64_t creg_cap = 0;
+    bwa_b200_region_compact_t *p_cregions = nullptr; uint64_t p_creg_cap = 0;
 };
 
 extern "C" void bwa_b200_chain_params_default(bwa_b200_chain_params_t *p)
@@ -260,10 +329,15 @@ extern "C" int bwa_b200_aligner_create(const bwa_b200_index_t *idx, uint64_t max
     B200_CUDA(cudaMalloc(&a->d_tot, sizeof(Cnt))); B200_CUDA(cudaHostAlloc(&a->h_tot, sizeof(Cnt), cudaHostAllocDefault));
     B200_CUDA(cudaMalloc(&a->d_nregs, max_reads * 4)); B200_CUDA(cudaMalloc(&a->d_nchains, max_reads * 4));
     B200_CUDA(cudaMalloc(&a->d_region_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_chain_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_cseed_off, max_reads * 8));
-    B200_CUDA(cudaMalloc(&a->d_err, 8)); B200_CUDA(cudaMemset(a->d_err, 0, 8)); B200_CUDA(cudaHostAlloc(&a->h_err, 8, cudaHostAllocDefault));
-    a->h_err[0] = a->h_err[1] = 0;
+    B200_CUDA(cudaMalloc(&a->d_err, 16)); B200_CUDA(cudaMemset(a->d_err, 0, 16)); B200_CUDA(cudaHostAlloc(&a->h_err, 16, cudaHostAllocDefault));
+    a->h_err[0] = a->h_err[1] = a->h_err[2] = a->h_err[3] = 0;
     B200_CUDA(cudaMalloc(&a->d_skipped, (max_reads ? max_reads : 1) * 4));
     B200_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, a->cub_bytes, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)max_reads, a->stream));
+    {   // the compact boundary scans word counts with the same scratch
+        size_t b2 = 0;
+        B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint64_t *)nullptr, (uint64_t *)nullptr, (int)(max_reads + 1), a->stream));
+        a->cub_bytes = std::max(a->cub_bytes, b2);
+    }
     B200_CUDA(cudaMalloc(&a->d_cub, a->cub_bytes + 16));
     if (idx->l_pac < 0x7fffffffull) {           // default: one sequence [0, l_pac)
         const int64_t off0 = 0; const int32_t len0 = (int32_t)idx->l_pac;
@@ -293,6 +367,7 @@ extern "C" void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a)
     cudaFree(a->d_res); cudaFree(a->d_qp); cudaFree(a->d_tp);
     cudaFree(a->g_rbeg); cudaFree(a->g_seed_off); cudaFree(a->g_qq); cudaFree(a->g_score); cudaFree(a->g_nseeds);
     cudaFreeHost(a->p_nregs); cudaFreeHost(a->p_region_off); cudaFreeHost(a->p_regions);
+    cudaFree(a->d_p2); cudaFree(a->d_woff2); cudaFree(a->d_nlist); cudaFree(a->d_cregions); cudaFreeHost(a->p_cregions);
     delete a;
 }
 
@@ -608,6 +683,108 @@ extern "C" int bwa_b200_align_seeds_host(bwa_b200_aligner_t *a, const uint32_t *
     rc = aligner_run(a, S, false, s->d_packed, s->d_woff, s->d_len, n_reads, cp, ep, want_detail != 0);
     if (rc) return rc;
     return aligner_download(a, want_detail, out);
+}
+
+// The compact boundary.  reserve(n_regions) returns where the batch's records go (pinned host memory), or nullptr to refuse.
+int b200_align_compact(bwa_b200_aligner *a, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len, uint64_t n_reads,
+                       const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp, const bwa_b200_chain_params_t *cp,
+                       const bwa_b200_ext_params_t *ep, uint32_t *dst_nregs, uint64_t *n_regions,
+                       const std::function<bwa_b200_region_compact_t *(uint64_t)> &reserve)
+{
+    bwa_b200_seeder *s = a->seeder;
+    if (n_reads > a->max_reads) { b200::set_error("align_compact: %llu reads > capacity", (unsigned long long)n_reads); return BWA_B200_ERR_CAPACITY; }
+    uint64_t tot2 = 0, tot4 = 0;
+    uint32_t max_len = uniform_len;
+    if (read_len) {
+        max_len = 0;
+        for (uint64_t r = 0; r < n_reads; ++r) { const uint32_t l = read_len[r]; tot2 += ((uint64_t)l + 15) >> 4; tot4 += ((uint64_t)l + 7) >> 3; max_len = l > max_len ? l : max_len; }
+    } else { tot2 = n_reads * (((uint64_t)uniform_len + 15) >> 4); tot4 = n_reads * (((uint64_t)uniform_len + 7) >> 3); }
+    if (max_len > 0xffffu) { b200::set_error("align_compact: reads beyond 65535 bases do not fit the compact record; use bwa_b200_align_host_view"); return BWA_B200_ERR_ARG; }
+    if (tot4 > s->max_words) { b200::set_error("align_compact: batch exceeds the aligner's capacity"); return BWA_B200_ERR_CAPACITY; }
+    B200_CUDA(cudaSetDevice(a->device));
+    cudaStream_t st = a->stream;
+    int rc = grow(a->d_p2, a->p2_cap, tot2, tot2 / 8);
+    if (!a->d_woff2) { uint64_t c = 0; rc |= grow(a->d_woff2, c, a->max_reads + 1); }
+    if (n_n) rc |= grow(a->d_nlist, a->nlist_cap, n_n, n_n / 4);
+    if (rc) return BWA_B200_ERR_NOMEM;
+    const uint32_t n = (uint32_t)n_reads;
+    B200_CUDA(cudaMemcpyAsync(a->d_p2, packed2, tot2 * 4, cudaMemcpyHostToDevice, st));
+    if (n_n) B200_CUDA(cudaMemcpyAsync(a->d_nlist, n_list, n_n * 8, cudaMemcpyHostToDevice, st));
+    if (read_len) {
+        // lengths ride in the seeder's own length array; the word counts are scanned in place into both offset arrays
+        B200_CUDA(cudaMemcpyAsync(s->d_len, read_len, n_reads * 4, cudaMemcpyHostToDevice, st));
+        layout2_kernel<<<(n + 256) / 256, 256, 0, st>>>(n, s->d_len, 0, s->d_len, s->d_woff, a->d_woff2);
+        size_t tmp = a->cub_bytes;
+        B200_CUDA(cub::DeviceScan::ExclusiveSum(a->d_cub, tmp, s->d_woff, s->d_woff, (int)(n + 1), st));
+        tmp = a->cub_bytes;
+        B200_CUDA(cub::DeviceScan::ExclusiveSum(a->d_cub, tmp, a->d_woff2, a->d_woff2, (int)(n + 1), st));
+        a->launches += 3;
+    } else {
+        layout2_uniform_kernel<<<(n + 256) / 256, 256, 0, st>>>(n, uniform_len, s->d_len, s->d_woff, a->d_woff2);
+        a->launches += 1;
+    }
+    {
+        const uint64_t warps = n_reads < (uint64_t)s->n_sm * 64 ? n_reads : (uint64_t)s->n_sm * 64;
+        expand2_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(n, a->d_p2, a->d_woff2, s->d_len, s->d_woff, s->d_packed);
+        a->launches += 1;
+    }
+    int *d_err2 = a->d_err + 2;
+    B200_CUDA(cudaMemsetAsync(d_err2, 0, 4, st));
+    if (n_n) { npatch_kernel<<<(unsigned)((n_n + 255) / 256), 256, 0, st>>>(n_n, a->d_nlist, n, s->d_len, s->d_woff, s->d_packed, d_err2); a->launches += 1; }
+    B200_CUDA(cudaGetLastError());
+    rc = bwa_b200_align_device(a, s->d_packed, s->d_woff, s->d_len, n_reads, max_len, sp, cp, ep);
+    if (rc) return rc;
+    const uint64_t nr = a->b_tot.regs;
+    rc = grow(a->d_cregions, a->creg_cap, nr, nr / 8);
+    if (rc) return rc;
+    if (nr) { compact_regions_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(nr, a->d_regions, a->d_cregions, d_err2); a->launches += 1; }
+    bwa_b200_region_compact_t *dst = reserve(nr);
+    if (!dst && nr) { b200::set_error("align_compact: no room for %llu region records", (unsigned long long)nr); return BWA_B200_ERR_CAPACITY; }
+    B200_CUDA(cudaMemcpyAsync(dst_nregs, a->d_nregs, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    if (nr) B200_CUDA(cudaMemcpyAsync(dst, a->d_cregions, nr * sizeof(bwa_b200_region_compact_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(a->h_err + 2, d_err2, 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (a->h_err[2]) {
+        const int e = a->h_err[2]; a->h_err[2] = 0;
+        b200::set_error(e == 3 ? "align_compact: an entry of the N list names a read or a position outside the batch" : "align_compact: a region does not fit the compact record (band beyond 65535)");
+        return BWA_B200_ERR_ARG;
+    }
+    *n_regions = nr;
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_align_host_compact(bwa_b200_aligner_t *a, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len,
+                                           uint64_t n_reads, const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp,
+                                           const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep, uint64_t *n_regions,
+                                           const uint32_t **n_regions_per_read, const bwa_b200_region_compact_t **regions)
+{
+    if (!a || !sp || !cp || !ep || !n_regions || !n_regions_per_read || !regions || (n_reads && !packed2) || (n_n && !n_list)) {
+        b200::set_error("align_host_compact: bad argument"); return BWA_B200_ERR_ARG;
+    }
+    *n_regions = 0; *n_regions_per_read = nullptr; *regions = nullptr;
+    if (n_reads == 0) return BWA_B200_OK;
+    B200_CUDA(cudaSetDevice(a->device));
+    if (n_reads > a->p_reads) {
+        cudaFreeHost(a->p_nregs); cudaFreeHost(a->p_region_off); a->p_nregs = nullptr; a->p_region_off = nullptr; a->p_reads = 0;
+        const uint64_t c = std::max<uint64_t>(n_reads, a->max_reads);
+        B200_CUDA(cudaHostAlloc(&a->p_nregs, c * 4, cudaHostAllocDefault));
+        B200_CUDA(cudaHostAlloc(&a->p_region_off, c * 8, cudaHostAllocDefault));
+        a->p_reads = c;
+    }
+    bool alloc_failed = false;
+    auto reserve = [&](uint64_t nr) -> bwa_b200_region_compact_t * {
+        if (nr > a->p_creg_cap) {
+            cudaFreeHost(a->p_cregions); a->p_cregions = nullptr; a->p_creg_cap = 0;
+            const uint64_t c = nr + nr / 4 + 1024;
+            if (cudaHostAlloc(&a->p_cregions, c * sizeof(bwa_b200_region_compact_t), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); alloc_failed = true; return nullptr; }
+            a->p_creg_cap = c;
+        }
+        return a->p_cregions;
+    };
+    const int rc = b200_align_compact(a, packed2, read_len, uniform_len, n_reads, n_list, n_n, sp, cp, ep, a->p_nregs, n_regions, reserve);
+    if (rc) return alloc_failed ? BWA_B200_ERR_NOMEM : rc;
+    *n_regions_per_read = a->p_nregs; *regions = a->p_cregions;
+    return BWA_B200_OK;
 }
 
 extern "C" void *bwa_b200_aligner_stream(bwa_b200_aligner_t *a) { return a ? (void *)a->stream : nullptr; }

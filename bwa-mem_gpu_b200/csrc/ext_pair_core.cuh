@@ -13,11 +13,27 @@
 // excluded from the row maximum), so the state of a cell outside the window is never changed
 // (src/ksw.c:909-970 semantics are kept exactly; nothing is speculated).
 //
-// Per-lane state (lane stride NT elements, conflict-free):
-//   HE[p] = uint2 { H(i-1, 2p-1) | H(i-1, 2p) << 16 ,  E(i, 2p) | E(i, 2p+1) << 16 }     p = 0 .. qlen/2
+// Instruction budget of a column pair.  Measured on the B200 (bwa_b200_measure_int_alu): the ALU pipe (PRMT, VIADDMNMX,
+// VIMNMX3) and the FMA pipe (IMAD) each issue 0.5 warp instructions per clock per SMSP, both together 0.68, IMAD.HI
+// half of IMAD -- so the kernel is bound by the instructions it issues, whatever their pipe:
+//   ALU: PRMT (score lookup), VIADDMNMX (M), VIADDMNMX.RELU (gap open, once when the insertion and deletion
+//        penalties are equal), 2 x VIADDMNMX + PRMT (F chain and its two halves), VIMNMX3 (h), VIADDMNMX (E),
+//        PRMT (H(i, j-1) realigned for the stored diagonal), half a VIMNMX3.U16x2 (row maximum of two pairs)  = 9.5
+//   FMA: H * 32 (zero test of the diagonal), t << 16, key = h * 64 + index
+//   LSU: LDS.64 {H, E}, LDS.U16 selectors, STS.64
+//
+// Per-lane state (lane stride NT elements, conflict-free), SLOT = pair index, or pair index modulo the ring size:
+//   HE[s] = uint2 { H(i-1, 2p-1) | H(i-1, 2p) << 16 ,  E(i, 2p) | E(i, 2p+1) << 16 }
 //           i.e. the reference's eh[j] = {H(i-1,j-1), E(i,j)} for j = 2p (low halves) and 2p+1 (high halves)
-//   QS[g] = PRMT selectors of query columns 4g .. 4g+3, one byte each: code * 17 + 0x80
+//   QS[s] = the two PRMT selector bytes of the pair, one per column: code * 17 + 0x80
 //           (low nibble picks the score byte, high nibble replicates its sign into the upper byte)
+//
+// Band-sized state (RING): with a band, row i only touches columns [i - w, i + w + 1] (src/ksw.c:902-907, and
+// eh[end] at :940), and beg never decreases, so a column left of i - w is never read again.  The state is then a
+// ring of R >= w + 2 pairs instead of qlen / 2 + 1.  A column that enters the band for the first time must read what
+// the reference's untouched eh[] holds there -- the first-row initialisation (src/ksw.c:880-883) -- so the pair that
+// enters at row i is (re)initialised in closed form before the row is evaluated; columns that were inside, fell
+// out of [beg, end) and come back keep their stale values, because they never left the ring.
 #pragma once
 #include <stdint.h>
 #include "bwamem_b200.h"
@@ -30,6 +46,13 @@ __device__ __forceinline__ uint32_t b200_prmt(uint32_t a, uint32_t b, uint32_t c
 {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// a * b + c as IMAD (the FMA pipe; callers pass multipliers the compiler cannot see through)
+__device__ __forceinline__ uint32_t b200_mad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 #else
@@ -54,10 +77,13 @@ struct PairParams {
     uint32_t tab[5];             // tab[t]: score bytes against query codes 0..3 for target base t (t = 4: N)
     uint32_t tab_n;              // byte 0: score against query code 4 (N)
     uint32_t noe_del2, ne_del2, noe_ins2, ne_ins2;   // negative penalties in both halves
+    int32_t  ring;               // pairs in the state ring; 0 = one slot per pair of the longest query (no ring)
+    uint32_t ring_magic;         // ceil(2^20 / ring): p / ring == (p * ring_magic) >> 20 for every pair index of the class
 };
 
-constexpr int PAIR_MAX_SCORE = 1023;   // H * 32 must stay below 2^15 (zero test of the diagonal, see PAIR_STEP)
-constexpr int PAIR_KEYED_MAX_Q = 128;  // (score, column pair) fits one 16-bit key: score < 2^10, pair index < 2^6
+constexpr int PAIR_MAX_SCORE = 1023;   // H * 32 must stay below 2^15 (zero test of the diagonal, see PAIR_CORE)
+constexpr int PAIR_MAX_Q = 512;        // longest query of the class
+constexpr int PAIR_CHUNK = 64;         // (score, pair index within the chunk) is one 16-bit key: score < 2^10, index < 2^6
 
 // Fill the per-batch constants; returns 0 when the matrix / penalties are not eligible (any matrix whose
 // entries fit a signed byte with 0 < max <= 31 is; penalties must fit 16 bits with room to spare).
@@ -77,7 +103,18 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
     S->tab_n = (uint32_t)(uint8_t)p->mat[4];
     S->noe_del2 = (uint32_t)(uint16_t)(int16_t)(-oe_del) * 0x00010001u; S->ne_del2 = (uint32_t)(uint16_t)(int16_t)(-p->e_del) * 0x00010001u;
     S->noe_ins2 = (uint32_t)(uint16_t)(int16_t)(-oe_ins) * 0x00010001u; S->ne_ins2 = (uint32_t)(uint16_t)(int16_t)(-p->e_ins) * 0x00010001u;
+    S->ring = 0; S->ring_magic = 0;
     return ok;
+}
+static inline bool pair_same_gap(const bwa_b200_ext_params_t *p) { return p->o_del == p->o_ins && p->e_del == p->e_ins; }
+// state slots per lane for queries up to max_q: the ring when the band makes it smaller
+static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairParams *S)
+{
+    const int full = max_q / 2 + 1;
+    int ring = 0;
+    if (p->use_band && p->w >= 0 && p->w + 2 < full) ring = p->w + 2;
+    if (S) { S->ring = ring; S->ring_magic = ring ? (uint32_t)(((1 << 20) + ring - 1) / ring) : 0u; }
+    return ring ? ring : full;
 }
 
 // One column pair (2p, 2p+1) of row i.  SEL: low 16 bits = the two PRMT selector bytes of the pair.
@@ -86,34 +123,23 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
 //                                                        which every later use treats like 0; Hd > 0 gives Hd + score
 //   c    : chain register, HIGH half = F(i,2p); Fh.hi = F(i,2p+1); new c.hi = F(i,2p+2)
 //   max(x - pen, 0) is the RELU form of VIADDMNMX with the (negative) penalty as its own third operand
-//   key  = h * 64 + p (KEYED): unsigned max keeps the LAST column among equal maxima (src/ksw.c:928);
-//          pp = {p0, p0} for the loop iteration's first pair, KOFF the pair's offset from it
 #define PAIR_CORE(HE, SEL)                                                                       \
         const uint32_t S_ = b200_prmt(tlo, tab_n, (SEL));                                        \
         const uint32_t M_ = __viaddmin_s16x2((HE).x, S_, (HE).x * 32u);                          \
         const uint32_t t2_ = __viaddmax_s16x2_relu(M_, noe_ins2, noe_ins2);                      \
+        const uint32_t t1_ = SAME_GAP ? t2_ : __viaddmax_s16x2_relu(M_, noe_del2, noe_del2);     \
         const uint32_t Fh_ = __viaddmax_s16x2(c, ne_ins2, t2_ << 16);                            \
         const uint32_t F_ = __byte_perm(c, Fh_, 0x7632);                                         \
         c = __viaddmax_s16x2(Fh_, ne_ins2, t2_);                                                 \
         const uint32_t h_ = __vimax3_s16x2(M_, (HE).y, F_);                                      \
-        const uint32_t t1_ = __viaddmax_s16x2_relu(M_, noe_del2, noe_del2);                      \
         const uint32_t En_ = __viaddmax_s16x2((HE).y, ne_del2, t1_);
 
-#define PAIR_MAX(HK, PIDX, KOFF)                                                                 \
-        if (KEYED) m2 = (KOFF) ? __viaddmax_u16x2((HK) * 64u + pp, (KOFF), m2) : __vmaxu2(m2, (HK) * 64u + pp); \
-        else {                                                                                   \
-            bool pH_, pL_;                                                                       \
-            m2 = __vibmax_s16x2((HK), m2, &pH_, &pL_);                                           \
-            pjL = pL_ ? (PIDX) : pjL;                                                            \
-            pjH = pH_ ? (PIDX) : pjH;                                                            \
-        }
-
-// a pair wholly inside the window
-#define PAIR_STEP(HP, PIDX, SEL, KOFF)                                                           \
+// a pair wholly inside the window: HEV = its loaded state, KEY receives h * 64 + PPK (PPK = the pair's index within the
+// chunk, in both halves -- or a literal offset, added to the index later); the store leaves {H(i, 2p-1) | H(i, 2p) << 16, E(i+1, .)} = what the next row reads
+#define PAIR_STEP(HP, HEV, SEL, PPK, KEY)                                                        \
     {                                                                                            \
-        const uint2 he_ = *(HP);                                                                 \
-        PAIR_CORE(he_, SEL)                                                                      \
-        PAIR_MAX(h_, PIDX, KOFF)                                                                 \
+        PAIR_CORE(HEV, SEL)                                                                      \
+        KEY = h_ * k64 + (PPK);                                                                  \
         uint2 o_;                                                                                \
         o_.y = En_;                                                                              \
         o_.x = __byte_perm(hprev, h_, 0x5432);                                                   \
@@ -124,8 +150,8 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
 // the first / last pair of the window.  LO_OUT: the low column (beg - 1) lies outside: its inputs are zeroed, which
 // makes its H, F and gap-open terms 0 = the reference's initial h1 and f of the row, and its stored state is kept.
 // HI_OUT: the high column (end) lies outside: it is computed and discarded, except that eh[end] = {H(i,end-1), 0}
-// (src/ksw.c:940) is exactly what the pair store leaves there.
-#define PAIR_STEP_EDGE(HP, PIDX, SEL, LO_OUT, HI_OUT)                                            \
+// (src/ksw.c:940) is exactly what the pair store leaves there.  OUT receives what was stored.
+#define PAIR_STEP_EDGE(HP, SEL, PPK, LO_OUT, HI_OUT, OUT)                                        \
     {                                                                                            \
         const uint2 old_ = *(HP);                                                                \
         const uint32_t inm_ = (LO_OUT) ? 0xffff0000u : 0xffffffffu;                              \
@@ -135,54 +161,28 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
         if (LO_OUT) hprev = old_.x << 16;                                                        \
         PAIR_CORE(he_, SEL)                                                                      \
         const uint32_t hk_ = (HI_OUT) ? (h_ & 0x0000ffffu) : h_;                                 \
-        PAIR_MAX(hk_, PIDX, 0u)                                                                  \
-        uint2 o_;                                                                                \
-        o_.y = (En_ & outm_) | (old_.y & ~inm_);                                                 \
-        o_.x = __byte_perm(hprev, h_, 0x5432);                                                   \
-        *(HP) = o_;                                                                              \
+        m2 = __vmaxu2(m2, hk_ * 64u + (PPK));                                                    \
+        (OUT).y = (En_ & outm_) | (old_.y & ~inm_);                                              \
+        (OUT).x = __byte_perm(hprev, h_, 0x5432);                                                \
+        *(HP) = (OUT);                                                                           \
         hprev = h_;                                                                              \
     }
 
-// One job.  HEp / QSp are this lane's element 0 of the [index][lane] arrays.
-template <bool BYTES, int NT, bool KEYED>
-B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J, uint32_t a, int qlen, int tlen, int h0,
-                       uint2 *const HEp, uint32_t *const QSp, bwa_b200_ext_result_t &r, unsigned long long &my_cells)
+// One job.  HEp / QSp are this lane's element 0 of the [slot][lane] arrays; tab = S.tab in memory that can be indexed.
+// RING: the state is a ring of S.ring pairs (see the header); CHUNKED: a row may hold more than PAIR_CHUNK pairs, so the row
+// maximum is folded chunk by chunk; U: pairs per trip of the longest unrolled loop (4 or 8).
+template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U>
+B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *const tab, const JobView &J, uint32_t a, int qlen, int tlen, int h0,
+                       uint2 *const HEp, uint16_t *const QSp, bwa_b200_ext_result_t &r, unsigned long long &my_cells)
 {
     const uint32_t qo = J.qoff[a], to = J.toff[a];
     const int oe_ins = P.o_ins + P.e_ins;
+    const int R = RING ? S.ring : 0;
+    const uint32_t rmagic = S.ring_magic;
     uint16_t *const hw = reinterpret_cast<uint16_t *>(HEp);
-#define H16(j) hw[((j) >> 1) * (NT * 4) + ((j) & 1)]
-#define E16(j) hw[((j) >> 1) * (NT * 4) + 2 + ((j) & 1)]
-    const uint16_t *const qs16 = reinterpret_cast<const uint16_t *>(QSp);   // selector pair of column pair p: qs16[(p >> 1) * (NT * 2) + (p & 1)]
-    // stage the query as PRMT selector bytes, four columns per word, through column qlen (columns >= qlen: N)
-    for (int j8 = 0; j8 <= qlen; j8 += 8) {
-        uint32_t wv = 0;
-        if (!BYTES && j8 < qlen) wv = J.qp[(qo + j8) >> 3];
-        uint32_t s0 = 0, s1 = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            uint32_t cde = 4u;
-            if (j8 + u < qlen) { cde = BYTES ? (uint32_t)J.qb[qo + j8 + u] : (wv >> (28 - 4 * u)) & 15u; cde = cde > 4u ? 4u : cde; }
-            const uint32_t sb = cde * 17u + 0x80u;
-            if (u < 4) s0 |= sb << (8 * u); else s1 |= sb << (8 * (u - 4));
-        }
-        QSp[(j8 >> 2) * NT] = s0;
-        if (j8 + 4 <= qlen) QSp[((j8 >> 2) + 1) * NT] = s1;
-    }
-    // first row: H(-1,-1) = h0, then one gap open, then extensions (src/ksw.c:880-883); E = 0
-    {
-        int v = h0 > oe_ins ? h0 - oe_ins : 0;       // eh[1].h
-        uint32_t lo = (uint32_t)h0;
-        for (int p = 0; 2 * p <= qlen; ++p) {
-            uint2 o;
-            o.x = lo | (uint32_t)v << 16;            // eh[2p].h, eh[2p+1].h
-            o.y = 0u;
-            HEp[p * NT] = o;
-            v = v > P.e_ins ? v - P.e_ins : 0;
-            lo = (uint32_t)v;                        // eh[2p+2].h
-            v = v > P.e_ins ? v - P.e_ins : 0;
-        }
-    }
+#define SLOT(p) (RING ? (int)((uint32_t)(p) - (((uint32_t)(p) * rmagic) >> 20) * (uint32_t)R) : (int)(p))
+#define H16(j) hw[SLOT((j) >> 1) * (NT * 4) + ((j) & 1)]
+#define E16(j) hw[SLOT((j) >> 1) * (NT * 4) + 2 + ((j) & 1)]
     // band clamp (src/ksw.c:885-893)
     int w = P.w;
     {
@@ -193,19 +193,56 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
         max_del = max_del > 1 ? max_del : 1;
         w = w < max_del ? w : max_del;
     }
+    // Staging of pair p: the query as two PRMT selector bytes (columns >= qlen: N), and the first row of eh[]:
+    // H(-1,-1) = h0, then one gap open, then extensions, clipped at 0 (src/ksw.c:880-883); E = 0
+    uint32_t qword = 0;
+    int qword_g = -1;                                       // packed query word held in qword
+    auto stage = [&](int p) {
+        uint32_t c0 = 4u, c1 = 4u;
+        const int j0 = 2 * p;
+        if (BYTES) {
+            if (j0 < qlen) c0 = J.qb[qo + j0];
+            if (j0 + 1 < qlen) c1 = J.qb[qo + j0 + 1];
+        } else if (j0 < qlen) {
+            if ((j0 >> 3) != qword_g) { qword_g = j0 >> 3; qword = J.qp[(qo >> 3) + qword_g]; }
+            c0 = (qword >> (28 - 4 * (j0 & 7))) & 15u;
+            if (j0 + 1 < qlen) c1 = (qword >> (24 - 4 * (j0 & 7))) & 15u;
+        }
+        c0 = c0 > 4u ? 4u : c0; c1 = c1 > 4u ? 4u : c1;
+        const int s = SLOT(p);
+        QSp[s * NT] = (uint16_t)((c0 * 17u + 0x80u) | (c1 * 17u + 0x80u) << 8);
+        int v0 = j0 == 0 ? h0 : h0 - oe_ins - (j0 - 1) * P.e_ins;
+        int v1 = h0 - oe_ins - j0 * P.e_ins;
+        v0 = v0 > 0 ? v0 : 0; v1 = v1 > 0 ? v1 : 0;
+        uint2 o;
+        o.x = (uint32_t)v0 | (uint32_t)v1 << 16;
+        o.y = 0u;
+        HEp[s * NT] = o;
+    };
+    const int p_last = qlen >> 1;                           // pair of column qlen (eh[qlen] is written, never evaluated)
+    int pinit = 0;                                          // pairs [0, pinit) are staged
+    {
+        const int first = RING ? ((w + 1) >> 1) : p_last;   // row 0 reaches column min(qlen, w + 1)
+        const int upto = first < p_last ? first : p_last;
+        for (; pinit <= upto; ++pinit) stage(pinit);
+    }
     int best = h0, best_i = -1, best_j = -1, best_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen;
-    uint32_t tword = 0;
+    uint32_t tword = 0, cells = 0;
     // per-batch constants, made to depend on a run-time zero so that they stay in registers (ptxas otherwise
-    // re-reads the kernel parameter bank inside the column loop)
+    // re-reads the kernel parameter bank inside the column loop) and so that IMAD stays IMAD
     const uint32_t rz = (uint32_t)tlen >> 31;
     const uint32_t tab_n = S.tab_n + rz, noe_del2 = S.noe_del2 + rz, ne_del2 = S.ne_del2 + rz, noe_ins2 = S.noe_ins2 + rz, ne_ins2 = S.ne_ins2 + rz;
+    const uint32_t k64 = 64u + rz;
+    (void)noe_del2;
+    int h1_edge = h0 - P.o_del;                             // h0 - (o_del + e_del * (i + 1)), the first column of row i while beg == 0
     for (int i = 0; i < tlen; ++i) {
         int tbv;
         if (BYTES) tbv = J.tb[to + i];
         else {
             if ((i & 7) == 0) tword = J.tp[(to + i) >> 3];
-            tbv = (int)((tword >> (28 - 4 * (i & 7))) & 15u);
+            tbv = (int)(tword >> 28);
+            tword <<= 4;
         }
         tbv = tbv > 4 ? 4 : tbv;
         if (P.use_band) {
@@ -213,49 +250,105 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
             if (end > i + w + 1) end = i + w + 1;
             if (end > qlen) end = qlen;
         }
-        const uint32_t tlo = tbv == 0 ? S.tab[0] : (tbv == 1 ? S.tab[1] : (tbv == 2 ? S.tab[2] : (tbv == 3 ? S.tab[3] : S.tab[4])));
+        if (RING) {                                         // the pair that enters the band at this row (see the header)
+            int need = (i + w + 1) >> 1;
+            need = need < p_last ? need : p_last;
+            for (; pinit <= need; ++pinit) stage(pinit);
+        }
+        const uint32_t tlo = tab[tbv];                    // row of the matrix (shared memory on the device: one broadcast load)
+        h1_edge -= P.e_del;
         int h1 = 0, m = 0, mj = -1;
-        if (beg == 0) { h1 = h0 - (P.o_del + P.e_del * (i + 1)); h1 = h1 < 0 ? 0 : h1; }
+        if (beg == 0) h1 = h1_edge < 0 ? 0 : h1_edge;
+        bool beg_live = false;                              // eh[beg] is known to be non-zero after the row
         if (beg < end) {
             const int p0 = beg >> 1, p1 = (end - 1) >> 1;          // first and last column pair of the window
             const bool lo_out = (beg & 1) != 0, hi_out = (end & 1) != 0;
             uint32_t hprev = (uint32_t)h1 << 16, c = 0u, m2 = 0u;   // c.hi = F(i, beg) = 0
-            uint32_t pp = (uint32_t)p0 * 0x00010001u;
-            int pjL = p0, pjH = p0;
-            uint2 *hp = HEp + p0 * NT;
-            const uint16_t *qp = qs16 + (p0 >> 1) * (NT * 2) + (p0 & 1);
-            PAIR_STEP_EDGE(hp, p0, (uint32_t)*qp, lo_out, hi_out && p0 == p1)
-            int p = p0 + 1;
-            pp += 0x00010001u; hp += NT; qp += (p0 & 1) ? (NT * 2 - 1) : 1;
-            for (; p + 4 <= p1; p += 4, pp += 0x00040004u, hp += 4 * NT, qp += 2 * (NT * 2)) {
-                const int o1 = (p & 1) ? (NT * 2 - 1) : 1;          // selectors of pairs p .. p+3 (two per word, words NT apart)
-                const uint32_t s0 = qp[0], s1 = qp[o1], s2 = qp[NT * 2], s3 = qp[NT * 2 + o1];
-                PAIR_STEP(hp, p, s0, 0u)
-                PAIR_STEP(hp + NT, p + 1, s1, 0x00010001u)
-                PAIR_STEP(hp + 2 * NT, p + 2, s2, 0x00020002u)
-                PAIR_STEP(hp + 3 * NT, p + 3, s3, 0x00030003u)
-            }
-            for (; p < p1; ++p, pp += 0x00010001u, hp += NT) {
-                const uint32_t s0 = *qp;
-                qp += (p & 1) ? (NT * 2 - 1) : 1;
-                PAIR_STEP(hp, p, s0, 0u)
-            }
-            if (p1 > p0) { PAIR_STEP_EDGE(hp, p1, (uint32_t)*qp, false, hi_out) }
-            h1 = hi_out ? (int)(hprev & 0xffffu) : (int)(hprev >> 16);
-            // row maximum; among equal maxima the last column wins (src/ksw.c:928)
-            int sL, cL, sH, cH;
-            if (KEYED) {
+            const int s0 = SLOT(p0);
+            uint2 *hp = HEp + s0 * NT;
+            const uint16_t *qp = QSp + s0 * NT;
+            int pw = RING ? p0 - s0 + R : 0x7fffffff;               // first pair at or after p0 that sits in slot 0
+            int pbase = p0, climit = CHUNKED ? p0 + PAIR_CHUNK : 0x7fffffff;     // the chunk of the row maximum's keys
+            uint32_t pp = 0u;                                       // (p - pbase) in both halves
+            auto fold = [&]() {                                     // (m, mj) <- chunk maximum; the later column wins ties (src/ksw.c:928)
                 const uint32_t kl = m2 & 0xffffu, kh = m2 >> 16;
-                sL = (int)(kl >> 6); cL = (int)(kl & 63u) * 2; sH = (int)(kh >> 6); cH = (int)(kh & 63u) * 2 + 1;
-            } else {
-                sL = (int)(m2 & 0xffffu); cL = pjL * 2; sH = (int)(m2 >> 16); cH = pjH * 2 + 1;
+                const int sL = (int)(kl >> 6), cL = (pbase + (int)(kl & 63u)) * 2, sH = (int)(kh >> 6), cH = (pbase + (int)(kh & 63u)) * 2 + 1;
+                const bool hi_wins = sH > sL || (sH == sL && cH > cL);
+                const int cs = hi_wins ? sH : sL, cc = hi_wins ? cH : cL;
+                if (!CHUNKED || cs >= m) { m = cs; mj = cc; }
+            };
+            uint2 o0;
+            PAIR_STEP_EDGE(hp, (uint32_t)*qp, pp, lo_out, hi_out && p0 == p1, o0)
+            beg_live = lo_out ? ((o0.x | o0.y) >> 16) != 0u : ((o0.x | o0.y) & 0xffffu) != 0u;
+            int p = p0 + 1;
+            pp += 0x00010001u; hp += NT; qp += NT;
+            if (RING && p == pw) { hp -= R * NT; qp -= R * NT; pw += R; }
+            while (p < p1) {
+                int stop = p1;
+                if (RING) stop = stop < pw ? stop : pw;
+                if (CHUNKED) stop = stop < climit ? stop : climit;
+                // unrolled trips of 8, then 4 pairs: keys carry the pair's offset within the trip as a literal; the trip's maximum
+                // gets the trip's index (pp) added inside the VIADDMNMX that merges it into the row maximum.  Eight pairs per trip
+                // measured 12 % faster than four on the bins whose shared-memory state leaves ten warps per SM (more independent
+                // work between dependent instructions); sixteen measured slower again.
+                if (U == 8 && p + 8 <= stop) {
+                    const int n8 = (stop - p) >> 3;
+                    uint2 *const hp_end = hp + n8 * (8 * NT);
+                    p += n8 * 8;
+                    do {
+                        const uint2 e0 = hp[0], e1 = hp[NT], e2 = hp[2 * NT], e3 = hp[3 * NT], e4 = hp[4 * NT], e5 = hp[5 * NT], e6 = hp[6 * NT], e7 = hp[7 * NT];
+                        const uint32_t s0_ = qp[0], s1_ = qp[NT], s2_ = qp[2 * NT], s3_ = qp[3 * NT], s4_ = qp[4 * NT], s5_ = qp[5 * NT], s6_ = qp[6 * NT], s7_ = qp[7 * NT];
+                        uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
+                        PAIR_STEP(hp, e0, s0_, 0u, k0)
+                        PAIR_STEP(hp + NT, e1, s1_, 0x00010001u, k1)
+                        PAIR_STEP(hp + 2 * NT, e2, s2_, 0x00020002u, k2)
+                        PAIR_STEP(hp + 3 * NT, e3, s3_, 0x00030003u, k3)
+                        PAIR_STEP(hp + 4 * NT, e4, s4_, 0x00040004u, k4)
+                        PAIR_STEP(hp + 5 * NT, e5, s5_, 0x00050005u, k5)
+                        PAIR_STEP(hp + 6 * NT, e6, s6_, 0x00060006u, k6)
+                        PAIR_STEP(hp + 7 * NT, e7, s7_, 0x00070007u, k7)
+                        k0 = __vimax3_u16x2(k0, k1, k2);
+                        k3 = __vimax3_u16x2(k3, k4, k5);
+                        k0 = __vimax3_u16x2(k0, k3, k6);
+                        k0 = __vmaxu2(k0, k7);
+                        m2 = __viaddmax_u16x2(k0, pp, m2);
+                        pp += 0x00080008u; hp += 8 * NT; qp += 8 * NT;
+                    } while (hp != hp_end);
+                }
+                if (p + 4 <= stop) {
+                    const int n4 = (stop - p) >> 2;
+                    uint2 *const hp_end = hp + n4 * (4 * NT);
+                    p += n4 * 4;
+                    do {
+                        const uint2 e0 = hp[0], e1 = hp[NT], e2 = hp[2 * NT], e3 = hp[3 * NT];
+                        const uint32_t s0_ = qp[0], s1_ = qp[NT], s2_ = qp[2 * NT], s3_ = qp[3 * NT];
+                        uint32_t k0, k1, k2, k3;
+                        PAIR_STEP(hp, e0, s0_, 0u, k0)
+                        PAIR_STEP(hp + NT, e1, s1_, 0x00010001u, k1)
+                        PAIR_STEP(hp + 2 * NT, e2, s2_, 0x00020002u, k2)
+                        PAIR_STEP(hp + 3 * NT, e3, s3_, 0x00030003u, k3)
+                        k0 = __vimax3_u16x2(k0, k1, k2);
+                        k0 = __vmaxu2(k0, k3);
+                        m2 = __viaddmax_u16x2(k0, pp, m2);
+                        pp += 0x00040004u; hp += 4 * NT; qp += 4 * NT;
+                    } while (hp != hp_end);
+                }
+                for (; p < stop; ++p, pp += 0x00010001u, hp += NT, qp += NT) {
+                    const uint2 e0 = hp[0];
+                    uint32_t k0;
+                    PAIR_STEP(hp, e0, (uint32_t)*qp, pp, k0)
+                    m2 = __vmaxu2(m2, k0);
+                }
+                if (RING && p == pw) { hp -= R * NT; qp -= R * NT; pw += R; }
+                if (CHUNKED && p == climit) { fold(); m2 = 0u; pp = 0u; pbase = p; climit += PAIR_CHUNK; }
             }
-            const bool hi_wins = sH > sL || (sH == sL && cH > cL);
-            m = hi_wins ? sH : sL; mj = hi_wins ? cH : cL;
+            if (p1 > p0) { uint2 o1; PAIR_STEP_EDGE(hp, (uint32_t)*qp, pp, false, hi_out, o1) (void)o1; }
+            h1 = hi_out ? (int)(hprev & 0xffffu) : (int)(hprev >> 16);
+            fold();
+            cells += (uint32_t)(end - beg);
         }
         // ---- row i is complete (src/ksw.c:940-959)
         H16(end) = (uint16_t)h1; E16(end) = 0;           // eh[end] = {h1, 0}
-        my_cells += (unsigned long long)(end > beg ? end - beg : 0);
         if ((beg < end ? end : beg) == qlen) {
             best_ie = gscore > h1 ? best_ie : i;
             gscore = gscore > h1 ? gscore : h1;
@@ -270,15 +363,23 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const JobView &J
             if (di > dj) { if (best - m - (di - dj) * P.e_del > P.zdrop) break; }
             else         { if (best - m - (dj - di) * P.e_ins > P.zdrop) break; }
         }
-        // window of the next row (src/ksw.c:965-970)
-        int j = beg;
-        while (j < end && H16(j) == 0 && E16(j) == 0) ++j;
-        beg = j;
-        j = end;
-        while (j >= beg && H16(j) == 0 && E16(j) == 0) --j;
+        // window of the next row (src/ksw.c:965-970); the common answers are already in registers: eh[beg] as stored by
+        // the first pair, and eh[end] = {h1, 0}
+        if (!beg_live) {
+            int j = beg;
+            while (j < end && H16(j) == 0 && E16(j) == 0) ++j;
+            beg = j;
+        }
+        int j = end;
+        if (h1 == 0) {
+            --j;
+            while (j >= beg && H16(j) == 0 && E16(j) == 0) --j;
+        }
         end = j + 2 < qlen ? j + 2 : qlen;
     }
 #undef H16
 #undef E16
+#undef SLOT
+    my_cells += cells;
     r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = best_ie + 1; r.gscore = gscore; r.max_off = max_off;
 }

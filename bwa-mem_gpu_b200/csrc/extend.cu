@@ -12,8 +12,9 @@
 //                      carries from column to column, so a column pair costs ~11 packed ALU
 //                      instructions (VIADDMNMX / VIMNMX3 / PRMT) instead of ~2 x 15 scalar ones.
 //                      State {H(i-1,j-1), E(i,j)} of a column pair is one uint2 in shared memory,
-//                      laid out [pair][lane].  Takes every job whose score bound h0 + qlen * max(mat)
-//                      is at most 1023 and whose query is at most 512 bases.
+//                      laid out [slot][lane]; with a band the slots are a ring of w + 2 pairs (the state is
+//                      sized by the band, not by the query).  Takes every job whose score bound
+//                      h0 + qlen * max(mat) is at most 1023 and whose query is at most 512 bases.
 //   ext_inter_kernel   one job per lane, one column per step in 32-bit arithmetic: the general
 //                      fallback (scores up to 2^15, queries up to 1024, any matrix).  The per-column
 //                      state lives in shared memory as one 32-bit word per column, [column][lane];
@@ -41,10 +42,8 @@ namespace {
 constexpr int N_BINS = 7;
 __constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
 
-constexpr int N_PBINS = 16;              // bins of the column-pair kernel; the first N_KEYED use the 16-bit (score, pair) key
-constexpr int N_KEYED = 8;
+constexpr int N_PBINS = 16;              // bins of the column-pair kernel (PAIR_MAX_Q = the last one)
 __constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512};
-constexpr int PAIR_MAX_Q = 512;          // longest query the column-pair kernel stages (shared memory)
 constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
 constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
 
@@ -396,17 +395,20 @@ ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     if (lane == 0 && my_cells) atomicAdd(cells_total, my_cells);
 }
 
-// ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh)
-template <bool BYTES, bool KEYED, int NT>
+// ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh); n_slots = state slots per lane
+template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U>
 __global__ void __launch_bounds__(NT)
 ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
-                int max_q, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
+                int max_q, int n_slots, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
                 int *__restrict__ err_flag)
 {
     extern __shared__ uint2 smem2[];
+    __shared__ uint32_t stab[8];                                                                 // S.tab, indexed by the target base
     const int tid = threadIdx.x;
-    uint2 *const HEp = smem2 + tid;                                                              // HE[p] = HEp[p * NT]
-    uint32_t *const QSp = reinterpret_cast<uint32_t *>(smem2 + (size_t)(max_q / 2 + 1) * NT) + tid;   // QS[g] = QSp[g * NT]
+    if (tid < 5) stab[tid] = S.tab[tid];
+    __syncthreads();
+    uint2 *const HEp = smem2 + tid;                                                              // HE[s] = HEp[s * NT]
+    uint16_t *const QSp = reinterpret_cast<uint16_t *>(smem2 + (size_t)n_slots * NT) + tid;      // QS[s] = QSp[s * NT]
     const uint32_t lo = range[bin], hi = range[bin + 1];
     unsigned long long my_cells = 0;
     for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
@@ -421,7 +423,7 @@ ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict
                 continue;
             }
             if (qlen > max_q || h0 < 1) { atomicExch(err_flag, 1); continue; }
-            pair_job<BYTES, NT, KEYED>(P, S, J, a, qlen, tlen, h0, HEp, QSp, r, my_cells);
+            pair_job<BYTES, NT, SAME_GAP, RING, CHUNKED, U>(P, S, stab, J, a, qlen, tlen, h0, HEp, QSp, r, my_cells);
             res[a] = r;
         }
     }
@@ -456,6 +458,29 @@ __global__ void pack_kernel(const uint8_t *__restrict__ bytes, uint64_t n_words,
 }
 
 } // namespace
+
+// the instantiations of ext_pair_kernel: blocks of 32 lanes only where a row can be longer than a chunk (the long, unbanded bins)
+using pair_kern_t = void (*)(ExtParams, PairParams, JobView, const uint32_t *, const uint32_t *, int, int, int, bwa_b200_ext_result_t *,
+                             unsigned long long *, int *);
+template <bool BYTES, bool SG, bool RG, bool CH>
+static pair_kern_t pair_kernel_pick(int nt, int u)
+{
+    if (nt == 32) {
+        if (!CH) return nullptr;
+        (void)u; return (pair_kern_t)ext_pair_kernel<BYTES, 32, SG, RG, true, 8>;
+    }
+    return (pair_kern_t)ext_pair_kernel<BYTES, 64, SG, RG, CH, 8>;
+}
+template <bool BYTES>
+static const void *pair_kernel_ptr(int nt, bool sg, bool rg, bool ch, int u)
+{
+    pair_kern_t k;
+    if (sg) k = rg ? (ch ? pair_kernel_pick<BYTES, true, true, true>(nt, u) : pair_kernel_pick<BYTES, true, true, false>(nt, u))
+                   : (ch ? pair_kernel_pick<BYTES, true, false, true>(nt, u) : pair_kernel_pick<BYTES, true, false, false>(nt, u));
+    else    k = rg ? (ch ? pair_kernel_pick<BYTES, false, true, true>(nt, u) : pair_kernel_pick<BYTES, false, true, false>(nt, u))
+                   : (ch ? pair_kernel_pick<BYTES, false, false, true>(nt, u) : pair_kernel_pick<BYTES, false, false, false>(nt, u));
+    return (const void *)k;
+}
 
 static int ext_grow_jobs(bwa_b200_extender *e, uint64_t n)
 {
@@ -547,11 +572,13 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
                              (const void *)ext_inter_kernel<true, 64>, (const void *)ext_inter_kernel<false, 64>,
                              (const void *)ext_inter_kernel<true, 32>, (const void *)ext_inter_kernel<false, 32>};
         for (const void *k : ks) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
-        const void *kp[6] = {(const void *)ext_pair_kernel<true, true, 64>, (const void *)ext_pair_kernel<true, false, 64>,
-                             (const void *)ext_pair_kernel<false, true, 64>, (const void *)ext_pair_kernel<false, false, 64>,
-                             (const void *)ext_pair_kernel<true, false, 32>, (const void *)ext_pair_kernel<false, false, 32>};
-        for (const void *k : kp) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+        for (int v = 0; v < 64; ++v) {          // every instantiation (the unroll bit is a no-op: one unroll factor is shipped)
+            const void *k = pair_kernel_ptr<true>(v & 1 ? 32 : 64, (v & 2) != 0, (v & 4) != 0, (v & 8) != 0, v & 16 ? 16 : 8);
+            if (v & 32) k = pair_kernel_ptr<false>(v & 1 ? 32 : 64, (v & 2) != 0, (v & 4) != 0, (v & 8) != 0, v & 16 ? 16 : 8);
+            if (k) B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+        }
     }
+    e->pair_no_ring = getenv("BWA_B200_PAIR_NO_RING") != nullptr;
     int rc = ext_grow_jobs(e, max_jobs ? max_jobs : 1024);
     if (rc) return rc;
     rc = ext_grow_seq(e, max_query_bytes ? max_query_bytes : 1024, max_target_bytes ? max_target_bytes : 1024);
@@ -635,19 +662,23 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     }
     auto bin_stream = [&]() -> cudaStream_t { if (!fan) return e->stream; cudaStream_t st = e->side[next_side]; next_side = (next_side + 1) % e->n_side; return st; };
     // column-pair s16x2 kernel, longest bins first
+    const bool same_gap = pair_same_gap(p);
     for (int b = N_PBINS - 1; b >= 0 && simd_ok; --b) {
         const int L = pbin_hi[b];
-        // The column state of a lane lives in shared memory, so the longest query of a bin bounds the resident lanes per SM.  Blocks
-        // of 64 lanes waste up to 63 lanes' worth of it on the long bins; there, blocks of 32 lanes fit more lanes (q384: 96 vs 64).
-        const size_t per_lane = (size_t)(L / 2 + 1) * 8 + (size_t)((L + 3) / 4 + 1) * 4;
+        // The column state of a lane lives in shared memory: with a band it is a ring of w + 2 column pairs whatever the query
+        // length, otherwise one slot per pair of the bin's longest query, which then bounds the resident lanes per SM.  Blocks of
+        // 64 lanes waste up to 63 lanes' worth of it on the long bins; there, blocks of 32 lanes fit more lanes (q384: 96 vs 64).
+        bwa_b200_ext_params_t pr = *p;
+        if (e->pair_no_ring) pr.use_band = 0;                    // sizing only: the kernel still applies the band
+        const int n_slots = pair_slots(&pr, L, &S);
+        const size_t per_lane = (size_t)n_slots * 10;
         if (per_lane * 32 > (size_t)e->smem_optin) { b200::set_error("extend: query bin %d does not fit shared memory", L); return BWA_B200_ERR_CAPACITY; }
+        const bool ring = S.ring != 0, chunked = n_slots > PAIR_CHUNK + 1;      // a row of at most 64 pairs needs no chunk fold
+        const pair_kern_t k64 = (pair_kern_t)pair_kernel_ptr<BYTES>(64, same_gap, ring, chunked, e->pair_unroll);
+        const pair_kern_t k32 = (pair_kern_t)pair_kernel_ptr<BYTES>(32, same_gap, ring, chunked, e->pair_unroll);
         int occ64 = 0, occ32 = 0;
-        if (b < N_KEYED) {
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ext_pair_kernel<BYTES, true, 64>, 64, per_lane * 64));
-        } else {
-            if (per_lane * 64 <= (size_t)e->smem_optin) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ext_pair_kernel<BYTES, false, 64>, 64, per_lane * 64));
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, ext_pair_kernel<BYTES, false, 32>, 32, per_lane * 32));
-        }
+        if (per_lane * 64 <= (size_t)e->smem_optin) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k64, 64, per_lane * 64));
+        if (k32) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k32, 32, per_lane * 32));
         const bool use32 = occ32 * 32 > occ64 * 64;
         const int nt = use32 ? 32 : 64;
         int occ = use32 ? occ32 : occ64;
@@ -658,15 +689,8 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         if (grid > max_blocks) grid = max_blocks;
         if (grid < 1) grid = 1;
         cudaStream_t st = bin_stream();
-        if (b < N_KEYED)
-            B200_LAUNCH(e->prof, pbin_name[b], st,
-                (ext_pair_kernel<BYTES, true, 64><<<grid, 64, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
-        else if (use32)
-            B200_LAUNCH(e->prof, pbin_name[b], st,
-                (ext_pair_kernel<BYTES, false, 32><<<grid, 32, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
-        else
-            B200_LAUNCH(e->prof, pbin_name[b], st,
-                (ext_pair_kernel<BYTES, false, 64><<<grid, 64, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, d_res, e->d_cells, e->d_err)));
+        B200_LAUNCH(e->prof, pbin_name[b], st,
+            ((use32 ? k32 : k64)<<<grid, nt, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, n_slots, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     // 32-bit kernel for everything else

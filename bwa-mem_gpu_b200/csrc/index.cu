@@ -184,7 +184,7 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
     bwa_b200_index *idx = new bwa_b200_index(*src);
     idx->device = device;
     idx->d_bkt = idx->d_sa = idx->d_sa_hi = nullptr;
-    idx->d_pac = nullptr; idx->l_pac = 0;
+    idx->d_pac = nullptr;
     idx->d_kt = nullptr; idx->v.kt = nullptr;
     uint64_t padded = (src->n_words + 7) / 8 * 8 + 8;
     B200_CUDA(cudaMalloc(&idx->d_bkt, padded * 4));
@@ -202,6 +202,11 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
         B200_CUDA(cudaMemcpyPeer(idx->d_kt, device, src->d_kt, src->device, bytes));
         idx->v.kt = idx->d_kt;
     }
+    if (src->d_pac) {          // the attached 2-bit forward reference (bwa_b200_index_attach_ref) travels with the index
+        const uint64_t words = (src->l_pac + 15) / 16 + 1;
+        B200_CUDA(cudaMalloc(&idx->d_pac, words * 4));
+        B200_CUDA(cudaMemcpyPeer(idx->d_pac, device, src->d_pac, src->device, words * 4));
+    } else idx->l_pac = 0;
     *out = idx;
     return BWA_B200_OK;
 }

@@ -68,7 +68,75 @@ int pack_impl(const uint8_t *src, const uint64_t *base_off, uint64_t n_reads, ui
     return BWA_B200_OK;
 }
 
+// the compact wire layout (bwa_b200_align_host_compact): 2 bits per base, 16 bases per word, base 0 in bits 31..30; anything that is
+// not A/C/G/T is written as 0 and listed in n_list as (read << 32 | position)
+template <bool ASCII>
+int pack2_impl(const uint8_t *src, const uint64_t *base_off, uint64_t n_reads, uint32_t *packed2, uint32_t *read_len,
+               uint64_t *n_list, uint64_t n_cap, uint64_t *n_n, int n_threads)
+{
+    if (!src || !base_off || !packed2 || !n_n || (n_cap && !n_list)) { b200::set_error("pack2: null argument"); return BWA_B200_ERR_ARG; }
+    if (n_threads < 1) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<uint64_t> woff(n_reads + 1);
+    uint64_t w = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        const uint64_t len = base_off[r + 1] - base_off[r];
+        if (len > 0xffffffffull) { b200::set_error("pack2: read %llu too long", (unsigned long long)r); return BWA_B200_ERR_ARG; }
+        if (read_len) read_len[r] = (uint32_t)len;
+        woff[r] = w;
+        w += (len + 15) / 16;
+    }
+    woff[n_reads] = w;
+    const int nt = n_threads;
+    std::vector<std::vector<uint64_t>> found(nt);       // per thread, reads ascending: concatenation keeps the list sorted
+    const uint64_t chunk = (n_reads + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const uint64_t a = std::min(n_reads, chunk * t), b = std::min(n_reads, a + chunk);
+        if (a >= b) continue;
+        th.emplace_back([=, &found, &woff] {
+            for (uint64_t r = a; r < b; ++r) {
+                const uint8_t *s = src + base_off[r];
+                const uint32_t len = (uint32_t)(base_off[r + 1] - base_off[r]);
+                uint32_t *dst = packed2 + woff[r];
+                for (uint32_t i = 0; i < len; i += 16) {
+                    uint32_t word = 0;
+                    for (uint32_t j = 0; j < 16 && i + j < len; ++j) {
+                        uint32_t c = ASCII ? g_nt4.t[s[i + j]] : (uint32_t)s[i + j];
+                        if (c > 3) { found[t].push_back(r << 32 | (uint64_t)(i + j)); c = 0; }
+                        word |= c << (30 - 2 * j);
+                    }
+                    dst[i >> 4] = word;
+                }
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    uint64_t k = 0;
+    for (int t = 0; t < nt; ++t) for (uint64_t e : found[t]) { if (k < n_cap) n_list[k] = e; ++k; }
+    *n_n = k;
+    if (k > n_cap) { b200::set_error("pack2: %llu bases are not A/C/G/T, room for %llu", (unsigned long long)k, (unsigned long long)n_cap); return BWA_B200_ERR_CAPACITY; }
+    return BWA_B200_OK;
+}
+
 } // namespace
+
+extern "C" size_t bwa_b200_packed2_words(const uint32_t *read_len, uint64_t n_reads, uint32_t uniform_len)
+{
+    if (!read_len) return (size_t)n_reads * (((size_t)uniform_len + 15) / 16);
+    size_t w = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) w += ((size_t)read_len[r] + 15) / 16;
+    return w;
+}
+extern "C" int bwa_b200_pack2_codes(const uint8_t *codes, const uint64_t *base_off, uint64_t n_reads, uint32_t *packed2, uint32_t *read_len,
+                                    uint64_t *n_list, uint64_t n_cap, uint64_t *n_n, int n_threads)
+{
+    return pack2_impl<false>(codes, base_off, n_reads, packed2, read_len, n_list, n_cap, n_n, n_threads);
+}
+extern "C" int bwa_b200_pack2_ascii(const char *bases, const uint64_t *base_off, uint64_t n_reads, uint32_t *packed2, uint32_t *read_len,
+                                    uint64_t *n_list, uint64_t n_cap, uint64_t *n_n, int n_threads)
+{
+    return pack2_impl<true>((const uint8_t *)bases, base_off, n_reads, packed2, read_len, n_list, n_cap, n_n, n_threads);
+}
 
 extern "C" size_t bwa_b200_packed_words(const uint32_t *read_len, uint64_t n_reads)
 {

@@ -19,6 +19,7 @@ __device__ __forceinline__ uint32_t ub_op(uint32_t a, uint32_t b, uint32_t c)
     if (OP == 6) return __viaddmax_s16x2(a, b, c);               // VIADDMNMX.S16x2
     if (OP == 7) return __vimax3_s16x2(a, b, c);                 // VIMNMX3.S16x2
     if (OP == 8) return a * b + c;                               // IMAD (fma pipe)
+    if (OP == 9) return __umulhi(a, b) + c;                      // IMAD.HI (fma pipe)
     return a;
 }
 
@@ -34,6 +35,26 @@ __global__ void __launch_bounds__(256) ub_kernel(uint32_t *out, int iters, uint3
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int i = 0; i < CHAINS; ++i) v[i] = ub_op<OP>(v[i], v[(i + 3) & 7], c);
+    }
+    uint32_t r = s1;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) r ^= v[i];
+    if (r == 0x12345678u) out[0] = r;
+}
+
+// half of the chains on the ALU pipe (VIADDMNMX.S16x2), half on the FMA pipe (IMAD): do the two pipes issue side by side?
+template <>
+__global__ void __launch_bounds__(256) ub_kernel<10>(uint32_t *out, int iters, uint32_t s0, uint32_t s1)
+{
+    uint32_t v[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) v[i] = threadIdx.x * 7 + i + s0;
+    const uint32_t c = s0 ^ 0x00030003;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) v[i] = (i & 1) ? v[i] * v[(i + 2) & 7] + c : __viaddmax_s16x2(v[i], v[(i + 2) & 7], c);
     }
     uint32_t r = s1;
 #pragma unroll
@@ -74,8 +95,8 @@ template <int OP> double ub_run(uint32_t *out, int sms, double mhz)
 
 extern "C" const char *bwa_b200_int_alu_op_name(int i)
 {
-    static const char *names[] = {"IADD3", "LOP3", "PRMT", "VIMNMX.S32", "VIADDMNMX.S32", "VIMNMX3.S32", "VIADDMNMX.S16x2", "VIMNMX3.S16x2", "IMAD"};
-    return i >= 0 && i < 9 ? names[i] : nullptr;
+    static const char *names[] = {"IADD3", "LOP3", "PRMT", "VIMNMX.S32", "VIADDMNMX.S32", "VIMNMX3.S32", "VIADDMNMX.S16x2", "VIMNMX3.S16x2", "IMAD", "IMAD.HI", "VIADDMNMX.S16x2+IMAD"};
+    return i >= 0 && i < 11 ? names[i] : nullptr;
 }
 
 // rates[i] = warp-instructions per clock per SM of op i (names above), at the SM clock measured under load (*sm_mhz);
@@ -106,9 +127,11 @@ extern "C" int bwa_b200_measure_int_alu(int device, double *rates, int cap, doub
     rates[0] = ub_run<0>(out, sms, mhz); rates[1] = ub_run<1>(out, sms, mhz); rates[2] = ub_run<2>(out, sms, mhz);
     rates[3] = ub_run<3>(out, sms, mhz); rates[4] = ub_run<4>(out, sms, mhz); rates[5] = ub_run<5>(out, sms, mhz);
     rates[6] = ub_run<6>(out, sms, mhz); rates[7] = ub_run<7>(out, sms, mhz); rates[8] = ub_run<8>(out, sms, mhz);
+    int n_ops = 9;
+    if (cap >= 11) { rates[9] = ub_run<9>(out, sms, mhz); rates[10] = ub_run<10>(out, sms, mhz); n_ops = 11; }
     cudaFree(out); cudaFree(clk);
     B200_CUDA(cudaGetLastError());
     if (sm_mhz) *sm_mhz = mhz;
     if (n_sm) *n_sm = sms;
-    return 9;
+    return n_ops;
 }

@@ -452,6 +452,59 @@ int  bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v)
 /* reads of the last batch that were not aligned because mem_flt_chained_seeds would run mem_seed_sw on them (see above): *n of them,
  * indexes ascending in *read_idx (owned by the aligner, valid until its next call; NULL when there are none) */
 int  bwa_b200_aligner_skipped_reads(bwa_b200_aligner_t *a, uint64_t *n, const uint32_t **read_idx);
+/* ---- the compact host boundary of the aligner: the smallest transfers that carry the same information (SURVEY 8e names the host leg
+ * -- PCIe and host memory traffic of 8 GPUs behind one socket -- as the scaling risk; the reference ships one byte per base,
+ * GASAL2/src/host_batch.cpp:79-153).
+ * Reads: 2 bits per base (A0 C1 G2 T3), 16 bases per u32, base 0 in bits 31..30, every read on a word boundary; bases that are not
+ * A/C/G/T are listed apart, one entry (read << 32 | position) each, and patched in on the device.  read_len == NULL: every read
+ * has uniform_len bases, and no per-read array crosses the bus at all.  Regions: 40-byte records holding the mem_alnreg_t fields
+ * the stages after extension read (src/bwamem.h:82-112); regions of read r follow those of read r - 1, n_regions_per_read[r] of
+ * them.  Reads beyond 65535 bases do not fit the record (use bwa_b200_align_host_view).  Results live in pinned buffers owned by
+ * the aligner, valid until its next call. */
+typedef struct {
+    int64_t  rb;                 /* [rb, rb + rlen) on the reference */
+    int32_t  rlen;
+    uint16_t qb, qe;
+    int32_t  score, truesc, seedcov, rid;
+    uint16_t w, seedlen0;
+    float    frac_rep;
+} bwa_b200_region_compact_t;
+size_t bwa_b200_packed2_words(const uint32_t *read_len, uint64_t n_reads, uint32_t uniform_len);
+/* codes 0..3 or anything else (= N) / ASCII -> the 2-bit layout; n_list receives up to n_cap entries, *n_n their number (sorted by
+ * read, then position); BWA_B200_ERR_CAPACITY when there are more */
+int  bwa_b200_pack2_codes(const uint8_t *codes, const uint64_t *base_off, uint64_t n_reads, uint32_t *packed2, uint32_t *read_len,
+                          uint64_t *n_list, uint64_t n_cap, uint64_t *n_n, int n_threads);
+int  bwa_b200_pack2_ascii(const char *bases, const uint64_t *base_off, uint64_t n_reads, uint32_t *packed2, uint32_t *read_len,
+                          uint64_t *n_list, uint64_t n_cap, uint64_t *n_n, int n_threads);
+int  bwa_b200_align_host_compact(bwa_b200_aligner_t *a, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len,
+                                 uint64_t n_reads, const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp,
+                                 const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep, uint64_t *n_regions,
+                                 const uint32_t **n_regions_per_read, const bwa_b200_region_compact_t **regions);
+
+/* ---- every GPU of the box behind one call: a dispatcher deals chunks of chunk_reads reads to worker threads,
+ * workers_per_device per device (two keep one chunk's copies under the other's kernels), each with its own aligner; the index
+ * -- with its attached reference and k-mer table -- is replicated to devices[1..] by peer copies (bwa_b200_index_clone_to).  The
+ * reference has no counterpart: it never selects a device (src/fastmap.c:143).  Input as bwa_b200_align_host_compact (pinned
+ * host memory makes the copies asynchronous; the N list sorted by read).  Output, in pinned memory owned by the handle and valid
+ * until its next call: n_regions_per_read in read order; the records of chunk k (reads [k * chunk_reads, ...)) are
+ * regions[chunk_region_off[k] ...], in read order within the chunk. */
+typedef struct bwa_b200_multi bwa_b200_multi_t;
+typedef struct {
+    uint64_t n_reads, n_regions, n_chunks, chunk_reads;
+    const uint32_t *n_regions_per_read;
+    const uint64_t *chunk_region_off;
+    const bwa_b200_region_compact_t *regions;
+} bwa_b200_multi_result_t;
+int  bwa_b200_multi_create(const bwa_b200_index_t *idx, const int *devices, int n_devices, int workers_per_device,
+                           uint64_t chunk_reads, uint32_t max_read_len, bwa_b200_multi_t **out);
+int  bwa_b200_multi_set_contigs(bwa_b200_multi_t *m, int32_t n, const int64_t *offset, const int32_t *len, const int32_t *is_alt);
+int  bwa_b200_multi_align_compact(bwa_b200_multi_t *m, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len,
+                                  uint64_t n_reads, const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp,
+                                  const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep, bwa_b200_multi_result_t *out);
+int  bwa_b200_multi_n_workers(const bwa_b200_multi_t *m);
+uint64_t bwa_b200_multi_worker_chunks(const bwa_b200_multi_t *m, int worker);   /* chunks a worker has processed since creation */
+uint64_t bwa_b200_multi_launches(const bwa_b200_multi_t *m);
+void bwa_b200_multi_destroy(bwa_b200_multi_t *m);
 void *bwa_b200_aligner_stream(bwa_b200_aligner_t *a);
 uint64_t bwa_b200_aligner_launches(const bwa_b200_aligner_t *a);
 int  bwa_b200_aligner_profile(bwa_b200_aligner_t *a, int enable);

@@ -42,12 +42,15 @@ static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
 { return umx(a & 0xffffu, b & 0xffffu) | umx(a >> 16, b >> 16) << 16; }
 static inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c)
 { return umx((a + b) & 0xffffu, c & 0xffffu) | umx(((a >> 16) + (b >> 16)) & 0xffffu, c >> 16) << 16; }
+static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
+static inline uint32_t b200_mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 
 #include "ext_pair_core.cuh"
 
 // jobs in the GASAL byte layout; res6 = n x 6 int32; returns the number of evaluated cells, or -1 if the parameters
-// are not eligible for the pair kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > max_q)
-extern "C" long long ext_pair_host_run(const bwa_b200_ext_params_t *p, int keyed, uint64_t n, const uint8_t *qseq, const uint32_t *qoff,
+// are not eligible for the pair kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > 512).
+// variant: bit 0 = four pairs per trip of the longest unrolled loop instead of eight, bit 1 = band-sized ring state (when the band allows one)
+extern "C" long long ext_pair_host_run(const bwa_b200_ext_params_t *p, int variant, uint64_t n, const uint8_t *qseq, const uint32_t *qoff,
                                        const uint32_t *qlen, const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen,
                                        const uint32_t *h0, int32_t *res6, uint8_t *skipped)
 {
@@ -64,16 +67,26 @@ extern "C" long long ext_pair_host_run(const bwa_b200_ext_params_t *p, int keyed
     JobView J{qseq, tseq, nullptr, nullptr, qoff, qlen, toff, tlen, h0};
     unsigned long long cells = 0;
     std::vector<uint2> HE;
-    std::vector<uint32_t> QS;
+    std::vector<uint16_t> QS;
+    const bool same = pair_same_gap(p);
     for (uint64_t a = 0; a < n; ++a) {
         const int ql = (int)qlen[a], tl = (int)tlen[a], h = (int)h0[a];
         const uint64_t bound = (uint64_t)h + (uint64_t)ql * (uint64_t)mxs;
-        skipped[a] = (bound > (uint64_t)PAIR_MAX_SCORE || ql > (keyed ? PAIR_KEYED_MAX_Q : 512) || ql < 1 || h < 1) ? 1 : 0;
+        skipped[a] = (bound > (uint64_t)PAIR_MAX_SCORE || ql > PAIR_MAX_Q || ql < 1 || h < 1) ? 1 : 0;
         if (skipped[a]) continue;
-        HE.assign(ql / 2 + 1, uint2{0xdeadbeefu, 0xdeadbeefu}); QS.assign((ql + 3) / 4 + 1, 0xdeadbeefu);
+        // the kernel sizes the state by the longest query of the job's length bin; here: the next multiple of 16
+        const int bin_q = (ql + 15) / 16 * 16;
+        int slots = bin_q / 2 + 1;
+        S.ring = 0; S.ring_magic = 0;
+        if (variant & 2) slots = pair_slots(p, bin_q, &S);
+        HE.assign(slots, uint2{0xdeadbeefu, 0xdeadbeefu}); QS.assign(slots, 0xdeadu);
         bwa_b200_ext_result_t r;
-        if (keyed) pair_job<true, 1, true>(P, S, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
-        else pair_job<true, 1, false>(P, S, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
+        const bool ring = S.ring != 0, chunked = slots > PAIR_CHUNK + 1;
+#define RUN(SG, RG, CH, UU) pair_job<true, 1, SG, RG, CH, UU>(P, S, S.tab, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells)
+#define RUN_U(SG, RG, CH) do { if (variant & 1) RUN(SG, RG, CH, 4); else RUN(SG, RG, CH, 8); } while (0)
+#define RUN_C(SG, RG) do { if (chunked) RUN_U(SG, RG, true); else RUN_U(SG, RG, false); } while (0)
+#define RUN_R(SG) do { if (ring) RUN_C(SG, true); else RUN_C(SG, false); } while (0)
+        if (same) RUN_R(true); else RUN_R(false);
         memcpy(res6 + a * 6, &r, 24);
     }
     return (long long)cells;

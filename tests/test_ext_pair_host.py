@@ -26,11 +26,11 @@ def emul(pkg):
     L.ext_pair_host_run.restype = C.c_longlong
     L.ext_pair_host_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64] + [C.c_void_p] * 9
 
-    def run(jobs, ep, keyed):
+    def run(jobs, ep, variant):
         n = jobs["qlen"].size
         res = np.zeros((n, 6), np.int32)
         skipped = np.zeros(n, np.uint8)
-        cells = L.ext_pair_host_run(C.addressof(ep), int(keyed), n, jobs["qseq"].ctypes.data, jobs["qoff"].ctypes.data, jobs["qlen"].ctypes.data,
+        cells = L.ext_pair_host_run(C.addressof(ep), int(variant), n, jobs["qseq"].ctypes.data, jobs["qoff"].ctypes.data, jobs["qlen"].ctypes.data,
                                     jobs["tseq"].ctypes.data, jobs["toff"].ctypes.data, jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data,
                                     res.ctypes.data, skipped.ctypes.data)
         return res, skipped.astype(bool), cells
@@ -47,13 +47,13 @@ SETS = [(61, dict(qlen_range=(1, 260), h0_range=(1, 250))),
         (66, dict(qlen_range=(100, 128), h0_range=(800, 895), sub_rate=0.01, indel_rate=0.005))]   # scores up to the 1023 bound
 
 
-@pytest.mark.parametrize("keyed", [True, False])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["u8", "u4", "ring_u8", "ring_u4"])
 @pytest.mark.parametrize("kw", KW)
-def test_pair_source_matches_oracle(pkg, oracle, emul, kw, keyed):
+def test_pair_source_matches_oracle(pkg, oracle, emul, kw, variant):
     for seed, extra in SETS:
         jobs = synth.make_ext_jobs(3000, w=kw["w"], seed=seed, **extra)
         want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
-        res, skipped, cells = emul(jobs, pkg.ext_params(**kw), keyed)
+        res, skipped, cells = emul(jobs, pkg.ext_params(**kw), variant)
         assert cells >= 0
         ok = ~skipped
         if seed not in (63, 66):
@@ -75,8 +75,17 @@ def test_pair_source_general_matrix(pkg, oracle, emul):
         P.mat[i] = int(mat.reshape(-1)[i])
         ep.mat[i] = int(mat.reshape(-1)[i])
     want, _ = oracle.ksw_batch(jobs, P, n_threads=4)
-    for keyed in (True, False):
-        res, skipped, cells = emul(jobs, ep, keyed)
+    for variant in (0, 3):
+        res, skipped, cells = emul(jobs, ep, variant)
         ok = ~skipped
         assert cells >= 0 and ok.sum() > 1000
         assert (res[ok] == want[ok]).all()
+
+
+def test_ring_slot_division_is_exact():
+    """SLOT(p) = p - ((p * ceil(2^20 / R)) >> 20) * R is p mod R for every pair index and every ring size the kernel can meet"""
+    p = np.arange(0, 600, dtype=np.uint64)
+    for R in range(2, 258):
+        magic = ((1 << 20) + R - 1) // R
+        assert int(600 * magic) < (1 << 32)
+        assert ((p - ((p * magic) >> 20) * R) == p % R).all(), R

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--genome", type=int, default=100_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only-long", action="store_true", help="only the long-read extension points")
+    ap.add_argument("--only-c4", action="store_true", help="skip the seeding sweep")
+    ap.add_argument("--zdrop", type=int, default=100)
     args = ap.parse_args()
     pkg = ge.load_package(); pkg.build()
     torch.cuda.set_device(0)
@@ -61,7 +63,7 @@ def main():
             ex.pack_device(dq.data_ptr(), dq.numel(), qp.data_ptr()); ex.pack_device(dt.data_ptr(), dt.numel(), tp.data_ptr())
             dev = {k: torch.from_numpy(jobs[k].view(np.int32)).cuda() for k in ("qoff", "toff", "qlen", "tlen", "h0")}
             res = torch.zeros(n * 6, dtype=torch.int32, device="cuda")
-            ep = pkg.ext_params(w=w, zdrop=100)
+            ep = pkg.ext_params(w=w, zdrop=args.zdrop)
 
             def fn():
                 ex.extend_device(ep, n, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(), tp.data_ptr(), dev["toff"].data_ptr(),
@@ -73,7 +75,7 @@ def main():
             print(out["c4_extension"][-1], file=sys.stderr, flush=True)
             del dq, dt, qp, tp, dev, res
     ex.destroy()
-    if args.only_long:
+    if args.only_long or args.only_c4:
         print(json.dumps(out))
         return
     # ---- C5
