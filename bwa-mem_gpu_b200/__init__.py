@@ -119,7 +119,7 @@ SYMBOLS = [
     "bwa_b200_aligner_destroy", "bwa_b200_align_host", "bwa_b200_align_host_view", "bwa_b200_align_seeds_host", "bwa_b200_align_device",
     "bwa_b200_align_device_view", "bwa_b200_aligner_skipped_reads", "bwa_b200_aligner_stream", "bwa_b200_aligner_launches", "bwa_b200_aligner_profile",
     "bwa_b200_aligner_kernel_times",
-    "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_cigars_free",
+    "bwa_b200_cigar_create", "bwa_b200_cigar_destroy", "bwa_b200_cigar_band", "bwa_b200_global_host", "bwa_b200_global_host_view", "bwa_b200_cigars_free",
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
     "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
     "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
@@ -292,6 +292,7 @@ def lib():
         L.bwa_b200_cigar_destroy.argtypes = [vp]
         L.bwa_b200_cigar_band.argtypes = [C.POINTER(ExtParams), C.c_int, C.c_int, C.c_int64]
         L.bwa_b200_global_host.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.POINTER(Cigars)]
+        L.bwa_b200_global_host_view.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, C.POINTER(Cigars)]
         L.bwa_b200_cigars_free.argtypes = [C.POINTER(Cigars)]
         L.bwa_b200_global_device.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         L.bwa_b200_global_device_view.argtypes = [vp, C.POINTER(Cigars)]
@@ -802,6 +803,17 @@ class Cigar:
                    cigar_off=_take(out.cigar_off, n, np.uint64), cigar=_take(out.cigar, out.n_ops, np.uint32))
         lib().bwa_b200_cigars_free(C.byref(out))
         return res
+
+    def global_host_view(self, n, qseq_ptr, q_bytes, qoff_ptr, qlen_ptr, tseq_ptr, t_bytes, toff_ptr, tlen_ptr, w_ptr, ext_p: ExtParams, copy=False):
+        """bwa_b200_global_host_view: host pointers in (pinned memory makes the copies asynchronous), results as views of the handle's
+        pinned buffers (valid until its next call) or copies"""
+        out = Cigars()
+        check(lib().bwa_b200_global_host_view(self.h, C.byref(ext_p), n, qseq_ptr, q_bytes, qoff_ptr, qlen_ptr, tseq_ptr, t_bytes, toff_ptr, tlen_ptr, w_ptr, C.byref(out)))
+
+        def arr(ptr, cnt, dt):
+            return _view(C.cast(ptr, vp), cnt, dt, copy)
+        return dict(score=arr(out.score, n, np.int32), nm=arr(out.nm, n, np.int32), n_cigar=arr(out.n_cigar, n, np.uint32),
+                    cigar_off=arr(out.cigar_off, n, np.uint64), cigar=arr(out.cigar, out.n_ops, np.uint32))
 
     def reg2aln_host(self, index, ctg_off, packed, word_off, read_len, alns, ext_p: ExtParams, match_score: int):
         """mem_reg2aln over a batch (bwa_b200_reg2aln_host).  alns: ALN_IN_DTYPE records.  Returns (ALN_OUT_DTYPE records, flat cigar)."""

@@ -39,25 +39,31 @@
 
 namespace {
 
+#include "ext_wave.cuh"
+
 constexpr int N_BINS = 7;
 __constant__ int c_bin_hi[N_BINS] = {16, 32, 64, 128, 256, 512, 1024};   // max qlen of each bin
 
 constexpr int N_PBINS = 16;              // bins of the column-pair kernel (PAIR_MAX_Q = the last one)
 __constant__ int c_pbin_hi[N_PBINS] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384, 448, 512};
-constexpr uint32_t CLS_BIT = 1u << 19;   // key bit: job runs in the 32-bit kernel
-constexpr uint32_t BAD_BIT = 1u << 20;   // key bit: scores could reach 2^15, not handled
+constexpr uint32_t CLS_BIT = 1u << 19;   // key bits 19-20 = the job's class: 0 column-pair kernel, 1 32-bit per-lane kernel, 2 ext_wave_kernel
+constexpr uint32_t CLS_WAVE = 2u << 19;  // (one job per warp, s16x2), 3 ext_intra_kernel (one job per warp, int32, no band needed)
+constexpr uint32_t CLS_INTRA = 3u << 19;
 
-// sort key: query length; bit 19 = not eligible for the column-pair s16x2 kernel (score bound above 1023, query
-// too long, or ineligible matrix / penalties); bit 20 = scores could reach 2^15
-__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, int simd_ok, uint32_t *keys, uint32_t *vals)
+// sort key: query length | class << 19.  Class 0: eligible for the column-pair s16x2 kernel (score bound at most 1023, query at most
+// 512, eligible matrix / penalties); 2: ext_wave_kernel (banded batch, query of WAVE_MIN_Q + 1 .. 65535 bases, score bound at most
+// WAVE_MAX_SCORE); 1: the 32-bit per-lane kernel (query at most 1024, scores below 2^15); 3: ext_intra_kernel (everything else)
+__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, int simd_ok, int wave_ok, uint32_t *keys, uint32_t *vals)
 {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     uint32_t q = qlen[a];
     uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
     uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
-    if (!simd_ok || bound > (uint64_t)PAIR_MAX_SCORE || q > (uint32_t)PAIR_MAX_Q) k |= CLS_BIT;
-    if (bound >= 32767ull) k |= BAD_BIT;
+    if (simd_ok && bound <= (uint64_t)PAIR_MAX_SCORE && q <= (uint32_t)PAIR_MAX_Q) { }
+    else if (wave_ok && q > (uint32_t)WAVE_MIN_Q && q <= 0xffffu && bound <= (uint64_t)WAVE_MAX_SCORE) k |= CLS_WAVE;
+    else if (q <= 1024u && bound < 32767ull) k |= CLS_BIT;
+    else k |= CLS_INTRA;
     keys[a] = k;
     vals[a] = a;
 }
@@ -73,17 +79,19 @@ __device__ __forceinline__ uint32_t lower_bound_key(const uint32_t *sorted_keys,
 __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag, int intra_ok)
 {
     const int k = threadIdx.x;
-    if (k > N_PBINS + N_BINS + 1) return;
+    if (k > N_PBINS + N_BINS + 2) return;
     uint32_t thr;
     if (k <= N_PBINS) thr = k == 0 ? 0u : (uint32_t)c_pbin_hi[k - 1] + 1u;
-    else thr = CLS_BIT | (k == N_PBINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_PBINS - 2] + 1u);
+    else if (k <= N_PBINS + N_BINS + 1) thr = CLS_BIT | (k == N_PBINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_PBINS - 2] + 1u);
+    else thr = CLS_INTRA;
     const uint32_t lo = lower_bound_key(sorted_keys, n, thr);
     range[k] = lo;
-    // anything between the last bin of a class and the next class, or with the bad bit, is not handled
+    // class-0 keys beyond the last pair bin cannot exist (key_kernel); if one does, it is reported, not dropped
     if (k == N_PBINS && lo < lower_bound_key(sorted_keys, n, CLS_BIT)) atomicExch(err_flag, 2);
-    // keys at or beyond range[N_PBINS + N_BINS + 1] (longer than the last bin, or scores beyond 16 bits) run in ext_intra_kernel; a caller
-    // that ruled such jobs out (no slabs, no launch) and was wrong gets an error, not missing results
-    if (k == N_PBINS + N_BINS + 1 && !intra_ok && lo < n) atomicExch(err_flag, 3);
+    // keys at or beyond range[N_PBINS + N_BINS + 1] run one per warp: ext_wave_kernel up to range[N_PBINS + N_BINS + 2] (class 2 exists only
+    // when that kernel is launched), ext_intra_kernel beyond; a caller that ruled the latter out (no slabs, no launch) and was wrong gets
+    // an error, not missing results
+    if (k == N_PBINS + N_BINS + 2 && !intra_ok && lo < n) atomicExch(err_flag, 3);
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -545,7 +553,7 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
         B200_CUDA(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
     }
     B200_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 2) * 4));
+    B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 4) * 4));
     B200_CUDA(cudaMalloc(&e->d_cells, 8));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
     e->intra_max_q = getenv("BWA_B200_EXT_INTRA_MAX_Q") ? atoi(getenv("BWA_B200_EXT_INTRA_MAX_Q")) : 16384;
@@ -622,9 +630,10 @@ static void to_dev_params(const bwa_b200_ext_params_t *p, ExtParams *d)
 // sort by query length, derive bin ranges, launch one kernel per bin (empty bins exit at once)
 template <bool BYTES>
 // may_intra: some job of the batch may be beyond the per-lane kernels (query longer than 1024 bases or scores beyond 16 bits); callers
-// that know the batch cannot hold one (short reads) pass false and neither the launch nor the slab allocation happens
+// that know the batch cannot hold one (short reads) pass false and neither the launch nor the slab allocation happens.  may_wave:
+// some job may be outside the column-pair class with a query beyond WAVE_MIN_Q bases (ext_wave_kernel takes those of a banded batch)
 static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint32_t n, const JobView &J,
-                      bwa_b200_ext_result_t *d_res, bool may_intra = true)
+                      bwa_b200_ext_result_t *d_res, bool may_intra = true, bool may_wave = true)
 {
     if (p->e_del <= 0 || p->e_ins <= 0) { b200::set_error("extend: gap extension penalties must be positive"); return BWA_B200_ERR_ARG; }
     ExtParams P;
@@ -638,7 +647,16 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     memset(&S, 0, sizeof(S));
     int simd_ok = pair_params_from(p, &S);
     if (getenv("BWA_B200_EXT_NO_SIMD")) simd_ok = 0;
-    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, e->d_keys, e->d_vals);
+    // ext_wave_kernel: banded batches whose ring (w + 2 pairs per job, WAVE_WARPS jobs per block) fits shared memory
+    PairParams SW = S;
+    bool wave_ok = simd_ok && may_wave && p->use_band && p->w >= 0 && p->w + 2 + WAVE_AHEAD <= WAVE_MAX_RING && !getenv("BWA_B200_EXT_NO_WAVE");
+    size_t wave_smem = 0;
+    if (wave_ok) {
+        SW.ring = p->w + 2 + WAVE_AHEAD; SW.ring_magic = (uint32_t)(((1 << 20) + SW.ring - 1) / SW.ring);
+        wave_smem = (size_t)WAVE_WARPS * SW.ring * 10 + 16;
+        if (wave_smem > (size_t)e->smem_optin) wave_ok = false;
+    }
+    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, wave_ok ? 1 : 0, e->d_keys, e->d_vals);
     size_t tmp = e->cub_bytes;
     B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
     range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err, may_intra ? 1 : 0);
@@ -713,12 +731,27 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
             (kern<<<grid, nt, smem, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
+    if (wave_ok) {     // one warp per job, s16x2, band-sized state: long queries and scores beyond 1023 of a banded batch
+        const bool sg = pair_same_gap(p);
+        auto kern = sg ? ext_wave_kernel<BYTES, true> : ext_wave_kernel<BYTES, false>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WAVE_WARPS * 32, wave_smem));
+        if (occ < 1) occ = 1;
+        if (occ > 4) occ = 4;
+        uint32_t grid = (uint32_t)(e->n_sm * occ), max_blocks = (n + WAVE_WARPS - 1) / WAVE_WARPS;
+        if (grid > max_blocks) grid = max_blocks;
+        cudaStream_t st = bin_stream();
+        B200_LAUNCH(e->prof, "ext_wave_kernel", st,
+            (kern<<<grid, WAVE_WARPS * 32, wave_smem, st>>>(P, SW, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), d_res, e->d_cells, e->d_err)));
+        e->launches += 1;
+    }
     if (may_intra && !e->d_intra)
         B200_CUDA(cudaMalloc(&e->d_intra, (size_t)e->intra_grid * INTRA_WARPS * ((size_t)e->intra_max_q + 1) * sizeof(int2)));
-    if (may_intra) {   // one warp per job for what is left (queries beyond the last bin, scores beyond 16 bits); exits at once when there is none
+    if (may_intra) {   // one warp per job in int32 for what is left (no band, scores beyond 16 bits); exits at once when there is none
         cudaStream_t st = bin_stream();
         B200_LAUNCH(e->prof, "ext_intra_kernel", st,
-            (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), n, e->intra_max_q,
+            (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + N_BINS + 2), n, e->intra_max_q,
                                                                                 e->d_intra, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
@@ -768,14 +801,17 @@ extern "C" int bwa_b200_extend_async_paged(bwa_b200_extender_t *e, const bwa_b20
     B200_CUDA(cudaMemcpyAsync(e->d_tlen, tlen, n * 4ull, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(e->d_h0, h0, n * 4ull, cudaMemcpyHostToDevice, st));
     JobView J{e->d_q, e->d_t, nullptr, nullptr, e->d_qoff, e->d_qlen, e->d_toff, e->d_tlen, e->d_h0};
-    bool may_intra = false;                    // host arrays: the exact test of key_kernel / range_kernel
+    bool may_intra = false, may_wave = false;  // host arrays: the exact tests of key_kernel / range_kernel
     {
         int mx = 0;
         for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
-        for (uint32_t a = 0; a < n && !may_intra; ++a)
-            may_intra = qlen[a] > 1024u || (uint64_t)h0[a] + (uint64_t)qlen[a] * (uint64_t)mx >= 32767ull;
+        for (uint32_t a = 0; a < n && !(may_intra && may_wave); ++a) {
+            const uint64_t bound = (uint64_t)h0[a] + (uint64_t)qlen[a] * (uint64_t)mx;
+            may_intra |= qlen[a] > 1024u || bound >= 32767ull;
+            may_wave |= qlen[a] > (uint32_t)WAVE_MIN_Q && (qlen[a] > (uint32_t)PAIR_MAX_Q || bound > (uint64_t)PAIR_MAX_SCORE);
+        }
     }
-    rc = ext_launch<true>(e, p, n, J, e->d_res, may_intra);
+    rc = ext_launch<true>(e, p, n, J, e->d_res, may_intra, may_wave);
     if (rc) return rc;
     if (res6) B200_CUDA(cudaMemcpyAsync(res6, e->d_res, n * sizeof(bwa_b200_ext_result_t), cudaMemcpyDeviceToHost, st));
     if (aln_score || query_end || target_end) {
@@ -866,7 +902,8 @@ int b200_ext_run_packed(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, ui
     int mx = 1;
     for (int i = 0; i < 25; ++i) mx = mx > p->mat[i] ? mx : p->mat[i];
     const bool may_intra = max_read_len < 0 || max_read_len > 1024 || (uint64_t)max_read_len * (uint64_t)(2 * mx) >= 32767ull;
-    rc = ext_launch<false>(e, p, n, J, d_res, may_intra);
+    const bool may_wave = max_read_len < 0 || (max_read_len > WAVE_MIN_Q && (max_read_len > PAIR_MAX_Q || (uint64_t)max_read_len * (uint64_t)(2 * mx) > (uint64_t)PAIR_MAX_SCORE));
+    rc = ext_launch<false>(e, p, n, J, d_res, may_intra, may_wave);
     if (rc) return rc;
     B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, e->stream));
     e->pending = true;

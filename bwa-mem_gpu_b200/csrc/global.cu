@@ -440,6 +440,9 @@ struct bwa_b200_cigar {
     uint64_t z_off[5] = {};
     uint64_t last_n = 0, last_ops = 0, last_cells = 0, launches = 0;
     b200::Prof prof; int profiling = 0;
+    // pinned host results of bwa_b200_global_host_view (grown geometrically, reused batch after batch)
+    int32_t *p_score = nullptr, *p_nm = nullptr; uint32_t *p_ncig = nullptr, *p_flat = nullptr; uint64_t *p_off = nullptr;
+    uint64_t p_jobs_cap = 0, p_ops_cap = 0;
 };
 
 // resident blocks of one class for the shared memory its longest sequences need: at most 24 warps per SM, so that the backtrack
@@ -487,6 +490,7 @@ extern "C" void bwa_b200_cigar_destroy(bwa_b200_cigar_t *c)
     cudaFree(c->d_rows); cudaFree(c->d_flat); cudaFree(c->d_z); cudaFree(c->d_cub); cudaFree(c->d_counters);
     cudaFree(c->r_packed); cudaFree(c->r_woff); cudaFree(c->r_jobs);
     cudaFreeHost(c->h_counters);
+    cudaFreeHost(c->p_score); cudaFreeHost(c->p_nm); cudaFreeHost(c->p_ncig); cudaFreeHost(c->p_off); cudaFreeHost(c->p_flat);
     for (int k = 0; k < 5; ++k) { if (c->side[k]) cudaStreamDestroy(c->side[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     cudaStreamDestroy(c->stream);
@@ -688,15 +692,11 @@ extern "C" void bwa_b200_cigars_free(bwa_b200_cigars_t *r)
     memset(r, 0, sizeof(*r));
 }
 
-extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
-                                    const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
-                                    const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
-                                    const uint32_t *w, bwa_b200_cigars_t *out)
+// host job batch -> device, kernels; results left on the device (c->d_score, d_nm, d_ncig, d_off, d_flat; c->last_ops operations)
+static int global_host_run(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                           const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                           const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen, const uint32_t *w)
 {
-    if (!c || !p || !out || (n_jobs && (!qseq || !qoff || !qlen || !tseq || !toff || !tlen || !w))) { b200::set_error("global_host: bad argument"); return BWA_B200_ERR_ARG; }
-    memset(out, 0, sizeof(*out));
-    out->n_jobs = n_jobs;
-    if (n_jobs == 0) return BWA_B200_OK;
     bool al = true;                        // the GASAL host layout: 8-byte aligned, padded sequences -> 64-bit loads in the kernel
     for (uint64_t a = 0; a < n_jobs; ++a) {
         if ((uint64_t)qoff[a] + qlen[a] > q_bytes || (uint64_t)toff[a] + tlen[a] > t_bytes) { b200::set_error("global_host: job %llu reaches past its sequence buffer", (unsigned long long)a); return BWA_B200_ERR_ARG; }
@@ -716,19 +716,74 @@ extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_para
     B200_CUDA(cudaMemcpyAsync(c->d_toff, toff, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_tlen, tlen, n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(c->d_w, w, n_jobs * 4, cudaMemcpyHostToDevice, st));
-    int rc = cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, qlen, tlen, w, al);
+    return cigar_run(c, p, n_jobs, c->d_q, c->d_qoff, c->d_qlen, c->d_t, c->d_toff, c->d_tlen, c->d_w, qlen, tlen, w, al);
+}
+
+static int global_download(bwa_b200_cigar_t *c, uint64_t n_jobs, int32_t *score, int32_t *nm, uint32_t *n_cigar, uint64_t *cigar_off, uint32_t *cigar)
+{
+    cudaStream_t st = c->stream;
+    const uint64_t ops = c->last_ops;
+    B200_CUDA(cudaMemcpyAsync(score, c->d_score, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(nm, c->d_nm, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(n_cigar, c->d_ncig, n_jobs * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(cigar_off, c->d_off, n_jobs * 8, cudaMemcpyDeviceToHost, st));
+    if (ops) B200_CUDA(cudaMemcpyAsync(cigar, c->d_flat, ops * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return BWA_B200_OK;
+}
+
+extern "C" int bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                    const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                                    const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                                    const uint32_t *w, bwa_b200_cigars_t *out)
+{
+    if (!c || !p || !out || (n_jobs && (!qseq || !qoff || !qlen || !tseq || !toff || !tlen || !w))) { b200::set_error("global_host: bad argument"); return BWA_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    out->n_jobs = n_jobs;
+    if (n_jobs == 0) return BWA_B200_OK;
+    int rc = global_host_run(c, p, n_jobs, qseq, q_bytes, qoff, qlen, tseq, t_bytes, toff, tlen, w);
     if (rc) return rc;
     const uint64_t ops = c->last_ops;
     out->n_ops = ops;
     out->score = (int32_t *)malloc(n_jobs * 4); out->nm = (int32_t *)malloc(n_jobs * 4); out->n_cigar = (uint32_t *)malloc(n_jobs * 4);
     out->cigar_off = (uint64_t *)malloc(n_jobs * 8); out->cigar = (uint32_t *)malloc((ops ? ops : 1) * 4);
     if (!out->score || !out->nm || !out->n_cigar || !out->cigar_off || !out->cigar) { bwa_b200_cigars_free(out); b200::set_error("global_host: out of host memory"); return BWA_B200_ERR_NOMEM; }
-    B200_CUDA(cudaMemcpyAsync(out->score, c->d_score, n_jobs * 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(out->nm, c->d_nm, n_jobs * 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(out->n_cigar, c->d_ncig, n_jobs * 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaMemcpyAsync(out->cigar_off, c->d_off, n_jobs * 8, cudaMemcpyDeviceToHost, st));
-    if (ops) B200_CUDA(cudaMemcpyAsync(out->cigar, c->d_flat, ops * 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    rc = global_download(c, n_jobs, out->score, out->nm, out->n_cigar, out->cigar_off, out->cigar);
+    if (rc) bwa_b200_cigars_free(out);
+    return rc;
+}
+
+// the same with the results in pinned buffers owned by the handle: the per-batch path of a driver (no allocation, no pageable
+// staging; with the inputs in pinned memory as well, every copy is one asynchronous DMA)
+extern "C" int bwa_b200_global_host_view(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                                         const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                                         const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                                         const uint32_t *w, bwa_b200_cigars_t *view)
+{
+    if (!c || !p || !view || (n_jobs && (!qseq || !qoff || !qlen || !tseq || !toff || !tlen || !w))) { b200::set_error("global_host_view: bad argument"); return BWA_B200_ERR_ARG; }
+    memset(view, 0, sizeof(*view));
+    view->n_jobs = n_jobs;
+    if (n_jobs == 0) return BWA_B200_OK;
+    int rc = global_host_run(c, p, n_jobs, qseq, q_bytes, qoff, qlen, tseq, t_bytes, toff, tlen, w);
+    if (rc) return rc;
+    const uint64_t ops = c->last_ops;
+    if (n_jobs > c->p_jobs_cap) {
+        cudaFreeHost(c->p_score); cudaFreeHost(c->p_nm); cudaFreeHost(c->p_ncig); cudaFreeHost(c->p_off);
+        c->p_score = c->p_nm = nullptr; c->p_ncig = nullptr; c->p_off = nullptr; c->p_jobs_cap = 0;
+        const uint64_t cap = n_jobs + n_jobs / 4 + 256;
+        B200_CUDA(cudaHostAlloc(&c->p_score, cap * 4, cudaHostAllocDefault)); B200_CUDA(cudaHostAlloc(&c->p_nm, cap * 4, cudaHostAllocDefault));
+        B200_CUDA(cudaHostAlloc(&c->p_ncig, cap * 4, cudaHostAllocDefault)); B200_CUDA(cudaHostAlloc(&c->p_off, cap * 8, cudaHostAllocDefault));
+        c->p_jobs_cap = cap;
+    }
+    if (ops > c->p_ops_cap || !c->p_flat) {
+        cudaFreeHost(c->p_flat); c->p_flat = nullptr; c->p_ops_cap = 0;
+        const uint64_t cap = ops + ops / 4 + 1024;
+        B200_CUDA(cudaHostAlloc(&c->p_flat, cap * 4, cudaHostAllocDefault));
+        c->p_ops_cap = cap;
+    }
+    rc = global_download(c, n_jobs, c->p_score, c->p_nm, c->p_ncig, c->p_off, c->p_flat);
+    if (rc) return rc;
+    view->n_ops = ops; view->score = c->p_score; view->nm = c->p_nm; view->n_cigar = c->p_ncig; view->cigar_off = c->p_off; view->cigar = c->p_flat;
     return BWA_B200_OK;
 }
 

@@ -42,10 +42,19 @@ finish_kernel(Opt o, int64_t l_pac, const int32_t *__restrict__ ctg_alt, const u
     }
 }
 
+// The call owns a non-blocking stream and takes its buffers from the stream-ordered allocator: nothing here touches the legacy
+// default stream or synchronises the device (cudaMalloc / cudaFree / cudaDeviceSynchronize would stall every other handle's streams --
+// two batches in flight is the normal way to drive the library), and the pool keeps the memory between calls.
+struct CallStream {
+    cudaStream_t st = nullptr;
+    ~CallStream() { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } }
+    int open() { return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess ? 0 : -1; }
+};
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s) == cudaSuccess ? 0 : -1; }
 };
 
 } // namespace
@@ -87,26 +96,39 @@ extern "C" int bwa_b200_finish_regions_host(const bwa_b200_index_t *idx, int32_t
     B200_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, idx->device));
     const unsigned grid = (unsigned)std::min<uint64_t>((n_reads + FIN_THREADS - 1) / FIN_THREADS, (uint64_t)sm * 8);
     const uint32_t eh_stride = max_len + 2;
+    CallStream cs;                         // declared before the buffers: they are released on it, then it is drained and destroyed
+    if (cs.open()) { cudaGetLastError(); b200::set_error("finish_regions: cudaStreamCreate failed"); return BWA_B200_ERR_CUDA; }
+    cudaStream_t st = cs.st;
+    {
+        static bool pool_kept[64] = {};    // keep freed blocks in the device's pool instead of returning them to the driver at every sync
+        if (idx->device < 64 && !pool_kept[idx->device]) {
+            cudaMemPool_t pool;
+            uint64_t keep = ~0ull;
+            if (cudaDeviceGetDefaultMemPool(&pool, idx->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaGetLastError();
+            pool_kept[idx->device] = true;
+        }
+    }
     DevBuf d_packed, d_woff, d_off, d_regs, d_n, d_pri, d_alt, d_eh, d_z;
-    if (d_packed.alloc(n_words * 4) || d_woff.alloc((n_reads + 1) * 8) || d_off.alloc((n_reads + 1) * 8) || d_regs.alloc(n_regs * sizeof(Reg)) ||
-        d_n.alloc(n_reads * 4) || d_pri.alloc(n_reads * 4) || d_alt.alloc((size_t)(n_ctg > 0 ? n_ctg : 1) * 4) ||
-        d_eh.alloc((size_t)grid * FIN_THREADS * eh_stride * sizeof(EH)) || d_z.alloc(n_regs * 4))
-        { cudaGetLastError(); b200::set_error("finish_regions: cudaMalloc failed"); return BWA_B200_ERR_CUDA; }
-    B200_CUDA(cudaMemcpy(d_packed.p, packed, n_words * 4, cudaMemcpyHostToDevice));
-    B200_CUDA(cudaMemcpy(d_woff.p, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
-    B200_CUDA(cudaMemcpy(d_off.p, region_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
-    if (n_regs) B200_CUDA(cudaMemcpy(d_regs.p, regs, n_regs * sizeof(Reg), cudaMemcpyHostToDevice));
+    if (d_packed.alloc(n_words * 4, st) || d_woff.alloc((n_reads + 1) * 8, st) || d_off.alloc((n_reads + 1) * 8, st) || d_regs.alloc(n_regs * sizeof(Reg), st) ||
+        d_n.alloc(n_reads * 4, st) || d_pri.alloc(n_reads * 4, st) || d_alt.alloc((size_t)(n_ctg > 0 ? n_ctg : 1) * 4, st) ||
+        d_eh.alloc((size_t)grid * FIN_THREADS * eh_stride * sizeof(EH), st) || d_z.alloc(n_regs * 4, st))
+        { cudaGetLastError(); b200::set_error("finish_regions: device allocation failed"); return BWA_B200_ERR_CUDA; }
+    B200_CUDA(cudaMemcpyAsync(d_packed.p, packed, n_words * 4, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(d_woff.p, word_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(d_off.p, region_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_regs) B200_CUDA(cudaMemcpyAsync(d_regs.p, regs, n_regs * sizeof(Reg), cudaMemcpyHostToDevice, st));
     const bool have_alt = n_ctg > 0 && ctg_alt;
-    if (have_alt) B200_CUDA(cudaMemcpy(d_alt.p, ctg_alt, (size_t)n_ctg * 4, cudaMemcpyHostToDevice));
+    if (have_alt) B200_CUDA(cudaMemcpyAsync(d_alt.p, ctg_alt, (size_t)n_ctg * 4, cudaMemcpyHostToDevice, st));
     Opt o;
     memcpy(&o, opt, sizeof(o));
-    finish_kernel<<<grid, FIN_THREADS>>>(o, (int64_t)idx->l_pac, have_alt ? (const int32_t *)d_alt.p : nullptr, idx->d_pac,
-                                         (const uint32_t *)d_packed.p, (const uint64_t *)d_woff.p, n_reads, (const uint64_t *)d_off.p,
-                                         (Reg *)d_regs.p, (uint32_t *)d_n.p, (int32_t *)d_pri.p, first_read_id, (EH *)d_eh.p, eh_stride, (int32_t *)d_z.p);
+    finish_kernel<<<grid, FIN_THREADS, 0, st>>>(o, (int64_t)idx->l_pac, have_alt ? (const int32_t *)d_alt.p : nullptr, idx->d_pac,
+                                                (const uint32_t *)d_packed.p, (const uint64_t *)d_woff.p, n_reads, (const uint64_t *)d_off.p,
+                                                (Reg *)d_regs.p, (uint32_t *)d_n.p, (int32_t *)d_pri.p, first_read_id, (EH *)d_eh.p, eh_stride, (int32_t *)d_z.p);
     B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaDeviceSynchronize());
-    if (n_regs) B200_CUDA(cudaMemcpy(regs, d_regs.p, n_regs * sizeof(Reg), cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(n_regs_out, d_n.p, n_reads * 4, cudaMemcpyDeviceToHost));
-    B200_CUDA(cudaMemcpy(n_pri, d_pri.p, n_reads * 4, cudaMemcpyDeviceToHost));
+    if (n_regs) B200_CUDA(cudaMemcpyAsync(regs, d_regs.p, n_regs * sizeof(Reg), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(n_regs_out, d_n.p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(n_pri, d_pri.p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
     return BWA_B200_OK;
 }

@@ -311,6 +311,13 @@ int  bwa_b200_global_host(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, u
                           const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
                           const uint32_t *w, bwa_b200_cigars_t *out);
 void bwa_b200_cigars_free(bwa_b200_cigars_t *r);
+/* the same with the results in pinned host buffers owned by the handle (valid until its next call or its destruction; not to be
+ * freed): the per-batch path of a driver -- no allocation, no pageable staging; with the inputs in pinned memory too, every copy
+ * is one asynchronous DMA (the reference keeps its result arrays pinned for the same reason, GASAL2/src/res.cpp:10-60) */
+int  bwa_b200_global_host_view(bwa_b200_cigar_t *c, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
+                               const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
+                               const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
+                               const uint32_t *w, bwa_b200_cigars_t *view);
 /* sequences and job tables already in HBM; host copies of qlen, tlen and w drive the band-width binning and the sizing.
  * aligned8 != 0: the caller guarantees the GASAL layout -- every offset a multiple of 8 and every sequence padded to a multiple of 8
  * bytes inside its buffer -- so the kernel loads 8 bases at a time (bwa_b200_global_host checks this itself).  Results stay on the

@@ -393,3 +393,39 @@ def test_seeding_kmer_table_variants(gpu, dev_index, monkeypatch, K, sat):
         monkeypatch.delenv("BWA_B200_KMER_SAT", raising=False)
         monkeypatch.delenv("BWA_B200_WIDE_ROWS", raising=False)
         idx.set_kmer_table(9)
+
+
+@pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=1, zdrop=0), dict(w=2, zdrop=20), dict(w=7, zdrop=100), dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=2, b=3),
+                                dict(w=64, zdrop=0, end_bonus=0), dict(w=500, zdrop=100), dict(w=2030, zdrop=100)],
+                         ids=lambda k: f"w{k['w']}z{k['zdrop']}")
+def test_extension_wave_kernel_banded_long_and_wide(gpu, oracle, kw):
+    """ext_wave_kernel (one job per warp, two columns per lane in s16x2, F by a warp max-plus scan, ring of w + 2 column pairs in shared
+    memory): queries of 257 .. 3000 bases and scores beyond 1023 of a banded batch, mixed with jobs of the per-lane kernels, through
+    the byte-per-base host call and the packed device call; bit-exact against the oracle, evaluated cells included"""
+    import torch
+    ex = gpu.Extender(0)
+    jobs = synth.make_ext_jobs(700, w=kw["w"], seed=97 + kw["w"], qlen_range=(200, 3000), h0_range=(1, 900), sub_rate=0.06, indel_rate=0.02, n_job_frac=0.1)
+    short = synth.make_ext_jobs(500, w=kw["w"], seed=98, qlen_range=(1, 300), h0_range=(1, 150))
+    want, cnt = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+    l0 = ex.launches
+    res, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
+    assert ex.launches > l0
+    bad = np.nonzero((res != want).any(axis=1))[0]
+    assert bad.size == 0, (bad[:5], jobs["qlen"][bad[:5]], jobs["tlen"][bad[:5]], jobs["h0"][bad[:5]], res[bad[:3]], want[bad[:3]])
+    assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == cnt["cells"]
+    # packed device path, long and short jobs in one batch
+    both = {k: np.concatenate([jobs[k], short[k]]) for k in ("qseq", "tseq", "qlen", "tlen", "h0")}
+    both["qoff"] = np.concatenate([jobs["qoff"], short["qoff"] + np.uint32(jobs["qseq"].size)]).astype(np.uint32)
+    both["toff"] = np.concatenate([jobs["toff"], short["toff"] + np.uint32(jobs["tseq"].size)]).astype(np.uint32)
+    want2, _ = oracle.ksw_batch(both, oracle.make_params(**kw), n_threads=4)
+    n = both["qlen"].size
+    dq = torch.from_numpy(both["qseq"]).cuda(); dt = torch.from_numpy(both["tseq"]).cuda()
+    qp = torch.empty((dq.numel() + 7) // 8, dtype=torch.int32, device="cuda"); tp = torch.empty((dt.numel() + 7) // 8, dtype=torch.int32, device="cuda")
+    ex.pack_device(dq.data_ptr(), dq.numel(), qp.data_ptr()); ex.pack_device(dt.data_ptr(), dt.numel(), tp.data_ptr())
+    dev = {k: torch.from_numpy(both[k].view(np.int32)).cuda() for k in ("qoff", "toff", "qlen", "tlen", "h0")}
+    out = torch.zeros(n * 6, dtype=torch.int32, device="cuda")
+    ex.extend_device(gpu.ext_params(**kw), n, qp.data_ptr(), dev["qoff"].data_ptr(), dev["qlen"].data_ptr(), tp.data_ptr(), dev["toff"].data_ptr(),
+                     dev["tlen"].data_ptr(), dev["h0"].data_ptr(), out.data_ptr())
+    ex.wait()
+    assert (out.cpu().numpy().reshape(-1, 6) == want2).all()
+    ex.destroy()
