@@ -55,9 +55,11 @@ __device__ __forceinline__ uint32_t b200_mad(uint32_t a, uint32_t b, uint32_t c)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t b200_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 #else
 #define B200_DEV static inline
 struct uint2 { uint32_t x, y; };
+static inline uint32_t b200_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 #endif
 
 struct ExtParams {
@@ -78,11 +80,13 @@ struct PairParams {
     uint32_t tab_n;              // byte 0: score against query code 4 (N)
     uint32_t noe_del2, ne_del2, noe_ins2, ne_ins2;   // negative penalties in both halves
     int32_t  ring;               // pairs in the state ring; 0 = one slot per pair of the longest query (no ring)
-    uint32_t ring_magic;         // ceil(2^20 / ring): p / ring == (p * ring_magic) >> 20 for every pair index of the class
+    uint32_t ring_magic;         // ceil(2^32 / ring): p / ring == umulhi(p, ring_magic) whenever p * ring < 2^32
 };
 
 constexpr int PAIR_MAX_SCORE = 1023;   // H * 32 must stay below 2^15 (zero test of the diagonal, see PAIR_CORE)
 constexpr int PAIR_MAX_Q = 512;        // longest query of the class
+constexpr int PAIR_WIDE_MAX_SCORE = 32700;   // WIDE: scores as s16 with the zero test min(H + s, min(H, 1023) * 32), exact below 2^15 - 32
+constexpr int PAIR_WIDE_MAX_Q = 65535;       // WIDE: the row maximum is a 32-bit key per column, score << 16 | column
 constexpr int PAIR_CHUNK = 64;         // (score, pair index within the chunk) is one 16-bit key: score < 2^10, index < 2^6
 
 // Fill the per-batch constants; returns 0 when the matrix / penalties are not eligible (any matrix whose
@@ -106,6 +110,7 @@ static inline int pair_params_from(const bwa_b200_ext_params_t *p, PairParams *S
     S->ring = 0; S->ring_magic = 0;
     return ok;
 }
+static inline uint32_t pair_ring_magic(int ring) { return ring > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)ring - 1) / (uint64_t)ring) : 0u; }
 static inline bool pair_same_gap(const bwa_b200_ext_params_t *p) { return p->o_del == p->o_ins && p->e_del == p->e_ins; }
 // state slots per lane for queries up to max_q: the ring when the band makes it smaller
 static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairParams *S)
@@ -113,7 +118,7 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
     const int full = max_q / 2 + 1;
     int ring = 0;
     if (p->use_band && p->w >= 0 && p->w + 2 < full) ring = p->w + 2;
-    if (S) { S->ring = ring; S->ring_magic = ring ? (uint32_t)(((1 << 20) + ring - 1) / ring) : 0u; }
+    if (S) { S->ring = ring; S->ring_magic = pair_ring_magic(ring); }
     return ring ? ring : full;
 }
 
@@ -125,7 +130,7 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 //   max(x - pen, 0) is the RELU form of VIADDMNMX with the (negative) penalty as its own third operand
 #define PAIR_CORE(HE, SEL)                                                                       \
         const uint32_t S_ = b200_prmt(tlo, tab_n, (SEL));                                        \
-        const uint32_t M_ = __viaddmin_s16x2((HE).x, S_, (HE).x * 32u);                          \
+        const uint32_t M_ = __viaddmin_s16x2((HE).x, S_, (WIDE ? __vmins2((HE).x, 0x03ff03ffu) : (HE).x) * 32u); \
         const uint32_t t2_ = __viaddmax_s16x2_relu(M_, noe_ins2, noe_ins2);                      \
         const uint32_t t1_ = SAME_GAP ? t2_ : __viaddmax_s16x2_relu(M_, noe_del2, noe_del2);     \
         const uint32_t Fh_ = __viaddmax_s16x2(c, ne_ins2, t2_ << 16);                            \
@@ -135,11 +140,13 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
         const uint32_t En_ = __viaddmax_s16x2((HE).y, ne_del2, t1_);
 
 // a pair wholly inside the window: HEV = its loaded state, KEY receives h * 64 + PPK (PPK = the pair's index within the
+// (WIDE: the larger of the two 32-bit keys score << 16 | column, PPK = the low column's offset, a literal, or the column itself)
 // chunk, in both halves -- or a literal offset, added to the index later); the store leaves {H(i, 2p-1) | H(i, 2p) << 16, E(i+1, .)} = what the next row reads
 #define PAIR_STEP(HP, HEV, SEL, PPK, KEY)                                                        \
     {                                                                                            \
         PAIR_CORE(HEV, SEL)                                                                      \
-        KEY = h_ * k64 + (PPK);                                                                  \
+        if (WIDE) KEY = max(__byte_perm((PPK), h_, 0x5410), __byte_perm((PPK), h_, 0x7610) + 1u); \
+        else KEY = h_ * k64 + (PPK);                                                             \
         uint2 o_;                                                                                \
         o_.y = En_;                                                                              \
         o_.x = __byte_perm(hprev, h_, 0x5432);                                                   \
@@ -161,7 +168,8 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
         if (LO_OUT) hprev = old_.x << 16;                                                        \
         PAIR_CORE(he_, SEL)                                                                      \
         const uint32_t hk_ = (HI_OUT) ? (h_ & 0x0000ffffu) : h_;                                 \
-        m2 = __vmaxu2(m2, hk_ * 64u + (PPK));                                                    \
+        if (WIDE) m2 = max(m2, max(__byte_perm((PPK), hk_, 0x5410), __byte_perm((PPK), hk_, 0x7610) + 1u)); \
+        else m2 = __vmaxu2(m2, hk_ * 64u + (PPK));                                               \
         (OUT).y = (En_ & outm_) | (old_.y & ~inm_);                                              \
         (OUT).x = __byte_perm(hprev, h_, 0x5432);                                                \
         *(HP) = (OUT);                                                                           \
@@ -170,8 +178,9 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 
 // One job.  HEp / QSp are this lane's element 0 of the [slot][lane] arrays; tab = S.tab in memory that can be indexed.
 // RING: the state is a ring of S.ring pairs (see the header); CHUNKED: a row may hold more than PAIR_CHUNK pairs, so the row
-// maximum is folded chunk by chunk; U: pairs per trip of the longest unrolled loop (4 or 8).
-template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U>
+// maximum is folded chunk by chunk; U: pairs per trip of the longest unrolled loop (4 or 8); WIDE: scores up to PAIR_WIDE_MAX_SCORE and
+// queries up to PAIR_WIDE_MAX_Q (the row maximum as 32-bit keys; needs RING or a state array for the whole query, never CHUNKED).
+template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U, bool WIDE = false>
 B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *const tab, const JobView &J, uint32_t a, int qlen, int tlen, int h0,
                        uint2 *const HEp, uint16_t *const QSp, bwa_b200_ext_result_t &r, unsigned long long &my_cells)
 {
@@ -180,7 +189,7 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
     const int R = RING ? S.ring : 0;
     const uint32_t rmagic = S.ring_magic;
     uint16_t *const hw = reinterpret_cast<uint16_t *>(HEp);
-#define SLOT(p) (RING ? (int)((uint32_t)(p) - (((uint32_t)(p) * rmagic) >> 20) * (uint32_t)R) : (int)(p))
+#define SLOT(p) (RING ? (int)((uint32_t)(p) - b200_umulhi((uint32_t)(p), rmagic) * (uint32_t)R) : (int)(p))
 #define H16(j) hw[SLOT((j) >> 1) * (NT * 4) + ((j) & 1)]
 #define E16(j) hw[SLOT((j) >> 1) * (NT * 4) + 2 + ((j) & 1)]
     // band clamp (src/ksw.c:885-893)
@@ -234,7 +243,11 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
     const uint32_t rz = (uint32_t)tlen >> 31;
     const uint32_t tab_n = S.tab_n + rz, noe_del2 = S.noe_del2 + rz, ne_del2 = S.ne_del2 + rz, noe_ins2 = S.noe_ins2 + rz, ne_ins2 = S.ne_ins2 + rz;
     const uint32_t k64 = 64u + rz;
-    (void)noe_del2;
+    (void)noe_del2; (void)k64;
+    constexpr uint32_t PPI = WIDE ? 2u : 0x00010001u;         // what one pair adds to pp: its low column (WIDE) / its index in both halves
+#define KMAX3(a, b, c) (WIDE ? __vimax3_u32((a), (b), (c)) : __vimax3_u16x2((a), (b), (c)))
+#define KMAX2(a, b) (WIDE ? max((a), (b)) : __vmaxu2((a), (b)))
+#define KMERGE(k, base, acc) (WIDE ? max((acc), (k) + (base)) : __viaddmax_u16x2((k), (base), (acc)))
     int h1_edge = h0 - P.o_del;                             // h0 - (o_del + e_del * (i + 1)), the first column of row i while beg == 0
     for (int i = 0; i < tlen; ++i) {
         int tbv;
@@ -269,8 +282,9 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
             const uint16_t *qp = QSp + s0 * NT;
             int pw = RING ? p0 - s0 + R : 0x7fffffff;               // first pair at or after p0 that sits in slot 0
             int pbase = p0, climit = CHUNKED ? p0 + PAIR_CHUNK : 0x7fffffff;     // the chunk of the row maximum's keys
-            uint32_t pp = 0u;                                       // (p - pbase) in both halves
+            uint32_t pp = WIDE ? 2u * (uint32_t)p0 : 0u;            // (p - pbase) in both halves; WIDE: the pair's low column
             auto fold = [&]() {                                     // (m, mj) <- chunk maximum; the later column wins ties (src/ksw.c:928)
+                if (WIDE) { m = (int)(m2 >> 16); mj = (int)(m2 & 0xffffu); return; }
                 const uint32_t kl = m2 & 0xffffu, kh = m2 >> 16;
                 const int sL = (int)(kl >> 6), cL = (pbase + (int)(kl & 63u)) * 2, sH = (int)(kh >> 6), cH = (pbase + (int)(kh & 63u)) * 2 + 1;
                 const bool hi_wins = sH > sL || (sH == sL && cH > cL);
@@ -281,7 +295,7 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
             PAIR_STEP_EDGE(hp, (uint32_t)*qp, pp, lo_out, hi_out && p0 == p1, o0)
             beg_live = lo_out ? ((o0.x | o0.y) >> 16) != 0u : ((o0.x | o0.y) & 0xffffu) != 0u;
             int p = p0 + 1;
-            pp += 0x00010001u; hp += NT; qp += NT;
+            pp += PPI; hp += NT; qp += NT;
             if (RING && p == pw) { hp -= R * NT; qp -= R * NT; pw += R; }
             while (p < p1) {
                 int stop = p1;
@@ -300,19 +314,19 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
                         const uint32_t s0_ = qp[0], s1_ = qp[NT], s2_ = qp[2 * NT], s3_ = qp[3 * NT], s4_ = qp[4 * NT], s5_ = qp[5 * NT], s6_ = qp[6 * NT], s7_ = qp[7 * NT];
                         uint32_t k0, k1, k2, k3, k4, k5, k6, k7;
                         PAIR_STEP(hp, e0, s0_, 0u, k0)
-                        PAIR_STEP(hp + NT, e1, s1_, 0x00010001u, k1)
-                        PAIR_STEP(hp + 2 * NT, e2, s2_, 0x00020002u, k2)
-                        PAIR_STEP(hp + 3 * NT, e3, s3_, 0x00030003u, k3)
-                        PAIR_STEP(hp + 4 * NT, e4, s4_, 0x00040004u, k4)
-                        PAIR_STEP(hp + 5 * NT, e5, s5_, 0x00050005u, k5)
-                        PAIR_STEP(hp + 6 * NT, e6, s6_, 0x00060006u, k6)
-                        PAIR_STEP(hp + 7 * NT, e7, s7_, 0x00070007u, k7)
-                        k0 = __vimax3_u16x2(k0, k1, k2);
-                        k3 = __vimax3_u16x2(k3, k4, k5);
-                        k0 = __vimax3_u16x2(k0, k3, k6);
-                        k0 = __vmaxu2(k0, k7);
-                        m2 = __viaddmax_u16x2(k0, pp, m2);
-                        pp += 0x00080008u; hp += 8 * NT; qp += 8 * NT;
+                        PAIR_STEP(hp + NT, e1, s1_, PPI, k1)
+                        PAIR_STEP(hp + 2 * NT, e2, s2_, 2u * PPI, k2)
+                        PAIR_STEP(hp + 3 * NT, e3, s3_, 3u * PPI, k3)
+                        PAIR_STEP(hp + 4 * NT, e4, s4_, 4u * PPI, k4)
+                        PAIR_STEP(hp + 5 * NT, e5, s5_, 5u * PPI, k5)
+                        PAIR_STEP(hp + 6 * NT, e6, s6_, 6u * PPI, k6)
+                        PAIR_STEP(hp + 7 * NT, e7, s7_, 7u * PPI, k7)
+                        k0 = KMAX3(k0, k1, k2);
+                        k3 = KMAX3(k3, k4, k5);
+                        k0 = KMAX3(k0, k3, k6);
+                        k0 = KMAX2(k0, k7);
+                        m2 = KMERGE(k0, pp, m2);
+                        pp += 8u * PPI; hp += 8 * NT; qp += 8 * NT;
                     } while (hp != hp_end);
                 }
                 if (p + 4 <= stop) {
@@ -324,20 +338,20 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
                         const uint32_t s0_ = qp[0], s1_ = qp[NT], s2_ = qp[2 * NT], s3_ = qp[3 * NT];
                         uint32_t k0, k1, k2, k3;
                         PAIR_STEP(hp, e0, s0_, 0u, k0)
-                        PAIR_STEP(hp + NT, e1, s1_, 0x00010001u, k1)
-                        PAIR_STEP(hp + 2 * NT, e2, s2_, 0x00020002u, k2)
-                        PAIR_STEP(hp + 3 * NT, e3, s3_, 0x00030003u, k3)
-                        k0 = __vimax3_u16x2(k0, k1, k2);
-                        k0 = __vmaxu2(k0, k3);
-                        m2 = __viaddmax_u16x2(k0, pp, m2);
-                        pp += 0x00040004u; hp += 4 * NT; qp += 4 * NT;
+                        PAIR_STEP(hp + NT, e1, s1_, PPI, k1)
+                        PAIR_STEP(hp + 2 * NT, e2, s2_, 2u * PPI, k2)
+                        PAIR_STEP(hp + 3 * NT, e3, s3_, 3u * PPI, k3)
+                        k0 = KMAX3(k0, k1, k2);
+                        k0 = KMAX2(k0, k3);
+                        m2 = KMERGE(k0, pp, m2);
+                        pp += 4u * PPI; hp += 4 * NT; qp += 4 * NT;
                     } while (hp != hp_end);
                 }
-                for (; p < stop; ++p, pp += 0x00010001u, hp += NT, qp += NT) {
+                for (; p < stop; ++p, pp += PPI, hp += NT, qp += NT) {
                     const uint2 e0 = hp[0];
                     uint32_t k0;
                     PAIR_STEP(hp, e0, (uint32_t)*qp, pp, k0)
-                    m2 = __vmaxu2(m2, k0);
+                    m2 = KMAX2(m2, k0);
                 }
                 if (RING && p == pw) { hp -= R * NT; qp -= R * NT; pw += R; }
                 if (CHUNKED && p == climit) { fold(); m2 = 0u; pp = 0u; pbase = p; climit += PAIR_CHUNK; }
@@ -380,6 +394,9 @@ B200_DEV void pair_job(const ExtParams &P, const PairParams &S, const uint32_t *
 #undef H16
 #undef E16
 #undef SLOT
+#undef KMAX3
+#undef KMAX2
+#undef KMERGE
     my_cells += cells;
     r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = best_ie + 1; r.gscore = gscore; r.max_off = max_off;
 }
