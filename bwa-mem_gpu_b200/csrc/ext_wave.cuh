@@ -1,7 +1,8 @@
 // ext_wave.cuh -- ext_wave_kernel: one ksw_extend2 job per WARP, a row evaluated 64 columns at a time -- two columns per lane in one
 // s16x2 register (the arithmetic of ext_pair_core.cuh), the F carry of the row done as a warp max-plus scan over the lanes' column
 // pairs, the diagonal H(i, j-1) passed to the next lane by a shuffle.  The intra-query kernel for what the per-lane kernels do not
-// take -- queries beyond 512 bases, scores beyond 1023 (up to 2^15 - 64) -- when the batch has a band.
+// take -- queries beyond 512 bases, scores beyond 1023 (up to 2^15 - 64) -- when the batch has a band and holds too few such jobs to
+// fill the machine one job per lane (those batches go to ext_pair_kernel<WIDE>, which is several times faster per cell).
 //
 // State sized by the band, not by the query: a ring of w + 2 column pairs {H(i-1, .), E(i, .)} and their PRMT selectors per warp in
 // shared memory (10 bytes per pair: 1 KB per job at w = 100, whatever the read length); a pair that enters the band for the first
@@ -27,7 +28,7 @@ constexpr int WAVE_MAX_RING = 2048;      // pairs: bands up to 2048 - 2 - WAVE_A
 
 template <bool BYTES, bool SAME_GAP>
 __global__ void __launch_bounds__(WAVE_WARPS * 32)
-ext_wave_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range,
+ext_wave_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, uint32_t max_jobs,
                 bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total, int *__restrict__ err_flag)
 {
     extern __shared__ uint2 wave_smem[];
@@ -40,8 +41,9 @@ ext_wave_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict
     uint2 *const HE = wave_smem + (size_t)wid * R;                                                         // HE[slot]
     uint16_t *const QS = reinterpret_cast<uint16_t *>(wave_smem + (size_t)WAVE_WARPS * R) + (size_t)wid * R;   // QS[slot]
     uint16_t *const hw = reinterpret_cast<uint16_t *>(HE);
-#define WSLOT(p) ((int)((uint32_t)(p) - (((uint32_t)(p) * rmagic) >> 20) * (uint32_t)R))
+#define WSLOT(p) ((int)((uint32_t)(p) - __umulhi((uint32_t)(p), rmagic) * (uint32_t)R))
     const uint32_t lo = range[0], hi = range[1];
+    if (hi - lo >= max_jobs) return;                        // a batch this large fills the machine one job per lane: ext_pair_kernel<WIDE> takes it
     const uint32_t gw = blockIdx.x * WAVE_WARPS + wid, n_warps = gridDim.x * WAVE_WARPS;
     const int oe_ins = P.o_ins + P.e_ins, e_ins = P.e_ins;
     const uint32_t tab_n = S.tab_n, noe_del2 = S.noe_del2, ne_del2 = S.ne_del2, noe_ins2 = S.noe_ins2;

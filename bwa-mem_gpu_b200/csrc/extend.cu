@@ -36,6 +36,7 @@
 #include "internal.h"
 #include "ext_pair_core.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace {
 
@@ -404,11 +405,13 @@ ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
 }
 
 // ext_pair_kernel: one job per lane, two query columns per s16x2 register (ext_pair_core.cuh); n_slots = state slots per lane
-template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U>
+// WIDE: the class of ext_wave_kernel (scores to 32700, any query length, ring state), one job per lane, taken when the batch holds at
+// least min_jobs such jobs
+template <bool BYTES, int NT, bool SAME_GAP, bool RING, bool CHUNKED, int U, bool WIDE = false>
 __global__ void __launch_bounds__(NT)
 ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ range, int bin,
                 int max_q, int n_slots, bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ cells_total,
-                int *__restrict__ err_flag)
+                int *__restrict__ err_flag, uint32_t min_jobs = 0)
 {
     extern __shared__ uint2 smem2[];
     __shared__ uint32_t stab[8];                                                                 // S.tab, indexed by the target base
@@ -418,6 +421,7 @@ ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict
     uint2 *const HEp = smem2 + tid;                                                              // HE[s] = HEp[s * NT]
     uint16_t *const QSp = reinterpret_cast<uint16_t *>(smem2 + (size_t)n_slots * NT) + tid;      // QS[s] = QSp[s * NT]
     const uint32_t lo = range[bin], hi = range[bin + 1];
+    if (hi - lo < min_jobs) return;
     unsigned long long my_cells = 0;
     for (uint32_t base = lo + blockIdx.x * NT; base < hi; base += gridDim.x * NT) {
         const uint32_t pos = base + tid;
@@ -430,8 +434,8 @@ ext_pair_kernel(ExtParams P, PairParams S, JobView J, const uint32_t *__restrict
                 res[a] = r;
                 continue;
             }
-            if (qlen > max_q || h0 < 1) { atomicExch(err_flag, 1); continue; }
-            pair_job<BYTES, NT, SAME_GAP, RING, CHUNKED, U>(P, S, stab, J, a, qlen, tlen, h0, HEp, QSp, r, my_cells);
+            if (qlen > max_q || h0 < 1 || (WIDE && (long long)h0 + (long long)qlen * P.max_score > PAIR_WIDE_MAX_SCORE)) { atomicExch(err_flag, 1); continue; }
+            pair_job<BYTES, NT, SAME_GAP, RING, CHUNKED, U, WIDE>(P, S, stab, J, a, qlen, tlen, h0, HEp, QSp, r, my_cells);
             res[a] = r;
         }
     }
@@ -469,7 +473,7 @@ __global__ void pack_kernel(const uint8_t *__restrict__ bytes, uint64_t n_words,
 
 // the instantiations of ext_pair_kernel: blocks of 32 lanes only where a row can be longer than a chunk (the long, unbanded bins)
 using pair_kern_t = void (*)(ExtParams, PairParams, JobView, const uint32_t *, const uint32_t *, int, int, int, bwa_b200_ext_result_t *,
-                             unsigned long long *, int *);
+                             unsigned long long *, int *, uint32_t);
 template <bool BYTES, bool SG, bool RG, bool CH>
 static pair_kern_t pair_kernel_pick(int nt, int u)
 {
@@ -652,7 +656,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     bool wave_ok = simd_ok && may_wave && p->use_band && p->w >= 0 && p->w + 2 + WAVE_AHEAD <= WAVE_MAX_RING && !getenv("BWA_B200_EXT_NO_WAVE");
     size_t wave_smem = 0;
     if (wave_ok) {
-        SW.ring = p->w + 2 + WAVE_AHEAD; SW.ring_magic = (uint32_t)(((1 << 20) + SW.ring - 1) / SW.ring);
+        SW.ring = p->w + 2 + WAVE_AHEAD; SW.ring_magic = pair_ring_magic(SW.ring);
         wave_smem = (size_t)WAVE_WARPS * SW.ring * 10 + 16;
         if (wave_smem > (size_t)e->smem_optin) wave_ok = false;
     }
@@ -708,7 +712,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         if (grid < 1) grid = 1;
         cudaStream_t st = bin_stream();
         B200_LAUNCH(e->prof, pbin_name[b], st,
-            ((use32 ? k32 : k64)<<<grid, nt, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, n_slots, d_res, e->d_cells, e->d_err)));
+            ((use32 ? k32 : k64)<<<grid, nt, smem, st>>>(P, S, J, e->d_order, e->d_range, b, L, n_slots, d_res, e->d_cells, e->d_err, 0u)));
         e->launches += 1;
     }
     // 32-bit kernel for everything else
@@ -731,8 +735,32 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
             (kern<<<grid, nt, smem, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + 1), b, L, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
-    if (wave_ok) {     // one warp per job, s16x2, band-sized state: long queries and scores beyond 1023 of a banded batch
+    if (wave_ok) {
+        // The jobs of a banded batch outside the column-pair class (long queries, scores beyond 1023).  A batch with enough of them to
+        // fill the machine one job per lane runs ext_pair_kernel<WIDE> (ring of w + 2 pairs per lane); a smaller one runs one job per
+        // warp in ext_wave_kernel.  Both are launched; the count decides on the device which of the two returns at once.
         const bool sg = pair_same_gap(p);
+        uint32_t wide_min = 0xffffffffu;                    // no wide launch: ext_wave_kernel takes any count
+        {
+            PairParams SP = S;
+            SP.ring = p->w + 2; SP.ring_magic = pair_ring_magic(SP.ring);
+            const size_t smem = (size_t)SP.ring * 10 * 32;
+            if (smem <= (size_t)e->smem_optin && !getenv("BWA_B200_EXT_NO_WIDE")) {
+                pair_kern_t kern = sg ? (pair_kern_t)ext_pair_kernel<BYTES, 32, true, true, false, 8, true> : (pair_kern_t)ext_pair_kernel<BYTES, 32, false, true, false, 8, true>;
+                B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem_optin));
+                int occ = 0;
+                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+                if (occ < 1) occ = 1;
+                wide_min = (uint32_t)std::max(1024, e->n_sm * occ * 32 / 4);       // a quarter of the resident lanes: where the two kernels break even
+                if (getenv("BWA_B200_EXT_WIDE_MIN")) wide_min = (uint32_t)std::max(1, atoi(getenv("BWA_B200_EXT_WIDE_MIN")));   // tests: force either kernel
+                uint32_t grid = (uint32_t)(e->n_sm * occ), max_blocks = (n + 31) / 32;
+                if (grid > max_blocks) grid = max_blocks;
+                cudaStream_t st = bin_stream();
+                B200_LAUNCH(e->prof, "ext_pair_kernel_wide", st,
+                    (kern<<<grid, 32, smem, st>>>(P, SP, J, e->d_order, e->d_range, N_PBINS + 1 + N_BINS, PAIR_WIDE_MAX_Q, SP.ring, d_res, e->d_cells, e->d_err, wide_min)));
+                e->launches += 1;
+            }
+        }
         auto kern = sg ? ext_wave_kernel<BYTES, true> : ext_wave_kernel<BYTES, false>;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
         int occ = 0;
@@ -743,7 +771,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         if (grid > max_blocks) grid = max_blocks;
         cudaStream_t st = bin_stream();
         B200_LAUNCH(e->prof, "ext_wave_kernel", st,
-            (kern<<<grid, WAVE_WARPS * 32, wave_smem, st>>>(P, SW, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), d_res, e->d_cells, e->d_err)));
+            (kern<<<grid, WAVE_WARPS * 32, wave_smem, st>>>(P, SW, J, e->d_order, e->d_range + (N_PBINS + 1 + N_BINS), wide_min, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
     if (may_intra && !e->d_intra)

@@ -44,8 +44,47 @@ static inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c)
 { return umx((a + b) & 0xffffu, c & 0xffffu) | umx(((a >> 16) + (b >> 16)) & 0xffffu, c >> 16) << 16; }
 static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
 static inline uint32_t b200_mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t __vimax3_u32(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+static inline uint32_t __vmins2(uint32_t a, uint32_t b) { return pk(mn(lo16(a), lo16(b)), mn(hi16(a), hi16(b))); }
 
 #include "ext_pair_core.cuh"
+
+// the WIDE instantiation (scores up to 32700, queries up to 65535, ring state): every job whose score bound fits runs, whatever its
+// length; skipped[a] = 1 otherwise.  Returns the evaluated cells, -1 for ineligible parameters, -2 when the band allows no ring.
+extern "C" long long ext_pair_host_run_wide(const bwa_b200_ext_params_t *p, uint64_t n, const uint8_t *qseq, const uint32_t *qoff,
+                                            const uint32_t *qlen, const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen,
+                                            const uint32_t *h0, int32_t *res6, uint8_t *skipped)
+{
+    PairParams S;
+    if (!pair_params_from(p, &S)) return -1;
+    if (!p->use_band) return -2;
+    ExtParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(P.mat, p->mat, 25);
+    P.o_del = p->o_del; P.e_del = p->e_del; P.o_ins = p->o_ins; P.e_ins = p->e_ins;
+    P.w = p->w; P.end_bonus = p->end_bonus; P.zdrop = p->zdrop; P.use_band = p->use_band; P.pen_clip = p->pen_clip;
+    int mxs = 0;
+    for (int i = 0; i < 25; ++i) mxs = mxs > p->mat[i] ? mxs : p->mat[i];
+    P.max_score = mxs;
+    JobView J{qseq, tseq, nullptr, nullptr, qoff, qlen, toff, tlen, h0};
+    unsigned long long cells = 0;
+    S.ring = p->w + 2; S.ring_magic = pair_ring_magic(S.ring);
+    std::vector<uint2> HE(S.ring, uint2{0xdeadbeefu, 0xdeadbeefu});
+    std::vector<uint16_t> QS(S.ring, 0xdeadu);
+    const bool same = pair_same_gap(p);
+    for (uint64_t a = 0; a < n; ++a) {
+        const int ql = (int)qlen[a], tl = (int)tlen[a], h = (int)h0[a];
+        const uint64_t bound = (uint64_t)h + (uint64_t)ql * (uint64_t)mxs;
+        skipped[a] = (bound > (uint64_t)PAIR_WIDE_MAX_SCORE || ql > PAIR_WIDE_MAX_Q || ql < 1 || h < 1) ? 1 : 0;
+        if (skipped[a]) continue;
+        bwa_b200_ext_result_t r;
+        if (same) pair_job<true, 1, true, true, false, 8, true>(P, S, S.tab, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
+        else pair_job<true, 1, false, true, false, 8, true>(P, S, S.tab, J, (uint32_t)a, ql, tl, h, HE.data(), QS.data(), r, cells);
+        memcpy(res6 + a * 6, &r, 24);
+    }
+    return (long long)cells;
+}
 
 // jobs in the GASAL byte layout; res6 = n x 6 int32; returns the number of evaluated cells, or -1 if the parameters
 // are not eligible for the pair kernel; skipped[a] = 1 for jobs outside its class (score bound > 1023, query > 512).

@@ -25,6 +25,8 @@ def emul(pkg):
     L = C.CDLL(so)
     L.ext_pair_host_run.restype = C.c_longlong
     L.ext_pair_host_run.argtypes = [C.c_void_p, C.c_int, C.c_uint64] + [C.c_void_p] * 9
+    L.ext_pair_host_run_wide.restype = C.c_longlong
+    L.ext_pair_host_run_wide.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9
 
     def run(jobs, ep, variant):
         n = jobs["qlen"].size
@@ -34,6 +36,7 @@ def emul(pkg):
                                     jobs["tseq"].ctypes.data, jobs["toff"].ctypes.data, jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data,
                                     res.ctypes.data, skipped.ctypes.data)
         return res, skipped.astype(bool), cells
+    run.lib = L
     return run
 
 
@@ -83,9 +86,38 @@ def test_pair_source_general_matrix(pkg, oracle, emul):
 
 
 def test_ring_slot_division_is_exact():
-    """SLOT(p) = p - ((p * ceil(2^20 / R)) >> 20) * R is p mod R for every pair index and every ring size the kernel can meet"""
-    p = np.arange(0, 600, dtype=np.uint64)
-    for R in range(2, 258):
-        magic = ((1 << 20) + R - 1) // R
-        assert int(600 * magic) < (1 << 32)
-        assert ((p - ((p * magic) >> 20) * R) == p % R).all(), R
+    """SLOT(p) = p - umulhi(p, ceil(2^32 / R)) * R is p mod R for every pair index (queries up to 65535 bases) and every ring size"""
+    p = np.concatenate([np.arange(0, 3000), np.arange(32000, 32800)]).astype(np.uint64)
+    for R in list(range(2, 300)) + [511, 512, 513, 700, 1023, 2047, 2048]:
+        magic = ((1 << 32) + R - 1) // R
+        assert magic < (1 << 32)
+        assert ((p - ((p * magic) >> 32) * R) == p % R).all(), R
+
+
+@pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=16, zdrop=100), dict(w=2, zdrop=10), dict(w=1, zdrop=0, end_bonus=0),
+                                dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=3, b=2), dict(w=300, zdrop=0)],
+                         ids=lambda k: f"w{k['w']}")
+def test_pair_source_wide_scores_long_queries(pkg, oracle, emul, kw):
+    """the WIDE instantiation (lane per job for large batches of long banded jobs): scores beyond 1023, queries beyond 512, 32-bit
+    row-maximum keys, ring state, against the oracle -- results and evaluated cells"""
+    sets = [(81, dict(qlen_range=(1, 260), h0_range=(1, 250))),
+            (82, dict(qlen_range=(300, 3000), h0_range=(1, 900), sub_rate=0.05, indel_rate=0.02, n_job_frac=0.1)),
+            (83, dict(qlen_range=(100, 700), h0_range=(900, 3000), sub_rate=0.01, indel_rate=0.005)),
+            (84, dict(qlen_range=(1, 60), h0_range=(1, 5000), sub_rate=0.4, indel_rate=0.2, n_job_frac=0.3))]
+    for seed, extra in sets:
+        n = 150 if seed == 82 else 1500
+        jobs = synth.make_ext_jobs(n, w=kw["w"], seed=seed, **extra)
+        want, cnt = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+        res = np.zeros((n, 6), np.int32)
+        skipped = np.zeros(n, np.uint8)
+        ep = pkg.ext_params(**kw)
+        cells = emul.lib.ext_pair_host_run_wide(C.addressof(ep), n, jobs["qseq"].ctypes.data, jobs["qoff"].ctypes.data, jobs["qlen"].ctypes.data,
+                                                jobs["tseq"].ctypes.data, jobs["toff"].ctypes.data, jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data,
+                                                res.ctypes.data, skipped.ctypes.data)
+        assert cells >= 0
+        ok = ~skipped.astype(bool)
+        assert ok.sum() > 0.9 * n
+        bad = np.nonzero((res[ok] != want[ok]).any(axis=1))[0]
+        assert bad.size == 0, (seed, np.nonzero(ok)[0][bad[:3]], res[ok][bad[:3]], want[ok][bad[:3]])
+        if ok.all():
+            assert cells == cnt["cells"]

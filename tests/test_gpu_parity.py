@@ -398,11 +398,17 @@ def test_seeding_kmer_table_variants(gpu, dev_index, monkeypatch, K, sat):
 @pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=1, zdrop=0), dict(w=2, zdrop=20), dict(w=7, zdrop=100), dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=2, b=3),
                                 dict(w=64, zdrop=0, end_bonus=0), dict(w=500, zdrop=100), dict(w=2030, zdrop=100)],
                          ids=lambda k: f"w{k['w']}z{k['zdrop']}")
-def test_extension_wave_kernel_banded_long_and_wide(gpu, oracle, kw):
-    """ext_wave_kernel (one job per warp, two columns per lane in s16x2, F by a warp max-plus scan, ring of w + 2 column pairs in shared
-    memory): queries of 257 .. 3000 bases and scores beyond 1023 of a banded batch, mixed with jobs of the per-lane kernels, through
-    the byte-per-base host call and the packed device call; bit-exact against the oracle, evaluated cells included"""
+@pytest.mark.parametrize("wide", [False, True], ids=["wave", "wide"])
+def test_extension_wave_kernel_banded_long_and_wide(gpu, oracle, kw, wide, monkeypatch):
+    """the jobs of a banded batch outside the column-pair class -- queries of 257 .. 3000 bases, scores beyond 1023 -- through both kernels
+    that take them: ext_wave_kernel (one job per warp, two columns per lane in s16x2, F by a warp max-plus scan, ring of column pairs in
+    shared memory; small batches) and ext_pair_kernel<WIDE> (one job per lane, 32-bit row-maximum keys, ring state; batches that fill
+    the machine -- forced here by BWA_B200_EXT_WIDE_MIN).  Mixed with jobs of the other kernels, through the byte-per-base host call and
+    the packed device call; bit-exact against the oracle, evaluated cells included"""
     import torch
+    if wide and kw["w"] > 600:
+        pytest.skip("the ring of this band does not fit a lane's shared memory: ext_wave_kernel takes it whatever the count")
+    monkeypatch.setenv("BWA_B200_EXT_WIDE_MIN", "1" if wide else "1000000000")
     ex = gpu.Extender(0)
     jobs = synth.make_ext_jobs(700, w=kw["w"], seed=97 + kw["w"], qlen_range=(200, 3000), h0_range=(1, 900), sub_rate=0.06, indel_rate=0.02, n_job_frac=0.1)
     short = synth.make_ext_jobs(500, w=kw["w"], seed=98, qlen_range=(1, 300), h0_range=(1, 150))

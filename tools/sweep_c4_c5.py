@@ -47,9 +47,10 @@ def main():
     st = torch.cuda.ExternalStream(ex.stream)
     base_n = 1 << 14
     points = [(q, w, base_n, args.jobs) for q in (100, 150, 200, 250, 300) for w in (16, 32, 50, 64, 100)]
-    points += [(2000, 100, 512, 8192), (10000, 100, 128, 2048)]          # long reads: one job per warp (ext_intra_kernel)
+    points += [(2000, 100, 512, 8192), (10000, 100, 128, 2048),          # long reads, small batches: one job per warp (ext_wave_kernel)
+               (1000, 100, 1024, 131072), (2000, 100, 512, 65536), (10000, 100, 128, 16384)]   # large batches: one job per lane (ext_pair_kernel<WIDE>)
     if args.only_long:
-        points = points[-2:]
+        points = points[-5:]
     for qlen, w, bn, total in points:
         if True:
             base = synth.make_ext_jobs(bn, w=w, seed=777 + qlen + w, qlen_range=(qlen, qlen), h0_range=(19, 150))
