@@ -24,6 +24,7 @@
 #include <string.h>
 #include <math.h>
 #include "chain_oracle.h"
+#include "sw_oracle.h"
 
 void chain_opt_default(chain_opt_t *o)
 { /* mem_opt_init, src/bwamem.c:107-150 (the fork's defaults: w = 300) */
@@ -262,14 +263,32 @@ static void flt_introsort(const chn_t *ch, size_t n, int *a)
  * mem_seed_v_gpu, src/bwamem.c:419-431); layout_all == 0: a group holds only the sampled rows, consecutively
  * (bwa_b200_seeds_t with max_occ > 0).  chains / cseeds need room for n_seeds entries.
  * Returns 0; -2 when mem_flt_chained_seeds would not return early for this read length. */
+static int chain_read_impl(const chain_opt_t *opt, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                           int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qq, const uint32_t *score, int layout_all,
+                           int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds, int stop_at_long);
+
 int chain_oracle_read(const chain_opt_t *opt, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
                       int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qq, const uint32_t *score, int layout_all,
                       int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds)
 {
+    return chain_read_impl(opt, l_pac, n_ctg, ctg_off, ctg_len, ctg_alt, l_query, n_seeds, rbeg, qq, score, layout_all, n_chains, chains, cseeds, 1);
+}
+/* the same for a read of any length: the caller runs chain_oracle_flt_seeds on the result (mem_flt_chained_seeds) */
+int chain_oracle_read_any(const chain_opt_t *opt, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                          int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qq, const uint32_t *score, int layout_all,
+                          int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds)
+{
+    return chain_read_impl(opt, l_pac, n_ctg, ctg_off, ctg_len, ctg_alt, l_query, n_seeds, rbeg, qq, score, layout_all, n_chains, chains, cseeds, 0);
+}
+
+static int chain_read_impl(const chain_opt_t *opt, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                           int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qq, const uint32_t *score, int layout_all,
+                           int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds, int stop_at_long)
+{
     (void)ctg_len;
     *n_chains = 0;
     if (l_query < opt->min_seed_len) return 0;
-    {   /* mem_flt_chained_seeds, src/bwamem.c:972-977 (MEM_HSP_COEF 1.1, MEM_MINSC_COEF 5.5, MEM_SEEDSW_COEF 0.05) */
+    if (stop_at_long) {   /* mem_flt_chained_seeds, src/bwamem.c:972-977 (MEM_HSP_COEF 1.1, MEM_MINSC_COEF 5.5, MEM_SEEDSW_COEF 0.05) */
         double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
         if (!(min_l > 0.05f * l_query)) return -2;
     }
@@ -416,6 +435,67 @@ static uint8_t text_base(const uint8_t *fwd, int64_t l_pac, int64_t p)
 { /* base p of fwd + revcomp(fwd): bns_get_seq, src/bntseq.c:506-529 */
     return p < l_pac ? fwd[p] : (uint8_t)(3 - fwd[(l_pac << 1) - 1 - p]);
 }
+/* mem_seed_sw, src/bwamem.c:774-808: a local alignment of the read around the seed against the reference around it, 50 bases either
+ * side; -1 when the seed or its windows reach MEM_SHORT_LEN (200) */
+static int seed_sw(const chain_opt_t *opt, const int8_t *mat, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len,
+                   const uint8_t *fwd, int l_query, const uint8_t *query, const chain_seed_t *s)
+{
+    int qb, qe, is_rev, rid;
+    int64_t rb, re, mid, far_beg, far_end;
+    uint8_t rseq[256];
+    if (s->len >= 200) return -1;
+    qb = s->qbeg; qe = s->qbeg + s->len;
+    rb = s->rbeg; re = s->rbeg + s->len;
+    mid = (rb + re) >> 1;
+    qb -= 50; qb = qb > 0 ? qb : 0;
+    qe += 50; qe = qe < l_query ? qe : l_query;
+    rb -= 50; rb = rb > 0 ? rb : 0;
+    re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+    if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+    if (qe - qb >= 200 || re - rb >= 200) return -1;
+    /* bns_fetch_seq, src/bntseq.c:531-552: clamp to the contig that holds mid */
+    rid = pos2rid(l_pac, n_ctg, ctg_off, depos(l_pac, mid, &is_rev));
+    far_beg = ctg_off[rid]; far_end = far_beg + ctg_len[rid];
+    if (is_rev) { int64_t tmp = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - tmp; }
+    rb = rb > far_beg ? rb : far_beg;
+    re = re < far_end ? re : far_end;
+    for (int64_t k = rb; k < re; ++k) rseq[k - rb] = text_base(fwd, l_pac, k);
+    sw_result_t x = sw_align2_oracle(qe - qb, query + qb, (int)(re - rb), rseq, 5, mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, SW_XSTART);
+    return x.score;
+}
+
+/* mem_flt_chained_seeds, src/bwamem.c:970-990, on the chains chain_oracle_read_any left: seeds whose local alignment scores below
+ * min_HSP_score leave their chain (chains[i].n shrinks; the kept seeds of all chains are packed and seed_off re-assigned), the others take the
+ * alignment's score (seed length * a when mem_seed_sw declined).  Returns 1 when the read was long enough for the filter to run. */
+int chain_oracle_flt_seeds(const chain_opt_t *opt, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len,
+                           const uint8_t *fwd, int l_query, const uint8_t *query, int n_chains, chain_rec_t *chains, chain_seed_t *cseeds)
+{
+    double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
+    int min_HSP_score = (int)(opt->a * min_l + .499);
+    int8_t mat[25];
+    int i, j, k;
+    if (min_l > 0.05f * l_query) return 0;
+    for (i = k = 0; i < 4; ++i) { for (j = 0; j < 4; ++j) mat[k++] = (int8_t)(i == j ? opt->a : -opt->b); mat[k++] = -1; }   /* bwa_fill_scmat */
+    for (j = 0; j < 5; ++j) mat[k++] = -1;
+    int so = 0;                                   /* the kept seeds are packed: chain after chain, seed_off re-assigned */
+    for (i = 0; i < n_chains; ++i) {
+        const chain_seed_t *sd = cseeds + chains[i].seed_off;
+        const int first = so;
+        for (j = 0; j < chains[i].n; ++j) {
+            chain_seed_t s = sd[j];
+            s.score = seed_sw(opt, mat, l_pac, n_ctg, ctg_off, ctg_len, fwd, l_query, query, &s);
+            if (s.score < 0 || s.score >= min_HSP_score) {
+                s.score = s.score < 0 ? s.len * opt->a : s.score;
+                cseeds[so++] = s;
+            }
+        }
+        chains[i].n = so - first;
+        chains[i].seed_off = first;
+    }
+    (void)k;
+    return 1;
+}
+
 static int cmp_u64(const void *x, const void *y) { uint64_t a = *(const uint64_t *)x, b = *(const uint64_t *)y; return a < b ? -1 : a > b; }
 
 typedef struct { chain_job_t *jobs; uint8_t *q, *t; uint32_t nq, nt; int n; } side_t;

@@ -24,6 +24,11 @@ void chain_opt_default(chain_opt_t *o);
 int chain_oracle_read(const chain_opt_t *o, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
                       int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qbeg_qend, const uint32_t *score, int layout_all,
                       int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds);
+int chain_oracle_read_any(const chain_opt_t *o, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
+                          int l_query, uint32_t n_seeds, const uint64_t *rbeg, const int32_t *qbeg_qend, const uint32_t *score, int layout_all,
+                          int32_t *n_chains, chain_rec_t *chains, chain_seed_t *cseeds);
+int chain_oracle_flt_seeds(const chain_opt_t *o, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len,
+                           const uint8_t *fwd, int l_query, const uint8_t *query, int n_chains, chain_rec_t *chains, chain_seed_t *cseeds);
 int chain2aln_oracle_read(const chain_opt_t *o, int64_t l_pac, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len,
                           const uint8_t *fwd, int l_query, const uint8_t *query,
                           int n_chains, const chain_rec_t *chains, const chain_seed_t *cseeds,

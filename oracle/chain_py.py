@@ -64,6 +64,10 @@ def _bind_oracle():
     L.chain_oracle_read.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, C.c_uint32, _vp, _vp, _vp, C.c_int,
                                     C.POINTER(C.c_int32), _vp, _vp]
     L.chain_oracle_read.restype = C.c_int
+    L.chain_oracle_read_any.argtypes = L.chain_oracle_read.argtypes
+    L.chain_oracle_read_any.restype = C.c_int
+    L.chain_oracle_flt_seeds.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]
+    L.chain_oracle_flt_seeds.restype = C.c_int
     L.chain2aln_oracle_read.argtypes = [C.POINTER(ChainOpt), C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp,
                                         C.POINTER(C.c_int32), _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_uint64]
     L.chain2aln_oracle_read.restype = C.c_int
@@ -72,15 +76,23 @@ def _bind_oracle():
     return L
 
 
-def oracle_chains(opt, ctg: Contigs, l_query, rbeg, qq, score, layout_all):
-    """mem_chain + mem_chain_flt of one read -> (chains[CHAIN_DT], seeds[CSEED_DT])"""
+def oracle_chains(opt, ctg: Contigs, l_query, rbeg, qq, score, layout_all, fwd=None, query=None):
+    """mem_chain + mem_chain_flt of one read -> (chains[CHAIN_DT], seeds[CSEED_DT]); with the reference and the read given, a read long enough
+    for mem_flt_chained_seeds to run goes through it as well (mem_seed_sw on every chained seed), otherwise such a read raises"""
     L = _bind_oracle()
     n = len(rbeg)
     rbeg = np.ascontiguousarray(rbeg, dtype=np.uint64); qq = np.ascontiguousarray(qq, dtype=np.int32); score = np.ascontiguousarray(score, dtype=np.uint32)
     chains = np.zeros(max(n, 1), dtype=CHAIN_DT); cs = np.zeros(max(n, 1), dtype=CSEED_DT)
     nc = C.c_int32(0)
-    rc = L.chain_oracle_read(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(ctg.alt), l_query, n, _ptr(rbeg), _ptr(qq),
-                             _ptr(score), int(layout_all), C.byref(nc), _ptr(chains), _ptr(cs))
+    args = (C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(ctg.alt), l_query, n, _ptr(rbeg), _ptr(qq),
+            _ptr(score), int(layout_all), C.byref(nc), _ptr(chains), _ptr(cs))
+    rc = L.chain_oracle_read(*args)
+    if rc == -2 and fwd is not None and query is not None:
+        rc = L.chain_oracle_read_any(*args)
+        if rc == 0:
+            q = np.ascontiguousarray(query, dtype=np.uint8)
+            ran = L.chain_oracle_flt_seeds(C.byref(opt), ctg.l_pac, ctg.n, _ptr(ctg.off), _ptr(ctg.len), _ptr(fwd), l_query, _ptr(q), nc.value, _ptr(chains), _ptr(cs))
+            assert ran == 1
     if rc:
         raise RuntimeError(f"chain_oracle_read rc={rc}")
     chains = chains[:nc.value]
@@ -198,7 +210,7 @@ def oracle_align_batch(opt, ctg: Contigs, fwd, reads, rbeg, qq, score, n_seeds, 
     per = []
     for r, query in enumerate(reads):
         so, ns = int(seed_off[r]), int(n_seeds[r])
-        oc, osd = oracle_chains(opt, ctg, len(query), rbeg[so:so + ns], qq[so:so + ns], score[so:so + ns], layout_all)
+        oc, osd = oracle_chains(opt, ctg, len(query), rbeg[so:so + ns], qq[so:so + ns], score[so:so + ns], layout_all, fwd, query)
         regs, jobs, seqs = oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
         per.append((oc, osd, regs, jobs, seqs))
     out = dict(n_chains=np.array([len(p[0]) for p in per], np.uint32), n_regions=np.array([len(p[2]) for p in per], np.uint32),
