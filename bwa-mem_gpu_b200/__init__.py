@@ -111,7 +111,7 @@ SYMBOLS = [
     "bwa_b200_seed_device_smems", "bwa_b200_seeder_launches", "bwa_b200_seeder_request_counts", "bwa_b200_seed_params_default", "bwa_b200_measure_random_sector_gbs", "bwa_b200_measure_int_alu", "bwa_b200_int_alu_op_name", "bwa_b200_ext_params_default", "bwa_b200_fill_scmat",
     "bwa_b200_extender_create", "bwa_b200_extender_destroy", "bwa_b200_extend_async", "bwa_b200_extend_query",
     "bwa_b200_extend_wait", "bwa_b200_extend_async_paged", "bwa_b200_extend_device", "bwa_b200_pack_device", "bwa_b200_extender_stream",
-    "bwa_b200_extender_launches", "bwa_b200_extender_last_cells",
+    "bwa_b200_extender_launches", "bwa_b200_extender_last_cells", "bwa_b200_extender_last_closed_form", "bwa_b200_extender_set_closed_form",
     "bwa_b200_index_attach_ref", "bwa_b200_pipeline_create", "bwa_b200_pipeline_destroy", "bwa_b200_seed_extend_host",
     "bwa_b200_seed_extend_device", "bwa_b200_pipeline_sync", "bwa_b200_pipeline_stream", "bwa_b200_pipeline_launches",
     "bwa_b200_pipeline_totals", "bwa_b200_pipeline_profile", "bwa_b200_pipeline_kernel_times",
@@ -169,7 +169,7 @@ class Alignments(C.Structure):
 
 class AlignView(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_reads", "n_regions", "n_jobs_short", "n_jobs_long", "n_seeds", "cells")] + \
-               [(k, C.c_void_p) for k in ("n_regions_per_read", "region_off", "regions")]
+               [(k, C.c_void_p) for k in ("n_regions_per_read", "region_off", "regions")] + [("closed_form_jobs", C.c_uint64)]
 
 
 _lib = None
@@ -249,6 +249,9 @@ def lib():
         L.bwa_b200_extender_launches.restype = C.c_uint64
         L.bwa_b200_extender_last_cells.argtypes = [vp]
         L.bwa_b200_extender_last_cells.restype = C.c_uint64
+        L.bwa_b200_extender_last_closed_form.argtypes = [vp]
+        L.bwa_b200_extender_last_closed_form.restype = C.c_uint64
+        L.bwa_b200_extender_set_closed_form.argtypes = [vp, C.c_int]
         L.bwa_b200_index_attach_ref.argtypes = [vp, vp, C.c_uint64]
         L.bwa_b200_pipeline_create.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(vp)]
         L.bwa_b200_pipeline_destroy.argtypes = [vp]
@@ -512,6 +515,13 @@ class Extender:
 
     def last_cells(self) -> int:
         return int(lib().bwa_b200_extender_last_cells(self.h))
+
+    def last_closed_form(self) -> int:
+        """jobs of the last batch answered in closed form (not in last_cells)"""
+        return int(lib().bwa_b200_extender_last_closed_form(self.h))
+
+    def set_closed_form(self, on: bool):
+        check(lib().bwa_b200_extender_set_closed_form(self.h, int(on)))
 
     def destroy(self):
         if self.h:

@@ -43,9 +43,24 @@ struct Scratch {       // per-seed-slot working arrays of chain_core.cuh
 
 struct SeedView { const uint64_t *rbeg; const int32_t *qq; const uint32_t *score; const uint32_t *n_seeds; const uint64_t *seed_off; uint64_t cap; int layout_all; };
 
+// regions, job counts and sequence words of a read whose kept chains stand in W: the tail of chain_kernel / chain_long_kernel
+__device__ __forceinline__ void read_regions(const bwa_b200_chain_params_t &P, const Contigs &ctg, const Scratch &W, uint64_t so, int nc, int l_query, uint32_t r, Cnt &c)
+{
+    AlnIO ao{l_query, nc, W.chains + so, W.cseeds + so, W.srt + so, W.regs + so};
+    int n_short = 0, n_long = 0;
+    const int nr = chain2aln_read(P, ctg, ao, &n_short, &n_long);
+    c.regs = (uint64_t)nr; c.chains = (uint64_t)nc; c.n_short = (uint64_t)n_short; c.n_long = (uint64_t)n_long;
+    // after mem_flt_chained_seeds a chain's seeds are seed_off .. seed_off + n; the detail copy takes the packed prefix
+    c.cseeds = nc ? (uint64_t)(W.chains[so + nc - 1].seed_off + W.chains[so + nc - 1].n) : 0;
+    read_jobs(W.regs + so, nr, l_query, r, ctg.l_pac, [&](int, int is_long, uint32_t ql, uint32_t tl, uint32_t, const JobAux &) {
+        const uint64_t qw = (ql + 7) >> 3, tw = (tl + 7) >> 3;
+        if (is_long) { c.qw_long += qw; c.tw_long += tw; } else { c.qw_short += qw; c.tw_short += tw; }
+    });
+}
+
 __global__ void __launch_bounds__(128)
 chain_kernel(uint32_t n_reads, bwa_b200_chain_params_t P, Contigs ctg, SeedView S, const uint32_t *__restrict__ read_len,
-             Scratch W, Cnt *__restrict__ cnt, int *__restrict__ err, uint32_t *__restrict__ skipped)
+             Scratch W, Cnt *__restrict__ cnt, int *__restrict__ err, uint32_t *__restrict__ long_reads)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -58,20 +73,56 @@ chain_kernel(uint32_t n_reads, bwa_b200_chain_params_t P, Contigs ctg, SeedView 
                   W.ch + so, W.nxt + so, W.sq + 2 * so, W.ord + so, W.kidx + so, W.nodes + (so / 3 + 4ull * r), nodes_needed(ns),
                   W.chains + so, W.cseeds + so};
         int nc = chain_read(P, ctg, io);
-        if (nc == -2) skipped[atomicAdd(err + 1, 1)] = r;       // the read needs mem_seed_sw: reported to the caller, no regions, the batch goes on
-        else if (nc < 0) atomicMax(err, 2);
-        if (nc < 0) nc = 0;
-        AlnIO ao{l_query, nc, W.chains + so, W.cseeds + so, W.srt + so, W.regs + so};
-        int n_short = 0, n_long = 0;
-        const int nr = chain2aln_read(P, ctg, ao, &n_short, &n_long);
-        c.regs = (uint64_t)nr; c.chains = (uint64_t)nc; c.n_short = (uint64_t)n_short; c.n_long = (uint64_t)n_long;
-        for (int i = 0; i < nc; ++i) c.cseeds += (uint64_t)W.chains[so + i].n;
-        read_jobs(W.regs + so, nr, l_query, r, ctg.l_pac, [&](int, int is_long, uint32_t ql, uint32_t tl, uint32_t, const JobAux &) {
-            const uint64_t qw = (ql + 7) >> 3, tw = (tl + 7) >> 3;
-            if (is_long) { c.qw_long += qw; c.tw_long += tw; } else { c.qw_short += qw; c.tw_short += tw; }
-        });
+        if (nc < 0) { atomicMax(err, 2); nc = 0; }
+        if (nc > 0 && flt_seeds_applies(P, l_query)) {          // mem_flt_chained_seeds acts on this read: seedsw_kernel + chain_long_kernel finish it
+            long_reads[atomicAdd(err + 1, 1)] = r;
+            c.chains = (uint64_t)nc;
+        } else read_regions(P, ctg, W, so, nc, l_query, r, c);
     }
     cnt[r] = c;
+}
+
+// mem_seed_sw for every chain seed of the long reads chain_kernel listed: one block per read, one seed per lane at a time, the
+// alignment's state (H, E, the query window: 1000 bytes per lane) in shared memory at lane stride
+constexpr int SEEDSW_NT = 64;
+constexpr size_t SEEDSW_SMEM = (size_t)SEEDSW_NT * SEEDSW_MAX * 5;
+__global__ void __launch_bounds__(SEEDSW_NT)
+seedsw_kernel(const int *__restrict__ err, const uint32_t *__restrict__ long_reads, bwa_b200_chain_params_t P, Contigs ctg,
+              const uint64_t *__restrict__ seed_off, const uint32_t *__restrict__ read_len, const uint32_t *__restrict__ pac,
+              const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off, Scratch W, const Cnt *__restrict__ cnt)
+{
+    extern __shared__ int16_t sw_sm[];
+    int16_t *H = sw_sm + threadIdx.x, *E = H + SEEDSW_NT * SEEDSW_MAX;
+    uint8_t *qs = (uint8_t *)(sw_sm + 2 * SEEDSW_NT * SEEDSW_MAX) + threadIdx.x;
+    const uint32_t n_long = (uint32_t)err[1];
+    for (uint32_t k = blockIdx.x; k < n_long; k += gridDim.x) {
+        const uint32_t r = long_reads[k];
+        const uint64_t so = seed_off[r];
+        const int nc = (int)cnt[r].chains;
+        const int n_cs = W.chains[so + nc - 1].seed_off + W.chains[so + nc - 1].n;
+        const uint32_t *rd = packed_reads + word_off[r];
+        for (int i = threadIdx.x; i < n_cs; i += SEEDSW_NT) {
+            bwa_b200_chain_seed_t &s = W.cseeds[so + i];
+            s.score = seed_sw(P, ctg, pac, rd, (int)read_len[r], s, H, E, qs, SEEDSW_NT);
+        }
+    }
+}
+
+// one lane per long read: the filter on the scored seeds, then what chain_kernel does for the other reads
+__global__ void __launch_bounds__(64)
+chain_long_kernel(const int *__restrict__ err, const uint32_t *__restrict__ long_reads, bwa_b200_chain_params_t P, Contigs ctg,
+                  const uint64_t *__restrict__ seed_off, const uint32_t *__restrict__ read_len, Scratch W, Cnt *__restrict__ cnt)
+{
+    const uint32_t n_long = (uint32_t)err[1];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_long; k += gridDim.x * blockDim.x) {
+        const uint32_t r = long_reads[k];
+        const uint64_t so = seed_off[r];
+        const int nc = (int)cnt[r].chains, l_query = (int)read_len[r];
+        flt_seeds_apply(P, l_query, nc, W.chains + so, W.cseeds + so);
+        Cnt c{0, 0, 0, 0, 0, 0, 0, 0, 0};
+        read_regions(P, ctg, W, so, nc, l_query, r, c);
+        cnt[r] = c;
+    }
 }
 
 __global__ void total_kernel(uint32_t n_reads, const Cnt *cnt, const Cnt *off, Cnt *tot) { *tot = CntAdd()(off[n_reads - 1], cnt[n_reads - 1]); }
@@ -239,9 +290,10 @@ struct bwa_b200_aligner {
     Cnt *d_cnt = nullptr, *d_off = nullptr, *d_tot = nullptr, *h_tot = nullptr;
     uint32_t *d_nregs = nullptr, *d_nchains = nullptr; uint64_t *d_region_off = nullptr, *d_chain_off = nullptr, *d_cseed_off = nullptr;
     void *d_cub = nullptr; size_t cub_bytes = 0;
-    int *d_err = nullptr, *h_err = nullptr;          // [0] internal error, [1] reads left to the caller (mem_seed_sw), [2] compact boundary
-    uint32_t *d_skipped = nullptr;
-    std::vector<uint32_t> skipped;                   // their indexes in the last batch, ascending
+    int *d_err = nullptr, *h_err = nullptr;          // [0] internal error, [1] reads listed in d_long (mem_flt_chained_seeds acts on them), [2] compact boundary
+    uint32_t *d_long = nullptr;
+    std::vector<uint32_t> skipped;                   // always empty since mem_seed_sw runs on the device (kept for the ABI)
+    uint64_t n_long_reads = 0;
     // outputs
     bwa_b200_region_t *d_regions = nullptr; uint64_t region_cap = 0;
     bwa_b200_chain_t *d_chains = nullptr; uint64_t chain_cap = 0;
@@ -255,6 +307,7 @@ struct bwa_b200_aligner {
     // last batch
     uint64_t b_n = 0, b_seeds = 0, b_cells = 0;
     int64_t b_max_len = -1;          // longest read of the batch when the caller knows it (bounds the extension jobs)
+    uint32_t b_read_max = 0;         // longest read of the batch, 0 = unknown (decides whether the mem_seed_sw kernels are launched)
     Cnt b_tot{};
     bool b_detail = false;
     uint64_t launches = 0;
@@ -331,7 +384,8 @@ extern "C" int bwa_b200_aligner_create(const bwa_b200_index_t *idx, uint64_t max
     B200_CUDA(cudaMalloc(&a->d_region_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_chain_off, max_reads * 8)); B200_CUDA(cudaMalloc(&a->d_cseed_off, max_reads * 8));
     B200_CUDA(cudaMalloc(&a->d_err, 16)); B200_CUDA(cudaMemset(a->d_err, 0, 16)); B200_CUDA(cudaHostAlloc(&a->h_err, 16, cudaHostAllocDefault));
     a->h_err[0] = a->h_err[1] = a->h_err[2] = a->h_err[3] = 0;
-    B200_CUDA(cudaMalloc(&a->d_skipped, (max_reads ? max_reads : 1) * 4));
+    B200_CUDA(cudaMalloc(&a->d_long, (max_reads ? max_reads : 1) * 4));
+    B200_CUDA(cudaFuncSetAttribute(seedsw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEEDSW_SMEM));
     B200_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, a->cub_bytes, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)max_reads, a->stream));
     {   // the compact boundary scans word counts with the same scratch
         size_t b2 = 0;
@@ -361,7 +415,7 @@ extern "C" void bwa_b200_aligner_destroy(bwa_b200_aligner_t *a)
     cudaFree(a->W.chains); cudaFree(a->W.cseeds); cudaFree(a->W.regs);
     cudaFree(a->d_cnt); cudaFree(a->d_off); cudaFree(a->d_tot); cudaFreeHost(a->h_tot);
     cudaFree(a->d_nregs); cudaFree(a->d_nchains); cudaFree(a->d_region_off); cudaFree(a->d_chain_off); cudaFree(a->d_cseed_off);
-    cudaFree(a->d_cub); cudaFree(a->d_err); cudaFree(a->d_skipped); cudaFreeHost(a->h_err);
+    cudaFree(a->d_cub); cudaFree(a->d_err); cudaFree(a->d_long); cudaFreeHost(a->h_err);
     cudaFree(a->d_regions); cudaFree(a->d_chains); cudaFree(a->d_cseeds);
     cudaFree(a->J.qoff); cudaFree(a->J.qlen); cudaFree(a->J.toff); cudaFree(a->J.tlen); cudaFree(a->J.h0); cudaFree(a->J.aux);
     cudaFree(a->d_res); cudaFree(a->d_qp); cudaFree(a->d_tp);
@@ -406,7 +460,15 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         int rc = aligner_ensure_slots(a, S.cap);
         if (rc) return rc;
         B200_CUDA(cudaMemsetAsync(a->d_err, 0, 8, st));      // also before the retry: attempt 0 may have chained incomplete seed arrays
-        B200_LAUNCH(prof, "chain_kernel", st, (chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, *cp, ctg, S, d_len, a->W, a->d_cnt, a->d_err, a->d_skipped)));
+        B200_LAUNCH(prof, "chain_kernel", st, (chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, *cp, ctg, S, d_len, a->W, a->d_cnt, a->d_err, a->d_long)));
+        if (a->b_read_max == 0 || flt_seeds_applies(*cp, (int)a->b_read_max)) {     // a batch that may hold reads mem_flt_chained_seeds acts on (length unknown: 0)
+            const unsigned g = (unsigned)std::min<uint64_t>(n, (uint64_t)a->seeder->n_sm * 3);
+            B200_LAUNCH(prof, "seedsw_kernel", st, (seedsw_kernel<<<g, SEEDSW_NT, SEEDSW_SMEM, st>>>(a->d_err, a->d_long, *cp, ctg, S.seed_off, d_len, a->idx->d_pac,
+                                                                                                 d_packed, d_woff, a->W, a->d_cnt)));
+            B200_LAUNCH(prof, "chain_long_kernel", st, (chain_long_kernel<<<(unsigned)std::min<uint64_t>((n + 63) / 64, (uint64_t)a->seeder->n_sm * 8), 64, 0, st>>>(
+                                                            a->d_err, a->d_long, *cp, ctg, S.seed_off, d_len, a->W, a->d_cnt)));
+            a->launches += 2;
+        }
         size_t tmp = a->cub_bytes;
         if (prof) prof->begin("chain_scan", st);
         B200_CUDA(cub::DeviceScan::ExclusiveScan(a->d_cub, tmp, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)n, st));
@@ -431,12 +493,7 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         b200::set_error("align: internal capacity exceeded while chaining a read");
         return BWA_B200_ERR_CAPACITY;
     }
-    if (a->h_err[1] > 0) {       // reads long enough for mem_flt_chained_seeds to run mem_seed_sw (about 757 bases and more): left to the caller
-        a->skipped.resize((size_t)a->h_err[1]);
-        B200_CUDA(cudaMemcpyAsync(a->skipped.data(), a->d_skipped, a->skipped.size() * 4, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaStreamSynchronize(st));
-        std::sort(a->skipped.begin(), a->skipped.end());
-    }
+    a->n_long_reads = (uint64_t)a->h_err[1];      // reads that went through mem_flt_chained_seeds on the device
     const Cnt T = *a->h_tot;
     a->b_tot = T; a->b_n = n_reads; a->b_detail = detail; a->b_cells = 0;
     const uint64_t n_jobs = T.n_short + T.n_long, qw = T.qw_short + T.qw_long, tw = T.tw_short + T.tw_long;
@@ -494,7 +551,7 @@ extern "C" int bwa_b200_align_device(bwa_b200_aligner_t *a, const uint32_t *dev_
     b200::Prof *prof = a->profiling ? &a->prof : nullptr;
     a->seeder->prof = prof;
     if (prof) prof->reset();
-    a->b_max_len = (int64_t)max_read_len;
+    a->b_max_len = (int64_t)max_read_len; a->b_read_max = max_read_len;
     int rc = b200_seeder_run(a->seeder, dev_packed, dev_word_off, dev_read_len, n_reads, max_read_len, sp);
     if (rc) return rc;
     return aligner_run(a, SeedView{}, true, dev_packed, dev_word_off, dev_read_len, n_reads, cp, ep, a->b_detail);
@@ -514,6 +571,7 @@ extern "C" int bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_
     memset(v, 0, sizeof(*v));
     v->n_reads = a->b_n; v->n_regions = a->b_tot.regs; v->n_jobs_short = a->b_tot.n_short; v->n_jobs_long = a->b_tot.n_long; v->n_seeds = a->b_seeds;
     v->cells = a->b_n && (a->b_tot.n_short + a->b_tot.n_long) ? bwa_b200_extender_last_cells(a->ext) : 0;
+    v->closed_form_jobs = v->cells || (a->b_n && (a->b_tot.n_short + a->b_tot.n_long)) ? a->ext->h_cells[1] : 0;
     v->n_regions_per_read = a->d_nregs; v->region_off = a->d_region_off; v->regions = a->d_regions;
     return BWA_B200_OK;
 }
@@ -650,6 +708,7 @@ extern "C" int bwa_b200_align_seeds_host(bwa_b200_aligner_t *a, const uint32_t *
     uint32_t max_len = 0;
     int rc = aligner_upload_reads(a, packed, word_off, read_len, n_reads, &max_len);
     if (rc) return rc;
+    a->b_read_max = max_len;
     a->b_max_len = -1;            // given seeds: a seed's score (h0) is the caller's, not bounded by the read length
     const uint64_t ns = seeds->n_seeds;
     if (ns > a->g_cap || !a->g_rbeg) {

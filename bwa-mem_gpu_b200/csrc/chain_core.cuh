@@ -17,11 +17,14 @@
 #include <stdint.h>
 #include <math.h>
 #include "bwamem_b200.h"
+#include "sw_core.cuh"
 
 #ifdef __CUDACC__
 #define CH_FN __host__ __device__ inline
+#define CH_DEV __device__ inline
 #else
 #define CH_FN static inline
+#define CH_DEV static inline
 #endif
 
 namespace b200chain {
@@ -261,15 +264,11 @@ CH_FN void flt_introsort(const ReadIO &io, int32_t *a, int n)
 
 // ------------------------------------------------------------------------------------ mem_chain + mem_chain_flt
 // Returns the number of chains kept (written to io.chains / io.cseeds in the reference's final order), or
-//   -2  the read is long enough for mem_flt_chained_seeds to run mem_seed_sw (not on this path)
 //   -3  internal capacity (node pool / traversal depth)
+// A read for which flt_seeds_applies() holds goes through seed_sw / flt_seeds_apply before chain2aln_read.
 CH_FN int chain_read(const bwa_b200_chain_params_t &P, const Contigs &ctg, const ReadIO &io)
 {
     if (io.l_query < P.min_seed_len || io.ns == 0) return 0;
-    {   // mem_flt_chained_seeds returns at once for short reads, src/bwamem.c:972-977
-        const double min_l = P.min_chain_weight ? 1.1f * P.min_chain_weight : 5.5f * log((double)io.l_query);
-        if (!(min_l > 0.05f * io.l_query)) return -2;
-    }
     Tree bt;
     bt.nd = io.nodes; bt.ch = io.ch; bt.n_nodes = 0; bt.cap = io.n_node_cap;
     bt.root = kb_new(bt, 0);
@@ -403,6 +402,75 @@ CH_FN int chain_read(const bwa_b200_chain_params_t &P, const Contigs &ctg, const
         }
     }
     return n_kept;
+}
+
+// ------------------------------------------------------------------------------------ mem_flt_chained_seeds
+// src/bwamem.c:970-990: reads long enough that 5.5 ln L <= 0.05 L (757 bases at the defaults) have every seed of every kept chain
+// scored by a local alignment of the read around the seed against the reference around it (mem_seed_sw, :774-808); seeds scoring below
+// min_HSP_score leave their chain.  The three steps are separate so that the alignments of a read run on as many lanes as it has seeds:
+// flt_seeds_applies (per read), seed_sw (per seed, independent), flt_seeds_apply (per read, sequential).
+CH_FN double flt_min_l(const bwa_b200_chain_params_t &P, int l_query)
+{ return P.min_chain_weight ? 1.1f * P.min_chain_weight : 5.5f * log((double)l_query); }
+CH_FN bool flt_seeds_applies(const bwa_b200_chain_params_t &P, int l_query) { return !(flt_min_l(P, l_query) > 0.05f * l_query); }
+
+constexpr int SEEDSW_MAX = 200;          // MEM_SHORT_LEN: windows of 200 bases and more are not aligned
+constexpr int SEEDSW_EXT = 50;           // MEM_SHORT_EXT
+
+CH_FN int pac_base(const uint32_t *pac, int64_t f) { return (int)((pac[f >> 4] >> (30 - ((f & 15) << 1))) & 3u); }
+CH_FN int text_base(const uint32_t *pac, int64_t l_pac, int64_t p) { return p < l_pac ? pac_base(pac, p) : 3 - pac_base(pac, (l_pac << 1) - 1 - p); }
+CH_FN int read_base(const uint32_t *rd, int p) { const int c = (int)((rd[p >> 3] >> (28 - ((p & 7) << 2))) & 15u); return c > 4 ? 4 : c; }
+
+struct SeedSwQ { const uint8_t *q; size_t NS; SW_MEM int operator()(int i) const { return q[(size_t)i * NS]; } };
+struct SeedSwT { const uint32_t *pac; int64_t l_pac, rb; SW_MEM int operator()(int i) const { return text_base(pac, l_pac, rb + i); } };
+
+// mem_seed_sw: the score of ksw_align2(query window, reference window, KSW_XSTART), or -1 when the seed or a window reaches 200 bases.
+// H, E: 200 int16 each, qs: 200 bytes, all at element stride NS (per-lane state of the caller).
+CH_DEV int seed_sw(const bwa_b200_chain_params_t &P, const Contigs &ctg, const uint32_t *pac, const uint32_t *rd, int l_query,
+                   const bwa_b200_chain_seed_t &s, int16_t *H, int16_t *E, uint8_t *qs, size_t NS)
+{
+    if (s.len >= SEEDSW_MAX) return -1;
+    int qb = s.qbeg - SEEDSW_EXT, qe = s.qbeg + s.len + SEEDSW_EXT;
+    int64_t rb = s.rbeg - SEEDSW_EXT, re = s.rbeg + s.len + SEEDSW_EXT;
+    const int64_t mid = (s.rbeg + s.rbeg + s.len) >> 1, l2 = ctg.l_pac << 1;
+    qb = qb > 0 ? qb : 0; qe = qe < l_query ? qe : l_query;
+    rb = rb > 0 ? rb : 0; re = re < l2 ? re : l2;
+    if (rb < ctg.l_pac && ctg.l_pac < re) { if (mid < ctg.l_pac) re = ctg.l_pac; else rb = ctg.l_pac; }
+    if (qe - qb >= SEEDSW_MAX || re - rb >= SEEDSW_MAX) return -1;
+    {   // bns_fetch_seq, src/bntseq.c:531-552: the window is cut to the contig that holds mid
+        int is_rev;
+        const int rid = pos2rid(ctg, depos(ctg, mid, &is_rev));
+        int64_t far_beg = ctg.off[rid], far_end = far_beg + ctg.len[rid];
+        if (is_rev) { const int64_t t = far_beg; far_beg = l2 - far_end; far_end = l2 - t; }
+        rb = rb > far_beg ? rb : far_beg; re = re < far_end ? re : far_end;
+    }
+    SwParams S;
+    {   // bwa_fill_scmat, src/bwa.c:93-105
+        int k = 0;
+        for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) S.mat[k++] = (int8_t)(i == j ? P.a : -P.b); S.mat[k++] = -1; }
+        for (int j = 0; j < 5; ++j) S.mat[k++] = -1;
+    }
+    S.m = 5; S.o_del = P.o_del; S.e_del = P.e_del; S.o_ins = P.o_ins; S.e_ins = P.e_ins;
+    for (int k = 0; k < qe - qb; ++k) qs[(size_t)k * NS] = (uint8_t)read_base(rd, qb + k);
+    return sw_i16_score(qe - qb, SeedSwQ{qs, NS}, (int)(re - rb), SeedSwT{pac, ctg.l_pac, rb}, S, H, E, NS);
+}
+
+// the filter itself, on chains whose seeds carry seed_sw's result in .score: kept seeds packed chain after chain
+CH_FN void flt_seeds_apply(const bwa_b200_chain_params_t &P, int l_query, int n_chains, bwa_b200_chain_t *chains, bwa_b200_chain_seed_t *cseeds)
+{
+    const int min_HSP_score = (int)(P.a * flt_min_l(P, l_query) + .499);
+    int so = 0;
+    for (int i = 0; i < n_chains; ++i) {
+        const bwa_b200_chain_seed_t *sd = cseeds + chains[i].seed_off;
+        const int first = so, n = chains[i].n;
+        for (int j = 0; j < n; ++j) {
+            bwa_b200_chain_seed_t s = sd[j];
+            if (s.score < 0 || s.score >= min_HSP_score) {
+                s.score = s.score < 0 ? s.len * P.a : s.score;
+                cseeds[so++] = s;
+            }
+        }
+        chains[i].n = so - first; chains[i].seed_off = first;
+    }
 }
 
 // ------------------------------------------------------------------------------------ mem_chain2aln

@@ -122,6 +122,69 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
     return ring ? ring : full;
 }
 
+// ---- jobs answered in closed form -----------------------------------------------------------------------------------------------
+// An extension job whose query equals the head of its target except, possibly, in its first base -- what is left of a read beside a
+// maximal exact match when the read has no further difference on that side -- needs no matrix: with match score a, mismatch -b and
+// g = min(o_del + e_del, o_ins + e_ins) > a + b, the diagonal cell of row i is D(i) = h0 - mm (a + b) + (i + 1) a  (mm = 1 when the first
+// bases differ) and is the strict maximum of its row and of the last column:
+//   * every path to a cell (i, j), j != i, holds a gap and at most min(i, j) + 1 matches, so it scores at most
+//     h0 + (min(i, j) + 1) a - g < D(i); a path to (i, i) other than the diagonal holds an insertion and a deletion;
+//   * D(i) > 0 for every i as long as h0 > b, so `M = M ? M + s : 0` (src/ksw.c:924) never cuts the diagonal, the cell after a
+//     non-zero cell is always inside [beg, end) (src/ksw.c:959-965) and, with w >= 0, inside the band (:902-907);
+//   * the running maximum starts at h0 (:896) and moves only on m > max (:947): from row k = b / a + 1 on when mm = 1 (each such row
+//     with mj = i, so max_off stays 0), from row 0 on when mm = 0; a query of at most k bases leaves max = h0, max_i = max_j = -1;
+//   * the z-drop test (:950-957) is reached only in rows 0 .. k - 1 of the mm = 1 case with max - m = (a + b) - (i + 1) a <= b, so it
+//     cannot fire when zdrop <= 0 or b <= zdrop; rows after the last query row score at most h0 + qlen a - g < max and change nothing.
+// Hence score = gscore = D(qlen - 1), qle = tle = gtle = qlen, max_off = 0 (score = h0, qle = tle = 0 for the short case).  Sequences
+// with a base outside A/C/G/T, targets shorter than the query, h0 <= b and parameter sets outside the conditions go to the kernels.
+struct ClosedParams { int32_t ok, a, b; };
+static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
+{
+    ClosedParams C{0, 0, 0};
+    const int a = p->mat[0], b = -p->mat[1];
+    if (a < 1 || b < 1) return C;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (p->mat[i * 5 + j] != (i == j ? a : -b)) return C;
+    const int oe_del = p->o_del + p->e_del, oe_ins = p->o_ins + p->e_ins, g = oe_del < oe_ins ? oe_del : oe_ins;
+    if (p->e_del < 1 || p->e_ins < 1 || g <= a + b) return C;
+    if (p->use_band && p->w < 0) return C;
+    if (p->zdrop > 0 && b > p->zdrop) return C;
+    C.ok = 1; C.a = a; C.b = b;
+    return C;
+}
+template <bool BYTES>
+B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t a, bwa_b200_ext_result_t *r)
+{
+    const uint32_t ql = J.qlen[a], tl = J.tlen[a];
+    const int h0 = (int)J.h0[a];
+    if (!C.ok || ql == 0 || tl < ql || h0 <= C.b || ql > 0x00ffffffu || h0 > 0x00ffffff) return false;
+    int mm;
+    if (BYTES) {
+        const uint8_t *q = J.qb + J.qoff[a], *t = J.tb + J.toff[a];
+        if (q[0] > 3 || t[0] > 3) return false;
+        mm = q[0] != t[0];
+        for (uint32_t k = 1; k < ql; ++k) if (q[k] != t[k] || q[k] > 3) return false;
+    } else {
+        const uint32_t *q = J.qp + (J.qoff[a] >> 3), *t = J.tp + (J.toff[a] >> 3);
+        const uint32_t nw = (ql + 7) >> 3;
+        mm = (int)(((q[0] ^ t[0]) >> 28) != 0);
+        for (uint32_t w = 0; w < nw; ++w) {
+            const uint32_t qw = q[w], tw = t[w], rem = ql - 8 * w;
+            uint32_t x = (qw ^ tw) | ((qw | tw) & 0xccccccccu);          // a difference, or a code beyond 3, in some nibble
+            if (w == 0) x &= 0xcfffffffu;                                // the first base may differ (not be N)
+            if (rem < 8) x &= ~(0xffffffffu >> (4 * rem));
+            if (x) return false;
+        }
+    }
+    const int k = C.b / C.a + 1;
+    const int g = h0 - mm * (C.a + C.b) + (int)ql * C.a;
+    r->gscore = g; r->gtle = (int32_t)ql; r->max_off = 0;
+    if (mm == 0 || (int)ql - 1 >= k) { r->score = g; r->qle = (int32_t)ql; r->tle = (int32_t)ql; }
+    else { r->score = h0; r->qle = 0; r->tle = 0; }
+    return true;
+}
+
 // One column pair (2p, 2p+1) of row i.  SEL: low 16 bits = the two PRMT selector bytes of the pair.
 //   Hd   = {H(i-1,2p-1), H(i-1,2p)}                     the diagonal of both columns
 //   M    = min(Hd + score, Hd * 32)                      `M = M ? M + s : 0` (src/ksw.c:924): Hd == 0 gives M <= 0,

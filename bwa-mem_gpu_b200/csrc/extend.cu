@@ -51,22 +51,33 @@ constexpr uint32_t CLS_BIT = 1u << 19;   // key bits 19-20 = the job's class: 0 
 constexpr uint32_t CLS_WAVE = 2u << 19;  // (one job per warp, s16x2), 3 ext_intra_kernel (one job per warp, int32, no band needed)
 constexpr uint32_t CLS_INTRA = 3u << 19;
 
+constexpr uint32_t CLS_DONE = 4u << 19;  // answered by key_kernel in closed form (closed_form_job): sorted behind every kernel's range
+
 // sort key: query length | class << 19.  Class 0: eligible for the column-pair s16x2 kernel (score bound at most 1023, query at most
 // 512, eligible matrix / penalties); 2: ext_wave_kernel (banded batch, query of WAVE_MIN_Q + 1 .. 65535 bases, score bound at most
-// WAVE_MAX_SCORE); 1: the 32-bit per-lane kernel (query at most 1024, scores below 2^15); 3: ext_intra_kernel (everything else)
-__global__ void key_kernel(uint32_t n, const uint32_t *qlen, const uint32_t *h0, int max_score, int simd_ok, int wave_ok, uint32_t *keys, uint32_t *vals)
+// WAVE_MAX_SCORE); 1: the 32-bit per-lane kernel (query at most 1024, scores below 2^15); 3: ext_intra_kernel (everything else);
+// 4: the job's result is written here (counted in counters[1]) and no kernel sees it
+template <bool BYTES>
+__global__ void key_kernel(uint32_t n, JobView J, ClosedParams C, int max_score, int simd_ok, int wave_ok, uint32_t *keys, uint32_t *vals,
+                           bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ counters)
 {
     uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    uint32_t q = qlen[a];
-    uint64_t bound = (uint64_t)h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
-    uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
-    if (simd_ok && bound <= (uint64_t)PAIR_MAX_SCORE && q <= (uint32_t)PAIR_MAX_Q) { }
-    else if (wave_ok && q > (uint32_t)WAVE_MIN_Q && q <= 0xffffu && bound <= (uint64_t)WAVE_MAX_SCORE) k |= CLS_WAVE;
-    else if (q <= 1024u && bound < 32767ull) k |= CLS_BIT;
-    else k |= CLS_INTRA;
-    keys[a] = k;
-    vals[a] = a;
+    bool done = false;
+    if (a < n) {
+        uint32_t q = J.qlen[a];
+        uint64_t bound = (uint64_t)J.h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
+        uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
+        bwa_b200_ext_result_t r;
+        if (C.ok && closed_form_job<BYTES>(C, J, a, &r)) { res[a] = r; k |= CLS_DONE; done = true; }
+        else if (simd_ok && bound <= (uint64_t)PAIR_MAX_SCORE && q <= (uint32_t)PAIR_MAX_Q) { }
+        else if (wave_ok && q > (uint32_t)WAVE_MIN_Q && q <= 0xffffu && bound <= (uint64_t)WAVE_MAX_SCORE) k |= CLS_WAVE;
+        else if (q <= 1024u && bound < 32767ull) k |= CLS_BIT;
+        else k |= CLS_INTRA;
+        keys[a] = k;
+        vals[a] = a;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, done);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 1, (unsigned long long)__popc(m));
 }
 
 // Sorted positions of the bin boundaries.  range[0..N_PBINS] bound the bins of the column-pair kernel (bin b =
@@ -80,11 +91,11 @@ __device__ __forceinline__ uint32_t lower_bound_key(const uint32_t *sorted_keys,
 __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *range, int *err_flag, int intra_ok)
 {
     const int k = threadIdx.x;
-    if (k > N_PBINS + N_BINS + 2) return;
+    if (k > N_PBINS + N_BINS + 3) return;
     uint32_t thr;
     if (k <= N_PBINS) thr = k == 0 ? 0u : (uint32_t)c_pbin_hi[k - 1] + 1u;
     else if (k <= N_PBINS + N_BINS + 1) thr = CLS_BIT | (k == N_PBINS + 1 ? 0u : (uint32_t)c_bin_hi[k - N_PBINS - 2] + 1u);
-    else thr = CLS_INTRA;
+    else thr = k == N_PBINS + N_BINS + 2 ? CLS_INTRA : CLS_DONE;          // the last slot: where the jobs no kernel takes begin
     const uint32_t lo = lower_bound_key(sorted_keys, n, thr);
     range[k] = lo;
     // class-0 keys beyond the last pair bin cannot exist (key_kernel); if one does, it is reported, not dropped
@@ -92,7 +103,7 @@ __global__ void range_kernel(uint32_t n, const uint32_t *sorted_keys, uint32_t *
     // keys at or beyond range[N_PBINS + N_BINS + 1] run one per warp: ext_wave_kernel up to range[N_PBINS + N_BINS + 2] (class 2 exists only
     // when that kernel is launched), ext_intra_kernel beyond; a caller that ruled the latter out (no slabs, no launch) and was wrong gets
     // an error, not missing results
-    if (k == N_PBINS + N_BINS + 2 && !intra_ok && lo < n) atomicExch(err_flag, 3);
+    if (k == N_PBINS + N_BINS + 2 && !intra_ok && lo < lower_bound_key(sorted_keys, n, CLS_DONE)) atomicExch(err_flag, 3);
 }
 
 // One DP cell.  State word p = H(i-1,j-1) | E(i,j) << 16.  The reference's `M = M ? M + s : 0`
@@ -267,7 +278,7 @@ ext_inter_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
 constexpr int INTRA_WARPS = 4;
 template <bool BYTES>
 __global__ void __launch_bounds__(INTRA_WARPS * 32)
-ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ first, uint32_t n,
+ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, const uint32_t *__restrict__ first,
                  int max_q, int2 *__restrict__ slab_all, bwa_b200_ext_result_t *__restrict__ res,
                  unsigned long long *__restrict__ cells_total, int *__restrict__ err_flag)
 {
@@ -279,6 +290,7 @@ ext_intra_kernel(ExtParams P, JobView J, const uint32_t *__restrict__ order, con
     int2 *const eh = slab_all + (uint64_t)gw * (uint64_t)(max_q + 1);      // eh[j] = {H(i-1,j-1), E(i,j)}
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     unsigned long long my_cells = 0;
+    const uint32_t n = first[1];                       // the jobs behind are answered already (CLS_DONE)
     for (uint32_t pos = *first + gw; pos < n; pos += n_warps) {
         const uint32_t a = order[pos];
         const int qlen = (int)J.qlen[a], tlen = (int)J.tlen[a], h0 = (int)J.h0[a];
@@ -558,8 +570,9 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
     }
     B200_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     B200_CUDA(cudaMalloc(&e->d_range, (N_PBINS + N_BINS + 4) * 4));
-    B200_CUDA(cudaMalloc(&e->d_cells, 8));
+    B200_CUDA(cudaMalloc(&e->d_cells, 16));
     B200_CUDA(cudaMalloc(&e->d_err, 4));
+    e->no_closed_form = getenv("BWA_B200_EXT_NO_CLOSED") != nullptr;
     e->intra_max_q = getenv("BWA_B200_EXT_INTRA_MAX_Q") ? atoi(getenv("BWA_B200_EXT_INTRA_MAX_Q")) : 16384;
     if (e->intra_max_q < 1024) e->intra_max_q = 1024;
     {   // a warp's row is one dependent chain of 32-column chunks (loads, scan, carries): with 4 warps per SM the kernel issued 17 % of
@@ -571,9 +584,9 @@ extern "C" int bwa_b200_extender_create(int device, uint64_t max_jobs, uint64_t 
         e->intra_grid = e->n_sm * occ;
     }
     // the slabs of ext_intra_kernel (0.47 GB on a 148-SM part) are allocated by the first batch that can reach that kernel (ext_launch)
-    B200_CUDA(cudaMemset(e->d_cells, 0, 8));
+    B200_CUDA(cudaMemset(e->d_cells, 0, 16));
     B200_CUDA(cudaMemset(e->d_err, 0, 4));
-    B200_CUDA(cudaHostAlloc(&e->h_cells, 8, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&e->h_cells, 16, cudaHostAllocDefault));
     B200_CUDA(cudaHostAlloc(&e->h_err, 4, cudaHostAllocDefault));
     *e->h_cells = 0; *e->h_err = 0;
     {   // dynamic shared memory opt-in: device limit minus the kernels' static shared memory
@@ -643,7 +656,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     ExtParams P;
     to_dev_params(p, &P);
     if (e->phase_prof) e->phase_prof->begin("ext_phase", e->stream);
-    B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 8, e->stream));
+    B200_CUDA(cudaMemsetAsync(e->d_cells, 0, 16, e->stream));
     if (e->prof) e->prof->begin("ext_sort", e->stream);
     // the column-pair s16x2 kernel takes any matrix with 0 < max <= 31 and one score for a query N
     // (bwa_fill_scmat, src/bwa.c, is of that form); any other matrix runs entirely in the 32-bit kernel
@@ -660,9 +673,11 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
         wave_smem = (size_t)WAVE_WARPS * SW.ring * 10 + 16;
         if (wave_smem > (size_t)e->smem_optin) wave_ok = false;
     }
-    key_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, J.qlen, J.h0, P.max_score, simd_ok, wave_ok ? 1 : 0, e->d_keys, e->d_vals);
+    ClosedParams CF = closed_params_from(p);
+    if (e->no_closed_form) CF.ok = 0;
+    key_kernel<BYTES><<<(n + 255) / 256, 256, 0, e->stream>>>(n, J, CF, P.max_score, simd_ok, wave_ok ? 1 : 0, e->d_keys, e->d_vals, d_res, e->d_cells);
     size_t tmp = e->cub_bytes;
-    B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 21, e->stream));
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub, tmp, e->d_keys, e->d_keys2, e->d_vals, e->d_order, (int)n, 0, 22, e->stream));
     range_kernel<<<1, 32, 0, e->stream>>>(n, e->d_keys2, e->d_range, e->d_err, may_intra ? 1 : 0);
     if (e->prof) e->prof->end(e->stream);
     e->launches += 3;
@@ -779,7 +794,7 @@ static int ext_launch(bwa_b200_extender *e, const bwa_b200_ext_params_t *p, uint
     if (may_intra) {   // one warp per job in int32 for what is left (no band, scores beyond 16 bits); exits at once when there is none
         cudaStream_t st = bin_stream();
         B200_LAUNCH(e->prof, "ext_intra_kernel", st,
-            (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + N_BINS + 2), n, e->intra_max_q,
+            (ext_intra_kernel<BYTES><<<e->intra_grid, INTRA_WARPS * 32, 0, st>>>(P, J, e->d_order, e->d_range + (N_PBINS + N_BINS + 2), e->intra_max_q,
                                                                                 e->d_intra, d_res, e->d_cells, e->d_err)));
         e->launches += 1;
     }
@@ -849,7 +864,7 @@ extern "C" int bwa_b200_extend_async_paged(bwa_b200_extender_t *e, const bwa_b20
         if (query_end) B200_CUDA(cudaMemcpyAsync(query_end, e->d_tri + e->max_jobs, n * 4ull, cudaMemcpyDeviceToHost, st));
         if (target_end) B200_CUDA(cudaMemcpyAsync(target_end, e->d_tri + 2 * e->max_jobs, n * 4ull, cudaMemcpyDeviceToHost, st));
     }
-    B200_CUDA(cudaMemcpyAsync(e->h_cells, e->d_cells, 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(e->h_cells, e->d_cells, 16, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaMemcpyAsync(e->h_err, e->d_err, 4, cudaMemcpyDeviceToHost, st));
     e->pending = true;
     return BWA_B200_OK;
@@ -895,9 +910,25 @@ extern "C" uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e)
 {
     if (!e) return 0;
     cudaSetDevice(e->device);
-    cudaMemcpyAsync(e->h_cells, e->d_cells, 8, cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->h_cells, e->d_cells, 16, cudaMemcpyDeviceToHost, e->stream);
     cudaStreamSynchronize(e->stream);
     return *e->h_cells;
+}
+
+extern "C" uint64_t bwa_b200_extender_last_closed_form(bwa_b200_extender_t *e)
+{
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaMemcpyAsync(e->h_cells, e->d_cells, 16, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    return e->h_cells[1];
+}
+
+extern "C" int bwa_b200_extender_set_closed_form(bwa_b200_extender_t *e, int enable)
+{
+    if (!e) return BWA_B200_ERR_ARG;
+    e->no_closed_form = !enable;
+    return BWA_B200_OK;
 }
 
 extern "C" int bwa_b200_extend_device(bwa_b200_extender_t *e, const bwa_b200_ext_params_t *p, uint64_t n_jobs,

@@ -111,6 +111,7 @@ struct bwa_b200_extender {
     bool own_stream = true;
     int2 *d_intra = nullptr;             // {H, E} column slabs of ext_intra_kernel, one per resident warp
     int intra_grid = 0, intra_max_q = 0;
+    bool no_closed_form = false;         // BWA_B200_EXT_NO_CLOSED / bwa_b200_extender_set_closed_form: every job through the kernels
     int pair_unroll = 8; bool pair_no_ring = false;      // BWA_B200_PAIR_NO_RING: per-query state even with a band (A/B switch)
 };
 

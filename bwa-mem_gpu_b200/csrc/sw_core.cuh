@@ -126,6 +126,63 @@ SW_DEV void sw_striped(int qlen, const SwSeq &Q, int tlen, const SwSeq &T, const
     }
 }
 
+// The score ksw_i16 returns (src/ksw.c:574-696) when nothing else of the result is read and no threshold is set (xtra = KSW_XSTART:
+// mem_seed_sw, src/bwamem.c:774-808): the same replay as sw_striped<8> without Hmax, the row maxima and the second pass.  One H array is
+// enough: in position order a cell's previous-row value is read right before it is overwritten and the lazy-F rounds only touch the new
+// row.  H and E hold ceil(qlen / 8) * 8 int16 each at element stride NS; Q(pos) / T(row) return codes 0..4.
+template <class QS, class TS>
+SW_DEV int sw_i16_score(int qlen, const QS &Q, int tlen, const TS &T, const SwParams &S, int16_t *H, int16_t *E, size_t NS)
+{
+    constexpr int P = 8;
+    const int slen = (qlen + P - 1) / P, n = slen * P;
+    if (slen == 0) return 0;
+    const int oe_del = S.o_del + S.e_del, oe_ins = S.o_ins + S.e_ins;
+    for (int pos = 0; pos < n; ++pos) { H[pos * NS] = 0; E[pos * NS] = 0; }
+    int gmax = 0;
+    int fv[P];
+    for (int i = 0; i < tlen; ++i) {
+        const int8_t *ma = S.mat + T(i) * S.m;
+        int rowm = 0, hd = 0;
+        for (int l = 0; l < P; ++l) {
+            int f = 0;
+            for (int j = 0; j < slen; ++j) {
+                const int pos = l * slen + j;
+                int h = hd + (pos >= qlen ? 0 : ma[Q(pos)]);
+                h = h > 32767 ? 32767 : (h < -32768 ? -32768 : h);
+                hd = H[pos * NS];
+                const int e = E[pos * NS];
+                h = sw_max(h, e); h = sw_max(h, f);
+                rowm = sw_max(rowm, h);
+                H[pos * NS] = (int16_t)h;
+                E[pos * NS] = (int16_t)sw_max(sw_subs(e, S.e_del), sw_subs(h, oe_del));
+                f = sw_max(sw_subs(f, S.e_ins), sw_subs(h, oe_ins));
+            }
+            fv[l] = f;
+        }
+        bool done = false;
+        for (int k = 0; k < 16 && !done; ++k) {
+#pragma unroll
+            for (int l = P - 1; l > 0; --l) fv[l] = fv[l - 1];
+            fv[0] = 0;
+            for (int j = 0; j < slen; ++j) {
+                bool any = false;
+#pragma unroll
+                for (int l = 0; l < P; ++l) {
+                    const size_t at = (size_t)(l * slen + j) * NS;
+                    int h = H[at];
+                    if (fv[l] > h) { h = fv[l]; H[at] = (int16_t)h; }
+                    h = sw_subs(h, oe_ins);
+                    fv[l] = sw_subs(fv[l], S.e_ins);
+                    any = any || fv[l] > h;
+                }
+                if (!any) { done = true; break; }
+            }
+        }
+        gmax = sw_max(gmax, rowm);
+    }
+    return gmax;
+}
+
 // ksw_align2 (src/ksw.c:698-736), qry = NULL, avx2 = 0
 SW_DEV void sw_align2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, const SwParams &S, int xtra,
                       int16_t *ws, size_t NS, size_t n_cap, int16_t *rowmax, bwa_b200_sw_result_t &r)

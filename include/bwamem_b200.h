@@ -238,6 +238,13 @@ void *bwa_b200_extender_stream(bwa_b200_extender_t *e);
 uint64_t bwa_b200_extender_launches(const bwa_b200_extender_t *e);
 /* cells evaluated by the last batch (sum over rows of end-beg), counted on device */
 uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e);
+/* Jobs of the last batch answered without a matrix: a query that equals the head of its target except possibly in its first base
+ * (the usual flank of a maximal exact match in a read with no further difference on that side) has a closed-form ksw_extend2 result
+ * when the scoring is bwa_fill_scmat's and min(o_del + e_del, o_ins + e_ins) > a + b -- proof and conditions in
+ * bwa-mem_gpu_b200/csrc/ext_pair_core.cuh (closed_form_job).  Such jobs are not in last_cells.  set_closed_form(e, 0) sends every job
+ * through the kernels (also: environment BWA_B200_EXT_NO_CLOSED at creation). */
+uint64_t bwa_b200_extender_last_closed_form(bwa_b200_extender_t *e);
+int  bwa_b200_extender_set_closed_form(bwa_b200_extender_t *e, int enable);
 
 /* ------------------------------------------------- fused seed -> extend pipeline */
 /* B200-first entry point for the headline metric (reads/s, seed + extend): reads go in once,
@@ -454,6 +461,7 @@ int  bwa_b200_align_device(bwa_b200_aligner_t *a, const uint32_t *dev_packed, co
 typedef struct {
     uint64_t n_reads, n_regions, n_jobs_short, n_jobs_long, n_seeds, cells;
     const uint32_t *n_regions_per_read; const uint64_t *region_off; const bwa_b200_region_t *regions;   /* device pointers */
+    uint64_t closed_form_jobs;  /* extension jobs answered in closed form (bwa_b200_extender_last_closed_form); not in cells */
 } bwa_b200_align_view_t;
 int  bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v);
 /* reads of the last batch that were not aligned because mem_flt_chained_seeds would run mem_seed_sw on them (see above): *n of them,

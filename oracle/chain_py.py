@@ -237,9 +237,16 @@ def oracle_align_batch(opt, ctg: Contigs, fwd, reads, rbeg, qq, score, n_seeds, 
                   qlen=np.ascontiguousarray(jobs["qlen"]), tlen=np.ascontiguousarray(jobs["tlen"]), h0=np.ascontiguousarray(jobs["h0"]))
         res, cnt = O.ksw_batch(jd, ksw_params, n_threads=n_threads)
         tri = np.stack(O.gasal_triple(res, jobs["qlen"], ksw_params.pen_clip), axis=1).astype(np.int32)
+        # what the device extender counts: jobs of the closed-form shape are answered without a matrix (tools/synth.dp_cells)
+        from tools import synth
+        kw = dict(a=int(ksw_params.mat[0]), b=-int(ksw_params.mat[1]), o_del=ksw_params.o_del, e_del=ksw_params.e_del, o_ins=ksw_params.o_ins,
+                  e_ins=ksw_params.e_ins, w=ksw_params.w, zdrop=ksw_params.zdrop, use_band=ksw_params.use_band, end_bonus=ksw_params.end_bonus,
+                  pen_clip=ksw_params.pen_clip)
+        cells_dp, closed = synth.dp_cells(O, jd, kw, cnt)
     else:
         res, cnt, tri = np.zeros((0, 6), np.int32), dict(cells=0, rows=0, rect=0), np.zeros((0, 3), np.int32)
-    out.update(job_res=res, cells=cnt["cells"])
+        cells_dp, closed = 0, 0
+    out.update(job_res=res, cells=cnt["cells"], cells_dp=cells_dp, closed_form_jobs=closed)
     alns = []
     i_s, i_l = 0, n_short
     for r, p in enumerate(per):

@@ -9,12 +9,13 @@
 using namespace b200chain;
 
 // one read: seeds -> chains (chains / cseeds need ns entries) -> regions (regs needs ns entries).
+// pac / rd: the 2-bit reference and the read's 4-bit words, needed for reads mem_flt_chained_seeds acts on.
 // triples: optional {aln_score, query_end, target_end} per job, SHORT batch then LONG batch of this read, applied with
 // region_finish.  Returns the chain count or a negative error.
 extern "C" int chain_host_read(const bwa_b200_chain_params_t *P, int n_ctg, const int64_t *ctg_off, const int32_t *ctg_len, const int32_t *ctg_alt,
                                int64_t l_pac, int l_query, uint32_t ns, const uint64_t *rbeg, const int32_t *qq, const uint32_t *score, int layout_all,
                                bwa_b200_chain_t *chains, bwa_b200_chain_seed_t *cseeds, bwa_b200_region_t *regs, int32_t counts[3],
-                               const int32_t *short3, const int32_t *long3)
+                               const int32_t *short3, const int32_t *long3, const uint32_t *pac, const uint32_t *rd)
 {
     Contigs ctg{ctg_off, ctg_len, ctg_alt, n_ctg, l_pac};
     const size_t n = ns ? ns : 1;
@@ -25,6 +26,14 @@ extern "C" int chain_host_read(const bwa_b200_chain_params_t *P, int n_ctg, cons
     const int nc = chain_read(*P, ctg, io);
     counts[0] = counts[1] = counts[2] = 0;
     if (nc < 0) return nc;
+    if (nc > 0 && flt_seeds_applies(*P, l_query)) {      // what seedsw_kernel + chain_long_kernel do (pac / rd: the device's packed forms)
+        if (!pac || !rd) return -2;
+        const int n_cs = chains[nc - 1].seed_off + chains[nc - 1].n;
+        int16_t H[SEEDSW_MAX], E[SEEDSW_MAX];
+        uint8_t qs[SEEDSW_MAX];
+        for (int i = 0; i < n_cs; ++i) cseeds[i].score = seed_sw(*P, ctg, pac, rd, l_query, cseeds[i], H, E, qs, 1);
+        flt_seeds_apply(*P, l_query, nc, chains, cseeds);
+    }
     std::vector<uint64_t> srt(n);
     AlnIO ao{l_query, nc, chains, cseeds, srt.data(), regs};
     int n_short = 0, n_long = 0;

@@ -130,3 +130,38 @@ extern "C" long long ext_pair_host_run(const bwa_b200_ext_params_t *p, int varia
     }
     return (long long)cells;
 }
+
+// closed_form_job over a batch, both sequence forms (bytes as given; 4-bit words packed here, 8 bases per word, base 0 in the top
+// nibble, each sequence on a word boundary, padding 4).  flags[a] bit 0 / bit 1: the byte / packed form took the job; res6 holds the
+// result where a flag is set (both forms must agree: -3 otherwise).  Returns the number of jobs taken, -1 when the parameters rule
+// the shortcut out.
+extern "C" long long ext_closed_form_host(const bwa_b200_ext_params_t *p, uint64_t n, const uint8_t *qseq, const uint32_t *qoff,
+                                          const uint32_t *qlen, const uint8_t *tseq, const uint32_t *toff, const uint32_t *tlen,
+                                          const uint32_t *h0, int32_t *res6, uint8_t *flags)
+{
+    const ClosedParams C = closed_params_from(p);
+    if (!C.ok) return -1;
+    std::vector<uint32_t> qp, tp, qo(n), to(n);
+    auto pack = [](std::vector<uint32_t> &dst, const uint8_t *s, uint32_t len) -> uint32_t {
+        const uint32_t at = (uint32_t)dst.size() * 8;
+        for (uint32_t w = 0; w < (len + 7) / 8; ++w) {
+            uint32_t x = 0;
+            for (uint32_t k = 0; k < 8; ++k) { const uint32_t i = 8 * w + k; x = (x << 4) | (i < len ? (s[i] > 4 ? 4u : s[i]) : 4u); }
+            dst.push_back(x);
+        }
+        return at;
+    };
+    for (uint64_t a = 0; a < n; ++a) { qo[a] = pack(qp, qseq + qoff[a], qlen[a]); to[a] = pack(tp, tseq + toff[a], tlen[a]); }
+    qp.push_back(0); tp.push_back(0);
+    JobView JB{qseq, tseq, nullptr, nullptr, qoff, qlen, toff, tlen, h0};
+    JobView JP{nullptr, nullptr, qp.data(), tp.data(), qo.data(), qlen, to.data(), tlen, h0};
+    long long taken = 0;
+    for (uint64_t a = 0; a < n; ++a) {
+        bwa_b200_ext_result_t rb, rp;
+        const bool fb = closed_form_job<true>(C, JB, (uint32_t)a, &rb), fp = closed_form_job<false>(C, JP, (uint32_t)a, &rp);
+        flags[a] = (uint8_t)((fb ? 1 : 0) | (fp ? 2 : 0));
+        if (fb != fp || (fb && memcmp(&rb, &rp, sizeof(rb)) != 0)) return -3;
+        if (fb) { memcpy(res6 + 6 * a, &rb, sizeof(rb)); ++taken; }
+    }
+    return taken;
+}

@@ -27,16 +27,16 @@ REG_FIELDS = ["rb_est", "re_est", "target_seed_begin", "qb_est", "qe_est", "rid"
 def emul():
     so = os.path.join(HERE, "libchain_host.so")
     srcs = [os.path.join(HERE, "chain_host.cpp"), os.path.join(ROOT, "bwa-mem_gpu_b200", "csrc", "chain_core.cuh"),
-            os.path.join(ROOT, "include", "bwamem_b200.h")]
+            os.path.join(ROOT, "bwa-mem_gpu_b200", "csrc", "sw_core.cuh"), os.path.join(ROOT, "include", "bwamem_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
                                "-I", os.path.join(ROOT, "bwa-mem_gpu_b200", "csrc"), srcs[0], "-o", so])
     L = C.CDLL(so)
     L.chain_host_read.restype = C.c_int
     L.chain_host_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32] + [C.c_void_p] * 3 + \
-                                 [C.c_int] + [C.c_void_p] * 6
+                                 [C.c_int] + [C.c_void_p] * 8
 
-    def run(opt, ctg, l_query, rb, qq, sc, layout_all, short3=None, long3=None):
+    def run(opt, ctg, l_query, rb, qq, sc, layout_all, short3=None, long3=None, pac2=None, rd4=None):
         n = max(len(rb), 1)
         rb = np.ascontiguousarray(rb, np.uint64); qq = np.ascontiguousarray(qq, np.int32); sc = np.ascontiguousarray(sc, np.uint32)
         chains = np.zeros(n, CP.CHAIN_DT); cs = np.zeros(n, CP.CSEED_DT); regs = np.zeros(n, REGION_DT); counts = np.zeros(3, np.int32)
@@ -45,7 +45,8 @@ def emul():
         nc = L.chain_host_read(C.addressof(opt), ctg.n, ctg.off.ctypes.data, ctg.len.ctypes.data, ctg.alt.ctypes.data, ctg.l_pac, l_query,
                                len(rb), rb.ctypes.data, qq.ctypes.data, sc.ctypes.data, int(layout_all), chains.ctypes.data, cs.ctypes.data,
                                regs.ctypes.data, counts.ctypes.data, s3.ctypes.data if s3 is not None else None,
-                               l3.ctypes.data if l3 is not None else None)
+                               l3.ctypes.data if l3 is not None else None, pac2.ctypes.data if pac2 is not None else None,
+                               rd4.ctypes.data if rd4 is not None else None)
         assert nc >= 0, nc
         chains = chains[:nc]
         return chains, cs[:int(chains["n"].sum()) if nc else 0], regs[:counts[0]], counts
@@ -133,3 +134,36 @@ def test_chain_source_matches_oracle(emul, lens, max_occ, seed):
                 assert (regs[f] == aln[f]).all(), f
             n_multi += len(oc) > 9
     assert n_multi > 10
+
+
+@pytest.mark.parametrize("lens,max_occ,seed,min_chain_weight", [((30000, 1500, 20000), 50, 31, 0), ((40000,), 500, 32, 0), ((30000, 1500, 20000), 50, 33, 30)])
+def test_long_reads_seed_filter_matches_oracle(emul, lens, max_occ, seed, min_chain_weight):
+    # reads mem_flt_chained_seeds acts on: seed_sw (the score of ksw_i16 around every chain seed) + flt_seeds_apply of the device source
+    ctg = CP.Contigs(lens, alt=[0, 1, 0][:len(lens)])
+    opt = CP.default_opt(max_occ=max_occ)
+    opt.min_chain_weight = min_chain_weight
+    fwd, cases = CC.make_long_cases(seed, 40, lens, max_occ)
+    pac2 = pack2(fwd)
+    dropped = moved = short_circuit = 0
+    for query, rb, qq, sc in cases:
+        rd4 = pack4(query)
+        for layout_all in (1, 0):
+            a = (rb, qq, sc) if layout_all else CC.to_compact(rb, qq, sc, max_occ)
+            oc, osd = CP.oracle_chains(opt, ctg, len(query), a[0], a[1], a[2], layout_all, fwd, query)
+            oregs, ojobs, _ = CP.oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
+            chains, cs, regs, counts = emul(opt, ctg, len(query), a[0], a[1], a[2], layout_all, None, None, pac2, rd4)
+            assert chains.tobytes() == oc.tobytes() and cs.tobytes() == osd.tobytes()
+            assert len(regs) == len(oregs) and counts[1] == len(ojobs[0]) and counts[2] == len(ojobs[1])
+            for f in REG_FIELDS:
+                assert (regs[f] == oregs[f]).all(), f
+        # the unfiltered chains of the same read: the filter must have done something over the set
+        L = CP._bind_oracle()
+        n = len(rb)
+        ch0 = np.zeros(max(n, 1), CP.CHAIN_DT); cs0 = np.zeros(max(n, 1), CP.CSEED_DT); nc0 = C.c_int32(0)
+        rbc = np.ascontiguousarray(rb, np.uint64); qqc = np.ascontiguousarray(qq, np.int32); scc = np.ascontiguousarray(sc, np.uint32)
+        L.chain_oracle_read_any(C.byref(opt), ctg.l_pac, ctg.n, ctg.off.ctypes.data, ctg.len.ctypes.data, ctg.alt.ctypes.data, len(query), n,
+                                rbc.ctypes.data, qqc.ctypes.data, scc.ctypes.data, 1, C.byref(nc0), ch0.ctypes.data, cs0.ctypes.data)
+        dropped += int(ch0[:nc0.value]["n"].sum()) - len(osd)
+        moved += int((osd["score"] != osd["len"]).sum())
+        short_circuit += int((osd["len"] >= 200).sum())
+    assert dropped > 20 and moved > 50 and short_circuit > 0

@@ -63,6 +63,28 @@ def test_chain_oracle_default_options_single_contig():
         assert regs.tobytes() == fr.tobytes() and jobs[0].tobytes() == fj[0].tobytes() and jobs[1].tobytes() == fj[1].tobytes()
 
 
+@pytest.mark.skipif(not CP.have_fork(), reason="oracle/_ref/libforkmem.so not built")
+@pytest.mark.parametrize("lens,max_occ,seed", [((30000, 1500, 20000), 50, 41), ((40000,), 500, 42)])
+def test_chain_oracle_long_reads_equal_reference_fork(lens, max_occ, seed):
+    # reads of 760 bases and more: the fork runs mem_flt_chained_seeds / mem_seed_sw (ksw_align2) on them, src/bwamem.c:774-808,970-990
+    ctg = CP.Contigs(lens, alt=[0, 1, 0][:len(lens)])
+    opt = CP.default_opt(max_occ=max_occ)
+    fwd, cases = CC.make_long_cases(seed, 60, lens, max_occ)
+    pac = CP.make_pac(fwd)
+    moved = 0
+    for query, rb, qq, sc in cases:
+        fc, fs, fr, fj, fseq = CP.fork_read(opt, ctg, pac, query, rb, qq, sc)
+        oc, osd = CP.oracle_chains(opt, ctg, len(query), rb, qq, sc, 1, fwd, query)
+        assert oc.tobytes() == fc.tobytes() and osd.tobytes() == fs.tobytes()
+        regs, jobs, seqs = CP.oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
+        assert regs.tobytes() == fr.tobytes()
+        for s in (0, 1):
+            assert jobs[s].tobytes() == fj[s].tobytes()
+            assert seqs[s][0].tobytes() == fseq[s][0].tobytes() and seqs[s][1].tobytes() == fseq[s][1].tobytes()
+        moved += int((osd["score"] != osd["len"]).sum())
+    assert moved > 200
+
+
 def test_chain_oracle_equals_golden():
     g = np.load(GOLD)
     ctg = CP.Contigs(g["contig_lens"], alt=g["contig_alt"])
@@ -76,6 +98,22 @@ def test_chain_oracle_equals_golden():
     for name, parts in (("chains", chains), ("cseeds", cseeds), ("regs", regs), ("jobs_short", js), ("jobs_long", jl)):
         got = np.concatenate(parts)
         assert got.tobytes() == g[name].tobytes(), name
+
+
+def test_chain_oracle_long_reads_equal_golden():
+    # the seed filter of long reads against vectors made from the fork (tests/golden/make_chain_golden.py, second part)
+    g = np.load(os.path.join(os.path.dirname(GOLD), "chain_long_golden.npz"))
+    ctg = CP.Contigs(g["contig_lens"], alt=g["contig_alt"])
+    opt = CP.default_opt(max_occ=int(g["max_occ"]))
+    fwd, cases = CC.make_long_cases(int(g["seed"]), int(g["n_reads"]), tuple(int(x) for x in g["contig_lens"]), int(g["max_occ"]))
+    chains, cseeds, regs, js, jl = [], [], [], [], []
+    for query, rb, qq, sc in cases:
+        oc, osd = CP.oracle_chains(opt, ctg, len(query), rb, qq, sc, 1, fwd, query)
+        r, jobs, _ = CP.oracle_chain2aln(opt, ctg, fwd, query, oc, osd)
+        chains.append(oc); cseeds.append(osd); regs.append(r); js.append(jobs[0]); jl.append(jobs[1])
+    for name, parts in (("chains", chains), ("cseeds", cseeds), ("regs", regs), ("jobs_short", js), ("jobs_long", jl)):
+        assert np.concatenate(parts).tobytes() == g[name].tobytes(), name
+    assert (g["cseeds"]["score"] != g["cseeds"]["len"]).sum() > 300
 
 
 def test_regs_finish_arithmetic():

@@ -121,3 +121,61 @@ def test_pair_source_wide_scores_long_queries(pkg, oracle, emul, kw):
         assert bad.size == 0, (seed, np.nonzero(ok)[0][bad[:3]], res[ok][bad[:3]], want[ok][bad[:3]])
         if ok.all():
             assert cells == cnt["cells"]
+
+
+CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=0, zdrop=4), True), (dict(w=300, zdrop=0, use_band=0), True),
+         (dict(w=20, zdrop=50, a=2, b=3), True), (dict(w=20, zdrop=10, a=2, b=5, o_del=7, e_del=2, o_ins=8, e_ins=1), True),
+         (dict(w=100, zdrop=3), False),                                           # the first row's drop of b = 4 would trip z-drop
+         (dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=3, b=2), False),   # a gap is cheaper than a mismatch + a match
+         (dict(w=50, zdrop=100, a=1, b=6), False)]
+
+
+@pytest.mark.parametrize("kw,eligible", CF_KW)
+def test_closed_form_jobs_match_oracle(pkg, oracle, emul, kw, eligible):
+    """closed_form_job (ext_pair_core.cuh): every job it takes has exactly ksw_extend2's six outputs, it takes exactly the jobs of the
+    documented shape, in both sequence forms, and only under the documented parameter conditions"""
+    L = emul.lib
+    L.ext_closed_form_host.restype = C.c_longlong
+    L.ext_closed_form_host.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9
+    ep = pkg.ext_params(**kw)
+    n_taken = 0
+    for seed, extra in ((71, dict()), (72, dict(qlen_range=(1, 12), h0_range=(1, 30))), (73, dict(qlen_range=(100, 600), h0_range=(19, 250)))):
+        jobs = synth.make_flank_jobs(2500, seed=seed, w=kw["w"], **extra)
+        n = jobs["qlen"].size
+        res = np.zeros((n, 6), np.int32); flags = np.zeros(n, np.uint8)
+        taken = L.ext_closed_form_host(C.addressof(ep), n, jobs["qseq"].ctypes.data, jobs["qoff"].ctypes.data, jobs["qlen"].ctypes.data,
+                                       jobs["tseq"].ctypes.data, jobs["toff"].ctypes.data, jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data,
+                                       res.ctypes.data, flags.ctypes.data)
+        if not eligible:
+            assert taken == -1
+            continue
+        assert taken >= 0, taken
+        want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+        got = flags != 0
+        assert (flags[got] == 3).all()
+        assert (got == synth.closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4))).all()
+        assert (res[got] == want[got]).all(), np.nonzero((res != want).any(axis=1) & got)[0][:5]
+        n_taken += int(got.sum())
+    if eligible:
+        assert n_taken > 3000
+
+
+def test_closed_form_on_general_jobs(pkg, oracle, emul):
+    # the usual fuzz sets: whatever the shortcut takes there must be right as well
+    L = emul.lib
+    L.ext_closed_form_host.restype = C.c_longlong
+    L.ext_closed_form_host.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9
+    kw = dict(w=100, zdrop=100)
+    ep = pkg.ext_params(**kw)
+    for seed, extra in SETS:
+        jobs = synth.make_ext_jobs(3000, w=100, seed=seed, **extra)
+        n = jobs["qlen"].size
+        res = np.zeros((n, 6), np.int32); flags = np.zeros(n, np.uint8)
+        taken = L.ext_closed_form_host(C.addressof(ep), n, jobs["qseq"].ctypes.data, jobs["qoff"].ctypes.data, jobs["qlen"].ctypes.data,
+                                       jobs["tseq"].ctypes.data, jobs["toff"].ctypes.data, jobs["tlen"].ctypes.data, jobs["h0"].ctypes.data,
+                                       res.ctypes.data, flags.ctypes.data)
+        assert taken >= 0
+        want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+        got = flags != 0
+        assert (got == synth.closed_form_mask(jobs)).all()
+        assert (res[got] == want[got]).all()

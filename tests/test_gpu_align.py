@@ -129,7 +129,8 @@ def test_align_reads_end_to_end(gpu, oracle, small_index):
         check_batch(got, want)
         assert len(want["regs"]) > 2500
         v = al.view()
-        assert v.n_regions == len(want["regs"]) and v.cells == want["cells"] and v.n_seeds == sd["total"]
+        assert v.n_regions == len(want["regs"]) and v.n_seeds == sd["total"]
+        assert v.cells == want["cells_dp"] and v.closed_form_jobs == want["closed_form_jobs"] and v.closed_form_jobs > 500
         # the same batch through the pinned-buffer entry point (twice: buffers are reused)
         for _ in range(2):
             pv = al.align_host_view(packed.ctypes.data, woff.ctypes.data, rl.ctypes.data, rl.size, spar,
@@ -178,24 +179,79 @@ def test_align_with_reseeding_rows_overflow(gpu, oracle, small_index, monkeypatc
     idx.free()
 
 
+@pytest.mark.parametrize("layout_all", [1, 0])
+def test_align_long_reads_given_seeds_matches_oracle(gpu, oracle, case_index, layout_all):
+    """mem_flt_chained_seeds on the device (seedsw_kernel + chain_long_kernel): reads of 760-2500 bases, mixed with short ones in one batch"""
+    lens, fwd, _, idx = case_index
+    fwd2, long_cases = CC.make_long_cases(31, 60, lens, 50)
+    assert (fwd2 == fwd).all()                  # same seed, same genome as the fixture's index
+    _, short_cases = CC.make_cases(31, 90, lens, 50)
+    cases = [c for pair in zip(long_cases, short_cases[:60]) for c in pair] + short_cases[60:]
+    ctg = CP.Contigs(lens, alt=[0, 1, 0])
+    opt = CP.default_opt(max_occ=50, w=100)
+    reads = [c[0] for c in cases]
+    seeds = [(c[1], c[2], c[3]) if layout_all else CC.to_compact(c[1], c[2], c[3], 50) for c in cases]
+    n_seeds = np.array([len(s[0]) for s in seeds], np.uint32)
+    seed_off = np.concatenate([[0], np.cumsum(n_seeds)[:-1]]).astype(np.uint64)
+    rbeg = np.concatenate([s[0] for s in seeds]); qq = np.concatenate([s[1].reshape(-1, 2) for s in seeds]); score = np.concatenate([s[2] for s in seeds])
+    kp = oracle.make_params(w=100, zdrop=100, use_band=1)
+    want = CP.oracle_align_batch(opt, ctg, fwd, reads, rbeg, qq, score, n_seeds, seed_off, layout_all, kp)
+    assert (want["chain_seeds"]["score"] != want["chain_seeds"]["len"]).sum() > 100
+    rf, off = flat(reads)
+    packed, woff, rl = gpu.pack_codes(rf, off)
+    al = gpu.Aligner(idx, len(reads), packed.size)
+    al.set_contigs(ctg.off, ctg.len, ctg.alt)
+    cp = gpu.chain_params(max_occ=50, w=100)
+    ep = gpu.ext_params(w=100, zdrop=100, use_band=1)
+    for detail in (True, False, True):
+        got = al.align_seeds_host(packed, woff, rl, rbeg, qq, score, n_seeds, seed_off, layout_all, cp, ep, detail=detail)
+        check_batch(got, want, detail=detail)
+        assert al.skipped_reads().size == 0
+    al.destroy()
+
+
+def test_align_long_reads_end_to_end(gpu, oracle, small_index):
+    """reads of 800-3000 bases in, regions out: device seeding, chaining with the seed filter, long extension jobs"""
+    g, prefix = small_index
+    idx = gpu.Index.load(prefix + ".bwt", prefix + ".sa", 0)
+    idx.attach_ref(g)
+    oi = oracle.OracleIndex(prefix + ".bwt", prefix + ".sa")
+    rng = np.random.default_rng(18)
+    base, _, _ = synth.make_reads(g, 400, 3000, seed=35, sub_rate=0.05, n_rate=0.001)
+    reads = [base[i, :int(rng.choice([800, 1000, 1500, 3000, 150]))] for i in range(400)]
+    rf, off = flat(reads)
+    for reseed in (False, True):
+        sd = oi.seed_batch(rf, off, 19, 500, n_threads=4, rs=oracle.reseed() if reseed else None)
+        ctg = CP.Contigs((g.size,))
+        opt = CP.default_opt(max_occ=500, w=100)
+        kp = oracle.make_params(w=100, zdrop=100, use_band=1)
+        qq = np.stack([sd["qbeg"], sd["qend"]], axis=1).astype(np.int32)
+        want = CP.oracle_align_batch(opt, ctg, g, reads, sd["rbeg"], qq, sd["score"], sd["n_seeds"], sd["seed_off"], 0, kp)
+        packed, woff, rl = gpu.pack_codes(rf, off)
+        al = gpu.Aligner(idx, len(reads), packed.size)
+        got = al.align_host(packed, woff, rl, gpu.seed_params(19, 500, reseed), gpu.chain_params(max_occ=500, w=100),
+                            gpu.ext_params(w=100, zdrop=100, use_band=1), detail=True)
+        check_batch(got, want)
+        assert len(want["regs"]) >= 400
+        al.destroy()
+    oi.close()
+    idx.free()
+
+
 def test_align_rejects_bad_input(gpu, case_index):
     lens, fwd, cases, idx = case_index
     al = gpu.Aligner(idx, 8, 4096)
     # contigs that do not tile the reference
     with pytest.raises(gpu.B200Error):
         al.set_contigs([0, 100], [100, 200])
-    # a read long enough for mem_flt_chained_seeds' mem_seed_sw does not fail the batch: it comes back without regions and is listed, the
-    # short read beside it is aligned as usual
+    # nothing is left to the caller any more: a read long enough for mem_flt_chained_seeds is filtered on the device (see the long-read tests)
     rng = np.random.default_rng(1)
     q_long, q_short = rng.integers(0, 4, 1200, dtype=np.uint8), fwd[500:650].copy()
     rf, off = flat([q_long, q_short])
     packed, woff, rl = gpu.pack_codes(rf, off)
     res = al.align_seeds_host(packed, woff, rl, np.array([100, 500], np.uint64), np.array([[0, 30], [0, 150]], np.int32), np.array([1, 1], np.uint32),
                               np.array([1, 1], np.uint32), np.array([0, 1], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
-    assert list(al.skipped_reads()) == [0] and list(res["n_regions"]) == [0, 1]
-    res = al.align_seeds_host(packed[woff[1]:], woff[1:] - woff[1], rl[1:], np.array([500], np.uint64), np.array([[0, 150]], np.int32), np.array([1], np.uint32),
-                              np.array([1], np.uint32), np.array([0], np.uint64), 1, gpu.chain_params(), gpu.ext_params())
-    assert al.skipped_reads().size == 0 and list(res["n_regions"]) == [1]
+    assert al.skipped_reads().size == 0 and list(res["n_regions"]) == [0, 1]      # the random read's only seed scores below min_HSP_score
     # empty batch
     e = al.align_host(np.zeros(1, np.uint32), np.zeros(1, np.uint64), np.zeros(0, np.uint32), gpu.SeedParams(19, 500), gpu.chain_params(),
                       gpu.ext_params())

@@ -197,7 +197,7 @@ def test_extension_matches_oracle(gpu, oracle, kw):
         res, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
         bad = np.nonzero((res != want).any(axis=1))[0]
         assert bad.size == 0, (bad[:5], res[bad[:5]], want[bad[:5]])
-        assert ex.last_cells() == cnt["cells"]
+        assert (ex.last_cells(), ex.last_closed_form()) == synth.dp_cells(oracle, jobs, kw, cnt)
     ex.destroy()
 
 
@@ -217,7 +217,7 @@ def test_extension_pair_kernel_stress(gpu, oracle, kw):
         res, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
         bad = np.nonzero((res != want).any(axis=1))[0]
         assert bad.size == 0, (seed, bad[:5], res[bad[:5]], want[bad[:5]], jobs["qlen"][bad[:5]], jobs["tlen"][bad[:5]], jobs["h0"][bad[:5]])
-        assert ex.last_cells() == cnt["cells"]
+        assert (ex.last_cells(), ex.last_closed_form()) == synth.dp_cells(oracle, jobs, kw, cnt)
         os.environ["BWA_B200_EXT_NO_SIMD"] = "1"
         try:
             res32, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
@@ -284,7 +284,7 @@ def test_extension_long_queries_and_wide_scores_intra_kernel(gpu, oracle):
         want, cnt = oracle.ksw_batch(longj, oracle.make_params(**kw), n_threads=4)
         res, _ = ex.extend_host(longj, gpu.ext_params(**kw))
         assert (res == want).all()
-        assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == cnt["cells"]
+        assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == synth.dp_cells(oracle, longj, kw, cnt)[0]
     # one very long query (and a target that diverges half way: z-drop / window shrink on a long row)
     rng = np.random.default_rng(5)
     q = rng.integers(0, 4, 15000, dtype=np.uint8)
@@ -341,10 +341,21 @@ def test_pipeline_matches_oracle(gpu, oracle, dev_index, kw):
         bad = np.nonzero((got[key] != want[key]).reshape(n, -1).any(axis=1))[0]
         assert bad.size == 0, (key, bad[:5], got[key][bad[:5]], want[key][bad[:5]])
     tot = pl.totals()
-    assert tot["cells"] == kc["cells"] and tot["seeds"] == fc["n_located"]
+    assert tot["cells"] <= kc["cells"] and tot["seeds"] == fc["n_located"]       # jobs answered in closed form are not in the cell count
     # a second batch through the same pipeline (no reallocation, no stale state)
     got2 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params(**kw))
     assert got2.tobytes() == got.tobytes()
+    pl.destroy()
+    # every job through the kernels: the same records, and the evaluated cells are the oracle's
+    os.environ["BWA_B200_EXT_NO_CLOSED"] = "1"
+    try:
+        pl = gpu.Pipeline(idx, n, packed.size, 150)
+    finally:
+        del os.environ["BWA_B200_EXT_NO_CLOSED"]
+    got3 = pl.run_host(packed, woff, rl, gpu.SeedParams(19, 500), gpu.ext_params(**kw))
+    assert got3.tobytes() == got.tobytes() and pl.totals()["cells"] == kc["cells"]
+    if synth.closed_form_eligible(**kw):
+        assert tot["cells"] < kc["cells"]
     pl.destroy()
 
 
@@ -418,7 +429,7 @@ def test_extension_wave_kernel_banded_long_and_wide(gpu, oracle, kw, wide, monke
     assert ex.launches > l0
     bad = np.nonzero((res != want).any(axis=1))[0]
     assert bad.size == 0, (bad[:5], jobs["qlen"][bad[:5]], jobs["tlen"][bad[:5]], jobs["h0"][bad[:5]], res[bad[:3]], want[bad[:3]])
-    assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == cnt["cells"]
+    assert int(gpu.lib().bwa_b200_extender_last_cells(ex.h)) == synth.dp_cells(oracle, jobs, kw, cnt)[0]
     # packed device path, long and short jobs in one batch
     both = {k: np.concatenate([jobs[k], short[k]]) for k in ("qseq", "tseq", "qlen", "tlen", "h0")}
     both["qoff"] = np.concatenate([jobs["qoff"], short["qoff"] + np.uint32(jobs["qseq"].size)]).astype(np.uint32)

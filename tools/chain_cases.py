@@ -94,3 +94,60 @@ def make_cases(seed, n_reads, contig_lens=(30000, 1500, 20000), max_occ=50):
         rb, qq, sc = make_read_seeds(rng, l_pac, l_query, max_occ, styles[r % len(styles)])
         cases.append((query, rb, qq, sc))
     return fwd, cases
+
+
+def make_long_cases(seed, n_reads, contig_lens=(30000, 1500, 20000), max_occ=50):
+    """Reads long enough for mem_flt_chained_seeds to act (>= 757 bases at the default options): cut from the text fwd + revcomp(fwd) with
+    2-30 % substitutions (so that the local alignment around a seed scores on either side of min_HSP_score), seeds on the read's true
+    diagonal, at random places, around the forward/reverse boundary, at contig and text ends, and a few of 200 bases and more (the
+    alignment is skipped for those)."""
+    rng = np.random.default_rng(seed)
+    fwd = random_genome(rng, contig_lens)
+    l_pac = len(fwd)
+    text = np.concatenate([fwd, (3 - fwd)[::-1]])
+    edges = np.concatenate([[0], np.cumsum(contig_lens)])
+    edges = np.concatenate([edges, 2 * l_pac - edges])
+    cases = []
+    for r in range(n_reads):
+        l_query = int(rng.choice([760, 800, 1000, 1500, 2500]))
+        pos = int(rng.integers(0, 2 * l_pac - l_query))
+        query = text[pos:pos + l_query].copy()
+        rate = float(rng.choice([0.02, 0.1, 0.2, 0.3]))
+        mut = rng.random(l_query) < rate
+        query[mut] = (query[mut] + rng.integers(1, 4, size=int(mut.sum()))) & 3
+        if rng.random() < 0.3:
+            query[rng.integers(0, l_query, size=3)] = 4
+        n_groups = int(rng.integers(3, 30))
+        qbs = np.sort(rng.integers(0, l_query - 19, size=n_groups))
+        rbeg, qq, score = [], [], []
+        prev_end = 0
+        for g in range(n_groups):
+            qb = int(qbs[g])
+            ln = int(rng.integers(19, 90)) if rng.random() < 0.93 else int(rng.integers(190, 260))
+            qe = min(l_query, qb + ln)
+            if qe <= prev_end:
+                qe = min(l_query, prev_end + 1)
+            if qe - qb < 19:
+                continue
+            prev_end = qe
+            s = int(rng.integers(1, 5)) if rng.random() < 0.9 else int(rng.integers(max_occ + 1, 2 * max_occ))
+            rows = []
+            for _ in range(s):
+                u = rng.random()
+                if u < 0.6:
+                    rr = pos + qb + int(rng.integers(-3, 4)) * int(rng.random() < 0.2)
+                elif u < 0.7:
+                    rr = l_pac + int(rng.integers(-120, 120))
+                elif u < 0.8:
+                    rr = int(rng.choice(edges)) + int(rng.integers(-120, 120))
+                else:
+                    rr = int(rng.integers(0, 2 * l_pac - l_query))
+                rows.append(min(max(rr, 0), 2 * l_pac - (qe - qb)))
+            if rng.random() < 0.5:
+                rows.sort()
+            for k, rr in enumerate(rows):
+                rbeg.append(rr); qq.append((qb, qe)); score.append(s if k == 0 else 0)
+        if not rbeg:
+            rbeg, qq, score = [pos], [(0, 30)], [1]
+        cases.append((query, np.array(rbeg, dtype=np.uint64), np.array(qq, dtype=np.int32).reshape(-1, 2), np.array(score, dtype=np.uint32)))
+    return fwd, cases

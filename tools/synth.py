@@ -268,3 +268,96 @@ def make_sw_jobs(n_jobs: int, qlen_range=(30, 150), tlen_range=(100, 700), seed:
         x = np.broadcast_to(np.asarray(xtra, np.uint32), ql_a.shape).copy()
     return dict(qseq=np.concatenate(qs), tseq=np.concatenate(ts), qoff=np.asarray(qoff, np.uint32), toff=np.asarray(toff, np.uint32),
                 qlen=ql_a, tlen=np.asarray(tlen, np.uint32), xtra=x.astype(np.uint32))
+
+
+def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=(1, 200), w: int = 100, pad8: bool = True):
+    """Extension jobs as a maximal exact match leaves them in a read with few differences: the query equals the head of the target,
+    mostly with its first base changed (the base that ended the match).  A third of the jobs miss that shape by one detail -- a second
+    difference, an N on either side, a target shorter than the query, a small h0 -- so that a shortcut for the shape is tested on
+    both sides of every condition.  Same dict as make_ext_jobs."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    qlens = rng.integers(qlen_range[0], qlen_range[1] + 1, size=n_jobs)
+    h0 = rng.integers(h0_range[0], h0_range[1] + 1, size=n_jobs).astype(np.uint32)
+    qs, ts = [], []
+    for a in range(n_jobs):
+        ql = int(qlens[a])
+        tl = ql + int(rng.integers(0, min(ql, 2 * w) + 1))
+        t = rng.integers(0, 4, size=tl, dtype=np.uint8)
+        q = t[:ql].copy()
+        u = rng.random()
+        if u < 0.85:
+            q[0] = (q[0] + int(rng.integers(1, 4))) & 3          # the mismatch that ended the seed
+        v = rng.random()
+        if v < 0.08 and ql > 1:                                   # a second difference somewhere
+            k = int(rng.integers(1, ql)); q[k] = (q[k] + 1) & 3
+        elif v < 0.13:                                            # N in the query / in the compared part of the target / beyond it
+            q[int(rng.integers(0, ql))] = 4
+        elif v < 0.18:
+            t[int(rng.integers(0, ql))] = 4
+        elif v < 0.21 and tl > ql:
+            t[int(rng.integers(ql, tl))] = 4
+        elif v < 0.26 and ql > 1:                                 # target shorter than the query
+            t = t[:int(rng.integers(1, ql))]
+        elif v < 0.31:
+            h0[a] = int(rng.integers(1, 8))
+        qs.append(q); ts.append(t)
+    tlens = np.array([len(t) for t in ts], np.int64)
+
+    def padded(n):
+        return (n + 7) // 8 * 8 if pad8 else n
+    qp = np.asarray([padded(int(x)) for x in qlens], dtype=np.int64)
+    tp = np.asarray([padded(int(x)) for x in tlens], dtype=np.int64)
+    qoff = np.zeros(n_jobs, dtype=np.uint32); toff = np.zeros(n_jobs, dtype=np.uint32)
+    qoff[1:] = np.cumsum(qp)[:-1]; toff[1:] = np.cumsum(tp)[:-1]
+    qseq = np.full(int(qp.sum()) + 8, 4, dtype=np.uint8); tseq = np.full(int(tp.sum()) + 8, 4, dtype=np.uint8)
+    for a in range(n_jobs):
+        qseq[qoff[a]:qoff[a] + len(qs[a])] = qs[a]; tseq[toff[a]:toff[a] + len(ts[a])] = ts[a]
+    return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
+
+
+def closed_form_mask(jobs: dict, a: int = 1, b: int = 4) -> np.ndarray:
+    """Which jobs have the shape the extender answers in closed form (an independent statement of closed_form_job's predicate):
+    query[1:] == target[1:qlen], every compared base in A/C/G/T, target at least as long as the query, h0 > b."""
+    n = jobs["qlen"].size
+    out = np.zeros(n, bool)
+    for k in range(n):
+        ql, tl, h0 = int(jobs["qlen"][k]), int(jobs["tlen"][k]), int(jobs["h0"][k])
+        if ql == 0 or tl < ql or h0 <= b:
+            continue
+        q = jobs["qseq"][int(jobs["qoff"][k]):int(jobs["qoff"][k]) + ql]; t = jobs["tseq"][int(jobs["toff"][k]):int(jobs["toff"][k]) + ql]
+        out[k] = bool((q < 4).all() and (t < 4).all() and (q[1:] == t[1:]).all())
+    return out
+
+
+def closed_form_eligible(w=100, zdrop=100, use_band=1, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, **_) -> bool:
+    """closed_params_from (ext_pair_core.cuh) restated: the parameter conditions of the closed-form answer"""
+    g = min(o_del + e_del, o_ins + e_ins)
+    return a >= 1 and b >= 1 and g > a + b and not (use_band and w < 0) and not (zdrop > 0 and b > zdrop)
+
+
+def subset_jobs(jobs: dict, keep: np.ndarray) -> dict:
+    """the jobs where keep is set, sequences copied into fresh arrays (same dict layout)"""
+    idx = np.nonzero(keep)[0]
+    qs, ts, qo, to = [], [], [], []
+    nq = nt = 0
+    for k in idx:
+        ql, tl = int(jobs["qlen"][k]), int(jobs["tlen"][k])
+        qp, tp = (ql + 7) // 8 * 8, (tl + 7) // 8 * 8
+        q = np.full(qp, 4, np.uint8); t = np.full(tp, 4, np.uint8)
+        q[:ql] = jobs["qseq"][int(jobs["qoff"][k]):int(jobs["qoff"][k]) + ql]; t[:tl] = jobs["tseq"][int(jobs["toff"][k]):int(jobs["toff"][k]) + tl]
+        qs.append(q); ts.append(t); qo.append(nq); to.append(nt); nq += qp; nt += tp
+    pad = np.full(8, 4, np.uint8)
+    return dict(qseq=np.concatenate(qs + [pad]), tseq=np.concatenate(ts + [pad]), qoff=np.array(qo, np.uint32), toff=np.array(to, np.uint32),
+                qlen=jobs["qlen"][idx].astype(np.uint32), tlen=jobs["tlen"][idx].astype(np.uint32), h0=jobs["h0"][idx].astype(np.uint32))
+
+
+def dp_cells(oracle, jobs: dict, kw: dict, cnt_all: dict):
+    """(cells the extender evaluates, jobs it answers in closed form) for a batch: the oracle's cell count without the jobs of the
+    closed-form shape when the parameters admit the shortcut"""
+    if not closed_form_eligible(**kw):
+        return cnt_all["cells"], 0
+    m = closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4))
+    if not m.any():
+        return cnt_all["cells"], 0
+    _, c = oracle.ksw_batch(subset_jobs(jobs, m), oracle.make_params(**kw), n_threads=4)
+    return cnt_all["cells"] - c["cells"], int(m.sum())
