@@ -391,7 +391,7 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
     al.destroy()
     al = None
     chunk = max(1, (n + args.e2e_chunks - 1) // args.e2e_chunks)
-    multi = pkg.MultiAligner(idx, [torch.cuda.current_device()], 2, chunk, L)
+    multi = pkg.MultiAligner(idx, [torch.cuda.current_device()], args.e2e_workers, chunk, L)
     if len(lens) > 1:
         multi.set_contigs(np.concatenate([[0], np.cumsum(lens[:-1])]), lens)
 
@@ -584,6 +584,59 @@ def run_cigar(args, pkg, flush):
         res["cpu_baseline"] = {"value": sample / cdt, "unit": "jobs/s", "cores": threads, "kind": "port", "sample": f"first {sample} jobs",
                                "gpu_output_identical_on_sample": same}
     cg.destroy()
+    return res
+
+
+def run_mate_sw(args, pkg):
+    """Mate rescue's local alignment (second half): ksw_align2 as mem_matesw calls it (src/bwamem_pair.c:159) -- a 150 bp
+    mate against a window of 300-700 reference bases, xtra = KSW_XSUBO | KSW_XSTART | KSW_XBYTE | min_seed_len * a -- host buffers in,
+    kswr_t records out through bwa_b200_sw_align2_host."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_py as O
+    base = synth.make_sw_jobs(16_384, qlen_range=(150, 150), tlen_range=(300, 700), seed=2031)       # generated once, tiled (generation is a Python loop)
+    reps_t = 8
+    n = reps_t * 16_384
+    jobs = {k: np.tile(base[k], reps_t) for k in ("qseq", "tseq", "qlen", "tlen", "xtra")}
+    jobs["qoff"] = np.concatenate([base["qoff"] + np.uint32(r * base["qseq"].size) for r in range(reps_t)]).astype(np.uint32)
+    jobs["toff"] = np.concatenate([base["toff"] + np.uint32(r * base["tseq"].size) for r in range(reps_t)]).astype(np.uint32)
+    ep = pkg.ext_params()
+    la = pkg.LocalAligner(torch.cuda.current_device())
+    got = la.align2_host(jobs, ep)
+    la.align2_host(jobs, ep)
+    reps = 3
+    kms = []
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        la.align2_host(jobs, ep)
+        kms.append(la.last_kernel_ms)
+    e2e_s = (time.perf_counter() - t0) / reps
+    cells = int((jobs["qlen"].astype(np.int64) * jobs["tlen"].astype(np.int64)).sum())
+    res = {"jobs": n, "kernel_ms": float(np.mean(kms)), "jobs_per_s_kernel": n / (np.mean(kms) / 1e3), "e2e_jobs_per_s": n / e2e_s,
+           "cells_first_pass": cells, "GCUPS_first_pass_cells_over_kernel_time": cells / (np.mean(kms) / 1e3) / 1e9, "gpu_launches": 1,
+           "e2e_h2d_bytes": int(jobs["qseq"].size + jobs["tseq"].size + 5 * 4 * n), "e2e_d2h_bytes": int(n * 28),
+           "workload": "131072 jobs (16384 distinct, tiled 8 x): 150 bp query, 300-700 bp target holding a 4 %-diverged copy of part of it (10 % none), "
+                       "xtra = XSUBO | XSTART | XBYTE | 19; cells = qlen x tlen of the first pass (the second pass on the reversed prefixes is extra work)"}
+    if not args.no_cpu_baseline and O.have_ref():
+        sample = 16_384
+        threads = O.default_threads()
+        cuts = np.linspace(0, sample, threads + 1).astype(int)
+
+        def part(k):
+            sl = slice(cuts[k], cuts[k + 1])
+            sj = {key: (v if key in ("qseq", "tseq") else v[sl]) for key, v in jobs.items()}
+            return O.fork_sw_align2_batch(sj, O.make_params())
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(part, range(threads)))
+            t0 = time.perf_counter()
+            want = np.concatenate(list(ex.map(part, range(threads))))
+            cdt = time.perf_counter() - t0
+        same = bool(all((got[f][:sample] == want[f]).all() for f in ("score", "te", "qe", "score2", "te2", "tb", "qb")))
+        assert same, "ksw_align2 on the device differs from the reference's ksw_align2 on the bench sample"
+        res["cpu_baseline"] = {"value": sample / cdt, "unit": "jobs/s", "cores": threads, "kind": "reference",
+                               "sample": f"first {sample} jobs, the reference's own ksw_align2 (SSE2 ksw_u8 + second pass), one slice per thread",
+                               "gpu_output_identical_on_sample": same}
+    la.destroy()
     return res
 
 
@@ -831,6 +884,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the re-seeding, CIGAR and bwa-mem sub-metrics")
     ap.add_argument("--no-c3", action="store_true", help="skip BASELINE config 3 (3.1 Gb genome)")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks the host-to-host step deals its batch in")
+    ap.add_argument("--e2e-workers", type=int, default=2, help="worker threads (aligner + stream each) of the rank's device in the host-to-host step")
     ap.add_argument("--c3-genome", type=int, default=3_100_000_000)
     ap.add_argument("--c3-reads", type=int, default=1_250_000, help="reads per GPU of config 3 (10 M reads over 8 GPUs)")
     ap.add_argument("--c3-cpu-sample", type=int, default=50_000)
@@ -907,8 +961,10 @@ def main():
         if dref:
             dist.destroy_process_group()
         return
+    mate_sw = None
     if not args.no_extras:
         cigar = run_cigar(args, pkg, flush)
+        mate_sw = run_mate_sw(args, pkg)
 
     # ---- rooflines: dominant seeding kernel (HBM sectors) and the extension launch set (INT ALU), both from live CUDA-event times
     kavg = chained["kernel_ms"]
@@ -991,9 +1047,10 @@ def main():
                 "identical_to_full_records": chained["e2e_identical_to_full_records"],
                 "full_records_one_batch_in_flight": chained["e2e_full_records_one_batch_in_flight"],
                 "how": "bwa_b200_multi_align_compact from pinned host buffers: 2-bit reads in, 40-byte region records out, the batch dealt in chunks to "
-                       "two worker threads of the rank's device (the reference's NB_STREAMS = 2 pattern, src/fastmap.c:31), every chunk's H2D and D2H inside the timed region"},
+                       "%d worker threads of the rank's device (the reference's NB_STREAMS pattern, src/fastmap.c:31), every chunk's H2D and D2H inside the timed region" % args.e2e_workers,
+                "workers": args.e2e_workers},
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
-        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,
+        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "mate_rescue_sw": mate_sw, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,
                         "extension_GCUPS": gcups, "oracle_work_per_read": per_read,
                         "seeding_Mreads_per_s": n / (sum(kavg[k] for k in ("fwd_kernel", "back_kernel", "fill_kernel", "locate_kernel") if k in kavg) / 1e3) / 1e6},
     }

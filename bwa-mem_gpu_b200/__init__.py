@@ -123,7 +123,7 @@ SYMBOLS = [
     "bwa_b200_global_device", "bwa_b200_global_device_view", "bwa_b200_cigar_stream", "bwa_b200_cigar_launches",
     "bwa_b200_cigar_last_cells", "bwa_b200_cigar_profile", "bwa_b200_cigar_kernel_times", "bwa_b200_reg2aln_host",
     "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
-    "bwa_b200_sw_create", "bwa_b200_sw_destroy", "bwa_b200_sw_align2_host", "bwa_b200_sw_launches",
+    "bwa_b200_sw_create", "bwa_b200_sw_destroy", "bwa_b200_sw_align2_host", "bwa_b200_sw_launches", "bwa_b200_sw_last_kernel_ms",
     "bwa_b200_packed2_words", "bwa_b200_pack2_codes", "bwa_b200_pack2_ascii", "bwa_b200_align_host_compact",
     "bwa_b200_multi_create", "bwa_b200_multi_set_contigs", "bwa_b200_multi_align_compact", "bwa_b200_multi_n_workers",
     "bwa_b200_multi_worker_chunks", "bwa_b200_multi_launches", "bwa_b200_multi_destroy",
@@ -291,6 +291,8 @@ def lib():
         L.bwa_b200_sw_align2_host.argtypes = [vp, C.POINTER(ExtParams), C.c_uint64, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp, vp, vp, vp]
         L.bwa_b200_sw_launches.argtypes = [vp]
         L.bwa_b200_sw_launches.restype = C.c_uint64
+        L.bwa_b200_sw_last_kernel_ms.argtypes = [vp]
+        L.bwa_b200_sw_last_kernel_ms.restype = C.c_float
         L.bwa_b200_cigar_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.bwa_b200_cigar_destroy.argtypes = [vp]
         L.bwa_b200_cigar_band.argtypes = [C.POINTER(ExtParams), C.c_int, C.c_int, C.c_int64]
@@ -756,7 +758,7 @@ class Aligner:
         check(lib().bwa_b200_align_device(self.h, d_packed, d_woff, d_len, n, max_read_len, C.byref(seed_p), C.byref(chain_p), C.byref(ext_p)))
 
     def skipped_reads(self) -> np.ndarray:
-        """indexes of the last batch's reads left to the caller (long reads that need mem_seed_sw)"""
+        """always empty: reads long enough for mem_flt_chained_seeds are aligned on the device (kept for ABI compatibility)"""
         n, p = C.c_uint64(0), vp()
         check(lib().bwa_b200_aligner_skipped_reads(self.h, C.byref(n), C.byref(p)))
         if not n.value:
@@ -942,6 +944,10 @@ class LocalAligner:
     @property
     def launches(self) -> int:
         return int(lib().bwa_b200_sw_launches(self.h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(lib().bwa_b200_sw_last_kernel_ms(self.h))
 
     def destroy(self):
         if self.h:

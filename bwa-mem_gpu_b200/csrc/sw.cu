@@ -5,6 +5,9 @@
 // Mate rescue is a minor share of a paired-end run (a few jobs per unpaired read); this kernel is about identity, not about the roofline.
 #include "common.h"
 #include "sw_core.cuh"
+#include "sw_stripe.cuh"
+#include <algorithm>
+#include <vector>
 
 struct bwa_b200_sw {
     int device = 0, n_sm = 0;
@@ -14,8 +17,13 @@ struct bwa_b200_sw {
     uint32_t *d_qoff = nullptr, *d_qlen = nullptr, *d_toff = nullptr, *d_tlen = nullptr, *d_xtra = nullptr;
     bwa_b200_sw_result_t *d_res = nullptr;
     int16_t *d_ws = nullptr;
+    uint32_t *d_jobs = nullptr;                      // job indexes: the byte-kernel jobs of sw_stripe_kernel (longest target first), then the others
+    uint64_t jobs_cap = 0;
+    int smem_optin = 0;
     uint64_t ws_elems = 0;
     uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;        // around the kernel of the last batch
+    float last_kernel_ms = 0.f;
 };
 
 namespace {
@@ -25,13 +33,15 @@ constexpr int SW_THREADS = 64;
 __global__ void __launch_bounds__(SW_THREADS)
 sw_align2_kernel(SwParams S, uint32_t n, const uint8_t *__restrict__ qseq, const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qlen,
                  const uint8_t *__restrict__ tseq, const uint32_t *__restrict__ toff, const uint32_t *__restrict__ tlen,
-                 const uint32_t *__restrict__ xtra, int16_t *__restrict__ ws, uint32_t n_cap, uint32_t t_cap, bwa_b200_sw_result_t *__restrict__ res)
+                 const uint32_t *__restrict__ xtra, int16_t *__restrict__ ws, uint32_t n_cap, uint32_t t_cap, bwa_b200_sw_result_t *__restrict__ res,
+                 const uint32_t *__restrict__ jobs)
 {
     const size_t NS = (size_t)gridDim.x * blockDim.x;
     const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int16_t *my = ws + lane;                                   // H0 | H1 | E | Hmax, n_cap elements each, then t_cap row maxima
     int16_t *rowmax = ws + 4 * (size_t)n_cap * NS + lane;
-    for (size_t a = lane; a < n; a += NS) {
+    for (size_t k = lane; k < n; k += NS) {
+        const size_t a = jobs[k];
         bwa_b200_sw_result_t r;
         sw_align2((int)qlen[a], qseq + qoff[a], (int)tlen[a], tseq + toff[a], S, (int)xtra[a], my, NS, n_cap, rowmax, r);
         res[a] = r;
@@ -59,7 +69,9 @@ extern "C" int bwa_b200_sw_create(int device, bwa_b200_sw_t **out)
     cudaDeviceProp prop;
     B200_CUDA(cudaGetDeviceProperties(&prop, device));
     s->n_sm = prop.multiProcessorCount;
+    s->smem_optin = (int)prop.sharedMemPerBlockOptin;
     B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreate(&s->ev0)); B200_CUDA(cudaEventCreate(&s->ev1));
     *out = s;
     return BWA_B200_OK;
 }
@@ -70,12 +82,14 @@ extern "C" void bwa_b200_sw_destroy(bwa_b200_sw_t *s)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     cudaFree(s->d_q); cudaFree(s->d_t); cudaFree(s->d_qoff); cudaFree(s->d_qlen); cudaFree(s->d_toff); cudaFree(s->d_tlen); cudaFree(s->d_xtra);
-    cudaFree(s->d_res); cudaFree(s->d_ws);
+    cudaFree(s->d_res); cudaFree(s->d_ws); cudaFree(s->d_jobs);
+    cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
     cudaStreamDestroy(s->stream);
     delete s;
 }
 
 extern "C" uint64_t bwa_b200_sw_launches(const bwa_b200_sw_t *s) { return s ? s->launches : 0; }
+extern "C" float bwa_b200_sw_last_kernel_ms(const bwa_b200_sw_t *s) { return s ? s->last_kernel_ms : 0.f; }
 
 extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_params_t *p, uint64_t n_jobs,
                                        const uint8_t *qseq, uint64_t q_bytes, const uint32_t *qoff, const uint32_t *qlen,
@@ -85,12 +99,31 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
     if (!s || !p || (n_jobs && (!qseq || !qoff || !qlen || !tseq || !toff || !tlen || !xtra || !out))) { b200::set_error("sw_align2_host: bad argument"); return BWA_B200_ERR_ARG; }
     if (n_jobs == 0) return BWA_B200_OK;
     if (n_jobs > 0x7fffffffull) { b200::set_error("sw_align2_host: at most 2^31 jobs per call"); return BWA_B200_ERR_ARG; }
-    uint32_t max_q = 0, max_t = 0;
-    for (uint64_t a = 0; a < n_jobs; ++a) {
-        if ((uint64_t)qoff[a] + qlen[a] > q_bytes || (uint64_t)toff[a] + tlen[a] > t_bytes) { b200::set_error("sw_align2_host: job %llu lies outside its buffer", (unsigned long long)a); return BWA_B200_ERR_ARG; }
-        if (qlen[a] == 0 || qlen[a] > 32000u || tlen[a] > 0x3fffffffu) { b200::set_error("sw_align2_host: job %llu: query of %u bases (1 .. 32000 supported)", (unsigned long long)a, qlen[a]); return BWA_B200_ERR_ARG; }
-        max_q = qlen[a] > max_q ? qlen[a] : max_q; max_t = tlen[a] > max_t ? tlen[a] : max_t;
+    // Two classes.  Byte-kernel jobs (KSW_XBYTE: mem_matesw sets it when the read's best score fits a byte, src/bwamem_pair.c:150)
+    // with at most 256 query bases and a target that fits the row buffer run in sw_stripe_kernel, longest target first so that the
+    // four jobs of a warp finish together; everything else in the replay kernel.
+    static const bool no_stripe = getenv("BWA_B200_SW_NO_STRIPE") != nullptr;
+    constexpr uint32_t STRIPE_MAX_Q = 256, STRIPE_MAX_T = 6000;
+    uint32_t max_q = 0, max_t = 0, fast_q = 0, fast_t = 0;
+    std::vector<uint32_t> order(n_jobs);
+    uint64_t n_fast = 0;
+    {
+        std::vector<uint32_t> slow;
+        std::vector<uint32_t> cnt(STRIPE_MAX_T / 16 + 2, 0);
+        std::vector<uint8_t> fast(n_jobs);
+        for (uint64_t a = 0; a < n_jobs; ++a) {
+            if ((uint64_t)qoff[a] + qlen[a] > q_bytes || (uint64_t)toff[a] + tlen[a] > t_bytes) { b200::set_error("sw_align2_host: job %llu lies outside its buffer", (unsigned long long)a); return BWA_B200_ERR_ARG; }
+            if (qlen[a] == 0 || qlen[a] > 32000u || tlen[a] > 0x3fffffffu) { b200::set_error("sw_align2_host: job %llu: query of %u bases (1 .. 32000 supported)", (unsigned long long)a, qlen[a]); return BWA_B200_ERR_ARG; }
+            fast[a] = !no_stripe && (xtra[a] & 0x10000u) && qlen[a] <= STRIPE_MAX_Q && tlen[a] <= STRIPE_MAX_T;
+            if (fast[a]) { ++cnt[tlen[a] / 16]; ++n_fast; fast_q = std::max(fast_q, qlen[a]); fast_t = std::max(fast_t, tlen[a]); }
+            else { slow.push_back((uint32_t)a); max_q = std::max(max_q, qlen[a]); max_t = std::max(max_t, tlen[a]); }
+        }
+        uint32_t at = 0;                                     // counting sort by target length / 16, descending
+        for (size_t b = cnt.size(); b-- > 0;) { const uint32_t c = cnt[b]; cnt[b] = at; at += c; }
+        for (uint64_t a = 0; a < n_jobs; ++a) if (fast[a]) order[cnt[tlen[a] / 16]++] = (uint32_t)a;
+        std::copy(slow.begin(), slow.end(), order.begin() + n_fast);
     }
+    const uint64_t n_slow = n_jobs - n_fast;
     B200_CUDA(cudaSetDevice(s->device));
     int rc;
     if ((rc = grow(s->d_q, s->q_cap, q_bytes + 16)) || (rc = grow(s->d_t, s->t_cap, t_bytes + 16))) return rc;
@@ -101,17 +134,22 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
             (rc = grow(s->d_xtra, c4, need)) || (rc = grow(s->d_res, c5, need))) { s->job_cap = 0; return rc; }
         s->job_cap = need;
     }
-    // lanes: as many as there are jobs, up to 8 blocks per SM, fewer when the per-lane state of this batch would not fit 2 GB
+    // replay kernel: as many lanes as it has jobs, up to 8 blocks per SM, fewer when the per-lane state of this batch would not fit 2 GB
     const uint32_t n_cap = (max_q + 15) / 16 * 16 + 16, t_cap = max_t + 1;
     const uint64_t per_lane = 4ull * n_cap + t_cap;
-    uint64_t lanes = (uint64_t)s->n_sm * 8 * SW_THREADS;
-    const uint64_t budget = (2ull << 30) / 2;                      // int16 elements
-    if (lanes * per_lane > budget) lanes = budget / per_lane;
-    if (lanes > n_jobs) lanes = n_jobs;
-    uint32_t grid = (uint32_t)((lanes + SW_THREADS - 1) / SW_THREADS);
-    if (grid < 1) grid = 1;
-    if ((rc = grow(s->d_ws, s->ws_elems, (uint64_t)grid * SW_THREADS * per_lane))) return rc;
+    uint32_t grid = 0;
+    if (n_slow) {
+        uint64_t lanes = (uint64_t)s->n_sm * 8 * SW_THREADS;
+        const uint64_t budget = (2ull << 30) / 2;                      // int16 elements
+        if (lanes * per_lane > budget) lanes = budget / per_lane;
+        if (lanes > n_slow) lanes = n_slow;
+        grid = (uint32_t)((lanes + SW_THREADS - 1) / SW_THREADS);
+        if (grid < 1) grid = 1;
+        if ((rc = grow(s->d_ws, s->ws_elems, (uint64_t)grid * SW_THREADS * per_lane))) return rc;
+    }
+    if ((rc = grow(s->d_jobs, s->jobs_cap, n_jobs + n_jobs / 4 + 64))) return rc;
     cudaStream_t st = s->stream;
+    B200_CUDA(cudaMemcpyAsync(s->d_jobs, order.data(), n_jobs * 4, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(s->d_q, qseq, q_bytes, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(s->d_t, tseq, t_bytes, cudaMemcpyHostToDevice, st));
     B200_CUDA(cudaMemcpyAsync(s->d_qoff, qoff, n_jobs * 4, cudaMemcpyHostToDevice, st));
@@ -123,11 +161,42 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
     memset(&S, 0, sizeof(S));
     memcpy(S.mat, p->mat, 25);
     S.m = 5; S.o_del = p->o_del; S.e_del = p->e_del; S.o_ins = p->o_ins; S.e_ins = p->e_ins;
-    sw_align2_kernel<<<grid, SW_THREADS, 0, st>>>(S, (uint32_t)n_jobs, s->d_q, s->d_qoff, s->d_qlen, s->d_t, s->d_toff, s->d_tlen, s->d_xtra,
-                                                  s->d_ws, n_cap, t_cap, s->d_res);
-    B200_CUDA(cudaGetLastError());
-    s->launches += 1;
+    B200_CUDA(cudaEventRecord(s->ev0, st));
+    if (n_fast) {
+        b200sw::StripeParams SP;
+        memset(&SP, 0, sizeof(SP));
+        int mn = 127, mx = 0;
+        for (int a = 0; a < 25; ++a) { mn = std::min(mn, (int)p->mat[a]); mx = std::max(mx, (int)p->mat[a]); }
+        SP.shift = (256 - mn) & 255; SP.qmax = mx;
+        for (int t = 0; t < 5; ++t) {
+            for (int q = 0; q < 4; ++q) SP.tab[t] |= (uint32_t)(uint8_t)p->mat[t * 5 + q] << (8 * q);
+            SP.tabn[t] = (uint32_t)(uint8_t)p->mat[t * 5 + 4];
+        }
+        const int oe_del = p->o_del + p->e_del, oe_ins = p->o_ins + p->e_ins;
+        SP.noe_del2 = (uint32_t)(uint16_t)(int16_t)(-oe_del) * 0x00010001u; SP.ne_del2 = (uint32_t)(uint16_t)(int16_t)(-p->e_del) * 0x00010001u;
+        SP.noe_ins2 = (uint32_t)(uint16_t)(int16_t)(-oe_ins) * 0x00010001u; SP.ne_ins2 = (uint32_t)(uint16_t)(int16_t)(-p->e_ins) * 0x00010001u;
+        const uint32_t tc = (fast_t + 15) / 16 * 16;
+        const size_t smem = (size_t)b200sw::JOBS_PER_BLOCK * tc;
+        const int slen_max = (int)(fast_q + 15) / 16;
+        auto kern = slen_max <= 8 ? b200sw::sw_stripe_kernel<8> : (slen_max <= 12 ? b200sw::sw_stripe_kernel<12> : b200sw::sw_stripe_kernel<16>);
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_optin));
+        int occ = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, b200sw::BLOCK, smem));
+        if (occ < 1) occ = 1;
+        uint32_t g = (uint32_t)std::min<uint64_t>((n_fast + b200sw::JOBS_PER_BLOCK - 1) / b200sw::JOBS_PER_BLOCK, (uint64_t)s->n_sm * occ);
+        kern<<<g, b200sw::BLOCK, smem, st>>>(SP, (uint32_t)n_fast, s->d_jobs, s->d_q, s->d_qoff, s->d_qlen, s->d_t, s->d_toff, s->d_tlen, s->d_xtra, tc, s->d_res);
+        B200_CUDA(cudaGetLastError());
+        s->launches += 1;
+    }
+    if (n_slow) {
+        sw_align2_kernel<<<grid, SW_THREADS, 0, st>>>(S, (uint32_t)n_slow, s->d_q, s->d_qoff, s->d_qlen, s->d_t, s->d_toff, s->d_tlen, s->d_xtra,
+                                                      s->d_ws, n_cap, t_cap, s->d_res, s->d_jobs + n_fast);
+        B200_CUDA(cudaGetLastError());
+        s->launches += 1;
+    }
+    B200_CUDA(cudaEventRecord(s->ev1, st));
     B200_CUDA(cudaMemcpyAsync(out, s->d_res, n_jobs * sizeof(bwa_b200_sw_result_t), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&s->last_kernel_ms, s->ev0, s->ev1);
     return BWA_B200_OK;
 }

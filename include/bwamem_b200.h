@@ -378,6 +378,7 @@ int  bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_params_t *p, u
                              const uint8_t *tseq, uint64_t t_bytes, const uint32_t *toff, const uint32_t *tlen,
                              const uint32_t *xtra, bwa_b200_sw_result_t *out);
 uint64_t bwa_b200_sw_launches(const bwa_b200_sw_t *s);
+float bwa_b200_sw_last_kernel_ms(const bwa_b200_sw_t *s);      /* device time of the last batch's kernel (CUDA events on its stream) */
 
 /* ------------------------------------- seeds -> chains -> extension jobs -> alignment regions */
 /* The step between the two hot paths in the reference worker (src/bwamem.c:2055-2093 and :2286-2306), on the
@@ -387,10 +388,10 @@ uint64_t bwa_b200_sw_launches(const bwa_b200_sw_t *s);
  *   mem_chain2aln (:1170-1479: rmax window per chain, seeds by descending score, the estimated-extent test that
  *   skips seeds inside an earlier region, left / right jobs with h0 = seed length, SHORT / LONG batch choice),
  *   the local-vs-to-end rule (:1892-1901) and the region arithmetic (:2286-2306).
- * mem_flt_chained_seeds (:970-990) only acts on reads of about 757 bases and more (5.5 ln L <= 0.05 L: it then runs mem_seed_sw on
- * every chained seed).  Such reads do not fail the batch: they come back with no regions and are listed by
- * bwa_b200_aligner_skipped_reads, so that the caller routes just those through its own path (the local alignment mem_seed_sw needs is
- * bwa_b200_sw_align2_host).  mem_sort_dedup_patch and everything after it stay with the caller. */
+ * mem_flt_chained_seeds (:970-990) acts on reads of 757 bases and more at the default options (5.5 ln L <= 0.05 L): every seed of a kept
+ * chain is scored by mem_seed_sw (:774-808, ksw_align2 around the seed) and the low ones dropped.  That runs on the device as well
+ * (seedsw_kernel / chain_long_kernel, csrc/chain.cu), so reads of any length go through the same call.
+ * mem_sort_dedup_patch and everything after it stay with the caller. */
 typedef struct {               /* the mem_opt_t fields this stage reads (src/bwamem.h:34-73) */
     int32_t a, b, o_del, e_del, o_ins, e_ins, w;
     int32_t min_seed_len, max_occ, max_chain_gap, min_chain_weight, max_chain_extend;
@@ -464,8 +465,8 @@ typedef struct {
     uint64_t closed_form_jobs;  /* extension jobs answered in closed form (bwa_b200_extender_last_closed_form); not in cells */
 } bwa_b200_align_view_t;
 int  bwa_b200_align_device_view(bwa_b200_aligner_t *a, bwa_b200_align_view_t *v);
-/* reads of the last batch that were not aligned because mem_flt_chained_seeds would run mem_seed_sw on them (see above): *n of them,
- * indexes ascending in *read_idx (owned by the aligner, valid until its next call; NULL when there are none) */
+/* Kept for ABI compatibility: earlier versions left the reads mem_flt_chained_seeds acts on to the caller and listed them here; they are
+ * now aligned on the device, so *n is always 0 and *read_idx NULL. */
 int  bwa_b200_aligner_skipped_reads(bwa_b200_aligner_t *a, uint64_t *n, const uint32_t **read_idx);
 /* ---- the compact host boundary of the aligner: the smallest transfers that carry the same information (SURVEY 8e names the host leg
  * -- PCIe and host memory traffic of 8 GPUs behind one socket -- as the scaling risk; the reference ships one byte per base,
