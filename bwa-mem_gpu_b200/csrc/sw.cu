@@ -103,7 +103,7 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
     // with at most 256 query bases and a target that fits the row buffer run in sw_stripe_kernel, longest target first so that the
     // four jobs of a warp finish together; everything else in the replay kernel.
     static const bool no_stripe = getenv("BWA_B200_SW_NO_STRIPE") != nullptr;
-    constexpr uint32_t STRIPE_MAX_Q = 256, STRIPE_MAX_T = 6000;
+    constexpr uint32_t STRIPE_MAX_Q = 256, STRIPE_MAX_T = 6000;         // 32 jobs x 6000 row bytes = 192 KB of shared memory at most
     uint32_t max_q = 0, max_t = 0, fast_q = 0, fast_t = 0;
     std::vector<uint32_t> order(n_jobs);
     uint64_t n_fast = 0;
@@ -170,7 +170,7 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
         SP.shift = (256 - mn) & 255; SP.qmax = mx;
         for (int t = 0; t < 5; ++t) {
             for (int q = 0; q < 4; ++q) SP.tab[t] |= (uint32_t)(uint8_t)p->mat[t * 5 + q] << (8 * q);
-            SP.tabn[t] = (uint32_t)(uint8_t)p->mat[t * 5 + 4];
+            SP.tabn[t] = (uint32_t)(uint8_t)p->mat[t * 5 + 4] | 0x00800000u;     // byte 1 = 0 (padding), byte 2 = 0x80 (unused registers)
         }
         const int oe_del = p->o_del + p->e_del, oe_ins = p->o_ins + p->e_ins;
         SP.noe_del2 = (uint32_t)(uint16_t)(int16_t)(-oe_del) * 0x00010001u; SP.ne_del2 = (uint32_t)(uint16_t)(int16_t)(-p->e_del) * 0x00010001u;
@@ -178,8 +178,14 @@ extern "C" int bwa_b200_sw_align2_host(bwa_b200_sw_t *s, const bwa_b200_ext_para
         const uint32_t tc = (fast_t + 15) / 16 * 16;
         const size_t smem = (size_t)b200sw::JOBS_PER_BLOCK * tc;
         const int slen_max = (int)(fast_q + 15) / 16;
-        auto kern = slen_max <= 8 ? b200sw::sw_stripe_kernel<8> : (slen_max <= 12 ? b200sw::sw_stripe_kernel<12> : b200sw::sw_stripe_kernel<16>);
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_optin));
+        const bool sg = oe_del == oe_ins;
+        // instantiated for the vector counts of the usual read lengths (7: up to 112 bases, 10: up to 160, 16: up to 256) besides 4, 8
+        // and 12: a batch of one read length then runs the variant of the row loop that has no bound check (pass_u8<.., UNI>)
+#define SW_PICK(N) (sg ? b200sw::sw_stripe_kernel<N, true> : b200sw::sw_stripe_kernel<N, false>)
+        auto kern = slen_max <= 4 ? SW_PICK(4) : slen_max <= 7 ? SW_PICK(7) : slen_max <= 8 ? SW_PICK(8) : slen_max <= 10 ? SW_PICK(10)
+                  : slen_max <= 12 ? SW_PICK(12) : SW_PICK(16);
+#undef SW_PICK
+        if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, b200sw::BLOCK, smem));
         if (occ < 1) occ = 1;
