@@ -173,7 +173,7 @@ __device__ __forceinline__ uint64_t L2_at(const IndexView &ix, int b)
 
 // ------------------------------------------------------------------------------- fwd_kernel
 #ifndef FWD_MIN_BLOCKS
-#define FWD_MIN_BLOCKS 8        // measured on B200 (C2): 8 -> 1.41 ms, 10 -> 1.64 ms, 16 -> 2.05 ms (spills)
+#define FWD_MIN_BLOCKS 6        // measured on B200: C2 (32-bit rows) 6 = 8 -> 1.46 ms, 10 -> 1.64 ms, 16 -> 2.05 ms (spills); C3 (64-bit rows) 6 -> 4.30 ms, 8 -> 4.43 ms
 #endif
 template <typename RowT, int MINB, bool KT>
 __global__ void __launch_bounds__(FWD_THREADS, MINB)
@@ -286,7 +286,8 @@ __device__ __forceinline__ uint32_t seeds_of(uint32_t s, int max_occ)
 }
 
 #ifndef BACK_MIN_BLOCKS
-#define BACK_MIN_BLOCKS 10
+#define BACK_MIN_BLOCKS 7       // measured on B200 (tools/gpu_visit_r2x.sh, r2y.sh), C2 / C3 ms: 12 -> 5.10 / 15.26 (spills), 10 -> 4.03 / 12.19, 8 -> 3.96 / 10.77,
+                                // 7 -> 3.95 / 10.27, 6 -> 4.08 / 10.26: the lanes a register cap adds cost more in spills and replays than they hide
 #endif
 // Work distribution.  A read has one candidate per change of interval size (~30 for a 150 bp read)
 // and each is walked only a few steps, so a lane moves to its next candidate every few iterations.
@@ -847,7 +848,7 @@ using BackFn = void (*)(IndexView, const uint32_t *, const uint64_t *, uint32_t,
 // register budget variants (blocks of 128 lanes per SM): more resident lanes = more sectors in flight; KT = with the k-mer table
 template <typename RowT, bool KT> FwdFn fwd_variant_t(int minb)
 {
-    return minb >= 12 ? fwd_kernel<RowT, 12, KT> : (minb >= 10 ? fwd_kernel<RowT, 10, KT> : fwd_kernel<RowT, 8, KT>);
+    return minb >= 12 ? fwd_kernel<RowT, 12, KT> : (minb >= 10 ? fwd_kernel<RowT, 10, KT> : (minb >= 8 ? fwd_kernel<RowT, 8, KT> : fwd_kernel<RowT, 6, KT>));
 }
 FwdFn fwd_variant(bool narrow, int minb, bool kt)
 {
@@ -856,7 +857,8 @@ FwdFn fwd_variant(bool narrow, int minb, bool kt)
 }
 template <typename RowT, bool RESEED, bool KT> BackFn back_variant_t(int minb)
 {
-    return minb >= 12 ? back_kernel<RowT, 12, RESEED, KT> : (minb >= 10 ? back_kernel<RowT, 10, RESEED, KT> : back_kernel<RowT, 8, RESEED, KT>);
+    return minb >= 12 ? back_kernel<RowT, 12, RESEED, KT> : (minb >= 10 ? back_kernel<RowT, 10, RESEED, KT> : (minb >= 8 ? back_kernel<RowT, 8, RESEED, KT>
+         : (minb >= 7 ? back_kernel<RowT, 7, RESEED, KT> : back_kernel<RowT, 6, RESEED, KT>)));
 }
 template <bool RESEED> BackFn back_variant_r(bool narrow, int minb, bool kt)
 {
