@@ -365,7 +365,7 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
     ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dist)
     launches = al.launches - l0
     v = al.view()
-    al.profile(2)
+    al.profile(int(os.environ.get("BWA_B200_BENCH_PROFILE_MODE", "2")))     # 2: one event pair around the extension launch set (bins overlap); 1: every bin alone
     kt = {}
     for k in range(min(steps, 5)):
         with torch.cuda.stream(stream):
