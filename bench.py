@@ -424,9 +424,9 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
            "closed_form_jobs": int(v.closed_form_jobs),
-           "closed_form_note": "extension jobs whose query equals the head of the target except in its first base are answered without a "
-                               "matrix (proof: csrc/ext_pair_core.cuh closed_form_job; identical results); they are not in cells_per_step "
-                               "nor in extension_GCUPS",
+           "closed_form_note": "extension jobs whose query equals the head of the target except for at most two substituted bases are answered "
+                               "without a matrix (proof and conditions: csrc/ext_pair_core.cuh closed_form_job; identical results); they are "
+                               "not in cells_per_step nor in extension_GCUPS",
            "gpu_launches": int(launches), "kernel_ms": kavg,
            "params": "chain w=100 max_occ=500 (mem_opt_init otherwise); extension w=100 zdrop=100 end_bonus=5 banded"
                      + ("; re-seeding split_factor 1.5 split_width 10 max_mem_intv 20" if reseed else "; SMEM pass 1 only")}

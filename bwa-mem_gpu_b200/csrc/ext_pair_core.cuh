@@ -123,34 +123,45 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 }
 
 // ---- jobs answered in closed form -----------------------------------------------------------------------------------------------
-// An extension job whose query equals the head of its target except, possibly, in its first base -- what is left of a read beside a
-// maximal exact match when the read has no further difference on that side -- needs no matrix: with match score a, mismatch -b and
-// g = min(o_del + e_del, o_ins + e_ins) > a + b, the diagonal cell of row i is D(i) = h0 - mm (a + b) + (i + 1) a  (mm = 1 when the first
-// bases differ) and is the strict maximum of its row and of the last column:
-//   * every path to a cell (i, j), j != i, holds a gap and at most min(i, j) + 1 matches, so it scores at most
-//     h0 + (min(i, j) + 1) a - g < D(i); a path to (i, i) other than the diagonal holds an insertion and a deletion;
-//   * D(i) > 0 for every i as long as h0 > b, so `M = M ? M + s : 0` (src/ksw.c:924) never cuts the diagonal, the cell after a
-//     non-zero cell is always inside [beg, end) (src/ksw.c:959-965) and, with w >= 0, inside the band (:902-907);
-//   * the running maximum starts at h0 (:896) and moves only on m > max (:947): from row k = b / a + 1 on when mm = 1 (each such row
-//     with mj = i, so max_off stays 0), from row 0 on when mm = 0; a query of at most k bases leaves max = h0, max_i = max_j = -1;
-//   * the z-drop test (:950-957) is reached only in rows 0 .. k - 1 of the mm = 1 case with max - m = (a + b) - (i + 1) a <= b, so it
-//     cannot fire when zdrop <= 0 or b <= zdrop; rows after the last query row score at most h0 + qlen a - g < max and change nothing.
-// Hence score = gscore = D(qlen - 1), qle = tle = gtle = qlen, max_off = 0 (score = h0, qle = tle = 0 for the short case).  Sequences
-// with a base outside A/C/G/T, targets shorter than the query, h0 <= b and parameter sets outside the conditions go to the kernels.
-struct ClosedParams { int32_t ok, a, b; };
+// What is left of a read beside a maximal exact match usually differs from the reference in the base that ended the match and in
+// little else.  When the query equals the head of its target except for at most TWO substituted bases (no base outside A/C/G/T,
+// target at least as long as the query), ksw_extend2's six outputs follow from h0, qlen and the positions r1 < r2 of the differing
+// bases, without a matrix -- provided the main diagonal is the strict maximum of every row and of the last column.  With match a,
+// mismatch -b, g = min(o_del + e_del, o_ins + e_ins) and D(i) = h0 + (i + 1) a - (a + b) * #{differing bases at or before i}:
+//   * H(i, i) = D(i) as long as D stays positive (h0 > k b for k differences), so `M = M ? M + s : 0` (src/ksw.c:924) never cuts the
+//     diagonal; the cell after a non-zero cell is always inside [beg, end) (src/ksw.c:959-965) and, with w >= 0, inside the band.
+//   * Any other path to a cell holds a gap.  Measured against the diagonal over the same rows it can gain at most (a + b) per
+//     difference it avoids, and loses the gap: with a + b < g a path with two gaps (2 g > 2 (a + b)) or one that avoids a single
+//     difference never reaches the diagonal's score.  That settles k <= 1 for every job.
+//   * For k = 2 the one remaining rival leaves the diagonal before r1, pays one gap of d <= dmax bases (o + e d <= 2 (a + b)) and
+//     then runs along the diagonal shifted by d WITHOUT A SINGLE MISMATCH past r2.  Such a run covers the rows r1 + dmax < c < r2 on
+//     that shifted diagonal, so one mismatch q[c +- d] != t[c] there (or a cell outside the matrix) rules the shift out; a job is
+//     taken only when all 2 dmax shifts are ruled out that way (random sequence does it within a base or two; tandem repeats and
+//     adjacent differences do not, and go to the kernels).
+//   * The running maximum starts at h0 (src/ksw.c:896) and moves only on m > max (:947), always with mj = i, so max_off = 0 and
+//     (max_i, max_j) is the first of D's peaks -- the rows before r1, before r2 and the last row -- that holds the largest value, if it
+//     exceeds h0; gscore = D(qlen - 1) at row qlen - 1.  The z-drop test (:950-957) sees max - m <= k b with equal row and column
+//     distance, so it cannot fire when zdrop <= 0 or k b <= zdrop.  Rows after the last query row score below max and D(qlen - 1).
+//   * With a band, the columns beyond i + w still hold the first row's values (src/ksw.c:880-883) when row i reaches them: a gap of
+//     more than dmax bases, out of the running for w > dmax + 1.
+// Every step is checked against the oracle on 30 k jobs built around the conditions (tests/test_ext_pair_host.py).
+struct ClosedParams { int32_t ok, a, b, dmax, zdrop; };
 static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
 {
-    ClosedParams C{0, 0, 0};
+    ClosedParams C{0, 0, 0, 0, 0};
     const int a = p->mat[0], b = -p->mat[1];
     if (a < 1 || b < 1) return C;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j)
             if (p->mat[i * 5 + j] != (i == j ? a : -b)) return C;
     const int oe_del = p->o_del + p->e_del, oe_ins = p->o_ins + p->e_ins, g = oe_del < oe_ins ? oe_del : oe_ins;
-    if (p->e_del < 1 || p->e_ins < 1 || g <= a + b) return C;
-    if (p->use_band && p->w < 0) return C;
-    if (p->zdrop > 0 && b > p->zdrop) return C;
-    C.ok = 1; C.a = a; C.b = b;
+    if (p->e_del < 1 || p->e_ins < 1 || p->o_del < 0 || p->o_ins < 0 || g <= a + b) return C;
+    const int d_del = (2 * (a + b) - p->o_del) / p->e_del, d_ins = (2 * (a + b) - p->o_ins) / p->e_ins;
+    int dmax = d_del > d_ins ? d_del : d_ins;
+    if (dmax < 0) dmax = 0;
+    if (dmax > 16) return C;
+    if (p->use_band && p->w < dmax + 2) return C;
+    C.ok = 1; C.a = a; C.b = b; C.dmax = dmax; C.zdrop = p->zdrop;
     return C;
 }
 template <bool BYTES>
@@ -158,30 +169,50 @@ B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t 
 {
     const uint32_t ql = J.qlen[a], tl = J.tlen[a];
     const int h0 = (int)J.h0[a];
-    if (!C.ok || ql == 0 || tl < ql || h0 <= C.b || ql > 0x00ffffffu || h0 > 0x00ffffff) return false;
-    int mm;
+    if (!C.ok || ql == 0 || tl < ql || ql > 0x00ffffffu || h0 > 0x00ffffff) return false;
+    const uint8_t *qb = BYTES ? J.qb + J.qoff[a] : nullptr, *tb = BYTES ? J.tb + J.toff[a] : nullptr;
+    const uint32_t *qp = BYTES ? nullptr : J.qp + (J.qoff[a] >> 3), *tp = BYTES ? nullptr : J.tp + (J.toff[a] >> 3);
+    auto qa = [&](int i) -> uint32_t { return BYTES ? (uint32_t)qb[i] : (qp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
+    auto ta = [&](int i) -> uint32_t { return BYTES ? (uint32_t)tb[i] : (tp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
+    // the differing bases: at most two, every compared base in A/C/G/T
+    int k = 0, rr[2] = {0, 0};
     if (BYTES) {
-        const uint8_t *q = J.qb + J.qoff[a], *t = J.tb + J.toff[a];
-        if (q[0] > 3 || t[0] > 3) return false;
-        mm = q[0] != t[0];
-        for (uint32_t k = 1; k < ql; ++k) if (q[k] != t[k] || q[k] > 3) return false;
+        for (uint32_t i = 0; i < ql; ++i) {
+            if (qb[i] > 3 || tb[i] > 3) return false;
+            if (qb[i] != tb[i]) { if (k == 2) return false; rr[k++] = (int)i; }
+        }
     } else {
-        const uint32_t *q = J.qp + (J.qoff[a] >> 3), *t = J.tp + (J.toff[a] >> 3);
         const uint32_t nw = (ql + 7) >> 3;
-        mm = (int)(((q[0] ^ t[0]) >> 28) != 0);
         for (uint32_t w = 0; w < nw; ++w) {
-            const uint32_t qw = q[w], tw = t[w], rem = ql - 8 * w;
-            uint32_t x = (qw ^ tw) | ((qw | tw) & 0xccccccccu);          // a difference, or a code beyond 3, in some nibble
-            if (w == 0) x &= 0xcfffffffu;                                // the first base may differ (not be N)
-            if (rem < 8) x &= ~(0xffffffffu >> (4 * rem));
-            if (x) return false;
+            const uint32_t qw = qp[w], tw = tp[w], rem = ql - 8 * w;
+            const uint32_t m = rem < 8 ? ~(0xffffffffu >> (4 * rem)) : 0xffffffffu;
+            if ((qw | tw) & 0xccccccccu & m) return false;
+            uint32_t x = (qw ^ tw) & m;
+            for (int n = 0; x; ++n, x <<= 4)
+                if (x >> 28) { if (k == 2) return false; rr[k++] = (int)(8 * w) + n; }
         }
     }
-    const int k = C.b / C.a + 1;
-    const int g = h0 - mm * (C.a + C.b) + (int)ql * C.a;
+    if (h0 <= k * C.b || (C.zdrop > 0 && k * C.b > C.zdrop)) return false;
+    if (k == 2 && C.dmax > 0) {       // every shifted diagonal a single affordable gap reaches must break between the two differences
+        const int lo = rr[0] + C.dmax + 1, hi = rr[1];
+        if (lo >= hi) return false;
+        for (int d = 1; d <= C.dmax; ++d)
+            for (int sg = -1; sg <= 1; sg += 2) {
+                const int s = sg * d;
+                bool broken = false;
+                for (int c = lo; c < hi && !broken; ++c) broken = c + s >= (int)ql || qa(c + s) != ta(c);     // c + s >= lo - dmax > 0
+                if (!broken) return false;
+            }
+    }
+    // D at its peaks, in row order; the first one holding the largest value is where the maximum was last raised
+    const int ab = C.a + C.b, last = (int)ql - 1;
+    int best = h0, row = -1;
+    if (k >= 1 && rr[0] >= 1) { const int v = h0 + rr[0] * C.a; if (v > best) { best = v; row = rr[0] - 1; } }
+    if (k == 2) { const int v = h0 + rr[1] * C.a - ab; if (v > best) { best = v; row = rr[1] - 1; } }
+    const int g = h0 + (int)ql * C.a - k * ab;
+    if (g > best) { best = g; row = last; }
+    r->score = best; r->qle = row + 1; r->tle = row + 1;
     r->gscore = g; r->gtle = (int32_t)ql; r->max_off = 0;
-    if (mm == 0 || (int)ql - 1 >= k) { r->score = g; r->qle = (int32_t)ql; r->tle = (int32_t)ql; }
-    else { r->score = h0; r->qle = 0; r->tle = 0; }
     return true;
 }
 

@@ -123,9 +123,10 @@ def test_pair_source_wide_scores_long_queries(pkg, oracle, emul, kw):
             assert cells == cnt["cells"]
 
 
-CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=0, zdrop=4), True), (dict(w=300, zdrop=0, use_band=0), True),
+CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=6, zdrop=4), True), (dict(w=300, zdrop=0, use_band=0), True),
          (dict(w=20, zdrop=50, a=2, b=3), True), (dict(w=20, zdrop=10, a=2, b=5, o_del=7, e_del=2, o_ins=8, e_ins=1), True),
-         (dict(w=100, zdrop=3), False),                                           # the first row's drop of b = 4 would trip z-drop
+         (dict(w=100, zdrop=3), True),                                            # only jobs without a difference pass the z-drop condition
+         (dict(w=5, zdrop=100), False),                                           # band narrower than the gaps that have to be ruled out + 2
          (dict(w=33, zdrop=100, o_del=3, e_del=1, o_ins=5, e_ins=2, a=3, b=2), False),   # a gap is cheaper than a mismatch + a match
          (dict(w=50, zdrop=100, a=1, b=6), False)]
 
@@ -133,13 +134,17 @@ CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=0, 
 @pytest.mark.parametrize("kw,eligible", CF_KW)
 def test_closed_form_jobs_match_oracle(pkg, oracle, emul, kw, eligible):
     """closed_form_job (ext_pair_core.cuh): every job it takes has exactly ksw_extend2's six outputs, it takes exactly the jobs of the
-    documented shape, in both sequence forms, and only under the documented parameter conditions"""
+    documented shape (up to two substitutions, shifted diagonals ruled out), in both sequence forms, and only under the documented
+    parameter conditions"""
     L = emul.lib
     L.ext_closed_form_host.restype = C.c_longlong
     L.ext_closed_form_host.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 9
     ep = pkg.ext_params(**kw)
-    n_taken = 0
-    for seed, extra in ((71, dict()), (72, dict(qlen_range=(1, 12), h0_range=(1, 30))), (73, dict(qlen_range=(100, 600), h0_range=(19, 250)))):
+    dmax = synth.closed_form_eligible(**kw)
+    assert (dmax is not None) == eligible
+    n_taken = n_two = n_rep = 0
+    for seed, extra in ((71, dict()), (72, dict(qlen_range=(1, 12), h0_range=(1, 30))), (73, dict(qlen_range=(100, 600), h0_range=(19, 250))),
+                        (74, dict(qlen_range=(20, 160), h0_range=(19, 150)))):
         jobs = synth.make_flank_jobs(2500, seed=seed, w=kw["w"], **extra)
         n = jobs["qlen"].size
         res = np.zeros((n, 6), np.int32); flags = np.zeros(n, np.uint8)
@@ -153,11 +158,21 @@ def test_closed_form_jobs_match_oracle(pkg, oracle, emul, kw, eligible):
         want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
         got = flags != 0
         assert (flags[got] == 3).all()
-        assert (got == synth.closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4))).all()
-        assert (res[got] == want[got]).all(), np.nonzero((res != want).any(axis=1) & got)[0][:5]
+        mask = synth.closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4), dmax, kw["zdrop"])
+        assert (got == mask).all(), np.nonzero(got != mask)[0][:5]
+        bad = np.nonzero((res != want).any(axis=1) & got)[0]
+        assert bad.size == 0, (bad[:5], res[bad[:3]], want[bad[:3]], jobs["qlen"][bad[:3]], jobs["h0"][bad[:3]])
         n_taken += int(got.sum())
-    if eligible:
-        assert n_taken > 3000
+        # how many of the taken jobs have two differences, and how many two-difference jobs were refused (repeats, adjacent differences)
+        for k in np.nonzero(jobs["tlen"] >= jobs["qlen"])[0]:
+            ql = int(jobs["qlen"][k])
+            q = jobs["qseq"][int(jobs["qoff"][k]):int(jobs["qoff"][k]) + ql]; t = jobs["tseq"][int(jobs["toff"][k]):int(jobs["toff"][k]) + ql]
+            if (q < 4).all() and (t < 4).all() and int((q != t).sum()) == 2:
+                n_two += int(got[k]); n_rep += int(not got[k])
+    if eligible and (kw["zdrop"] == 0 or kw["zdrop"] >= 2 * kw.get("b", 4)):
+        assert n_taken > 3000 and n_two > 800 and n_rep > 100
+    elif eligible:
+        assert n_taken > 300
 
 
 def test_closed_form_on_general_jobs(pkg, oracle, emul):
@@ -177,5 +192,5 @@ def test_closed_form_on_general_jobs(pkg, oracle, emul):
         assert taken >= 0
         want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
         got = flags != 0
-        assert (got == synth.closed_form_mask(jobs)).all()
+        assert (got == synth.closed_form_mask(jobs, 1, 4, 4, 100)).all()
         assert (res[got] == want[got]).all()

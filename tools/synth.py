@@ -272,9 +272,10 @@ def make_sw_jobs(n_jobs: int, qlen_range=(30, 150), tlen_range=(100, 700), seed:
 
 def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=(1, 200), w: int = 100, pad8: bool = True):
     """Extension jobs as a maximal exact match leaves them in a read with few differences: the query equals the head of the target,
-    mostly with its first base changed (the base that ended the match).  A third of the jobs miss that shape by one detail -- a second
-    difference, an N on either side, a target shorter than the query, a small h0 -- so that a shortcut for the shape is tested on
-    both sides of every condition.  Same dict as make_ext_jobs."""
+    mostly with its first base changed (the base that ended the match) and zero to three further substitutions, a quarter of them over
+    a tandem repeat (where a shifted diagonal matches as well as the main one).  Many jobs miss the closed-form shape by one detail -- a
+    third difference, adjacent differences, an N on either side, a target shorter than the query, a small h0 -- so that the shortcut is
+    tested on both sides of every condition.  Same dict as make_ext_jobs."""
     rng = np.random.Generator(np.random.PCG64(seed))
     qlens = rng.integers(qlen_range[0], qlen_range[1] + 1, size=n_jobs)
     h0 = rng.integers(h0_range[0], h0_range[1] + 1, size=n_jobs).astype(np.uint32)
@@ -284,11 +285,21 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
         tl = ql + int(rng.integers(0, min(ql, 2 * w) + 1))
         t = rng.integers(0, 4, size=tl, dtype=np.uint8)
         q = t[:ql].copy()
+        if rng.random() < 0.25 and tl > 8:                       # a tandem repeat (period 1 .. 4) somewhere: shifted diagonals match there
+            per = int(rng.integers(1, 5)); at = int(rng.integers(0, tl - 4)); ln = int(rng.integers(4, 60))
+            unit = t[at:at + per].copy()
+            for x in range(at, min(tl, at + ln)):
+                t[x] = unit[(x - at) % per]
+            q = t[:ql].copy()
         u = rng.random()
         if u < 0.85:
             q[0] = (q[0] + int(rng.integers(1, 4))) & 3          # the mismatch that ended the seed
+        for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2, 3]))):   # further substitutions, anywhere (next to the first one included)
+            if ql > 1:
+                k = int(rng.integers(1, ql)) if rng.random() < 0.8 else min(ql - 1, int(rng.integers(1, 8)))
+                q[k] = (q[k] + int(rng.integers(1, 4))) & 3
         v = rng.random()
-        if v < 0.08 and ql > 1:                                   # a second difference somewhere
+        if v < 0.04 and ql > 1:                                   # one more difference somewhere
             k = int(rng.integers(1, ql)); q[k] = (q[k] + 1) & 3
         elif v < 0.13:                                            # N in the query / in the compared part of the target / beyond it
             q[int(rng.integers(0, ql))] = 4
@@ -315,24 +326,50 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
     return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
 
 
-def closed_form_mask(jobs: dict, a: int = 1, b: int = 4) -> np.ndarray:
-    """Which jobs have the shape the extender answers in closed form (an independent statement of closed_form_job's predicate):
-    query[1:] == target[1:qlen], every compared base in A/C/G/T, target at least as long as the query, h0 > b."""
+def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax: int = 4, zdrop: int = 100) -> np.ndarray:
+    """Which jobs the extender answers in closed form (an independent statement of closed_form_job's predicate, ext_pair_core.cuh):
+    target at least as long as the query, every compared base in A/C/G/T, at most two substituted bases, h0 > k b, k b <= zdrop, and
+    -- with two -- every diagonal shifted by 1 .. dmax either way has a mismatch (or leaves the matrix) on the rows strictly between
+    the first difference + dmax and the second."""
     n = jobs["qlen"].size
     out = np.zeros(n, bool)
-    for k in range(n):
-        ql, tl, h0 = int(jobs["qlen"][k]), int(jobs["tlen"][k]), int(jobs["h0"][k])
-        if ql == 0 or tl < ql or h0 <= b:
+    for j in range(n):
+        ql, tl, h0 = int(jobs["qlen"][j]), int(jobs["tlen"][j]), int(jobs["h0"][j])
+        if ql == 0 or tl < ql:
             continue
-        q = jobs["qseq"][int(jobs["qoff"][k]):int(jobs["qoff"][k]) + ql]; t = jobs["tseq"][int(jobs["toff"][k]):int(jobs["toff"][k]) + ql]
-        out[k] = bool((q < 4).all() and (t < 4).all() and (q[1:] == t[1:]).all())
+        q = jobs["qseq"][int(jobs["qoff"][j]):int(jobs["qoff"][j]) + ql].astype(np.int64)
+        t = jobs["tseq"][int(jobs["toff"][j]):int(jobs["toff"][j]) + ql].astype(np.int64)
+        if (q > 3).any() or (t > 3).any():
+            continue
+        diff = np.nonzero(q != t)[0]
+        k = len(diff)
+        if k > 2 or h0 <= k * b or (zdrop > 0 and k * b > zdrop):
+            continue
+        ok = True
+        if k == 2 and dmax > 0:
+            lo, hi = int(diff[0]) + dmax + 1, int(diff[1])
+            ok = lo < hi
+            for s in [x for d in range(1, dmax + 1) for x in (-d, d)] if ok else []:
+                rows = np.arange(lo, hi)
+                cols = rows + s
+                inside = cols < ql
+                if not ((~inside).any() or (q[cols[inside]] != t[rows[inside]]).any()):
+                    ok = False
+                    break
+        out[j] = ok
     return out
 
 
-def closed_form_eligible(w=100, zdrop=100, use_band=1, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, **_) -> bool:
-    """closed_params_from (ext_pair_core.cuh) restated: the parameter conditions of the closed-form answer"""
+def closed_form_eligible(w=100, zdrop=100, use_band=1, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, **_):
+    """closed_params_from (ext_pair_core.cuh) restated: None when the parameters rule the closed-form answer out, else dmax, the longest
+    gap that costs no more than two mismatches"""
     g = min(o_del + e_del, o_ins + e_ins)
-    return a >= 1 and b >= 1 and g > a + b and not (use_band and w < 0) and not (zdrop > 0 and b > zdrop)
+    if a < 1 or b < 1 or g <= a + b:
+        return None
+    dmax = max((2 * (a + b) - o_del) // e_del, (2 * (a + b) - o_ins) // e_ins, 0)
+    if dmax > 16 or (use_band and w < dmax + 2):
+        return None
+    return dmax
 
 
 def subset_jobs(jobs: dict, keep: np.ndarray) -> dict:
@@ -354,9 +391,10 @@ def subset_jobs(jobs: dict, keep: np.ndarray) -> dict:
 def dp_cells(oracle, jobs: dict, kw: dict, cnt_all: dict):
     """(cells the extender evaluates, jobs it answers in closed form) for a batch: the oracle's cell count without the jobs of the
     closed-form shape when the parameters admit the shortcut"""
-    if not closed_form_eligible(**kw):
+    dmax = closed_form_eligible(**kw)
+    if dmax is None:
         return cnt_all["cells"], 0
-    m = closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4))
+    m = closed_form_mask(jobs, kw.get("a", 1), kw.get("b", 4), dmax, kw.get("zdrop", 100))
     if not m.any():
         return cnt_all["cells"], 0
     _, c = oracle.ksw_batch(subset_jobs(jobs, m), oracle.make_params(**kw), n_threads=4)
