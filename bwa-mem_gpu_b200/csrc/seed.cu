@@ -153,6 +153,16 @@ __device__ __forceinline__ void bucket_occ4(const Bkt &b, int n, uint32_t cnt[4]
     cnt[0] = b.c[0] + ((uint32_t)n - c - g - t); cnt[1] = b.c[1] + c; cnt[2] = b.c[2] + g; cnt[3] = b.c[3] + t;
 }
 
+// v[b] for b in 0..3 without a branch and without a local array: the two bits of b pick through masks (three LOP3).  The nested
+// `b == 0 ? .. : b == 1 ? ..` form of this compiled to divergent branches in the extension loops (profiles: BSSY / BRA / BSYNC around
+// every counter and L2 pick, lanes split three ways by their base).
+__device__ __forceinline__ uint32_t sel4(int b, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3)
+{
+    const uint32_t m1 = 0u - (uint32_t)(b & 1), m2 = 0u - (uint32_t)((b >> 1) & 1);
+    const uint32_t lo = (v0 & ~m1) | (v1 & m1), hi = (v2 & ~m1) | (v3 & m1);
+    return (lo & ~m2) | (hi & m2);
+}
+
 // occurrences of one base among the first n symbols; nl / nh = all ones where the base's low / high
 // bit is ZERO (so plane ^ mask has a one wherever the plane bit matches the base)
 __device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base, uint32_t nl, uint32_t nh)
@@ -160,8 +170,7 @@ __device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base, u
     uint32_t mlo, mhi;
     first_n(n, mlo, mhi);
     const uint32_t r = __popc((b.w[0] ^ nl) & ((b.w[2] ^ nh) & mlo)) + __popc((b.w[1] ^ nl) & ((b.w[3] ^ nh) & mhi));
-    const uint32_t base_cnt = base == 0 ? b.c[0] : (base == 1 ? b.c[1] : (base == 2 ? b.c[2] : b.c[3]));
-    return base_cnt + r;
+    return sel4(base, b.c[0], b.c[1], b.c[2], b.c[3]) + r;
 }
 
 // cumulative counts by select chain (a dynamic index into the kernel-parameter copy of the index
@@ -169,6 +178,15 @@ __device__ __forceinline__ uint32_t bucket_occ1(const Bkt &b, int n, int base, u
 __device__ __forceinline__ uint64_t L2_at(const IndexView &ix, int b)
 {
     return b == 0 ? ix.L2[0] : (b == 1 ? ix.L2[1] : (b == 2 ? ix.L2[2] : (b == 3 ? ix.L2[3] : ix.L2[4])));
+}
+// the same for a base (0..3), branch-free
+template <typename RowT>
+__device__ __forceinline__ RowT L2_base(const IndexView &ix, int b)
+{
+    const uint32_t lo = sel4(b, (uint32_t)ix.L2[0], (uint32_t)ix.L2[1], (uint32_t)ix.L2[2], (uint32_t)ix.L2[3]);
+    if (sizeof(RowT) == 4) return (RowT)lo;
+    const uint32_t hi = sel4(b, (uint32_t)(ix.L2[0] >> 32), (uint32_t)(ix.L2[1] >> 32), (uint32_t)(ix.L2[2] >> 32), (uint32_t)(ix.L2[3] >> 32));
+    return (RowT)((uint64_t)hi << 32 | lo);
 }
 
 // ------------------------------------------------------------------------------- fwd_kernel
@@ -247,13 +265,10 @@ fwd_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *__
             bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
             bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
             uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
-            ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
-            uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
-            nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
-            if (cb < 3) nk += s3;
-            if (cb < 2) nk += s2;
-            if (cb < 1) nk += s1;
-            nl = (RowT)L2_at(ix, cb) + 1 + tkc;
+            ns = sel4(cb, s0, s1, s2, s3);
+            const uint32_t tkc = sel4(cb, tk[0], tk[1], tk[2], tk[3]);
+            nk = k + (RowT)(l <= primary && l + s - 1 >= primary) + (RowT)sel4(cb, s3 + s2 + s1, s3 + s2, s3, 0u);
+            nl = L2_base<RowT>(ix, cb) + 1 + tkc;
             if (by_table) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); }
         }
         if (ns != s) {
@@ -447,7 +462,7 @@ back_kernel(IndexView ix, const uint32_t *__restrict__ packed, const uint64_t *_
                 const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
                 const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
                 ns = ol - ok;
-                nk = (RowT)L2_at(ix, b) + 1 + ok;
+                nk = L2_base<RowT>(ix, b) + 1 + ok;
                 if (by_table) { ns = (uint32_t)(e & KT_SAT); nk = (RowT)(e >> 24); }
                 fail = RESEED ? ns <= mi1 : ns == 0;
             }
@@ -507,13 +522,10 @@ __device__ __forceinline__ void fwd_extend(const IndexView &ix, uint64_t pol, Ro
     bucket_occ4(b0, (int)(j0 & 63) + 1, tk);
     bucket_occ4(b1, (int)(j1 & 63) + 1, tl);
     const uint32_t s3 = tl[3] - tk[3], s2 = tl[2] - tk[2], s1 = tl[1] - tk[1], s0 = tl[0] - tk[0];
-    ns = cb == 0 ? s0 : (cb == 1 ? s1 : (cb == 2 ? s2 : s3));
-    const uint32_t tkc = cb == 0 ? tk[0] : (cb == 1 ? tk[1] : (cb == 2 ? tk[2] : tk[3]));
-    nk = k + (RowT)(l <= primary && l + s - 1 >= primary);
-    if (cb < 3) nk += s3;
-    if (cb < 2) nk += s2;
-    if (cb < 1) nk += s1;
-    nl = (RowT)L2_at(ix, cb) + 1 + tkc;
+    ns = sel4(cb, s0, s1, s2, s3);
+    const uint32_t tkc = sel4(cb, tk[0], tk[1], tk[2], tk[3]);
+    nk = k + (RowT)(l <= primary && l + s - 1 >= primary) + (RowT)sel4(cb, s3 + s2 + s1, s3 + s2, s3, 0u);
+    nl = L2_base<RowT>(ix, cb) + 1 + tkc;
 }
 
 // backward extension of (k, s) by base b: x[0] and x[2] of bwt_extend(ik, ok, 1), ok[b]
@@ -528,7 +540,7 @@ __device__ __forceinline__ void back_extend(const IndexView &ix, uint64_t pol, R
     const uint32_t ok = bucket_occ1(b0, (int)(j0 & 63) + 1, b, nl, nh);
     const uint32_t ol = bucket_occ1(b1, (int)(j1 & 63) + 1, b, nl, nh);
     ns = ol - ok;
-    nk = (RowT)L2_at(ix, b) + 1 + ok;
+    nk = L2_base<RowT>(ix, b) + 1 + ok;
 }
 
 __device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, uint64_t woff, int i)
@@ -804,7 +816,7 @@ locate_kernel(IndexView ix, uint64_t *__restrict__ rbeg, const unsigned long lon
                 const int off = (int)(j & 63);
                 const uint32_t lw = off < 32 ? b.w[0] : b.w[1], hw = off < 32 ? b.w[2] : b.w[3];
                 const int sym = (int)(((lw >> (off & 31)) & 1u) | (((hw >> (off & 31)) & 1u) << 1));
-                k = (RowT)L2_at(ix, sym) + bucket_occ1(b, off + 1, sym, (sym & 1) ? 0u : 0xffffffffu, (sym & 2) ? 0u : 0xffffffffu);
+                k = L2_base<RowT>(ix, sym) + bucket_occ1(b, off + 1, sym, (sym & 1) ? 0u : 0xffffffffu, (sym & 2) ? 0u : 0xffffffffu);
                 ++steps;
             }
         }
