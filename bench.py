@@ -410,8 +410,25 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
     t0 = time.perf_counter()
     for _ in range(reps):
         step_compact()
-    e2e_s = max_over_ranks(time.perf_counter() - t0, dist)
+    e2e_sync_s = max_over_ranks(time.perf_counter() - t0, dist)
     e2e_launches = (multi.launches - l0m) // reps
+    # the same steps as a driver that streams batches issues them: the next batch is submitted before the previous one is waited for
+    # (bwa_b200_multi_submit_compact / _wait, two batches in flight; every batch's H2D and D2H still inside the timed region)
+    def submit():
+        return multi.submit_compact(pin["packed2"].data_ptr(), None, L, n, pin["nlist"].data_ptr() if bt.n_n else None, bt.n_n, sp, cp, ep)
+    chk = multi.wait(submit(), copy=True, gather=True)
+    assert chk["regions"].tobytes() == comp["regions"].tobytes(), "a streamed batch returned different regions than the synchronous call"
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tk = submit()
+    for _ in range(reps - 1):
+        tn = submit()
+        multi.wait(tk, copy=False, gather=False)
+        tk = tn
+    multi.wait(tk, copy=False, gather=False)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dist)
     multi.destroy()
     kavg = {k: float(np.mean(x)) for k, x in kt.items()}
     ext_ms = kavg.get("ext_phase", 0.0)
@@ -420,6 +437,7 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
     res = {"reads_per_s": world * n * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
            "e2e_reads_per_s": world * n * reps / e2e_s, "e2e_h2d_bytes_per_step": bt.h2d_compact, "e2e_d2h_bytes_per_step": d2h,
            "e2e_chunks_per_step": int((n + chunk - 1) // chunk), "e2e_gpu_launches": int(e2e_launches), "e2e_identical_to_full_records": same_c,
+           "e2e_one_batch_at_a_time_reads_per_s": world * n * reps / e2e_sync_s, "e2e_batches_in_flight": 2,
            "e2e_full_records_one_batch_in_flight": e2e_one, "e2e_full_records_h2d_bytes_per_step": bt.h2d, "e2e_full_records_d2h_bytes_per_step": d2h_full,
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
@@ -1046,8 +1064,11 @@ def main():
                 "d2h_bytes_per_step": chained["e2e_d2h_bytes_per_step"], "chunks_per_step": chained["e2e_chunks_per_step"],
                 "identical_to_full_records": chained["e2e_identical_to_full_records"],
                 "full_records_one_batch_in_flight": chained["e2e_full_records_one_batch_in_flight"],
-                "how": "bwa_b200_multi_align_compact from pinned host buffers: 2-bit reads in, 40-byte region records out, the batch dealt in chunks to "
-                       "%d worker threads of the rank's device (the reference's NB_STREAMS pattern, src/fastmap.c:31), every chunk's H2D and D2H inside the timed region" % args.e2e_workers,
+                "one_batch_at_a_time": chained["e2e_one_batch_at_a_time_reads_per_s"], "batches_in_flight": chained["e2e_batches_in_flight"],
+                "how": "bwa_b200_multi_submit_compact / _wait from pinned host buffers, as a driver that streams batches calls them (the next batch "
+                       "submitted before the previous one is waited for: two in flight, the reference's NB_STREAMS pattern, src/fastmap.c:31): 2-bit reads "
+                       "in, 40-byte region records out, every batch dealt in chunks to %d worker threads of the rank's device, every chunk's H2D and D2H "
+                       "inside the timed region; one_batch_at_a_time = the same through the synchronous bwa_b200_multi_align_compact" % args.e2e_workers,
                 "workers": args.e2e_workers},
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
         "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "mate_rescue_sw": mate_sw, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,

@@ -125,7 +125,7 @@ SYMBOLS = [
     "bwa_b200_region_opt_default", "bwa_b200_finish_regions_host",
     "bwa_b200_sw_create", "bwa_b200_sw_destroy", "bwa_b200_sw_align2_host", "bwa_b200_sw_launches", "bwa_b200_sw_last_kernel_ms",
     "bwa_b200_packed2_words", "bwa_b200_pack2_codes", "bwa_b200_pack2_ascii", "bwa_b200_align_host_compact",
-    "bwa_b200_multi_create", "bwa_b200_multi_set_contigs", "bwa_b200_multi_align_compact", "bwa_b200_multi_n_workers",
+    "bwa_b200_multi_create", "bwa_b200_multi_set_contigs", "bwa_b200_multi_align_compact", "bwa_b200_multi_submit_compact", "bwa_b200_multi_wait", "bwa_b200_multi_n_workers",
     "bwa_b200_multi_worker_chunks", "bwa_b200_multi_launches", "bwa_b200_multi_destroy",
 ]
 
@@ -226,6 +226,9 @@ def lib():
         L.bwa_b200_multi_set_contigs.argtypes = [vp, C.c_int32, vp, vp, vp]
         L.bwa_b200_multi_align_compact.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams),
                                                    C.POINTER(ExtParams), C.POINTER(MultiResult)]
+        L.bwa_b200_multi_submit_compact.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint64, C.POINTER(SeedParams), C.POINTER(ChainParams),
+                                                    C.POINTER(ExtParams), C.POINTER(C.c_int)]
+        L.bwa_b200_multi_wait.argtypes = [vp, C.c_int, C.POINTER(MultiResult)]
         L.bwa_b200_multi_n_workers.argtypes = [vp]
         L.bwa_b200_multi_worker_chunks.argtypes = [vp, C.c_int]
         L.bwa_b200_multi_worker_chunks.restype = C.c_uint64
@@ -653,12 +656,29 @@ class MultiAligner:
         alt = np.ascontiguousarray(is_alt, dtype=np.int32) if is_alt is not None else None
         check(lib().bwa_b200_multi_set_contigs(self.h, ln.size, _p(off), _p(ln), _p(alt)))
 
+    def submit_compact(self, packed2_ptr, len_ptr, uniform_len, n, nlist_ptr, n_n, seed_p, chain_p, ext_p) -> int:
+        """start a batch and return its ticket; at most two in flight (bwa_b200_multi_submit_compact)"""
+        t = C.c_int(-1)
+        check(lib().bwa_b200_multi_submit_compact(self.h, packed2_ptr, len_ptr or None, uniform_len, n, nlist_ptr or None, n_n, C.byref(seed_p), C.byref(chain_p),
+                                                  C.byref(ext_p), C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int, copy=True, gather=True):
+        """block until the batch behind the ticket is done; same dict as align_compact"""
+        out = MultiResult()
+        check(lib().bwa_b200_multi_wait(self.h, int(ticket), C.byref(out)))
+        return self._result(out, int(out.n_reads), copy, gather)
+
     def align_compact(self, packed2_ptr, len_ptr, uniform_len, n, nlist_ptr, n_n, seed_p, chain_p, ext_p, copy=True, gather=True):
         """regions of the whole batch; gather=True puts the chunks' records in read order (a host copy), False returns them as the chunks landed
         together with chunk_region_off"""
         out = MultiResult()
         check(lib().bwa_b200_multi_align_compact(self.h, packed2_ptr, len_ptr or None, uniform_len, n, nlist_ptr or None, n_n, C.byref(seed_p), C.byref(chain_p),
                                                  C.byref(ext_p), C.byref(out)))
+        return self._result(out, n, copy, gather)
+
+    @staticmethod
+    def _result(out, n, copy, gather):
         nregs = _view(out.n_regions_per_read, n, np.uint32, copy)
         coff = _view(out.chunk_region_off, out.n_chunks, np.uint64, True)
         regs = _view(out.regions, out.n_regions, REGION_COMPACT_DTYPE, copy and not gather)

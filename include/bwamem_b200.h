@@ -518,6 +518,17 @@ int  bwa_b200_multi_set_contigs(bwa_b200_multi_t *m, int32_t n, const int64_t *o
 int  bwa_b200_multi_align_compact(bwa_b200_multi_t *m, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len,
                                   uint64_t n_reads, const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp,
                                   const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep, bwa_b200_multi_result_t *out);
+/* The same with two batches in flight: submit returns at once with a ticket (0 or 1), wait blocks until that batch is done and hands
+ * out its results, which stay valid until the second submit after it.  The workers drain the older batch first and go straight on to
+ * the next, so the tail of one batch (its last chunk's results on their way to the host) and the head of the next (its first chunk's
+ * reads on their way to the device) run under kernels instead of between calls -- how a driver that streams batches uses the library
+ * (the reference keeps NB_STREAMS = 2 batches per thread in flight the same way, src/fastmap.c:31, src/bwamem.c:2040-2181).  The read
+ * buffers of a batch must stay untouched until its wait returns; the parameter blocks are copied.  Submit and wait from one thread.
+ * bwa_b200_multi_align_compact is submit + wait. */
+int  bwa_b200_multi_submit_compact(bwa_b200_multi_t *m, const uint32_t *packed2, const uint32_t *read_len, uint32_t uniform_len,
+                                   uint64_t n_reads, const uint64_t *n_list, uint64_t n_n, const bwa_b200_seed_params_t *sp,
+                                   const bwa_b200_chain_params_t *cp, const bwa_b200_ext_params_t *ep, int *ticket);
+int  bwa_b200_multi_wait(bwa_b200_multi_t *m, int ticket, bwa_b200_multi_result_t *out);
 int  bwa_b200_multi_n_workers(const bwa_b200_multi_t *m);
 uint64_t bwa_b200_multi_worker_chunks(const bwa_b200_multi_t *m, int worker);   /* chunks a worker has processed since creation */
 uint64_t bwa_b200_multi_launches(const bwa_b200_multi_t *m);

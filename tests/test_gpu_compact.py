@@ -135,3 +135,38 @@ def test_multi_refuses_unsorted_n_list(pkg, setup):
     with pytest.raises(pkg.B200Error):
         m.align_compact(p2.ctypes.data, rl.ctypes.data, 0, 300, bad.ctypes.data, bad.size, *params)
     m.destroy()
+
+
+@pytest.mark.parametrize("chunk,workers", [(200, 2), (5000, 1), (77, 3)])
+def test_multi_two_batches_in_flight(pkg, setup, chunk, workers):
+    """bwa_b200_multi_submit_compact / _wait: two different batches in flight, several rounds through the two slots; every batch's
+    results equal the synchronous call's, whatever the order the workers finished the chunks in; a third submit is refused"""
+    g, idx = setup
+    params = (pkg.seed_params(19, 500), pkg.chain_params(w=100), pkg.ext_params())
+    batches = []
+    for seed, n in ((21, 1800), (22, 2300), (23, 900)):
+        flat, off = ragged_reads(g, n, seed)
+        p2, rl, nl = pkg.pack2_codes(flat, off)
+        batches.append((p2, rl, nl, n))
+    m = pkg.MultiAligner(idx, [0], workers, chunk, 150)
+    want = [m.align_compact(p2.ctypes.data, rl.ctypes.data, 0, n, nl.ctypes.data, nl.size, *params) for p2, rl, nl, n in batches]
+
+    def submit(k):
+        p2, rl, nl, n = batches[k]
+        return m.submit_compact(p2.ctypes.data, rl.ctypes.data, 0, n, nl.ctypes.data, nl.size, *params)
+    order = [0, 1, 2, 1, 0, 2, 2, 0]
+    t_prev = submit(order[0])
+    for i in range(1, len(order)):
+        t_next = submit(order[i])                    # two in flight
+        if i == 1:
+            with pytest.raises(pkg.B200Error):
+                submit(2)                            # a third is refused, and refusing it leaves the two alone
+        got = m.wait(t_prev)
+        w = want[order[i - 1]]
+        assert (got["n_regions"] == w["n_regions"]).all() and got["regions"].tobytes() == w["regions"].tobytes()
+        t_prev = t_next
+    got = m.wait(t_prev)
+    assert got["regions"].tobytes() == want[order[-1]]["regions"].tobytes()
+    with pytest.raises(pkg.B200Error):
+        m.wait(t_prev)                               # nothing behind the ticket any more... until it is submitted again
+    m.destroy()
