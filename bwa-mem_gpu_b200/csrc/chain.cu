@@ -161,21 +161,23 @@ jobs_kernel(uint32_t n_reads, int64_t l_pac, const uint32_t *__restrict__ read_l
     });
 }
 
-// one warp per job
+// LPJ lanes per job (32 / LPJ jobs per warp): a job of a 150 bp read has at most 17 query and 30 target words, so a whole warp per
+// job leaves most lanes idle and pays the job's descriptor loads once per warp
+template <int LPJ>
 __global__ void __launch_bounds__(256)
 cut_jobs_kernel(uint32_t n_jobs, int64_t l_pac, const uint32_t *__restrict__ pac, int64_t pac_words,
                 const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off, JobArrays J,
                 uint32_t *__restrict__ qp, uint32_t *__restrict__ tp)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_jobs; j += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t sub = threadIdx.x & (LPJ - 1);
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / LPJ; j < n_jobs; j += (gridDim.x * blockDim.x) / LPJ) {
         const JobAux a = J.aux[j];
         const uint32_t ql = J.qlen[j], tl = J.tlen[j], read = a.read_flags & AUX_READ;
         const uint64_t w0 = word_off[read];
         const int64_t rd_words = (int64_t)(word_off[read + 1] - w0);
         uint32_t *q = qp + (J.qoff[j] >> 3), *t = tp + (J.toff[j] >> 3);
-        for (uint32_t w = lane; w < (ql + 7) >> 3; w += 32) q[w] = cut_query_word(packed_reads + w0, rd_words, a, w, ql);
-        for (uint32_t w = lane; w < (tl + 7) >> 3; w += 32) t[w] = cut_target_word(pac, pac_words, l_pac, a, w, tl);
+        for (uint32_t w = sub; w < (ql + 7) >> 3; w += LPJ) q[w] = cut_query_word(packed_reads + w0, rd_words, a, w, ql);
+        for (uint32_t w = sub; w < (tl + 7) >> 3; w += LPJ) t[w] = cut_target_word(pac, pac_words, l_pac, a, w, tl);
     }
 }
 
@@ -517,10 +519,13 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
                                                       a->d_chain_off, a->d_cseed_off)));
     a->launches += 1;
     if (n_jobs) {
-        const uint64_t warps = n_jobs < (uint64_t)a->seeder->n_sm * 64 ? n_jobs : (uint64_t)a->seeder->n_sm * 64;
+        static const int lpj = getenv("BWA_B200_CUT_LPJ") ? atoi(getenv("BWA_B200_CUT_LPJ")) : 16;     // C2: 32 -> 0.53 ms, 16 -> 0.46, 8 -> 0.46
+        auto kern = lpj <= 8 ? cut_jobs_kernel<8> : (lpj <= 16 ? cut_jobs_kernel<16> : cut_jobs_kernel<32>);
+        const uint64_t groups = (n_jobs * (uint64_t)(lpj <= 8 ? 8 : (lpj <= 16 ? 16 : 32)) + 31) / 32;      // warps' worth of work
+        const uint64_t warps = groups < (uint64_t)a->seeder->n_sm * 64 ? groups : (uint64_t)a->seeder->n_sm * 64;
         B200_LAUNCH(prof, "cut_jobs_kernel", st,
-            (cut_jobs_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((uint32_t)n_jobs, (int64_t)a->idx->l_pac, a->idx->d_pac, (int64_t)((a->idx->l_pac + 15) / 16 + 1),
-                                                                         d_packed, d_woff, a->J, a->d_qp, a->d_tp)));
+            (kern<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((uint32_t)n_jobs, (int64_t)a->idx->l_pac, a->idx->d_pac, (int64_t)((a->idx->l_pac + 15) / 16 + 1),
+                                                              d_packed, d_woff, a->J, a->d_qp, a->d_tp)));
         a->launches += 1;
         B200_CUDA(cudaGetLastError());
         rc = b200_ext_run_packed(a->ext, ep, (uint32_t)n_jobs, a->d_qp, a->J.qoff, a->J.qlen, a->d_tp, a->J.toff, a->J.tlen, a->J.h0, a->d_res, a->b_max_len);
