@@ -658,6 +658,39 @@ def run_mate_sw(args, pkg):
     return res
 
 
+def run_long_reads(args, pkg, idx, genome, prefix, flush, lens):
+    """Reads long enough for mem_flt_chained_seeds to act (src/bwamem.c:970-990: every seed of a kept chain scored by mem_seed_sw's local
+    alignment, :774-808, the low ones dropped) through the same bwa_b200_align_* step: 20 000 x 2 000 bp against the C2 index, 5 %
+    substitutions and one deletion of 1-5 bases per read; regions compared with the reference's own functions on a sample."""
+    n_l, L_l = 20_000, 2_000
+    rng = np.random.Generator(np.random.PCG64(4321))
+    pos = rng.integers(0, genome.size - L_l - 8, size=n_l, dtype=np.int64)
+    dpos = rng.integers(100, L_l - 100, size=n_l); dlen = rng.integers(1, 6, size=n_l)
+    col = np.arange(L_l, dtype=np.int64)[None, :]
+    reads = genome[pos[:, None] + col + (col >= dpos[:, None]) * dlen[:, None]].astype(np.uint8)
+    sub = rng.random(reads.shape) < 0.05
+    reads = np.where(sub, (reads + rng.integers(1, 4, size=reads.shape, dtype=np.uint8)) & 3, reads).astype(np.uint8)
+    odd = np.arange(n_l) % 2 == 1                       # every other read from the reverse strand
+    reads[odd] = (3 - reads[odd])[:, ::-1]
+    bt = Batch(pkg, reads)
+    res, host, _ = run_chained(args, pkg, idx, bt, flush, None, 1, lens, reseed=False, steps=3)
+    res["workload"] = f"{n_l} x {L_l} bp reads (5% substitutions, one 1-5 base deletion each, both strands) vs the {args.genome} bp genome"
+    if not args.no_cpu_baseline:
+        sample = 2_000
+        cpu = CpuChained(genome, prefix, lens)
+        cpu.run(reads[:200])
+        t0 = time.perf_counter()
+        out = cpu.run(reads[:sample])
+        cdt = time.perf_counter() - t0
+        same = same_regions(out, host, sample)
+        assert same, "long reads: GPU regions differ from the CPU reference on the bench sample"
+        res["cpu_baseline"] = {"value": sample / cdt, "unit": UNIT, "cores": cpu.threads, "kind": cpu.kind,
+                               "sample": f"first {sample} reads, {cpu.threads} host threads, the fork's mem_chain .. mem_flt_chained_seeds (mem_seed_sw) .. mem_chain2aln",
+                               "gpu_output_identical_on_sample": same}
+        cpu.close()
+    return res
+
+
 def seeding_roofline(pkg, local, genome, prefix, reads, kavg, n, index_bytes, pk, pk_src, idx=None, bt=None):
     """roofline block of the dominant seeding kernel: algorithmic bytes = the bucket sectors / LF steps / SA samples the reference's CPU
     algorithm touches on the same reads (instrumented oracle), over the kernel's live CUDA-event time"""
@@ -979,10 +1012,11 @@ def main():
         if dref:
             dist.destroy_process_group()
         return
-    mate_sw = None
+    mate_sw = long_reads = None
     if not args.no_extras:
         cigar = run_cigar(args, pkg, flush)
         mate_sw = run_mate_sw(args, pkg)
+        long_reads = run_long_reads(args, pkg, idx, genome, prefix, flush, lens)
 
     # ---- rooflines: dominant seeding kernel (HBM sectors) and the extension launch set (INT ALU), both from live CUDA-event times
     kavg = chained["kernel_ms"]
@@ -1071,7 +1105,7 @@ def main():
                        "inside the timed region; one_batch_at_a_time = the same through the synchronous bwa_b200_multi_align_compact" % args.e2e_workers,
                 "workers": args.e2e_workers},
         "roofline": roofline, "roofline_extension": ext_roof, "cpu_baseline": cpu_baseline,
-        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "mate_rescue_sw": mate_sw, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,
+        "sub_metrics": {"chained": chained, "chained_reseed": chained_rs, "fused_one_seed": fused, "cigar": cigar, "mate_rescue_sw": mate_sw, "long_reads": long_reads, "c3": c3, "c4_extension_sweep": c4, "c5_seeding": c5, "bwa_mem_cpu": bwa_mem,
                         "extension_GCUPS": gcups, "oracle_work_per_read": per_read,
                         "seeding_Mreads_per_s": n / (sum(kavg[k] for k in ("fwd_kernel", "back_kernel", "fill_kernel", "locate_kernel") if k in kavg) / 1e3) / 1e6},
     }

@@ -18,6 +18,7 @@
 //   finish_kernel   one lane per read: local-vs-to-end rule and the region arithmetic.
 #include "internal.h"
 #include "chain_core.cuh"
+#include "sw_stripe.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <functional>
@@ -82,28 +83,48 @@ chain_kernel(uint32_t n_reads, bwa_b200_chain_params_t P, Contigs ctg, SeedView 
     cnt[r] = c;
 }
 
-// mem_seed_sw for every chain seed of the long reads chain_kernel listed: one block per read, one seed per lane at a time, the
-// alignment's state (H, E, the query window: 1000 bytes per lane) in shared memory at lane stride
+// mem_seed_sw for every chain seed of the long reads chain_kernel listed: one block per read, one seed per group of FOUR lanes -- the
+// eight 16-bit lanes of the reference's striped ksw_i16, its vectors in registers (pass_i16_score, sw_stripe.cuh).  The first version
+// replayed the striping position by position, one seed per lane with the state in shared memory: 231 ms for the 0.8 M seeds of
+// 20 000 reads of 2 kb, 84 % of that batch's step.
 constexpr int SEEDSW_NT = 64;
-constexpr size_t SEEDSW_SMEM = (size_t)SEEDSW_NT * SEEDSW_MAX * 5;
+constexpr int SEEDSW_VEC = (SEEDSW_MAX + 7) / 8;             // vectors of the longest window (199 bases): 25
+struct SeedSwQ4 { const uint32_t *rd; int qb; __device__ __forceinline__ int operator()(int i) const { return read_base(rd, qb + i); } };
+struct SeedSwT2 { const uint32_t *pac; int64_t l_pac, rb; __device__ __forceinline__ int operator()(int i) const { return text_base(pac, l_pac, rb + i); } };
 __global__ void __launch_bounds__(SEEDSW_NT)
 seedsw_kernel(const int *__restrict__ err, const uint32_t *__restrict__ long_reads, bwa_b200_chain_params_t P, Contigs ctg,
               const uint64_t *__restrict__ seed_off, const uint32_t *__restrict__ read_len, const uint32_t *__restrict__ pac,
               const uint32_t *__restrict__ packed_reads, const uint64_t *__restrict__ word_off, Scratch W, const Cnt *__restrict__ cnt)
 {
-    extern __shared__ int16_t sw_sm[];
-    int16_t *H = sw_sm + threadIdx.x, *E = H + SEEDSW_NT * SEEDSW_MAX;
-    uint8_t *qs = (uint8_t *)(sw_sm + 2 * SEEDSW_NT * SEEDSW_MAX) + threadIdx.x;
+    __shared__ uint2 tabs[4];
+    if (threadIdx.x < 4) {       // bwa_fill_scmat's row of target base t against query A/C/G/T; query N scores -1, a padded position 0
+        uint32_t tab = 0;
+        for (int q = 0; q < 4; ++q) tab |= (uint32_t)(uint8_t)(int8_t)(q == (int)threadIdx.x ? P.a : -P.b) << (8 * q);
+        tabs[threadIdx.x] = make_uint2(tab, 0x008000ffu);
+    }
+    __syncthreads();
+    const int grp = threadIdx.x >> 2, gt = threadIdx.x & 3;
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const uint32_t noe_del2 = (uint32_t)(uint16_t)(int16_t)(-oe_del) * 0x00010001u, ne_del2 = (uint32_t)(uint16_t)(int16_t)(-P.e_del) * 0x00010001u;
+    const uint32_t noe_ins2 = (uint32_t)(uint16_t)(int16_t)(-oe_ins) * 0x00010001u, ne_ins2 = (uint32_t)(uint16_t)(int16_t)(-P.e_ins) * 0x00010001u;
     const uint32_t n_long = (uint32_t)err[1];
     for (uint32_t k = blockIdx.x; k < n_long; k += gridDim.x) {
         const uint32_t r = long_reads[k];
         const uint64_t so = seed_off[r];
-        const int nc = (int)cnt[r].chains;
+        const int nc = (int)cnt[r].chains, l_query = (int)read_len[r];
         const int n_cs = W.chains[so + nc - 1].seed_off + W.chains[so + nc - 1].n;
         const uint32_t *rd = packed_reads + word_off[r];
-        for (int i = threadIdx.x; i < n_cs; i += SEEDSW_NT) {
-            bwa_b200_chain_seed_t &s = W.cseeds[so + i];
-            s.score = seed_sw(P, ctg, pac, rd, (int)read_len[r], s, H, E, qs, SEEDSW_NT);
+        for (int base = 0; base < n_cs; base += SEEDSW_NT / 4) {
+            const int i = base + grp;
+            bwa_b200_chain_seed_t s;
+            s.rbeg = 0; s.qbeg = 0; s.len = SEEDSW_MAX; s.score = 0; s.pad = 0;
+            if (i < n_cs) s = W.cseeds[so + i];
+            int qb = 0, qe = 0;
+            int64_t rb = 0, re = 0;
+            const bool job = i < n_cs && seed_sw_window(ctg, l_query, s, qb, qe, rb, re);
+            const int sc = b200sw::pass_i16_score<SEEDSW_VEC>(job, SeedSwQ4{rd, qb}, qe - qb, SeedSwT2{pac, ctg.l_pac, rb}, (int)(re - rb), tabs,
+                                                              noe_del2, ne_del2, noe_ins2, ne_ins2, gt);
+            if (i < n_cs && gt == 0) W.cseeds[so + i].score = job ? sc : -1;
         }
     }
 }
@@ -387,7 +408,6 @@ extern "C" int bwa_b200_aligner_create(const bwa_b200_index_t *idx, uint64_t max
     B200_CUDA(cudaMalloc(&a->d_err, 16)); B200_CUDA(cudaMemset(a->d_err, 0, 16)); B200_CUDA(cudaHostAlloc(&a->h_err, 16, cudaHostAllocDefault));
     a->h_err[0] = a->h_err[1] = a->h_err[2] = a->h_err[3] = 0;
     B200_CUDA(cudaMalloc(&a->d_long, (max_reads ? max_reads : 1) * 4));
-    B200_CUDA(cudaFuncSetAttribute(seedsw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEEDSW_SMEM));
     B200_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, a->cub_bytes, a->d_cnt, a->d_off, CntAdd(), Cnt{}, (int)max_reads, a->stream));
     {   // the compact boundary scans word counts with the same scratch
         size_t b2 = 0;
@@ -464,8 +484,8 @@ static int aligner_run(bwa_b200_aligner *a, const SeedView &S0, bool seeds_from_
         B200_CUDA(cudaMemsetAsync(a->d_err, 0, 8, st));      // also before the retry: attempt 0 may have chained incomplete seed arrays
         B200_LAUNCH(prof, "chain_kernel", st, (chain_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, *cp, ctg, S, d_len, a->W, a->d_cnt, a->d_err, a->d_long)));
         if (a->b_read_max == 0 || flt_seeds_applies(*cp, (int)a->b_read_max)) {     // a batch that may hold reads mem_flt_chained_seeds acts on (length unknown: 0)
-            const unsigned g = (unsigned)std::min<uint64_t>(n, (uint64_t)a->seeder->n_sm * 3);
-            B200_LAUNCH(prof, "seedsw_kernel", st, (seedsw_kernel<<<g, SEEDSW_NT, SEEDSW_SMEM, st>>>(a->d_err, a->d_long, *cp, ctg, S.seed_off, d_len, a->idx->d_pac,
+            const unsigned g = (unsigned)std::min<uint64_t>(n, (uint64_t)a->seeder->n_sm * 8);
+            B200_LAUNCH(prof, "seedsw_kernel", st, (seedsw_kernel<<<g, SEEDSW_NT, 0, st>>>(a->d_err, a->d_long, *cp, ctg, S.seed_off, d_len, a->idx->d_pac,
                                                                                                  d_packed, d_woff, a->W, a->d_cnt)));
             B200_LAUNCH(prof, "chain_long_kernel", st, (chain_long_kernel<<<(unsigned)std::min<uint64_t>((n + 63) / 64, (uint64_t)a->seeder->n_sm * 8), 64, 0, st>>>(
                                                             a->d_err, a->d_long, *cp, ctg, S.seed_off, d_len, a->W, a->d_cnt)));

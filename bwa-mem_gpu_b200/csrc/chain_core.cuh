@@ -425,17 +425,17 @@ struct SeedSwT { const uint32_t *pac; int64_t l_pac, rb; SW_MEM int operator()(i
 
 // mem_seed_sw: the score of ksw_align2(query window, reference window, KSW_XSTART), or -1 when the seed or a window reaches 200 bases.
 // H, E: 200 int16 each, qs: 200 bytes, all at element stride NS (per-lane state of the caller).
-CH_DEV int seed_sw(const bwa_b200_chain_params_t &P, const Contigs &ctg, const uint32_t *pac, const uint32_t *rd, int l_query,
-                   const bwa_b200_chain_seed_t &s, int16_t *H, int16_t *E, uint8_t *qs, size_t NS)
+// the two windows of mem_seed_sw (src/bwamem.c:780-800): false when the seed or a window reaches 200 bases (no alignment: -1)
+CH_FN bool seed_sw_window(const Contigs &ctg, int l_query, const bwa_b200_chain_seed_t &s, int &qb, int &qe, int64_t &rb, int64_t &re)
 {
-    if (s.len >= SEEDSW_MAX) return -1;
-    int qb = s.qbeg - SEEDSW_EXT, qe = s.qbeg + s.len + SEEDSW_EXT;
-    int64_t rb = s.rbeg - SEEDSW_EXT, re = s.rbeg + s.len + SEEDSW_EXT;
+    if (s.len >= SEEDSW_MAX) return false;
+    qb = s.qbeg - SEEDSW_EXT; qe = s.qbeg + s.len + SEEDSW_EXT;
+    rb = s.rbeg - SEEDSW_EXT; re = s.rbeg + s.len + SEEDSW_EXT;
     const int64_t mid = (s.rbeg + s.rbeg + s.len) >> 1, l2 = ctg.l_pac << 1;
     qb = qb > 0 ? qb : 0; qe = qe < l_query ? qe : l_query;
     rb = rb > 0 ? rb : 0; re = re < l2 ? re : l2;
     if (rb < ctg.l_pac && ctg.l_pac < re) { if (mid < ctg.l_pac) re = ctg.l_pac; else rb = ctg.l_pac; }
-    if (qe - qb >= SEEDSW_MAX || re - rb >= SEEDSW_MAX) return -1;
+    if (qe - qb >= SEEDSW_MAX || re - rb >= SEEDSW_MAX) return false;
     {   // bns_fetch_seq, src/bntseq.c:531-552: the window is cut to the contig that holds mid
         int is_rev;
         const int rid = pos2rid(ctg, depos(ctg, mid, &is_rev));
@@ -443,6 +443,14 @@ CH_DEV int seed_sw(const bwa_b200_chain_params_t &P, const Contigs &ctg, const u
         if (is_rev) { const int64_t t = far_beg; far_beg = l2 - far_end; far_end = l2 - t; }
         rb = rb > far_beg ? rb : far_beg; re = re < far_end ? re : far_end;
     }
+    return true;
+}
+CH_DEV int seed_sw(const bwa_b200_chain_params_t &P, const Contigs &ctg, const uint32_t *pac, const uint32_t *rd, int l_query,
+                   const bwa_b200_chain_seed_t &s, int16_t *H, int16_t *E, uint8_t *qs, size_t NS)
+{
+    int qb, qe;
+    int64_t rb, re;
+    if (!seed_sw_window(ctg, l_query, s, qb, qe, rb, re)) return -1;
     SwParams S;
     {   // bwa_fill_scmat, src/bwa.c:93-105
         int k = 0;

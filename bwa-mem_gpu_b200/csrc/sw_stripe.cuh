@@ -203,6 +203,88 @@ __device__ __forceinline__ void pass_any(bool job, const Seq &Q, int qlen, const
     else pass_u8<SMAX, false, SG>(job, Q, qlen, T, tlen, S, tabs, xtra, gt, rowmax, r);
 }
 
+// ---- the 16-bit kernel's score alone (ksw_i16, src/ksw.c:574-696, as mem_seed_sw reads it: xtra = KSW_XSTART, only the score used,
+// src/bwamem.c:774-808): eight SSE lanes = a group of FOUR threads, up to SMAX vectors (8 SMAX query bases) in registers, eight jobs
+// per warp.  No saved row, no row list, no early stop: H, E and the selectors are 3 SMAX registers.  Same conventions as pass_u8
+// (reverse register order, unused registers scoring -32768, branch-free lazy-F loop); no cap on H: the 16-bit adds cannot saturate
+// for windows of under 200 bases.  Q(pos) / T(row) return codes 0..4.
+__device__ __forceinline__ uint32_t lane_shift_up4(uint32_t v, int gt) { return lane_shift_up(v, gt); }      // thread gt - 1 is in the same group for gt > 0
+__device__ __forceinline__ int group_max4(uint32_t v)
+{
+    int m = max((int)(int16_t)(v & 0xffffu), (int)(int16_t)(v >> 16));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    return max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+}
+template <int SMAX, class QF, class TF>
+__device__ __forceinline__ int pass_i16_score(bool job, const QF &Q, int qlen, const TF &T, int tlen, const uint2 *tabs,
+                                              uint32_t noe_del2_, uint32_t ne_del2_, uint32_t noe_ins2_, uint32_t ne_ins2_, int gt)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int gbase = (threadIdx.x & 31) & ~3;
+    const int slen = job ? (qlen + 7) >> 3 : 0;
+    const uint32_t noe_del2 = in_reg(noe_del2_), ne_del2 = in_reg(ne_del2_), noe_ins2 = in_reg(noe_ins2_), ne_ins2 = in_reg(ne_ins2_);
+    const int kmax = __reduce_max_sync(FULL, slen);
+    uint32_t H[SMAX], E[SMAX], sel[SMAX];
+#pragma unroll
+    for (int k = 0; k < SMAX; ++k) {
+        H[k] = 0; E[k] = 0;
+        uint32_t s = 0x65656565u;
+        if (k < slen) {      // vector j = slen - 1 - k: positions (2 gt) * slen + j and (2 gt + 1) * slen + j
+            const int j = slen - 1 - k, p0 = 2 * gt * slen + j, p1 = p0 + slen;
+            const uint32_t c0 = p0 < qlen ? (uint32_t)Q(p0) : 5u, c1 = p1 < qlen ? (uint32_t)Q(p1) : 5u;
+            s = (c0 * 17u + 0x80u) | (c1 * 17u + 0x80u) << 8;
+        }
+        sel[k] = s;
+    }
+    int gmax = 0;
+    int t_b = (job && tlen > 1) ? T(1) : 0;
+    uint2 tb = tabs[(job && tlen > 0) ? T(0) : 0];
+    for (int i = 0;; ++i) {
+        const bool act = job && i < tlen;
+        if (!__any_sync(FULL, act)) break;
+        const uint32_t tab = tb.x, tabn = tb.y;
+        tb = tabs[t_b];
+        t_b = (job && i + 2 < tlen) ? T(i + 2) : 0;
+        uint32_t hin = lane_shift_up4(H[0], gt), f = 0, rm = 0;
+#pragma unroll
+        for (int k = SMAX - 1; k >= 0; --k) {
+            if (k >= kmax) continue;
+            const uint32_t sc = prmt(tab, tabn, sel[k]);
+            const uint32_t e = E[k];
+            uint32_t h = __viaddmax_s16x2(hin, sc, e);                      // adds_epi16(h, profile), max with E
+            hin = k < slen ? H[k] : hin;
+            h = __vimax3_s16x2(h, f, f);
+            rm = __vimax3_s16x2(rm, h, h);
+            H[k] = h;
+            const uint32_t t1 = __viaddmax_s16x2(h, noe_del2, 0u);
+            E[k] = __viaddmax_s16x2(e, ne_del2, t1);
+            const uint32_t t2 = __viaddmax_s16x2(h, noe_ins2, 0u);
+            f = __viaddmax_s16x2(f, ne_ins2, t2);
+        }
+        if (!act) f = 0;
+        for (int round = 0; round < 16; ++round) {
+            if (!__any_sync(FULL, f != 0u)) break;
+            f = lane_shift_up4(f, gt);
+#pragma unroll
+            for (int k = SMAX - 1; k >= 0; --k) {
+                if (k >= kmax) continue;
+                const bool on = k < slen;
+                const uint32_t fe = on ? f : 0u;
+                const uint32_t h = __vimax3_s16x2(H[k], fe, fe);
+                H[k] = h;
+                const uint32_t h2 = __viaddmax_s16x2(h, noe_ins2, 0u);
+                const uint32_t f1 = __viaddmax_s16x2(fe, ne_ins2, 0u);
+                const uint32_t b = __ballot_sync(FULL, __vimax3_s16x2(f1, h2, h2) != h2);
+                if (on) f = ((b >> gbase) & 0xfu) ? f1 : 0u;
+                if ((k & 1) == 0 && !__any_sync(FULL, f != 0u)) break;
+            }
+        }
+        const int rowm = group_max4(rm);
+        if (act) gmax = max(gmax, rowm);
+    }
+    return gmax;
+}
+
 // ksw_align2 (src/ksw.c:698-736) for the byte kernel: the pass, then -- with KSW_XSTART and a score that reaches the threshold -- the
 // pass on the reversed prefixes that yields the start of the hit.
 template <int SMAX, bool SG>
