@@ -62,6 +62,13 @@ __global__ void planes_kernel(uint32_t *bkt, uint64_t n_buckets)
 
 static int ilog2(uint64_t x) { int r = 0; while ((1ull << r) < x) ++r; return r; }
 
+// a half-built index is freed when a CUDA call fails on the way (B200_CUDA returns from the function)
+struct IndexGuard {
+    bwa_b200_index *p;
+    ~IndexGuard() { if (p) bwa_b200_index_free(p); }
+    bwa_b200_index *release() { bwa_b200_index *q = p; p = nullptr; return q; }
+};
+
 extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], const uint32_t *bwt_words, uint64_t n_words,
                                         const uint32_t *sa, const uint32_t *sa_hi, uint64_t n_sa, int sa_intv, int pack_size,
                                         int device, bwa_b200_index_t **out)
@@ -75,6 +82,7 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
         fprintf(stderr, "[b200] L2 fetch granularity -> %zu (%s)\n", got, cudaGetErrorString(er));
     }
     bwa_b200_index *idx = new bwa_b200_index();
+    IndexGuard guard{idx};
     idx->device = device;
     idx->n_words = n_words;
     idx->n_sa = sa ? n_sa : 0;
@@ -119,9 +127,9 @@ extern "C" int bwa_b200_index_from_host(uint64_t primary, const uint64_t L2[5], 
         int K = ev ? atoi(ev) : (bkt_bytes <= (256ull << 20) ? 0 : (bkt_bytes < (1ull << 30) ? 12 : 13));
         while (K > 0 && (1ull << (2 * K)) > seq_len) --K;        // a tiny text does not need 4^K patterns
         int rc = b200_index_build_kmer_table(idx, K);
-        if (rc) { bwa_b200_index_free(idx); return rc; }
+        if (rc) return rc;                                       // the guard frees the index
     }
-    *out = idx;
+    *out = guard.release();
     return BWA_B200_OK;
 }
 
@@ -182,6 +190,7 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
     if (!src || !out) { b200::set_error("index_clone_to: bad argument"); return BWA_B200_ERR_ARG; }
     B200_CUDA(cudaSetDevice(device));
     bwa_b200_index *idx = new bwa_b200_index(*src);
+    IndexGuard guard{idx};
     idx->device = device;
     idx->d_bkt = idx->d_sa = idx->d_sa_hi = nullptr;
     idx->d_pac = nullptr;
@@ -207,7 +216,7 @@ extern "C" int bwa_b200_index_clone_to(const bwa_b200_index_t *src, int device, 
         B200_CUDA(cudaMalloc(&idx->d_pac, words * 4));
         B200_CUDA(cudaMemcpyPeer(idx->d_pac, device, src->d_pac, src->device, words * 4));
     } else idx->l_pac = 0;
-    *out = idx;
+    *out = guard.release();
     return BWA_B200_OK;
 }
 
