@@ -124,7 +124,7 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 
 // ---- jobs answered in closed form -----------------------------------------------------------------------------------------------
 // What is left of a read beside a maximal exact match usually differs from the reference in the base that ended the match and in
-// little else.  When the query equals the head of its target except for at most TWO substituted bases (no base outside A/C/G/T,
+// little else.  When the query equals the head of its target except for at most THREE substituted bases (no base outside A/C/G/T,
 // target at least as long as the query), ksw_extend2's six outputs follow from h0, qlen and the positions r1 < r2 of the differing
 // bases, without a matrix -- provided the main diagonal is the strict maximum of every row and of the last column.  With match a,
 // mismatch -b, g = min(o_del + e_del, o_ins + e_ins) and D(i) = h0 + (i + 1) a - (a + b) * #{differing bases at or before i}:
@@ -138,6 +138,12 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 //     that shifted diagonal, so one mismatch q[c +- d] != t[c] there (or a cell outside the matrix) rules the shift out; a job is
 //     taken only when all 2 dmax shifts are ruled out that way (random sequence does it within a base or two; tandem repeats and
 //     adjacent differences do not, and go to the kernels).
+//   * For k = 3 a rival can afford more: one gap of up to dmax3 bases (o + e d <= 3 (a + b)) with no mismatch past all three
+//     differences, one gap of up to dmax2 with a single mismatch, one gap that avoids two neighbouring differences, or two gaps
+//     (2 g <= 3 (a + b) is possible) with no mismatch at all.  Each of them runs along ONE shifted diagonal, shifted by at most dmax3,
+//     across the whole stretch between two neighbouring differences (a second gap inside one stretch leaves the other stretch to a
+//     single diagonal; a path back on the main diagonal gains nothing there), clean in that stretch.  So the same test, with dmax3 and
+//     applied to BOTH stretches, rules all of them out; three gaps cost more than three differences can give back.
 //   * The running maximum starts at h0 (src/ksw.c:896) and moves only on m > max (:947), always with mj = i, so max_off = 0 and
 //     (max_i, max_j) is the first of D's peaks -- the rows before r1, before r2 and the last row -- that holds the largest value, if it
 //     exceeds h0; gscore = D(qlen - 1) at row qlen - 1.  The z-drop test (:950-957) sees max - m <= k b with equal row and column
@@ -145,10 +151,10 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 //   * With a band, the columns beyond i + w still hold the first row's values (src/ksw.c:880-883) when row i reaches them: a gap of
 //     more than dmax bases, out of the running for w > dmax + 1.
 // Every step is checked against the oracle on 30 k jobs built around the conditions (tests/test_ext_pair_host.py).
-struct ClosedParams { int32_t ok, a, b, dmax, zdrop; };
+struct ClosedParams { int32_t ok, a, b, dmax2, dmax3, zdrop; };       // dmax_k: the longest gap that costs no more than k mismatches (-1: k differences not taken)
 static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
 {
-    ClosedParams C{0, 0, 0, 0, 0};
+    ClosedParams C{0, 0, 0, 0, -1, 0};
     const int a = p->mat[0], b = -p->mat[1];
     if (a < 1 || b < 1) return C;
     for (int i = 0; i < 4; ++i)
@@ -156,12 +162,17 @@ static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
             if (p->mat[i * 5 + j] != (i == j ? a : -b)) return C;
     const int oe_del = p->o_del + p->e_del, oe_ins = p->o_ins + p->e_ins, g = oe_del < oe_ins ? oe_del : oe_ins;
     if (p->e_del < 1 || p->e_ins < 1 || p->o_del < 0 || p->o_ins < 0 || g <= a + b) return C;
-    const int d_del = (2 * (a + b) - p->o_del) / p->e_del, d_ins = (2 * (a + b) - p->o_ins) / p->e_ins;
-    int dmax = d_del > d_ins ? d_del : d_ins;
-    if (dmax < 0) dmax = 0;
-    if (dmax > 16) return C;
-    if (p->use_band && p->w < dmax + 2) return C;
-    C.ok = 1; C.a = a; C.b = b; C.dmax = dmax; C.zdrop = p->zdrop;
+    auto dmax_of = [&](int k) {
+        const int d_del = (k * (a + b) - p->o_del) / p->e_del, d_ins = (k * (a + b) - p->o_ins) / p->e_ins;
+        const int d = d_del > d_ins ? d_del : d_ins;
+        return d < 0 ? 0 : d;
+    };
+    const int dmax2 = dmax_of(2), dmax3 = dmax_of(3);
+    if (dmax2 > 16) return C;
+    if (p->use_band && p->w < dmax2 + 2) return C;
+    C.ok = 1; C.a = a; C.b = b; C.dmax2 = dmax2; C.zdrop = p->zdrop;
+    // three differences: three gaps must cost more than they can gain (3 g > 3 (a + b) holds already), and the band must clear dmax3
+    if (dmax3 <= 24 && (!p->use_band || p->w >= dmax3 + 2)) C.dmax3 = dmax3;
     return C;
 }
 template <bool BYTES>
@@ -174,12 +185,13 @@ B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t 
     const uint32_t *qp = BYTES ? nullptr : J.qp + (J.qoff[a] >> 3), *tp = BYTES ? nullptr : J.tp + (J.toff[a] >> 3);
     auto qa = [&](int i) -> uint32_t { return BYTES ? (uint32_t)qb[i] : (qp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
     auto ta = [&](int i) -> uint32_t { return BYTES ? (uint32_t)tb[i] : (tp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
-    // the differing bases: at most two, every compared base in A/C/G/T
-    int k = 0, rr[2] = {0, 0};
+    // the differing bases: at most three, every compared base in A/C/G/T
+    const int kcap = C.dmax3 >= 0 ? 3 : 2;
+    int k = 0, rr[3] = {0, 0, 0};
     if (BYTES) {
         for (uint32_t i = 0; i < ql; ++i) {
             if (qb[i] > 3 || tb[i] > 3) return false;
-            if (qb[i] != tb[i]) { if (k == 2) return false; rr[k++] = (int)i; }
+            if (qb[i] != tb[i]) { if (k == kcap) return false; rr[k++] = (int)i; }
         }
     } else {
         const uint32_t nw = (ql + 7) >> 3;
@@ -189,26 +201,32 @@ B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t 
             if ((qw | tw) & 0xccccccccu & m) return false;
             uint32_t x = (qw ^ tw) & m;
             for (int n = 0; x; ++n, x <<= 4)
-                if (x >> 28) { if (k == 2) return false; rr[k++] = (int)(8 * w) + n; }
+                if (x >> 28) { if (k == kcap) return false; rr[k++] = (int)(8 * w) + n; }
         }
     }
     if (h0 <= k * C.b || (C.zdrop > 0 && k * C.b > C.zdrop)) return false;
-    if (k == 2 && C.dmax > 0) {       // every shifted diagonal a single affordable gap reaches must break between the two differences
-        const int lo = rr[0] + C.dmax + 1, hi = rr[1];
-        if (lo >= hi) return false;
-        for (int d = 1; d <= C.dmax; ++d)
-            for (int sg = -1; sg <= 1; sg += 2) {
-                const int s = sg * d;
-                bool broken = false;
-                for (int c = lo; c < hi && !broken; ++c) broken = c + s >= (int)ql || qa(c + s) != ta(c);     // c + s >= lo - dmax > 0
-                if (!broken) return false;
-            }
+    const int dmax = k == 3 ? C.dmax3 : C.dmax2;
+    if (k >= 2 && dmax > 0) {     // every shifted diagonal an affordable gap reaches must break between each two neighbouring differences
+        for (int m = 0; m + 1 < k; ++m) {
+            const int lo = rr[m] + dmax + 1, hi = rr[m + 1];
+            if (lo >= hi) return false;
+            for (int d = 1; d <= dmax; ++d)
+                for (int sg = -1; sg <= 1; sg += 2) {
+                    const int s = sg * d;
+                    bool broken = false;
+                    for (int c = lo; c < hi && !broken; ++c) broken = c + s >= (int)ql || qa(c + s) != ta(c);     // c + s >= lo - dmax > 0
+                    if (!broken) return false;
+                }
+        }
     }
     // D at its peaks, in row order; the first one holding the largest value is where the maximum was last raised
     const int ab = C.a + C.b, last = (int)ql - 1;
     int best = h0, row = -1;
-    if (k >= 1 && rr[0] >= 1) { const int v = h0 + rr[0] * C.a; if (v > best) { best = v; row = rr[0] - 1; } }
-    if (k == 2) { const int v = h0 + rr[1] * C.a - ab; if (v > best) { best = v; row = rr[1] - 1; } }
+    for (int m = 0; m < k; ++m) {
+        if (rr[m] < 1) continue;
+        const int v = h0 + rr[m] * C.a - m * ab;                 // D(rr[m] - 1): m differences before it
+        if (v > best) { best = v; row = rr[m] - 1; }
+    }
     const int g = h0 + (int)ql * C.a - k * ab;
     if (g > best) { best = g; row = last; }
     r->score = best; r->qle = row + 1; r->tle = row + 1;

@@ -123,7 +123,7 @@ def test_pair_source_wide_scores_long_queries(pkg, oracle, emul, kw):
             assert cells == cnt["cells"]
 
 
-CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=6, zdrop=4), True), (dict(w=300, zdrop=0, use_band=0), True),
+CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=6, zdrop=4), True), (dict(w=11, zdrop=12), True), (dict(w=300, zdrop=0, use_band=0), True),
          (dict(w=20, zdrop=50, a=2, b=3), True), (dict(w=20, zdrop=10, a=2, b=5, o_del=7, e_del=2, o_ins=8, e_ins=1), True),
          (dict(w=100, zdrop=3), True),                                            # only jobs without a difference pass the z-drop condition
          (dict(w=5, zdrop=100), False),                                           # band narrower than the gaps that have to be ruled out + 2
@@ -142,7 +142,7 @@ def test_closed_form_jobs_match_oracle(pkg, oracle, emul, kw, eligible):
     ep = pkg.ext_params(**kw)
     dmax = synth.closed_form_eligible(**kw)
     assert (dmax is not None) == eligible
-    n_taken = n_two = n_rep = 0
+    n_taken = n_two = n_rep = n_three = 0
     for seed, extra in ((71, dict()), (72, dict(qlen_range=(1, 12), h0_range=(1, 30))), (73, dict(qlen_range=(100, 600), h0_range=(19, 250))),
                         (74, dict(qlen_range=(20, 160), h0_range=(19, 150)))):
         jobs = synth.make_flank_jobs(2500, seed=seed, w=kw["w"], **extra)
@@ -169,8 +169,12 @@ def test_closed_form_jobs_match_oracle(pkg, oracle, emul, kw, eligible):
             q = jobs["qseq"][int(jobs["qoff"][k]):int(jobs["qoff"][k]) + ql]; t = jobs["tseq"][int(jobs["toff"][k]):int(jobs["toff"][k]) + ql]
             if (q < 4).all() and (t < 4).all() and int((q != t).sum()) == 2:
                 n_two += int(got[k]); n_rep += int(not got[k])
+            if (q < 4).all() and (t < 4).all() and int((q != t).sum()) == 3:
+                n_three += int(got[k])
     if eligible and (kw["zdrop"] == 0 or kw["zdrop"] >= 2 * kw.get("b", 4)):
         assert n_taken > 3000 and n_two > 800 and n_rep > 100
+        if dmax[1] is not None and (kw["zdrop"] == 0 or kw["zdrop"] >= 3 * kw.get("b", 4)):
+            assert n_three > 150
     elif eligible:
         assert n_taken > 300
 
@@ -192,5 +196,5 @@ def test_closed_form_on_general_jobs(pkg, oracle, emul):
         assert taken >= 0
         want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
         got = flags != 0
-        assert (got == synth.closed_form_mask(jobs, 1, 4, 4, 100)).all()
+        assert (got == synth.closed_form_mask(jobs, 1, 4, (4, 9), 100)).all()
         assert (res[got] == want[got]).all()

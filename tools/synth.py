@@ -285,8 +285,8 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
         tl = ql + int(rng.integers(0, min(ql, 2 * w) + 1))
         t = rng.integers(0, 4, size=tl, dtype=np.uint8)
         q = t[:ql].copy()
-        if rng.random() < 0.25 and tl > 8:                       # a tandem repeat (period 1 .. 4) somewhere: shifted diagonals match there
-            per = int(rng.integers(1, 5)); at = int(rng.integers(0, tl - 4)); ln = int(rng.integers(4, 60))
+        if rng.random() < 0.35 and tl > 8:                       # a tandem repeat (period 1 .. 12) somewhere: shifted diagonals match there
+            per = int(rng.integers(1, 13)); at = int(rng.integers(0, tl - 4)); ln = int(rng.integers(4, 120))
             unit = t[at:at + per].copy()
             for x in range(at, min(tl, at + ln)):
                 t[x] = unit[(x - at) % per]
@@ -326,13 +326,14 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
     return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
 
 
-def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax: int = 4, zdrop: int = 100) -> np.ndarray:
+def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax=(4, 9), zdrop: int = 100) -> np.ndarray:
     """Which jobs the extender answers in closed form (an independent statement of closed_form_job's predicate, ext_pair_core.cuh):
-    target at least as long as the query, every compared base in A/C/G/T, at most two substituted bases, h0 > k b, k b <= zdrop, and
-    -- with two -- every diagonal shifted by 1 .. dmax either way has a mismatch (or leaves the matrix) on the rows strictly between
-    the first difference + dmax and the second."""
+    target at least as long as the query, every compared base in A/C/G/T, at most three substituted bases (two when dmax[1] is None),
+    h0 > k b, k b <= zdrop, and -- with k >= 2 -- between each two neighbouring differences every diagonal shifted by 1 .. dmax_k either
+    way has a mismatch (or leaves the matrix) on the rows strictly between the earlier difference + dmax_k and the later one."""
     n = jobs["qlen"].size
     out = np.zeros(n, bool)
+    kcap = 3 if dmax[1] is not None else 2
     for j in range(n):
         ql, tl, h0 = int(jobs["qlen"][j]), int(jobs["tlen"][j]), int(jobs["h0"][j])
         if ql == 0 or tl < ql:
@@ -343,33 +344,40 @@ def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax: int = 4, zdrop: i
             continue
         diff = np.nonzero(q != t)[0]
         k = len(diff)
-        if k > 2 or h0 <= k * b or (zdrop > 0 and k * b > zdrop):
+        if k > kcap or h0 <= k * b or (zdrop > 0 and k * b > zdrop):
             continue
         ok = True
-        if k == 2 and dmax > 0:
-            lo, hi = int(diff[0]) + dmax + 1, int(diff[1])
-            ok = lo < hi
-            for s in [x for d in range(1, dmax + 1) for x in (-d, d)] if ok else []:
-                rows = np.arange(lo, hi)
-                cols = rows + s
-                inside = cols < ql
-                if not ((~inside).any() or (q[cols[inside]] != t[rows[inside]]).any()):
+        dk = dmax[1] if k == 3 else dmax[0]
+        if k >= 2 and dk > 0:
+            for m in range(k - 1):
+                lo, hi = int(diff[m]) + dk + 1, int(diff[m + 1])
+                if lo >= hi:
                     ok = False
+                    break
+                rows = np.arange(lo, hi)
+                for s_ in [x for d in range(1, dk + 1) for x in (-d, d)]:
+                    cols = rows + s_
+                    inside = cols < ql
+                    if not ((~inside).any() or (q[cols[inside]] != t[rows[inside]]).any()):
+                        ok = False
+                        break
+                if not ok:
                     break
         out[j] = ok
     return out
 
 
 def closed_form_eligible(w=100, zdrop=100, use_band=1, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, **_):
-    """closed_params_from (ext_pair_core.cuh) restated: None when the parameters rule the closed-form answer out, else dmax, the longest
-    gap that costs no more than two mismatches"""
+    """closed_params_from (ext_pair_core.cuh) restated: None when the parameters rule the closed-form answer out, else (dmax2, dmax3): the
+    longest gap that costs no more than two / three mismatches (dmax3 None: jobs with three differences are not taken)"""
     g = min(o_del + e_del, o_ins + e_ins)
     if a < 1 or b < 1 or g <= a + b:
         return None
-    dmax = max((2 * (a + b) - o_del) // e_del, (2 * (a + b) - o_ins) // e_ins, 0)
-    if dmax > 16 or (use_band and w < dmax + 2):
+    d2 = max((2 * (a + b) - o_del) // e_del, (2 * (a + b) - o_ins) // e_ins, 0)
+    d3 = max((3 * (a + b) - o_del) // e_del, (3 * (a + b) - o_ins) // e_ins, 0)
+    if d2 > 16 or (use_band and w < d2 + 2):
         return None
-    return dmax
+    return d2, (d3 if d3 <= 24 and (not use_band or w >= d3 + 2) else None)
 
 
 def subset_jobs(jobs: dict, keep: np.ndarray) -> dict:
