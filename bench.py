@@ -442,7 +442,7 @@ def run_chained(args, pkg, idx, bt, flush, dist, world, lens, reseed=False, step
            "regions_per_step": int(v.n_regions), "jobs_short": int(v.n_jobs_short), "jobs_long": int(v.n_jobs_long), "seeds": int(v.n_seeds),
            "cells_per_step": int(v.cells), "extension_GCUPS": (v.cells / (ext_ms / 1e3) / 1e9) if ext_ms > 0 else None,
            "closed_form_jobs": int(v.closed_form_jobs),
-           "closed_form_note": "extension jobs whose query equals the head of the target except for at most two substituted bases are answered "
+           "closed_form_note": "extension jobs whose query equals the head of the target except for a few substituted bases (up to six at the default penalties, far enough apart) are answered "
                                "without a matrix (proof and conditions: csrc/ext_pair_core.cuh closed_form_job; identical results); they are "
                                "not in cells_per_step nor in extension_GCUPS",
            "gpu_launches": int(launches), "kernel_ms": kavg,

@@ -124,37 +124,43 @@ static inline int pair_slots(const bwa_b200_ext_params_t *p, int max_q, PairPara
 
 // ---- jobs answered in closed form -----------------------------------------------------------------------------------------------
 // What is left of a read beside a maximal exact match usually differs from the reference in the base that ended the match and in
-// little else.  When the query equals the head of its target except for at most THREE substituted bases (no base outside A/C/G/T,
-// target at least as long as the query), ksw_extend2's six outputs follow from h0, qlen and the positions r1 < r2 of the differing
-// bases, without a matrix -- provided the main diagonal is the strict maximum of every row and of the last column.  With match a,
-// mismatch -b, g = min(o_del + e_del, o_ins + e_ins) and D(i) = h0 + (i + 1) a - (a + b) * #{differing bases at or before i}:
-//   * H(i, i) = D(i) as long as D stays positive (h0 > k b for k differences), so `M = M ? M + s : 0` (src/ksw.c:924) never cuts the
-//     diagonal; the cell after a non-zero cell is always inside [beg, end) (src/ksw.c:959-965) and, with w >= 0, inside the band.
-//   * Any other path to a cell holds a gap.  Measured against the diagonal over the same rows it can gain at most (a + b) per
-//     difference it avoids, and loses the gap: with a + b < g a path with two gaps (2 g > 2 (a + b)) or one that avoids a single
-//     difference never reaches the diagonal's score.  That settles k <= 1 for every job.
-//   * For k = 2 the one remaining rival leaves the diagonal before r1, pays one gap of d <= dmax bases (o + e d <= 2 (a + b)) and
-//     then runs along the diagonal shifted by d WITHOUT A SINGLE MISMATCH past r2.  Such a run covers the rows r1 + dmax < c < r2 on
-//     that shifted diagonal, so one mismatch q[c +- d] != t[c] there (or a cell outside the matrix) rules the shift out; a job is
-//     taken only when all 2 dmax shifts are ruled out that way (random sequence does it within a base or two; tandem repeats and
-//     adjacent differences do not, and go to the kernels).
-//   * For k = 3 a rival can afford more: one gap of up to dmax3 bases (o + e d <= 3 (a + b)) with no mismatch past all three
-//     differences, one gap of up to dmax2 with a single mismatch, one gap that avoids two neighbouring differences, or two gaps
-//     (2 g <= 3 (a + b) is possible) with no mismatch at all.  Each of them runs along ONE shifted diagonal, shifted by at most dmax3,
-//     across the whole stretch between two neighbouring differences (a second gap inside one stretch leaves the other stretch to a
-//     single diagonal; a path back on the main diagonal gains nothing there), clean in that stretch.  So the same test, with dmax3 and
-//     applied to BOTH stretches, rules all of them out; three gaps cost more than three differences can give back.
+// little else.  When the query equals the head of its target except for a FEW substituted bases r_1 < ... < r_k (k <= CF_KMAX, no
+// base outside A/C/G/T, target at least as long as the query), ksw_extend2's six outputs follow from h0, qlen and the r_m, without
+// a matrix -- provided the main diagonal is the strict maximum of every row and of every column.  With match a, mismatch -b,
+// g = min(o_del + e_del, o_ins + e_ins) > a + b and D(i) = h0 + (i + 1) a - (a + b) * #{differing bases at or before i}:
+//   * H(i, i) >= D(i) as long as D stays positive (h0 > k b), so `M = M ? M + s : 0` (src/ksw.c:924) never cuts the diagonal; the
+//     cell after a non-zero cell is always inside [beg, end) (src/ksw.c:959-965) and, with w >= 0, inside the band.  Every value the
+//     recurrence produces is the score of an alignment path from the origin (or 0): gaps opening from M only (:926-938), the first
+//     row's and column's gap from the origin (:880-883, :905) and cells that fell out of [beg, end) only remove paths.
+//   * Measure a path to (i, j) against D(i) (it enters at most i + 1 rows by a diagonal step) or against D(j) (at most j + 1 columns):
+//     it gains (a + b) for every difference whose diagonal step (r_m - 1, r_m - 1) -> (r_m, r_m) it does not take, loses (a + b) for
+//     every mismatch it meets elsewhere, and loses its gaps, each at least g.  Cut it into its stretches on the main diagonal (gain 0)
+//     and its EXCURSIONS off it.  An excursion avoids a run r_m .. r_m' of c neighbouring differences and is off the diagonal in every
+//     row between them; its first gap opens at or before row r_m.  A gap of more than dmax_k bases (dmax_k: the longest that costs no
+//     more than k (a + b)) costs more than all k differences give back, so inside an excursion worth considering every gap and every
+//     shift |j - i| is at most dmax_k.
+//   * THE TEST: between each two neighbouring differences, on the rows lo = r_m + dmax_k + 1 <= c < hi = r_m+1 (there must be one),
+//     every diagonal shifted by s, 1 <= |s| <= dmax_k, holds a mismatch q[c + s] != t[c] or leaves the matrix.  An excursion that
+//     avoids both r_m and r_m+1 either walks one such diagonal through all of [lo, hi) and meets that mismatch, or takes a gap step
+//     on those rows -- a gap that opened after row r_m (reaching back to r_m would take more than dmax_k bases) and before r_m+1, so
+//     it is a gap of its own, neither the excursion's first one nor the one counted for another pair of neighbours.  Either way the
+//     c - 1 pairs of neighbours inside the excursion cost it (a + b) each at least, its first gap costs g, and the excursion ends
+//     (a + b) c - (a + b)(c - 1) - g < 0 below the diagonal.  A path with an excursion is therefore strictly below D(i) (and D(j)):
+//     H(i, i) = D(i), every other cell of row i and of column i is smaller.  k <= 1 needs no test; random sequence passes it within a
+//     base or two per diagonal, tandem repeats and differences closer than dmax_k + 2 do not, and go to the kernels.
 //   * The running maximum starts at h0 (src/ksw.c:896) and moves only on m > max (:947), always with mj = i, so max_off = 0 and
-//     (max_i, max_j) is the first of D's peaks -- the rows before r1, before r2 and the last row -- that holds the largest value, if it
+//     (max_i, max_j) is the first of D's peaks -- the row before each difference and the last row -- that holds the largest value, if it
 //     exceeds h0; gscore = D(qlen - 1) at row qlen - 1.  The z-drop test (:950-957) sees max - m <= k b with equal row and column
-//     distance, so it cannot fire when zdrop <= 0 or k b <= zdrop.  Rows after the last query row score below max and D(qlen - 1).
+//     distance, so it cannot fire when zdrop <= 0 or k b <= zdrop.  Rows after the last query row score below D of their column, hence
+//     below max and, in the last column, below D(qlen - 1).
 //   * With a band, the columns beyond i + w still hold the first row's values (src/ksw.c:880-883) when row i reaches them: a gap of
-//     more than dmax bases, out of the running for w > dmax + 1.
-// Every step is checked against the oracle on 30 k jobs built around the conditions (tests/test_ext_pair_host.py).
-struct ClosedParams { int32_t ok, a, b, dmax2, dmax3, zdrop; };       // dmax_k: the longest gap that costs no more than k mismatches (-1: k differences not taken)
+//     more than dmax_k bases, out of the running for w > dmax_k + 1.
+// Every step is checked against the oracle on jobs built around the conditions (tests/test_ext_pair_host.py).
+constexpr int CF_KMAX = 6, CF_DMAX_CAP = 24;
+struct ClosedParams { int32_t ok, a, b, zdrop, kcap; int32_t dmax[CF_KMAX + 1]; };     // dmax[k]: the longest gap that costs no more than k mismatches; kcap: most differences taken
 static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
 {
-    ClosedParams C{0, 0, 0, 0, -1, 0};
+    ClosedParams C{};
     const int a = p->mat[0], b = -p->mat[1];
     if (a < 1 || b < 1) return C;
     for (int i = 0; i < 4; ++i)
@@ -167,12 +173,14 @@ static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
         const int d = d_del > d_ins ? d_del : d_ins;
         return d < 0 ? 0 : d;
     };
-    const int dmax2 = dmax_of(2), dmax3 = dmax_of(3);
-    if (dmax2 > 16) return C;
-    if (p->use_band && p->w < dmax2 + 2) return C;
-    C.ok = 1; C.a = a; C.b = b; C.dmax2 = dmax2; C.zdrop = p->zdrop;
-    // three differences: three gaps must cost more than they can gain (3 g > 3 (a + b) holds already), and the band must clear dmax3
-    if (dmax3 <= 24 && (!p->use_band || p->w >= dmax3 + 2)) C.dmax3 = dmax3;
+    if (dmax_of(2) > 16) return C;
+    if (p->use_band && p->w < dmax_of(2) + 2) return C;
+    C.ok = 1; C.a = a; C.b = b; C.zdrop = p->zdrop; C.kcap = 2;
+    for (int k = 2; k <= CF_KMAX; ++k) {       // more differences as long as the gaps they pay for stay short and inside the band
+        const int d = dmax_of(k);
+        if (k > 2 && (d > CF_DMAX_CAP || (p->use_band && p->w < d + 2))) break;
+        C.dmax[k] = d; C.kcap = k;
+    }
     return C;
 }
 template <bool BYTES>
@@ -185,9 +193,9 @@ B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t 
     const uint32_t *qp = BYTES ? nullptr : J.qp + (J.qoff[a] >> 3), *tp = BYTES ? nullptr : J.tp + (J.toff[a] >> 3);
     auto qa = [&](int i) -> uint32_t { return BYTES ? (uint32_t)qb[i] : (qp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
     auto ta = [&](int i) -> uint32_t { return BYTES ? (uint32_t)tb[i] : (tp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
-    // the differing bases: at most three, every compared base in A/C/G/T
-    const int kcap = C.dmax3 >= 0 ? 3 : 2;
-    int k = 0, rr[3] = {0, 0, 0};
+    // the differing bases: at most kcap, every compared base in A/C/G/T
+    const int kcap = C.kcap;
+    int k = 0, rr[CF_KMAX] = {};
     if (BYTES) {
         for (uint32_t i = 0; i < ql; ++i) {
             if (qb[i] > 3 || tb[i] > 3) return false;
@@ -205,7 +213,7 @@ B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t 
         }
     }
     if (h0 <= k * C.b || (C.zdrop > 0 && k * C.b > C.zdrop)) return false;
-    const int dmax = k == 3 ? C.dmax3 : C.dmax2;
+    const int dmax = C.dmax[k];
     if (k >= 2 && dmax > 0) {     // every shifted diagonal an affordable gap reaches must break between each two neighbouring differences
         for (int m = 0; m + 1 < k; ++m) {
             const int lo = rr[m] + dmax + 1, hi = rr[m + 1];

@@ -238,10 +238,10 @@ void *bwa_b200_extender_stream(bwa_b200_extender_t *e);
 uint64_t bwa_b200_extender_launches(const bwa_b200_extender_t *e);
 /* cells evaluated by the last batch (sum over rows of end-beg), counted on device */
 uint64_t bwa_b200_extender_last_cells(bwa_b200_extender_t *e);
-/* Jobs of the last batch answered without a matrix: a query that equals the head of its target except for at most two substituted
- * bases (the usual flank of a maximal exact match: the base that ended the match and little else) has a closed-form ksw_extend2 result
- * when the scoring is bwa_fill_scmat's, min(o_del + e_del, o_ins + e_ins) > a + b and -- with two substitutions -- no diagonal a single
- * affordable gap reaches matches all the way between them.  Proof and conditions: bwa-mem_gpu_b200/csrc/ext_pair_core.cuh
+/* Jobs of the last batch answered without a matrix: a query that equals the head of its target except for a few substituted
+ * bases (up to six at the default penalties; the usual flank of a maximal exact match: the base that ended the match and little else) has a closed-form ksw_extend2 result
+ * when the scoring is bwa_fill_scmat's, min(o_del + e_del, o_ins + e_ins) > a + b and -- with two or more substitutions -- no diagonal an
+ * affordable gap reaches matches all the way between two neighbouring ones.  Proof and conditions: bwa-mem_gpu_b200/csrc/ext_pair_core.cuh
  * (closed_form_job).  Such jobs are not in last_cells.  set_closed_form(e, 0) sends every job through the kernels (also: environment
  * BWA_B200_EXT_NO_CLOSED at creation); the results are identical either way. */
 uint64_t bwa_b200_extender_last_closed_form(bwa_b200_extender_t *e);

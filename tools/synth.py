@@ -272,7 +272,7 @@ def make_sw_jobs(n_jobs: int, qlen_range=(30, 150), tlen_range=(100, 700), seed:
 
 def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=(1, 200), w: int = 100, pad8: bool = True):
     """Extension jobs as a maximal exact match leaves them in a read with few differences: the query equals the head of the target,
-    mostly with its first base changed (the base that ended the match) and zero to three further substitutions, a quarter of them over
+    mostly with its first base changed (the base that ended the match) and zero to six further substitutions, a third of them over
     a tandem repeat (where a shifted diagonal matches as well as the main one).  Many jobs miss the closed-form shape by one detail -- a
     third difference, adjacent differences, an N on either side, a target shorter than the query, a small h0 -- so that the shortcut is
     tested on both sides of every condition.  Same dict as make_ext_jobs."""
@@ -294,7 +294,7 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
         u = rng.random()
         if u < 0.85:
             q[0] = (q[0] + int(rng.integers(1, 4))) & 3          # the mismatch that ended the seed
-        for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2, 3]))):   # further substitutions, anywhere (next to the first one included)
+        for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 5, 6]))):   # further substitutions, anywhere (next to the first one included)
             if ql > 1:
                 k = int(rng.integers(1, ql)) if rng.random() < 0.8 else min(ql - 1, int(rng.integers(1, 8)))
                 q[k] = (q[k] + int(rng.integers(1, 4))) & 3
@@ -326,20 +326,69 @@ def make_flank_jobs(n_jobs: int, seed: int = 515, qlen_range=(1, 160), h0_range=
     return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=h0)
 
 
-def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax=(4, 9), zdrop: int = 100) -> np.ndarray:
+def make_repeat_flank_jobs(n_jobs: int, seed: int, kw: dict) -> dict:
+    """Adversarial jobs for the closed-form answer (closed_form_job, ext_pair_core.cuh): targets that are tandem repeats of period
+    1 .. dmax_k + 2 with a few point breaks (so shifted diagonals are clean or nearly clean), two-letter sequences and random ones;
+    2 .. 7 substitutions planted in the query at spacings around the dmax_k + 2 boundary of the test; a third of the jobs with a small
+    h0.  kw: the extension parameters (they set dmax_k).  Same dict as make_ext_jobs."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    dm = closed_form_eligible(**kw) or {2: 4}
+    qs, ts, h0s = [], [], []
+    for _ in range(n_jobs):
+        k = int(rng.integers(2, 8))
+        dk = dm.get(min(k, max(dm)), 4)
+        ql = int(rng.integers(max(4, k * 3), 40 + k * (dk + 8)))
+        tl = ql + int(rng.integers(0, 40))
+        mode = rng.random()
+        if mode < 0.6:       # tandem repeat with breaks
+            per = int(rng.integers(1, dk + 3))
+            unit = rng.integers(0, 4, size=per, dtype=np.uint8)
+            t = np.tile(unit, tl // per + 2)[:tl].copy()
+            nb = int(rng.integers(0, 2 + ql // 12))
+            for x in rng.integers(0, tl, size=nb):
+                t[x] = (t[x] + int(rng.integers(1, 4))) & 3
+        elif mode < 0.8:     # low-complexity: two-letter alphabet
+            t = rng.integers(0, 2, size=tl, dtype=np.uint8) * int(rng.integers(1, 4))
+        else:
+            t = rng.integers(0, 4, size=tl, dtype=np.uint8)
+        q = t[:ql].copy()
+        # k differences: spacings near the boundary dk + 2
+        pos = [int(rng.integers(0, max(1, ql // (k + 1))))]
+        for _m in range(k - 1):
+            gap = dk + 2 + int(rng.integers(-2, 12)) if rng.random() < 0.7 else int(rng.integers(1, 60))
+            pos.append(pos[-1] + max(1, gap))
+        for x in pos:
+            if x < ql:
+                q[x] = (q[x] + int(rng.integers(1, 4))) & 3
+        qs.append(q); ts.append(t)
+        h0s.append(int(rng.integers(1, 40)) if rng.random() < 0.3 else int(rng.integers(19, 200)))
+    qlens = np.array([len(x) for x in qs]); tlens = np.array([len(x) for x in ts])
+    qp = (qlens + 7) // 8 * 8; tp = (tlens + 7) // 8 * 8
+    qoff = np.zeros(n_jobs, np.uint32); toff = np.zeros(n_jobs, np.uint32)
+    qoff[1:] = np.cumsum(qp)[:-1]; toff[1:] = np.cumsum(tp)[:-1]
+    qseq = np.full(int(qp.sum()) + 8, 4, np.uint8); tseq = np.full(int(tp.sum()) + 8, 4, np.uint8)
+    for a in range(n_jobs):
+        qseq[qoff[a]:qoff[a] + qlens[a]] = qs[a]; tseq[toff[a]:toff[a] + tlens[a]] = ts[a]
+    return dict(qseq=qseq, tseq=tseq, qoff=qoff, toff=toff, qlen=qlens.astype(np.uint32), tlen=tlens.astype(np.uint32), h0=np.array(h0s, np.uint32))
+
+
+def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax=None, zdrop: int = 100) -> np.ndarray:
     """Which jobs the extender answers in closed form (an independent statement of closed_form_job's predicate, ext_pair_core.cuh):
-    target at least as long as the query, every compared base in A/C/G/T, at most three substituted bases (two when dmax[1] is None),
-    h0 > k b, k b <= zdrop, and -- with k >= 2 -- between each two neighbouring differences every diagonal shifted by 1 .. dmax_k either
-    way has a mismatch (or leaves the matrix) on the rows strictly between the earlier difference + dmax_k and the later one."""
+    target at least as long as the query, every compared base in A/C/G/T, at most kcap = max(dmax) substituted bases, h0 > k b,
+    k b <= zdrop, and -- with k >= 2 -- between each two neighbouring differences every diagonal shifted by 1 .. dmax[k] either way has
+    a mismatch (or leaves the matrix) on the rows strictly between the earlier difference + dmax[k] and the later one.
+    dmax: {k: dmax_k} as closed_form_eligible returns it (default: the default penalties' table)."""
+    if dmax is None:
+        dmax = closed_form_eligible()
     n = jobs["qlen"].size
     out = np.zeros(n, bool)
-    kcap = 3 if dmax[1] is not None else 2
+    kcap = max(dmax)
     for j in range(n):
         ql, tl, h0 = int(jobs["qlen"][j]), int(jobs["tlen"][j]), int(jobs["h0"][j])
         if ql == 0 or tl < ql:
             continue
-        q = jobs["qseq"][int(jobs["qoff"][j]):int(jobs["qoff"][j]) + ql].astype(np.int64)
-        t = jobs["tseq"][int(jobs["toff"][j]):int(jobs["toff"][j]) + ql].astype(np.int64)
+        q = jobs["qseq"][int(jobs["qoff"][j]):int(jobs["qoff"][j]) + ql]
+        t = jobs["tseq"][int(jobs["toff"][j]):int(jobs["toff"][j]) + ql]
         if (q > 3).any() or (t > 3).any():
             continue
         diff = np.nonzero(q != t)[0]
@@ -347,7 +396,7 @@ def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax=(4, 9), zdrop: int
         if k > kcap or h0 <= k * b or (zdrop > 0 and k * b > zdrop):
             continue
         ok = True
-        dk = dmax[1] if k == 3 else dmax[0]
+        dk = dmax[k] if k >= 2 else 0
         if k >= 2 and dk > 0:
             for m in range(k - 1):
                 lo, hi = int(diff[m]) + dk + 1, int(diff[m + 1])
@@ -367,17 +416,27 @@ def closed_form_mask(jobs: dict, a: int = 1, b: int = 4, dmax=(4, 9), zdrop: int
     return out
 
 
+CF_KMAX, CF_DMAX_CAP = 6, 24
+
+
 def closed_form_eligible(w=100, zdrop=100, use_band=1, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, **_):
-    """closed_params_from (ext_pair_core.cuh) restated: None when the parameters rule the closed-form answer out, else (dmax2, dmax3): the
-    longest gap that costs no more than two / three mismatches (dmax3 None: jobs with three differences are not taken)"""
+    """closed_params_from (ext_pair_core.cuh) restated: None when the parameters rule the closed-form answer out, else {k: dmax_k} for
+    the numbers of differences k = 2 .. kcap that are taken, dmax_k the longest gap that costs no more than k mismatches"""
     g = min(o_del + e_del, o_ins + e_ins)
     if a < 1 or b < 1 or g <= a + b:
         return None
-    d2 = max((2 * (a + b) - o_del) // e_del, (2 * (a + b) - o_ins) // e_ins, 0)
-    d3 = max((3 * (a + b) - o_del) // e_del, (3 * (a + b) - o_ins) // e_ins, 0)
-    if d2 > 16 or (use_band and w < d2 + 2):
+
+    def dmax_of(k):
+        return max((k * (a + b) - o_del) // e_del, (k * (a + b) - o_ins) // e_ins, 0)
+    if dmax_of(2) > 16 or (use_band and w < dmax_of(2) + 2):
         return None
-    return d2, (d3 if d3 <= 24 and (not use_band or w >= d3 + 2) else None)
+    out = {2: dmax_of(2)}
+    for k in range(3, CF_KMAX + 1):
+        d = dmax_of(k)
+        if d > CF_DMAX_CAP or (use_band and w < d + 2):
+            break
+        out[k] = d
+    return out
 
 
 def subset_jobs(jobs: dict, keep: np.ndarray) -> dict:
