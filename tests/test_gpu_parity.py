@@ -227,6 +227,24 @@ def test_extension_pair_kernel_stress(gpu, oracle, kw):
     ex.destroy()
 
 
+@pytest.mark.parametrize("kw", [dict(w=100, zdrop=100), dict(w=21, zdrop=0), dict(w=40, zdrop=60, a=2, b=3)])
+def test_extension_closed_form_flanks_and_repeats(gpu, oracle, kw):
+    """the jobs key_kernel answers without a matrix (closed_form_job): flanks of exact matches with up to six substitutions, over random
+    sequence and over tandem repeats whose shifted diagonals are clean but for a break or two -- results and the count of jobs taken"""
+    ex = gpu.Extender(0)
+    taken = 0
+    for jobs in (synth.make_flank_jobs(4000, seed=81, w=kw["w"]), synth.make_flank_jobs(3000, seed=82, w=kw["w"], qlen_range=(100, 600), h0_range=(19, 250)),
+                 synth.make_repeat_flank_jobs(6000, 83, kw)):
+        want, cnt = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
+        res, _ = ex.extend_host(jobs, gpu.ext_params(**kw))
+        bad = np.nonzero((res != want).any(axis=1))[0]
+        assert bad.size == 0, (bad[:5], res[bad[:5]], want[bad[:5]], jobs["qlen"][bad[:5]], jobs["h0"][bad[:5]])
+        assert (ex.last_cells(), ex.last_closed_form()) == synth.dp_cells(oracle, jobs, kw, cnt)
+        taken += ex.last_closed_form()
+    assert taken > 3000
+    ex.destroy()
+
+
 def test_extension_general_matrix(gpu, oracle):
     """a general substitution matrix (transitions cheaper than transversions): PRMT score rows in the pair kernel"""
     jobs = synth.make_ext_jobs(3000, w=100, seed=71, qlen_range=(1, 200), h0_range=(1, 150))
