@@ -183,62 +183,98 @@ static inline ClosedParams closed_params_from(const bwa_b200_ext_params_t *p)
     }
     return C;
 }
+// The test in three steps, so that key_kernel can spread the second one over a warp: the shape (the differing bases and the cheap
+// conditions), one shifted diagonal of one stretch, the six outputs.
+struct ClosedShape { int32_t k; int32_t rr[CF_KMAX]; };
+// 0: not a closed-form job; 1: it is, nothing left to test; 2: it is if every shifted diagonal of every stretch is broken
 template <bool BYTES>
-B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t a, bwa_b200_ext_result_t *r)
+B200_DEV int closed_form_shape(const ClosedParams &C, const JobView &J, uint32_t a, ClosedShape &S)
 {
     const uint32_t ql = J.qlen[a], tl = J.tlen[a];
     const int h0 = (int)J.h0[a];
-    if (!C.ok || ql == 0 || tl < ql || ql > 0x00ffffffu || h0 > 0x00ffffff) return false;
-    const uint8_t *qb = BYTES ? J.qb + J.qoff[a] : nullptr, *tb = BYTES ? J.tb + J.toff[a] : nullptr;
-    const uint32_t *qp = BYTES ? nullptr : J.qp + (J.qoff[a] >> 3), *tp = BYTES ? nullptr : J.tp + (J.toff[a] >> 3);
-    auto qa = [&](int i) -> uint32_t { return BYTES ? (uint32_t)qb[i] : (qp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
-    auto ta = [&](int i) -> uint32_t { return BYTES ? (uint32_t)tb[i] : (tp[i >> 3] >> (28 - 4 * (i & 7))) & 15u; };
+    if (!C.ok || ql == 0 || tl < ql || ql > 0x00ffffffu || h0 > 0x00ffffff) return 0;
     // the differing bases: at most kcap, every compared base in A/C/G/T
     const int kcap = C.kcap;
-    int k = 0, rr[CF_KMAX] = {};
+    int k = 0;
+    for (int m = 0; m < CF_KMAX; ++m) S.rr[m] = 0;
     if (BYTES) {
+        const uint8_t *qb = J.qb + J.qoff[a], *tb = J.tb + J.toff[a];
         for (uint32_t i = 0; i < ql; ++i) {
-            if (qb[i] > 3 || tb[i] > 3) return false;
-            if (qb[i] != tb[i]) { if (k == kcap) return false; rr[k++] = (int)i; }
+            if (qb[i] > 3 || tb[i] > 3) return 0;
+            if (qb[i] != tb[i]) { if (k == kcap) return 0; S.rr[k++] = (int)i; }
         }
     } else {
+        const uint32_t *qp = J.qp + (J.qoff[a] >> 3), *tp = J.tp + (J.toff[a] >> 3);
         const uint32_t nw = (ql + 7) >> 3;
         for (uint32_t w = 0; w < nw; ++w) {
             const uint32_t qw = qp[w], tw = tp[w], rem = ql - 8 * w;
             const uint32_t m = rem < 8 ? ~(0xffffffffu >> (4 * rem)) : 0xffffffffu;
-            if ((qw | tw) & 0xccccccccu & m) return false;
+            if ((qw | tw) & 0xccccccccu & m) return 0;
             uint32_t x = (qw ^ tw) & m;
             for (int n = 0; x; ++n, x <<= 4)
-                if (x >> 28) { if (k == kcap) return false; rr[k++] = (int)(8 * w) + n; }
+                if (x >> 28) { if (k == kcap) return 0; S.rr[k++] = (int)(8 * w) + n; }
         }
     }
-    if (h0 <= k * C.b || (C.zdrop > 0 && k * C.b > C.zdrop)) return false;
+    S.k = k;
+    if (h0 <= k * C.b || (C.zdrop > 0 && k * C.b > C.zdrop)) return 0;
     const int dmax = C.dmax[k];
-    if (k >= 2 && dmax > 0) {     // every shifted diagonal an affordable gap reaches must break between each two neighbouring differences
-        for (int m = 0; m + 1 < k; ++m) {
-            const int lo = rr[m] + dmax + 1, hi = rr[m + 1];
-            if (lo >= hi) return false;
-            for (int d = 1; d <= dmax; ++d)
-                for (int sg = -1; sg <= 1; sg += 2) {
-                    const int s = sg * d;
-                    bool broken = false;
-                    for (int c = lo; c < hi && !broken; ++c) broken = c + s >= (int)ql || qa(c + s) != ta(c);     // c + s >= lo - dmax > 0
-                    if (!broken) return false;
-                }
+    if (k < 2 || dmax <= 0) return 1;
+    for (int m = 0; m + 1 < k; ++m)
+        if (S.rr[m] + dmax + 1 >= S.rr[m + 1]) return 0;      // no row left between two neighbouring differences to break a diagonal on
+    return 2;
+}
+// some row c of [lo, hi) has q[c + s] != t[c] or lies outside the matrix (c + s >= lo - dmax > 0)
+template <bool BYTES>
+B200_DEV bool closed_form_diag_broken(const JobView &J, uint32_t a, int ql, int lo, int hi, int s)
+{
+    if (hi - 1 + s >= ql) return true;
+    if (BYTES) {
+        const uint8_t *qb = J.qb + J.qoff[a], *tb = J.tb + J.toff[a];
+        for (int c = lo; c < hi; ++c)
+            if (qb[c + s] != tb[c]) return true;
+    } else {
+        const uint32_t *qp = J.qp + (J.qoff[a] >> 3), *tp = J.tp + (J.toff[a] >> 3);
+        for (int c = lo; c < hi; ++c) {
+            const int j = c + s;
+            if (((qp[j >> 3] >> (28 - 4 * (j & 7))) & 15u) != ((tp[c >> 3] >> (28 - 4 * (c & 7))) & 15u)) return true;
         }
     }
+    return false;
+}
+// check number x of a job with k differences (0 <= x < closed_form_checks): stretch x / (2 dmax), shift -1, +1, -2, +2 ...
+B200_DEV int closed_form_checks(const ClosedParams &C, int k) { return (k - 1) * 2 * C.dmax[k]; }
+template <bool BYTES>
+B200_DEV bool closed_form_check(const ClosedParams &C, const JobView &J, uint32_t a, int ql, int k, const int32_t *rr, int x)
+{
+    const int dmax = C.dmax[k], m = x / (2 * dmax), y = x - m * 2 * dmax, d = (y >> 1) + 1;
+    return closed_form_diag_broken<BYTES>(J, a, ql, rr[m] + dmax + 1, rr[m + 1], (y & 1) ? d : -d);
+}
+B200_DEV void closed_form_result(const ClosedParams &C, int h0, int ql, const ClosedShape &S, bwa_b200_ext_result_t *r)
+{
     // D at its peaks, in row order; the first one holding the largest value is where the maximum was last raised
-    const int ab = C.a + C.b, last = (int)ql - 1;
+    const int ab = C.a + C.b, last = ql - 1, k = S.k;
     int best = h0, row = -1;
     for (int m = 0; m < k; ++m) {
-        if (rr[m] < 1) continue;
-        const int v = h0 + rr[m] * C.a - m * ab;                 // D(rr[m] - 1): m differences before it
-        if (v > best) { best = v; row = rr[m] - 1; }
+        if (S.rr[m] < 1) continue;
+        const int v = h0 + S.rr[m] * C.a - m * ab;               // D(rr[m] - 1): m differences before it
+        if (v > best) { best = v; row = S.rr[m] - 1; }
     }
-    const int g = h0 + (int)ql * C.a - k * ab;
+    const int g = h0 + ql * C.a - k * ab;
     if (g > best) { best = g; row = last; }
     r->score = best; r->qle = row + 1; r->tle = row + 1;
     r->gscore = g; r->gtle = (int32_t)ql; r->max_off = 0;
+}
+template <bool BYTES>
+B200_DEV bool closed_form_job(const ClosedParams &C, const JobView &J, uint32_t a, bwa_b200_ext_result_t *r)
+{
+    ClosedShape S;
+    const int st = closed_form_shape<BYTES>(C, J, a, S);
+    if (st == 0) return false;
+    const int ql = (int)J.qlen[a];
+    if (st == 2)
+        for (int x = 0, n = closed_form_checks(C, S.k); x < n; ++x)
+            if (!closed_form_check<BYTES>(C, J, a, ql, S.k, S.rr, x)) return false;
+    closed_form_result(C, (int)J.h0[a], ql, S, r);
     return true;
 }
 

@@ -61,14 +61,34 @@ template <bool BYTES>
 __global__ void key_kernel(uint32_t n, JobView J, ClosedParams C, int max_score, int simd_ok, int wave_ok, uint32_t *keys, uint32_t *vals,
                            bwa_b200_ext_result_t *__restrict__ res, unsigned long long *__restrict__ counters)
 {
-    uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    bool done = false;
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    // closed-form jobs (closed_form_job, ext_pair_core.cuh).  The shape test is per lane; the shifted diagonals of the jobs that need
+    // them are tested by the whole warp, one job at a time, a diagonal per lane: a lane on its own would scan 8 .. 240 of them while
+    // the lanes whose jobs need none wait (0.38 ms for C2's batch that way).
+    ClosedShape S;
+    int st = 0;
+    if (a < n && C.ok) st = closed_form_shape<BYTES>(C, J, a, S);
+    uint32_t pend = __ballot_sync(0xffffffffu, st == 2);
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const uint32_t a_s = __shfl_sync(0xffffffffu, a, src);
+        const int k_s = __shfl_sync(0xffffffffu, S.k, src);
+        int32_t rr_s[CF_KMAX];
+#pragma unroll
+        for (int m = 0; m < CF_KMAX; ++m) rr_s[m] = __shfl_sync(0xffffffffu, S.rr[m], src);
+        const int ql_s = (int)J.qlen[a_s], n_checks = closed_form_checks(C, k_s);
+        bool ok = true;
+        for (int x = (int)lane; x < n_checks && ok; x += 32) ok = closed_form_check<BYTES>(C, J, a_s, ql_s, k_s, rr_s, x);
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        if ((int)lane == src) st = all_ok ? 1 : 0;
+    }
+    const bool done = st == 1;
     if (a < n) {
         uint32_t q = J.qlen[a];
         uint64_t bound = (uint64_t)J.h0[a] + (uint64_t)q * (uint64_t)(max_score > 0 ? max_score : 0);
         uint32_t k = q > 0x7ffffu ? 0x7ffffu : q;
-        bwa_b200_ext_result_t r;
-        if (C.ok && closed_form_job<BYTES>(C, J, a, &r)) { res[a] = r; k |= CLS_DONE; done = true; }
+        if (done) { bwa_b200_ext_result_t r; closed_form_result(C, (int)J.h0[a], (int)q, S, &r); res[a] = r; k |= CLS_DONE; }
         else if (simd_ok && bound <= (uint64_t)PAIR_MAX_SCORE && q <= (uint32_t)PAIR_MAX_Q) { }
         else if (wave_ok && q > (uint32_t)WAVE_MIN_Q && q <= 0xffffu && bound <= (uint64_t)WAVE_MAX_SCORE) k |= CLS_WAVE;
         else if (q <= 1024u && bound < 32767ull) k |= CLS_BIT;
@@ -77,7 +97,7 @@ __global__ void key_kernel(uint32_t n, JobView J, ClosedParams C, int max_score,
         vals[a] = a;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, done);
-    if (m && (threadIdx.x & 31) == 0) atomicAdd(counters + 1, (unsigned long long)__popc(m));
+    if (m && lane == 0) atomicAdd(counters + 1, (unsigned long long)__popc(m));
 }
 
 // Sorted positions of the bin boundaries.  range[0..N_PBINS] bound the bins of the column-pair kernel (bin b =
