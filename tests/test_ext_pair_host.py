@@ -54,7 +54,7 @@ SETS = [(61, dict(qlen_range=(1, 260), h0_range=(1, 250))),
 @pytest.mark.parametrize("kw", KW)
 def test_pair_source_matches_oracle(pkg, oracle, emul, kw, variant):
     for seed, extra in SETS:
-        jobs = synth.make_ext_jobs(3000, w=kw["w"], seed=seed, **extra)
+        jobs = synth.make_ext_jobs(700 if seed == 63 else 2000, w=kw["w"], seed=seed, **extra)       # the long queries are the slow ones on the host
         want, _ = oracle.ksw_batch(jobs, oracle.make_params(**kw), n_threads=4)
         res, skipped, cells = emul(jobs, pkg.ext_params(**kw), variant)
         assert cells >= 0
