@@ -125,7 +125,6 @@ def test_pair_source_wide_scores_long_queries(pkg, oracle, emul, kw):
 
 CF_KW = [(dict(w=100, zdrop=100), True), (dict(w=8, zdrop=0), True), (dict(w=6, zdrop=4), True), (dict(w=11, zdrop=12), True), (dict(w=300, zdrop=0, use_band=0), True),
          (dict(w=100, zdrop=0, end_bonus=0), True),                              # short queries: the band clamp of src/ksw.c:885-893 falls below dmax + 2
-        
          (dict(w=20, zdrop=50, a=2, b=3), True), (dict(w=20, zdrop=10, a=2, b=5, o_del=7, e_del=2, o_ins=8, e_ins=1), True),
          (dict(w=100, zdrop=3), True),                                            # only jobs without a difference pass the z-drop condition
          (dict(w=5, zdrop=100), False),                                           # band narrower than the gaps that have to be ruled out + 2
